@@ -1,0 +1,380 @@
+"""glmmrmcml_b200 — B200-native Monte-Carlo E-step and random-effect sampler behind glmmrMCML's API.
+
+Host-side mirror of the reference interface for this path.  The functions below carry the names, argument order and
+return shapes of the reference's exported R functions (R/RcppExports.R:35-304): ``mcml_full``, ``mcmc_sample``,
+``mcml_optim``, ``mcml_simlik``, ``mcml_hess``, ``aic_mcml``, ``mvn_ll``; ``ModelMCML`` mirrors the R6 class of
+R/R6ModelExtMCML.R for the ``usestan = FALSE`` code path.  Everything calls the C-ABI of
+``libglmmrmcml_b200.so`` (include/glmmrmcml_b200.h) with host numpy buffers — the same calls an Rcpp adapter makes
+(INTEGRATION.md).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import GmbError, HmcStats, lib, check  # noqa: F401
+
+__all__ = ["Context", "Model", "Covariance", "mvn_ll", "mcmc_sample", "mcml_optim", "mcml_simlik", "mcml_hess",
+           "aic_mcml", "mcml_full", "ModelMCML", "GmbError", "version"]
+
+
+def _f(a):
+    return np.asfortranarray(np.asarray(a, dtype=np.float64))
+
+
+def _v(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
+
+
+def _d(a):
+    return a.ctypes.data_as(_lib.dp) if a is not None else None
+
+
+def _covargs(cov, data, eff_range):
+    cov = np.asfortranarray(np.asarray(cov, dtype=np.int32).reshape(-1, 5))
+    data = _v(data)
+    eff = _v(eff_range) if eff_range is not None and np.size(eff_range) else np.zeros(cov.shape[0])
+    return (cov, data, eff), [cov.ctypes.data_as(_lib.ip), cov.shape[0], _d(data), data.size, _d(eff), eff.size]
+
+
+def version() -> str:
+    return lib().gmb_version().decode()
+
+
+class Context:
+    """One per process/GPU: stream, scratch memory, optional NCCL communicator (gmb_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        check(lib().gmb_ctx_create(int(device), C.byref(self._h)))
+        self.rank, self.world = 0, 1
+
+    def close(self):
+        if self._h:
+            lib().gmb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(lib().gmb_ctx_sync(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().gmb_ctx_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        """Raw cudaStream_t of the context (integer handle), for CUDA-event timing by callers."""
+        return int(lib().gmb_ctx_stream(self._h) or 0)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(lib().gmb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(uid, 128)
+        check(lib().gmb_comm_init(self._h, buf, int(rank), int(world)))
+        self.rank, self.world = int(rank), int(world)
+
+    def allreduce(self, a):
+        a = _v(a).copy()
+        check(lib().gmb_comm_allreduce_host(self._h, _d(a), a.size))
+        return a
+
+    def bcast(self, a):
+        a = _v(a).copy()
+        check(lib().gmb_comm_bcast_host(self._h, _d(a), a.size))
+        return a
+
+    def make_default(self):
+        """Route the reference-named entry points (mcml_full, ...) through this context."""
+        check(lib().gmb_set_default_ctx(self._h))
+
+
+class Model:
+    """Device-resident replacement of glmmr::mcmlModel (inst/include/glmmrmcml/mcmlmodel.h:28-307)."""
+
+    def __init__(self, ctx: Context, X, Z, y, family: str, link: str):
+        X = _f(X); Z = _f(Z); y = _v(y)
+        n, P = X.shape
+        if Z.shape[0] != n or y.size != n:
+            raise ValueError("X, Z and y must have the same number of rows")
+        self.n, self.P, self.Q = n, P, Z.shape[1]
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        check(lib().gmb_model_create(ctx._h, n, P, self.Q, _d(X), _d(Z), _d(y), family.encode(), link.encode(), C.byref(self._h)))
+        self.flink = lib().gmb_model_flink(self._h)
+
+    def close(self):
+        if self._h:
+            lib().gmb_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_u(self, U, m_total=None, niter_total=None):
+        """Upload this rank's sample columns (Q x m_local) and build zd = Z u once."""
+        U = _f(np.asarray(U, dtype=np.float64).reshape(self.Q, -1))
+        m_local = U.shape[1]
+        m_total = m_local if m_total is None else int(m_total)
+        niter_total = m_total if niter_total is None else int(niter_total)
+        check(lib().gmb_model_set_u(self._h, _d(U), self.Q, m_local, m_total, niter_total))
+
+    def use_device_u(self, niter_total=0):
+        check(lib().gmb_model_use_device_u(self._h, int(niter_total)))
+
+    def log_likelihood(self, beta, var_par=1.0) -> float:
+        """mcmlModel::log_likelihood after update_beta (mcmlmodel.h:100-102, 284-304)."""
+        beta = _v(beta)
+        if beta.size != self.P:
+            raise ValueError(f"beta has {beta.size} values, X has {self.P} columns")
+        out = C.c_double()
+        check(lib().gmb_model_loglik(self._h, _d(beta), float(var_par), C.byref(out)))
+        return out.value
+
+    def log_likelihood_batch(self, betas, var_pars):
+        betas = _f(np.asarray(betas, dtype=np.float64).reshape(self.P, -1))
+        k = betas.shape[1]
+        var_pars = _v(np.broadcast_to(np.asarray(var_pars, dtype=np.float64), (k,)))
+        out = np.zeros(k)
+        check(lib().gmb_model_loglik_batch(self._h, _d(betas), _d(var_pars), k, _d(out)))
+        return out
+
+    def mcnr(self, beta, var_par=1.0):
+        """mcmloptim::mcnr sufficient sums and Newton step (mcmloptim.h:198-236)."""
+        beta = _v(beta)
+        P = self.P
+        xtwx = np.zeros((P, P), order="F"); score = np.zeros(P); incr = np.zeros(P); sigma = C.c_double()
+        check(lib().gmb_model_mcnr(self._h, _d(beta), float(var_par), _d(xtwx), _d(score), _d(incr), C.byref(sigma)))
+        return dict(xtwx=xtwx, score=score, beta_incr=incr, sigma=sigma.value)
+
+    def hmc_sample(self, L, beta, var_par=1.0, warmup=500, nsamp_per_chain=250, lam=5.0, max_steps=100, target_accept=0.95,
+                   adapt=100, n_chains=1, chain_offset=0, seed=1, keep_on_device=False, want_u=True, want_v=False):
+        """n_chains batched copies of mcmcRunHMC::sample (mhmcmc.h:121-157).  Returns dict(u, v, stats)."""
+        Lh = _f(L) if L is not None else None
+        beta = _v(beta)
+        ncol = n_chains * (nsamp_per_chain + 1)
+        U = np.zeros((self.Q, ncol), order="F") if want_u else None
+        V = np.zeros((self.Q, ncol), order="F") if want_v else None
+        st = HmcStats()
+        check(lib().gmb_hmc_sample(self._h, _d(Lh), _d(beta), float(var_par), int(warmup), int(nsamp_per_chain), float(lam),
+                                   int(max_steps), float(target_accept), int(adapt), int(n_chains), int(chain_offset),
+                                   int(seed), int(bool(keep_on_device)), _d(U), _d(V), C.byref(st)))
+        stats = {k: getattr(st, k) for k, _ in HmcStats._fields_}
+        return dict(u=U, v=V, stats=stats)
+
+    def log_prob_grad(self, L, beta, var_par, V):
+        """mcmlModel::log_prob and log_grad (mcmlmodel.h:138-153, 156-279) for the columns of V (Q x C)."""
+        Lh = _f(L) if L is not None else None
+        beta = _v(beta)
+        V = _f(np.asarray(V, dtype=np.float64).reshape(self.Q, -1))
+        Cn = V.shape[1]
+        lp = np.zeros(Cn); g = np.zeros((self.Q, Cn), order="F")
+        check(lib().gmb_model_logprob_grad(self._h, _d(Lh), _d(beta), float(var_par), _d(V), Cn, _d(lp), _d(g)))
+        return lp, g
+
+
+class Covariance:
+    """Device-resident replacement of glmmr::DData + glmmr::MCMLDmatrix (mcmldmatrix.h:18-79)."""
+
+    def __init__(self, ctx: Context, cov, data, eff_range=None):
+        self._keep, args = _covargs(cov, data, eff_range)
+        self.ctx = ctx
+        self._h = C.c_void_p()
+        check(lib().gmb_cov_create(ctx._h, *args, C.byref(self._h)))
+        B, Q, R = C.c_int(), C.c_int(), C.c_int()
+        check(lib().gmb_cov_dims(self._h, C.byref(B), C.byref(Q), C.byref(R)))
+        self.B, self.Q, self.R = B.value, Q.value, R.value
+
+    def close(self):
+        if self._h:
+            lib().gmb_cov_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def genD(self, theta, chol=True):
+        """DMatrix::genD(0, chol, false): dense Q x Q block-diagonal D(theta) or its lower Cholesky factor."""
+        theta = _v(theta)
+        out = np.zeros((self.Q, self.Q), order="F")
+        check(lib().gmb_cov_gen(self._h, _d(theta), int(bool(chol)), _d(out)))
+        return out
+
+    def loglik(self, theta, U, m_total=None) -> float:
+        """MCMLDmatrix::loglik(u) (mcmldmatrix.h:23-41)."""
+        theta = _v(theta)
+        U = _f(np.asarray(U, dtype=np.float64).reshape(self.Q, -1))
+        m = U.shape[1]
+        out = C.c_double()
+        check(lib().gmb_cov_mvn_ll(self._h, _d(theta), _d(U), self.Q, m, m if m_total is None else int(m_total), C.byref(out)))
+        return out.value
+
+    def loglik_model(self, theta, model: Model, ncols_total=0) -> float:
+        theta = _v(theta)
+        out = C.c_double()
+        check(lib().gmb_cov_mvn_ll_model(self._h, _d(theta), model._h, int(ncols_total), C.byref(out)))
+        return out.value
+
+    def logdet(self, theta) -> float:
+        theta = _v(theta)
+        out = C.c_double()
+        check(lib().gmb_cov_logdet(self._h, _d(theta), C.byref(out)))
+        return out.value
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference-named functions (R/RcppExports.R), same argument order
+# ----------------------------------------------------------------------------------------------------------------------
+
+def _fixed_u(cov, data, eff_range, Z, X, y, u, family, link):
+    keep, cargs = _covargs(cov, data, eff_range)
+    Z = _f(Z); X = _f(X); y = _v(y)
+    n, P = X.shape
+    Q = Z.shape[1]
+    u = _f(np.asarray(u, dtype=np.float64).reshape(Q, -1))
+    keep = keep + (Z, X, y, u)
+    return keep, cargs + [_d(Z), _d(X), _d(y), _d(u), n, P, Q, u.shape[1], family.encode(), link.encode()], (n, P, Q, u.shape[1])
+
+
+def _cov_R(cov):
+    """number of covariance parameters implied by the cov matrix (DData::n_cov_pars)."""
+    npar = {1: 1, 2: 1, 3: 1, 4: 2, 5: 2, 6: 1, 7: 2, 8: 2, 9: 2, 10: 2, 11: 2, 12: 2, 13: 2, 14: 1}   # R/R6ModelExtMCML.R:430
+    cov = np.asarray(cov, dtype=np.int64).reshape(-1, 5)
+    return int(max(int(r[4]) + npar.get(int(r[2]), 1) for r in cov))
+
+
+def mvn_ll(cov, data, eff_range, gamma, u) -> float:
+    """src/mcml_optim.cpp:406-414."""
+    keep, cargs = _covargs(cov, data, eff_range)
+    gamma = _v(gamma)
+    u = np.asarray(u, dtype=np.float64)
+    Q = int(sum({int(r[0]): int(r[1]) for r in keep[0]}.values()))     # sum of the block dimensions
+    u = _f(u.reshape(Q, -1))
+    out = C.c_double()
+    check(lib().gmb_mvn_ll(*cargs, _d(gamma), gamma.size, _d(u), Q, u.shape[1], C.byref(out)))
+    return out.value
+
+
+def mcmc_sample(Z, L, X, y, beta, family, link, warmup, nsamp, lam, var_par=1.0, trace=0, refresh=500, maxsteps=100,
+                target_accept=0.9, n_chains=1, seed=1):
+    """src/mcml_full.cpp:314-338 — returns Q x (nsamp + 1) samples of u = L v."""
+    Z = _f(Z); L = _f(L); X = _f(X); y = _v(y); beta = _v(beta)
+    n, P = X.shape; Q = Z.shape[1]
+    out = np.zeros((Q, nsamp + 1), order="F")
+    check(lib().gmb_mcmc_sample(_d(Z), _d(L), _d(X), _d(y), _d(beta), n, P, Q, family.encode(), link.encode(), int(warmup),
+                                int(nsamp), float(lam), float(var_par), int(trace), int(refresh), int(maxsteps),
+                                float(target_accept), int(n_chains), int(seed), _d(out)))
+    return out
+
+
+def mcml_optim(cov, data, eff_range, Z, X, y, u, family, link, start, trace=0, mcnr=False):
+    """src/mcml_optim.cpp:35-68 — list(beta, theta, sigma)."""
+    keep, args, (n, P, Q, m) = _fixed_u(cov, data, eff_range, Z, X, y, u, family, link)
+    start = _v(start); R = _cov_R(cov)
+    beta = np.zeros(P); theta = np.zeros(R); sigma = C.c_double()
+    check(lib().gmb_mcml_optim(*args, _d(start), start.size, int(trace), int(bool(mcnr)), _d(beta), _d(theta), C.byref(sigma)))
+    return dict(beta=beta, theta=theta, sigma=sigma.value)
+
+
+def mcml_simlik(cov, data, eff_range, Z, X, y, u, family, link, start, trace=0):
+    """src/mcml_optim.cpp:90-117."""
+    keep, args, (n, P, Q, m) = _fixed_u(cov, data, eff_range, Z, X, y, u, family, link)
+    start = _v(start); R = _cov_R(cov)
+    beta = np.zeros(P); theta = np.zeros(R); sigma = C.c_double()
+    check(lib().gmb_mcml_simlik(*args, _d(start), start.size, int(trace), _d(beta), _d(theta), C.byref(sigma)))
+    return dict(beta=beta, theta=theta, sigma=sigma.value)
+
+
+def mcml_hess(cov, data, eff_range, Z, X, y, u, family, link, start, tol=1e-5, trace=0):
+    """src/mcml_optim.cpp:263-285 — (P + R) x (P + R) finite-difference Hessian of the negative joint log-likelihood."""
+    keep, args, (n, P, Q, m) = _fixed_u(cov, data, eff_range, Z, X, y, u, family, link)
+    start = _v(start); R = _cov_R(cov)
+    H = np.zeros((P + R, P + R), order="F")
+    check(lib().gmb_mcml_hess(*args, _d(start), start.size, float(tol), int(trace), _d(H)))
+    return H
+
+
+def aic_mcml(cov, data, eff_range, Z, X, y, u, family, link, beta_par, cov_par) -> float:
+    """src/mcml_optim.cpp:356-392."""
+    keep, args, _ = _fixed_u(cov, data, eff_range, Z, X, y, u, family, link)
+    beta_par = _v(beta_par); cov_par = _v(cov_par)
+    out = C.c_double()
+    check(lib().gmb_aic_mcml(*args, _d(beta_par), beta_par.size, _d(cov_par), cov_par.size, C.byref(out)))
+    return out.value
+
+
+def mcml_full(cov, data, eff_range, Z, X, y, family, link, start, mcnr=False, m=500, maxiter=30, warmup=500, tol=1e-3,
+              verbose=True, lam=0.05, trace=0, refresh=500, maxsteps=100, target_accept=0.9, n_chains=0, seed=1):
+    """src/mcml_full.cpp:41-148 — list(beta, theta, sigma, converged, u); u is Q x (m + 1)."""
+    keep, cargs = _covargs(cov, data, eff_range)
+    Z = _f(Z); X = _f(X); y = _v(y); start = _v(start)
+    n, P = X.shape; Q = Z.shape[1]; R = _cov_R(cov)
+    beta = np.zeros(P); theta = np.zeros(R); sigma = C.c_double(); conv = C.c_int(); it = C.c_int()
+    u = np.zeros((Q, m + 1), order="F")
+    check(lib().gmb_mcml_full(*cargs, _d(Z), _d(X), _d(y), n, P, Q, family.encode(), link.encode(), _d(start), start.size,
+                              int(bool(mcnr)), int(m), int(maxiter), int(warmup), float(tol), int(bool(verbose)), float(lam),
+                              int(trace), int(refresh), int(maxsteps), float(target_accept), int(n_chains), int(seed),
+                              _d(beta), _d(theta), C.byref(sigma), C.byref(conv), C.byref(it), _d(u)))
+    return dict(beta=beta, theta=theta, sigma=sigma.value, converged=bool(conv.value), iter=it.value, u=u)
+
+
+class ModelMCML:
+    """Mirror of the R6 class ``ModelMCML`` (R/R6ModelExtMCML.R) for the internal-sampler path (``usestan = FALSE``).
+
+    Holds what ``Model$new(covariance, mean.function, family)`` holds in R: the design matrices, the covariance in
+    ``get_D_data()`` form, the family and starting parameters.  ``MCML(y)`` runs ``mcml_full`` (R/R6ModelExtMCML.R:399-419)
+    and optionally the Hessian standard errors (``mcml_hess``, :448-474) and the conditional AIC (``aic_mcml``, :542-553).
+    """
+
+    def __init__(self, cov, data, eff_range, Z, X, family, link, beta_start, theta_start, var_par=1.0):
+        self.cov, self.data, self.eff_range = cov, data, eff_range
+        self.Z, self.X = _f(Z), _f(X)
+        self.family, self.link = family, link
+        self.beta = _v(beta_start); self.theta = _v(theta_start); self.var_par = float(var_par)
+        # R/R6ModelExtMCML.R:867-872
+        self.mcmc_options = dict(warmup=500, samps=250, lam=5.0, refresh=500, maxsteps=100, target_accept=0.95)
+
+    def MCML(self, y, start=None, se_theta=True, verbose=True, tol=1e-2, max_iter=30, method="mcnr", usestan=False,
+             n_chains=0, seed=1):
+        if usestan:
+            raise NotImplementedError("the Stan programs of inst/stan are replaced by the native sampler on this path; "
+                                      "call MCML(..., usestan=False)")
+        if method not in ("mcem", "mcnr"):
+            raise ValueError("method must be 'mcem' or 'mcnr'")
+        P = self.X.shape[1]
+        if start is None:                                         # R/R6ModelExtMCML.R:159-179
+            start = np.concatenate([self.beta, self.theta, [self.var_par if self.family == "gaussian" else 1.0]])
+        o = self.mcmc_options
+        fit = mcml_full(self.cov, self.data, self.eff_range, self.Z, self.X, y, self.family, self.link, start,
+                        mcnr=(method == "mcnr"), m=o["samps"], maxiter=max_iter, warmup=o["warmup"], tol=tol,
+                        verbose=verbose, lam=o["lam"], trace=0, refresh=o["refresh"], maxsteps=o["maxsteps"],
+                        target_accept=o["target_accept"], n_chains=n_chains, seed=seed)
+        out = dict(fit)
+        pars = np.concatenate([fit["beta"], fit["theta"]])
+        if se_theta:
+            H = mcml_hess(self.cov, self.data, self.eff_range, self.Z, self.X, y, fit["u"], self.family, self.link, pars)
+            out["hessian"] = H
+            try:
+                out["se"] = np.sqrt(np.diag(np.linalg.inv(H)))
+            except np.linalg.LinAlgError:
+                out["se"] = np.full(pars.size, np.nan)
+        bp = np.concatenate([fit["beta"], [fit["sigma"]]]) if self.family == "gaussian" else fit["beta"]
+        out["aic"] = aic_mcml(self.cov, self.data, self.eff_range, self.Z, self.X, y, fit["u"], self.family, self.link, bp, fit["theta"])
+        return out

@@ -1,0 +1,248 @@
+// common.cuh — internal declarations shared by the CUDA translation units of libglmmrmcml_b200.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <cmath>
+
+#include "../../include/glmmrmcml_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// errors (thread-local message, integer codes; nothing throws across the C boundary)
+// ------------------------------------------------------------------------------------------------
+int gmb_set_error(int code, const char* fmt, ...);
+
+#define GMB_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return gmb_set_error(GMB_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define GMB_TRY(call)                       \
+    do {                                    \
+        int rc__ = (call);                  \
+        if (rc__ != GMB_OK) return rc__;    \
+    } while (0)
+
+#define GMB_RESULT_DOUBLES 16384
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// ------------------------------------------------------------------------------------------------
+// host-side objects
+// ------------------------------------------------------------------------------------------------
+struct gmb_ctx {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    // device scratch for partial sums / small results, and its pinned host mirror
+    double* d_scratch = nullptr;
+    size_t scratch_doubles = 0;
+    double* h_pinned = nullptr;
+    size_t pinned_doubles = 0;
+    // fixed-address device buffers: small results (never reallocated) and the "last CTA done" counter
+    double* d_result = nullptr;          // GMB_RESULT_DOUBLES doubles
+    unsigned int* d_counter = nullptr;   // zero between kernels
+    // NCCL (loaded with dlopen; see comm.cu)
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+int gmb_ctx_scratch(gmb_ctx* ctx, size_t doubles);   // grow d_scratch to at least `doubles`
+int gmb_comm_allreduce_dev(gmb_ctx* ctx, double* dbuf, int count);   // in place on ctx->stream; no-op if world==1
+
+struct gmb_model {
+    gmb_ctx* ctx = nullptr;
+    int n = 0, P = 0, Q = 0, flink = 0;
+    int ldn = 0;                 // padded leading dimension of n-row matrices (multiple of 4)
+    int ldq = 0;                 // padded leading dimension of Q-row matrices (multiple of 4)
+    double* dX = nullptr;        // ldn x P
+    double* dZ = nullptr;        // ldn x Q
+    double* dy = nullptr;        // ldn
+    double* drowc = nullptr;     // ldn : per-row constant of the family term (poisson: log y! approx)
+    double* dxb = nullptr;       // ldn : X beta of the last evaluation
+    double* dbeta = nullptr;     // beta_cap doubles
+    int beta_cap = 0;
+    // samples (this rank's columns)
+    double* dU = nullptr;        // ldq x m_cap
+    double* dzd = nullptr;       // ldn x m_cap
+    int m_cap = 0;
+    int m_local = 0, niter_local = 0, m_total = 0, niter_total = 0;
+    bool zd_valid = false;
+    // sampler state
+    double* dZL = nullptr;       // ldn x Q   (Z L)
+    double* dL = nullptr;        // ldq x Q
+    bool zl_valid = false;
+    double* dV = nullptr;        // whitened samples of the last gmb_hmc_sample, ldq x v_cap
+    size_t v_cap = 0;
+    double* hmc_work = nullptr;  // chain state + work buffers of the sampler
+    size_t hmc_work_doubles = 0;
+};
+
+struct CovFn { int id, nvar, par0, col0; double eff; };
+struct CovBlock { int n, start, fn0, nfn, ncol, all_gr; long long data0; long long l0; };
+// leading dimension of a block's factor inside gmb_cov::d_Lblk: packed for warp-sized blocks, padded otherwise
+#define GMB_COV_SMALL_MAX 32
+__host__ __device__ static inline int gmb_cov_ld(int n) { return n <= GMB_COV_SMALL_MAX ? n : (n + 3) / 4 * 4; }
+
+struct gmb_cov {
+    gmb_ctx* ctx = nullptr;
+    int B = 0, Q = 0, R = 0, max_n = 0;
+    std::vector<CovBlock> blocks;
+    std::vector<CovFn> fns;
+    CovBlock* d_blocks = nullptr;
+    CovFn* d_fns = nullptr;
+    double* d_data = nullptr;
+    double* d_theta = nullptr;
+    double* d_Lblk = nullptr;    // concatenated per-block factors (col-major n_b x n_b each), offsets CovBlock::l0
+    long long lblk_doubles = 0;
+    double* d_logdet = nullptr;  // per-block sum of 2 log L_ii
+    int* d_status = nullptr;     // first non-PD pivot (global row index + 1), 0 if fine
+    std::vector<double> theta_cached;
+    bool factor_valid = false;
+    // buffers for host-provided U
+    double* dU = nullptr; size_t dU_doubles = 0;
+    // large-block workspace
+    double* d_work = nullptr; size_t work_doubles = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// kernels' host launchers (defined in the respective .cu files)
+// ------------------------------------------------------------------------------------------------
+// gemm_f64.cu : C (M x N, ldc) = alpha * op(A) * B + beta * C ; A is M x K col-major (transA=0) or K x M (transA=1)
+int gmb_dgemm(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+              const double* B, int ldb, double beta, double* C, int ldc);
+
+// estep.cu
+int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb);
+int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, double* d_out /* 1 double: sum over local cols */);
+int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* d_out /* P*P + P + 1 doubles: local sums */);
+
+// cov.cu
+int gmb_cov_factor(gmb_cov* cv, const double* theta);   // builds + factorises all blocks on the device
+int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_out /* 1 double: sum_j sum_b l_b(u_j) */);
+
+// model.cu
+int gmb_model_reserve_samples(gmb_model* mdl, int m);
+int gmb_model_build_zd(gmb_model* mdl);
+int gmb_solve_small(int P, const double* A, const double* b, double* x);
+
+// hmc.cu
+int gmb_hmc_prepare(gmb_model* mdl, const double* L_host);   // uploads L and forms ZL = Z L
+
+// optim.cpp — batched objective: evaluates k points (columns of X, n x k) into f[k]; returns a GMB_* code
+typedef int (*gmb_objective_batch)(const double* X, int n, int k, double* f, void* user);
+int gmb_minimize_bounded(gmb_objective_batch f, void* user, int n, double* x, const double* lower, const double* upper,
+                         double rhobeg, double xtol, int maxit, double* fmin, int* nfev);
+int gmb_fd_gradient(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
+                    const double* lower, const double* upper, int usebounds, double* grad);
+int gmb_fd_hessian(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
+                   const double* lower, const double* upper, int usebounds, double* hess, int* nfev);
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+#define GMB_PI_FAMILY 3.141593   /* moremaths.h:21,76 write pi like this */
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum; result valid in thread 0.  `red` must hold >= 32 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    int nw = (blockDim.x * blockDim.y * blockDim.z + 31) >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (l < nw) ? red[l] : 0.0;
+        v = warp_sum(v);
+    }
+    return v;
+}
+
+// moremaths.h:16-24
+__device__ __forceinline__ double dev_log_factorial_approx(double n) {
+    if (n == 0) return 0.0;
+    return n * log(n) - n + log(n * (1 + 4 * n * (1 + 2 * n))) / 6 + log(GMB_PI_FAMILY) / 2;
+}
+
+// Per-observation log-density with the reference's algebra (moremaths.h:26-102), in-scope cases.
+//   FL 1: poisson/log   : y*eta - exp(eta) - rowc        (rowc = log_factorial_approx(y), hoisted per row)
+//   FL 3: binomial/logit: y==1: log(1/(1+exp(-eta))) ; y==0: log(1 - 1/(1+exp(-eta)))
+//   FL 7: gaussian/id   : c0 - 0.5*((y-eta)*inv_sigma)^2  (c0 = -log(sigma) - 0.5*log(2*3.141593))
+template <int FL>
+__device__ __forceinline__ double dev_family_ll(double y, double eta, double rowc, double c0, double sigma) {
+    if (FL == 1) {
+        return y * eta - exp(eta) - rowc;
+    } else if (FL == 3) {
+        double p = 1.0 / (1.0 + exp(-1.0 * eta));
+        double r = 0.0;
+        if (y == 1.0) r = log(p);
+        else if (y == 0.0) r = log(1.0 - p);
+        return r;
+    } else {
+        double z = (y - eta) / sigma;
+        return c0 - 0.5 * z * z;
+    }
+}
+
+// gradient residual r(eta) of mcmlmodel.h:170-175 (FL 1), :184-193 (FL 3), :233-238 (FL 7, without the 1/sigma^2)
+template <int FL>
+__device__ __forceinline__ double dev_family_resid(double y, double eta) {
+    if (FL == 1) return y - exp(eta);
+    if (FL == 3) return 1.0 / (exp(eta) + 1.0) + y - 1.0;
+    return y - eta;
+}
+
+// Philox4x32-10; counter = (idx, iteration, chain, stream), key = seed.  Must match oracle/oracle.cpp.
+__device__ __forceinline__ void philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ double dev_u01(uint32_t lo, uint32_t hi) {
+    unsigned long long x = ((unsigned long long)hi << 32) | lo;
+    return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__device__ __forceinline__ void dev_rng_uniform2(unsigned long long seed, uint32_t idx, uint32_t iter, uint32_t chain,
+                                                 uint32_t stream, double& u1, double& u2) {
+    uint32_t c0 = idx, c1 = iter, c2 = chain, c3 = stream;
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    u1 = dev_u01(c0, c1); u2 = dev_u01(c2, c3);
+}
+
+// Box-Muller pair p (elements 2p, 2p+1 of the normal vector)
+__device__ __forceinline__ void dev_rng_normal2(unsigned long long seed, uint32_t p, uint32_t iter, uint32_t chain,
+                                                uint32_t stream, double& z0, double& z1) {
+    double u1, u2;
+    dev_rng_uniform2(seed, p, iter, chain, stream, u1, u2);
+    double r = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    z0 = r * c; z1 = r * s;
+}
+
+#endif  // __CUDACC__

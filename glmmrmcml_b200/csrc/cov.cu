@@ -1,0 +1,463 @@
+// cov.cu — covariance update: D(theta) build, block Cholesky and the multivariate-normal objective.
+//
+// K4: glmmrBase DMatrix::genD / gen_block_mat / DSubMatrix::get_val as reconstructed in SURVEY.md App. C
+//     (call sites mcmldmatrix.h:46,59 ; src/mcml_full.cpp:68,121) — entries D_b(i,j) = prod_k f_k(dist_k(i,j); theta),
+//     lower Cholesky by Cholesky–Banachiewicz.
+// K5: MCMLDmatrix::loglik / loglik_block (mcmldmatrix.h:23-41, 57-78) + algo::forward_sub (moremaths.h:166-179).
+//
+// The reference re-factorises every block once per SAMPLE (mcmldmatrix.h:33-36 -> :59).  Here every block is
+// factorised once per theta; the per-sample work is only the forward substitution, which for small blocks is an
+// HBM stream of u (8 Q m bytes) and for large blocks a blocked TRSM on the DMMA GEMM.
+#include "common.cuh"
+
+namespace {
+
+// SURVEY.md App. C.2 — the id -> function table lives here (and in oracle/oracle.cpp cov_fn) so that it can be
+// corrected in one place should the glmmrBase sources become available.
+__host__ __device__ inline int cov_fn_npar(int id) {
+    switch (id) { case 1: case 2: case 3: case 6: case 14: return 1; case 4: case 5: case 7: case 8: case 9: case 10: case 11: case 12: case 13: return 2; }
+    return 0;
+}
+__host__ __device__ inline bool cov_fn_supported(int id) { return id == 1 || id == 2 || id == 3 || id == 4 || id == 13 || id == 14; }
+
+__device__ __forceinline__ double cov_fn_eval(int id, double d, const double* th) {
+    switch (id) {
+    case 1:  return d == 0.0 ? th[0] * th[0] : 0.0;                 // gr
+    case 2:  return exp(-d / th[0]);                                // fexp0
+    case 3:  return pow(th[0], d);                                  // ar1
+    case 4:  return th[0] * exp(-d * d / (th[1] * th[1]));          // sqexp
+    case 13: return th[0] * exp(-d / th[1]);                        // fexp
+    case 14: return exp(-d * d / (th[0] * th[0]));                  // sqexp0
+    }
+    return nan("");
+}
+
+// DSubMatrix::get_val(i, j)
+__device__ __forceinline__ double block_val(const CovBlock& b, const CovFn* __restrict__ fns, const double* __restrict__ data,
+                                            const double* __restrict__ theta, int i, int j) {
+    double v = 1.0;
+    const double* dat = data + b.data0;
+    for (int f = 0; f < b.nfn; f++) {
+        const CovFn fn = fns[b.fn0 + f];
+        double d2 = 0.0;
+        for (int k = 0; k < fn.nvar; k++) {
+            double di = dat[i + (size_t)(fn.col0 + k) * b.n] - dat[j + (size_t)(fn.col0 + k) * b.n];
+            d2 += di * di;
+        }
+        v *= cov_fn_eval(fn.id, sqrt(d2), theta + fn.par0);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4 small: one warp per block with n_b <= 32.  Lane i owns row i.  Writes the factor (col-major n_b x n_b),
+// the block's log-determinant sum_i 2 log L_ii and a non-PD status.
+// ---------------------------------------------------------------------------------------------------
+constexpr int SMALL_MAX = GMB_COV_SMALL_MAX;
+constexpr int FACT_WARPS = 4;
+
+__global__ void __launch_bounds__(FACT_WARPS * 32) factor_small_kernel(int B, const CovBlock* __restrict__ blocks,
+                                                                        const CovFn* __restrict__ fns, const double* __restrict__ data,
+                                                                        const double* __restrict__ theta, double* __restrict__ Lblk,
+                                                                        double* __restrict__ logdet, int* __restrict__ status) {
+    __shared__ double sL[FACT_WARPS][SMALL_MAX][SMALL_MAX + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bi = blockIdx.x * FACT_WARPS + warp;
+    if (bi >= B) return;
+    const CovBlock b = blocks[bi];
+    if (b.n > SMALL_MAX) return;
+    const int n = b.n;
+    double (*L)[SMALL_MAX + 1] = sL[warp];
+    // entries of the lower triangle, row = lane
+    if (lane < n) for (int j = 0; j <= lane; j++) L[lane][j] = block_val(b, fns, data, theta, lane, j);
+    __syncwarp();
+    bool bad = false;
+    for (int j = 0; j < n; j++) {
+        // Cholesky–Banachiewicz column j: s accumulated in ascending k exactly like the oracle
+        double s = 0.0;
+        if (lane >= j && lane < n) for (int k = 0; k < j; k++) s += L[lane][k] * L[j][k];
+        double djj = __shfl_sync(0xffffffffu, L[j][j] - s, j);   // lane j holds a_jj - sum
+        if (!(djj > 0.0)) { bad = true; if (lane == 0) atomicCAS(status, 0, b.start + j + 1); break; }
+        double d = sqrt(djj);
+        __syncwarp();
+        if (lane == j) L[j][j] = d;
+        else if (lane > j && lane < n) L[lane][j] = (L[lane][j] - s) / d;
+        __syncwarp();
+    }
+    if (bad) { if (lane == 0) logdet[bi] = nan(""); return; }
+    double ld = (lane < n) ? 2.0 * log(L[lane][lane]) : 0.0;
+    ld = warp_sum(ld);
+    if (lane == 0) logdet[bi] = ld;
+    double* out = Lblk + b.l0;
+    for (int e = lane; e < n * n; e += 32) {
+        int i = e % n, j = e / n;
+        out[e] = (j <= i) ? L[i][j] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5 small: forward substitution for blocks with n_b <= 16.  CTA = 8 warps handles a group of 32 consecutive blocks
+// (lane = block) and a chunk of sample columns (warp w takes columns j0 + w, j0 + w + 8, ...).  The group's factors
+// are staged in shared memory once and reused for every column, so the only HBM traffic is the stream of u.
+// Emits sum over (blocks in group, columns in chunk) of ||L_b^{-1} u_bj||^2.
+// ---------------------------------------------------------------------------------------------------
+constexpr int QUAD_SMALL_MAX = 16;
+
+__global__ void __launch_bounds__(256) quad_small_kernel(int B, const CovBlock* __restrict__ blocks, const double* __restrict__ Lblk,
+                                                         const double* __restrict__ U, int ldu, int ncols, int cols_per_cta,
+                                                         double* __restrict__ partials) {
+    extern __shared__ double sL[];                  // factors of the group, block stride padded to an odd count
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b0 = blockIdx.x * 32;
+    const int nb = min(32, B - b0);
+    const int j0 = blockIdx.y * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
+    const int stride = QUAD_SMALL_MAX * QUAD_SMALL_MAX + 1;
+    // stage factors; store 1/L_ii on the diagonal so the inner loop multiplies
+    for (int bb = 0; bb < nb; bb++) {
+        const CovBlock b = blocks[b0 + bb];
+        if (b.n > QUAD_SMALL_MAX) continue;
+        for (int e = threadIdx.x; e < b.n * b.n; e += 256) {
+            int i = e % b.n, j = e / b.n;
+            double v = Lblk[b.l0 + e];
+            sL[bb * stride + i * QUAD_SMALL_MAX + j] = (i == j) ? 1.0 / v : v;
+        }
+    }
+    __syncthreads();
+    double acc = 0.0;
+    if (lane < nb) {
+        const CovBlock b = blocks[b0 + lane];
+        if (b.n <= QUAD_SMALL_MAX) {
+            const double* L = sL + lane * stride;
+            const int n = b.n;
+            for (int j = j0 + warp; j < j1; j += 8) {
+                const double* u = U + (size_t)j * ldu + b.start;
+                double z[QUAD_SMALL_MAX];
+                double q = 0.0;
+#pragma unroll
+                for (int i = 0; i < QUAD_SMALL_MAX; i++) {
+                    if (i < n) {
+                        double lsum = 0.0;
+#pragma unroll
+                        for (int k = 0; k < i; k++) lsum += L[i * QUAD_SMALL_MAX + k] * z[k];     // moremaths.h:172-175
+                        z[i] = (u[i] - lsum) * L[i * QUAD_SMALL_MAX + i];                         // :176 (reciprocal staged)
+                        q += z[i] * z[i];
+                    }
+                }
+                acc += q;
+            }
+        }
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
+// K5 medium: one block with 16 < n_b <= 64, factor in shared memory, one thread per sample column.
+constexpr int QUAD_MED_MAX = 64;
+
+__global__ void __launch_bounds__(128) quad_medium_kernel(CovBlock b, const double* __restrict__ Lblk, const double* __restrict__ U,
+                                                          int ldu, int ncols, double* __restrict__ partials) {
+    extern __shared__ double smm[];
+    __shared__ double red[32];
+    const int n = b.n;
+    double* L = smm;                         // n x n col-major, diagonal holds reciprocals
+    double* z = smm + n * n;                 // [n][128]
+    const int ldb = gmb_cov_ld(n);
+    for (int e = threadIdx.x; e < n * n; e += 128) {
+        int i = e % n, j = e / n;
+        double v = Lblk[b.l0 + i + (size_t)j * ldb];
+        L[e] = (i == j) ? 1.0 / v : v;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    for (int j = blockIdx.x * 128 + threadIdx.x; j < ncols; j += gridDim.x * 128) {
+        const double* u = U + (size_t)j * ldu + b.start;
+        double q = 0.0;
+        for (int i = 0; i < n; i++) {
+            double lsum = 0.0;
+            for (int k = 0; k < i; k++) lsum += L[i + k * n] * z[k * 128 + threadIdx.x];
+            double zi = (u[i] - lsum) * L[i + i * n];
+            z[i * 128 + threadIdx.x] = zi;
+            q += zi * zi;
+        }
+        acc += q;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+
+// final: out[0] = ncols * sum_b (-0.5 n_b log(2 pi) - 0.5 logdet_b) - 0.5 * sum(partials)   (mcmldmatrix.h:63,75: M_PI)
+__global__ void __launch_bounds__(256) mvn_finish_kernel(int B, const CovBlock* __restrict__ blocks, const double* __restrict__ logdet,
+                                                         const double* __restrict__ partials, int npart, int ncols,
+                                                         double* __restrict__ out) {
+    __shared__ double red[32];
+    double c = 0.0, q = 0.0;
+    for (int b = threadIdx.x; b < B; b += 256) c += -0.5 * blocks[b].n * log(2 * 3.14159265358979323846) - 0.5 * logdet[b];
+    for (int k = threadIdx.x; k < npart; k += 256) q += partials[k];
+    c = block_sum(c, red);
+    q = block_sum(q, red);
+    if (threadIdx.x == 0) out[0] = (double)ncols * c - 0.5 * q;
+}
+
+__global__ void logdet_sum_kernel(int B, const double* __restrict__ logdet, double* __restrict__ out) {
+    __shared__ double red[32];
+    double c = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) c += logdet[b];
+    c = block_sum(c, red);
+    if (threadIdx.x == 0) out[0] = c;
+}
+
+// expand the per-block factors (or, with chol == 0, the blocks of D) into a dense ldq x Q matrix
+__global__ void expand_blocks_kernel(int B, const CovBlock* __restrict__ blocks, const CovFn* __restrict__ fns,
+                                     const double* __restrict__ data, const double* __restrict__ theta,
+                                     const double* __restrict__ Lblk, int chol, double* __restrict__ out, int ld) {
+    const CovBlock b = blocks[blockIdx.x];
+    for (int e = threadIdx.x; e < b.n * b.n; e += blockDim.x) {
+        int i = e % b.n, j = e / b.n;
+        double v = chol ? ((j <= i) ? Lblk[b.l0 + i + (size_t)j * gmb_cov_ld(b.n)] : 0.0) : block_val(b, fns, data, theta, i, j);
+        out[(size_t)(b.start + j) * ld + b.start + i] = v;
+    }
+}
+
+}  // namespace
+
+int gmb_cov_factor_large(gmb_cov* cv, int bi);                                        // cov_large.cu
+int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols, double* d_partial);
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+extern "C" int gmb_cov_create(gmb_ctx* ctx, const int32_t* cov, int rows, const double* data, int n_data,
+                              const double* eff_range, int n_eff, gmb_cov** out) {
+    if (!ctx || !cov || !data || !out || rows <= 0) return gmb_set_error(GMB_EINVAL, "gmb_cov_create: bad arguments");
+    gmb_cov* cv = new gmb_cov();
+    cv->ctx = ctx;
+    int maxb = -1;
+    for (int r = 0; r < rows; r++) { if (cov[r] < 0) { delete cv; return gmb_set_error(GMB_EINVAL, "negative block id"); } if (cov[r] > maxb) maxb = cov[r]; }
+    cv->B = maxb + 1;
+    cv->blocks.assign(cv->B, CovBlock{0, 0, -1, 0, 0, 1, 0, 0});
+    // rows of one block are expected to be contiguous (that is how get_D_data() emits them)
+    for (int r = 0; r < rows; r++) {
+        int b = cov[r], nb = cov[r + rows], id = cov[r + 2 * rows], nv = cov[r + 3 * rows], p0 = cov[r + 4 * rows];
+        if (!cov_fn_supported(id)) { delete cv; return gmb_set_error(GMB_ECOV, "covariance function id %d is not supported (supported: 1 gr, 2 fexp0, 3 ar1, 4 sqexp, 13 fexp, 14 sqexp0)", id); }
+        if (nb <= 0 || nv < 0 || p0 < 0) { delete cv; return gmb_set_error(GMB_EINVAL, "bad covariance row %d", r); }
+        CovBlock& blk = cv->blocks[b];
+        if (blk.fn0 < 0) blk.fn0 = (int)cv->fns.size();
+        else if (blk.fn0 + blk.nfn != (int)cv->fns.size()) { delete cv; return gmb_set_error(GMB_EINVAL, "rows of block %d are not contiguous", b); }
+        blk.n = nb;
+        cv->fns.push_back(CovFn{id, nv, p0, blk.ncol, (eff_range && r < n_eff) ? eff_range[r] : 0.0});
+        blk.nfn++; blk.ncol += nv;
+        if (id != 1) blk.all_gr = 0;
+        if (p0 + cov_fn_npar(id) > cv->R) cv->R = p0 + cov_fn_npar(id);
+    }
+    long long off = 0, loff = 0; int start = 0;
+    for (auto& b : cv->blocks) {
+        if (b.n == 0) { delete cv; return gmb_set_error(GMB_EINVAL, "block ids must be 0..B-1 without gaps"); }
+        b.data0 = off; b.start = start; b.l0 = loff;
+        off += (long long)b.n * b.ncol; start += b.n;
+        long long sz = (long long)gmb_cov_ld(b.n) * b.n;     // packed for n <= 32, ld = round_up(n, 4) otherwise
+        loff += (sz + 1) & ~1LL;                              // keep every block 16-byte aligned
+        if (b.n > cv->max_n) cv->max_n = b.n;
+    }
+    if (off > n_data) { delete cv; return gmb_set_error(GMB_EINVAL, "covariance data has %d values, %lld required", n_data, off); }
+    cv->Q = start;
+    cv->lblk_doubles = loff;
+    cudaSetDevice(ctx->device);
+    GMB_CUDA(cudaMalloc(&cv->d_blocks, sizeof(CovBlock) * cv->B));
+    GMB_CUDA(cudaMalloc(&cv->d_fns, sizeof(CovFn) * cv->fns.size()));
+    GMB_CUDA(cudaMalloc(&cv->d_data, sizeof(double) * (off > 0 ? off : 1)));
+    GMB_CUDA(cudaMalloc(&cv->d_theta, sizeof(double) * (cv->R > 0 ? cv->R : 1)));
+    GMB_CUDA(cudaMalloc(&cv->d_Lblk, sizeof(double) * (loff > 0 ? loff : 1)));
+    GMB_CUDA(cudaMalloc(&cv->d_logdet, sizeof(double) * cv->B));
+    GMB_CUDA(cudaMalloc(&cv->d_status, sizeof(int)));
+    GMB_CUDA(cudaMemcpyAsync(cv->d_blocks, cv->blocks.data(), sizeof(CovBlock) * cv->B, cudaMemcpyHostToDevice, ctx->stream));
+    GMB_CUDA(cudaMemcpyAsync(cv->d_fns, cv->fns.data(), sizeof(CovFn) * cv->fns.size(), cudaMemcpyHostToDevice, ctx->stream));
+    GMB_CUDA(cudaMemcpyAsync(cv->d_data, data, sizeof(double) * off, cudaMemcpyHostToDevice, ctx->stream));
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = cv;
+    return GMB_OK;
+}
+
+extern "C" void gmb_cov_destroy(gmb_cov* cv) {
+    if (!cv) return;
+    cudaSetDevice(cv->ctx->device);
+    cudaStreamSynchronize(cv->ctx->stream);
+    cudaFree(cv->d_blocks); cudaFree(cv->d_fns); cudaFree(cv->d_data); cudaFree(cv->d_theta); cudaFree(cv->d_Lblk);
+    cudaFree(cv->d_logdet); cudaFree(cv->d_status);
+    if (cv->dU) cudaFree(cv->dU);
+    if (cv->d_work) cudaFree(cv->d_work);
+    delete cv;
+}
+
+extern "C" int gmb_cov_dims(gmb_cov* cv, int* B, int* Q, int* R) {
+    if (!cv) return gmb_set_error(GMB_EINVAL, "cov is NULL");
+    if (B) *B = cv->B;
+    if (Q) *Q = cv->Q;
+    if (R) *R = cv->R;
+    return GMB_OK;
+}
+
+// Builds and factorises every block for `theta` (cached: repeated calls with the same theta are free).
+int gmb_cov_factor(gmb_cov* cv, const double* theta) {
+    gmb_ctx* ctx = cv->ctx;
+    if (cv->factor_valid && (int)cv->theta_cached.size() == cv->R &&
+        memcmp(cv->theta_cached.data(), theta, sizeof(double) * cv->R) == 0)
+        return GMB_OK;
+    cv->factor_valid = false;
+    for (int r = 0; r < cv->R; r++) ctx->h_pinned[r] = theta[r];
+    GMB_CUDA(cudaMemcpyAsync(cv->d_theta, ctx->h_pinned, sizeof(double) * cv->R, cudaMemcpyHostToDevice, ctx->stream));
+    GMB_CUDA(cudaMemsetAsync(cv->d_status, 0, sizeof(int), ctx->stream));
+    bool any_small = false;
+    for (const auto& b : cv->blocks) if (b.n <= SMALL_MAX) { any_small = true; break; }
+    if (any_small) {
+        factor_small_kernel<<<(cv->B + FACT_WARPS - 1) / FACT_WARPS, FACT_WARPS * 32, 0, ctx->stream>>>(
+            cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_Lblk, cv->d_logdet, cv->d_status);
+        ctx->launches++;
+        GMB_CUDA(cudaGetLastError());
+    }
+    for (int bi = 0; bi < cv->B; bi++)
+        if (cv->blocks[bi].n > SMALL_MAX) GMB_TRY(gmb_cov_factor_large(cv, bi));
+    int* hstat = reinterpret_cast<int*>(ctx->h_pinned + 64);
+    GMB_CUDA(cudaMemcpyAsync(hstat, cv->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*hstat != 0) return gmb_set_error(GMB_ENOTPD, "D(theta) is not positive definite: pivot %d", *hstat - 1);
+    cv->theta_cached.assign(theta, theta + cv->R);
+    cv->factor_valid = true;
+    return GMB_OK;
+}
+
+// d_out[0] = sum over the given columns of sum_b log N(u_j[b]; 0, D_b)   (raw sum; caller divides by m)
+int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_out) {
+    gmb_ctx* ctx = cv->ctx;
+    if (ncols <= 0) { GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream)); return GMB_OK; }
+    int n_small = 0, n_other = 0;
+    for (const auto& b : cv->blocks) { if (b.n <= QUAD_SMALL_MAX) n_small++; else n_other++; }
+    int groups = (cv->B + 31) / 32;
+    int CC = 1, cols_per_cta = ncols;
+    if (n_small) {
+        int want = (ctx->sms * 4 + groups - 1) / groups;
+        int maxcc = (ncols + 15) / 16;
+        CC = want < maxcc ? want : maxcc; if (CC < 1) CC = 1;
+        cols_per_cta = (ncols + CC - 1) / CC;
+        CC = (ncols + cols_per_cta - 1) / cols_per_cta;
+    }
+    const int MED_CTAS = 64;
+    size_t npart_small = n_small ? (size_t)groups * CC : 0;
+    size_t npart = npart_small + (size_t)n_other * MED_CTAS;
+    GMB_TRY(gmb_ctx_scratch(ctx, npart));
+    double* partials = ctx->d_scratch;
+    if (n_other) GMB_CUDA(cudaMemsetAsync(partials + npart_small, 0, sizeof(double) * n_other * MED_CTAS, ctx->stream));
+    if (n_small) {
+        size_t smem = (size_t)32 * (QUAD_SMALL_MAX * QUAD_SMALL_MAX + 1) * sizeof(double);
+        static bool configured = false;
+        if (!configured) { GMB_CUDA(cudaFuncSetAttribute(quad_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+        quad_small_kernel<<<dim3(groups, CC), 256, smem, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_Lblk, dU, ldu, ncols, cols_per_cta, partials);
+        ctx->launches++;
+        GMB_CUDA(cudaGetLastError());
+    }
+    int k = 0;
+    for (int bi = 0; bi < cv->B; bi++) {
+        const CovBlock& b = cv->blocks[bi];
+        if (b.n <= QUAD_SMALL_MAX) continue;
+        double* dst = partials + npart_small + (size_t)k * MED_CTAS;
+        if (b.n <= QUAD_MED_MAX) {
+            size_t smem = ((size_t)b.n * b.n + (size_t)b.n * 128) * sizeof(double);
+            static bool configured = false;
+            if (!configured) { GMB_CUDA(cudaFuncSetAttribute(quad_medium_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((64 * 64 + 64 * 128) * sizeof(double)))); configured = true; }
+            int ctas = (ncols + 127) / 128; if (ctas > MED_CTAS) ctas = MED_CTAS;
+            quad_medium_kernel<<<ctas, 128, smem, ctx->stream>>>(b, cv->d_Lblk, dU, ldu, ncols, dst);
+            ctx->launches++;
+            GMB_CUDA(cudaGetLastError());
+        } else {
+            GMB_TRY(gmb_cov_quad_large(cv, bi, dU, ldu, ncols, dst));
+        }
+        k++;
+    }
+    mvn_finish_kernel<<<1, 256, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_logdet, partials, (int)npart, ncols, d_out);
+    ctx->launches++;
+    GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}
+
+extern "C" int gmb_cov_gen(gmb_cov* cv, const double* theta, int chol, double* L_out) {
+    if (!cv || !theta) return gmb_set_error(GMB_EINVAL, "gmb_cov_gen: bad arguments");
+    gmb_ctx* ctx = cv->ctx;
+    cudaSetDevice(ctx->device);
+    if (chol) GMB_TRY(gmb_cov_factor(cv, theta));
+    else {
+        for (int r = 0; r < cv->R; r++) ctx->h_pinned[r] = theta[r];
+        GMB_CUDA(cudaMemcpyAsync(cv->d_theta, ctx->h_pinned, sizeof(double) * cv->R, cudaMemcpyHostToDevice, ctx->stream));
+        cv->factor_valid = false;
+    }
+    if (!L_out) return GMB_OK;
+    size_t Q = cv->Q;
+    double* dense = nullptr;
+    GMB_CUDA(cudaMalloc(&dense, sizeof(double) * Q * Q));
+    GMB_CUDA(cudaMemsetAsync(dense, 0, sizeof(double) * Q * Q, ctx->stream));
+    expand_blocks_kernel<<<cv->B, 256, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_Lblk, chol, dense, (int)Q);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(L_out, dense, sizeof(double) * Q * Q, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dense);
+    if (e != cudaSuccess) return gmb_set_error(GMB_ECUDA, "gmb_cov_gen: %s", cudaGetErrorString(e));
+    return GMB_OK;
+}
+
+static int cov_upload_u(gmb_cov* cv, const double* U, int Q, int m, int* ldu) {
+    gmb_ctx* ctx = cv->ctx;
+    int ld = round_up(Q, 4);
+    size_t need = (size_t)ld * (m > 0 ? m : 1);
+    if (need > cv->dU_doubles) {
+        if (cv->dU) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(cv->dU)); cv->dU = nullptr; }
+        GMB_CUDA(cudaMalloc(&cv->dU, need * sizeof(double)));
+        cv->dU_doubles = need;
+    }
+    if (m > 0)
+        GMB_CUDA(cudaMemcpy2DAsync(cv->dU, ld * sizeof(double), U, Q * sizeof(double), Q * sizeof(double), m, cudaMemcpyHostToDevice, ctx->stream));
+    *ldu = ld;
+    return GMB_OK;
+}
+
+static int cov_finish_ll(gmb_cov* cv, double* d_out, int m_total, double* out) {
+    gmb_ctx* ctx = cv->ctx;
+    GMB_TRY(gmb_comm_allreduce_dev(ctx, d_out, 1));
+    GMB_CUDA(cudaMemcpyAsync(ctx->h_pinned, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = ctx->h_pinned[0] / m_total;      // mcmldmatrix.h:40
+    return GMB_OK;
+}
+
+extern "C" int gmb_cov_mvn_ll(gmb_cov* cv, const double* theta, const double* U, int Q, int m_local, int m_total, double* out) {
+    if (!cv || !theta || !out || (m_local > 0 && !U)) return gmb_set_error(GMB_EINVAL, "gmb_cov_mvn_ll: bad arguments");
+    if (Q != cv->Q) return gmb_set_error(GMB_EINVAL, "u has %d rows, covariance has %d", Q, cv->Q);
+    if (m_total <= 0 || m_local < 0) return gmb_set_error(GMB_EINVAL, "bad column counts");
+    cudaSetDevice(cv->ctx->device);
+    GMB_TRY(gmb_cov_factor(cv, theta));
+    int ldu;
+    GMB_TRY(cov_upload_u(cv, U, Q, m_local, &ldu));
+    GMB_TRY(gmb_cov_quad(cv, cv->dU, ldu, m_local, cv->ctx->d_result));
+    return cov_finish_ll(cv, cv->ctx->d_result, m_total, out);
+}
+
+extern "C" int gmb_cov_mvn_ll_model(gmb_cov* cv, const double* theta, gmb_model* mdl, int ncols_total, double* out) {
+    if (!cv || !theta || !mdl || !out) return gmb_set_error(GMB_EINVAL, "gmb_cov_mvn_ll_model: bad arguments");
+    if (mdl->Q != cv->Q) return gmb_set_error(GMB_EINVAL, "model has Q=%d, covariance has %d", mdl->Q, cv->Q);
+    if (!mdl->dU || mdl->m_local < 0) return gmb_set_error(GMB_ESTATE, "the model holds no samples (call gmb_model_set_u or gmb_hmc_sample first)");
+    cudaSetDevice(cv->ctx->device);
+    GMB_TRY(gmb_cov_factor(cv, theta));
+    GMB_TRY(gmb_cov_quad(cv, mdl->dU, mdl->ldq, mdl->m_local, cv->ctx->d_result));
+    return cov_finish_ll(cv, cv->ctx->d_result, ncols_total > 0 ? ncols_total : mdl->m_total, out);
+}
+
+extern "C" int gmb_cov_logdet(gmb_cov* cv, const double* theta, double* out) {
+    if (!cv || !theta || !out) return gmb_set_error(GMB_EINVAL, "gmb_cov_logdet: bad arguments");
+    gmb_ctx* ctx = cv->ctx;
+    cudaSetDevice(ctx->device);
+    GMB_TRY(gmb_cov_factor(cv, theta));
+    logdet_sum_kernel<<<1, 256, 0, ctx->stream>>>(cv->B, cv->d_logdet, ctx->d_result);
+    ctx->launches++;
+    GMB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = ctx->h_pinned[0];
+    return GMB_OK;
+}

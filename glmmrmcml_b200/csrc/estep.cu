@@ -1,0 +1,370 @@
+// estep.cu — Monte-Carlo E-step kernels over the cached n x m matrix zd = Z u.
+//
+// K2: E-step objective, mcmlModel::log_likelihood (mcmlmodel.h:284-304) + maths::log_likelihood (moremaths.h:26-102)
+// K3: MCNR sufficient sums, mcmloptim::mcnr (mcmloptim.h:198-236) + update_W (mcmlmodel.h:120-134) + detadmu
+//     (moremaths.h:118-161), using mean_j X^T W_j X = X^T diag(mean_j w_j) X.
+//
+// Both stream zd exactly once (algorithmic bytes 8 n m + 16 n): thread-fixed rows, vectorised
+// 16-byte loads that are contiguous across the warp, xb/y held in registers, column loop unrolled for
+// memory-level parallelism, deterministic two-level reduction (no floating-point atomics).
+#include "common.cuh"
+
+namespace {
+
+__global__ void xb_kernel(int n, int P, int ldn, const double* __restrict__ X, const double* __restrict__ beta,
+                          double* __restrict__ xb) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int p = 0; p < P; p++) s += X[i + (size_t)p * ldn] * beta[p];   // update_beta, mcmlmodel.h:100-102
+    xb[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2.  blockDim = (TX, TY): thread (tx, ty) owns rows 2*(rt*TX + tx) + {0,1} and columns j0 + ty + k*TY.
+// X beta (update_beta, mcmlmodel.h:100-102) is recomputed per thread for its two rows (P fused multiply-adds, X is
+// L2-resident) so that one evaluation is ONE launch.
+// Output: raw sum over the local columns [0, ncols) in out[0] (divide by niter on the host after the all-reduce).
+//
+// binomial/logit: l = log(1/(1+exp(-eta))) (y = 1) or log(1 - 1/(1+exp(-eta))) (y = 0), moremaths.h:47-53; both equal
+// -log(1 + exp(s eta)) with s = -1 (y = 1) or +1 (y = 0).  The FP64 log is the slowest instruction sequence of the
+// stream (profiles/r01_microbench_fp64.txt: log 0.35 Telem/s vs the 0.82 Telem/s that HBM can feed), so the kernel
+// multiplies the 8 factors (1 + exp(s eta)) of one unrolled step and takes ONE log of the product — the same sum to
+// within a few ulp per term, at one eighth of the log count.
+// ---------------------------------------------------------------------------------------------------
+constexpr double LOGIT_PROD_GUARD = 80.0;   // 8 factors below exp(80) cannot overflow a double
+
+template <int FL>
+struct RowTerm {
+    double xb, y, rowc, sg;
+    __device__ __forceinline__ void init(double xb_, double y_, double rowc_) {
+        xb = xb_; y = y_; rowc = rowc_;
+        sg = (y_ == 1.0) ? -1.0 : ((y_ == 0.0) ? 1.0 : 0.0);   // other y contribute nothing (reference leaves logl unset)
+    }
+};
+
+// accumulates the contribution of one element into (acc, prod)
+template <int FL>
+__device__ __forceinline__ void ll_accum(const RowTerm<FL>& r, double z, double c0, double inv_sigma, double& acc, double& prod) {
+    const double eta = r.xb + z;                                     // mcmlmodel.h:298
+    if (FL == 1) {
+        acc += r.y * eta - exp(eta) - r.rowc;                        // moremaths.h:33-40
+    } else if (FL == 3) {
+        const double x = r.sg * eta;
+        const double t = 1.0 + ((r.sg != 0.0) ? exp(x) : 0.0);
+        if (x > LOGIT_PROD_GUARD) acc -= log(t);                     // rare: keep the product finite
+        else prod *= t;
+    } else {
+        const double zz = (r.y - eta) * inv_sigma;                   // moremaths.h:75-78
+        acc += c0 - 0.5 * zz * zz;
+    }
+}
+
+template <int FL>
+__global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int ncols, int cols_per_cta,
+                                                     const double* __restrict__ zd, const double* __restrict__ X,
+                                                     const double* __restrict__ beta,
+                                                     const double* __restrict__ y, const double* __restrict__ rowc,
+                                                     double sigma, double* __restrict__ partials,
+                                                     unsigned int* __restrict__ counter, double* __restrict__ out) {
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const int TX = blockDim.x, TY = blockDim.y;
+    const int i0 = 2 * (blockIdx.x * TX + threadIdx.x);
+    const int j0 = blockIdx.y * cols_per_cta;
+    const int j1 = min(j0 + cols_per_cta, ncols);
+    const double c0 = (FL == 7) ? (-1.0 * log(sigma) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
+    const double inv_sigma = (FL == 7) ? 1.0 / sigma : 1.0;
+
+    double acc = 0.0;
+    if (i0 < n) {
+        const bool two = (i0 + 1 < n);
+        double xb0 = 0.0, xb1 = 0.0;
+        for (int p = 0; p < P; p++) {                                // same order as xb_kernel
+            const double b = beta[p];
+            xb0 += X[i0 + (size_t)p * ldn] * b;
+            if (two) xb1 += X[i0 + 1 + (size_t)p * ldn] * b;
+        }
+        RowTerm<FL> r0, r1;
+        r0.init(xb0, y[i0], (FL == 1) ? rowc[i0] : 0.0);
+        r1.init(xb1, two ? y[i0 + 1] : 0.0, (FL == 1 && two) ? rowc[i0 + 1] : 0.0);
+        if (!two) r1.sg = 0.0;
+        const double* col = zd + i0;
+        int j = j0 + threadIdx.y;
+        // 4 independent 16-byte loads in flight per thread
+        for (; j + 3 * TY < j1; j += 4 * TY) {
+            double2 z[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const double2*>(col + (size_t)(j + u * TY) * ldn);
+            double prod = 1.0, a1 = 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                ll_accum<FL>(r0, z[u].x, c0, inv_sigma, acc, prod);
+                ll_accum<FL>(r1, z[u].y, c0, inv_sigma, a1, prod);
+            }
+            if (FL == 3) acc += a1 - log(prod);
+            else if (two) acc += a1;
+        }
+        for (; j < j1; j += TY) {
+            double2 z = *reinterpret_cast<const double2*>(col + (size_t)j * ldn);
+            double prod = 1.0, a1 = 0.0;
+            ll_accum<FL>(r0, z.x, c0, inv_sigma, acc, prod);
+            ll_accum<FL>(r1, z.y, c0, inv_sigma, a1, prod);
+            if (FL == 3) acc += a1 - log(prod);
+            else if (two) acc += a1;
+        }
+    }
+    // flatten thread index for the block reduction
+    double v = warp_sum(acc);
+    const int t = threadIdx.y * TX + threadIdx.x;
+    const int w = t >> 5, l = t & 31;
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    const int nblocks = gridDim.x * gridDim.y;
+    if (w == 0) {
+        v = (l < 8) ? red[l] : 0.0;
+        v = warp_sum(v);
+        if (l == 0) {
+            partials[bid] = v;
+            __threadfence();
+            unsigned int done = atomicAdd(counter, 1u);
+            is_last = (done == (unsigned)nblocks - 1);
+        }
+    }
+    __syncthreads();
+    if (is_last) {
+        // the last CTA sums the per-CTA partials in a fixed order -> bitwise reproducible result
+        __threadfence();
+        double s = 0.0;
+        for (int k = t; k < nblocks; k += 256) s += partials[k];
+        s = warp_sum(s);
+        __syncthreads();
+        if (l == 0) red[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            s = (l < 8) ? red[l] : 0.0;
+            s = warp_sum(s);
+            if (l == 0) { out[0] = s; *counter = 0u; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3 pass 1.  CTA = 8 warps, row tile of 256 rows (lane owns rows 64k + 2 lane + {0,1}, k = 0..3), warp w walks
+// columns j0 + w, j0 + w + 8, ...  Per element: IRLS weight w_ij, score term wu_ij, residual r_ij.
+// Emits per-(column-chunk) row partial sums and per-(row-tile) column sums of r and r^2.
+// ---------------------------------------------------------------------------------------------------
+template <int FL>
+__device__ __forceinline__ void mcnr_terms(double y, double eta, double inv_phi, double& w, double& wu, double& r) {
+    if (FL == 1) {               // poisson/log : dhdmu = exp(-eta), detadmu = exp(-eta)
+        double mu = exp(eta);
+        r = y - mu; w = mu; wu = r;
+    } else if (FL == 3) {        // binomial/logit : dhdmu = detadmu = 1/(p(1-p))
+        double e = exp(eta);
+        double p = e / (1.0 + e);
+        r = y - p; w = p * (1.0 - p); wu = r;
+    } else {                     // gaussian/identity : W = 1/sigma^2
+        r = y - eta; w = inv_phi; wu = inv_phi * r;
+    }
+}
+
+template <int FL>
+__global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int ncols, int cols_per_cta,
+                                                         const double* __restrict__ zd, const double* __restrict__ xb,
+                                                         const double* __restrict__ y, double inv_phi,
+                                                         double* __restrict__ rowpart /* [gridDim.y][2][ldn] */,
+                                                         double* __restrict__ colpart /* [gridDim.x][2][ncols] */) {
+    extern __shared__ double sm[];   // [8 warps][2][256]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rbase = blockIdx.x * 256;
+    const int j0 = blockIdx.y * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
+
+    double xbr[8], yr[8], wacc[8], sacc[8];
+    bool ok[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            int i = rbase + 64 * k + 2 * lane + v;
+            ok[2 * k + v] = i < n;
+            xbr[2 * k + v] = ok[2 * k + v] ? xb[i] : 0.0;
+            yr[2 * k + v] = ok[2 * k + v] ? y[i] : 0.0;
+            wacc[2 * k + v] = 0.0; sacc[2 * k + v] = 0.0;
+        }
+    for (int j = j0 + warp; j < j1; j += 8) {
+        const double* col = zd + (size_t)j * ldn + rbase + 2 * lane;
+        double2 z[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            z[k] = (rbase + 64 * k + 2 * lane < ldn) ? *reinterpret_cast<const double2*>(col + 64 * k) : make_double2(0.0, 0.0);
+        }
+        double sr = 0.0, sr2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int v = 0; v < 2; v++) {
+                int e = 2 * k + v;
+                if (ok[e]) {
+                    double w, wu, r;
+                    mcnr_terms<FL>(yr[e], xbr[e] + (v ? z[k].y : z[k].x), inv_phi, w, wu, r);
+                    wacc[e] += w; sacc[e] += wu; sr += r; sr2 += r * r;
+                }
+            }
+        sr = warp_sum(sr); sr2 = warp_sum(sr2);
+        if (lane == 0) {
+            colpart[((size_t)blockIdx.x * 2 + 0) * ncols + j] = sr;
+            colpart[((size_t)blockIdx.x * 2 + 1) * ncols + j] = sr2;
+        }
+    }
+    // cross-warp reduction of the row accumulators
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            int r = 64 * k + 2 * lane + v;
+            sm[(warp * 2 + 0) * 256 + r] = wacc[2 * k + v];
+            sm[(warp * 2 + 1) * 256 + r] = sacc[2 * k + v];
+        }
+    __syncthreads();
+    {
+        int r = threadIdx.x;   // 256 threads <-> 256 rows
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { a += sm[(w * 2 + 0) * 256 + r]; b += sm[(w * 2 + 1) * 256 + r]; }
+        int i = rbase + r;
+        if (i < n) {
+            rowpart[((size_t)blockIdx.y * 2 + 0) * ldn + i] = a;
+            rowpart[((size_t)blockIdx.y * 2 + 1) * ldn + i] = b;
+        }
+    }
+}
+
+// K3 pass 2a: rows — sum the column-chunk partials;  2b: columns — sigma_j = sd(resid_j) (mcmloptim.h:216), summed.
+__global__ void mcnr_rows_kernel(int n, int ldn, int nchunks, const double* __restrict__ rowpart,
+                                 double* __restrict__ wsum, double* __restrict__ ssum) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double a = 0.0, b = 0.0;
+    for (int c = 0; c < nchunks; c++) {
+        a += rowpart[((size_t)c * 2 + 0) * ldn + i];
+        b += rowpart[((size_t)c * 2 + 1) * ldn + i];
+    }
+    wsum[i] = a; ssum[i] = b;
+}
+
+__global__ void __launch_bounds__(256) mcnr_sigma_kernel(int n, int ncols, int ntiles, const double* __restrict__ colpart,
+                                                         double* __restrict__ partial /* [gridDim.x] */) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ncols; j += gridDim.x * blockDim.x) {
+        double sr = 0.0, sr2 = 0.0;
+        for (int t = 0; t < ntiles; t++) {
+            sr += colpart[((size_t)t * 2 + 0) * ncols + j];
+            sr2 += colpart[((size_t)t * 2 + 1) * ncols + j];
+        }
+        double mean = sr / n;
+        double ss = sr2 - n * mean * mean;          // sum (r - mean)^2
+        acc += sqrt(fmax(ss, 0.0) / (n - 1));
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+// K3 pass 3: out[a + b P] = sum_i X_ia wsum_i X_ib ; out[P*P + a] = sum_i X_ia ssum_i ; out[P*P+P] = sum_j sigma_j.
+__global__ void __launch_bounds__(256) mcnr_assemble_kernel(int n, int P, int ldn, const double* __restrict__ X,
+                                                            const double* __restrict__ wsum, const double* __restrict__ ssum,
+                                                            const double* __restrict__ sigpart, int nsig,
+                                                            double* __restrict__ out) {
+    __shared__ double red[32];
+    int e = blockIdx.x;
+    double acc = 0.0;
+    if (e < P * P) {
+        int a = e % P, b = e / P;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) acc += X[i + (size_t)a * ldn] * wsum[i] * X[i + (size_t)b * ldn];
+    } else if (e < P * P + P) {
+        int a = e - P * P;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) acc += X[i + (size_t)a * ldn] * ssum[i];
+    } else {
+        for (int i = threadIdx.x; i < nsig; i += blockDim.x) acc += sigpart[i];
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[e] = acc;
+}
+
+}  // namespace
+
+int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb) {
+    gmb_ctx* ctx = mdl->ctx;
+    xb_kernel<<<(mdl->n + 255) / 256, 256, 0, ctx->stream>>>(mdl->n, mdl->P, mdl->ldn, mdl->dX, d_beta, d_xb);
+    ctx->launches++;
+    GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}
+
+int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, double* d_out) {
+    gmb_ctx* ctx = mdl->ctx;
+    const int n = mdl->n, ncols = mdl->niter_local;
+    if (ncols <= 0) { GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream)); return GMB_OK; }
+    int half = (n + 1) / 2;
+    int TX = 32; while (TX < 256 && TX < half) TX <<= 1;
+    int TY = 256 / TX;
+    int RT = (half + TX - 1) / TX;
+    // enough CTAs for ~6 per SM, but keep >= 4*TY columns per CTA so the unrolled loop is used
+    int want_cc = (ctx->sms * 6 + RT - 1) / RT;
+    int max_cc = (ncols + 4 * TY - 1) / (4 * TY);
+    int CC = want_cc < max_cc ? want_cc : max_cc; if (CC < 1) CC = 1;
+    int cols_per_cta = (ncols + CC - 1) / CC;
+    cols_per_cta = round_up(cols_per_cta, TY);
+    CC = (ncols + cols_per_cta - 1) / cols_per_cta;
+    size_t nblocks = (size_t)RT * CC;
+    GMB_TRY(gmb_ctx_scratch(ctx, nblocks));
+    double* partials = ctx->d_scratch;
+    unsigned int* counter = ctx->d_counter;   // zeroed at ctx creation and re-zeroed by the last CTA
+    dim3 grid(RT, CC), block(TX, TY);
+    switch (mdl->flink) {
+    case 1: loglik_kernel<1><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dzd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 3: loglik_kernel<3><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dzd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 7: loglik_kernel<7><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dzd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    default: return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
+    }
+    ctx->launches++;
+    GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}
+
+int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* d_out) {
+    gmb_ctx* ctx = mdl->ctx;
+    const int n = mdl->n, P = mdl->P, ldn = mdl->ldn, ncols = mdl->niter_local;
+    const int nout = P * P + P + 1;
+    if (ncols <= 0) { GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * nout, ctx->stream)); return GMB_OK; }
+    int RT = (n + 255) / 256;
+    int want_cc = (ctx->sms * 4 + RT - 1) / RT;
+    int max_cc = (ncols + 31) / 32;
+    int CC = want_cc < max_cc ? want_cc : max_cc; if (CC < 1) CC = 1;
+    int cols_per_cta = (ncols + CC - 1) / CC;
+    CC = (ncols + cols_per_cta - 1) / cols_per_cta;
+    const int NSIG = 64;
+    size_t need = (size_t)CC * 2 * ldn + (size_t)RT * 2 * ncols + 2 * (size_t)ldn + NSIG;
+    GMB_TRY(gmb_ctx_scratch(ctx, need));
+    double* rowpart = ctx->d_scratch;
+    double* colpart = rowpart + (size_t)CC * 2 * ldn;
+    double* wsum = colpart + (size_t)RT * 2 * ncols;
+    double* ssum = wsum + ldn;
+    double* sigpart = ssum + ldn;
+    double inv_phi = (mdl->flink == 7) ? 1.0 / (var_par * var_par) : 1.0;   // mcmlmodel.h:123-133
+    dim3 grid(RT, CC);
+    size_t smem = 8 * 2 * 256 * sizeof(double);
+    switch (mdl->flink) {
+    case 1: mcnr_pass1_kernel<1><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
+    case 3: mcnr_pass1_kernel<3><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
+    case 7: mcnr_pass1_kernel<7><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
+    default: return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
+    }
+    mcnr_rows_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ldn, CC, rowpart, wsum, ssum);
+    mcnr_sigma_kernel<<<NSIG, 256, 0, ctx->stream>>>(n, ncols, RT, colpart, sigpart);
+    mcnr_assemble_kernel<<<nout, 256, 0, ctx->stream>>>(n, P, ldn, mdl->dX, wsum, ssum, sigpart, NSIG, d_out);
+    ctx->launches += 4;
+    GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}

@@ -1,0 +1,248 @@
+// model.cu — host side of gmb_model: the device-resident replacement of glmmr::mcmlModel
+// (inst/include/glmmrmcml/mcmlmodel.h:28-307).
+//
+// What the reference object caches per evaluation is hoisted here to "once per sample matrix":
+//   zd = Z u  is built once in gmb_model_set_u (the reference rebuilds it in every log_likelihood call,
+//   mcmlmodel.h:286, and m times per mcnr() call, mcmloptim.h:213 -> mcmlmodel.h:121).
+// The dense n x n weight matrix W_ (mcmlmodel.h:36,62) is never materialised.
+#include "common.cuh"
+
+namespace {
+
+// family+link -> flink, mcmlmodel.h:74-87
+int flink_from_strings(const char* family, const char* link) {
+    static const char* keys[12] = {"poissonlog", "poissonidentity", "binomiallogit", "binomiallog",
+                                   "binomialidentity", "binomialprobit", "gaussianidentity", "gaussianlog",
+                                   "gammalog", "gammainverse", "gammaidentity", "betalogit"};
+    std::string k = std::string(family ? family : "") + std::string(link ? link : "");
+    for (int i = 0; i < 12; i++) if (k == keys[i]) return i + 1;
+    return 0;
+}
+
+__global__ void rowc_kernel(int n, int flink, const double* __restrict__ y, double* __restrict__ rowc) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rowc[i] = (flink == 1) ? dev_log_factorial_approx(y[i]) : 0.0;   // moremaths.h:34-39
+}
+
+int upload_matrix(gmb_ctx* ctx, double* dst, int ld, const double* src, int rows, int cols) {
+    if (rows == 0 || cols == 0) return GMB_OK;
+    GMB_CUDA(cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(double), src, (size_t)rows * sizeof(double),
+                               (size_t)rows * sizeof(double), cols, cudaMemcpyHostToDevice, ctx->stream));
+    return GMB_OK;
+}
+
+int upload_params(gmb_model* mdl, const double* beta, int count) {
+    gmb_ctx* ctx = mdl->ctx;
+    if ((size_t)count > ctx->pinned_doubles / 2) return gmb_set_error(GMB_EINVAL, "too many parameter values in one call (%d)", count);
+    if (count > mdl->beta_cap) {
+        if (mdl->dbeta) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(mdl->dbeta)); mdl->dbeta = nullptr; }
+        GMB_CUDA(cudaMalloc(&mdl->dbeta, sizeof(double) * count));
+        mdl->beta_cap = count;
+    }
+    // the pinned staging area is reused by every call: make sure the previous copy has been consumed
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->h_pinned, beta, sizeof(double) * count);
+    GMB_CUDA(cudaMemcpyAsync(mdl->dbeta, ctx->h_pinned, sizeof(double) * count, cudaMemcpyHostToDevice, ctx->stream));
+    return GMB_OK;
+}
+
+}  // namespace
+
+extern "C" int gmb_model_create(gmb_ctx* ctx, int n, int P, int Q, const double* X, const double* Z, const double* y,
+                                const char* family, const char* link, gmb_model** out) {
+    if (!ctx || !out || !X || !Z || !y || n <= 0 || P <= 0 || Q <= 0)
+        return gmb_set_error(GMB_EINVAL, "gmb_model_create: bad arguments (n=%d P=%d Q=%d)", n, P, Q);
+    int fl = flink_from_strings(family, link);
+    if (fl == 0)
+        return gmb_set_error(GMB_EFAMILY, "unknown family/link '%s'/'%s' (mcmlmodel.h:74-87 lists the valid pairs)",
+                             family ? family : "", link ? link : "");
+    if (fl != 1 && fl != 3 && fl != 7)
+        return gmb_set_error(GMB_EFAMILY, "family/link '%s'/'%s' (code %d) has no device kernel; in scope: poisson/log, "
+                             "binomial/logit, gaussian/identity", family, link, fl);
+    GMB_CUDA(cudaSetDevice(ctx->device));
+    gmb_model* mdl = new gmb_model();
+    mdl->ctx = ctx; mdl->n = n; mdl->P = P; mdl->Q = Q; mdl->flink = fl;
+    mdl->ldn = round_up(n, 4); mdl->ldq = round_up(Q, 4);
+    const size_t ldn = mdl->ldn;
+    cudaError_t e = cudaSuccess;
+    auto alloc0 = [&](double** p, size_t doubles) {
+        if (e != cudaSuccess) return;
+        e = cudaMalloc(p, doubles * sizeof(double));
+        if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, doubles * sizeof(double), ctx->stream);
+    };
+    alloc0(&mdl->dX, ldn * P); alloc0(&mdl->dZ, ldn * Q); alloc0(&mdl->dy, ldn); alloc0(&mdl->drowc, ldn); alloc0(&mdl->dxb, ldn);
+    if (e != cudaSuccess) { gmb_model_destroy(mdl); return gmb_set_error(GMB_ECUDA, "gmb_model_create: %s", cudaGetErrorString(e)); }
+    int rc = upload_matrix(ctx, mdl->dX, mdl->ldn, X, n, P);
+    if (!rc) rc = upload_matrix(ctx, mdl->dZ, mdl->ldn, Z, n, Q);
+    if (!rc) rc = upload_matrix(ctx, mdl->dy, mdl->ldn, y, n, 1);
+    if (rc) { gmb_model_destroy(mdl); return rc; }
+    rowc_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, fl, mdl->dy, mdl->drowc);
+    ctx->launches++;
+    e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { gmb_model_destroy(mdl); return gmb_set_error(GMB_ECUDA, "gmb_model_create: %s", cudaGetErrorString(e)); }
+    *out = mdl;
+    return GMB_OK;
+}
+
+extern "C" void gmb_model_destroy(gmb_model* mdl) {
+    if (!mdl) return;
+    cudaSetDevice(mdl->ctx->device);
+    cudaStreamSynchronize(mdl->ctx->stream);
+    cudaFree(mdl->dX); cudaFree(mdl->dZ); cudaFree(mdl->dy); cudaFree(mdl->drowc); cudaFree(mdl->dxb); cudaFree(mdl->dbeta);
+    cudaFree(mdl->dU); cudaFree(mdl->dzd); cudaFree(mdl->dZL); cudaFree(mdl->dL);
+    cudaFree(mdl->dV); cudaFree(mdl->hmc_work);
+    delete mdl;
+}
+
+extern "C" int gmb_model_flink(gmb_model* mdl) { return mdl ? mdl->flink : 0; }
+
+// grow the sample buffers (dU: ldq x m_cap, dzd: ldn x m_cap); contents are NOT preserved
+int gmb_model_reserve_samples(gmb_model* mdl, int m) {
+    gmb_ctx* ctx = mdl->ctx;
+    if (m <= mdl->m_cap) return GMB_OK;
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (mdl->dU) { cudaFree(mdl->dU); mdl->dU = nullptr; }
+    if (mdl->dzd) { cudaFree(mdl->dzd); mdl->dzd = nullptr; }
+    mdl->m_cap = 0;
+    size_t cap = (size_t)m;
+    GMB_CUDA(cudaMalloc(&mdl->dU, sizeof(double) * mdl->ldq * cap));
+    GMB_CUDA(cudaMalloc(&mdl->dzd, sizeof(double) * mdl->ldn * cap));
+    // padding rows must hold finite values: the streaming kernels load them (and mask the result)
+    GMB_CUDA(cudaMemsetAsync(mdl->dU, 0, sizeof(double) * mdl->ldq * cap, ctx->stream));
+    GMB_CUDA(cudaMemsetAsync(mdl->dzd, 0, sizeof(double) * mdl->ldn * cap, ctx->stream));
+    mdl->m_cap = m;
+    return GMB_OK;
+}
+
+// zd = Z u for the first m_local columns of dU (mcmlmodel.h:286 / :117, hoisted)
+int gmb_model_build_zd(gmb_model* mdl) {
+    if (mdl->m_local > 0)
+        GMB_TRY(gmb_dgemm(mdl->ctx, 0, 0, mdl->n, mdl->m_local, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dU, mdl->ldq, 0.0, mdl->dzd, mdl->ldn));
+    mdl->zd_valid = true;
+    return GMB_OK;
+}
+
+static int set_counts(gmb_model* mdl, int m_local, int m_total, int niter_total) {
+    gmb_ctx* ctx = mdl->ctx;
+    if (m_total <= 0) m_total = m_local;
+    if (niter_total <= 0 || niter_total > m_total) niter_total = m_total;
+    if (ctx->world == 1 && m_total != m_local) return gmb_set_error(GMB_EINVAL, "m_total (%d) != m_local (%d) on a single rank", m_total, m_local);
+    // the E-step uses the leading niter_total columns (mcmlmodel.h:73,295); ranks own consecutive column ranges,
+    // so only the trailing rank(s) drop columns
+    int drop = m_total - niter_total;
+    int nl = m_local;
+    if (drop > 0) {
+        if (ctx->world == 1) nl = m_local - drop;
+        else if (ctx->rank == ctx->world - 1) {
+            if (drop > m_local) return gmb_set_error(GMB_EINVAL, "niter_total leaves the last rank with a negative column count");
+            nl = m_local - drop;
+        }
+    }
+    mdl->m_local = m_local; mdl->m_total = m_total; mdl->niter_total = niter_total; mdl->niter_local = nl;
+    return GMB_OK;
+}
+
+extern "C" int gmb_model_set_u(gmb_model* mdl, const double* U, int Q, int m_local, int m_total, int niter_total) {
+    if (!mdl || m_local < 0 || (m_local > 0 && !U)) return gmb_set_error(GMB_EINVAL, "gmb_model_set_u: bad arguments");
+    if (Q != mdl->Q) return gmb_set_error(GMB_EINVAL, "u has %d rows, Z has %d columns", Q, mdl->Q);
+    gmb_ctx* ctx = mdl->ctx;
+    GMB_CUDA(cudaSetDevice(ctx->device));
+    mdl->zd_valid = false;
+    GMB_TRY(set_counts(mdl, m_local, m_total, niter_total));
+    GMB_TRY(gmb_model_reserve_samples(mdl, m_local > 0 ? m_local : 1));
+    GMB_TRY(upload_matrix(ctx, mdl->dU, mdl->ldq, U, Q, m_local));
+    GMB_TRY(gmb_model_build_zd(mdl));
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));   // U is a caller buffer: do not return before it has been read
+    return GMB_OK;
+}
+
+extern "C" int gmb_model_use_device_u(gmb_model* mdl, int niter_total) {
+    if (!mdl) return gmb_set_error(GMB_EINVAL, "model is NULL");
+    if (!mdl->dU || mdl->m_local <= 0 && mdl->ctx->world == 1) return gmb_set_error(GMB_ESTATE, "the model holds no device samples (run gmb_hmc_sample with keep_on_device)");
+    GMB_CUDA(cudaSetDevice(mdl->ctx->device));
+    GMB_TRY(set_counts(mdl, mdl->m_local, mdl->m_total, niter_total));
+    if (!mdl->zd_valid) GMB_TRY(gmb_model_build_zd(mdl));
+    return GMB_OK;
+}
+
+static int check_ready(gmb_model* mdl, const double* beta) {
+    if (!mdl || !beta) return gmb_set_error(GMB_EINVAL, "model or beta is NULL");
+    if (!mdl->zd_valid) return gmb_set_error(GMB_ESTATE, "no samples set: call gmb_model_set_u (or gmb_hmc_sample + gmb_model_use_device_u) first");
+    if (mdl->niter_total <= 0) return gmb_set_error(GMB_ESTATE, "the sample matrix has no columns");
+    return GMB_OK;
+}
+
+extern "C" int gmb_model_loglik_batch(gmb_model* mdl, const double* beta_mat, const double* var_par, int n_eval, double* out) {
+    GMB_TRY(check_ready(mdl, beta_mat));
+    if (!var_par || !out || n_eval <= 0) return gmb_set_error(GMB_EINVAL, "gmb_model_loglik_batch: bad arguments");
+    if (n_eval > GMB_RESULT_DOUBLES) return gmb_set_error(GMB_EINVAL, "at most %d evaluations per batch", GMB_RESULT_DOUBLES);
+    gmb_ctx* ctx = mdl->ctx;
+    GMB_CUDA(cudaSetDevice(ctx->device));
+    if (mdl->flink == 7) for (int e = 0; e < n_eval; e++) if (!(var_par[e] > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0 (got %g)", var_par[e]);
+    GMB_TRY(upload_params(mdl, beta_mat, mdl->P * n_eval));
+    for (int e = 0; e < n_eval; e++)
+        GMB_TRY(gmb_launch_loglik(mdl, mdl->dbeta + (size_t)e * mdl->P, var_par[e], ctx->d_result + e));
+    GMB_TRY(gmb_comm_allreduce_dev(ctx, ctx->d_result, n_eval));
+    double* hres = ctx->h_pinned + ctx->pinned_doubles / 2;
+    GMB_CUDA(cudaMemcpyAsync(hres, ctx->d_result, sizeof(double) * n_eval, cudaMemcpyDeviceToHost, ctx->stream));
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int e = 0; e < n_eval; e++) out[e] = hres[e] / mdl->niter_total;   // mcmlmodel.h:303 ll.mean()
+    return GMB_OK;
+}
+
+extern "C" int gmb_model_loglik(gmb_model* mdl, const double* beta, double var_par, double* out) {
+    return gmb_model_loglik_batch(mdl, beta, &var_par, 1, out);
+}
+
+// Solves A x = b for a small P x P system by Gaussian elimination with partial pivoting
+// (stands in for Eigen's .inverse() at mcmloptim.h:230).  Returns non-zero when singular.
+int gmb_solve_small(int P, const double* A_in, const double* b_in, double* x) {
+    std::vector<double> A(A_in, A_in + (size_t)P * P), b(b_in, b_in + P);
+    for (int c = 0; c < P; c++) {
+        int piv = c; double best = fabs(A[c + (size_t)c * P]);
+        for (int r = c + 1; r < P; r++) if (fabs(A[r + (size_t)c * P]) > best) { best = fabs(A[r + (size_t)c * P]); piv = r; }
+        if (!(best > 0.0)) return 1;
+        if (piv != c) { for (int k = 0; k < P; k++) std::swap(A[c + (size_t)k * P], A[piv + (size_t)k * P]); std::swap(b[c], b[piv]); }
+        for (int r = c + 1; r < P; r++) {
+            double f = A[r + (size_t)c * P] / A[c + (size_t)c * P];
+            for (int k = c; k < P; k++) A[r + (size_t)k * P] -= f * A[c + (size_t)k * P];
+            b[r] -= f * b[c];
+        }
+    }
+    for (int r = P - 1; r >= 0; r--) {
+        double s = b[r];
+        for (int k = r + 1; k < P; k++) s -= A[r + (size_t)k * P] * x[k];
+        x[r] = s / A[r + (size_t)r * P];
+    }
+    return 0;
+}
+
+extern "C" int gmb_model_mcnr(gmb_model* mdl, const double* beta, double var_par,
+                              double* xtwx, double* score, double* beta_incr, double* sigma) {
+    GMB_TRY(check_ready(mdl, beta));
+    gmb_ctx* ctx = mdl->ctx;
+    GMB_CUDA(cudaSetDevice(ctx->device));
+    const int P = mdl->P, nout = P * P + P + 1;
+    if (nout > GMB_RESULT_DOUBLES) return gmb_set_error(GMB_EINVAL, "P = %d is too large for the MCNR sums buffer", P);
+    if (mdl->n < 2) return gmb_set_error(GMB_EINVAL, "MCNR needs n >= 2 (sd of the residuals, mcmloptim.h:216)");
+    GMB_TRY(upload_params(mdl, beta, P));
+    GMB_TRY(gmb_launch_xb(mdl, mdl->dbeta, mdl->dxb));
+    GMB_TRY(gmb_launch_mcnr(mdl, mdl->dxb, var_par, ctx->d_result));
+    GMB_TRY(gmb_comm_allreduce_dev(ctx, ctx->d_result, nout));      // the P^2 + P + 1 sufficient sums, SURVEY §8e
+    double* hres = ctx->h_pinned + ctx->pinned_doubles / 2;
+    GMB_CUDA(cudaMemcpyAsync(hres, ctx->d_result, sizeof(double) * nout, cudaMemcpyDeviceToHost, ctx->stream));
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double inv = 1.0 / mdl->niter_total;
+    std::vector<double> A((size_t)P * P), sc(P), incr(P);
+    for (int k = 0; k < P * P; k++) A[k] = hres[k] * inv;          // mcmloptim.h:227-229
+    for (int k = 0; k < P; k++) sc[k] = hres[P * P + k] * inv;     // :231-232
+    if (xtwx) memcpy(xtwx, A.data(), sizeof(double) * P * P);
+    if (score) memcpy(score, sc.data(), sizeof(double) * P);
+    if (sigma) *sigma = hres[P * P + P] * inv;                     // :235
+    if (beta_incr) {
+        if (gmb_solve_small(P, A.data(), sc.data(), incr.data())) return gmb_set_error(GMB_EINVAL, "MCNR: X^T W X is singular");
+        memcpy(beta_incr, incr.data(), sizeof(double) * P);
+    }
+    return GMB_OK;
+}

@@ -1,0 +1,191 @@
+/* glmmrmcml_b200.h — C-ABI of the B200-native Monte-Carlo E-step + random-effect sampler of glmmrMCML.
+ *
+ * This is the drop-in boundary: the entry points below are what the reference's Rcpp
+ * exports (src/RcppExports.cpp:291-305) bind to once their bodies are replaced by thin adapters; see
+ * INTEGRATION.md for the adapter code.  Conventions:
+ *   - every pointer is a HOST pointer owned by the caller; matrices are column-major double
+ *     (what R / Eigen hand over), integer matrices column-major int32;
+ *   - the library never keeps a host pointer past return; opaque handles own device memory;
+ *   - every function returns 0 on success or a GMB_E* code; gmb_last_error() gives the message
+ *     (thread-local).  No C++ exception crosses this boundary;
+ *   - there is NO CPU fallback: without a CUDA device every call that computes fails with GMB_ECUDA.
+ *
+ * All paths cited are relative to the reference tree.
+ */
+#ifndef GLMMRMCML_B200_H
+#define GLMMRMCML_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMB_OK        0
+#define GMB_EINVAL    1   /* bad argument / size mismatch */
+#define GMB_EFAMILY   2   /* unknown family+link (the reference throws std::out_of_range, mcmlmodel.h:89) */
+#define GMB_ECUDA     3   /* CUDA runtime / no device */
+#define GMB_ENOTPD    4   /* D(theta) not positive definite; message carries the pivot index */
+#define GMB_ENCCL     5   /* NCCL failure */
+#define GMB_ESTATE    6   /* call order (e.g. loglik before set_u) */
+#define GMB_ECOV      7   /* unsupported covariance function id */
+
+typedef struct gmb_ctx   gmb_ctx;     /* one per process: device, streams, scratch, optional NCCL communicator */
+typedef struct gmb_model gmb_model;   /* replaces glmmr::mcmlModel (inst/include/glmmrmcml/mcmlmodel.h:28-307) */
+typedef struct gmb_cov   gmb_cov;     /* replaces glmmr::DData + glmmr::MCMLDmatrix (mcmldmatrix.h:18-79) */
+
+const char* gmb_last_error(void);
+const char* gmb_version(void);
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int  gmb_ctx_create(int device, gmb_ctx** out);
+void gmb_ctx_destroy(gmb_ctx* ctx);
+int  gmb_ctx_sync(gmb_ctx* ctx);
+/* Number of kernels this library launched on this context so far (bench.py's "gpu_launches"). */
+int64_t gmb_ctx_launch_count(gmb_ctx* ctx);
+/* Raw cudaStream_t the kernels are launched on (so callers can bracket it with CUDA events). */
+void* gmb_ctx_stream(gmb_ctx* ctx);
+
+/* Multi-GPU: one process per GPU; Monte-Carlo samples and chains are sharded over ranks, the
+ * per-evaluation sufficient sums are summed with ncclAllReduce on the context's stream.  The 128-byte NCCL
+ * unique id is created on rank 0 and distributed by the caller (torch.distributed / MPI / R sockets). */
+int gmb_comm_unique_id(void* id128);
+int gmb_comm_init(gmb_ctx* ctx, const void* id128, int rank, int world);
+int gmb_comm_rank(gmb_ctx* ctx, int* rank, int* world);
+/* Sum `count` doubles over ranks, in place, host buffer (used by host-side callers; no-op when world == 1). */
+int gmb_comm_allreduce_host(gmb_ctx* ctx, double* buf, int count);
+/* Broadcast `count` doubles from rank 0 (the (beta, theta, sigma) broadcast of each MCML iteration). */
+int gmb_comm_bcast_host(gmb_ctx* ctx, double* buf, int count);
+
+/* ---- model: replaces glmmr::mcmlModel ------------------------------------------------------------------ */
+/* mcmlModel ctor, mcmlmodel.h:51-98.  X is n x P, Z is n x Q, y length n.  family/link as in :74-87;
+ * in scope: poisson/log (1), binomial/logit (3), gaussian/identity (7). */
+int  gmb_model_create(gmb_ctx* ctx, int n, int P, int Q, const double* X, const double* Z, const double* y,
+                      const char* family, const char* link, gmb_model** out);
+void gmb_model_destroy(gmb_model* mdl);
+int  gmb_model_flink(gmb_model* mdl);
+
+/* Set the Monte-Carlo sample matrix u (Q x m_local columns of THIS rank; m_total = columns over all ranks) and
+ * build zd = Z u once (the reference rebuilds it on every evaluation, mcmlmodel.h:286).
+ * niter_total = number of leading columns the E-step averages over (mcmlmodel.h:73 niter_; pass m_total unless
+ * reproducing the Q x (m+1) quirk of mhmcmc.h:126,155 where niter_ = m). */
+int gmb_model_set_u(gmb_model* mdl, const double* U, int Q, int m_local, int m_total, int niter_total);
+/* Same, but the samples are already on the device from gmb_hmc_sample(..., keep_on_device=1). */
+int gmb_model_use_device_u(gmb_model* mdl, int niter_total);
+
+/* E-step objective, mcmlModel::log_likelihood mcmlmodel.h:284-304 after update_beta(beta) (:100-102):
+ * mean_j sum_i l(y_i, (X beta)_i + zd_ij ; var_par).  All-reduced over ranks. */
+int gmb_model_loglik(gmb_model* mdl, const double* beta, double var_par, double* out);
+/* Batched: evaluates n_eval parameter vectors (columns of beta_mat P x n_eval, var_par[n_eval]) back to back with
+ * one device->host read at the end (the pattern of f_hess's 4k^2 stencil, mcmloptim.h:333-355). */
+int gmb_model_loglik_batch(gmb_model* mdl, const double* beta_mat, const double* var_par, int n_eval, double* out);
+
+/* MCNR sufficient sums and Newton step, mcmloptim::mcnr mcmloptim.h:198-236 (serial semantics):
+ * xtwx (P x P) = mean_j X^T W_j X, score (P) = X^T mean_j Wu_j, beta_incr = xtwx^{-1} score, sigma = mean_j sd(resid_j).
+ * Any output pointer may be NULL. */
+int gmb_model_mcnr(gmb_model* mdl, const double* beta, double var_par,
+                   double* xtwx, double* score, double* beta_incr, double* sigma);
+
+/* ---- covariance: replaces glmmr::DData / MCMLDmatrix --------------------------------------------------- */
+/* cov: rows x 5 int32 column-major [block, block dim, function id, n vars, first parameter index]
+ * (src/mcml_optim.cpp:20-22); data, eff_range as produced by Covariance$get_D_data(). */
+int  gmb_cov_create(gmb_ctx* ctx, const int32_t* cov, int rows, const double* data, int n_data,
+                    const double* eff_range, int n_eff, gmb_cov** out);
+void gmb_cov_destroy(gmb_cov* cv);
+int  gmb_cov_dims(gmb_cov* cv, int* B, int* Q, int* R);
+/* DMatrix::genD(0, chol, false): dense block-diagonal Q x Q D(theta) or its lower Cholesky factor
+ * (call sites src/mcml_full.cpp:68,121).  L_out may be NULL to only factorise on the device. */
+int gmb_cov_gen(gmb_cov* cv, const double* theta, int chol, double* L_out);
+/* MCMLDmatrix::loglik(u), mcmldmatrix.h:23-41: (1/m) sum_b sum_j log N(u_j[b]; 0, D_b(theta)); U is Q x m_local host
+ * columns of this rank (m_total over ranks).  All-reduced over ranks. */
+int gmb_cov_mvn_ll(gmb_cov* cv, const double* theta, const double* U, int Q, int m_local, int m_total, double* out);
+/* Same on the device-resident samples of a model (set by gmb_model_set_u / gmb_hmc_sample); ncols_total = how many
+ * leading columns to average (m+1 in mcml_full, mcmldmatrix.h:24,40). */
+int gmb_cov_mvn_ll_model(gmb_cov* cv, const double* theta, gmb_model* mdl, int ncols_total, double* out);
+/* MCMLDmatrix::logdet, mcmldmatrix.h:43-54. */
+int gmb_cov_logdet(gmb_cov* cv, const double* theta, double* out);
+
+/* ---- sampler: replaces glmmr::mcmc::mcmcRunHMC (mhmcmc.h:16-160) and the Stan programs in inst/stan -------- */
+typedef struct gmb_hmc_stats {
+    double accept_rate;      /* mean over chains of accept_/(warmup+nsamp), mhmcmc.h:152 */
+    double step_size_mean;   /* mean final e_ over chains */
+    double steps_mean;       /* mean leapfrog steps per proposal */
+    double leapfrog_total;   /* total leapfrog steps over chains and proposals */
+    double kernel_ms;        /* device time of the sampling kernel(s) */
+    int    n_chains;
+    int    nsamp_per_chain;
+} gmb_hmc_stats;
+
+/* Runs n_chains independent copies of mcmcRunHMC::sample(warmup, .) (mhmcmc.h:121-157), each with its own
+ * step-size adaptation (:107-117), as one batched kernel.  L is the Q x Q lower Cholesky factor of D (host),
+ * xb = X beta is formed from beta.  Each chain yields nsamp_per_chain + 1 whitened states (column 0 = state after
+ * warm-up, :142); U_out (Q x n_chains*(nsamp_per_chain+1), may be NULL) receives L v, chain-major.
+ * V_out (same shape, may be NULL) receives the whitened states v.  RNG: Philox4x32-10 keyed by `seed`
+ * with counter (idx, iteration, chain_offset + chain, stream) — reproducible, unlike mhmcmc.h:55.
+ * keep_on_device != 0 keeps L v on the device as the model's sample matrix (then call gmb_model_use_device_u). */
+int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* beta, double var_par,
+                   int warmup, int nsamp_per_chain, double lambda, int max_steps, double target_accept, int adapt,
+                   int n_chains, uint32_t chain_offset, uint64_t seed, int keep_on_device,
+                   double* U_out, double* V_out, gmb_hmc_stats* stats);
+
+/* mcmlModel::log_prob / log_grad (mcmlmodel.h:138-153, 156-279, usezl = true) for C whitened states V (Q x C):
+ * lp[C], grad (Q x C).  Either output may be NULL.  Used by the parity tests and by mcml_la. */
+int gmb_model_logprob_grad(gmb_model* mdl, const double* L, const double* beta, double var_par,
+                           const double* V, int C, double* lp, double* grad);
+
+/* ---- reference-named entry points (what the Rcpp exports forward to) -----------------------------------
+ * These run on the process-wide default context: created lazily on the current CUDA device, or installed with
+ * gmb_set_default_ctx (e.g. a context that gmb_comm_init joined to an NCCL communicator, so that mcml_full shards its
+ * chains over the ranks).  The library does not take ownership of an installed context. */
+int gmb_set_default_ctx(gmb_ctx* ctx);
+
+/* mvn_ll, src/mcml_optim.cpp:406-414 */
+int gmb_mvn_ll(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
+               const double* gamma, int n_gamma, const double* u, int Q, int m, double* out);
+
+/* mcmc_sample, src/mcml_full.cpp:314-338: returns Q x (nsamp+1) samples (column 0 = state after warm-up).
+ * n_chains <= 0 lets the library choose; n_chains = 1 reproduces the reference's single chain. */
+int gmb_mcmc_sample(const double* Z, const double* L, const double* X, const double* y, const double* beta,
+                    int n, int P, int Q, const char* family, const char* link, int warmup, int nsamp, double lambda,
+                    double var_par, int trace, int refresh, int maxsteps, double target_accept,
+                    int n_chains, uint64_t seed, double* samples_out);
+
+/* mcml_optim, src/mcml_optim.cpp:35-68: one M-step on fixed samples u (Q x m).
+ * start has length >= P + R (+1 for gaussian).  Outputs beta[P], theta[R], sigma. */
+int gmb_mcml_optim(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
+                   const double* Z, const double* X, const double* y, const double* u, int n, int P, int Q, int m,
+                   const char* family, const char* link, const double* start, int n_start, int trace, int mcnr,
+                   double* beta_out, double* theta_out, double* sigma_out);
+
+/* mcml_simlik, src/mcml_optim.cpp:90-117 (joint optimisation of beta, theta; F_likelihood likelihood.h:67-110). */
+int gmb_mcml_simlik(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
+                    const double* Z, const double* X, const double* y, const double* u, int n, int P, int Q, int m,
+                    const char* family, const char* link, const double* start, int n_start, int trace,
+                    double* beta_out, double* theta_out, double* sigma_out);
+
+/* mcml_hess, src/mcml_optim.cpp:263-285: (P+R) x (P+R) finite-difference Hessian of F_likelihood (optimhess stencil). */
+int gmb_mcml_hess(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
+                  const double* Z, const double* X, const double* y, const double* u, int n, int P, int Q, int m,
+                  const char* family, const char* link, const double* start, int n_start, double tol, int trace,
+                  double* hess_out);
+
+/* aic_mcml, src/mcml_optim.cpp:356-392 */
+int gmb_aic_mcml(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
+                 const double* Z, const double* X, const double* y, const double* u, int n, int P, int Q, int m,
+                 const char* family, const char* link, const double* beta_par, int n_beta_par,
+                 const double* cov_par, int n_cov_par, double* out);
+
+/* mcml_full, src/mcml_full.cpp:41-148: the whole MCML loop with the native sampler; samples never leave the device
+ * between the E- and M-step.  u_out is Q x (m+1) (may be NULL).  n_chains <= 0 lets the library choose. */
+int gmb_mcml_full(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
+                  const double* Z, const double* X, const double* y, int n, int P, int Q,
+                  const char* family, const char* link, const double* start, int n_start,
+                  int mcnr, int m, int maxiter, int warmup, double tol, int verbose, double lambda, int trace,
+                  int refresh, int maxsteps, double target_accept, int n_chains, uint64_t seed,
+                  double* beta_out, double* theta_out, double* sigma_out, int* converged_out, int* iter_out,
+                  double* u_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLMMRMCML_B200_H */

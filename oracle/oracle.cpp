@@ -1,0 +1,685 @@
+// oracle.cpp — CPU restatement of the glmmrMCML hot path (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+//
+// This file restates, in plain loops, the arithmetic of the reference's Monte-Carlo E-step and
+// random-effect sampler so that the CUDA path can be checked against it on identical inputs.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load it.  Nothing under glmmrmcml_b200/ links, imports or executes it.
+//
+// PARITY STATUS: "parity unpinned" by the reference's own tests — the reference ships no tests,
+// fixtures or golden vectors, and cannot be compiled as-is here (no R/Rcpp/Eigen/
+// glmmrBase/rminqa).  The restatement is pinned instead by (i) closed-form checks against
+// scipy/mpmath (tests/test_oracle_closed_form.py) and (ii) oracle/_ref, the reference's own
+// headers compiled unmodified against the stand-in headers in oracle/shim/ (see oracle/Makefile
+// and tests/test_oracle_vs_ref.py) wherever that build is present.
+//
+// Every function cites the reference file:line it follows (paths relative to /root/reference).
+// All matrices are column-major double, exactly as R/Eigen hand them over.
+//
+// Two cost modes are provided for the three E-step objectives:
+//   *_faithful : keeps the reference's loop structure INCLUDING its redundant work
+//                (Z*u GEMM per evaluation, Z*u GEMM per sample in mcnr, block Cholesky per sample).
+//                This is "the reference CPU path" that bench.py times.
+//   *_hoisted  : same arithmetic with the redundant work hoisted; the fast checker.
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <cstdio>
+#include <vector>
+#include <algorithm>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+#define ORC_API extern "C" __attribute__((visibility("default")))
+
+// ----------------------------------------------------------------------------------------------
+// family terms — inst/include/glmmrmcml/moremaths.h:16-102
+// ----------------------------------------------------------------------------------------------
+
+// moremaths.h:16-24 (Ramanujan approximation, pi written as 3.141593)
+static inline double log_factorial_approx(double n) {
+    if (n == 0) return 0.0;
+    return n * std::log(n) - n + std::log(n * (1 + 4 * n * (1 + 2 * n))) / 6 + std::log(3.141593) / 2;
+}
+
+// standard normal cdf standing in for R::pnorm (moremaths.h:70-72)
+static inline double pnorm_std(double x) { return 0.5 * std::erfc(-x / std::sqrt(2.0)); }
+
+// moremaths.h:26-102; flink codes from mcmlmodel.h:74-87
+static inline double family_ll(double y, double mu, double var_par, int flink) {
+    double logl = 0.0;  // the reference leaves it uninitialised for y not in {0,1}; we use 0
+    switch (flink) {
+    case 1: logl = y * mu - std::exp(mu) - log_factorial_approx(y); break;            // :33-40
+    case 2: logl = y * std::log(mu) - mu - log_factorial_approx(y); break;            // :41-46
+    case 3:                                                                            // :47-53
+        if (y == 1) logl = std::log(1 / (1 + std::exp(-1.0 * mu)));
+        else if (y == 0) logl = std::log(1 - 1 / (1 + std::exp(-1.0 * mu)));
+        break;
+    case 4:                                                                            // :54-60
+        if (y == 1) logl = mu;
+        else if (y == 0) logl = std::log(1 - std::exp(mu));
+        break;
+    case 5:                                                                            // :61-67
+        if (y == 1) logl = std::log(mu);
+        else if (y == 0) logl = std::log(1 - mu);
+        break;
+    case 6:                                                                            // :68-74
+        if (y == 1) logl = std::log(pnorm_std(mu));
+        else if (y == 0) logl = std::log(1 - pnorm_std(mu));
+        break;
+    case 7:                                                                            // :75-78
+        logl = -1 * std::log(var_par) - 0.5 * std::log(2 * 3.141593) -
+               0.5 * ((y - mu) / var_par) * ((y - mu) / var_par);
+        break;
+    case 8:                                                                            // :79-82 (double log kept)
+        logl = -1 * std::log(var_par) - 0.5 * std::log(2 * 3.141593) -
+               0.5 * ((std::log(y) - mu) / var_par) * ((std::log(y) - mu) / var_par);
+        break;
+    case 9: {                                                                          // :83-88
+        double ymu = var_par * y / std::exp(mu);
+        logl = std::log(1 / (std::tgamma(var_par) * y)) + var_par * std::log(ymu) - ymu;
+        break;
+    }
+    case 10: {                                                                         // :89-94
+        double ymu = var_par * y * mu;
+        logl = std::log(1 / (std::tgamma(var_par) * y)) + var_par * std::log(ymu) - ymu;
+        break;
+    }
+    case 11:                                                                           // :95-97
+        logl = std::log(1 / (std::tgamma(var_par) * y)) + var_par * std::log(var_par * y / mu) - var_par * y / mu;
+        break;
+    case 12:                                                                           // :98-99
+        logl = (mu * var_par - 1) * std::log(y) + ((1 - mu) * var_par - 1) * std::log(1 - y) -
+               std::lgamma(mu * var_par) - std::lgamma((1 - mu) * var_par) + std::lgamma(var_par);
+        break;
+    }
+    return logl;
+}
+
+ORC_API double orc_log_factorial_approx(double n) { return log_factorial_approx(n); }
+ORC_API double orc_family_ll(double y, double mu, double var_par, int flink) { return family_ll(y, mu, var_par, flink); }
+
+// flink from family+link strings — mcmlmodel.h:74-89 (returns 0 where the reference throws)
+ORC_API int orc_flink(const char* family, const char* link) {
+    static const char* keys[12] = {"poissonlog", "poissonidentity", "binomiallogit", "binomiallog",
+                                   "binomialidentity", "binomialprobit", "gaussianidentity", "gaussianlog",
+                                   "gammalog", "gammainverse", "gammaidentity", "betalogit"};
+    char buf[64];
+    std::snprintf(buf, sizeof buf, "%s%s", family, link);
+    for (int i = 0; i < 12; i++) if (std::strcmp(buf, keys[i]) == 0) return i + 1;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------------------------
+// dense helpers (stand in for Eigen products)
+// ----------------------------------------------------------------------------------------------
+
+// C (M x N) = A (M x K) * B (K x N), all column-major; register-blocked over 4 columns of C so the
+// CPU baseline is not handicapped by a naive triple loop.
+static void gemm_nn(int M, int N, int K, const double* A, const double* B, double* C) {
+#pragma omp parallel for schedule(static)
+    for (int j0 = 0; j0 < N; j0 += 4) {
+        int jb = std::min(4, N - j0);
+        for (int jj = 0; jj < jb; jj++) std::memset(C + (size_t)(j0 + jj) * M, 0, sizeof(double) * M);
+        for (int k = 0; k < K; k++) {
+            const double* a = A + (size_t)k * M;
+            double b[4] = {0, 0, 0, 0};
+            for (int jj = 0; jj < jb; jj++) b[jj] = B[(size_t)(j0 + jj) * K + k];
+            if (jb == 4) {
+                if (b[0] == 0 && b[1] == 0 && b[2] == 0 && b[3] == 0) continue;
+                double* c0 = C + (size_t)j0 * M; double* c1 = c0 + M; double* c2 = c1 + M; double* c3 = c2 + M;
+                for (int i = 0; i < M; i++) {
+                    double av = a[i];
+                    c0[i] += av * b[0]; c1[i] += av * b[1]; c2[i] += av * b[2]; c3[i] += av * b[3];
+                }
+            } else {
+                for (int jj = 0; jj < jb; jj++) {
+                    double* c = C + (size_t)(j0 + jj) * M;
+                    for (int i = 0; i < M; i++) c[i] += a[i] * b[jj];
+                }
+            }
+        }
+    }
+}
+
+// y = A (M x K) * x
+static void gemv_n(int M, int K, const double* A, const double* x, double* y) {
+    for (int i = 0; i < M; i++) y[i] = 0;
+    for (int k = 0; k < K; k++) {
+        const double* a = A + (size_t)k * M; double xv = x[k];
+        for (int i = 0; i < M; i++) y[i] += a[i] * xv;
+    }
+}
+
+// y = A^T (K x M from A M x K) * x  (x length M, y length K)
+static void gemv_t(int M, int K, const double* A, const double* x, double* y) {
+    for (int k = 0; k < K; k++) {
+        const double* a = A + (size_t)k * M; double s = 0;
+        for (int i = 0; i < M; i++) s += a[i] * x[i];
+        y[k] = s;
+    }
+}
+
+ORC_API void orc_gemm(int M, int N, int K, const double* A, const double* B, double* C) { gemm_nn(M, N, K, A, B, C); }
+ORC_API void orc_xb(int n, int P, const double* X, const double* beta, double* xb) { gemv_n(n, P, X, beta, xb); }
+
+// ----------------------------------------------------------------------------------------------
+// E-step objective — mcmlmodel.h:284-304 ; likelihood.h:57-64
+// ----------------------------------------------------------------------------------------------
+
+// hoisted: zd = Z*U supplied by the caller.  ll(j) = sum_i l(y_i, xb_i + zd_ij); returns mean_j.
+// ll_per_sample (length m) may be NULL.
+ORC_API double orc_loglik_zd(int n, int m, const double* zd, const double* xb, const double* y,
+                             double var_par, int flink, double* ll_per_sample) {
+    std::vector<double> ll(m, 0.0);
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < m; j++) {
+        const double* z = zd + (size_t)j * n; double s = 0;
+        for (int i = 0; i < n; i++) s += family_ll(y[i], xb[i] + z[i], var_par, flink);   // :296-300
+        ll[j] = s;
+    }
+    double tot = 0; for (int j = 0; j < m; j++) tot += ll[j];
+    if (ll_per_sample) std::memcpy(ll_per_sample, ll.data(), sizeof(double) * m);
+    return tot / m;                                                                       // :303 ll.mean()
+}
+
+// faithful: recomputes zd = Z * U on every evaluation (mcmlmodel.h:286), then as above.
+// niter = number of columns used (mcmlmodel.h:73 niter_; may be < cols of U).
+ORC_API double orc_loglik_faithful(int n, int P, int Q, int niter, const double* X, const double* Z, const double* U,
+                                   const double* y, const double* beta, double var_par, int flink) {
+    std::vector<double> xb(n), zd((size_t)n * niter);
+    gemv_n(n, P, X, beta, xb.data());                 // update_beta, mcmlmodel.h:100-102
+    gemm_nn(n, niter, Q, Z, U, zd.data());            // :286
+    return orc_loglik_zd(n, niter, zd.data(), xb.data(), y, var_par, flink, nullptr);
+}
+
+// ----------------------------------------------------------------------------------------------
+// MCNR — mcmloptim.h:198-236, mcmlmodel.h:120-134, moremaths.h:118-161, glmmrBase dhdmu/mod_inv_func
+// (glmmrBase pieces reconstructed)
+// ----------------------------------------------------------------------------------------------
+
+// family index: 0 poisson, 1 binomial, 2 gaussian ; link index: 0 log, 1 identity, 2 logit
+static inline void flink_to_family_link(int flink, int* fam, int* lnk) {
+    switch (flink) {
+    case 1: *fam = 0; *lnk = 0; break;
+    case 2: *fam = 0; *lnk = 1; break;
+    case 3: *fam = 1; *lnk = 2; break;
+    case 4: *fam = 1; *lnk = 0; break;
+    case 5: *fam = 1; *lnk = 1; break;
+    case 7: *fam = 2; *lnk = 1; break;
+    case 8: *fam = 2; *lnk = 0; break;
+    default: *fam = -1; *lnk = -1;
+    }
+}
+
+// glmmrBase maths::mod_inv_func (App. C.3): inverse link
+static inline double inv_link(double eta, int lnk) {
+    switch (lnk) {
+    case 0: return std::exp(eta);
+    case 1: return eta;
+    case 2: return std::exp(eta) / (1 + std::exp(eta));
+    }
+    return eta;
+}
+
+// glmmrBase maths::dhdmu (App. C.3): reciprocal IRLS weight (without the dispersion)
+static inline double dhdmu(double eta, int fam, int lnk) {
+    if (fam == 0 && lnk == 0) return std::exp(-eta);
+    if (fam == 0 && lnk == 1) return eta;                                  // var(mu)=mu, deta/dmu=1
+    if (fam == 1 && lnk == 2) { double p = inv_link(eta, 2); return 1 / (p * (1 - p)); }
+    if (fam == 1 && lnk == 0) { double p = std::exp(eta); return (1 - p) / p; }
+    if (fam == 1 && lnk == 1) { return eta * (1 - eta); }
+    return 1.0;                                                            // gaussian
+}
+
+// moremaths.h:118-161 detadmu
+static inline double detadmu(double eta, int lnk) {
+    switch (lnk) {
+    case 0: return std::exp(-1.0 * eta);                                    // :132-134
+    case 1: return 1.0;                                                     // :135-139
+    case 2: { double p = inv_link(eta, 2); return 1 / (p * (1.0 - p)); }    // :140-145
+    }
+    return 1.0;
+}
+
+// One MCNR step with serial semantics.  Outputs:
+//   xtwx (P x P) = mean_j X^T W_j X ; score (P) = X^T mean_j Wu_j ; beta_incr (P) = xtwx^{-1} score ;
+//   sigma = mean_j sd(resid_j).  Returns 0, or 1 when xtwx is singular.
+// `faithful` != 0 recomputes Z*U for every sample as update_W(i) does (mcmlmodel.h:121).
+static int solve_spd_or_lu(int P, std::vector<double> A, std::vector<double> b, double* x) {
+    // Gaussian elimination with partial pivoting (stands in for Eigen .inverse(), mcmloptim.h:230)
+    for (int c = 0; c < P; c++) {
+        int piv = c; double best = std::fabs(A[c + (size_t)c * P]);
+        for (int r = c + 1; r < P; r++) if (std::fabs(A[r + (size_t)c * P]) > best) { best = std::fabs(A[r + (size_t)c * P]); piv = r; }
+        if (best == 0) return 1;
+        if (piv != c) { for (int k = 0; k < P; k++) std::swap(A[c + (size_t)k * P], A[piv + (size_t)k * P]); std::swap(b[c], b[piv]); }
+        for (int r = c + 1; r < P; r++) {
+            double f = A[r + (size_t)c * P] / A[c + (size_t)c * P];
+            for (int k = c; k < P; k++) A[r + (size_t)k * P] -= f * A[c + (size_t)k * P];
+            b[r] -= f * b[c];
+        }
+    }
+    for (int r = P - 1; r >= 0; r--) {
+        double s = b[r];
+        for (int k = r + 1; k < P; k++) s -= A[r + (size_t)k * P] * x[k];
+        x[r] = s / A[r + (size_t)r * P];
+    }
+    return 0;
+}
+
+ORC_API int orc_solve(int P, const double* A, const double* b, double* x) {
+    return solve_spd_or_lu(P, std::vector<double>(A, A + (size_t)P * P), std::vector<double>(b, b + P), x);
+}
+
+ORC_API int orc_mcnr(int n, int P, int Q, int niter, const double* X, const double* Z, const double* U,
+                     const double* y, const double* beta, double var_par, int flink, int faithful,
+                     double* xtwx, double* score, double* beta_incr, double* sigma) {
+    int fam, lnk; flink_to_family_link(flink, &fam, &lnk);
+    if (fam < 0) return 2;
+    std::vector<double> xb(n), zd((size_t)n * niter);
+    gemv_n(n, P, X, beta, xb.data());
+    gemm_nn(n, niter, Q, Z, U, zd.data());                                  // mcmloptim.h:207 get_zu()
+    double nvar_par = 1.0;                                                  // mcmlmodel.h:123-130
+    if (fam == 2) nvar_par *= var_par * var_par;
+    std::vector<double> XtWX((size_t)P * P, 0.0), Wum(n, 0.0), sigmas(niter, 0.0);
+    std::vector<double> zd2;
+    if (faithful) zd2.resize((size_t)n * niter);
+    std::vector<double> W(n), resid(n), XtWXj((size_t)P * P);
+    for (int j = 0; j < niter; j++) {                                       // :211 (serial semantics)
+        const double* z = zd.data() + (size_t)j * n;
+        if (faithful) { gemm_nn(n, niter, Q, Z, U, zd2.data()); z = zd2.data() + (size_t)j * n; }   // update_W(i): mcmlmodel.h:121
+        for (int i = 0; i < n; i++) W[i] = 1 / (dhdmu(xb[i] + z[i], fam, lnk) * nvar_par);           // mcmlmodel.h:122,131-133
+        double mean = 0;
+        for (int i = 0; i < n; i++) { resid[i] = y[i] - inv_link(xb[i] + z[i], lnk); mean += resid[i]; }   // :214-215
+        mean /= n;
+        double ss = 0; for (int i = 0; i < n; i++) ss += (resid[i] - mean) * (resid[i] - mean);
+        sigmas[j] = std::sqrt(ss / (n - 1));                                // :216
+        std::fill(XtWXj.begin(), XtWXj.end(), 0.0);                         // :217 X^T W X
+        for (int a = 0; a < P; a++)
+            for (int b = 0; b < P; b++) {
+                double s = 0;
+                for (int i = 0; i < n; i++) s += X[i + (size_t)a * n] * W[i] * X[i + (size_t)b * n];
+                XtWXj[a + (size_t)b * P] = s;
+            }
+        for (size_t k = 0; k < XtWXj.size(); k++) XtWX[k] += XtWXj[k] * (1.0 / niter);   // :227-229
+        for (int i = 0; i < n; i++) Wum[i] += W[i] * detadmu(xb[i] + z[i], lnk) * resid[i];   // :218-223
+    }
+    for (int i = 0; i < n; i++) Wum[i] /= niter;                            // :231 rowwise().mean()
+    std::vector<double> sc(P);
+    gemv_t(n, P, X, Wum.data(), sc.data());                                 // :232 X^T Wum
+    double sg = 0; for (int j = 0; j < niter; j++) sg += sigmas[j];
+    *sigma = sg / niter;                                                    // :235
+    std::memcpy(xtwx, XtWX.data(), sizeof(double) * P * P);
+    std::memcpy(score, sc.data(), sizeof(double) * P);
+    return solve_spd_or_lu(P, XtWX, sc, beta_incr);                         // :230,232
+}
+
+// ----------------------------------------------------------------------------------------------
+// Covariance D(theta) — glmmrBase DData/DMatrix/DSubMatrix as reconstructed in SURVEY App. C
+// (call sites: mcmldmatrix.h:19-21,26-30,46,59,61 ; src/mcml_full.cpp:62,68,121)
+// ----------------------------------------------------------------------------------------------
+
+struct CovSpec {
+    int B = 0, Q = 0, R = 0;
+    struct Fn { int id, nvar, par0, col0; double eff; };
+    struct Block { int n, start; size_t data0; int ncol; std::vector<Fn> fns; bool all_gr; };
+    std::vector<Block> blocks;
+    std::vector<double> data;
+};
+
+static int fn_npar(int id) {       // R/R6ModelExtMCML.R:430 fnpar
+    static const int np[15] = {0, 1, 1, 1, 2, 2, 1, 2, 2, 2, 2, 2, 2, 2, 1};
+    return (id >= 1 && id <= 14) ? np[id] : 0;
+}
+
+// cov: rows x 5 int32 column-major [block id, block dim, function id, n vars, first parameter index]
+static int parse_cov(const int32_t* cov, int rows, const double* data, int n_data, const double* eff, CovSpec& cs) {
+    cs = CovSpec();
+    int maxb = -1;
+    for (int r = 0; r < rows; r++) maxb = std::max(maxb, (int)cov[r]);
+    cs.B = maxb + 1;
+    cs.blocks.resize(cs.B);
+    for (auto& b : cs.blocks) { b.n = 0; b.ncol = 0; b.all_gr = true; }
+    for (int r = 0; r < rows; r++) {
+        int b = cov[r], nb = cov[r + rows], id = cov[r + 2 * rows], nv = cov[r + 3 * rows], p0 = cov[r + 4 * rows];
+        if (b < 0 || nb <= 0 || fn_npar(id) == 0) return 1;
+        CovSpec::Block& blk = cs.blocks[b];
+        blk.n = nb;
+        blk.fns.push_back({id, nv, p0, blk.ncol, eff ? eff[r] : 0.0});
+        blk.ncol += nv;
+        if (id != 1) blk.all_gr = false;
+        cs.R = std::max(cs.R, p0 + fn_npar(id));
+    }
+    size_t off = 0; int start = 0;
+    for (auto& b : cs.blocks) {
+        if (b.n == 0) return 1;
+        b.data0 = off; b.start = start;
+        off += (size_t)b.n * b.ncol; start += b.n;
+    }
+    if ((size_t)n_data < off) return 1;
+    cs.Q = start;
+    cs.data.assign(data, data + off);
+    return 0;
+}
+
+// kernel functions
+static inline double cov_fn(int id, double d, const double* th) {
+    switch (id) {
+    case 1:  return d == 0 ? th[0] * th[0] : 0.0;            // gr
+    case 2:  return std::exp(-d / th[0]);                     // fexp0
+    case 3:  return std::pow(th[0], d);                       // ar1
+    case 4:  return th[0] * std::exp(-d * d / (th[1] * th[1]));   // sqexp
+    case 13: return th[0] * std::exp(-d / th[1]);             // fexp
+    case 14: return std::exp(-d * d / (th[0] * th[0]));       // sqexp0
+    }
+    return NAN;
+}
+
+// DSubMatrix::get_val(i,j)
+static inline double block_val(const CovSpec& cs, const CovSpec::Block& b, const double* theta, int i, int j) {
+    double v = 1.0;
+    const double* dat = cs.data.data() + b.data0;
+    for (const auto& f : b.fns) {
+        double d2 = 0;
+        for (int k = 0; k < f.nvar; k++) {
+            double di = dat[i + (size_t)(f.col0 + k) * b.n] - dat[j + (size_t)(f.col0 + k) * b.n];
+            d2 += di * di;
+        }
+        v *= cov_fn(f.id, std::sqrt(d2), theta + f.par0);
+    }
+    return v;
+}
+
+// gen_block_mat(b, chol, upper=false): dense block (col-major n_b x n_b), or its lower Cholesky factor by
+// Cholesky–Banachiewicz evaluated from get_val on the fly (App. C.3).  Returns 0 or 1+index of a non-PD pivot.
+static int gen_block(const CovSpec& cs, int bi, const double* theta, bool chol, double* out) {
+    const CovSpec::Block& b = cs.blocks[bi];
+    int n = b.n;
+    if (!chol) {
+        for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) out[i + (size_t)j * n] = block_val(cs, b, theta, i, j);
+        return 0;
+    }
+    std::fill(out, out + (size_t)n * n, 0.0);
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j <= i; j++) {
+            double s = 0;
+            for (int k = 0; k < j; k++) s += out[i + (size_t)k * n] * out[j + (size_t)k * n];
+            double a = block_val(cs, b, theta, i, j);
+            if (i == j) {
+                double d = a - s;
+                if (!(d > 0)) return 1 + i;
+                out[i + (size_t)i * n] = std::sqrt(d);
+            } else {
+                out[i + (size_t)j * n] = (a - s) / out[j + (size_t)j * n];
+            }
+        }
+    }
+    return 0;
+}
+
+ORC_API int orc_cov_dims(const int32_t* cov, int rows, const double* data, int n_data, int* B, int* Q, int* R) {
+    CovSpec cs; int rc = parse_cov(cov, rows, data, n_data, nullptr, cs);
+    if (rc) return rc;
+    *B = cs.B; *Q = cs.Q; *R = cs.R; return 0;
+}
+
+// genD(0, chol, false): block-diagonal Q x Q (col-major) D or its lower Cholesky factor
+ORC_API int orc_genD(const int32_t* cov, int rows, const double* data, int n_data, const double* eff,
+                     const double* theta, int chol, double* out) {
+    CovSpec cs; int rc = parse_cov(cov, rows, data, n_data, eff, cs);
+    if (rc) return -1;
+    int Q = cs.Q;
+    std::fill(out, out + (size_t)Q * Q, 0.0);
+    for (int bi = 0; bi < cs.B; bi++) {
+        const auto& b = cs.blocks[bi];
+        std::vector<double> blk((size_t)b.n * b.n);
+        rc = gen_block(cs, bi, theta, chol != 0, blk.data());
+        if (rc) return b.start + rc;
+        for (int j = 0; j < b.n; j++) for (int i = 0; i < b.n; i++) out[(b.start + i) + (size_t)(b.start + j) * Q] = blk[i + (size_t)j * b.n];
+    }
+    return 0;
+}
+
+// moremaths.h:166-179 forward_sub
+static inline void forward_sub(const double* L, const double* u, int n, double* yv) {
+    for (int i = 0; i < n; i++) {
+        double lsum = 0;
+        for (int j = 0; j < i; j++) lsum += L[i + (size_t)j * n] * yv[j];
+        yv[i] = (u[i] - lsum) / L[i + (size_t)i * n];
+    }
+}
+
+// mcmldmatrix.h:57-78 loglik_block given the block's Cholesky factor dmat
+static inline double loglik_block(const double* dmat, int n, bool all_gr, const double* u, double* scratch) {
+    double logl = 0;
+    if (all_gr) {                                                            // :61-65
+        for (int k = 0; k < n; k++) {
+            double d = dmat[k + (size_t)k * n];
+            logl += -0.5 * std::log(d * d) - 0.5 * std::log(2 * M_PI) - 0.5 * u[k] * u[k] / (d * d);
+        }
+    } else {                                                                 // :67-75
+        double logdetD = 0;
+        for (int i = 0; i < n; i++) logdetD += 2 * std::log(dmat[i + (size_t)i * n]);
+        forward_sub(dmat, u, n, scratch);
+        double quadform = 0;
+        for (int i = 0; i < n; i++) quadform += scratch[i] * scratch[i];
+        logl = (-0.5 * n * std::log(2 * M_PI) - 0.5 * logdetD - 0.5 * quadform);
+    }
+    return logl;
+}
+
+// MCMLDmatrix::loglik(u) — mcmldmatrix.h:23-41.  U is Q x m col-major; ALL m columns are averaged (:24,:40).
+// faithful != 0 re-factorises the block for every sample (:33-36 -> :59).  Returns NaN on a non-PD block.
+ORC_API double orc_mvn_loglik(const int32_t* cov, int rows, const double* data, int n_data, const double* eff,
+                              const double* theta, const double* U, int Q, int m, int faithful) {
+    CovSpec cs; if (parse_cov(cov, rows, data, n_data, eff, cs) || cs.Q != Q) return NAN;
+    double loglV = 0; bool bad = false;
+    for (int bi = 0; bi < cs.B; bi++) {
+        const auto& b = cs.blocks[bi];
+        int n = b.n;
+        std::vector<double> dm((size_t)n * n);
+        if (!faithful && gen_block(cs, bi, theta, true, dm.data())) return NAN;
+        std::vector<double> loglB(m, 0.0);
+#pragma omp parallel
+        {
+            std::vector<double> scratch(n), dml;
+            if (faithful) dml.resize((size_t)n * n);
+#pragma omp for schedule(static)
+            for (int j = 0; j < m; j++) {
+                const double* dmat = dm.data();
+                if (faithful) { if (gen_block(cs, bi, theta, true, dml.data())) { bad = true; continue; } dmat = dml.data(); }
+                loglB[j] = loglik_block(dmat, n, b.all_gr, U + (size_t)j * Q + b.start, scratch.data());
+            }
+        }
+        double s = 0; for (int j = 0; j < m; j++) s += loglB[j];              // :38 loglB.sum()
+        loglV += s;
+    }
+    if (bad) return NAN;
+    return loglV / m;                                                        // :40
+}
+
+// MCMLDmatrix::logdet — mcmldmatrix.h:43-54
+ORC_API double orc_logdet(const int32_t* cov, int rows, const double* data, int n_data, const double* eff, const double* theta) {
+    CovSpec cs; if (parse_cov(cov, rows, data, n_data, eff, cs)) return NAN;
+    double ld = 0;
+    for (int bi = 0; bi < cs.B; bi++) {
+        int n = cs.blocks[bi].n;
+        std::vector<double> dm((size_t)n * n);
+        if (gen_block(cs, bi, theta, true, dm.data())) return NAN;
+        for (int i = 0; i < n; i++) ld += 2 * std::log(dm[i + (size_t)i * n]);
+    }
+    return ld;
+}
+
+// ----------------------------------------------------------------------------------------------
+// HMC target — mcmlmodel.h:138-153 (log_prob), :156-279 (log_grad, usezl = true)
+// ----------------------------------------------------------------------------------------------
+
+ORC_API double orc_log_prob(int n, int Q, const double* ZL, const double* xb, const double* y,
+                            double var_par, int flink, const double* v) {
+    std::vector<double> mu(n);
+    gemv_n(n, Q, ZL, v, mu.data());
+    double ll = 0, lp = 0;
+    for (int i = 0; i < n; i++) ll += family_ll(y[i], xb[i] + mu[i], var_par, flink);   // :144-146
+    for (int q = 0; q < Q; q++) lp += family_ll(v[q], 0, 1, 7);                          // :148-150
+    return ll + lp;                                                                      // :151
+}
+
+static void log_grad(int n, int Q, const double* ZL, const double* xb, const double* y,
+                     double var_par, int flink, const double* v, double* grad, double* mu /* scratch n */) {
+    gemv_n(n, Q, ZL, v, mu);
+    for (int i = 0; i < n; i++) mu[i] += xb[i];                                          // :160-162
+    switch (flink) {
+    case 1: for (int i = 0; i < n; i++) mu[i] = y[i] - std::exp(mu[i]); break;           // :170-175
+    case 2: for (int i = 0; i < n; i++) mu[i] = y[i] * (1 / mu[i]) - 1; break;           // :176-183
+    case 3: for (int i = 0; i < n; i++) mu[i] = 1 / (std::exp(mu[i]) + 1) + y[i] - 1; break;   // :184-193
+    case 4: for (int i = 0; i < n; i++) { if (y[i] == 1) mu[i] = 1; else if (y[i] == 0) mu[i] = std::exp(mu[i]) / (1 - std::exp(mu[i])); } break;   // :194-206
+    case 5: for (int i = 0; i < n; i++) { if (y[i] == 1) mu[i] = 1 / mu[i]; else if (y[i] == 0) mu[i] = -1 / (1 - mu[i]); } break;                    // :207-219
+    case 7: case 8: for (int i = 0; i < n; i++) mu[i] = (y[i] - mu[i]); break;           // :233-244 (scaled below)
+    default: for (int i = 0; i < n; i++) mu[i] = NAN;
+    }
+    gemv_t(n, Q, ZL, mu, grad);
+    double sc = (flink == 7 || flink == 8) ? 1.0 / (var_par * var_par) : 1.0;
+    for (int q = 0; q < Q; q++) grad[q] = -1.0 * v[q] + sc * grad[q];                    // :163, :173
+}
+
+ORC_API void orc_log_grad(int n, int Q, const double* ZL, const double* xb, const double* y,
+                          double var_par, int flink, const double* v, double* grad) {
+    std::vector<double> mu(n);
+    log_grad(n, Q, ZL, xb, y, var_par, flink, v, grad, mu.data());
+}
+
+// ----------------------------------------------------------------------------------------------
+// Counter-based RNG shared (by definition) with the CUDA sampler: Philox4x32-10.
+// The reference draws from R's RNG / std::minstd_rand seeded by std::random_device (mhmcmc.h:48-55,62),
+// i.e. it is not reproducible; the boundary (SURVEY §8b "RNG") replaces that by this stream.
+//   counter = (idx, iteration, chain, stream), key = (seed_lo, seed_hi)
+//   stream 0: initial state v (Box-Muller pairs, idx = q/2) ; stream 2: momentum ; stream 3: accept uniform
+// ----------------------------------------------------------------------------------------------
+
+static inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+static inline double u01(uint32_t lo, uint32_t hi) {
+    uint64_t x = ((uint64_t)hi << 32) | lo;
+    return ((double)(x >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+static inline void rng_uniform2(uint64_t seed, uint32_t idx, uint32_t iter, uint32_t chain, uint32_t stream, double* u1, double* u2) {
+    uint32_t c[4] = {idx, iter, chain, stream};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    *u1 = u01(c[0], c[1]); *u2 = u01(c[2], c[3]);
+}
+
+static inline void rng_normal_vec(uint64_t seed, uint32_t iter, uint32_t chain, uint32_t stream, int Q, double* z) {
+    for (int p = 0; p < (Q + 1) / 2; p++) {
+        double u1, u2; rng_uniform2(seed, (uint32_t)p, iter, chain, stream, &u1, &u2);
+        double r = std::sqrt(-2.0 * std::log(u1));
+        double a = 2.0 * M_PI * u2;
+        z[2 * p] = r * std::cos(a);
+        if (2 * p + 1 < Q) z[2 * p + 1] = r * std::sin(a);
+    }
+}
+
+ORC_API void orc_rng_normal_vec(uint64_t seed, uint32_t iter, uint32_t chain, uint32_t stream, int Q, double* z) { rng_normal_vec(seed, iter, chain, stream, Q, z); }
+ORC_API double orc_rng_uniform(uint64_t seed, uint32_t iter, uint32_t chain, uint32_t stream) { double a, b; rng_uniform2(seed, 0, iter, chain, stream, &a, &b); return a; }
+
+// ----------------------------------------------------------------------------------------------
+// HMC chain — mhmcmc.h:47-59 (initialise_u), :61-119 (new_proposal), :121-157 (sample)
+// ----------------------------------------------------------------------------------------------
+
+// One chain.  out_v: Q x (nsamp+1) whitened states (column 0 = state after warmup, mhmcmc.h:142) ;
+// out_u (may be NULL): L * out_v (mhmcmc.h:155), L is Q x Q col-major.
+// stats[0]=accept rate, [1]=final step size e, [2]=ebar, [3]=steps of the last proposal, [4]=total leapfrog steps.
+// trace_prob (may be NULL): warmup+nsamp acceptance probabilities.
+ORC_API void orc_hmc_chain(int n, int Q, const double* ZL, const double* L, const double* xb, const double* y,
+                           double var_par, int flink, int warmup, int nsamp, double lambda, int max_steps,
+                           double target_accept, int adapt, uint64_t seed, uint32_t chain,
+                           double* out_v, double* out_u, double* stats, double* trace_prob) {
+    std::vector<double> u(Q), up(Q), r(Q), grad(Q), mu(n);
+    // initialise_u (:47-59)
+    rng_normal_vec(seed, 0, chain, 0, Q, u.data());
+    int accept = 0; double H = 0, e = 0.001, ebar = 1.0; int steps = 0; double total_steps = 0;
+    int total = warmup + nsamp;
+    for (int t = 0; t < total; t++) {
+        bool do_adapt = (t < warmup) && (t < adapt);                         // :131-136
+        int iter = t + 1;
+        // new_proposal (:61-119)
+        rng_normal_vec(seed, (uint32_t)t, chain, 2, Q, r.data());            // :62-63
+        log_grad(n, Q, ZL, xb, y, var_par, flink, u.data(), grad.data(), mu.data());   // :64
+        double lpr = 0; for (int q = 0; q < Q; q++) lpr += r[q] * r[q]; lpr *= 0.5;     // :66
+        up = u;                                                              // :67
+        steps = std::max(1, (int)std::round(lambda / e));                    // :69
+        steps = std::min(steps, max_steps);                                  // :70
+        for (int s = 0; s < steps; s++) {                                    // :73-78
+            for (int q = 0; q < Q; q++) r[q] += (e / 2) * grad[q];
+            for (int q = 0; q < Q; q++) up[q] += e * r[q];
+            log_grad(n, Q, ZL, xb, y, var_par, flink, up.data(), grad.data(), mu.data());
+            for (int q = 0; q < Q; q++) r[q] += (e / 2) * grad[q];
+        }
+        total_steps += steps;
+        double lprt = 0; for (int q = 0; q < Q; q++) lprt += r[q] * r[q]; lprt *= 0.5;  // :80
+        double l1 = orc_log_prob(n, Q, ZL, xb, y, var_par, flink, u.data());            // :82
+        double l2 = orc_log_prob(n, Q, ZL, xb, y, var_par, flink, up.data());           // :83
+        double prob = std::min(1.0, std::exp(-l1 + lpr + l2 - lprt));                   // :84
+        double runif = orc_rng_uniform(seed, (uint32_t)t, chain, 3);                    // :85
+        bool acc = runif < prob;                                                        // :86
+        if (trace_prob) trace_prob[t] = prob;
+        if (acc) { u = up; accept++; }                                                  // :102-105
+        if (do_adapt) {                                                                 // :107-114
+            double f1 = 1.0 / (iter + 10);
+            H = (1 - f1) * H + f1 * (target_accept - prob);
+            double loge = -4.60517 - (std::sqrt((double)iter / 0.05)) * H;
+            double powm = std::pow((double)iter, -0.75);
+            double logbare = powm * loge + (1 - powm) * std::log(ebar);
+            e = std::exp(loge);
+            ebar = std::exp(logbare);
+        } else {
+            e = ebar;                                                                   // :115-117
+        }
+        if (t == warmup - 1 || (warmup == 0 && t == 0 && false)) {}
+        if (t >= warmup) std::memcpy(out_v + (size_t)(t - warmup + 1) * Q, u.data(), sizeof(double) * Q);   // :147
+        if (t == warmup - 1) std::memcpy(out_v, u.data(), sizeof(double) * Q);                               // :142
+    }
+    if (warmup == 0) {
+        // samples.col(0) = u_ before any proposal (:142 with an empty warm-up loop)
+        std::vector<double> u0(Q); rng_normal_vec(seed, 0, chain, 0, Q, u0.data());
+        std::memcpy(out_v, u0.data(), sizeof(double) * Q);
+    }
+    if (out_u) gemm_nn(Q, nsamp + 1, Q, L, out_v, out_u);                               // :155
+    if (stats) { stats[0] = (double)accept / total; stats[1] = e; stats[2] = ebar; stats[3] = steps; stats[4] = total_steps; }
+}
+
+// ----------------------------------------------------------------------------------------------
+// thread control for the timed CPU baseline
+// ----------------------------------------------------------------------------------------------
+ORC_API int orc_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+ORC_API void orc_set_threads(int t) {
+#ifdef _OPENMP
+    omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}

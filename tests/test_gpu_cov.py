@@ -1,0 +1,95 @@
+"""GPU parity of the covariance path (K4 D(theta) build + Cholesky, K5 mvn_ll) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from glmmrmcml_b200 import synth
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def mixed_blocks(rng):
+    """blocks of many sizes and kernels in one specification: gr 1x1, gr*ar1 5x5, fexp 12x12 / 40x40 / 150x150, sqexp 7x7"""
+    cov, data = [], []
+    b = 0
+    for _ in range(5):
+        cov.append([b, 1, 1, 1, 0]); data += [float(b + 1)]; b += 1
+    for c in range(4):
+        cov.append([b, 5, 1, 1, 0]); cov.append([b, 5, 3, 1, 1]); data += [c + 1.0] * 5 + [1.0, 2.0, 3.0, 4.0, 5.0]; b += 1
+    for nb in (12, 40, 150):
+        xy = rng.random((nb, 2))
+        cov.append([b, nb, 13, 2, 2]); data += list(xy[:, 0]) + list(xy[:, 1]); b += 1
+    x = rng.random(7)
+    cov.append([b, 7, 4, 1, 4]); data += list(x); b += 1
+    theta = np.array([0.3, 0.7, 0.25, 0.15, 0.5, 0.4])
+    return np.array(cov, dtype=np.int32), np.array(data), theta
+
+
+CASES = {
+    "C1": lambda: synth.config1(m=250),
+    "C2": lambda: synth.config2(m=1000),
+    "C3": lambda: synth.config3(nloc=250, m=250),
+    "C4": lambda: synth.config4(ncl=100, nt=10, k=1, m=300),
+    "C5": lambda: synth.config5(nloc=700, nobs=2, m=200),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_chol_and_mvn_ll(name, gctx, oracle):
+    import glmmrmcml_b200 as g
+    cfg = CASES[name]()
+    cv = g.Covariance(gctx, cfg["cov"], cfg["data"], cfg["eff_range"])
+    assert (cv.B, cv.Q, cv.R) == oracle.cov_dims(cfg["cov"], cfg["data"])
+    for scale in (1.0, 1.3):
+        theta = cfg["theta"] * np.array([scale, 1.0 / scale if name in ("C3", "C5") else min(0.95, scale * cfg["theta"][1]) / cfg["theta"][1]])[: cfg["theta"].size]
+        Lw = oracle.genD(cfg["cov"], cfg["data"], cfg["eff_range"], theta, chol=True)
+        Lg = cv.genD(theta, chol=True)
+        assert np.max(np.abs(Lg - Lw)) <= 1e-11 * np.max(np.abs(Lw)) * max(1.0, np.linalg.cond(Lw))
+        Dw = oracle.genD(cfg["cov"], cfg["data"], cfg["eff_range"], theta, chol=False)
+        Dg = cv.genD(theta, chol=False)
+        assert np.max(np.abs(Dg - Dw)) <= 1e-14 * np.max(np.abs(Dw))
+        want = oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], theta, cfg["U"])
+        got = cv.loglik(theta, cfg["U"])
+        kappa = np.linalg.cond(Lw) ** 2
+        assert abs(got - want) <= max(RTOL, 1e-15 * kappa) * abs(want), (got, want, kappa)
+        assert abs(cv.logdet(theta) - oracle.logdet(cfg["cov"], cfg["data"], cfg["eff_range"], theta)) <= 1e-10 * max(1.0, abs(want))
+    cv.close()
+
+
+def test_mixed_blocks(gctx, oracle):
+    import glmmrmcml_b200 as g
+    rng = np.random.default_rng(5)
+    cov, data, theta = mixed_blocks(rng)
+    eff = np.zeros(cov.shape[0])
+    cv = g.Covariance(gctx, cov, data, eff)
+    L = oracle.genD(cov, data, eff, theta, chol=True)
+    U = np.asfortranarray(L @ rng.standard_normal((L.shape[0], 333)))
+    assert np.max(np.abs(cv.genD(theta) - L)) <= 1e-10 * np.max(np.abs(L))
+    want = oracle.mvn_loglik(cov, data, eff, theta, U)
+    got = cv.loglik(theta, U)
+    assert abs(got - want) <= 1e-9 * abs(want), (got, want)
+    # the stateless reference-named entry point gives the same number
+    assert g.mvn_ll(cov, data, eff, theta, U) == got
+    cv.close()
+
+
+def test_vector_u_and_single_column(gctx, oracle):
+    """mvn_ll accepts a vector u (man/mvn_ll.Rd:19 'Matrix (or vector)')."""
+    import glmmrmcml_b200 as g
+    cfg = synth.config2(m=1)
+    want = oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], cfg["theta"], cfg["U"])
+    got = g.mvn_ll(cfg["cov"], cfg["data"], cfg["eff_range"], cfg["theta"], cfg["U"][:, 0])
+    assert abs(got - want) <= RTOL * abs(want)
+
+
+def test_not_positive_definite(gctx):
+    import glmmrmcml_b200 as g
+    cfg = synth.config2(m=4)
+    cv = g.Covariance(gctx, cfg["cov"], cfg["data"], cfg["eff_range"])
+    with pytest.raises(g.GmbError) as e:
+        cv.loglik(np.array([0.25, 1.5]), cfg["U"])        # ar1 with rho > 1 is not positive definite
+    assert e.value.code == 4
+    with pytest.raises(g.GmbError) as e:
+        g.Covariance(gctx, np.array([[0, 3, 5, 1, 0]], dtype=np.int32), np.zeros(3), None)   # matern: not supported
+    assert e.value.code == 7
+    cv.close()

@@ -1,0 +1,104 @@
+"""GPU parity of the E-step kernels (K1 zd = Z u, K2 log-likelihood, K3 MCNR sums) against the CPU oracle.
+
+Tolerance: 1e-10 relative in fp64 (BASELINE.json north_star).  All calls go through the C-ABI (ctypes).
+"""
+import numpy as np
+import pytest
+
+from glmmrmcml_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+CASES = {
+    "C1": lambda: synth.config1(m=250),
+    "C2": lambda: synth.config2(m=2000),
+    "C3": lambda: synth.config3(nloc=250, m=250),
+    "C4": lambda: synth.config4(ncl=100, nt=10, k=1, m=512),
+    "C5": lambda: synth.config5(nloc=300, nobs=10, m=600),
+    "ragged": lambda: synth.config4(ncl=37, nt=7, k=3, m=131),      # n = 777, odd sizes everywhere
+}
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request, gctx):
+    import glmmrmcml_b200 as g
+    cfg = CASES[request.param]()
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    mdl.set_u(cfg["U"])
+    yield cfg, mdl
+    mdl.close()
+
+
+def test_loglik_matches_oracle(case, oracle):
+    cfg, mdl = case
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    rng = np.random.default_rng(7)
+    for trial in range(3):
+        beta = cfg["beta"] + 0.1 * trial * rng.standard_normal(cfg["P"])
+        sigma = 1.0 + 0.3 * trial
+        want = oracle.loglik_faithful(cfg["X"], cfg["Z"], cfg["U"], cfg["y"], beta, sigma, fl)
+        got = mdl.log_likelihood(beta, sigma)
+        assert abs(got - want) <= RTOL * abs(want), (got, want)
+
+
+def test_loglik_batch_equals_single(case):
+    cfg, mdl = case
+    rng = np.random.default_rng(11)
+    betas = cfg["beta"][:, None] + 0.05 * rng.standard_normal((cfg["P"], 9))
+    sig = 1.0 + 0.1 * np.arange(9)
+    b = mdl.log_likelihood_batch(betas, sig)
+    s = np.array([mdl.log_likelihood(betas[:, k], sig[k]) for k in range(9)])
+    assert np.array_equal(b, s)          # same kernel, deterministic reduction -> bitwise equal
+
+
+def test_loglik_is_deterministic(case):
+    cfg, mdl = case
+    a = mdl.log_likelihood(cfg["beta"], 1.0)
+    for _ in range(3):
+        assert mdl.log_likelihood(cfg["beta"], 1.0) == a
+
+
+def test_niter_quirk(case, oracle):
+    """niter_ < cols(u): the E-step averages the leading niter columns only (mcmlmodel.h:73,295)."""
+    cfg, mdl = case
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    m = cfg["U"].shape[1]
+    mdl.set_u(cfg["U"], m_total=m, niter_total=m - 1)
+    want = oracle.loglik_faithful(cfg["X"], cfg["Z"], cfg["U"], cfg["y"], cfg["beta"], 1.0, fl, niter=m - 1)
+    got = mdl.log_likelihood(cfg["beta"], 1.0)
+    mdl.set_u(cfg["U"])
+    assert abs(got - want) <= RTOL * abs(want)
+
+
+def test_mcnr_matches_oracle(case, oracle):
+    cfg, mdl = case
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    for sigma in (1.0, 0.7):
+        want = oracle.mcnr(cfg["X"], cfg["Z"], cfg["U"], cfg["y"], cfg["beta"], sigma, fl)
+        got = mdl.mcnr(cfg["beta"], sigma)
+        assert rel(got["xtwx"], want["xtwx"]) <= RTOL
+        # the score is a sum of signed terms: scale by the size of its terms (max |X|^T mean |Wu|) rather than the result
+        assert np.max(np.abs(got["score"] - want["score"])) <= RTOL * max(np.max(np.abs(want["score"])), np.max(np.abs(want["xtwx"])))
+        assert abs(got["sigma"] - want["sigma"]) <= RTOL * abs(want["sigma"])
+        assert rel(got["beta_incr"], want["beta_incr"]) <= 1e-8     # solve amplifies by cond(X^T W X)
+
+
+def test_errors(gctx):
+    import glmmrmcml_b200 as g
+    cfg = synth.config1(m=8)
+    with pytest.raises(g.GmbError) as e:
+        g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], "binomial", "cloglog")
+    assert e.value.code == 2
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], "binomial", "logit")
+    with pytest.raises(g.GmbError) as e:
+        mdl.log_likelihood(cfg["beta"])          # no samples yet
+    assert e.value.code == 6
+    mdl.close()

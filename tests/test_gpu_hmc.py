@@ -1,0 +1,103 @@
+"""GPU parity of the batched random-effect sampler (K6) against the CPU oracle chain driven by the same Philox stream,
+and against the closed-form Gaussian posterior."""
+import numpy as np
+import pytest
+
+from glmmrmcml_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "C1": lambda: synth.config1(m=4),
+    "C2": lambda: synth.config2(m=4),
+    "C3": lambda: synth.config3(nloc=120, m=4),
+    "C4": lambda: synth.config4(ncl=30, nt=10, k=2, m=4),
+    "ragged": lambda: synth.config4(ncl=13, nt=7, k=3, m=4),
+}
+
+
+@pytest.fixture(scope="module", params=list(CASES))
+def case(request, gctx):
+    import glmmrmcml_b200 as g
+    cfg = CASES[request.param]()
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    yield cfg, mdl
+    mdl.close()
+
+
+def test_log_prob_and_grad(case, oracle):
+    """mcmlmodel.h:138-153 and :156-279 on fixed whitened states: 1e-10 relative."""
+    cfg, mdl = case
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    rng = np.random.default_rng(3)
+    V = np.asfortranarray(0.7 * rng.standard_normal((cfg["Q"], 11)))
+    sigma = 0.8
+    lp, G = mdl.log_prob_grad(cfg["L"], cfg["beta"], sigma, V)
+    ZL = cfg["Z"] @ cfg["L"]
+    xb = cfg["X"] @ cfg["beta"]
+    for c in range(V.shape[1]):
+        want = oracle.log_prob(ZL, xb, cfg["y"], sigma, fl, V[:, c])
+        assert abs(lp[c] - want) <= 1e-10 * abs(want)
+        gw = oracle.log_grad(ZL, xb, cfg["y"], sigma, fl, V[:, c])
+        assert np.max(np.abs(G[:, c] - gw)) <= 1e-10 * max(np.max(np.abs(gw)), 1.0)
+
+
+def test_chain_follows_oracle(case, oracle):
+    """Same seed, same counter-based RNG: the device chains must reproduce the oracle chains' states (to the accuracy
+    the leapfrog map preserves), acceptance rate, step size and step count."""
+    cfg, mdl = case
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    ZL = cfg["Z"] @ cfg["L"]
+    xb = cfg["X"] @ cfg["beta"]
+    warm, ns, lam, ms, ta, seed, nch = 12, 6, 0.02, 25, 0.9, 424242, 5
+    out = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=warm, nsamp_per_chain=ns, lam=lam, max_steps=ms,
+                         target_accept=ta, adapt=100, n_chains=nch, chain_offset=3, seed=seed, want_u=True, want_v=True)
+    acc = []
+    for c in range(nch):
+        ref = oracle.hmc_chain(ZL, cfg["L"], xb, cfg["y"], 1.0, fl, warm, ns, lam, ms, ta, seed, chain=3 + c)
+        vg = out["v"][:, c * (ns + 1):(c + 1) * (ns + 1)]
+        ug = out["u"][:, c * (ns + 1):(c + 1) * (ns + 1)]
+        assert np.max(np.abs(vg - ref["v"])) <= 1e-7 * max(1.0, np.max(np.abs(ref["v"])))
+        assert np.max(np.abs(ug - ref["u"])) <= 1e-7 * max(1.0, np.max(np.abs(ref["u"])))
+        acc.append(ref["accept"])
+    assert abs(out["stats"]["accept_rate"] - np.mean(acc)) < 1e-12
+
+
+def test_gaussian_posterior_moments(gctx):
+    """Gaussian-identity: v | y ~ N(A^-1 ZL^T (y - xb)/s^2, A^-1), A = I + ZL^T ZL / s^2."""
+    import glmmrmcml_b200 as g
+    cfg = synth.config3(nloc=40, m=4)
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], "gaussian", "identity")
+    sigma = 0.9
+    ZL = cfg["Z"] @ cfg["L"]
+    A = np.eye(cfg["Q"]) + ZL.T @ ZL / sigma ** 2
+    cov = np.linalg.inv(A)
+    mean = cov @ ZL.T @ (cfg["y"] - cfg["X"] @ cfg["beta"]) / sigma ** 2
+    nch, ns = 256, 40
+    out = mdl.hmc_sample(cfg["L"], cfg["beta"], sigma, warmup=150, nsamp_per_chain=ns, lam=1.5, max_steps=50,
+                         target_accept=0.9, n_chains=nch, seed=99, want_u=False, want_v=True)
+    V = out["v"].reshape(cfg["Q"], nch, ns + 1, order="F")[:, :, 1:]
+    # chains are independent: use per-chain means to get an honest Monte-Carlo standard error
+    cm = V.mean(axis=2)
+    est = cm.mean(axis=1); se = cm.std(axis=1, ddof=1) / np.sqrt(nch)
+    assert np.all(np.abs(est - mean) <= 5 * se + 1e-12), np.max(np.abs(est - mean) / se)
+    var_est = V.reshape(cfg["Q"], -1).var(axis=1, ddof=1)
+    assert np.all(np.abs(var_est / np.diag(cov) - 1) < 0.12)
+    assert 0.6 < out["stats"]["accept_rate"] <= 1.0
+    mdl.close()
+
+
+def test_mcmc_sample_shape_and_reference_quirk(gctx):
+    """mcmc_sample returns Q x (nsamp + 1) (mhmcmc.h:126,155)."""
+    import glmmrmcml_b200 as g
+    cfg = synth.config1(m=4)
+    s = g.mcmc_sample(cfg["Z"], cfg["L"], cfg["X"], cfg["y"], cfg["beta"], "binomial", "logit", warmup=10, nsamp=21, lam=0.05,
+                      n_chains=1, seed=5)
+    assert s.shape == (cfg["Q"], 22) and np.all(np.isfinite(s))
+    s4 = g.mcmc_sample(cfg["Z"], cfg["L"], cfg["X"], cfg["y"], cfg["beta"], "binomial", "logit", warmup=10, nsamp=21, lam=0.05,
+                       n_chains=4, seed=5)
+    assert s4.shape == (cfg["Q"], 22) and np.all(np.isfinite(s4))
+    # reproducible under a fixed seed (the reference is not: mhmcmc.h:55)
+    s2 = g.mcmc_sample(cfg["Z"], cfg["L"], cfg["X"], cfg["y"], cfg["beta"], "binomial", "logit", warmup=10, nsamp=21, lam=0.05,
+                       n_chains=1, seed=5)
+    assert np.array_equal(s, s2)
