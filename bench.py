@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the glmmrMCML hot path (Monte-Carlo E-step + random-effect sampler) on B200.
+
+Workload (BASELINE.json configs[1], "C2"): cluster RCT, binomial-logit, n = 500, P = 6, Q = 50 (10 blocks of
+gr(cl)*ar1(t)), m = 10^4 Monte-Carlo samples per GPU, MCNR + Hessian standard errors.
+
+One STEP = one pass of the hot path over one batch of m samples, the work of one MCML iteration with Hessian SEs:
+  1. draw m samples of u with the batched HMC sampler (C chains x (warmup + m/C) proposals; R defaults of
+     ModelMCML$mcmc_options: warmup 500, lambda 5, maxsteps 100, target_accept 0.95)            [mhmcmc.h:121-157]
+  2. zd = Z u                                                                                     [mcmlmodel.h:286]
+  3. one MCNR step (per-sample sufficient sums + Newton increment)                                [mcmloptim.h:198-236]
+  4. N_D mvn_ll evaluations (the d_optim objective; D(theta) build + Cholesky + forward solves)   [mcmldmatrix.h:23-78]
+  5. the 4k^2 = 256 point Hessian stencil: 256 E-step log-likelihood evaluations + 256 mvn_ll     [mcmloptim.h:333-355]
+value = u-samples/s = (m x ranks) / step time; the E-step evaluations/s and sampler samples/s (ESS/s) of
+BASELINE.json's metric are reported beside it, each timed in isolation in the same run.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+(N > 1: launched by torchrun, one rank per GPU; samples and chains are sharded over ranks — weak scaling.)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+M_PER_GPU = 10_000
+N_CHAINS = 500            # per GPU; 20 post-warm-up samples each
+HMC = dict(warmup=500, lam=5.0, max_steps=100, target_accept=0.95, adapt=100)
+N_D_EVALS = 64            # mvn_ll evaluations of one d_optim (BOBYQA over 2 parameters takes 40-80)
+N_HESS = 256              # 4 k^2, k = P + R = 8
+FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: profiles/r01_microbench_fp64.txt (tools/microbench_fp64.cu)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def stencil_points(rng, P, R, beta, theta, npts, h=1e-5):
+    """npts distinct parameter vectors around (beta, theta) like the optimhess stencil (every point evaluated, no memo)."""
+    B = beta[:, None] + h * rng.integers(-2, 3, size=(P, npts))
+    B[:, 0] = beta
+    B += 1e-9 * np.arange(npts)[None, :]            # all distinct
+    T = theta[:, None] + h * rng.integers(-2, 3, size=(R, npts)) + 1e-9 * np.arange(npts)[None, :]
+    return np.asfortranarray(B), np.asfortranarray(T)
+
+
+def ess_geyer(x):
+    """Multi-chain effective sample size (Geyer initial positive sequence on chain-averaged autocovariances).
+    x: chains x draws."""
+    C, N = x.shape
+    if N < 4:
+        return float(C * N)
+    xm = x - x.mean(axis=1, keepdims=True)
+    acov = np.array([np.mean(np.sum(xm[:, :N - t] * xm[:, t:], axis=1) / N) for t in range(N)])
+    W = np.mean(x.var(axis=1, ddof=1))
+    Bv = x.mean(axis=1).var(ddof=1) if C > 1 else 0.0
+    var_plus = W * (N - 1) / N + Bv
+    if not var_plus > 0:
+        return float(C * N)
+    rho = 1.0 - (W - acov) / var_plus
+    tau = -1.0
+    t = 0
+    while t + 1 < N:
+        pair = rho[t] + rho[t + 1]
+        if pair < 0:
+            break
+        tau += 2.0 * pair
+        t += 2
+    tau = max(tau, 1.0 / np.log10(max(C * N, 10)))
+    return float(C * N / tau)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle's FAITHFUL restatement of the reference CPU path, bounded sample, extrapolated to one step
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(cfg, threads=None, quick=False):
+    """Times the reference's CPU path (oracle FAITHFUL mode) on a bounded sample of the C2 step and extrapolates to the
+    full step.  Returns (seconds for one full step, detail dict)."""
+    import oracle
+    oracle.build()
+    if threads:
+        oracle.set_threads(threads)
+    nthr = oracle.max_threads() if not threads else threads
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    X, Z, y, U, beta, theta = cfg["X"], cfg["Z"], cfg["y"], cfg["U"], cfg["beta"], cfg["theta"]
+    m = U.shape[1]
+    ZL = Z @ cfg["L"]
+    xb = X @ beta
+    d = {}
+    # 1. sampler: single sequential chain as in the reference; time post-adaptation proposals
+    wu, ns = (100, 60) if quick else (120, 200)
+    t0 = time.perf_counter()
+    ch = oracle.hmc_chain(ZL, cfg["L"], xb, y, 1.0, fl, wu, ns, HMC["lam"], HMC["max_steps"], HMC["target_accept"], 12345, want_u=False)
+    t_h = time.perf_counter() - t0
+    per_prop = t_h / (wu + ns)
+    d["hmc_s_per_proposal"] = per_prop
+    d["hmc_steps_per_proposal"] = ch["total_steps"] / (wu + ns)
+    t_hmc = per_prop * (HMC["warmup"] + m)
+    # 2+5a. E-step log-likelihood, Z u GEMM recomputed per evaluation (mcmlmodel.h:286)
+    reps = 1 if quick else 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        oracle.loglik_faithful(X, Z, U, y, beta, 1.0, fl)
+    t_ll = (time.perf_counter() - t0) / reps
+    d["loglik_s_per_eval"] = t_ll
+    # 3. MCNR: Z u GEMM recomputed for EVERY sample (mcmloptim.h:213 -> mcmlmodel.h:121) => O(m^2); time at reduced m
+    ms1, ms2 = (192, 384) if quick else (384, 768)
+    ts = []
+    for msub in (ms1, ms2):
+        best = np.inf
+        for _ in range(2):
+            t0 = time.perf_counter()
+            oracle.mcnr(X, Z, U[:, :msub], y, beta, 1.0, fl, faithful=True)
+            best = min(best, time.perf_counter() - t0)
+        ts.append(best)
+    expo = np.log(ts[1] / ts[0]) / np.log(ms2 / ms1)
+    d["mcnr_scaling_exponent"] = float(expo)
+    t_mcnr = ts[1] * (m / ms2) ** 2
+    d["mcnr_s_extrapolated"] = float(t_mcnr)
+    # 4+5b. mvn_ll with the block Cholesky re-done per sample (mcmldmatrix.h:33-36)
+    t0 = time.perf_counter()
+    oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], theta, U, faithful=True)
+    t_d = time.perf_counter() - t0
+    d["mvn_ll_s_per_eval"] = t_d
+    total = t_hmc + t_mcnr + N_HESS * t_ll + (N_D_EVALS + N_HESS) * t_d
+    d.update(hmc_s=t_hmc, estep_s=N_HESS * t_ll, mvn_s=(N_D_EVALS + N_HESS) * t_d, threads=nthr)
+    # the same step with the redundant work hoisted (stronger CPU baseline, reported beside the faithful one)
+    zd = oracle.gemm(Z, U)
+    t0 = time.perf_counter()
+    oracle.loglik_zd(zd, xb, y, 1.0, fl)
+    t_llh = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], theta, U, faithful=False)
+    t_dh = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    oracle.mcnr(X, Z, U, y, beta, 1.0, fl, faithful=False)
+    t_mh = time.perf_counter() - t0
+    d["hoisted_step_s"] = float(t_hmc + t_mh + N_HESS * t_llh + (N_D_EVALS + N_HESS) * t_dh)
+    d["hoisted_loglik_s_per_eval"] = t_llh
+    return float(total), d
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="smaller CPU samples (for tests)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    from glmmrmcml_b200 import synth
+    cfg = synth.config2(m=M_PER_GPU)
+    workload = {"workload": "C2: cluster RCT binomial-logit n=500 P=6 Q=50 (10 blocks gr(cl)*ar1(t)), m=10^4 samples per GPU, "
+                            "MCNR + Hessian SEs",
+                "m_per_gpu": M_PER_GPU, "chains_per_gpu": N_CHAINS, "hmc": HMC,
+                "per_step": {"hmc_samples": M_PER_GPU, "mcnr_steps": 1, "loglik_evals": N_HESS, "mvn_ll_evals": N_D_EVALS + N_HESS},
+                "l2": "every step rewrites all sampler state, U (4 MB) and zd (40 MB); the roofline probe streams 1 GB > L2"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle
+        oracle.build()
+        vals, det = [], None
+        for it in range(args.warmup + args.steps):
+            t, det = cpu_reference_step(cfg, quick=args.quick)
+            if it >= args.warmup:
+                vals.append(t)
+        t_step = float(np.median(vals)) if vals else float("nan")
+        v = M_PER_GPU / t_step
+        line = {"metric": "u-samples/s through sampler + E-step", "value": v, "unit": "u-samples/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": workload,
+                "cpu_baseline": {"value": v, "unit": "u-samples/s", "cores": det["threads"], "kind": "port",
+                                 "sample": "oracle FAITHFUL (reference loop structure; the reference itself needs R/Eigen/glmmrBase and "
+                                           "cannot be built here): 320 HMC proposals of one chain, 2 full log-lik evals, MCNR at m=192/384 "
+                                           "(cost ~ m^2), 1 full mvn_ll eval; extrapolated to one full step", "detail": det},
+                "e2e": {"value": v, "unit": "u-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------- our arm ----------------
+    import torch
+    import glmmrmcml_b200 as g
+
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ctx = g.Context(local_rank)
+    if world > 1:
+        ids = [g.Context.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], rank, world)
+    ctx.make_default()
+
+    P, Q, R = cfg["P"], cfg["Q"], cfg["theta"].size
+    beta, theta = cfg["beta"], cfg["theta"]
+    mdl = g.Model(ctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    cv = g.Covariance(ctx, cfg["cov"], cfg["data"], cfg["eff_range"])
+    L = cv.genD(theta, chol=True)
+    rng = np.random.default_rng(1234)
+    Bst, Tst = stencil_points(rng, P, R, beta, theta, N_HESS)
+    _, Td = stencil_points(rng, P, R, beta, theta, N_D_EVALS, h=1e-3)
+    per = M_PER_GPU // N_CHAINS          # columns per chain incl. the post-warm-up state (k + 1)
+    seed0 = 20221208
+
+    first = {"done": False}
+
+    def step(i):
+        # 1. sampler (device-resident: L/ZL uploaded once)
+        mdl.hmc_sample(None if first["done"] else L, beta, 1.0, warmup=HMC["warmup"], nsamp_per_chain=per - 1, lam=HMC["lam"],
+                       max_steps=HMC["max_steps"], target_accept=HMC["target_accept"], adapt=HMC["adapt"], n_chains=N_CHAINS,
+                       chain_offset=rank * N_CHAINS, seed=seed0 + i, keep_on_device=True, want_u=False)
+        first["done"] = True
+        mdl.use_device_u()                                   # 2. zd = Z u
+        nr = mdl.mcnr(beta, 1.0)                             # 3.
+        for k in range(N_D_EVALS):                           # 4.
+            cv.loglik_model(Td[:, k], mdl)
+        ll = mdl.log_likelihood_batch(Bst, np.ones(N_HESS))  # 5.
+        dl = [cv.loglik_model(Tst[:, k], mdl) for k in range(N_HESS)]
+        return nr, ll, dl
+
+    for i in range(args.warmup):
+        step(i)
+    clocks = ClockSampler(local_rank)
+    ctx.sync(); torch.cuda.synchronize(); barrier()
+    if rank == 0:
+        clocks.start()
+    l0 = ctx.launch_count
+    ctx.timer_start()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        out = step(args.warmup + i)
+    ms = ctx.timer_stop()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = sum_over_ranks(ctx.launch_count - l0)
+    ms_step = max_over_ranks(ms) / args.steps
+    value = M_PER_GPU * world / (ms_step * 1e-3)
+    assert np.all(np.isfinite(out[1])) and np.all(np.isfinite(out[2]))
+
+    # ---- end to end through the reference-named C-ABI entry points with host buffers (what the R loop calls) ----
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    Zp = np.asfortranarray(pin(cfg["Z"].T).T); Xp = np.asfortranarray(pin(cfg["X"].T).T); yp = pin(cfg["y"]); Lp = np.asfortranarray(pin(L.T).T)
+    start = np.concatenate([beta, theta, [1.0]])
+
+    def e2e_step(i):
+        u = g.mcmc_sample(Zp, Lp, Xp, yp, beta, cfg["family"], cfg["link"], HMC["warmup"], M_PER_GPU - 1, HMC["lam"], 1.0, 0, 500,
+                          HMC["max_steps"], HMC["target_accept"], n_chains=N_CHAINS, seed=seed0 + 100 + i + 1000 * rank)
+        fit = g.mcml_optim(cfg["cov"], cfg["data"], cfg["eff_range"], Zp, Xp, yp, u, cfg["family"], cfg["link"], start, 0, True)
+        H = g.mcml_hess(cfg["cov"], cfg["data"], cfg["eff_range"], Zp, Xp, yp, u, cfg["family"], cfg["link"],
+                        np.concatenate([fit["beta"], fit["theta"]]), 1e-5, 0)
+        return u, fit, H
+
+    n_e2e = max(2, min(args.steps, 3))
+    e2e_step(-1)
+    ctx.sync(); barrier()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        u_last, fit_last, H_last = e2e_step(i)
+    ctx.sync()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / n_e2e)
+    e2e_val = M_PER_GPU * world / e2e_s
+    base_b = (Zp.nbytes + Xp.nbytes + yp.nbytes)
+    h2d = (base_b + Lp.nbytes) + 2 * (base_b + u_last.nbytes)
+    d2h = u_last.nbytes + (P + R + 1) * 8 + (P + R) ** 2 * 8
+
+    # ---- isolated components on rank 0's shard (device-resident), for BASELINE.json's two-part metric ----
+    extra = {}
+    res = mdl.hmc_sample(None, beta, 1.0, warmup=HMC["warmup"], nsamp_per_chain=per - 1, lam=HMC["lam"], max_steps=HMC["max_steps"],
+                         target_accept=HMC["target_accept"], adapt=HMC["adapt"], n_chains=N_CHAINS, chain_offset=rank * N_CHAINS,
+                         seed=seed0 + 7, keep_on_device=True, want_u=True)
+    st = res["stats"]
+    hmc_ms = st["kernel_ms"]
+    Uall = res["u"].reshape(Q, N_CHAINS, per, order="F")[:, :, 1:]           # drop each chain's column 0 (warm-up end state)
+    ess = np.array([ess_geyer(Uall[q]) for q in range(Q)])
+    n_post = N_CHAINS * (per - 1)
+    extra["hmc"] = {"u_samples_per_s": sum_over_ranks(N_CHAINS * per / (hmc_ms * 1e-3)),
+                    "ess_per_s_min": sum_over_ranks(float(ess.min()) / (hmc_ms * 1e-3)),
+                    "ess_per_s_median": sum_over_ranks(float(np.median(ess)) / (hmc_ms * 1e-3)),
+                    "ess_over_n_median": float(np.median(ess) / n_post), "accept_rate": st["accept_rate"],
+                    "step_size_mean": st["step_size_mean"], "steps_mean": st["steps_mean"], "ms": hmc_ms,
+                    "leapfrog_per_s": sum_over_ranks(st["leapfrog_total"] / (hmc_ms * 1e-3))}
+    hmc_flops = st["leapfrog_total"] * 4.0 * cfg["n"] * Q                     # 4 n Q per leapfrog step per chain
+    hmc_tflops = hmc_flops / (hmc_ms * 1e-3) / 1e12
+    mdl.use_device_u()
+    # E-step evaluations/s on the step's own zd (40 MB, L2-resident between evaluations) and cold (L2 flushed before each)
+    ctx.timer_start(); mdl.log_likelihood_batch(Bst, np.ones(N_HESS)); t_b = ctx.timer_stop()
+    cold = []
+    for k in range(8):
+        ctx.flush_l2(); ctx.sync()
+        ctx.timer_start(); mdl.log_likelihood(Bst[:, k], 1.0); cold.append(ctx.timer_stop())
+    extra["estep"] = {"loglik_evals_per_s_batched": N_HESS / (t_b * 1e-3), "loglik_evals_per_s_single_cold": 1e3 / float(np.median(cold)),
+                      "m": M_PER_GPU * world, "note": "m=10^4 x n=500: 40 MB, below launch latency; see roofline_estep for the streaming rate"}
+    ctx.timer_start(); [cv.loglik_model(Tst[:, k], mdl) for k in range(64)]; t_d = ctx.timer_stop()
+    extra["mvn_ll_evals_per_s"] = 64 / (t_d * 1e-3)
+    ctx.timer_start(); [mdl.mcnr(beta, 1.0) for _ in range(16)]; t_n = ctx.timer_stop()
+    extra["mcnr_steps_per_s"] = 16 / (t_n * 1e-3)
+
+    peaks, peak_src = load_peaks()
+    roofline_estep = None
+    if rank == 0:
+        # HBM roofline probe of the E-step kernels: same model, 1 GB of zd (> 4 x L2), 8 evaluations in one batch
+        mbig = 250_000
+        rngb = np.random.default_rng(5)
+        Ubig = np.asfortranarray(cfg["L"] @ rngb.standard_normal((Q, mbig)))
+        mdl2 = g.Model(ctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+        mdl2.set_u(Ubig)
+        mdl2.log_likelihood_batch(Bst[:, :4], np.ones(4))
+        ctx.timer_start(); mdl2.log_likelihood_batch(Bst[:, :8], np.ones(8)); t_big = ctx.timer_stop() / 8
+        bytes_ll = 8.0 * cfg["n"] * mbig + 16.0 * cfg["n"]
+        mdl2.mcnr(beta, 1.0)
+        ctx.timer_start(); [mdl2.mcnr(beta, 1.0) for _ in range(4)]; t_nr = ctx.timer_stop() / 4
+        bytes_nr = 8.0 * cfg["n"] * mbig + 8.0 * cfg["n"] * (P + 2)
+        roofline_estep = {"kernel": "loglik_kernel<binomial-logit>", "bound": "hbm", "achieved": bytes_ll / (t_big * 1e-3) / 1e9,
+                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bytes_ll / (t_big * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "bytes_per_launch": bytes_ll, "ms": t_big, "zd_bytes": 8.0 * cfg["n"] * mbig, "peak_source": peak_src,
+                          "mcnr": {"achieved": bytes_nr / (t_nr * 1e-3) / 1e9, "frac": bytes_nr / (t_nr * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": t_nr}}
+        mdl2.close()
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        t_cpu, det = cpu_reference_step(cfg, quick=args.quick)
+        cpu = {"value": M_PER_GPU / t_cpu, "unit": "u-samples/s", "cores": det["threads"], "kind": "port",
+               "sample": "oracle FAITHFUL mode (reference loop structure incl. its redundant Z u GEMMs and per-sample Cholesky): 320 HMC "
+                         "proposals of one chain, 2 full log-lik evals, MCNR at m=384/768 (cost ~ m^2), 1 full mvn_ll eval; "
+                         "extrapolated to one full step", "step_s": t_cpu, "hoisted_value": M_PER_GPU / det["hoisted_step_s"], "detail": det}
+    line = {"metric": "u-samples/s through sampler + E-step", "value": value, "unit": "u-samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
+            "e2e": {"value": e2e_val, "unit": "u-samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "calls": "gmb_mcmc_sample + gmb_mcml_optim(mcnr) + gmb_mcml_hess with host buffers", "s_per_step": e2e_s},
+            "gpu_launches": int(launches), "clocks": clk, "wall_s": wall,
+            "roofline": {"kernel": "dgemm_kernel<EpiResid>/<EpiLeapfrog> (sampler contractions)", "bound": "tensor",
+                         "achieved": hmc_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": hmc_tflops / FP64_DMMA_PEAK_TFLOPS,
+                         "traffic": None, "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q,
+                         "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_microbench_fp64.txt); "
+                                        "MEASURED_PEAKS.json has no fp64 entry (bf16 tensor peak does not apply to an fp64 kernel)"},
+            "roofline_estep": roofline_estep, "cpu_baseline": cpu}
+    line.update(extra)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,6 +74,18 @@ class Context:
         """Raw cudaStream_t of the context (integer handle), for CUDA-event timing by callers."""
         return int(lib().gmb_ctx_stream(self._h) or 0)
 
+    def timer_start(self):
+        check(lib().gmb_ctx_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        """Device time in ms since timer_start, measured with CUDA events on the context's stream."""
+        ms = C.c_double()
+        check(lib().gmb_ctx_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        check(lib().gmb_ctx_flush_l2(self._h))
+
     @staticmethod
     def unique_id() -> bytes:
         buf = C.create_string_buffer(128)

@@ -42,6 +42,9 @@ PROTOTYPES = {
     "gmb_ctx_sync": (C.c_int, [vp]),
     "gmb_ctx_launch_count": (C.c_int64, [vp]),
     "gmb_ctx_stream": (vp, [vp]),
+    "gmb_ctx_timer_start": (C.c_int, [vp]),
+    "gmb_ctx_timer_stop": (C.c_int, [vp, dp]),
+    "gmb_ctx_flush_l2": (C.c_int, [vp]),
     "gmb_comm_unique_id": (C.c_int, [vp]),
     "gmb_comm_init": (C.c_int, [vp, vp, C.c_int, C.c_int]),
     "gmb_comm_rank": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -168,7 +168,7 @@ struct Fit {
 };
 
 struct Handles {
-    gmb_cov* cv = nullptr; gmb_model* mdl = nullptr;
+    gmb_cov* cv = nullptr; gmb_model* mdl = nullptr; int m_total = 0;
     ~Handles() { if (mdl) gmb_model_destroy(mdl); if (cv) gmb_cov_destroy(cv); }
 };
 
@@ -189,7 +189,11 @@ int setup_fixed_u(gmb_ctx* ctx, const int32_t* cov, int cov_rows, const double* 
     GMB_TRY(gmb_cov_dims(h.cv, &B, &Qc, &R));
     if (Qc != Q) return gmb_set_error(GMB_EINVAL, "covariance has %d random effects, Z has %d columns", Qc, Q);
     GMB_TRY(gmb_model_create(ctx, n, P, Q, X, Z, y, family, link, &h.mdl));
-    GMB_TRY(gmb_model_set_u(h.mdl, u, Q, m, m, m));
+    // with an NCCL-enabled default context every rank passes ITS columns of u; the averages run over all of them
+    double mt = (double)m;
+    GMB_TRY(gmb_comm_allreduce_host(ctx, &mt, 1));
+    h.m_total = (int)(mt + 0.5);
+    GMB_TRY(gmb_model_set_u(h.mdl, u, Q, m, h.m_total, h.m_total));
     return GMB_OK;
 }
 
@@ -254,7 +258,7 @@ extern "C" int gmb_mcml_optim(const int32_t* cov, int cov_rows, const double* da
     Fit mc;
     GMB_TRY(mc.init(ctx, h.cv, h.mdl, start, n_start, family));
     mc.model_var_par = 1.0;                                       // :52
-    mc.d_cols_total = m;
+    mc.d_cols_total = h.m_total;
     if (!mcnr) GMB_TRY(mc.l_optim()); else GMB_TRY(mc.mcnr());    // :55-59
     GMB_TRY(mc.d_optim());                                        // :60
     if (beta_out) memcpy(beta_out, mc.beta.data(), sizeof(double) * P);
@@ -275,7 +279,7 @@ extern "C" int gmb_mcml_simlik(const int32_t* cov, int cov_rows, const double* d
     GMB_TRY(setup_fixed_u(ctx, cov, cov_rows, data, n_data, eff_range, n_eff, Z, X, y, u, n, P, Q, m, family, link, h));
     Fit mc;
     GMB_TRY(mc.init(ctx, h.cv, h.mdl, start, n_start, family));
-    mc.d_cols_total = m;
+    mc.d_cols_total = h.m_total;
     GMB_TRY(mc.f_optim());                                        // :108
     if (beta_out) memcpy(beta_out, mc.beta.data(), sizeof(double) * P);
     if (theta_out) memcpy(theta_out, mc.theta.data(), sizeof(double) * mc.R);
@@ -296,7 +300,7 @@ extern "C" int gmb_mcml_hess(const int32_t* cov, int cov_rows, const double* dat
     GMB_TRY(setup_fixed_u(ctx, cov, cov_rows, data, n_data, eff_range, n_eff, Z, X, y, u, n, P, Q, m, family, link, h));
     Fit mc;
     GMB_TRY(mc.init(ctx, h.cv, h.mdl, start, n_start, family));
-    mc.d_cols_total = m;
+    mc.d_cols_total = h.m_total;
     return mc.f_hess(tol, hess_out);                              // :283
 }
 
@@ -318,7 +322,7 @@ extern "C" int gmb_aic_mcml(const int32_t* cov, int cov_rows, const double* data
     const double var_par = has_var ? beta_par[P] : 0.0;            // :375-382
     const int dof = n_beta_par + n_cov_par;                        // :371
     double dmvvec, ll;
-    GMB_TRY(gmb_cov_mvn_ll_model(h.cv, cov_par, h.mdl, m, &dmvvec));   // :386
+    GMB_TRY(gmb_cov_mvn_ll_model(h.cv, cov_par, h.mdl, h.m_total, &dmvvec));   // :386
     GMB_TRY(gmb_model_loglik(h.mdl, beta_par, var_par, &ll));          // :387
     *out = -2 * (ll + dmvvec) + 2 * dof;                           // :389
     return GMB_OK;

@@ -54,7 +54,9 @@ struct gmb_ctx {
     // NCCL (loaded with dlopen; see comm.cu)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // internal (sampler kernel time)
+    cudaEvent_t ev2 = nullptr, ev3 = nullptr;   // gmb_ctx_timer_start / _stop
+    void* d_flush = nullptr; int flush_val = 0; // gmb_ctx_flush_l2
 };
 
 int gmb_ctx_scratch(gmb_ctx* ctx, size_t doubles);   // grow d_scratch to at least `doubles`

@@ -32,6 +32,8 @@ extern "C" int gmb_ctx_create(int device, gmb_ctx** out) {
     GMB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     GMB_CUDA(cudaEventCreate(&ctx->ev0));
     GMB_CUDA(cudaEventCreate(&ctx->ev1));
+    GMB_CUDA(cudaEventCreate(&ctx->ev2));
+    GMB_CUDA(cudaEventCreate(&ctx->ev3));
     ctx->pinned_doubles = 1 << 16;
     GMB_CUDA(cudaMallocHost(&ctx->h_pinned, ctx->pinned_doubles * sizeof(double)));
     GMB_CUDA(cudaMalloc(&ctx->d_result, GMB_RESULT_DOUBLES * sizeof(double)));
@@ -55,6 +57,31 @@ int gmb_ctx_scratch(gmb_ctx* ctx, size_t doubles) {
 extern "C" int gmb_ctx_sync(gmb_ctx* ctx) {
     if (!ctx) return gmb_set_error(GMB_EINVAL, "ctx is NULL");
     GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GMB_OK;
+}
+
+// CUDA-event timer on the context's own stream (torch.cuda.Event only sees torch's current stream)
+extern "C" int gmb_ctx_timer_start(gmb_ctx* ctx) {
+    if (!ctx) return gmb_set_error(GMB_EINVAL, "ctx is NULL");
+    GMB_CUDA(cudaEventRecord(ctx->ev2, ctx->stream));
+    return GMB_OK;
+}
+extern "C" int gmb_ctx_timer_stop(gmb_ctx* ctx, double* ms) {
+    if (!ctx || !ms) return gmb_set_error(GMB_EINVAL, "ctx or ms is NULL");
+    GMB_CUDA(cudaEventRecord(ctx->ev3, ctx->stream));
+    GMB_CUDA(cudaEventSynchronize(ctx->ev3));
+    float f = 0.f;
+    GMB_CUDA(cudaEventElapsedTime(&f, ctx->ev2, ctx->ev3));
+    *ms = f;
+    return GMB_OK;
+}
+// Overwrites a buffer larger than the L2 cache (126 MB on B200) so that the next kernel starts cold.
+extern "C" int gmb_ctx_flush_l2(gmb_ctx* ctx) {
+    if (!ctx) return gmb_set_error(GMB_EINVAL, "ctx is NULL");
+    const size_t bytes = (size_t)256 << 20;
+    if (!ctx->d_flush) GMB_CUDA(cudaMalloc(&ctx->d_flush, bytes));
+    ctx->flush_val ^= 1;
+    GMB_CUDA(cudaMemsetAsync(ctx->d_flush, ctx->flush_val, bytes, ctx->stream));
     return GMB_OK;
 }
 
@@ -172,6 +199,9 @@ extern "C" void gmb_ctx_destroy(gmb_ctx* ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+    if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->d_flush) cudaFree(ctx->d_flush);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

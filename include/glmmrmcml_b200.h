@@ -45,6 +45,12 @@ int  gmb_ctx_sync(gmb_ctx* ctx);
 int64_t gmb_ctx_launch_count(gmb_ctx* ctx);
 /* Raw cudaStream_t the kernels are launched on (so callers can bracket it with CUDA events). */
 void* gmb_ctx_stream(gmb_ctx* ctx);
+/* CUDA-event stopwatch on that stream: start records an event, stop records a second one, waits for it and returns
+ * the elapsed device time in milliseconds. */
+int gmb_ctx_timer_start(gmb_ctx* ctx);
+int gmb_ctx_timer_stop(gmb_ctx* ctx, double* ms);
+/* Overwrites a 256 MiB scratch buffer (larger than the 126 MB L2) on the stream: cold-cache timing of the next kernel. */
+int gmb_ctx_flush_l2(gmb_ctx* ctx);
 
 /* Multi-GPU: one process per GPU; Monte-Carlo samples and chains are sharded over ranks, the
  * per-evaluation sufficient sums are summed with ncclAllReduce on the context's stream.  The 128-byte NCCL
