@@ -67,6 +67,7 @@ PROTOTYPES = {
     "gmb_cov_logdet": (C.c_int, [vp, dp, dp]),
     "gmb_hmc_sample": (C.c_int, [vp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                  C.c_int, C.c_uint32, C.c_uint64, C.c_int, dp, dp, C.POINTER(HmcStats)]),
+    "gmb_hmc_set_variant": (C.c_int, [C.c_int]),
     "gmb_model_logprob_grad": (C.c_int, [vp, dp, dp, C.c_double, dp, C.c_int, dp, dp]),
     "gmb_set_default_ctx": (C.c_int, [vp]),
     "gmb_mvn_ll": (C.c_int, _cov_args + [dp, C.c_int, dp, C.c_int, C.c_int, dp]),

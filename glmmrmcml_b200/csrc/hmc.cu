@@ -339,6 +339,40 @@ static int hmc_run(gmb_model* mdl, double var_par, int warmup, int nsamp, double
     return GMB_OK;
 }
 
+// hmc_fused.cu
+bool gmb_hmc_fused_applicable(const gmb_model* mdl);
+int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
+                      int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs);
+
+// 0 = choose (on-chip variant when the model fits one SM's shared memory), 1 = force the two-GEMM variant, 2 = force on-chip
+static int g_hmc_variant = 0;
+extern "C" int gmb_hmc_set_variant(int variant) {
+    if (variant < 0 || variant > 2) return gmb_set_error(GMB_EINVAL, "variant must be 0 (auto), 1 (two-GEMM) or 2 (on-chip)");
+    g_hmc_variant = variant;
+    return GMB_OK;
+}
+
+static int hmc_run_fused_timed(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
+                               int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, std::vector<double>* host_cs, float* ms) {
+    gmb_ctx* ctx = mdl->ctx;
+    const size_t need = (size_t)CS_COUNT * C + 16;
+    if (need > mdl->hmc_work_doubles) {
+        if (mdl->hmc_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(mdl->hmc_work)); mdl->hmc_work = nullptr; mdl->hmc_work_doubles = 0; }
+        GMB_CUDA(cudaMalloc(&mdl->hmc_work, need * sizeof(double)));
+        mdl->hmc_work_doubles = need;
+    }
+    GMB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    GMB_TRY(gmb_hmc_run_fused(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
+    GMB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (host_cs) {
+        host_cs->resize((size_t)CS_COUNT * C);
+        GMB_CUDA(cudaMemcpyAsync(host_cs->data(), mdl->hmc_work, sizeof(double) * CS_COUNT * C, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ms) GMB_CUDA(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return GMB_OK;
+}
+
 static int set_xb(gmb_model* mdl, const double* beta) {
     gmb_ctx* ctx = mdl->ctx;
     if (mdl->beta_cap < mdl->P) {
@@ -379,8 +413,14 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     }
     std::vector<double> hcs;
     float ms = 0.f;
-    GMB_TRY(hmc_run(mdl, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
-                    mdl->dV, stats ? &hcs : nullptr, &ms));
+    const bool fits = gmb_hmc_fused_applicable(mdl);
+    if (g_hmc_variant == 2 && !fits) return gmb_set_error(GMB_EINVAL, "the on-chip sampler variant was forced but Z L (%d x %d) does not fit in shared memory", mdl->n, mdl->Q);
+    if (fits && g_hmc_variant != 1)
+        GMB_TRY(hmc_run_fused_timed(mdl, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
+                                    mdl->dV, stats ? &hcs : nullptr, &ms));
+    else
+        GMB_TRY(hmc_run(mdl, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
+                        mdl->dV, stats ? &hcs : nullptr, &ms));
     if (stats) {
         double acc = 0, eps = 0, tot = 0;
         for (int c = 0; c < C; c++) { acc += hcs[(size_t)CS_ACCEPT * C + c]; eps += hcs[(size_t)CS_EPS * C + c]; tot += hcs[(size_t)CS_TOTSTEPS * C + c]; }

@@ -134,6 +134,11 @@ int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* beta, double v
                    int n_chains, uint32_t chain_offset, uint64_t seed, int keep_on_device,
                    double* U_out, double* V_out, gmb_hmc_stats* stats);
 
+/* Sampler kernel selection: 0 = automatic (the on-chip kernel, Z L resident in shared memory, when the model fits one
+ * SM; otherwise two fused-epilogue GEMMs per leapfrog step), 1 = force the two-GEMM variant, 2 = force the on-chip one.
+ * Both variants follow the same chain arithmetic and the same random streams. */
+int gmb_hmc_set_variant(int variant);
+
 /* mcmlModel::log_prob / log_grad (mcmlmodel.h:138-153, 156-279, usezl = true) for C whitened states V (Q x C):
  * lp[C], grad (Q x C).  Either output may be NULL.  Used by the parity tests and by mcml_la. */
 int gmb_model_logprob_grad(gmb_model* mdl, const double* L, const double* beta, double var_par,

@@ -42,14 +42,28 @@ def test_log_prob_and_grad(case, oracle):
         assert np.max(np.abs(G[:, c] - gw)) <= 1e-10 * max(np.max(np.abs(gw)), 1.0)
 
 
-def test_chain_follows_oracle(case, oracle):
+@pytest.mark.parametrize("variant", [1, 2], ids=["two-gemm", "on-chip"])
+def test_chain_follows_oracle(case, oracle, variant):
     """Same seed, same counter-based RNG: the device chains must reproduce the oracle chains' states (to the accuracy
-    the leapfrog map preserves), acceptance rate, step size and step count."""
+    the leapfrog map preserves), acceptance rate, step size and step count — for both sampler kernels."""
+    import glmmrmcml_b200 as g
     cfg, mdl = case
+    g.hmc_set_variant(variant)
+    try:
+        _chain_follows_oracle(cfg, mdl, oracle)
+    except g.GmbError as e:
+        if variant == 2 and "does not fit" in str(e):
+            pytest.skip("model too large for the on-chip variant")
+        raise
+    finally:
+        g.hmc_set_variant(0)
+
+
+def _chain_follows_oracle(cfg, mdl, oracle):
     fl = oracle.flink(cfg["family"], cfg["link"])
     ZL = cfg["Z"] @ cfg["L"]
     xb = cfg["X"] @ cfg["beta"]
-    warm, ns, lam, ms, ta, seed, nch = 12, 6, 0.02, 25, 0.9, 424242, 5
+    warm, ns, lam, ms, ta, seed, nch = 12, 6, 0.02, 25, 0.9, 424242, 11
     out = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=warm, nsamp_per_chain=ns, lam=lam, max_steps=ms,
                          target_accept=ta, adapt=100, n_chains=nch, chain_offset=3, seed=seed, want_u=True, want_v=True)
     acc = []
