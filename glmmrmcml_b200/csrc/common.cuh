@@ -178,6 +178,47 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
     return v;
 }
 
+// exp(x) for the streaming kernels.  Same algorithm class as the library exp (Cody-Waite reduction by ln 2, polynomial,
+// exponent insertion; error < 1 ulp on the fast path) but with every constant taken from the constant bank as a direct
+// DFMA operand: the library version materialises each 64-bit coefficient with two UMOV instructions, which made uniform
+// moves 34% of the issued instructions of the E-step kernel (profiles/r01_ncu_summary.md).
+static __constant__ double GMB_EXPC[20] = {
+    1.4426950408889634074,          // 0: log2(e)
+    6755399441055744.0,             // 1: 1.5 * 2^52 (round-to-nearest-integer by addition)
+    -6.93147180369123816490e-01,    // 2: -ln2 high part (trailing zeros: k * ln2_hi is exact)
+    -1.90821492927058770002e-10,    // 3: -ln2 low part
+    1.0 / 6227020800.0,             // 4: 1/13!
+    1.0 / 479001600.0,              // 5: 1/12!
+    1.0 / 39916800.0,               // 6
+    1.0 / 3628800.0,                // 7
+    1.0 / 362880.0,                 // 8
+    1.0 / 40320.0,                  // 9
+    1.0 / 5040.0,                   // 10
+    1.0 / 720.0,                    // 11
+    1.0 / 120.0,                    // 12
+    1.0 / 24.0,                     // 13
+    1.0 / 6.0,                      // 14
+    0.5,                            // 15
+    1.0,                            // 16
+    700.0,                          // 17: beyond this the library exp handles overflow / subnormal results
+    0.0, 0.0};
+
+__device__ __forceinline__ double dev_exp(double x) {
+    const double* c = GMB_EXPC;
+    double t = fma(x, c[0], c[1]);
+    const int k = __double2loint(t);
+    t -= c[1];
+    double r = fma(t, c[2], x);
+    r = fma(t, c[3], r);
+    double p = c[4];
+#pragma unroll
+    for (int i = 5; i <= 16; i++) p = fma(p, r, c[i]);
+    p = fma(p, r, c[16]);
+    double res = __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+    if (!(fabs(x) < c[17])) res = exp(x);
+    return res;
+}
+
 // moremaths.h:16-24
 __device__ __forceinline__ double dev_log_factorial_approx(double n) {
     if (n == 0) return 0.0;
@@ -191,9 +232,9 @@ __device__ __forceinline__ double dev_log_factorial_approx(double n) {
 template <int FL>
 __device__ __forceinline__ double dev_family_ll(double y, double eta, double rowc, double c0, double sigma) {
     if (FL == 1) {
-        return y * eta - exp(eta) - rowc;
+        return y * eta - dev_exp(eta) - rowc;
     } else if (FL == 3) {
-        double p = 1.0 / (1.0 + exp(-1.0 * eta));
+        double p = 1.0 / (1.0 + dev_exp(-1.0 * eta));
         double r = 0.0;
         if (y == 1.0) r = log(p);
         else if (y == 0.0) r = log(1.0 - p);
@@ -207,8 +248,8 @@ __device__ __forceinline__ double dev_family_ll(double y, double eta, double row
 // gradient residual r(eta) of mcmlmodel.h:170-175 (FL 1), :184-193 (FL 3), :233-238 (FL 7, without the 1/sigma^2)
 template <int FL>
 __device__ __forceinline__ double dev_family_resid(double y, double eta) {
-    if (FL == 1) return y - exp(eta);
-    if (FL == 3) return 1.0 / (exp(eta) + 1.0) + y - 1.0;
+    if (FL == 1) return y - dev_exp(eta);
+    if (FL == 3) return __drcp_rn(dev_exp(eta) + 1.0) + y - 1.0;
     return y - eta;
 }
 

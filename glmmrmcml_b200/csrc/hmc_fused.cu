@@ -39,16 +39,71 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-template <int FL, int KSMAX>
+// Gradient contributions of `NT` (1 or 2) tiles of 8 observations, rows r0[t] .. r0[t]+7, for the 8 chains of the CTA.
+// MASK: rows >= n exist in the tile (only the last tile of a model whose n is not a multiple of 8).
+// LL: also accumulate the family log-likelihood of the chains that are on their last leapfrog step.
+template <int FL, int KS, int NT, bool MASK, bool LL>
+__device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, const double (&bf)[KS], const int (&r0)[NT], int n,
+                                            const double* __restrict__ xb, const double* __restrict__ y, const double* __restrict__ rowc,
+                                            double c0, double sigma, bool want0, bool want1, int fr, int fk,
+                                            double (&gacc)[(KS + 1) / 2][2], double& ll0, double& ll1) {
+    constexpr int LD = 4 * KS, QT8 = (KS + 1) / 2;
+    double a[NT][2], xbv[NT], yv[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        const int row = r0[t] + fr;
+        const bool ok = !MASK || row < n;
+        xbv[t] = ok ? __ldg(xb + row) : 0.0;
+        yv[t] = ok ? __ldg(y + row) : 0.0;
+        a[t][0] = a[t][1] = 0.0;
+    }
+    // eta tiles: rows x 8 chains; NT independent accumulator chains
+#pragma unroll
+    for (int j = 0; j < KS; j++)
+#pragma unroll
+        for (int t = 0; t < NT; t++) dmma884(a[t][0], a[t][1], sZL[(r0[t] + fr) * LD + 4 * j + fk], bf[j]);
+    double res[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        const double eta0 = xbv[t] + a[t][0], eta1 = xbv[t] + a[t][1];
+        res[t][0] = dev_family_resid<FL>(yv[t], eta0);
+        res[t][1] = dev_family_resid<FL>(yv[t], eta1);
+        if (MASK) { const bool ok = r0[t] + fr < n; if (!ok) { res[t][0] = 0.0; res[t][1] = 0.0; } }
+        if (LL) {
+            const bool ok = !MASK || r0[t] + fr < n;
+            const double rc = (FL == 1 && ok) ? __ldg(rowc + r0[t] + fr) : 0.0;
+            const double l0 = dev_family_ll<FL>(yv[t], eta0, rc, c0, sigma), l1 = dev_family_ll<FL>(yv[t], eta1, rc, c0, sigma);
+            if (want0 && ok) ll0 += l0;
+            if (want1 && ok) ll1 += l1;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            // res is held as C fragment [row = lane/4][chain = 2(lane%4) + {0,1}]; the transposed product needs it as
+            // B fragment [k = row = 4h + lane%4][n = chain = lane/4]
+            const int src = 4 * (4 * h + fk) + (fr >> 1);
+            const double t0 = __shfl_sync(0xffffffffu, res[t][0], src);
+            const double t1 = __shfl_sync(0xffffffffu, res[t][1], src);
+            const double b = (fr & 1) ? t1 : t0;
+            const double* zt = sZL + (r0[t] + 4 * h + fk) * LD + fr;
+#pragma unroll
+            for (int i = 0; i < QT8; i++) dmma884(gacc[i][0], gacc[i][1], zt[8 * i], b);
+        }
+}
+
+template <int FL, int KS>
 __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams p) {
-    constexpr int QT8MAX = (KSMAX + 1) / 2;          // 8-row tiles of the gradient
-    constexpr int QT32 = (KSMAX * 4 + 31) / 32;      // state elements per lane
+    constexpr int LD = 4 * KS;                       // row stride of the Z L tile; KS = 1 (mod 4) makes it 4 (mod 16)
+    constexpr int QT8 = (KS + 1) / 2;                // 8-row tiles of the gradient
+    constexpr int QP8 = QT8 * 8;
+    constexpr int QT32 = (KS * 4 + 31) / 32;         // state elements per lane
     extern __shared__ __align__(16) double sm[];
-    const int ld = p.ld, ks = p.ks, qt8 = p.qt8, n = p.n, Q = p.Q;
-    const int QP8 = qt8 * 8;
-    double* sZL = sm;                                 // n8 x ld (+8 spill-over doubles for the padded q-tile reads)
-    double* sVP = sZL + (size_t)p.n8 * ld + 8;        // [chain][ld]
-    double* sSlot = sVP + CB * ld;                    // [4][QP8][9]
+    const int n = p.n, Q = p.Q;
+    double* sZL = sm;                                 // n8 x LD (+8 spill-over doubles for the padded q-tile reads)
+    double* sVP = sZL + (size_t)p.n8 * LD + 8;        // [chain][LD]
+    double* sSlot = sVP + CB * LD;                    // [4][QP8][9]
     double* sLL = sSlot + 4 * QP8 * 9;                // [NWARP][CB]
     int* sSteps = reinterpret_cast<int*>(sLL + NWARP * CB);   // [CB]
 
@@ -59,19 +114,20 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     const uint32_t gchain = p.chain_offset + (uint32_t)chain;
 
     // ---- stage Z L (global: n x Q column-major) into shared memory, row-major, zero padded ----
-    for (int idx = tid; idx < p.n8 * ld + 8; idx += THREADS) sZL[idx] = 0.0;
-    for (int idx = tid; idx < CB * ld; idx += THREADS) sVP[idx] = 0.0;
+    for (int idx = tid; idx < p.n8 * LD + 8; idx += THREADS) sZL[idx] = 0.0;
+    for (int idx = tid; idx < CB * LD; idx += THREADS) sVP[idx] = 0.0;
     __syncthreads();
     for (int idx = tid; idx < n * Q; idx += THREADS) {
         const int row = idx % n, q = idx / n;
-        sZL[(size_t)row * ld + q] = p.ZL[row + (size_t)q * p.ldn];
+        sZL[(size_t)row * LD + q] = p.ZL[row + (size_t)q * p.ldn];
     }
 
     const double sigma = p.var_par;
     const double sc = (FL == 7) ? 1.0 / (sigma * sigma) : 1.0;
     const double c0 = (FL == 7) ? (-1.0 * log(sigma) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
     const double pc = -1.0 * log(1.0) - 0.5 * log(2 * GMB_PI_FAMILY);   // log_likelihood(v, 0, 1, 7), mcmlmodel.h:149
-    const int ntiles = p.n8 / 8;
+    const int nfull = n / 8;                          // tiles without padding rows
+    const bool has_tail = (n % 8) != 0;
 
     // ---- chain state (warp = chain, lane = q mod 32) ----
     double v[QT32], vp[QT32], r[QT32], gc[QT32], g[QT32];
@@ -85,62 +141,59 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         dev_rng_normal2(p.seed, (uint32_t)(q >> 1), 0u, gchain, 0u, z0, z1);
         v[k] = (q < Q) ? ((q & 1) ? z1 : z0) : 0.0;
         vp[k] = v[k]; r[k] = 0.0; gc[k] = 0.0; g[k] = 0.0;
-        if (q < Q) sVP[warp * ld + q] = vp[k];
+        if (q < Q) sVP[warp * LD + q] = vp[k];
     }
     if (lane == 0) sSteps[warp] = 1;
     __syncthreads();
 
     // One evaluation of the gradient at the v' currently in sVP, for the 8 chains of the CTA.
-    // s = leapfrog step index; the log-likelihood of chain c is accumulated when s == sSteps[c] - 1.
-    // On return g[] holds grad(v') for this warp's chain and llnew its family log-likelihood (if it was wanted).
-    auto grad_eval = [&](int s) {
-        double bf[KSMAX];
+    // s = leapfrog step index; the log-likelihood of chain c is accumulated when s == sSteps[c] - 1 (with_ll says whether
+    // any chain of the CTA is on its last step).  On return g[] holds grad(v') for this warp's chain and llnew its
+    // family log-likelihood (if this was its last step).
+    auto grad_eval = [&](int s, bool with_ll) {
+        double bf[KS];
 #pragma unroll
-        for (int j = 0; j < KSMAX; j++) bf[j] = (j < ks) ? sVP[fr * ld + 4 * j + fk] : 0.0;
-        double gacc[QT8MAX][2];
+        for (int j = 0; j < KS; j++) bf[j] = sVP[fr * LD + 4 * j + fk];
+        double gacc[QT8][2];
 #pragma unroll
-        for (int i = 0; i < QT8MAX; i++) gacc[i][0] = gacc[i][1] = 0.0;
+        for (int i = 0; i < QT8; i++) gacc[i][0] = gacc[i][1] = 0.0;
         const bool want0 = (s == sSteps[2 * fk] - 1), want1 = (s == sSteps[2 * fk + 1] - 1);
         double ll0 = 0.0, ll1 = 0.0;
-        for (int tile = warp; tile < ntiles; tile += NWARP) {
-            const int r0 = tile * 8;
-            double a0 = 0.0, a1 = 0.0;
-            const double* zr = sZL + (size_t)(r0 + fr) * ld + fk;
-#pragma unroll
-            for (int j = 0; j < KSMAX; j++) if (j < ks) dmma884(a0, a1, zr[4 * j], bf[j]);      // eta tile: rows r0..r0+7 x 8 chains
-            const int row = r0 + fr;
-            const bool ok = row < n;
-            const double xbv = ok ? __ldg(p.xb + row) : 0.0, yv = ok ? __ldg(p.y + row) : 0.0;
-            const double eta0 = xbv + a0, eta1 = xbv + a1;
-            const double res0 = ok ? dev_family_resid<FL>(yv, eta0) : 0.0;
-            const double res1 = ok ? dev_family_resid<FL>(yv, eta1) : 0.0;
-            if (want0 | want1) {
-                const double rc = (FL == 1 && ok) ? __ldg(p.rowc + row) : 0.0;
-                if (want0 && ok) ll0 += dev_family_ll<FL>(yv, eta0, rc, c0, sigma);
-                if (want1 && ok) ll1 += dev_family_ll<FL>(yv, eta1, rc, c0, sigma);
+        int tile = warp;
+        if (!with_ll) {
+            for (; tile + NWARP < nfull; tile += 2 * NWARP) {
+                const int r0[2] = {tile * 8, (tile + NWARP) * 8};
+                fused_tiles<FL, KS, 2, false, false>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                // res is held as C fragment [row = lane/4][chain = 2(lane%4) + {0,1}]; the transposed product needs it as
-                // B fragment [k = row = 4h + lane%4][n = chain = lane/4]
-                const int src = 4 * (4 * h + fk) + (fr >> 1);
-                const double t0 = __shfl_sync(0xffffffffu, res0, src);
-                const double t1 = __shfl_sync(0xffffffffu, res1, src);
-                const double b = (fr & 1) ? t1 : t0;
-                const double* zt = sZL + (size_t)(r0 + 4 * h + fk) * ld + fr;
-#pragma unroll
-                for (int i = 0; i < QT8MAX; i++) if (i < qt8) dmma884(gacc[i][0], gacc[i][1], zt[8 * i], b);
+            for (; tile < nfull; tile += NWARP) {
+                const int r0[1] = {tile * 8};
+                fused_tiles<FL, KS, 1, false, false>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+            }
+            if (has_tail && tile == nfull) {
+                const int r0[1] = {tile * 8};
+                fused_tiles<FL, KS, 1, true, false>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+            }
+        } else {
+            for (; tile < nfull; tile += NWARP) {
+                const int r0[1] = {tile * 8};
+                fused_tiles<FL, KS, 1, false, true>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+            }
+            if (has_tail && tile == nfull) {
+                const int r0[1] = {tile * 8};
+                fused_tiles<FL, KS, 1, true, true>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
         }
         // ---- deterministic cross-warp sum of the partial gradients: warps 4-7 -> slots, warps 0-3 add, then 4-term sums ----
-        ll0 += __shfl_xor_sync(0xffffffffu, ll0, 4);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 4);
-        ll0 += __shfl_xor_sync(0xffffffffu, ll0, 8);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 8);
-        ll0 += __shfl_xor_sync(0xffffffffu, ll0, 16); ll1 += __shfl_xor_sync(0xffffffffu, ll1, 16);
-        if (fr == 0) { sLL[warp * CB + 2 * fk] = ll0; sLL[warp * CB + 2 * fk + 1] = ll1; }
-        double* slot = sSlot + (size_t)(warp & 3) * QP8 * 9;
+        if (with_ll) {
+            ll0 += __shfl_xor_sync(0xffffffffu, ll0, 4);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 4);
+            ll0 += __shfl_xor_sync(0xffffffffu, ll0, 8);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 8);
+            ll0 += __shfl_xor_sync(0xffffffffu, ll0, 16); ll1 += __shfl_xor_sync(0xffffffffu, ll1, 16);
+            if (fr == 0) { sLL[warp * CB + 2 * fk] = ll0; sLL[warp * CB + 2 * fk + 1] = ll1; }
+        }
+        double* slot = sSlot + (warp & 3) * QP8 * 9;
         if (warp >= 4) {
 #pragma unroll
-            for (int i = 0; i < QT8MAX; i++) if (i < qt8) {
+            for (int i = 0; i < QT8; i++) {
                 slot[(8 * i + fr) * 9 + 2 * fk] = gacc[i][0];
                 slot[(8 * i + fr) * 9 + 2 * fk + 1] = gacc[i][1];
             }
@@ -148,7 +201,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         __syncthreads();
         if (warp < 4) {
 #pragma unroll
-            for (int i = 0; i < QT8MAX; i++) if (i < qt8) {
+            for (int i = 0; i < QT8; i++) {
                 slot[(8 * i + fr) * 9 + 2 * fk] += gacc[i][0];
                 slot[(8 * i + fr) * 9 + 2 * fk + 1] += gacc[i][1];
             }
@@ -162,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
                 g[k] = -1.0 * vp[k] + sc * gs;                                  // mcmlmodel.h:163 + :173/:191/:235
             }
         }
-        if (s == steps - 1) {
+        if (with_ll && s == steps - 1) {
             double l = 0.0;
 #pragma unroll
             for (int w = 0; w < NWARP; w++) l += sLL[w * CB + warp];
@@ -171,7 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     };
 
     // gradient and log-likelihood at the initial state (carried over between proposals instead of recomputed, mhmcmc.h:64,82)
-    grad_eval(0);
+    grad_eval(0, true);
 #pragma unroll
     for (int k = 0; k < QT32; k++) gc[k] = g[k];
     llcur = llnew;
@@ -197,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
                 k0 += z * z;
                 r[k] = z + (eps / 2) * gc[k];                                                       // :74 (first step)
                 vp[k] = v[k] + eps * r[k];                                                          // :67, :75
-                sVP[warp * ld + q] = vp[k];
+                sVP[warp * LD + q] = vp[k];
             }
         }
         k0 = 0.5 * warp_sum(k0);                                                                    // :66
@@ -210,12 +263,12 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
             if (lane == 0) sSteps[warp] = steps;
         }
         __syncthreads();
-        int smax = 1;
+        int smax = 1, smin = 1 << 30;
 #pragma unroll
-        for (int w = 0; w < CB; w++) smax = max(smax, sSteps[w]);
+        for (int w = 0; w < CB; w++) { smax = max(smax, sSteps[w]); smin = min(smin, sSteps[w]); }
         // ---- leapfrog integrator, :73-78 ----
         for (int s = 0; s < smax; s++) {
-            grad_eval(s);
+            grad_eval(s, s >= smin - 1);
             if (s < steps) {
 #pragma unroll
                 for (int k = 0; k < QT32; k++) {
@@ -225,7 +278,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
                         if (s < steps - 1) {
                             rr = rr + (eps / 2) * g[k];                                             // :74 of the next step
                             vp[k] = vp[k] + eps * rr;                                               // :75
-                            sVP[warp * ld + q] = vp[k];
+                            sVP[warp * LD + q] = vp[k];
                         }
                         r[k] = rr;
                     }
@@ -279,7 +332,8 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     }
 }
 
-size_t fused_smem_bytes(int n8, int ld, int qt8) {
+size_t fused_smem_bytes(int n8, int ld) {
+    const int qt8 = (ld / 4 + 1) / 2;
     return sizeof(double) * ((size_t)n8 * ld + 8 + (size_t)CB * ld + (size_t)4 * qt8 * 8 * 9 + NWARP * CB) + sizeof(int) * CB + 16;
 }
 
@@ -289,9 +343,9 @@ int fused_ld(int Q) {
     return l;
 }
 
-template <int FL, int KSMAX>
+template <int FL, int KS>
 int launch_fused(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
-    auto kern = hmc_fused_kernel<FL, KSMAX>;
+    auto kern = hmc_fused_kernel<FL, KS>;
     GMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ctas = (p.C + CB - 1) / CB;
     kern<<<ctas, THREADS, smem, ctx->stream>>>(p);
@@ -302,10 +356,18 @@ int launch_fused(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
 
 template <int FL>
 int launch_fused_ks(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
-    if (p.ks <= 5) return launch_fused<FL, 5>(ctx, p, smem);
-    if (p.ks <= 13) return launch_fused<FL, 13>(ctx, p, smem);
-    if (p.ks <= 21) return launch_fused<FL, 21>(ctx, p, smem);
-    return launch_fused<FL, 33>(ctx, p, smem);
+    switch (p.ks) {      // ld / 4; ld = 4 (mod 16)
+    case 1: return launch_fused<FL, 1>(ctx, p, smem);
+    case 5: return launch_fused<FL, 5>(ctx, p, smem);
+    case 9: return launch_fused<FL, 9>(ctx, p, smem);
+    case 13: return launch_fused<FL, 13>(ctx, p, smem);
+    case 17: return launch_fused<FL, 17>(ctx, p, smem);
+    case 21: return launch_fused<FL, 21>(ctx, p, smem);
+    case 25: return launch_fused<FL, 25>(ctx, p, smem);
+    case 29: return launch_fused<FL, 29>(ctx, p, smem);
+    case 33: return launch_fused<FL, 33>(ctx, p, smem);
+    }
+    return gmb_set_error(GMB_EINVAL, "no on-chip sampler instantiation for Q = %d", p.Q);
 }
 
 }  // namespace
@@ -314,8 +376,8 @@ int launch_fused_ks(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
 bool gmb_hmc_fused_applicable(const gmb_model* mdl) {
     const int ld = fused_ld(mdl->Q);
     if (ld / 4 > 33) return false;
-    const int n8 = (mdl->n + 7) / 8 * 8, qt8 = (mdl->Q + 7) / 8;
-    return fused_smem_bytes(n8, ld, qt8) <= (size_t)227 * 1024;
+    const int n8 = (mdl->n + 7) / 8 * 8;
+    return fused_smem_bytes(n8, ld) <= (size_t)227 * 1024;
 }
 
 // Same contract as the two-GEMM hmc_run of hmc.cu: dV_out is ldq x (C * (nsamp + 1)) chain-major, d_cs is FS_COUNT x C.
@@ -329,7 +391,7 @@ int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, dou
     p.var_par = var_par; p.lambda = lambda; p.target_accept = target_accept;
     p.warmup = warmup; p.nsamp = nsamp; p.max_steps = max_steps; p.adapt = adapt; p.C = C;
     p.chain_offset = chain_offset; p.seed = seed; p.dV_out = dV_out; p.cs_out = d_cs;
-    const size_t smem = fused_smem_bytes(p.n8, p.ld, p.qt8);
+    const size_t smem = fused_smem_bytes(p.n8, p.ld);
     switch (mdl->flink) {
     case 1: return launch_fused_ks<1>(ctx, p, smem);
     case 3: return launch_fused_ks<3>(ctx, p, smem);
