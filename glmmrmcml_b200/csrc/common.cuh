@@ -232,9 +232,9 @@ __device__ __forceinline__ double dev_log_factorial_approx(double n) {
 template <int FL>
 __device__ __forceinline__ double dev_family_ll(double y, double eta, double rowc, double c0, double sigma) {
     if (FL == 1) {
-        return y * eta - dev_exp(eta) - rowc;
+        return y * eta - exp(eta) - rowc;
     } else if (FL == 3) {
-        double p = 1.0 / (1.0 + dev_exp(-1.0 * eta));
+        double p = 1.0 / (1.0 + exp(-1.0 * eta));
         double r = 0.0;
         if (y == 1.0) r = log(p);
         else if (y == 0.0) r = log(1.0 - p);
@@ -246,10 +246,15 @@ __device__ __forceinline__ double dev_family_ll(double y, double eta, double row
 }
 
 // gradient residual r(eta) of mcmlmodel.h:170-175 (FL 1), :184-193 (FL 3), :233-238 (FL 7, without the 1/sigma^2)
-template <int FL>
+template <int FL, bool FAST = false>
 __device__ __forceinline__ double dev_family_resid(double y, double eta) {
-    if (FL == 1) return y - dev_exp(eta);
-    if (FL == 3) return __drcp_rn(dev_exp(eta) + 1.0) + y - 1.0;
+    if (FAST) {
+        if (FL == 1) return y - dev_exp(eta);
+        if (FL == 3) return __drcp_rn(dev_exp(eta) + 1.0) + y - 1.0;
+    } else {
+        if (FL == 1) return y - exp(eta);
+        if (FL == 3) return 1.0 / (exp(eta) + 1.0) + y - 1.0;
+    }
     return y - eta;
 }
 

@@ -48,10 +48,10 @@ template <int FL>
 __device__ __forceinline__ void ll_accum(const RowTerm<FL>& r, double z, double c0, double inv_sigma, double& acc, double& prod) {
     const double eta = r.xb + z;                                     // mcmlmodel.h:298
     if (FL == 1) {
-        acc += r.y * eta - dev_exp(eta) - r.rowc;                        // moremaths.h:33-40
+        acc += r.y * eta - exp(eta) - r.rowc;                        // moremaths.h:33-40
     } else if (FL == 3) {
         const double x = r.sg * eta;
-        const double t = fma(fabs(r.sg), dev_exp(x), 1.0);        // |sg| = 0 drops rows whose y is neither 0 nor 1
+        const double t = fma(fabs(r.sg), exp(x), 1.0);        // |sg| = 0 drops rows whose y is neither 0 nor 1
         if (x > LOGIT_PROD_GUARD) acc -= log(t);                     // rare: keep the product finite
         else prod *= t;
     } else {
@@ -158,11 +158,11 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
 template <int FL>
 __device__ __forceinline__ void mcnr_terms(double y, double eta, double inv_phi, double& w, double& wu, double& r) {
     if (FL == 1) {               // poisson/log : dhdmu = exp(-eta), detadmu = exp(-eta)
-        double mu = dev_exp(eta);
+        double mu = exp(eta);
         r = y - mu; w = mu; wu = r;
     } else if (FL == 3) {        // binomial/logit : dhdmu = detadmu = 1/(p(1-p))
-        double e = dev_exp(eta);
-        double p = e * __drcp_rn(1.0 + e);
+        double e = exp(eta);
+        double p = e / (1.0 + e);
         r = y - p; w = p * (1.0 - p); wu = r;
     } else {                     // gaussian/identity : W = 1/sigma^2
         r = y - eta; w = inv_phi; wu = inv_phi * r;

@@ -16,6 +16,7 @@
 // the A-fragment reads of the forward product (8 rows x 4 k) and of the transposed product (4 rows x 8 q) conflict
 // free.  The variant applies when 8 n ld + 20 KB fits; larger models take the two-GEMM path.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -42,7 +43,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // Gradient contributions of `NT` (1 or 2) tiles of 8 observations, rows r0[t] .. r0[t]+7, for the 8 chains of the CTA.
 // MASK: rows >= n exist in the tile (only the last tile of a model whose n is not a multiple of 8).
 // LL: also accumulate the family log-likelihood of the chains that are on their last leapfrog step.
-template <int FL, int KS, int NT, bool MASK, bool LL>
+template <int FL, int KS, int NT, bool MASK, bool LL, bool FASTEXP>
 __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, const double (&bf)[KS], const int (&r0)[NT], int n,
                                             const double* __restrict__ xb, const double* __restrict__ y, const double* __restrict__ rowc,
                                             double c0, double sigma, bool want0, bool want1, int fr, int fk,
@@ -66,8 +67,8 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
 #pragma unroll
     for (int t = 0; t < NT; t++) {
         const double eta0 = xbv[t] + a[t][0], eta1 = xbv[t] + a[t][1];
-        res[t][0] = dev_family_resid<FL>(yv[t], eta0);
-        res[t][1] = dev_family_resid<FL>(yv[t], eta1);
+        res[t][0] = dev_family_resid<FL, FASTEXP>(yv[t], eta0);
+        res[t][1] = dev_family_resid<FL, FASTEXP>(yv[t], eta1);
         if (MASK) { const bool ok = r0[t] + fr < n; if (!ok) { res[t][0] = 0.0; res[t][1] = 0.0; } }
         if (LL) {
             const bool ok = !MASK || r0[t] + fr < n;
@@ -93,8 +94,9 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
         }
 }
 
-template <int FL, int KS>
+template <int FL, int KS, int TUNE>
 __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams p) {
+    constexpr bool FASTEXP = (TUNE & 1) != 0, PAIR = (TUNE & 2) != 0;
     constexpr int LD = 4 * KS;                       // row stride of the Z L tile; KS = 1 (mod 4) makes it 4 (mod 16)
     constexpr int QT8 = (KS + 1) / 2;                // 8-row tiles of the gradient
     constexpr int QP8 = QT8 * 8;
@@ -161,26 +163,26 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         double ll0 = 0.0, ll1 = 0.0;
         int tile = warp;
         if (!with_ll) {
-            for (; tile + NWARP < nfull; tile += 2 * NWARP) {
+            if (PAIR) for (; tile + NWARP < nfull; tile += 2 * NWARP) {
                 const int r0[2] = {tile * 8, (tile + NWARP) * 8};
-                fused_tiles<FL, KS, 2, false, false>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 2, false, false, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
             for (; tile < nfull; tile += NWARP) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, false>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, false, false, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
             if (has_tail && tile == nfull) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, false>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, true, false, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
         } else {
             for (; tile < nfull; tile += NWARP) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, true>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, false, true, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
             if (has_tail && tile == nfull) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, true>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, true, true, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
         }
         // ---- deterministic cross-warp sum of the partial gradients: warps 4-7 -> slots, warps 0-3 add, then 4-term sums ----
@@ -263,12 +265,15 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
             if (lane == 0) sSteps[warp] = steps;
         }
         __syncthreads();
-        int smax = 1, smin = 1 << 30;
+        int smax = 1, stc[CB];
 #pragma unroll
-        for (int w = 0; w < CB; w++) { smax = max(smax, sSteps[w]); smin = min(smin, sSteps[w]); }
+        for (int w = 0; w < CB; w++) { stc[w] = sSteps[w]; smax = max(smax, stc[w]); }
         // ---- leapfrog integrator, :73-78 ----
         for (int s = 0; s < smax; s++) {
-            grad_eval(s, s >= smin - 1);
+            bool any_last = false;                      // is any chain of the CTA on its last step (needs its log-likelihood)?
+#pragma unroll
+            for (int w = 0; w < CB; w++) any_last |= (s == stc[w] - 1);
+            grad_eval(s, any_last);
             if (s < steps) {
 #pragma unroll
                 for (int k = 0; k < QT32; k++) {
@@ -343,9 +348,32 @@ int fused_ld(int Q) {
     return l;
 }
 
+static int fused_tune() {
+    static int t = -1;
+    if (t < 0) { const char* e = getenv("GMB_FUSED_TUNE"); t = e ? atoi(e) & 3 : 2; }
+    return t;
+}
+
+template <int FL, int KS, int TUNE>
+int launch_fused_t(gmb_ctx* ctx, const FusedParams& p, size_t smem);
+
 template <int FL, int KS>
 int launch_fused(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
-    auto kern = hmc_fused_kernel<FL, KS>;
+#ifdef GMB_FUSED_TUNING
+    if (KS == 13 && FL == 3) {
+        switch (fused_tune()) {
+        case 0: return launch_fused_t<FL, KS, 0>(ctx, p, smem);
+        case 1: return launch_fused_t<FL, KS, 1>(ctx, p, smem);
+        case 2: return launch_fused_t<FL, KS, 2>(ctx, p, smem);
+        }
+    }
+#endif
+    return launch_fused_t<FL, KS, 2>(ctx, p, smem);   // library exp + tile pairs: fastest of the four measured variants
+}
+
+template <int FL, int KS, int TUNE>
+int launch_fused_t(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
+    auto kern = hmc_fused_kernel<FL, KS, TUNE>;
     GMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ctas = (p.C + CB - 1) / CB;
     kern<<<ctas, THREADS, smem, ctx->stream>>>(p);
