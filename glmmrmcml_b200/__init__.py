@@ -270,11 +270,16 @@ def _fixed_u(cov, data, eff_range, Z, X, y, u, family, link):
     return keep, cargs + [_d(Z), _d(X), _d(y), _d(u), n, P, Q, u.shape[1], family.encode(), link.encode()], (n, P, Q, u.shape[1])
 
 
+def cov_shape(cov):
+    """(B, Q, R): blocks, total dimension and number of covariance parameters of a cov matrix (gmb_cov_shape)."""
+    cov = np.asfortranarray(np.asarray(cov, dtype=np.int32).reshape(-1, 5))
+    B, Q, R = C.c_int(), C.c_int(), C.c_int()
+    check(lib().gmb_cov_shape(cov.ctypes.data_as(_lib.ip), cov.shape[0], C.byref(B), C.byref(Q), C.byref(R)))
+    return B.value, Q.value, R.value
+
+
 def _cov_R(cov):
-    """number of covariance parameters implied by the cov matrix (DData::n_cov_pars)."""
-    npar = {1: 1, 2: 1, 3: 1, 4: 2, 5: 2, 6: 1, 7: 2, 8: 2, 9: 2, 10: 2, 11: 2, 12: 2, 13: 2, 14: 1}   # R/R6ModelExtMCML.R:430
-    cov = np.asarray(cov, dtype=np.int64).reshape(-1, 5)
-    return int(max(int(r[4]) + npar.get(int(r[2]), 1) for r in cov))
+    return cov_shape(cov)[2]
 
 
 def mvn_ll(cov, data, eff_range, gamma, u) -> float:
@@ -282,7 +287,7 @@ def mvn_ll(cov, data, eff_range, gamma, u) -> float:
     keep, cargs = _covargs(cov, data, eff_range)
     gamma = _v(gamma)
     u = np.asarray(u, dtype=np.float64)
-    Q = int(sum({int(r[0]): int(r[1]) for r in keep[0]}.values()))     # sum of the block dimensions
+    Q = cov_shape(cov)[1]
     u = _f(u.reshape(Q, -1))
     out = C.c_double()
     check(lib().gmb_mvn_ll(*cargs, _d(gamma), gamma.size, _d(u), Q, u.shape[1], C.byref(out)))
@@ -350,6 +355,42 @@ def mcml_full(cov, data, eff_range, Z, X, y, family, link, start, mcnr=False, m=
                               int(trace), int(refresh), int(maxsteps), float(target_accept), int(n_chains), int(seed),
                               _d(beta), _d(theta), C.byref(sigma), C.byref(conv), C.byref(it), _d(u)))
     return dict(beta=beta, theta=theta, sigma=sigma.value, converged=bool(conv.value), iter=it.value, u=u)
+
+
+def _wrap_objective(fun, n):
+    """fun maps an (n, k) array of points to k values; returns the ctypes callback (keep a reference while in use)."""
+    def cb(Xp, n_, k, fp, _user):
+        try:
+            X = np.ctypeslib.as_array(Xp, shape=(k, n_)).T            # columns are points
+            f = np.asarray(fun(X), dtype=np.float64).reshape(k)
+            np.ctypeslib.as_array(fp, shape=(k,))[:] = f
+            return 0
+        except Exception:                                            # never let an exception cross the C boundary
+            return _lib.GMB_EINVAL
+    return _lib.OBJECTIVE(cb)
+
+
+def minimize_bounded(fun, x0, lower=None, upper=None, rhobeg=0.0, xtol=1e-8, maxit=200):
+    """gmb_minimize_bounded: batched projected-BFGS stand-in for rminqa's BOBYQA.  fun: (n, k) points -> k values."""
+    x = _v(x0).copy(); n = x.size
+    lo = _v(lower) if lower is not None else None
+    up = _v(upper) if upper is not None else None
+    cb = _wrap_objective(fun, n)
+    fmin = C.c_double(); nfev = C.c_int()
+    check(lib().gmb_minimize_bounded(cb, None, n, _d(x), _d(lo), _d(up), float(rhobeg), float(xtol), int(maxit), C.byref(fmin), C.byref(nfev)))
+    return dict(x=x, fun=fmin.value, nfev=nfev.value)
+
+
+def fd_hessian(fun, x, ndeps, lower=None, upper=None, usebounds=False):
+    """gmb_fd_hessian: the optimhess stencil (4 n^2 points evaluated as one batch)."""
+    x = _v(x); n = x.size
+    nd = _v(np.broadcast_to(np.asarray(ndeps, dtype=np.float64), (n,)))
+    lo = _v(lower) if lower is not None else None
+    up = _v(upper) if upper is not None else None
+    cb = _wrap_objective(fun, n)
+    H = np.zeros((n, n), order="F"); nfev = C.c_int()
+    check(lib().gmb_fd_hessian(cb, None, n, _d(x), _d(nd), _d(lo), _d(up), int(bool(usebounds)), _d(H), C.byref(nfev)))
+    return H, nfev.value
 
 
 class ModelMCML:

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "gmb_hmc_set_variant": (C.c_int, [C.c_int]),
     "gmb_model_logprob_grad": (C.c_int, [vp, dp, dp, C.c_double, dp, C.c_int, dp, dp]),
     "gmb_set_default_ctx": (C.c_int, [vp]),
+    "gmb_cov_shape": (C.c_int, [ip, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gmb_mvn_ll": (C.c_int, _cov_args + [dp, C.c_int, dp, C.c_int, C.c_int, dp]),
     "gmb_mcmc_sample": (C.c_int, [dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
                                   C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64, dp]),
@@ -82,6 +83,13 @@ PROTOTYPES = {
                                             C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64,
                                             dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp]),
 }
+
+OBJECTIVE = C.CFUNCTYPE(C.c_int, dp, C.c_int, C.c_int, dp, C.c_void_p)
+PROTOTYPES.update({
+    "gmb_minimize_bounded": (C.c_int, [OBJECTIVE, C.c_void_p, C.c_int, dp, dp, dp, C.c_double, C.c_double, C.c_int, dp, C.POINTER(C.c_int)]),
+    "gmb_fd_gradient": (C.c_int, [OBJECTIVE, C.c_void_p, C.c_int, dp, dp, dp, dp, C.c_int, dp]),
+    "gmb_fd_hessian": (C.c_int, [OBJECTIVE, C.c_void_p, C.c_int, dp, dp, dp, dp, C.c_int, dp, C.POINTER(C.c_int)]),
+})
 
 _LIB = None
 

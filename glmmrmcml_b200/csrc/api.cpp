@@ -204,6 +204,28 @@ int default_chains(int m) {
 
 }  // namespace
 
+// DData::n_cov_pars() and the total block dimension from the cov matrix alone (host arithmetic; lets an adapter size
+// its theta output before calling an entry point).  Parameter counts per function id: R/R6ModelExtMCML.R:430.
+extern "C" int gmb_cov_shape(const int32_t* cov, int rows, int* B_out, int* Q_out, int* R_out) {
+    if (!cov || rows <= 0) return gmb_set_error(GMB_EINVAL, "gmb_cov_shape: bad arguments");
+    static const int np[15] = {0, 1, 1, 1, 2, 2, 1, 2, 2, 2, 2, 2, 2, 2, 1};
+    int B = 0, R = 0;
+    for (int r = 0; r < rows; r++) {
+        const int b = cov[r], id = cov[r + 2 * rows], p0 = cov[r + 4 * rows];
+        if (b < 0 || id < 1 || id > 14 || p0 < 0) return gmb_set_error(GMB_EINVAL, "bad covariance row %d", r);
+        if (b + 1 > B) B = b + 1;
+        if (p0 + np[id] > R) R = p0 + np[id];
+    }
+    std::vector<int> dim(B, 0);
+    for (int r = 0; r < rows; r++) dim[cov[r]] = cov[r + rows];
+    long long Q = 0;
+    for (int b = 0; b < B; b++) { if (dim[b] <= 0) return gmb_set_error(GMB_EINVAL, "block ids must be 0..B-1 without gaps"); Q += dim[b]; }
+    if (B_out) *B_out = B;
+    if (Q_out) *Q_out = (int)Q;
+    if (R_out) *R_out = R;
+    return GMB_OK;
+}
+
 extern "C" int gmb_set_default_ctx(gmb_ctx* ctx) {
     if (g_default_ctx && g_default_owned && g_default_ctx != ctx) gmb_ctx_destroy(g_default_ctx);
     g_default_ctx = ctx; g_default_owned = false;

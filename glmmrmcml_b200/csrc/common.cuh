@@ -141,14 +141,7 @@ int gmb_solve_small(int P, const double* A, const double* b, double* x);
 // hmc.cu
 int gmb_hmc_prepare(gmb_model* mdl, const double* L_host);   // uploads L and forms ZL = Z L
 
-// optim.cpp — batched objective: evaluates k points (columns of X, n x k) into f[k]; returns a GMB_* code
-typedef int (*gmb_objective_batch)(const double* X, int n, int k, double* f, void* user);
-int gmb_minimize_bounded(gmb_objective_batch f, void* user, int n, double* x, const double* lower, const double* upper,
-                         double rhobeg, double xtol, int maxit, double* fmin, int* nfev);
-int gmb_fd_gradient(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
-                    const double* lower, const double* upper, int usebounds, double* grad);
-int gmb_fd_hessian(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
-                   const double* lower, const double* upper, int usebounds, double* hess, int* nfev);
+// optim.cpp: gmb_minimize_bounded / gmb_fd_gradient / gmb_fd_hessian are declared in the public header
 
 // ------------------------------------------------------------------------------------------------
 // device helpers

@@ -52,7 +52,7 @@ bool fd_gradient(Evaluator& ev, const std::vector<double>& x, const std::vector<
 
 // Minimises f over the box [lower, upper] (either may be NULL = unbounded; entries may be +-inf).
 // Projected BFGS on batched central-difference gradients with a batched line search.
-int gmb_minimize_bounded(gmb_objective_batch f, void* user, int n, double* x_io, const double* lower, const double* upper,
+extern "C" int gmb_minimize_bounded(gmb_objective_batch f, void* user, int n, double* x_io, const double* lower, const double* upper,
                          double rhobeg, double xtol, int maxit, double* fmin, int* nfev) {
     if (n <= 0) return gmb_set_error(GMB_EINVAL, "gmb_minimize_bounded: n must be positive");
     Evaluator ev{f, user, n};
@@ -146,7 +146,7 @@ int gmb_minimize_bounded(gmb_objective_batch f, void* user, int n, double* x_io,
 }
 
 // Gradient by bounded central differences (rminqa Functor::Gradient as used by mcmloptim::f_grad, mcmloptim.h:296-317).
-int gmb_fd_gradient(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
+extern "C" int gmb_fd_gradient(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
                     const double* lower, const double* upper, int usebounds, double* grad) {
     Evaluator ev{f, user, n};
     std::vector<double> xv(x, x + n), h(ndeps, ndeps + n), g;
@@ -159,7 +159,7 @@ int gmb_fd_gradient(gmb_objective_batch f, void* user, int n, const double* x, c
 // optimhess stencil (R's optim.c optimhess; rminqa Functor::Hessian as used by mcmloptim::f_hess, mcmloptim.h:333-355):
 //   H[i, .] = (Gradient(x + e_i h_i) - Gradient(x - e_i h_i)) / (2 h_i), Gradient = bounded central differences with the
 //   same steps; then H <- (H + H^T)/2.  All 4 n^2 points are evaluated in one batch.  hess is n x n column-major.
-int gmb_fd_hessian(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
+extern "C" int gmb_fd_hessian(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
                    const double* lower, const double* upper, int usebounds, double* hess, int* nfev) {
     if (n <= 0) return gmb_set_error(GMB_EINVAL, "gmb_fd_hessian: n must be positive");
     Evaluator ev{f, user, n};

@@ -144,11 +144,30 @@ int gmb_hmc_set_variant(int variant);
 int gmb_model_logprob_grad(gmb_model* mdl, const double* L, const double* beta, double var_par,
                            const double* V, int C, double* lp, double* grad);
 
+/* ---- host-side optimiser and finite-difference stencils: stand in for rminqa (Rbobyqa, Functor::Gradient/Hessian;
+ * call sites mcmloptim.h:58-66,73-85,93-109,300-304,335-352).  The objective is BATCHED: it receives k points (columns of
+ * X, n x k) and fills f[k], so that a GPU objective costs one synchronisation per batch instead of one per point.
+ * It returns GMB_OK or an error code, which aborts the optimisation.  These three functions run on the host only. */
+typedef int (*gmb_objective_batch)(const double* X, int n, int k, double* f, void* user);
+/* Minimises f over [lower, upper] (NULL = unbounded) by projected BFGS on batched central-difference gradients.
+ * rhobeg <= 0 selects BOBYQA's default min(0.95, 0.2 max|x0|).  x is updated in place. */
+int gmb_minimize_bounded(gmb_objective_batch f, void* user, int n, double* x, const double* lower, const double* upper,
+                         double rhobeg, double xtol, int maxit, double* fmin, int* nfev);
+/* Bounded central differences with steps ndeps (rminqa Functor::Gradient, mcmloptim.h:296-317). */
+int gmb_fd_gradient(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
+                    const double* lower, const double* upper, int usebounds, double* grad);
+/* optimhess stencil, 4 n^2 points in one batch (rminqa Functor::Hessian, mcmloptim.h:333-355); hess is n x n. */
+int gmb_fd_hessian(gmb_objective_batch f, void* user, int n, const double* x, const double* ndeps,
+                   const double* lower, const double* upper, int usebounds, double* hess, int* nfev);
+
 /* ---- reference-named entry points (what the Rcpp exports forward to) -----------------------------------
  * These run on the process-wide default context: created lazily on the current CUDA device, or installed with
  * gmb_set_default_ctx (e.g. a context that gmb_comm_init joined to an NCCL communicator, so that mcml_full shards its
  * chains over the ranks).  The library does not take ownership of an installed context. */
 int gmb_set_default_ctx(gmb_ctx* ctx);
+/* Number of blocks B, total dimension Q and number of covariance parameters R (DData::n_cov_pars(), mcmloptim.h:26) of a
+ * cov matrix; host arithmetic only, so adapters can size their outputs before calling an entry point. */
+int gmb_cov_shape(const int32_t* cov, int rows, int* B, int* Q, int* R);
 
 /* mvn_ll, src/mcml_optim.cpp:406-414 */
 int gmb_mvn_ll(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
