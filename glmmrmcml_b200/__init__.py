@@ -44,6 +44,11 @@ def hmc_set_variant(variant: int):
     check(lib().gmb_hmc_set_variant(int(variant)))
 
 
+def hmc_set_cluster_size(cs: int):
+    """On-chip sampler: 0 = automatic, 1 / 2 / 4 = CTAs (SMs) per group of 8 chains (see gmb_hmc_set_cluster_size)."""
+    check(lib().gmb_hmc_set_cluster_size(int(cs)))
+
+
 def version() -> str:
     return lib().gmb_version().decode()
 

@@ -340,7 +340,7 @@ static int hmc_run(gmb_model* mdl, double var_par, int warmup, int nsamp, double
 }
 
 // hmc_fused.cu
-bool gmb_hmc_fused_applicable(const gmb_model* mdl);
+bool gmb_hmc_fused_applicable(const gmb_model* mdl, int C);
 int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                       int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs);
 
@@ -413,7 +413,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     }
     std::vector<double> hcs;
     float ms = 0.f;
-    const bool fits = gmb_hmc_fused_applicable(mdl);
+    const bool fits = gmb_hmc_fused_applicable(mdl, C);
     if (g_hmc_variant == 2 && !fits) return gmb_set_error(GMB_EINVAL, "the on-chip sampler variant was forced but Z L (%d x %d) does not fit in shared memory", mdl->n, mdl->Q);
     if (fits && g_hmc_variant != 1)
         GMB_TRY(hmc_run_fused_timed(mdl, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,

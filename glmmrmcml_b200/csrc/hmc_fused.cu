@@ -1,346 +1,12 @@
-// hmc_fused.cu — on-chip variant of the batched random-effect sampler (mhmcmc.h:16-160): ONE launch runs the whole
-// sample(warmup, nsamp) call of 8 chains per CTA, with Z L resident in shared memory.
-//
-// Per leapfrog step the CTA makes a SINGLE pass over its Z L tile for all 8 chains (mcmlmodel.h:156-279):
-//   for every tile of 8 observations (one warp each, tiles interleaved over the 8 warps)
-//     eta  = xb + (Z L) v'            DMMA m8n8k4, A = Z L rows from shared memory, B = v' fragments in registers
-//     res  = r(eta)                   family residual in the accumulator registers (+ log-likelihood on the last step)
-//     G   += (Z L)^T res              DMMA m8n8k4 again: the SAME shared-memory rows read transposed, res moved from
-//                                     accumulator to B-fragment layout with warp shuffles
-// so eta and res never exist in memory, Z L is read from shared memory only, and the two contractions of the
-// two-GEMM variant (hmc.cu) plus their epilogues become one loop.  The per-warp partial gradients are summed in a
-// fixed order through shared memory (deterministic), then warp c advances chain c: leapfrog update (mhmcmc.h:73-78),
-// Metropolis test (:80-105) and dual-averaging step size (:107-117), all in registers.
-//
-// Shared-memory budget (227 KB): Z L is stored row-major with a row stride ld = 4 (mod 16) doubles, which makes both
-// the A-fragment reads of the forward product (8 rows x 4 k) and of the transposed product (4 rows x 8 q) conflict
-// free.  The variant applies when 8 n ld + 20 KB fits; larger models take the two-GEMM path.
-#include "common.cuh"
-#include <cstdlib>
+// hmc_fused.cu — host side of the on-chip sampler (kernel: hmc_fused.cuh; instantiated per family in hmc_fused_fl{1,3,7}.cu
+// so that the three families compile in parallel).
+#include "hmc_fused.cuh"
+
+int gmb_fused_launch_fl1(gmb_ctx* ctx, const FusedParams& p, size_t smem, int cs);
+int gmb_fused_launch_fl3(gmb_ctx* ctx, const FusedParams& p, size_t smem, int cs);
+int gmb_fused_launch_fl7(gmb_ctx* ctx, const FusedParams& p, size_t smem, int cs);
 
 namespace {
-
-constexpr int CB = 8;          // chains per CTA = one MMA n-tile; warp w owns the state of chain w
-constexpr int NWARP = 8;
-constexpr int THREADS = NWARP * 32;
-
-enum { FS_EPS = 0, FS_EBAR, FS_H, FS_LLCUR, FS_K0, FS_ACCEPT, FS_TOTSTEPS, FS_LASTPROB, FS_COUNT };   // = CS_* of hmc.cu
-
-struct FusedParams {
-    int n, Q, ld, ks, qt8, ldn, ldq, n8;
-    const double* ZL; const double* xb; const double* y; const double* rowc;
-    double var_par, lambda, target_accept;
-    int warmup, nsamp, max_steps, adapt, C;
-    uint32_t chain_offset; unsigned long long seed;
-    double* dV_out; double* cs_out;
-};
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-// Gradient contributions of `NT` (1 or 2) tiles of 8 observations, rows r0[t] .. r0[t]+7, for the 8 chains of the CTA.
-// MASK: rows >= n exist in the tile (only the last tile of a model whose n is not a multiple of 8).
-// LL: also accumulate the family log-likelihood of the chains that are on their last leapfrog step.
-template <int FL, int KS, int NT, bool MASK, bool LL, bool FASTEXP>
-__device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, const double (&bf)[KS], const int (&r0)[NT], int n,
-                                            const double* __restrict__ xb, const double* __restrict__ y, const double* __restrict__ rowc,
-                                            double c0, double sigma, bool want0, bool want1, int fr, int fk,
-                                            double (&gacc)[(KS + 1) / 2][2], double& ll0, double& ll1) {
-    constexpr int LD = 4 * KS, QT8 = (KS + 1) / 2;
-    double a[NT][2], xbv[NT], yv[NT];
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-        const int row = r0[t] + fr;
-        const bool ok = !MASK || row < n;
-        xbv[t] = ok ? __ldg(xb + row) : 0.0;
-        yv[t] = ok ? __ldg(y + row) : 0.0;
-        a[t][0] = a[t][1] = 0.0;
-    }
-    // eta tiles: rows x 8 chains; NT independent accumulator chains
-#pragma unroll
-    for (int j = 0; j < KS; j++)
-#pragma unroll
-        for (int t = 0; t < NT; t++) dmma884(a[t][0], a[t][1], sZL[(r0[t] + fr) * LD + 4 * j + fk], bf[j]);
-    double res[NT][2];
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-        const double eta0 = xbv[t] + a[t][0], eta1 = xbv[t] + a[t][1];
-        res[t][0] = dev_family_resid<FL, FASTEXP>(yv[t], eta0);
-        res[t][1] = dev_family_resid<FL, FASTEXP>(yv[t], eta1);
-        if (MASK) { const bool ok = r0[t] + fr < n; if (!ok) { res[t][0] = 0.0; res[t][1] = 0.0; } }
-        if (LL) {
-            const bool ok = !MASK || r0[t] + fr < n;
-            const double rc = (FL == 1 && ok) ? __ldg(rowc + r0[t] + fr) : 0.0;
-            const double l0 = dev_family_ll<FL>(yv[t], eta0, rc, c0, sigma), l1 = dev_family_ll<FL>(yv[t], eta1, rc, c0, sigma);
-            if (want0 && ok) ll0 += l0;
-            if (want1 && ok) ll1 += l1;
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < NT; t++)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            // res is held as C fragment [row = lane/4][chain = 2(lane%4) + {0,1}]; the transposed product needs it as
-            // B fragment [k = row = 4h + lane%4][n = chain = lane/4]
-            const int src = 4 * (4 * h + fk) + (fr >> 1);
-            const double t0 = __shfl_sync(0xffffffffu, res[t][0], src);
-            const double t1 = __shfl_sync(0xffffffffu, res[t][1], src);
-            const double b = (fr & 1) ? t1 : t0;
-            const double* zt = sZL + (r0[t] + 4 * h + fk) * LD + fr;
-#pragma unroll
-            for (int i = 0; i < QT8; i++) dmma884(gacc[i][0], gacc[i][1], zt[8 * i], b);
-        }
-}
-
-template <int FL, int KS, int TUNE>
-__global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams p) {
-    constexpr bool FASTEXP = (TUNE & 1) != 0, PAIR = (TUNE & 2) != 0;
-    constexpr int LD = 4 * KS;                       // row stride of the Z L tile; KS = 1 (mod 4) makes it 4 (mod 16)
-    constexpr int QT8 = (KS + 1) / 2;                // 8-row tiles of the gradient
-    constexpr int QP8 = QT8 * 8;
-    constexpr int QT32 = (KS * 4 + 31) / 32;         // state elements per lane
-    extern __shared__ __align__(16) double sm[];
-    const int n = p.n, Q = p.Q;
-    double* sZL = sm;                                 // n8 x LD (+8 spill-over doubles for the padded q-tile reads)
-    double* sVP = sZL + (size_t)p.n8 * LD + 8;        // [chain][LD]
-    double* sSlot = sVP + CB * LD;                    // [4][QP8][9]
-    double* sLL = sSlot + 4 * QP8 * 9;                // [NWARP][CB]
-    int* sSteps = reinterpret_cast<int*>(sLL + NWARP * CB);   // [CB]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int fr = lane >> 2, fk = lane & 3;
-    const int chain = blockIdx.x * CB + warp;         // chain whose state this warp owns (local index, < C if live)
-    const bool live = chain < p.C;
-    const uint32_t gchain = p.chain_offset + (uint32_t)chain;
-
-    // ---- stage Z L (global: n x Q column-major) into shared memory, row-major, zero padded ----
-    for (int idx = tid; idx < p.n8 * LD + 8; idx += THREADS) sZL[idx] = 0.0;
-    for (int idx = tid; idx < CB * LD; idx += THREADS) sVP[idx] = 0.0;
-    __syncthreads();
-    for (int idx = tid; idx < n * Q; idx += THREADS) {
-        const int row = idx % n, q = idx / n;
-        sZL[(size_t)row * LD + q] = p.ZL[row + (size_t)q * p.ldn];
-    }
-
-    const double sigma = p.var_par;
-    const double sc = (FL == 7) ? 1.0 / (sigma * sigma) : 1.0;
-    const double c0 = (FL == 7) ? (-1.0 * log(sigma) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
-    const double pc = -1.0 * log(1.0) - 0.5 * log(2 * GMB_PI_FAMILY);   // log_likelihood(v, 0, 1, 7), mcmlmodel.h:149
-    const int nfull = n / 8;                          // tiles without padding rows
-    const bool has_tail = (n % 8) != 0;
-
-    // ---- chain state (warp = chain, lane = q mod 32) ----
-    double v[QT32], vp[QT32], r[QT32], gc[QT32], g[QT32];
-    double eps = 0.001, ebar = 1.0, H = 0.0, llcur = 0.0, llnew = 0.0;   // initialise_u, mhmcmc.h:47-59
-    int accept = 0, steps = 1;
-    double totsteps = 0.0, lastprob = 0.0;
-#pragma unroll
-    for (int k = 0; k < QT32; k++) {
-        const int q = lane + 32 * k;
-        double z0, z1;
-        dev_rng_normal2(p.seed, (uint32_t)(q >> 1), 0u, gchain, 0u, z0, z1);
-        v[k] = (q < Q) ? ((q & 1) ? z1 : z0) : 0.0;
-        vp[k] = v[k]; r[k] = 0.0; gc[k] = 0.0; g[k] = 0.0;
-        if (q < Q) sVP[warp * LD + q] = vp[k];
-    }
-    if (lane == 0) sSteps[warp] = 1;
-    __syncthreads();
-
-    // One evaluation of the gradient at the v' currently in sVP, for the 8 chains of the CTA.
-    // s = leapfrog step index; the log-likelihood of chain c is accumulated when s == sSteps[c] - 1 (with_ll says whether
-    // any chain of the CTA is on its last step).  On return g[] holds grad(v') for this warp's chain and llnew its
-    // family log-likelihood (if this was its last step).
-    auto grad_eval = [&](int s, bool with_ll) {
-        double bf[KS];
-#pragma unroll
-        for (int j = 0; j < KS; j++) bf[j] = sVP[fr * LD + 4 * j + fk];
-        double gacc[QT8][2];
-#pragma unroll
-        for (int i = 0; i < QT8; i++) gacc[i][0] = gacc[i][1] = 0.0;
-        const bool want0 = (s == sSteps[2 * fk] - 1), want1 = (s == sSteps[2 * fk + 1] - 1);
-        double ll0 = 0.0, ll1 = 0.0;
-        int tile = warp;
-        if (!with_ll) {
-            if (PAIR) for (; tile + NWARP < nfull; tile += 2 * NWARP) {
-                const int r0[2] = {tile * 8, (tile + NWARP) * 8};
-                fused_tiles<FL, KS, 2, false, false, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
-            }
-            for (; tile < nfull; tile += NWARP) {
-                const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, false, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
-            }
-            if (has_tail && tile == nfull) {
-                const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, false, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
-            }
-        } else {
-            for (; tile < nfull; tile += NWARP) {
-                const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, true, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
-            }
-            if (has_tail && tile == nfull) {
-                const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, true, FASTEXP>(sZL, bf, r0, n, p.xb, p.y, p.rowc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
-            }
-        }
-        // ---- deterministic cross-warp sum of the partial gradients: warps 4-7 -> slots, warps 0-3 add, then 4-term sums ----
-        if (with_ll) {
-            ll0 += __shfl_xor_sync(0xffffffffu, ll0, 4);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 4);
-            ll0 += __shfl_xor_sync(0xffffffffu, ll0, 8);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 8);
-            ll0 += __shfl_xor_sync(0xffffffffu, ll0, 16); ll1 += __shfl_xor_sync(0xffffffffu, ll1, 16);
-            if (fr == 0) { sLL[warp * CB + 2 * fk] = ll0; sLL[warp * CB + 2 * fk + 1] = ll1; }
-        }
-        double* slot = sSlot + (warp & 3) * QP8 * 9;
-        if (warp >= 4) {
-#pragma unroll
-            for (int i = 0; i < QT8; i++) {
-                slot[(8 * i + fr) * 9 + 2 * fk] = gacc[i][0];
-                slot[(8 * i + fr) * 9 + 2 * fk + 1] = gacc[i][1];
-            }
-        }
-        __syncthreads();
-        if (warp < 4) {
-#pragma unroll
-            for (int i = 0; i < QT8; i++) {
-                slot[(8 * i + fr) * 9 + 2 * fk] += gacc[i][0];
-                slot[(8 * i + fr) * 9 + 2 * fk + 1] += gacc[i][1];
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < QT32; k++) {
-            const int q = lane + 32 * k;
-            if (q < Q) {
-                const double gs = ((sSlot[q * 9 + warp] + sSlot[(QP8 + q) * 9 + warp]) + sSlot[(2 * QP8 + q) * 9 + warp]) + sSlot[(3 * QP8 + q) * 9 + warp];
-                g[k] = -1.0 * vp[k] + sc * gs;                                  // mcmlmodel.h:163 + :173/:191/:235
-            }
-        }
-        if (with_ll && s == steps - 1) {
-            double l = 0.0;
-#pragma unroll
-            for (int w = 0; w < NWARP; w++) l += sLL[w * CB + warp];
-            llnew = l;
-        }
-    };
-
-    // gradient and log-likelihood at the initial state (carried over between proposals instead of recomputed, mhmcmc.h:64,82)
-    grad_eval(0, true);
-#pragma unroll
-    for (int k = 0; k < QT32; k++) gc[k] = g[k];
-    llcur = llnew;
-    __syncthreads();
-
-    const int total = p.warmup + p.nsamp;
-    const int cols = p.nsamp + 1;
-    if (p.warmup == 0 && live) {                                                   // samples.col(0) = u_, mhmcmc.h:142
-#pragma unroll
-        for (int k = 0; k < QT32; k++) { const int q = lane + 32 * k; if (q < Q) p.dV_out[((size_t)chain * cols) * p.ldq + q] = v[k]; }
-    }
-
-    for (int t = 0; t < total; t++) {
-        // ---- new_proposal, mhmcmc.h:61-75 ----
-        double k0 = 0.0;
-#pragma unroll
-        for (int k = 0; k < QT32; k++) {
-            const int q = lane + 32 * k;
-            double z0, z1;
-            dev_rng_normal2(p.seed, (uint32_t)(q >> 1), (uint32_t)t, gchain, 2u, z0, z1);          // :62-63
-            const double z = (q & 1) ? z1 : z0;
-            if (q < Q) {
-                k0 += z * z;
-                r[k] = z + (eps / 2) * gc[k];                                                       // :74 (first step)
-                vp[k] = v[k] + eps * r[k];                                                          // :67, :75
-                sVP[warp * LD + q] = vp[k];
-            }
-        }
-        k0 = 0.5 * warp_sum(k0);                                                                    // :66
-        {
-            const double sd = round(p.lambda / eps);                                                // :69
-            steps = sd >= (double)p.max_steps ? p.max_steps : (sd < 1.0 ? 1 : (int)sd);             // :69-70
-            if (!(sd == sd)) steps = p.max_steps;
-            if (!live) steps = 1;
-            totsteps += steps;
-            if (lane == 0) sSteps[warp] = steps;
-        }
-        __syncthreads();
-        int smax = 1, stc[CB];
-#pragma unroll
-        for (int w = 0; w < CB; w++) { stc[w] = sSteps[w]; smax = max(smax, stc[w]); }
-        // ---- leapfrog integrator, :73-78 ----
-        for (int s = 0; s < smax; s++) {
-            bool any_last = false;                      // is any chain of the CTA on its last step (needs its log-likelihood)?
-#pragma unroll
-            for (int w = 0; w < CB; w++) any_last |= (s == stc[w] - 1);
-            grad_eval(s, any_last);
-            if (s < steps) {
-#pragma unroll
-                for (int k = 0; k < QT32; k++) {
-                    const int q = lane + 32 * k;
-                    if (q < Q) {
-                        double rr = r[k] + (eps / 2) * g[k];                                        // :77
-                        if (s < steps - 1) {
-                            rr = rr + (eps / 2) * g[k];                                             // :74 of the next step
-                            vp[k] = vp[k] + eps * rr;                                               // :75
-                            sVP[warp * LD + q] = vp[k];
-                        }
-                        r[k] = rr;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-        // ---- Metropolis test and adaptation, :80-117 ----
-        double k1 = 0.0, pv = 0.0, pvp = 0.0;
-#pragma unroll
-        for (int k = 0; k < QT32; k++) {
-            const int q = lane + 32 * k;
-            if (q < Q) { k1 += r[k] * r[k]; pv += pc - 0.5 * v[k] * v[k]; pvp += pc - 0.5 * vp[k] * vp[k]; }
-        }
-        k1 = 0.5 * warp_sum(k1); pv = warp_sum(pv); pvp = warp_sum(pvp);
-        const double l1 = llcur + pv, l2 = llnew + pvp;                                            // :82-83
-        const double prob = fmin(1.0, exp(-l1 + k0 + l2 - k1));                                    // :84
-        double u1, u2;
-        dev_rng_uniform2(p.seed, 0u, (uint32_t)t, gchain, 3u, u1, u2);                             // :85
-        const bool acc = u1 < prob;                                                                // :86
-        lastprob = prob;
-        if (acc) {                                                                                 // :102-105
-            accept++; llcur = llnew;
-#pragma unroll
-            for (int k = 0; k < QT32; k++) { v[k] = vp[k]; gc[k] = g[k]; }
-        }
-        if (t < p.warmup && t < p.adapt) {                                                         // :107-114, :131-136
-            const int iter = t + 1;
-            const double f1 = 1.0 / (iter + 10);
-            const double pr = (prob == prob) ? prob : 0.0;
-            H = (1 - f1) * H + f1 * (p.target_accept - pr);
-            const double loge = -4.60517 - sqrt((double)iter / 0.05) * H;
-            const double powm = pow((double)iter, -0.75);
-            const double logbare = powm * loge + (1 - powm) * log(ebar);
-            eps = exp(loge);
-            ebar = exp(logbare);
-        } else {
-            eps = ebar;                                                                            // :115-117
-        }
-        const int col = t - p.warmup + 1;                                                          // :142 (col 0), :147
-        if (col >= 0 && live) {
-#pragma unroll
-            for (int k = 0; k < QT32; k++) { const int q = lane + 32 * k; if (q < Q) p.dV_out[((size_t)chain * cols + col) * p.ldq + q] = v[k]; }
-        }
-    }
-    if (live && lane == 0) {
-        const int C = p.C;
-        p.cs_out[FS_EPS * C + chain] = eps; p.cs_out[FS_EBAR * C + chain] = ebar; p.cs_out[FS_H * C + chain] = H;
-        p.cs_out[FS_LLCUR * C + chain] = llcur; p.cs_out[FS_K0 * C + chain] = 0.0; p.cs_out[FS_ACCEPT * C + chain] = (double)accept;
-        p.cs_out[FS_TOTSTEPS * C + chain] = totsteps; p.cs_out[FS_LASTPROB * C + chain] = lastprob;
-    }
-}
-
-size_t fused_smem_bytes(int n8, int ld) {
-    const int qt8 = (ld / 4 + 1) / 2;
-    return sizeof(double) * ((size_t)n8 * ld + 8 + (size_t)CB * ld + (size_t)4 * qt8 * 8 * 9 + NWARP * CB) + sizeof(int) * CB + 16;
-}
 
 int fused_ld(int Q) {
     int l = (Q + 3) / 4 * 4;
@@ -348,82 +14,82 @@ int fused_ld(int Q) {
     return l;
 }
 
-static int fused_tune() {
-    static int t = -1;
-    if (t < 0) { const char* e = getenv("GMB_FUSED_TUNE"); t = e ? atoi(e) & 3 : 2; }
-    return t;
+constexpr size_t SMEM_LIMIT = (size_t)227 * 1024;
+
+size_t fused_smem_bytes(int n8, int ld, int cs, int fl) {
+    return sizeof(double) * (size_t)fused_layout(n8, ld, cs, fl).total + 16;
 }
 
-template <int FL, int KS, int TUNE>
-int launch_fused_t(gmb_ctx* ctx, const FusedParams& p, size_t smem);
+int tiles_per_cta(int n, int cs) {
+    const int tiles = (n + 7) / 8;
+    return (tiles + cs - 1) / cs;
+}
 
-template <int FL, int KS>
-int launch_fused(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
-#ifdef GMB_FUSED_TUNING
-    if (KS == 13 && FL == 3) {
-        switch (fused_tune()) {
-        case 0: return launch_fused_t<FL, KS, 0>(ctx, p, smem);
-        case 1: return launch_fused_t<FL, KS, 1>(ctx, p, smem);
-        case 2: return launch_fused_t<FL, KS, 2>(ctx, p, smem);
-        }
+bool fused_fits(int n, int Q, int cs, int fl) {
+    const int ld = fused_ld(Q);
+    if (ld / 4 > 33) return false;
+    return fused_smem_bytes(tiles_per_cta(n, cs) * 8, ld, cs, fl) <= SMEM_LIMIT;
+}
+
+// forced cluster size (0 = choose): gmb_hmc_set_cluster_size or the environment variable GMB_FUSED_CS
+int g_forced_cs = -1;
+int forced_cs() {
+    if (g_forced_cs < 0) { const char* e = getenv("GMB_FUSED_CS"); g_forced_cs = e ? atoi(e) : 0; }
+    return g_forced_cs;
+}
+
+// Cluster size for a run of C chains: the one with the shortest estimated leapfrog step among those that fit.
+// Cost model per step (in units of one 8-row tile per warp): waves * (tiles per warp + fixed overhead of the reduction,
+// state update and barriers); a cluster launch keeps 148 (CS = 2) or 132 (CS = 4) SMs busy (B300_MICROARCH.md).
+int choose_cs(const gmb_model* mdl, int C) {
+    const int f = forced_cs();
+    if (f == 1 || f == 2 || f == 4) return fused_fits(mdl->n, mdl->Q, f, mdl->flink) ? f : 0;
+    const int groups = (C + CB - 1) / CB, sms = mdl->ctx->sms;
+    int best = 0; double best_cost = 0.0;
+    for (int cs = 1; cs <= 4; cs *= 2) {
+        if (!fused_fits(mdl->n, mdl->Q, cs, mdl->flink)) continue;
+        const int usable = cs == 4 ? (sms / 4 * 4 * 132) / 148 : sms / cs * cs;
+        const int waves = (groups * cs + usable - 1) / (usable > 0 ? usable : 1);
+        const int tpw = (tiles_per_cta(mdl->n, cs) + NWARP - 1) / NWARP;
+        const double cost = waves * (tpw + 2.0 + (cs > 1 ? 0.75 : 0.0));
+        if (!best || cost < best_cost) { best = cs; best_cost = cost; }
     }
-#endif
-    return launch_fused_t<FL, KS, 2>(ctx, p, smem);   // library exp + tile pairs: fastest of the four measured variants
-}
-
-template <int FL, int KS, int TUNE>
-int launch_fused_t(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
-    auto kern = hmc_fused_kernel<FL, KS, TUNE>;
-    GMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int ctas = (p.C + CB - 1) / CB;
-    kern<<<ctas, THREADS, smem, ctx->stream>>>(p);
-    ctx->launches++;
-    GMB_CUDA(cudaGetLastError());
-    return GMB_OK;
-}
-
-template <int FL>
-int launch_fused_ks(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
-    switch (p.ks) {      // ld / 4; ld = 4 (mod 16)
-    case 1: return launch_fused<FL, 1>(ctx, p, smem);
-    case 5: return launch_fused<FL, 5>(ctx, p, smem);
-    case 9: return launch_fused<FL, 9>(ctx, p, smem);
-    case 13: return launch_fused<FL, 13>(ctx, p, smem);
-    case 17: return launch_fused<FL, 17>(ctx, p, smem);
-    case 21: return launch_fused<FL, 21>(ctx, p, smem);
-    case 25: return launch_fused<FL, 25>(ctx, p, smem);
-    case 29: return launch_fused<FL, 29>(ctx, p, smem);
-    case 33: return launch_fused<FL, 33>(ctx, p, smem);
-    }
-    return gmb_set_error(GMB_EINVAL, "no on-chip sampler instantiation for Q = %d", p.Q);
+    return best;
 }
 
 }  // namespace
 
-// true when the on-chip variant can run this model (Z L tile + work buffers fit the 227 KB of one SM)
-bool gmb_hmc_fused_applicable(const gmb_model* mdl) {
-    const int ld = fused_ld(mdl->Q);
-    if (ld / 4 > 33) return false;
-    const int n8 = (mdl->n + 7) / 8 * 8;
-    return fused_smem_bytes(n8, ld) <= (size_t)227 * 1024;
+// 0 = choose per run, 1 = one CTA per group of 8 chains, 2 / 4 = split the observations over a cluster of 2 / 4 CTAs
+extern "C" int gmb_hmc_set_cluster_size(int cs) {
+    if (cs != 0 && cs != 1 && cs != 2 && cs != 4) return gmb_set_error(GMB_EINVAL, "cluster size must be 0 (auto), 1, 2 or 4");
+    g_forced_cs = cs;
+    return GMB_OK;
+}
+
+// true when the on-chip variant can run this model with C chains (its share of Z L + work buffers fit the 227 KB of one SM)
+bool gmb_hmc_fused_applicable(const gmb_model* mdl, int C) {
+    return choose_cs(mdl, C) != 0;
 }
 
 // Same contract as the two-GEMM hmc_run of hmc.cu: dV_out is ldq x (C * (nsamp + 1)) chain-major, d_cs is FS_COUNT x C.
 int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                       int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs) {
     gmb_ctx* ctx = mdl->ctx;
+    const int cs = choose_cs(mdl, C);
+    if (!cs) return gmb_set_error(GMB_EINVAL, "Z L (%d x %d) does not fit the on-chip sampler", mdl->n, mdl->Q);
     FusedParams p;
     p.n = mdl->n; p.Q = mdl->Q; p.ld = fused_ld(mdl->Q); p.ks = p.ld / 4; p.qt8 = (mdl->Q + 7) / 8;
-    p.ldn = mdl->ldn; p.ldq = mdl->ldq; p.n8 = (mdl->n + 7) / 8 * 8;
+    p.ldn = mdl->ldn; p.ldq = mdl->ldq;
+    p.tiles_per_cta = tiles_per_cta(mdl->n, cs); p.n8 = p.tiles_per_cta * 8;
     p.ZL = mdl->dZL; p.xb = mdl->dxb; p.y = mdl->dy; p.rowc = mdl->drowc;
     p.var_par = var_par; p.lambda = lambda; p.target_accept = target_accept;
     p.warmup = warmup; p.nsamp = nsamp; p.max_steps = max_steps; p.adapt = adapt; p.C = C;
     p.chain_offset = chain_offset; p.seed = seed; p.dV_out = dV_out; p.cs_out = d_cs;
-    const size_t smem = fused_smem_bytes(p.n8, p.ld);
+    const size_t smem = fused_smem_bytes(p.n8, p.ld, cs, mdl->flink);
     switch (mdl->flink) {
-    case 1: return launch_fused_ks<1>(ctx, p, smem);
-    case 3: return launch_fused_ks<3>(ctx, p, smem);
-    case 7: return launch_fused_ks<7>(ctx, p, smem);
+    case 1: return gmb_fused_launch_fl1(ctx, p, smem, cs);
+    case 3: return gmb_fused_launch_fl3(ctx, p, smem, cs);
+    case 7: return gmb_fused_launch_fl7(ctx, p, smem, cs);
     }
     return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
 }

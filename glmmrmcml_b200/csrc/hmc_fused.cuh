@@ -1,0 +1,507 @@
+// hmc_fused.cuh — on-chip variant of the batched random-effect sampler (mhmcmc.h:16-160): ONE launch runs the whole
+// sample(warmup, nsamp) call of 8 chains per CTA, with Z L resident in shared memory.
+//
+// Per leapfrog step the CTA makes a SINGLE pass over its Z L tile for all 8 chains (mcmlmodel.h:156-279):
+//   for every tile of 8 observations (one warp each, tiles interleaved over the 8 warps)
+//     eta  = xb + (Z L) v'            DMMA m8n8k4, A = Z L rows from shared memory, B = v' fragments in registers
+//     res  = r(eta)                   family residual in the accumulator registers (+ log-likelihood on the last step)
+//     G   += (Z L)^T res              DMMA m8n8k4 again: the SAME shared-memory rows read transposed, res moved from
+//                                     accumulator to B-fragment layout with warp shuffles
+// so eta and res never exist in memory, Z L is read from shared memory only, and the two contractions of the
+// two-GEMM variant (hmc.cu) plus their epilogues become one loop.  The per-warp partial gradients are summed in a
+// fixed order through shared memory (deterministic), then warp c advances chain c: leapfrog update (mhmcmc.h:73-78),
+// Metropolis test (:80-105) and dual-averaging step size (:107-117), all in registers.
+//
+// Shared-memory budget (227 KB): Z L is stored row-major with a row stride ld = 4 (mod 16) doubles, which makes both
+// the A-fragment reads of the forward product (8 rows x 4 k) and of the transposed product (4 rows x 8 q) conflict
+// free.
+//
+// Thread-block clusters (CS = 2 or 4 CTAs per group of 8 chains): the observations are split over the CTAs of a
+// cluster, each keeps only its rows of Z L (and of xb, y) in shared memory and computes a partial gradient; the
+// partials are exchanged through distributed shared memory (one remote store per gradient element, double buffered)
+// and one cluster barrier per leapfrog step, after which every CTA of the cluster sums them in rank order and advances
+// an identical replica of the chain state.  That (i) lets a group of 8 chains use CS SMs, so that a sampling run with
+// fewer than 148 groups still fills the GPU, and (ii) extends the on-chip variant to models CS times larger than one
+// SM's shared memory.  Models that do not fit even with CS = 4 take the two-GEMM path (hmc.cu).
+#pragma once
+#include "common.cuh"
+#include <cstdlib>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+struct FusedParams {
+    int n, Q, ld, ks, qt8, ldn, ldq, n8;          // n8: rows of Z L one CTA holds (tiles_per_cta * 8)
+    int tiles_per_cta;
+    const double* ZL; const double* xb; const double* y; const double* rowc;
+    double var_par, lambda, target_accept;
+    int warmup, nsamp, max_steps, adapt, C;
+    uint32_t chain_offset; unsigned long long seed;
+    double* dV_out; double* cs_out;
+};
+
+namespace {
+
+constexpr int CB = 8;          // chains per CTA = one MMA n-tile; warp w owns the state of chain w
+constexpr int NWARP = 8;
+constexpr int THREADS = NWARP * 32;
+
+enum { FS_EPS = 0, FS_EBAR, FS_H, FS_LLCUR, FS_K0, FS_ACCEPT, FS_TOTSTEPS, FS_LASTPROB, FS_COUNT };   // = CS_* of hmc.cu
+
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Gradient contributions of `NT` (1 or 2) tiles of 8 observations, local rows r0[t] .. r0[t]+7, for the 8 chains of the group.
+// MASK: rows >= nloc exist in the tile (only the last tile of a CTA whose row count is not a multiple of 8).
+// LL: also accumulate the family log-likelihood of the chains that are on their last leapfrog step.
+// SMROW: xb / y / rowc point to shared memory (cluster variant) instead of global memory.
+template <int FL, int KS, int NT, bool MASK, bool LL, bool FASTEXP, bool SMROW>
+__device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, const double (&bf)[KS], const int (&r0)[NT], int nloc,
+                                            const double* __restrict__ xb, const double* __restrict__ y, const double* __restrict__ rowc,
+                                            double c0, double sigma, bool want0, bool want1, int fr, int fk,
+                                            double (&gacc)[(KS + 1) / 2][2], double& ll0, double& ll1) {
+    constexpr int LD = 4 * KS, QT8 = (KS + 1) / 2;
+    double a[NT][2], xbv[NT], yv[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        const int row = r0[t] + fr;
+        const bool ok = !MASK || row < nloc;
+        if (SMROW) { xbv[t] = ok ? xb[row] : 0.0; yv[t] = ok ? y[row] : 0.0; }
+        else { xbv[t] = ok ? __ldg(xb + row) : 0.0; yv[t] = ok ? __ldg(y + row) : 0.0; }
+        a[t][0] = a[t][1] = 0.0;
+    }
+    // eta tiles: rows x 8 chains; NT independent accumulator chains
+#pragma unroll
+    for (int j = 0; j < KS; j++)
+#pragma unroll
+        for (int t = 0; t < NT; t++) dmma884(a[t][0], a[t][1], sZL[(r0[t] + fr) * LD + 4 * j + fk], bf[j]);
+    double res[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        const double eta0 = xbv[t] + a[t][0], eta1 = xbv[t] + a[t][1];
+        res[t][0] = dev_family_resid<FL, FASTEXP>(yv[t], eta0);
+        res[t][1] = dev_family_resid<FL, FASTEXP>(yv[t], eta1);
+        if (MASK) { const bool ok = r0[t] + fr < nloc; if (!ok) { res[t][0] = 0.0; res[t][1] = 0.0; } }
+        if (LL) {
+            const bool ok = !MASK || r0[t] + fr < nloc;
+            double rc = 0.0;
+            if (FL == 1 && ok) rc = SMROW ? rowc[r0[t] + fr] : __ldg(rowc + r0[t] + fr);
+            const double l0 = dev_family_ll<FL>(yv[t], eta0, rc, c0, sigma), l1 = dev_family_ll<FL>(yv[t], eta1, rc, c0, sigma);
+            if (want0 && ok) ll0 += l0;
+            if (want1 && ok) ll1 += l1;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            // res is held as C fragment [row = lane/4][chain = 2(lane%4) + {0,1}]; the transposed product needs it as
+            // B fragment [k = row = 4h + lane%4][n = chain = lane/4]
+            const int src = 4 * (4 * h + fk) + (fr >> 1);
+            const double t0 = __shfl_sync(0xffffffffu, res[t][0], src);
+            const double t1 = __shfl_sync(0xffffffffu, res[t][1], src);
+            const double b = (fr & 1) ? t1 : t0;
+            const double* zt = sZL + (r0[t] + 4 * h + fk) * LD + fr;
+#pragma unroll
+            for (int i = 0; i < QT8; i++) dmma884(gacc[i][0], gacc[i][1], zt[8 * i], b);
+        }
+}
+
+// Shared-memory carve-up (doubles), shared by the kernel and the host-side size computation.
+struct FusedLayout {
+    int zl, vp, rowv, slot, ll, xch, xll, steps_off, total;   // offsets in doubles
+};
+__host__ __device__ inline FusedLayout fused_layout(int n8, int ld, int cs, int fl) {
+    const int qp8 = ((ld / 4 + 1) / 2) * 8;
+    FusedLayout L;
+    int o = 0;
+    L.zl = o;    o += n8 * ld + 8;                        // Z L rows of this CTA (+8 spill-over doubles for the padded q-tile reads)
+    L.vp = o;    o += CB * ld;                            // v' of the 8 chains
+    L.rowv = o;  o += (cs > 1) ? (fl == 1 ? 3 : 2) * n8 : 0;   // xb, y (, rowc) of this CTA's rows (cluster variant)
+    L.slot = o;  o += ((cs > 1) ? NWARP : NWARP / 2) * qp8 * 9;   // per-warp partial gradients
+    L.ll = o;    o += NWARP * CB;                         // per-warp partial log-likelihoods
+    L.xch = o;   o += (cs > 1) ? 2 * cs * CB * qp8 : 0;   // [parity][rank][chain][q] partial gradients of every CTA of the cluster
+    L.xll = o;   o += (cs > 1) ? 2 * cs * CB : 0;         // [parity][rank][chain] partial log-likelihoods
+    L.steps_off = o; o += CB / 2 + 1;                     // int steps[CB]
+    L.total = o;
+    return L;
+}
+
+template <int FL, int KS, int CS>
+__global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams p) {
+    constexpr bool FASTEXP = false;
+    constexpr int LD = 4 * KS;                       // row stride of the Z L tile; KS = 1 (mod 4) makes it 4 (mod 16)
+    constexpr int QT8 = (KS + 1) / 2;                // 8-row tiles of the gradient
+    constexpr int QP8 = QT8 * 8;
+    constexpr int QT32 = (KS * 4 + 31) / 32;         // state elements per lane
+    constexpr bool CL = CS > 1;
+    extern __shared__ __align__(16) double sm[];
+    const int Q = p.Q;
+    const FusedLayout lay = fused_layout(p.n8, LD, CS, FL);
+    double* sZL = sm + lay.zl;
+    double* sVP = sm + lay.vp;                        // [chain][LD]
+    double* sXB = sm + lay.rowv;                      // cluster variant only
+    double* sY = sXB + p.n8;
+    double* sRC = sY + p.n8;
+    double* sSlot = sm + lay.slot;                    // [slots][QP8][9]
+    double* sLL = sm + lay.ll;                        // [NWARP][CB]
+    double* sXch = sm + lay.xch;                      // [2][CS][CB][QP8]
+    double* sXll = sm + lay.xll;                      // [2][CS][CB]
+    int* sSteps = reinterpret_cast<int*>(sm + lay.steps_off);   // [CB]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int crank = CL ? (int)(blockIdx.x % CS) : 0;            // rank of this CTA inside its cluster (cluster dims = (CS,1,1))
+    const int group = CL ? (int)(blockIdx.x / CS) : (int)blockIdx.x;
+    const int chain = group * CB + warp;              // chain whose state this warp owns (local index, < C if live)
+    const bool live = chain < p.C;
+    const bool writer = live && crank == 0;           // every CTA of a cluster holds the same chain state; rank 0 stores it
+    const uint32_t gchain = p.chain_offset + (uint32_t)chain;
+
+    // rows of this CTA: global rows [row0, row0 + nloc)
+    const int row0 = crank * p.tiles_per_cta * 8;
+    const int nloc = max(0, min(p.n - row0, p.tiles_per_cta * 8));
+
+    // ---- stage this CTA's rows of Z L (global: n x Q column-major) into shared memory, row-major, zero padded ----
+    for (int idx = tid; idx < p.n8 * LD + 8; idx += THREADS) sZL[idx] = 0.0;
+    for (int idx = tid; idx < CB * LD; idx += THREADS) sVP[idx] = 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < nloc * Q; idx += THREADS) {
+        const int row = idx % nloc, q = idx / nloc;
+        sZL[(size_t)row * LD + q] = p.ZL[row0 + row + (size_t)q * p.ldn];
+    }
+    if (CL) {
+        for (int idx = tid; idx < p.n8; idx += THREADS) {
+            const bool ok = idx < nloc;
+            sXB[idx] = ok ? p.xb[row0 + idx] : 0.0;
+            sY[idx] = ok ? p.y[row0 + idx] : 0.0;
+            if (FL == 1) sRC[idx] = ok ? p.rowc[row0 + idx] : 0.0;
+        }
+    }
+    const double* rxb = CL ? sXB : p.xb;
+    const double* ry = CL ? sY : p.y;
+    const double* rrc = CL ? sRC : p.rowc;
+    // remote views of the exchange buffers of every CTA of the cluster (distributed shared memory)
+    double* xch_of[CS];
+    double* xll_of[CS];
+    if (CL) {
+        cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+        for (int r = 0; r < CS; r++) {
+            xch_of[r] = cluster.map_shared_rank(sXch, r);
+            xll_of[r] = cluster.map_shared_rank(sXll, r);
+        }
+    }
+    int par = 0;                                      // parity of the exchange buffer in use
+
+    const double sigma = p.var_par;
+    const double sc = (FL == 7) ? 1.0 / (sigma * sigma) : 1.0;
+    const double c0 = (FL == 7) ? (-1.0 * log(sigma) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
+    const double pc = -1.0 * log(1.0) - 0.5 * log(2 * GMB_PI_FAMILY);   // log_likelihood(v, 0, 1, 7), mcmlmodel.h:149
+    const int nfull = nloc / 8;                       // tiles without padding rows
+    const bool has_tail = (nloc % 8) != 0;
+
+    // ---- chain state (warp = chain, lane = q mod 32) ----
+    double v[QT32], vp[QT32], r[QT32], gc[QT32], g[QT32];
+    double eps = 0.001, ebar = 1.0, H = 0.0, llcur = 0.0, llnew = 0.0;   // initialise_u, mhmcmc.h:47-59
+    int accept = 0, steps = 1;
+    double totsteps = 0.0, lastprob = 0.0;
+#pragma unroll
+    for (int k = 0; k < QT32; k++) {
+        const int q = lane + 32 * k;
+        double z0, z1;
+        dev_rng_normal2(p.seed, (uint32_t)(q >> 1), 0u, gchain, 0u, z0, z1);
+        v[k] = (q < Q) ? ((q & 1) ? z1 : z0) : 0.0;
+        vp[k] = v[k]; r[k] = 0.0; gc[k] = 0.0; g[k] = 0.0;
+        if (q < Q) sVP[warp * LD + q] = vp[k];
+    }
+    if (lane == 0) sSteps[warp] = 1;
+    if (CL) cg::this_cluster().sync();                // every CTA's shared memory is initialised before any remote store
+    else __syncthreads();
+
+    // One evaluation of the gradient at the v' currently in sVP, for the 8 chains of the group.
+    // s = leapfrog step index; the log-likelihood of chain c is accumulated when s == sSteps[c] - 1 (with_ll says whether
+    // any chain of the group is on its last step).  On return g[] holds grad(v') for this warp's chain and llnew its
+    // family log-likelihood (if this was its last step).
+    auto grad_eval = [&](int s, bool with_ll) {
+        double bf[KS];
+#pragma unroll
+        for (int j = 0; j < KS; j++) bf[j] = sVP[fr * LD + 4 * j + fk];
+        double gacc[QT8][2];
+#pragma unroll
+        for (int i = 0; i < QT8; i++) gacc[i][0] = gacc[i][1] = 0.0;
+        const bool want0 = (s == sSteps[2 * fk] - 1), want1 = (s == sSteps[2 * fk + 1] - 1);
+        double ll0 = 0.0, ll1 = 0.0;
+        int tile = warp;
+        if (!with_ll) {
+            for (; tile + NWARP < nfull; tile += 2 * NWARP) {
+                const int r0[2] = {tile * 8, (tile + NWARP) * 8};
+                fused_tiles<FL, KS, 2, false, false, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+            }
+            for (; tile < nfull; tile += NWARP) {
+                const int r0[1] = {tile * 8};
+                fused_tiles<FL, KS, 1, false, false, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+            }
+            if (has_tail && tile == nfull) {
+                const int r0[1] = {tile * 8};
+                fused_tiles<FL, KS, 1, true, false, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+            }
+        } else {
+            for (; tile < nfull; tile += NWARP) {
+                const int r0[1] = {tile * 8};
+                fused_tiles<FL, KS, 1, false, true, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+            }
+            if (has_tail && tile == nfull) {
+                const int r0[1] = {tile * 8};
+                fused_tiles<FL, KS, 1, true, true, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+            }
+        }
+        if (with_ll) {
+            ll0 += __shfl_xor_sync(0xffffffffu, ll0, 4);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 4);
+            ll0 += __shfl_xor_sync(0xffffffffu, ll0, 8);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 8);
+            ll0 += __shfl_xor_sync(0xffffffffu, ll0, 16); ll1 += __shfl_xor_sync(0xffffffffu, ll1, 16);
+            if (fr == 0) { sLL[warp * CB + 2 * fk] = ll0; sLL[warp * CB + 2 * fk + 1] = ll1; }
+        }
+        if (!CL) {
+            // ---- deterministic cross-warp sum of the partial gradients: warps 4-7 -> slots, warps 0-3 add, then 4-term sums ----
+            double* slot = sSlot + (warp & 3) * QP8 * 9;
+            if (warp >= 4) {
+#pragma unroll
+                for (int i = 0; i < QT8; i++) {
+                    slot[(8 * i + fr) * 9 + 2 * fk] = gacc[i][0];
+                    slot[(8 * i + fr) * 9 + 2 * fk + 1] = gacc[i][1];
+                }
+            }
+            __syncthreads();
+            if (warp < 4) {
+#pragma unroll
+                for (int i = 0; i < QT8; i++) {
+                    slot[(8 * i + fr) * 9 + 2 * fk] += gacc[i][0];
+                    slot[(8 * i + fr) * 9 + 2 * fk + 1] += gacc[i][1];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < QT32; k++) {
+                const int q = lane + 32 * k;
+                if (q < Q) {
+                    const double gs = ((sSlot[q * 9 + warp] + sSlot[(QP8 + q) * 9 + warp]) + sSlot[(2 * QP8 + q) * 9 + warp]) + sSlot[(3 * QP8 + q) * 9 + warp];
+                    g[k] = -1.0 * vp[k] + sc * gs;                                  // mcmlmodel.h:163 + :173/:191/:235
+                }
+            }
+            if (with_ll && s == steps - 1) {
+                double l = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARP; w++) l += sLL[w * CB + warp];
+                llnew = l;
+            }
+        } else {
+            // ---- cluster variant: every warp stores its partial, one barrier, warp c sums the 8 partials of chain c in warp
+            //      order and hands the CTA's partial to every CTA of the cluster; cluster barrier; sum over ranks in rank order ----
+            double* slot = sSlot + warp * QP8 * 9;
+#pragma unroll
+            for (int i = 0; i < QT8; i++) {
+                slot[(8 * i + fr) * 9 + 2 * fk] = gacc[i][0];
+                slot[(8 * i + fr) * 9 + 2 * fk + 1] = gacc[i][1];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < QT32; k++) {
+                const int q = lane + 32 * k;
+                if (q < Q) {
+                    double gs = sSlot[q * 9 + warp];
+#pragma unroll
+                    for (int w = 1; w < NWARP; w++) gs += sSlot[(w * QP8 + q) * 9 + warp];
+                    const int off = ((par * CS + crank) * CB + warp) * QP8 + q;
+#pragma unroll
+                    for (int rk = 0; rk < CS; rk++) xch_of[rk][off] = gs;
+                }
+            }
+            if (with_ll && lane == 0) {
+                double l = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARP; w++) l += sLL[w * CB + warp];
+                const int off = (par * CS + crank) * CB + warp;
+#pragma unroll
+                for (int rk = 0; rk < CS; rk++) xll_of[rk][off] = l;
+            }
+            cg::this_cluster().sync();
+#pragma unroll
+            for (int k = 0; k < QT32; k++) {
+                const int q = lane + 32 * k;
+                if (q < Q) {
+                    double gs = sXch[((par * CS + 0) * CB + warp) * QP8 + q];
+#pragma unroll
+                    for (int rk = 1; rk < CS; rk++) gs += sXch[((par * CS + rk) * CB + warp) * QP8 + q];
+                    g[k] = -1.0 * vp[k] + sc * gs;                                  // mcmlmodel.h:163 + :173/:191/:235
+                }
+            }
+            if (with_ll && s == steps - 1) {
+                double l = sXll[(par * CS + 0) * CB + warp];
+#pragma unroll
+                for (int rk = 1; rk < CS; rk++) l += sXll[(par * CS + rk) * CB + warp];
+                llnew = l;
+            }
+            par ^= 1;
+        }
+    };
+
+    // gradient and log-likelihood at the initial state (carried over between proposals instead of recomputed, mhmcmc.h:64,82)
+    grad_eval(0, true);
+#pragma unroll
+    for (int k = 0; k < QT32; k++) gc[k] = g[k];
+    llcur = llnew;
+    __syncthreads();
+
+    const int total = p.warmup + p.nsamp;
+    const int cols = p.nsamp + 1;
+    if (p.warmup == 0 && writer) {                                                 // samples.col(0) = u_, mhmcmc.h:142
+#pragma unroll
+        for (int k = 0; k < QT32; k++) { const int q = lane + 32 * k; if (q < Q) p.dV_out[((size_t)chain * cols) * p.ldq + q] = v[k]; }
+    }
+
+    for (int t = 0; t < total; t++) {
+        // ---- new_proposal, mhmcmc.h:61-75 ----
+        double k0 = 0.0;
+#pragma unroll
+        for (int k = 0; k < QT32; k++) {
+            const int q = lane + 32 * k;
+            double z0, z1;
+            dev_rng_normal2(p.seed, (uint32_t)(q >> 1), (uint32_t)t, gchain, 2u, z0, z1);          // :62-63
+            const double z = (q & 1) ? z1 : z0;
+            if (q < Q) {
+                k0 += z * z;
+                r[k] = z + (eps / 2) * gc[k];                                                       // :74 (first step)
+                vp[k] = v[k] + eps * r[k];                                                          // :67, :75
+                sVP[warp * LD + q] = vp[k];
+            }
+        }
+        k0 = 0.5 * warp_sum(k0);                                                                    // :66
+        {
+            const double sd = round(p.lambda / eps);                                                // :69
+            steps = sd >= (double)p.max_steps ? p.max_steps : (sd < 1.0 ? 1 : (int)sd);             // :69-70
+            if (!(sd == sd)) steps = p.max_steps;
+            if (!live) steps = 1;
+            totsteps += steps;
+            if (lane == 0) sSteps[warp] = steps;
+        }
+        __syncthreads();
+        int smax = 1, stc[CB];
+#pragma unroll
+        for (int w = 0; w < CB; w++) { stc[w] = sSteps[w]; smax = max(smax, stc[w]); }
+        // ---- leapfrog integrator, :73-78 ----
+        for (int s = 0; s < smax; s++) {
+            bool any_last = false;                      // is any chain of the group on its last step (needs its log-likelihood)?
+#pragma unroll
+            for (int w = 0; w < CB; w++) any_last |= (s == stc[w] - 1);
+            grad_eval(s, any_last);
+            if (s < steps) {
+#pragma unroll
+                for (int k = 0; k < QT32; k++) {
+                    const int q = lane + 32 * k;
+                    if (q < Q) {
+                        double rr = r[k] + (eps / 2) * g[k];                                        // :77
+                        if (s < steps - 1) {
+                            rr = rr + (eps / 2) * g[k];                                             // :74 of the next step
+                            vp[k] = vp[k] + eps * rr;                                               // :75
+                            sVP[warp * LD + q] = vp[k];
+                        }
+                        r[k] = rr;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- Metropolis test and adaptation, :80-117 ----
+        double k1 = 0.0, pv = 0.0, pvp = 0.0;
+#pragma unroll
+        for (int k = 0; k < QT32; k++) {
+            const int q = lane + 32 * k;
+            if (q < Q) { k1 += r[k] * r[k]; pv += pc - 0.5 * v[k] * v[k]; pvp += pc - 0.5 * vp[k] * vp[k]; }
+        }
+        k1 = 0.5 * warp_sum(k1); pv = warp_sum(pv); pvp = warp_sum(pvp);
+        const double l1 = llcur + pv, l2 = llnew + pvp;                                            // :82-83
+        const double prob = fmin(1.0, exp(-l1 + k0 + l2 - k1));                                    // :84
+        double u1, u2;
+        dev_rng_uniform2(p.seed, 0u, (uint32_t)t, gchain, 3u, u1, u2);                             // :85
+        const bool acc = u1 < prob;                                                                // :86
+        lastprob = prob;
+        if (acc) {                                                                                 // :102-105
+            accept++; llcur = llnew;
+#pragma unroll
+            for (int k = 0; k < QT32; k++) { v[k] = vp[k]; gc[k] = g[k]; }
+        }
+        if (t < p.warmup && t < p.adapt) {                                                         // :107-114, :131-136
+            const int iter = t + 1;
+            const double f1 = 1.0 / (iter + 10);
+            const double pr = (prob == prob) ? prob : 0.0;
+            H = (1 - f1) * H + f1 * (p.target_accept - pr);
+            const double loge = -4.60517 - sqrt((double)iter / 0.05) * H;
+            const double powm = pow((double)iter, -0.75);
+            const double logbare = powm * loge + (1 - powm) * log(ebar);
+            eps = exp(loge);
+            ebar = exp(logbare);
+        } else {
+            eps = ebar;                                                                            // :115-117
+        }
+        const int col = t - p.warmup + 1;                                                          // :142 (col 0), :147
+        if (col >= 0 && writer) {
+#pragma unroll
+            for (int k = 0; k < QT32; k++) { const int q = lane + 32 * k; if (q < Q) p.dV_out[((size_t)chain * cols + col) * p.ldq + q] = v[k]; }
+        }
+    }
+    if (writer && lane == 0) {
+        const int C = p.C;
+        p.cs_out[FS_EPS * C + chain] = eps; p.cs_out[FS_EBAR * C + chain] = ebar; p.cs_out[FS_H * C + chain] = H;
+        p.cs_out[FS_LLCUR * C + chain] = llcur; p.cs_out[FS_K0 * C + chain] = 0.0; p.cs_out[FS_ACCEPT * C + chain] = (double)accept;
+        p.cs_out[FS_TOTSTEPS * C + chain] = totsteps; p.cs_out[FS_LASTPROB * C + chain] = lastprob;
+    }
+    if (CL) cg::this_cluster().sync();                // no CTA may exit while a peer can still store into its shared memory
+}
+
+template <int FL, int KS, int CS>
+int launch_fused(gmb_ctx* ctx, const FusedParams& p, size_t smem) {
+    auto kern = hmc_fused_kernel<FL, KS, CS>;
+    GMB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int groups = (p.C + CB - 1) / CB;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(groups * CS); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = CS > 1 ? 1 : 0;
+    GMB_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    ctx->launches++;
+    GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}
+
+template <int FL, int KS>
+int launch_fused_cs(gmb_ctx* ctx, const FusedParams& p, size_t smem, int cs) {
+    switch (cs) {
+    case 1: return launch_fused<FL, KS, 1>(ctx, p, smem);
+    case 2: return launch_fused<FL, KS, 2>(ctx, p, smem);
+    case 4: return launch_fused<FL, KS, 4>(ctx, p, smem);
+    }
+    return gmb_set_error(GMB_EINVAL, "bad cluster size %d", cs);
+}
+
+template <int FL>
+int launch_fused_ks(gmb_ctx* ctx, const FusedParams& p, size_t smem, int cs) {
+    switch (p.ks) {      // ld / 4; ld = 4 (mod 16)
+    case 1: return launch_fused_cs<FL, 1>(ctx, p, smem, cs);
+    case 5: return launch_fused_cs<FL, 5>(ctx, p, smem, cs);
+    case 9: return launch_fused_cs<FL, 9>(ctx, p, smem, cs);
+    case 13: return launch_fused_cs<FL, 13>(ctx, p, smem, cs);
+    case 17: return launch_fused_cs<FL, 17>(ctx, p, smem, cs);
+    case 21: return launch_fused_cs<FL, 21>(ctx, p, smem, cs);
+    case 25: return launch_fused_cs<FL, 25>(ctx, p, smem, cs);
+    case 29: return launch_fused_cs<FL, 29>(ctx, p, smem, cs);
+    case 33: return launch_fused_cs<FL, 33>(ctx, p, smem, cs);
+    }
+    return gmb_set_error(GMB_EINVAL, "no on-chip sampler instantiation for Q = %d", p.Q);
+}
+
+}  // namespace

@@ -139,6 +139,12 @@ int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* beta, double v
  * Both variants follow the same chain arithmetic and the same random streams. */
 int gmb_hmc_set_variant(int variant);
 
+/* On-chip sampler: CTAs per group of 8 chains.  0 = automatic (per run: the cluster size with the shortest estimated
+ * leapfrog step among those whose share of Z L fits one SM's shared memory), 1 = one CTA per group, 2 / 4 = the
+ * observations of a group are split over a thread-block cluster of 2 / 4 SMs that exchange partial gradients through
+ * distributed shared memory.  All settings follow the same chain arithmetic and random streams. */
+int gmb_hmc_set_cluster_size(int cs);
+
 /* mcmlModel::log_prob / log_grad (mcmlmodel.h:138-153, 156-279, usezl = true) for C whitened states V (Q x C):
  * lp[C], grad (Q x C).  Either output may be NULL.  Used by the parity tests and by mcml_la. */
 int gmb_model_logprob_grad(gmb_model* mdl, const double* L, const double* beta, double var_par,

@@ -42,21 +42,25 @@ def test_log_prob_and_grad(case, oracle):
         assert np.max(np.abs(G[:, c] - gw)) <= 1e-10 * max(np.max(np.abs(gw)), 1.0)
 
 
-@pytest.mark.parametrize("variant", [1, 2], ids=["two-gemm", "on-chip"])
-def test_chain_follows_oracle(case, oracle, variant):
+@pytest.mark.parametrize("variant,cluster", [(1, 0), (2, 1), (2, 2), (2, 4), (0, 0)],
+                         ids=["two-gemm", "on-chip", "on-chip-cluster2", "on-chip-cluster4", "auto"])
+def test_chain_follows_oracle(case, oracle, variant, cluster):
     """Same seed, same counter-based RNG: the device chains must reproduce the oracle chains' states (to the accuracy
-    the leapfrog map preserves), acceptance rate, step size and step count — for both sampler kernels."""
+    the leapfrog map preserves), acceptance rate, step size and step count — for both sampler kernels and for every
+    cluster size of the on-chip one (observations split over 1, 2 or 4 SMs per group of 8 chains)."""
     import glmmrmcml_b200 as g
     cfg, mdl = case
     g.hmc_set_variant(variant)
+    g.hmc_set_cluster_size(cluster)
     try:
         _chain_follows_oracle(cfg, mdl, oracle)
     except g.GmbError as e:
         if variant == 2 and "does not fit" in str(e):
-            pytest.skip("model too large for the on-chip variant")
+            pytest.skip("model too large for the on-chip variant at this cluster size")
         raise
     finally:
         g.hmc_set_variant(0)
+        g.hmc_set_cluster_size(0)
 
 
 def _chain_follows_oracle(cfg, mdl, oracle):
