@@ -341,6 +341,8 @@ static int hmc_run(gmb_model* mdl, double var_par, int warmup, int nsamp, double
 
 // hmc_fused.cu
 bool gmb_hmc_fused_applicable(const gmb_model* mdl, int C);
+size_t gmb_hmc_fused_cs_doubles(int C);
+size_t gmb_hmc_fused_scratch_doubles(const gmb_model* mdl, int C);
 int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                       int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs);
 
@@ -355,7 +357,7 @@ extern "C" int gmb_hmc_set_variant(int variant) {
 static int hmc_run_fused_timed(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                                int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, std::vector<double>* host_cs, float* ms) {
     gmb_ctx* ctx = mdl->ctx;
-    const size_t need = (size_t)CS_COUNT * C + 16;
+    const size_t need = gmb_hmc_fused_cs_doubles(C) + gmb_hmc_fused_scratch_doubles(mdl, C);
     if (need > mdl->hmc_work_doubles) {
         if (mdl->hmc_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(mdl->hmc_work)); mdl->hmc_work = nullptr; mdl->hmc_work_doubles = 0; }
         GMB_CUDA(cudaMalloc(&mdl->hmc_work, need * sizeof(double)));

@@ -71,6 +71,13 @@ bool gmb_hmc_fused_applicable(const gmb_model* mdl, int C) {
     return choose_cs(mdl, C) != 0;
 }
 
+// doubles of global scratch the kernel needs behind the FS_COUNT x C chain statistics (d_cs + gmb_hmc_fused_cs_doubles(C))
+size_t gmb_hmc_fused_cs_doubles(int C) { return round_up_sz((size_t)FS_COUNT * C + 16, 16); }
+size_t gmb_hmc_fused_scratch_doubles(const gmb_model* mdl, int C) {
+    const int groups = (C + CB - 1) / CB;
+    return (size_t)groups * 4 /* max cluster size */ * CB * 4 * fused_ld(mdl->Q);
+}
+
 // Same contract as the two-GEMM hmc_run of hmc.cu: dV_out is ldq x (C * (nsamp + 1)) chain-major, d_cs is FS_COUNT x C.
 int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                       int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs) {
@@ -85,6 +92,7 @@ int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, dou
     p.var_par = var_par; p.lambda = lambda; p.target_accept = target_accept;
     p.warmup = warmup; p.nsamp = nsamp; p.max_steps = max_steps; p.adapt = adapt; p.C = C;
     p.chain_offset = chain_offset; p.seed = seed; p.dV_out = dV_out; p.cs_out = d_cs;
+    p.scratch = d_cs + gmb_hmc_fused_cs_doubles(C);
     const size_t smem = fused_smem_bytes(p.n8, p.ld, cs, mdl->flink);
     switch (mdl->flink) {
     case 1: return gmb_fused_launch_fl1(ctx, p, smem, cs);

@@ -1,16 +1,24 @@
 // hmc_fused.cuh — on-chip variant of the batched random-effect sampler (mhmcmc.h:16-160): ONE launch runs the whole
-// sample(warmup, nsamp) call of 8 chains per CTA, with Z L resident in shared memory.
+// sample(warmup, nsamp) call, 8 chains per group, with Z L resident in shared memory.
 //
-// Per leapfrog step the CTA makes a SINGLE pass over its Z L tile for all 8 chains (mcmlmodel.h:156-279):
-//   for every tile of 8 observations (one warp each, tiles interleaved over the 8 warps)
+// Per leapfrog step a group makes a SINGLE pass over its Z L rows for all 8 chains (mcmlmodel.h:156-279):
+//   for every tile of 8 observations (tiles interleaved over the 8 warps, up to 4 tiles in flight per warp)
 //     eta  = xb + (Z L) v'            DMMA m8n8k4, A = Z L rows from shared memory, B = v' fragments in registers
-//     res  = r(eta)                   family residual in the accumulator registers (+ log-likelihood on the last step)
+//     res  = r(eta)                   family residual in the accumulator registers (table-driven exp + Newton reciprocal,
+//                                     branch free so that the 8 residuals of 4 tiles interleave on the FP64 pipe)
 //     G   += (Z L)^T res              DMMA m8n8k4 again: the SAME shared-memory rows read transposed, res moved from
 //                                     accumulator to B-fragment layout with warp shuffles
 // so eta and res never exist in memory, Z L is read from shared memory only, and the two contractions of the
 // two-GEMM variant (hmc.cu) plus their epilogues become one loop.  The per-warp partial gradients are summed in a
-// fixed order through shared memory (deterministic), then warp c advances chain c: leapfrog update (mhmcmc.h:73-78),
-// Metropolis test (:80-105) and dual-averaging step size (:107-117), all in registers.
+// fixed order through shared memory (deterministic).
+//
+// Chain state.  v' and the momentum r of all 8 chains live in registers in the MMA B-fragment layout (lane (fr, fk) holds
+// elements q = 4 j + fk of chain fr), REPLICATED in every warp: after the gradient sum every warp reads the gradient in
+// that layout and applies the leapfrog update (mhmcmc.h:73-78) itself, so v' never goes through shared memory and no
+// barrier separates one step's update from the next step's products.  Metropolis test (:80-105) and dual-averaging step
+// size (:107-117) are likewise evaluated redundantly from replicated per-chain scalars (counter-based RNG: every replica
+// draws the same numbers).  The current state v and its gradient, needed once per proposal, sit in a small global
+// scratch area written by the "owner" lanes of each chain (warp w, fr == w).
 //
 // Shared-memory budget (227 KB): Z L is stored row-major with a row stride ld = 4 (mod 16) doubles, which makes both
 // the A-fragment reads of the forward product (8 rows x 4 k) and of the transposed product (4 rows x 8 q) conflict
@@ -37,28 +45,36 @@ struct FusedParams {
     int warmup, nsamp, max_steps, adapt, C;
     uint32_t chain_offset; unsigned long long seed;
     double* dV_out; double* cs_out;
+    double* scratch;                               // [grid][8 chains][2 parities][v | grad][ld] : state at the last accepted proposal
 };
 
 namespace {
 
-constexpr int CB = 8;          // chains per CTA = one MMA n-tile; warp w owns the state of chain w
+constexpr int CB = 8;          // chains per group = one MMA n-tile
 constexpr int NWARP = 8;
 constexpr int THREADS = NWARP * 32;
 
 enum { FS_EPS = 0, FS_EBAR, FS_H, FS_LLCUR, FS_K0, FS_ACCEPT, FS_TOTSTEPS, FS_LASTPROB, FS_COUNT };   // = CS_* of hmc.cu
 
-
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// Gradient contributions of `NT` (1 or 2) tiles of 8 observations, local rows r0[t] .. r0[t]+7, for the 8 chains of the group.
+// sum over the 4 lanes that share fr (the 4 k-positions of a fragment)
+__device__ __forceinline__ double quad_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+}
+
+// Gradient contributions of `NT` (1, 2 or 4) tiles of 8 observations, local rows r0[t] .. r0[t]+7, for the 8 chains of the group.
 // MASK: rows >= nloc exist in the tile (only the last tile of a CTA whose row count is not a multiple of 8).
 // LL: also accumulate the family log-likelihood of the chains that are on their last leapfrog step.
 // SMROW: xb / y / rowc point to shared memory (cluster variant) instead of global memory.
-template <int FL, int KS, int NT, bool MASK, bool LL, bool FASTEXP, bool SMROW>
-__device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, const double (&bf)[KS], const int (&r0)[NT], int nloc,
+template <int FL, int KS, int NT, bool MASK, bool LL, bool SMROW>
+__device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, const double* __restrict__ sTab, const double (&bf)[KS],
+                                            const int (&r0)[NT], int nloc,
                                             const double* __restrict__ xb, const double* __restrict__ y, const double* __restrict__ rowc,
                                             double c0, double sigma, bool want0, bool want1, int fr, int fk,
                                             double (&gacc)[(KS + 1) / 2][2], double& ll0, double& ll1) {
@@ -81,8 +97,8 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
 #pragma unroll
     for (int t = 0; t < NT; t++) {
         const double eta0 = xbv[t] + a[t][0], eta1 = xbv[t] + a[t][1];
-        res[t][0] = dev_family_resid<FL, FASTEXP>(yv[t], eta0);
-        res[t][1] = dev_family_resid<FL, FASTEXP>(yv[t], eta1);
+        res[t][0] = dev_family_resid_tab<FL>(yv[t], eta0, sTab);
+        res[t][1] = dev_family_resid_tab<FL>(yv[t], eta1, sTab);
         if (MASK) { const bool ok = r0[t] + fr < nloc; if (!ok) { res[t][0] = 0.0; res[t][1] = 0.0; } }
         if (LL) {
             const bool ok = !MASK || r0[t] + fr < nloc;
@@ -111,54 +127,54 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
 
 // Shared-memory carve-up (doubles), shared by the kernel and the host-side size computation.
 struct FusedLayout {
-    int zl, vp, rowv, slot, ll, xch, xll, steps_off, total;   // offsets in doubles
+    int zl, tab, rowv, slot, ll, xch, xll, total;   // offsets in doubles
 };
 __host__ __device__ inline FusedLayout fused_layout(int n8, int ld, int cs, int fl) {
     const int qp8 = ((ld / 4 + 1) / 2) * 8;
+    const int npar = cs > 1 ? 2 : 1;
     FusedLayout L;
     int o = 0;
     L.zl = o;    o += n8 * ld + 8;                        // Z L rows of this CTA (+8 spill-over doubles for the padded q-tile reads)
-    L.vp = o;    o += CB * ld;                            // v' of the 8 chains
+    L.tab = o;   o += 64;                                 // 2^(j/64)
     L.rowv = o;  o += (cs > 1) ? (fl == 1 ? 3 : 2) * n8 : 0;   // xb, y (, rowc) of this CTA's rows (cluster variant)
     L.slot = o;  o += ((cs > 1) ? NWARP : NWARP / 2) * qp8 * 9;   // per-warp partial gradients
     L.ll = o;    o += NWARP * CB;                         // per-warp partial log-likelihoods
-    L.xch = o;   o += (cs > 1) ? 2 * cs * CB * qp8 : 0;   // [parity][rank][chain][q] partial gradients of every CTA of the cluster
-    L.xll = o;   o += (cs > 1) ? 2 * cs * CB : 0;         // [parity][rank][chain] partial log-likelihoods
-    L.steps_off = o; o += CB / 2 + 1;                     // int steps[CB]
+    L.xch = o;   o += npar * cs * CB * ld;                // [parity][rank][chain][q] partial gradients of every CTA of the cluster
+    L.xll = o;   o += npar * cs * CB;                     // [parity][rank][chain] partial log-likelihoods
     L.total = o;
     return L;
 }
 
 template <int FL, int KS, int CS>
 __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams p) {
-    constexpr bool FASTEXP = false;
     constexpr int LD = 4 * KS;                       // row stride of the Z L tile; KS = 1 (mod 4) makes it 4 (mod 16)
     constexpr int QT8 = (KS + 1) / 2;                // 8-row tiles of the gradient
     constexpr int QP8 = QT8 * 8;
-    constexpr int QT32 = (KS * 4 + 31) / 32;         // state elements per lane
+    constexpr int QT32 = (LD + 31) / 32;             // gradient elements per lane in the [chain = warp][q = lane + 32 k] layout
     constexpr bool CL = CS > 1;
     extern __shared__ __align__(16) double sm[];
     const int Q = p.Q;
     const FusedLayout lay = fused_layout(p.n8, LD, CS, FL);
     double* sZL = sm + lay.zl;
-    double* sVP = sm + lay.vp;                        // [chain][LD]
+    double* sTab = sm + lay.tab;
     double* sXB = sm + lay.rowv;                      // cluster variant only
     double* sY = sXB + p.n8;
     double* sRC = sY + p.n8;
     double* sSlot = sm + lay.slot;                    // [slots][QP8][9]
     double* sLL = sm + lay.ll;                        // [NWARP][CB]
-    double* sXch = sm + lay.xch;                      // [2][CS][CB][QP8]
-    double* sXll = sm + lay.xll;                      // [2][CS][CB]
-    int* sSteps = reinterpret_cast<int*>(sm + lay.steps_off);   // [CB]
+    double* sXch = sm + lay.xch;                      // [parities][CS][CB][LD]
+    double* sXll = sm + lay.xll;                      // [parities][CS][CB]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
     const int crank = CL ? (int)(blockIdx.x % CS) : 0;            // rank of this CTA inside its cluster (cluster dims = (CS,1,1))
     const int group = CL ? (int)(blockIdx.x / CS) : (int)blockIdx.x;
-    const int chain = group * CB + warp;              // chain whose state this warp owns (local index, < C if live)
+    const int chain = group * CB + fr;                // the chain this lane holds a fragment of (local index, < C if live)
     const bool live = chain < p.C;
-    const bool writer = live && crank == 0;           // every CTA of a cluster holds the same chain state; rank 0 stores it
+    const bool owner = (fr == warp);                  // warp w's lanes with fr == w store chain w's state
+    const bool writer = owner && live && crank == 0;  // every CTA of a cluster holds the same state; rank 0 stores the samples
     const uint32_t gchain = p.chain_offset + (uint32_t)chain;
+    double* scr = p.scratch + ((size_t)blockIdx.x * CB + fr) * 4 * LD;   // this CTA's copy: [parity][v | grad][LD] of chain fr
 
     // rows of this CTA: global rows [row0, row0 + nloc)
     const int row0 = crank * p.tiles_per_cta * 8;
@@ -166,7 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
 
     // ---- stage this CTA's rows of Z L (global: n x Q column-major) into shared memory, row-major, zero padded ----
     for (int idx = tid; idx < p.n8 * LD + 8; idx += THREADS) sZL[idx] = 0.0;
-    for (int idx = tid; idx < CB * LD; idx += THREADS) sVP[idx] = 0.0;
+    if (tid < 64) sTab[tid] = GMB_EXP2_TAB[tid];
     __syncthreads();
     for (int idx = tid; idx < nloc * Q; idx += THREADS) {
         const int row = idx % nloc, q = idx / nloc;
@@ -189,12 +205,14 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     if (CL) {
         cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
-        for (int r = 0; r < CS; r++) {
-            xch_of[r] = cluster.map_shared_rank(sXch, r);
-            xll_of[r] = cluster.map_shared_rank(sXll, r);
+        for (int rk = 0; rk < CS; rk++) {
+            xch_of[rk] = cluster.map_shared_rank(sXch, rk);
+            xll_of[rk] = cluster.map_shared_rank(sXll, rk);
         }
+    } else {
+        xch_of[0] = sXch; xll_of[0] = sXll;
     }
-    int par = 0;                                      // parity of the exchange buffer in use
+    int par = 0;                                      // parity of the exchange buffer in use (cluster variant)
 
     const double sigma = p.var_par;
     const double sc = (FL == 7) ? 1.0 / (sigma * sigma) : 1.0;
@@ -203,69 +221,71 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     const int nfull = nloc / 8;                       // tiles without padding rows
     const bool has_tail = (nloc % 8) != 0;
 
-    // ---- chain state (warp = chain, lane = q mod 32) ----
-    double v[QT32], vp[QT32], r[QT32], gc[QT32], g[QT32];
+    // ---- chain state: fragments of v' and r, per-chain scalars (all replicated) ----
+    double vp[KS], r[KS], g[KS];
     double eps = 0.001, ebar = 1.0, H = 0.0, llcur = 0.0, llnew = 0.0;   // initialise_u, mhmcmc.h:47-59
-    int accept = 0, steps = 1;
+    int accept = 0, steps = 1, cur = 0;
     double totsteps = 0.0, lastprob = 0.0;
 #pragma unroll
-    for (int k = 0; k < QT32; k++) {
-        const int q = lane + 32 * k;
+    for (int j = 0; j < KS; j++) {
+        const int q = 4 * j + fk;
         double z0, z1;
         dev_rng_normal2(p.seed, (uint32_t)(q >> 1), 0u, gchain, 0u, z0, z1);
-        v[k] = (q < Q) ? ((q & 1) ? z1 : z0) : 0.0;
-        vp[k] = v[k]; r[k] = 0.0; gc[k] = 0.0; g[k] = 0.0;
-        if (q < Q) sVP[warp * LD + q] = vp[k];
+        vp[j] = (q < Q) ? ((q & 1) ? z1 : z0) : 0.0;
+        r[j] = 0.0;
     }
-    if (lane == 0) sSteps[warp] = 1;
     if (CL) cg::this_cluster().sync();                // every CTA's shared memory is initialised before any remote store
     else __syncthreads();
 
-    // One evaluation of the gradient at the v' currently in sVP, for the 8 chains of the group.
-    // s = leapfrog step index; the log-likelihood of chain c is accumulated when s == sSteps[c] - 1 (with_ll says whether
-    // any chain of the group is on its last step).  On return g[] holds grad(v') for this warp's chain and llnew its
-    // family log-likelihood (if this was its last step).
-    auto grad_eval = [&](int s, bool with_ll) {
-        double bf[KS];
-#pragma unroll
-        for (int j = 0; j < KS; j++) bf[j] = sVP[fr * LD + 4 * j + fk];
+    // One evaluation of the gradient at the v' held in vp[], for the 8 chains of the group.
+    // s = leapfrog step index; st0 / st1 = step counts of chains 2 fk and 2 fk + 1 (the accumulator columns of this lane):
+    // the log-likelihood of a chain is accumulated on its last step (with_ll: some chain of the group is on its last step).
+    // On return g[] holds grad(v') in fragment layout and llnew the family log-likelihood of chain fr (if this was its
+    // last step).
+    auto grad_eval = [&](int s, bool with_ll, int st0, int st1) {
         double gacc[QT8][2];
 #pragma unroll
         for (int i = 0; i < QT8; i++) gacc[i][0] = gacc[i][1] = 0.0;
-        const bool want0 = (s == sSteps[2 * fk] - 1), want1 = (s == sSteps[2 * fk + 1] - 1);
+        const bool want0 = (s == st0 - 1), want1 = (s == st1 - 1);
         double ll0 = 0.0, ll1 = 0.0;
         int tile = warp;
         if (!with_ll) {
+            for (; tile + 3 * NWARP < nfull; tile += 4 * NWARP) {
+                const int r0[4] = {tile * 8, (tile + NWARP) * 8, (tile + 2 * NWARP) * 8, (tile + 3 * NWARP) * 8};
+                fused_tiles<FL, KS, 4, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+            }
             for (; tile + NWARP < nfull; tile += 2 * NWARP) {
                 const int r0[2] = {tile * 8, (tile + NWARP) * 8};
-                fused_tiles<FL, KS, 2, false, false, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 2, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
             for (; tile < nfull; tile += NWARP) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, false, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
             if (has_tail && tile == nfull) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, false, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, true, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
         } else {
             for (; tile < nfull; tile += NWARP) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, true, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, false, true, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
             if (has_tail && tile == nfull) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, true, FASTEXP, CL>(sZL, bf, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, true, true, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
             }
-        }
-        if (with_ll) {
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, 4);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 4);
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, 8);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 8);
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, 16); ll1 += __shfl_xor_sync(0xffffffffu, ll1, 16);
             if (fr == 0) { sLL[warp * CB + 2 * fk] = ll0; sLL[warp * CB + 2 * fk + 1] = ll1; }
         }
+        // ---- deterministic cross-warp sum of the partial gradients (C-fragment layout -> [q][chain] slots) ----
+        double gsum[QT32];                            // this CTA's partial for chain `warp`, q = lane + 32 k
+#pragma unroll
+        for (int k = 0; k < QT32; k++) gsum[k] = 0.0;
         if (!CL) {
-            // ---- deterministic cross-warp sum of the partial gradients: warps 4-7 -> slots, warps 0-3 add, then 4-term sums ----
+            // warps 4-7 -> 4 slots, warps 0-3 add, then warp c sums the 4 slots of chain c
             double* slot = sSlot + (warp & 3) * QP8 * 9;
             if (warp >= 4) {
 #pragma unroll
@@ -286,20 +306,10 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
 #pragma unroll
             for (int k = 0; k < QT32; k++) {
                 const int q = lane + 32 * k;
-                if (q < Q) {
-                    const double gs = ((sSlot[q * 9 + warp] + sSlot[(QP8 + q) * 9 + warp]) + sSlot[(2 * QP8 + q) * 9 + warp]) + sSlot[(3 * QP8 + q) * 9 + warp];
-                    g[k] = -1.0 * vp[k] + sc * gs;                                  // mcmlmodel.h:163 + :173/:191/:235
-                }
-            }
-            if (with_ll && s == steps - 1) {
-                double l = 0.0;
-#pragma unroll
-                for (int w = 0; w < NWARP; w++) l += sLL[w * CB + warp];
-                llnew = l;
+                if (q < LD) gsum[k] = ((sSlot[q * 9 + warp] + sSlot[(QP8 + q) * 9 + warp]) + sSlot[(2 * QP8 + q) * 9 + warp]) + sSlot[(3 * QP8 + q) * 9 + warp];
             }
         } else {
-            // ---- cluster variant: every warp stores its partial, one barrier, warp c sums the 8 partials of chain c in warp
-            //      order and hands the CTA's partial to every CTA of the cluster; cluster barrier; sum over ranks in rank order ----
+            // every warp stores its partial; one barrier; warp c sums the 8 partials of chain c in warp order
             double* slot = sSlot + warp * QP8 * 9;
 #pragma unroll
             for (int i = 0; i < QT8; i++) {
@@ -310,129 +320,137 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
 #pragma unroll
             for (int k = 0; k < QT32; k++) {
                 const int q = lane + 32 * k;
-                if (q < Q) {
-                    double gs = sSlot[q * 9 + warp];
+                if (q < LD) {
+                    double t = sSlot[q * 9 + warp];
 #pragma unroll
-                    for (int w = 1; w < NWARP; w++) gs += sSlot[(w * QP8 + q) * 9 + warp];
-                    const int off = ((par * CS + crank) * CB + warp) * QP8 + q;
-#pragma unroll
-                    for (int rk = 0; rk < CS; rk++) xch_of[rk][off] = gs;
+                    for (int w = 1; w < NWARP; w++) t += sSlot[(w * QP8 + q) * 9 + warp];
+                    gsum[k] = t;
                 }
             }
-            if (with_ll && lane == 0) {
-                double l = 0.0;
-#pragma unroll
-                for (int w = 0; w < NWARP; w++) l += sLL[w * CB + warp];
-                const int off = (par * CS + crank) * CB + warp;
-#pragma unroll
-                for (int rk = 0; rk < CS; rk++) xll_of[rk][off] = l;
-            }
-            cg::this_cluster().sync();
-#pragma unroll
-            for (int k = 0; k < QT32; k++) {
-                const int q = lane + 32 * k;
-                if (q < Q) {
-                    double gs = sXch[((par * CS + 0) * CB + warp) * QP8 + q];
-#pragma unroll
-                    for (int rk = 1; rk < CS; rk++) gs += sXch[((par * CS + rk) * CB + warp) * QP8 + q];
-                    g[k] = -1.0 * vp[k] + sc * gs;                                  // mcmlmodel.h:163 + :173/:191/:235
-                }
-            }
-            if (with_ll && s == steps - 1) {
-                double l = sXll[(par * CS + 0) * CB + warp];
-#pragma unroll
-                for (int rk = 1; rk < CS; rk++) l += sXll[(par * CS + rk) * CB + warp];
-                llnew = l;
-            }
-            par ^= 1;
         }
+        // ---- hand this CTA's partial (chain `warp`) to every CTA of the cluster; barrier; read it back in fragment layout ----
+#pragma unroll
+        for (int k = 0; k < QT32; k++) {
+            const int q = lane + 32 * k;
+            if (q < LD) {
+                const int off = ((par * CS + crank) * CB + warp) * LD + q;
+#pragma unroll
+                for (int rk = 0; rk < CS; rk++) xch_of[rk][off] = gsum[k];
+            }
+        }
+        if (with_ll && lane == 0) {
+            double l = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) l += sLL[w * CB + warp];
+            const int off = (par * CS + crank) * CB + warp;
+#pragma unroll
+            for (int rk = 0; rk < CS; rk++) xll_of[rk][off] = l;
+        }
+        if (CL) cg::this_cluster().sync();
+        else __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KS; j++) {
+            double gs = sXch[((par * CS + 0) * CB + fr) * LD + 4 * j + fk];
+#pragma unroll
+            for (int rk = 1; rk < CS; rk++) gs += sXch[((par * CS + rk) * CB + fr) * LD + 4 * j + fk];
+            g[j] = -1.0 * vp[j] + sc * gs;                                          // mcmlmodel.h:163 + :173/:191/:235
+        }
+        if (with_ll && s == steps - 1) {
+            double l = sXll[(par * CS + 0) * CB + fr];
+#pragma unroll
+            for (int rk = 1; rk < CS; rk++) l += sXll[(par * CS + rk) * CB + fr];
+            llnew = l;
+        }
+        if (CL) par ^= 1;
     };
 
     // gradient and log-likelihood at the initial state (carried over between proposals instead of recomputed, mhmcmc.h:64,82)
-    grad_eval(0, true);
-#pragma unroll
-    for (int k = 0; k < QT32; k++) gc[k] = g[k];
+    grad_eval(0, true, 1, 1);
     llcur = llnew;
-    __syncthreads();
+    if (owner) {
+#pragma unroll
+        for (int j = 0; j < KS; j++) { scr[4 * j + fk] = vp[j]; scr[LD + 4 * j + fk] = g[j]; }
+    }
 
     const int total = p.warmup + p.nsamp;
     const int cols = p.nsamp + 1;
     if (p.warmup == 0 && writer) {                                                 // samples.col(0) = u_, mhmcmc.h:142
 #pragma unroll
-        for (int k = 0; k < QT32; k++) { const int q = lane + 32 * k; if (q < Q) p.dV_out[((size_t)chain * cols) * p.ldq + q] = v[k]; }
+        for (int j = 0; j < KS; j++) { const int q = 4 * j + fk; if (q < Q) p.dV_out[((size_t)chain * cols) * p.ldq + q] = vp[j]; }
     }
 
     for (int t = 0; t < total; t++) {
+        __syncthreads();                               // the owners' scratch stores of the previous proposal are visible
         // ---- new_proposal, mhmcmc.h:61-75 ----
-        double k0 = 0.0;
+        double k0 = 0.0, pv = 0.0;
+        {
+            const double* V = scr + cur * 2 * LD;
+            const double* G = V + LD;
 #pragma unroll
-        for (int k = 0; k < QT32; k++) {
-            const int q = lane + 32 * k;
-            double z0, z1;
-            dev_rng_normal2(p.seed, (uint32_t)(q >> 1), (uint32_t)t, gchain, 2u, z0, z1);          // :62-63
-            const double z = (q & 1) ? z1 : z0;
-            if (q < Q) {
-                k0 += z * z;
-                r[k] = z + (eps / 2) * gc[k];                                                       // :74 (first step)
-                vp[k] = v[k] + eps * r[k];                                                          // :67, :75
-                sVP[warp * LD + q] = vp[k];
+            for (int j = 0; j < KS; j++) {
+                const int q = 4 * j + fk;
+                double z0, z1;
+                dev_rng_normal2(p.seed, (uint32_t)(q >> 1), (uint32_t)t, gchain, 2u, z0, z1);      // :62-63
+                const double z = (q & 1) ? z1 : z0;
+                if (q < Q) {
+                    const double vq = V[q], gq = G[q];
+                    k0 += z * z;
+                    pv += pc - 0.5 * vq * vq;
+                    r[j] = z + (eps / 2) * gq;                                                      // :74 (first step)
+                    vp[j] = vq + eps * r[j];                                                        // :67, :75
+                } else { r[j] = 0.0; vp[j] = 0.0; }
             }
         }
-        k0 = 0.5 * warp_sum(k0);                                                                    // :66
+        k0 = 0.5 * quad_sum(k0);                                                                    // :66
+        pv = quad_sum(pv);
         {
             const double sd = round(p.lambda / eps);                                                // :69
             steps = sd >= (double)p.max_steps ? p.max_steps : (sd < 1.0 ? 1 : (int)sd);             // :69-70
             if (!(sd == sd)) steps = p.max_steps;
             if (!live) steps = 1;
             totsteps += steps;
-            if (lane == 0) sSteps[warp] = steps;
         }
-        __syncthreads();
-        int smax = 1, stc[CB];
-#pragma unroll
-        for (int w = 0; w < CB; w++) { stc[w] = sSteps[w]; smax = max(smax, stc[w]); }
+        int smax = steps;
+        smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, 4));
+        smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, 8));
+        smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, 16));
+        const int st0 = __shfl_sync(0xffffffffu, steps, 8 * fk), st1 = __shfl_sync(0xffffffffu, steps, 8 * fk + 4);
         // ---- leapfrog integrator, :73-78 ----
         for (int s = 0; s < smax; s++) {
-            bool any_last = false;                      // is any chain of the group on its last step (needs its log-likelihood)?
-#pragma unroll
-            for (int w = 0; w < CB; w++) any_last |= (s == stc[w] - 1);
-            grad_eval(s, any_last);
+            const bool any_last = __any_sync(0xffffffffu, s == steps - 1);   // some chain needs its log-likelihood on this step
+            grad_eval(s, any_last, st0, st1);
             if (s < steps) {
+                const bool more = s < steps - 1;
 #pragma unroll
-                for (int k = 0; k < QT32; k++) {
-                    const int q = lane + 32 * k;
-                    if (q < Q) {
-                        double rr = r[k] + (eps / 2) * g[k];                                        // :77
-                        if (s < steps - 1) {
-                            rr = rr + (eps / 2) * g[k];                                             // :74 of the next step
-                            vp[k] = vp[k] + eps * rr;                                               // :75
-                            sVP[warp * LD + q] = vp[k];
-                        }
-                        r[k] = rr;
+                for (int j = 0; j < KS; j++) {
+                    double rr = r[j] + (eps / 2) * g[j];                                            // :77
+                    if (more) {
+                        rr = rr + (eps / 2) * g[j];                                                 // :74 of the next step
+                        vp[j] = vp[j] + eps * rr;                                                   // :75
                     }
+                    r[j] = rr;
+                }
+                if (!more && owner) {                  // candidate state and its gradient, adopted if the proposal is accepted
+                    double* Vc = scr + (cur ^ 1) * 2 * LD;
+#pragma unroll
+                    for (int j = 0; j < KS; j++) { Vc[4 * j + fk] = vp[j]; Vc[LD + 4 * j + fk] = g[j]; }
                 }
             }
-            __syncthreads();
         }
         // ---- Metropolis test and adaptation, :80-117 ----
-        double k1 = 0.0, pv = 0.0, pvp = 0.0;
+        double k1 = 0.0, pvp = 0.0;
 #pragma unroll
-        for (int k = 0; k < QT32; k++) {
-            const int q = lane + 32 * k;
-            if (q < Q) { k1 += r[k] * r[k]; pv += pc - 0.5 * v[k] * v[k]; pvp += pc - 0.5 * vp[k] * vp[k]; }
+        for (int j = 0; j < KS; j++) {
+            if (4 * j + fk < Q) { k1 += r[j] * r[j]; pvp += pc - 0.5 * vp[j] * vp[j]; }
         }
-        k1 = 0.5 * warp_sum(k1); pv = warp_sum(pv); pvp = warp_sum(pvp);
+        k1 = 0.5 * quad_sum(k1); pvp = quad_sum(pvp);
         const double l1 = llcur + pv, l2 = llnew + pvp;                                            // :82-83
         const double prob = fmin(1.0, exp(-l1 + k0 + l2 - k1));                                    // :84
         double u1, u2;
         dev_rng_uniform2(p.seed, 0u, (uint32_t)t, gchain, 3u, u1, u2);                             // :85
         const bool acc = u1 < prob;                                                                // :86
         lastprob = prob;
-        if (acc) {                                                                                 // :102-105
-            accept++; llcur = llnew;
-#pragma unroll
-            for (int k = 0; k < QT32; k++) { v[k] = vp[k]; gc[k] = g[k]; }
-        }
+        if (acc) { accept++; llcur = llnew; cur ^= 1; }                                            // :102-105
         if (t < p.warmup && t < p.adapt) {                                                         // :107-114, :131-136
             const int iter = t + 1;
             const double f1 = 1.0 / (iter + 10);
@@ -448,11 +466,12 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         }
         const int col = t - p.warmup + 1;                                                          // :142 (col 0), :147
         if (col >= 0 && writer) {
+            const double* V = scr + cur * 2 * LD;      // own stores (same thread): visible without a barrier
 #pragma unroll
-            for (int k = 0; k < QT32; k++) { const int q = lane + 32 * k; if (q < Q) p.dV_out[((size_t)chain * cols + col) * p.ldq + q] = v[k]; }
+            for (int j = 0; j < KS; j++) { const int q = 4 * j + fk; if (q < Q) p.dV_out[((size_t)chain * cols + col) * p.ldq + q] = V[q]; }
         }
     }
-    if (writer && lane == 0) {
+    if (writer && fk == 0) {
         const int C = p.C;
         p.cs_out[FS_EPS * C + chain] = eps; p.cs_out[FS_EBAR * C + chain] = ebar; p.cs_out[FS_H * C + chain] = H;
         p.cs_out[FS_LLCUR * C + chain] = llcur; p.cs_out[FS_K0 * C + chain] = 0.0; p.cs_out[FS_ACCEPT * C + chain] = (double)accept;
