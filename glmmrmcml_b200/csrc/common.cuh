@@ -218,12 +218,12 @@ __device__ __forceinline__ double dev_exp(double x) {
 // Table-driven exp for the sampler's inner loop: exp(x) = 2^e * T[j] * exp(r) with x = (64 e + j) ln2/64 + r,
 // |r| <= ln2/128, T = 2^(j/64) (64 doubles staged in shared memory from GMB_EXP2_TAB) and a degree-5 polynomial for
 // exp(r) - 1 (truncation error r^6/720 < 4e-17).  10 FP64-pipe operations and no branch, against ~18 + a range branch for
-// the library exp; error <= 1 ulp.  The argument is clamped to [-700, 700]: beyond that the family residuals that use it
-// are already saturated (1/(1 + e^700) + y - 1 == y - 1 in double precision).
+// the library exp; error <= 1 ulp.  The binary exponent is saturated at +-1008 (e^+-698.7) with integer min/max: beyond
+// that the family residuals that use it are already saturated (1/(1 + e^698) + y - 1 == y - 1 in double precision);
+// valid for |x| < 2e7 (the integer part must fit 32 bits), NaN for NaN.
 __device__ __forceinline__ double dev_exp_tab(double x, const double* __restrict__ tab) {
-    x = fmin(fmax(x, -700.0), 700.0);
     double t = fma(x, 92.33248261689366, 6755399441055744.0);   // 64/ln2 ; 1.5 * 2^52 rounds to the nearest integer
-    const int k = __double2loint(t);
+    int k = __double2loint(t);
     t -= 6755399441055744.0;
     double r = fma(t, -0.010830424667801708, x);               // ln2/64 high part (24 trailing zero bits: t * hi is exact)
     r = fma(t, -2.8447437476627285e-11, r);                    // ln2/64 low part
@@ -234,6 +234,7 @@ __device__ __forceinline__ double dev_exp_tab(double x, const double* __restrict
     q = fma(q, r, 1.0);
     q = q * r;                                                 // exp(r) - 1
     const double m = fma(T, q, T);                             // in [1, 2)
+    k = min(max(k, -64512), 64512);                            // saturate at exp(+-698.7) (integer pipe; valid for |x| < 2e7)
     return __hiloint2double(__double2hiint(m) + ((k >> 6) << 20), __double2loint(m));
 }
 
@@ -247,12 +248,58 @@ __device__ __forceinline__ double dev_rcp_fast(double d) {
     return fma(y, e, y);
 }
 
-// gradient residual with the table-driven exp (same formulas as dev_family_resid below)
+// Gradient residual r(eta) of mcmlmodel.h:170-175 (FL 1: y - e^eta), :184-193 (FL 3: 1/(1 + e^eta) + y - 1), :233-238 (FL 7:
+// y - eta, without the 1/sigma^2) evaluated with dev_exp_tab / dev_rcp_fast, cut into four stages so that a caller can
+// interleave the stages of one tile with the tensor instructions of another (the sampler's software pipeline).
+template <int FL>
+struct ResidStages {
+    double y, x, t, r, T, q;
+    int k;
+    __device__ __forceinline__ void s0(double y_, double eta, const double* __restrict__ tab) {
+        y = y_; x = eta;
+        if (FL == 7) return;
+        t = fma(x, 92.33248261689366, 6755399441055744.0);
+        k = __double2loint(t);
+        t -= 6755399441055744.0;
+        r = fma(t, -0.010830424667801708, x);
+        r = fma(t, -2.8447437476627285e-11, r);
+        T = tab[k & 63];
+    }
+    __device__ __forceinline__ void s1() {
+        if (FL == 7) return;
+        q = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+        q = fma(q, r, 1.0 / 6.0);
+        q = fma(q, r, 0.5);
+        q = fma(q, r, 1.0);
+    }
+    __device__ __forceinline__ void s2() {
+        if (FL == 7) return;
+        q = q * r;
+        const double m = fma(T, q, T);
+        k = min(max(k, -64512), 64512);
+        q = __hiloint2double(__double2hiint(m) + ((k >> 6) << 20), __double2loint(m));   // e^eta
+        if (FL == 3) {
+            t = q + 1.0;                                                                    // d = e^eta + 1
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(t));                           // y0
+            q = fma(-t, r, 1.0);
+            r = fma(r, q, r);                                                               // y1
+        }
+    }
+    __device__ __forceinline__ double s3() {
+        if (FL == 7) return y - x;
+        if (FL == 1) return y - q;
+        q = fma(-t, r, 1.0);
+        r = fma(r, q, r);                                                                   // y2 = 1/(e^eta + 1)
+        return r + y - 1.0;
+    }
+};
+
+// gradient residual in one call (same arithmetic as the four stages)
 template <int FL>
 __device__ __forceinline__ double dev_family_resid_tab(double y, double eta, const double* __restrict__ tab) {
-    if (FL == 1) return y - dev_exp_tab(eta, tab);
-    if (FL == 3) return dev_rcp_fast(dev_exp_tab(eta, tab) + 1.0) + y - 1.0;
-    return y - eta;
+    ResidStages<FL> st;
+    st.s0(y, eta, tab); st.s1(); st.s2();
+    return st.s3();
 }
 
 // moremaths.h:16-24

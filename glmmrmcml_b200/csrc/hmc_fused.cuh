@@ -125,6 +125,90 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
         }
 }
 
+// Software-pipelined variant for NT = 2 or 4 full tiles (no masking, no log-likelihood): the tiles form two halves A and B;
+// the residual stages of A are placed between the eta products of B, and those of B between the gradient products of A,
+// so that the latency-bound scalar FP64 chains of one half overlap the tensor instructions of the other (all warps of a
+// CTA run the same phase at the same time after each barrier, so this overlap has to come from inside the warp).
+template <int FL, int KS, int NT, bool SMROW>
+__device__ __forceinline__ void fused_tiles_pipe(const double* __restrict__ sZL, const double* __restrict__ sTab, const double (&bf)[KS],
+                                                 const int (&r0)[NT], const double* __restrict__ xb, const double* __restrict__ y,
+                                                 int fr, int fk, double (&gacc)[(KS + 1) / 2][2]) {
+    constexpr int LD = 4 * KS, QT8 = (KS + 1) / 2, H = NT / 2;
+    double a[NT][2], xbv[NT], yv[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        const int row = r0[t] + fr;
+        if (SMROW) { xbv[t] = xb[row]; yv[t] = y[row]; }
+        else { xbv[t] = __ldg(xb + row); yv[t] = __ldg(y + row); }
+        a[t][0] = a[t][1] = 0.0;
+    }
+    ResidStages<FL> st[NT][2];
+    double res[NT][2];
+    // eta(A)
+#pragma unroll
+    for (int j = 0; j < KS; j++)
+#pragma unroll
+        for (int t = 0; t < H; t++) dmma884(a[t][0], a[t][1], sZL[(r0[t] + fr) * LD + 4 * j + fk], bf[j]);
+    // eta(B) with the residual stages of A in between
+#pragma unroll
+    for (int j = 0; j < KS; j++) {
+#pragma unroll
+        for (int t = H; t < NT; t++) dmma884(a[t][0], a[t][1], sZL[(r0[t] + fr) * LD + 4 * j + fk], bf[j]);
+#pragma unroll
+        for (int sgi = 0; sgi < 4; sgi++) {
+            if (j == (sgi * KS) / 4) {
+#pragma unroll
+                for (int t = 0; t < H; t++)
+#pragma unroll
+                    for (int c = 0; c < 2; c++) {
+                        if (sgi == 0) st[t][c].s0(yv[t], xbv[t] + a[t][c], sTab);
+                        if (sgi == 1) st[t][c].s1();
+                        if (sgi == 2) st[t][c].s2();
+                        if (sgi == 3) res[t][c] = st[t][c].s3();
+                    }
+            }
+        }
+    }
+    // grad(A) with the residual stages of B in between, then grad(B)
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+#pragma unroll
+        for (int tt = 0; tt < H; tt++) {
+            const int t = half * H + tt;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                // res is held as C fragment [row = lane/4][chain = 2(lane%4) + {0,1}]; the transposed product needs it as
+                // B fragment [k = row = 4h + lane%4][n = chain = lane/4]
+                const int src = 4 * (4 * h + fk) + (fr >> 1);
+                const double t0 = __shfl_sync(0xffffffffu, res[t][0], src);
+                const double t1 = __shfl_sync(0xffffffffu, res[t][1], src);
+                const double b = (fr & 1) ? t1 : t0;
+                const double* zt = sZL + (r0[t] + 4 * h + fk) * LD + fr;
+#pragma unroll
+                for (int i = 0; i < QT8; i++) dmma884(gacc[i][0], gacc[i][1], zt[8 * i], b);
+                if (half == 0) {
+                    // 2 H (tile, h) slots for the 4 stages of B
+                    const int slot = tt * 2 + h;
+#pragma unroll
+                    for (int sgi = 0; sgi < 4; sgi++) {
+                        if (slot == (sgi * 2 * H) / 4) {
+#pragma unroll
+                            for (int u = H; u < NT; u++)
+#pragma unroll
+                                for (int c = 0; c < 2; c++) {
+                                    if (sgi == 0) st[u][c].s0(yv[u], xbv[u] + a[u][c], sTab);
+                                    if (sgi == 1) st[u][c].s1();
+                                    if (sgi == 2) st[u][c].s2();
+                                    if (sgi == 3) res[u][c] = st[u][c].s3();
+                                }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 // Shared-memory carve-up (doubles), shared by the kernel and the host-side size computation.
 struct FusedLayout {
     int zl, tab, rowv, slot, ll, xch, xll, total;   // offsets in doubles
@@ -252,11 +336,11 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         if (!with_ll) {
             for (; tile + 3 * NWARP < nfull; tile += 4 * NWARP) {
                 const int r0[4] = {tile * 8, (tile + NWARP) * 8, (tile + 2 * NWARP) * 8, (tile + 3 * NWARP) * 8};
-                fused_tiles<FL, KS, 4, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles_pipe<FL, KS, 4, CL>(sZL, sTab, vp, r0, rxb, ry, fr, fk, gacc);
             }
             for (; tile + NWARP < nfull; tile += 2 * NWARP) {
                 const int r0[2] = {tile * 8, (tile + NWARP) * 8};
-                fused_tiles<FL, KS, 2, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles_pipe<FL, KS, 2, CL>(sZL, sTab, vp, r0, rxb, ry, fr, fk, gacc);
             }
             for (; tile < nfull; tile += NWARP) {
                 const int r0[1] = {tile * 8};
