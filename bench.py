@@ -340,12 +340,20 @@ def main():
     Zp = np.asfortranarray(pin(cfg["Z"].T).T); Xp = np.asfortranarray(pin(cfg["X"].T).T); yp = pin(cfg["y"]); Lp = np.asfortranarray(pin(L.T).T)
     start = np.concatenate([beta, theta, [1.0]])
 
+    e2e_parts = {"mcmc_sample_s": [], "mcml_optim_s": [], "mcml_hess_s": []}
+
     def e2e_step(i):
+        ta = time.perf_counter()
         u = g.mcmc_sample(Zp, Lp, Xp, yp, beta, cfg["family"], cfg["link"], HMC["warmup"], M_PER_GPU - 1, HMC["lam"], 1.0, 0, 500,
                           HMC["max_steps"], HMC["target_accept"], n_chains=N_CHAINS, seed=seed0 + 100 + i + 1000 * rank)
+        tb = time.perf_counter()
         fit = g.mcml_optim(cfg["cov"], cfg["data"], cfg["eff_range"], Zp, Xp, yp, u, cfg["family"], cfg["link"], start, 0, True)
+        tc = time.perf_counter()
         H = g.mcml_hess(cfg["cov"], cfg["data"], cfg["eff_range"], Zp, Xp, yp, u, cfg["family"], cfg["link"],
                         np.concatenate([fit["beta"], fit["theta"]]), 1e-5, 0)
+        td = time.perf_counter()
+        if i >= 0:
+            e2e_parts["mcmc_sample_s"].append(tb - ta); e2e_parts["mcml_optim_s"].append(tc - tb); e2e_parts["mcml_hess_s"].append(td - tc)
         return u, fit, H
 
     n_e2e = max(2, min(args.steps, 3))
@@ -427,9 +435,11 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
             "e2e": {"value": e2e_val, "unit": "u-samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "calls": "gmb_mcmc_sample + gmb_mcml_optim(mcnr) + gmb_mcml_hess with host buffers", "s_per_step": e2e_s},
+                    "calls": "gmb_mcmc_sample + gmb_mcml_optim(mcnr) + gmb_mcml_hess with host buffers", "s_per_step": e2e_s,
+                    "parts_s": {k: float(np.mean(v)) for k, v in e2e_parts.items()}},
             "gpu_launches": int(launches), "clocks": clk, "wall_s": wall,
-            "roofline": {"kernel": "dgemm_kernel<EpiResid>/<EpiLeapfrog> (sampler contractions)", "bound": "tensor",
+            "roofline": {"kernel": "hmc_fused_kernel<binomial-logit, KS=13> (on-chip sampler: eta = ZL v and grad = ZL^T r(eta) as FP64 DMMA)",
+                         "bound": "tensor",
                          "achieved": hmc_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": hmc_tflops / FP64_DMMA_PEAK_TFLOPS,
                          "traffic": None, "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q,
                          "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_microbench_fp64.txt); "

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libglmmrmcml_b200.so")
+LIB_PATH = os.environ.get("GMB_LIB") or os.path.join(_HERE, "libglmmrmcml_b200.so")   # GMB_LIB: instrumented builds (csrc/Makefile)
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)

@@ -63,6 +63,12 @@ struct gmb_ctx {
 };
 
 int gmb_ctx_scratch(gmb_ctx* ctx, size_t doubles);   // grow d_scratch to at least `doubles`
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync / cudaFreeAsync on the context's stream, release
+// threshold = keep everything): the reference-named entry points build and tear down their device objects on every call, and
+// a plain cudaFree costs between 1 ms and more than a second per call once the process holds larger allocations.
+cudaError_t gmb_dmalloc_raw(gmb_ctx* ctx, void** p, size_t bytes);
+void gmb_dfree(gmb_ctx* ctx, void* p);                // no-op for NULL
+template <class T> static inline cudaError_t gmb_dmalloc(gmb_ctx* ctx, T** p, size_t bytes) { return gmb_dmalloc_raw(ctx, reinterpret_cast<void**>(p), bytes); }
 int gmb_comm_allreduce_dev(gmb_ctx* ctx, double* dbuf, int count);   // in place on ctx->stream; no-op if world==1
 
 struct gmb_model {

@@ -30,6 +30,13 @@ extern "C" int gmb_ctx_create(int device, gmb_ctx** out) {
     GMB_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sms = prop.multiProcessorCount;
     GMB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        // keep freed blocks in the device's default memory pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        GMB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long keep = ~0ull;
+        GMB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     GMB_CUDA(cudaEventCreate(&ctx->ev0));
     GMB_CUDA(cudaEventCreate(&ctx->ev1));
     GMB_CUDA(cudaEventCreate(&ctx->ev2));
@@ -45,11 +52,19 @@ extern "C" int gmb_ctx_create(int device, gmb_ctx** out) {
     return GMB_OK;
 }
 
+cudaError_t gmb_dmalloc_raw(gmb_ctx* ctx, void** p, size_t bytes) {
+    return cudaMallocAsync(p, bytes > 0 ? bytes : 1, ctx->stream);
+}
+
+void gmb_dfree(gmb_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
 int gmb_ctx_scratch(gmb_ctx* ctx, size_t doubles) {
     if (doubles <= ctx->scratch_doubles) return GMB_OK;
-    if (ctx->d_scratch) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(ctx->d_scratch)); ctx->d_scratch = nullptr; }
+    if (ctx->d_scratch) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, ctx->d_scratch); ctx->d_scratch = nullptr; }
     size_t want = round_up_sz(doubles, 1 << 12);
-    GMB_CUDA(cudaMalloc(&ctx->d_scratch, want * sizeof(double)));
+    GMB_CUDA(gmb_dmalloc(ctx, &ctx->d_scratch, want * sizeof(double)));
     ctx->scratch_doubles = want;
     return GMB_OK;
 }
@@ -193,7 +208,7 @@ extern "C" void gmb_ctx_destroy(gmb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->nccl_comm && g_nccl.destroy) g_nccl.destroy(ctx->nccl_comm);
-    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_scratch) { gmb_dfree(ctx, ctx->d_scratch); cudaStreamSynchronize(ctx->stream); }
     if (ctx->d_result) cudaFree(ctx->d_result);
     if (ctx->d_counter) cudaFree(ctx->d_counter);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);

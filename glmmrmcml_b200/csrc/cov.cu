@@ -263,13 +263,13 @@ extern "C" int gmb_cov_create(gmb_ctx* ctx, const int32_t* cov, int rows, const 
     cv->Q = start;
     cv->lblk_doubles = loff;
     cudaSetDevice(ctx->device);
-    GMB_CUDA(cudaMalloc(&cv->d_blocks, sizeof(CovBlock) * cv->B));
-    GMB_CUDA(cudaMalloc(&cv->d_fns, sizeof(CovFn) * cv->fns.size()));
-    GMB_CUDA(cudaMalloc(&cv->d_data, sizeof(double) * (off > 0 ? off : 1)));
-    GMB_CUDA(cudaMalloc(&cv->d_theta, sizeof(double) * (cv->R > 0 ? cv->R : 1)));
-    GMB_CUDA(cudaMalloc(&cv->d_Lblk, sizeof(double) * (loff > 0 ? loff : 1)));
-    GMB_CUDA(cudaMalloc(&cv->d_logdet, sizeof(double) * cv->B));
-    GMB_CUDA(cudaMalloc(&cv->d_status, sizeof(int)));
+    GMB_CUDA(gmb_dmalloc(ctx, &cv->d_blocks, sizeof(CovBlock) * cv->B));
+    GMB_CUDA(gmb_dmalloc(ctx, &cv->d_fns, sizeof(CovFn) * cv->fns.size()));
+    GMB_CUDA(gmb_dmalloc(ctx, &cv->d_data, sizeof(double) * (off > 0 ? off : 1)));
+    GMB_CUDA(gmb_dmalloc(ctx, &cv->d_theta, sizeof(double) * (cv->R > 0 ? cv->R : 1)));
+    GMB_CUDA(gmb_dmalloc(ctx, &cv->d_Lblk, sizeof(double) * (loff > 0 ? loff : 1)));
+    GMB_CUDA(gmb_dmalloc(ctx, &cv->d_logdet, sizeof(double) * cv->B));
+    GMB_CUDA(gmb_dmalloc(ctx, &cv->d_status, sizeof(int)));
     GMB_CUDA(cudaMemcpyAsync(cv->d_blocks, cv->blocks.data(), sizeof(CovBlock) * cv->B, cudaMemcpyHostToDevice, ctx->stream));
     GMB_CUDA(cudaMemcpyAsync(cv->d_fns, cv->fns.data(), sizeof(CovFn) * cv->fns.size(), cudaMemcpyHostToDevice, ctx->stream));
     GMB_CUDA(cudaMemcpyAsync(cv->d_data, data, sizeof(double) * off, cudaMemcpyHostToDevice, ctx->stream));
@@ -282,10 +282,10 @@ extern "C" void gmb_cov_destroy(gmb_cov* cv) {
     if (!cv) return;
     cudaSetDevice(cv->ctx->device);
     cudaStreamSynchronize(cv->ctx->stream);
-    cudaFree(cv->d_blocks); cudaFree(cv->d_fns); cudaFree(cv->d_data); cudaFree(cv->d_theta); cudaFree(cv->d_Lblk);
-    cudaFree(cv->d_logdet); cudaFree(cv->d_status);
-    if (cv->dU) cudaFree(cv->dU);
-    if (cv->d_work) cudaFree(cv->d_work);
+    gmb_dfree(cv->ctx, cv->d_blocks); gmb_dfree(cv->ctx, cv->d_fns); gmb_dfree(cv->ctx, cv->d_data); gmb_dfree(cv->ctx, cv->d_theta); gmb_dfree(cv->ctx, cv->d_Lblk);
+    gmb_dfree(cv->ctx, cv->d_logdet); gmb_dfree(cv->ctx, cv->d_status);
+    if (cv->dU) gmb_dfree(cv->ctx, cv->dU);
+    if (cv->d_work) gmb_dfree(cv->ctx, cv->d_work);
     delete cv;
 }
 
@@ -392,13 +392,13 @@ extern "C" int gmb_cov_gen(gmb_cov* cv, const double* theta, int chol, double* L
     if (!L_out) return GMB_OK;
     size_t Q = cv->Q;
     double* dense = nullptr;
-    GMB_CUDA(cudaMalloc(&dense, sizeof(double) * Q * Q));
+    GMB_CUDA(gmb_dmalloc(ctx, &dense, sizeof(double) * Q * Q));
     GMB_CUDA(cudaMemsetAsync(dense, 0, sizeof(double) * Q * Q, ctx->stream));
     expand_blocks_kernel<<<cv->B, 256, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_Lblk, chol, dense, (int)Q);
     ctx->launches++;
     cudaError_t e = cudaMemcpyAsync(L_out, dense, sizeof(double) * Q * Q, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(dense);
+    gmb_dfree(ctx, dense);
     if (e != cudaSuccess) return gmb_set_error(GMB_ECUDA, "gmb_cov_gen: %s", cudaGetErrorString(e));
     return GMB_OK;
 }
@@ -408,8 +408,8 @@ static int cov_upload_u(gmb_cov* cv, const double* U, int Q, int m, int* ldu) {
     int ld = round_up(Q, 4);
     size_t need = (size_t)ld * (m > 0 ? m : 1);
     if (need > cv->dU_doubles) {
-        if (cv->dU) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(cv->dU)); cv->dU = nullptr; }
-        GMB_CUDA(cudaMalloc(&cv->dU, need * sizeof(double)));
+        if (cv->dU) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, cv->dU); cv->dU = nullptr; }
+        GMB_CUDA(gmb_dmalloc(ctx, &cv->dU, need * sizeof(double)));
         cv->dU_doubles = need;
     }
     if (m > 0)

@@ -174,8 +174,8 @@ int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols
     int chunk = ncols < (int)max_cols ? ncols : (int)max_cols;
     size_t need = (size_t)ldw * chunk;
     if (need > cv->work_doubles) {
-        if (cv->d_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(cv->d_work)); cv->d_work = nullptr; }
-        GMB_CUDA(cudaMalloc(&cv->d_work, need * sizeof(double)));
+        if (cv->d_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, cv->d_work); cv->d_work = nullptr; }
+        GMB_CUDA(gmb_dmalloc(ctx, &cv->d_work, need * sizeof(double)));
         cv->work_doubles = need;
     }
     double* W = cv->d_work;

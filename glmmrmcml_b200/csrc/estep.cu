@@ -32,32 +32,59 @@ __global__ void xb_kernel(int n, int P, int ldn, const double* __restrict__ X, c
 // multiplies the 8 factors (1 + exp(s eta)) of one unrolled step and takes ONE log of the product — the same sum to
 // within a few ulp per term, at one eighth of the log count.
 // ---------------------------------------------------------------------------------------------------
-constexpr double LOGIT_PROD_GUARD = 80.0;   // 8 factors below exp(80) cannot overflow a double
+constexpr int LOGIT_K_GUARD = 7386;   // 64 * 80 / ln 2: factors below exp(80) — 8 of them cannot overflow a double
 
 template <int FL>
 struct RowTerm {
-    double xb, y, rowc, sg;
+    double xb, y, rowc, mask;
+    int smask;      // binomial/logit: 0 for y = 0 (x = eta), -1 for y = 1 (x = -eta)
     __device__ __forceinline__ void init(double xb_, double y_, double rowc_) {
         xb = xb_; y = y_; rowc = rowc_;
-        sg = (y_ == 1.0) ? -1.0 : ((y_ == 0.0) ? 1.0 : 0.0);   // other y contribute nothing (reference leaves logl unset)
+        smask = (y_ == 1.0) ? -1 : 0;
+        mask = (y_ == 1.0 || y_ == 0.0) ? 1.0 : 0.0;   // other y contribute nothing (the reference leaves logl unset)
     }
 };
 
-// accumulates the contribution of one element into (acc, prod)
+// accumulates the contribution of one element into (acc, prod); kmax tracks the largest scaled exponent of the group
 template <int FL>
-__device__ __forceinline__ void ll_accum(const RowTerm<FL>& r, double z, double c0, double inv_sigma, double& acc, double& prod) {
+__device__ __forceinline__ void ll_accum(const RowTerm<FL>& r, double z, double c0, double inv_sigma, const double* __restrict__ tab,
+                                         double& acc, double& prod, int& kmax) {
     const double eta = r.xb + z;                                     // mcmlmodel.h:298
     if (FL == 1) {
-        acc += r.y * eta - exp(eta) - r.rowc;                        // moremaths.h:33-40
+        acc += r.y * eta - dev_exp_tab(eta, tab) - r.rowc;           // moremaths.h:33-40
     } else if (FL == 3) {
-        const double x = r.sg * eta;
-        const double t = fma(fabs(r.sg), exp(x), 1.0);        // |sg| = 0 drops rows whose y is neither 0 nor 1
-        if (x > LOGIT_PROD_GUARD) acc -= log(t);                     // rare: keep the product finite
-        else prod *= t;
+        // 1 + exp(x), x = -eta (y = 1) or eta (y = 0): dev_exp_tab's steps with the sign applied to the reduced argument and the
+        // scaled exponent (round(-a) = -round(a)), so that the sign costs integer instructions only
+        double t = fma(eta, 92.33248261689366, 6755399441055744.0);
+        int k = __double2loint(t);
+        t -= 6755399441055744.0;
+        double rr = fma(t, -0.010830424667801708, eta);
+        rr = fma(t, -2.8447437476627285e-11, rr);
+        k = (k ^ r.smask) - r.smask;
+        rr = __hiloint2double(__double2hiint(rr) ^ (r.smask & 0x80000000), __double2loint(rr));
+        const double T = tab[k & 63];
+        double q = fma(rr, 1.0 / 120.0, 1.0 / 24.0);
+        q = fma(q, rr, 1.0 / 6.0);
+        q = fma(q, rr, 0.5);
+        q = fma(q, rr, 1.0);
+        q = q * rr;
+        const double m = fma(T, q, T);
+        kmax = max(kmax, k);
+        const int kc = min(max(k, -64512), 64512);
+        const double e = __hiloint2double(__double2hiint(m) + ((kc >> 6) << 20), __double2loint(m));
+        prod *= fma(e, r.mask, 1.0);
     } else {
         const double zz = (r.y - eta) * inv_sigma;                   // moremaths.h:75-78
         acc += c0 - 0.5 * zz * zz;
     }
+}
+
+// binomial/logit, rare path: a group whose product could overflow is redone term by term
+template <int FL>
+__device__ __forceinline__ double ll_direct(const RowTerm<FL>& r, double z) {
+    const double eta = r.xb + z;
+    const double x = r.smask ? -eta : eta;
+    return r.mask != 0.0 ? -log(1.0 + exp(x)) : 0.0;
 }
 
 template <int FL>
@@ -68,8 +95,14 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
                                                      double sigma, double* __restrict__ partials,
                                                      unsigned int* __restrict__ counter, double* __restrict__ out) {
     __shared__ double red[32];
+    __shared__ double stab[64];
     __shared__ bool is_last;
     const int TX = blockDim.x, TY = blockDim.y;
+    {
+        const int tt = threadIdx.y * TX + threadIdx.x;
+        if (tt < 64) stab[tt] = GMB_EXP2_TAB[tt];
+        __syncthreads();
+    }
     const int i0 = 2 * (blockIdx.x * TX + threadIdx.x);
     const int j0 = blockIdx.y * cols_per_cta;
     const int j1 = min(j0 + cols_per_cta, ncols);
@@ -88,7 +121,7 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
         RowTerm<FL> r0, r1;
         r0.init(xb0, y[i0], (FL == 1) ? rowc[i0] : 0.0);
         r1.init(xb1, two ? y[i0 + 1] : 0.0, (FL == 1 && two) ? rowc[i0 + 1] : 0.0);
-        if (!two) r1.sg = 0.0;
+        if (!two) r1.mask = 0.0;
         const double* col = zd + i0;
         int j = j0 + threadIdx.y;
         // 4 independent 16-byte loads in flight per thread
@@ -97,21 +130,33 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
 #pragma unroll
             for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const double2*>(col + (size_t)(j + u * TY) * ldn);
             double prod = 1.0, a1 = 0.0;
+            int kmax = -(1 << 30);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                ll_accum<FL>(r0, z[u].x, c0, inv_sigma, acc, prod);
-                ll_accum<FL>(r1, z[u].y, c0, inv_sigma, a1, prod);
+                ll_accum<FL>(r0, z[u].x, c0, inv_sigma, stab, acc, prod, kmax);
+                ll_accum<FL>(r1, z[u].y, c0, inv_sigma, stab, a1, prod, kmax);
             }
-            if (FL == 3) acc += a1 - log(prod);
-            else if (two) acc += a1;
+            if (FL == 3) {
+                if (kmax > LOGIT_K_GUARD) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) d += ll_direct<FL>(r0, z[u].x) + ll_direct<FL>(r1, z[u].y);
+                    acc += d;
+                } else {
+                    acc -= log(prod);
+                }
+            } else if (two) acc += a1;
         }
         for (; j < j1; j += TY) {
             double2 z = *reinterpret_cast<const double2*>(col + (size_t)j * ldn);
             double prod = 1.0, a1 = 0.0;
-            ll_accum<FL>(r0, z.x, c0, inv_sigma, acc, prod);
-            ll_accum<FL>(r1, z.y, c0, inv_sigma, a1, prod);
-            if (FL == 3) acc += a1 - log(prod);
-            else if (two) acc += a1;
+            int kmax = -(1 << 30);
+            ll_accum<FL>(r0, z.x, c0, inv_sigma, stab, acc, prod, kmax);
+            ll_accum<FL>(r1, z.y, c0, inv_sigma, stab, a1, prod, kmax);
+            if (FL == 3) {
+                if (kmax > LOGIT_K_GUARD) acc += ll_direct<FL>(r0, z.x) + ll_direct<FL>(r1, z.y);
+                else acc -= log(prod);
+            } else if (two) acc += a1;
         }
     }
     // flatten thread index for the block reduction
@@ -156,14 +201,15 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
 // Emits per-(column-chunk) row partial sums and per-(row-tile) column sums of r and r^2.
 // ---------------------------------------------------------------------------------------------------
 template <int FL>
-__device__ __forceinline__ void mcnr_terms(double y, double eta, double inv_phi, double& w, double& wu, double& r) {
+__device__ __forceinline__ void mcnr_terms(double y, double eta, double inv_phi, const double* __restrict__ tab, double& w, double& wu, double& r) {
     if (FL == 1) {               // poisson/log : dhdmu = exp(-eta), detadmu = exp(-eta)
-        double mu = exp(eta);
+        double mu = dev_exp_tab(eta, tab);
         r = y - mu; w = mu; wu = r;
-    } else if (FL == 3) {        // binomial/logit : dhdmu = detadmu = 1/(p(1-p))
-        double e = exp(eta);
-        double p = e / (1.0 + e);
-        r = y - p; w = p * (1.0 - p); wu = r;
+    } else if (FL == 3) {        // binomial/logit : dhdmu = detadmu = 1/(p(1-p)); p = e/(1+e) = 1 - 1/(1+e)
+        const double e = dev_exp_tab(eta, tab);
+        const double rc = dev_rcp_fast(1.0 + e);
+        const double p = e * rc;
+        r = y - p; w = p * rc; wu = r;                   // p (1 - p) = e / (1 + e)^2
     } else {                     // gaussian/identity : W = 1/sigma^2
         r = y - eta; w = inv_phi; wu = inv_phi * r;
     }
@@ -176,6 +222,9 @@ __global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int nco
                                                          double* __restrict__ rowpart /* [gridDim.y][2][ldn] */,
                                                          double* __restrict__ colpart /* [gridDim.x][2][ncols] */) {
     extern __shared__ double sm[];   // [8 warps][2][256]
+    __shared__ double stab[64];
+    if (threadIdx.x < 64) stab[threadIdx.x] = GMB_EXP2_TAB[threadIdx.x];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rbase = blockIdx.x * 256;
     const int j0 = blockIdx.y * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
@@ -207,7 +256,7 @@ __global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int nco
                 int e = 2 * k + v;
                 if (ok[e]) {
                     double w, wu, r;
-                    mcnr_terms<FL>(yr[e], xbr[e] + (v ? z[k].y : z[k].x), inv_phi, w, wu, r);
+                    mcnr_terms<FL>(yr[e], xbr[e] + (v ? z[k].y : z[k].x), inv_phi, stab, w, wu, r);
                     wacc[e] += w; sacc[e] += wu; sr += r; sr2 += r * r;
                 }
             }

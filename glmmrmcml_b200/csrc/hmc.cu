@@ -227,8 +227,8 @@ int hmc_layout(gmb_model* mdl, int C, HmcBuffers& b) {
     b.row_tiles = (mdl->n + rt - 1) / rt;
     size_t need = 5 * ldq * C + ldn * C + (size_t)b.row_tiles * C + (size_t)CS_COUNT * C + (size_t)C /*steps as ints*/ + 16;
     if (need > mdl->hmc_work_doubles) {
-        if (mdl->hmc_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(mdl->hmc_work)); mdl->hmc_work = nullptr; mdl->hmc_work_doubles = 0; }
-        GMB_CUDA(cudaMalloc(&mdl->hmc_work, need * sizeof(double)));
+        if (mdl->hmc_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, mdl->hmc_work); mdl->hmc_work = nullptr; mdl->hmc_work_doubles = 0; }
+        GMB_CUDA(gmb_dmalloc(ctx, &mdl->hmc_work, need * sizeof(double)));
         mdl->hmc_work_doubles = need;
     }
     GMB_CUDA(cudaMemsetAsync(mdl->hmc_work, 0, need * sizeof(double), ctx->stream));
@@ -273,11 +273,11 @@ int gmb_hmc_prepare(gmb_model* mdl, const double* L_host) {
     gmb_ctx* ctx = mdl->ctx;
     const size_t ldq = mdl->ldq, ldn = mdl->ldn, Q = mdl->Q;
     if (!mdl->dL) {
-        GMB_CUDA(cudaMalloc(&mdl->dL, sizeof(double) * ldq * Q));
+        GMB_CUDA(gmb_dmalloc(ctx, &mdl->dL, sizeof(double) * ldq * Q));
         GMB_CUDA(cudaMemsetAsync(mdl->dL, 0, sizeof(double) * ldq * Q, ctx->stream));
     }
     if (!mdl->dZL) {
-        GMB_CUDA(cudaMalloc(&mdl->dZL, sizeof(double) * ldn * Q));
+        GMB_CUDA(gmb_dmalloc(ctx, &mdl->dZL, sizeof(double) * ldn * Q));
         GMB_CUDA(cudaMemsetAsync(mdl->dZL, 0, sizeof(double) * ldn * Q, ctx->stream));
     }
     if (L_host) {
@@ -359,8 +359,8 @@ static int hmc_run_fused_timed(gmb_model* mdl, double var_par, int warmup, int n
     gmb_ctx* ctx = mdl->ctx;
     const size_t need = gmb_hmc_fused_cs_doubles(C) + gmb_hmc_fused_scratch_doubles(mdl, C);
     if (need > mdl->hmc_work_doubles) {
-        if (mdl->hmc_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(mdl->hmc_work)); mdl->hmc_work = nullptr; mdl->hmc_work_doubles = 0; }
-        GMB_CUDA(cudaMalloc(&mdl->hmc_work, need * sizeof(double)));
+        if (mdl->hmc_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, mdl->hmc_work); mdl->hmc_work = nullptr; mdl->hmc_work_doubles = 0; }
+        GMB_CUDA(gmb_dmalloc(ctx, &mdl->hmc_work, need * sizeof(double)));
         mdl->hmc_work_doubles = need;
     }
     GMB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -378,8 +378,8 @@ static int hmc_run_fused_timed(gmb_model* mdl, double var_par, int warmup, int n
 static int set_xb(gmb_model* mdl, const double* beta) {
     gmb_ctx* ctx = mdl->ctx;
     if (mdl->beta_cap < mdl->P) {
-        if (mdl->dbeta) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(mdl->dbeta)); mdl->dbeta = nullptr; }
-        GMB_CUDA(cudaMalloc(&mdl->dbeta, sizeof(double) * mdl->P));
+        if (mdl->dbeta) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, mdl->dbeta); mdl->dbeta = nullptr; }
+        GMB_CUDA(gmb_dmalloc(ctx, &mdl->dbeta, sizeof(double) * mdl->P));
         mdl->beta_cap = mdl->P;
     }
     GMB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -408,8 +408,8 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     const size_t ncol = (size_t)C * cols;
     if (ncol > (size_t)1 << 30) return gmb_set_error(GMB_EINVAL, "too many sample columns");
     if (ncol > mdl->v_cap) {
-        if (mdl->dV) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(mdl->dV)); mdl->dV = nullptr; mdl->v_cap = 0; }
-        GMB_CUDA(cudaMalloc(&mdl->dV, sizeof(double) * mdl->ldq * ncol));
+        if (mdl->dV) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, mdl->dV); mdl->dV = nullptr; mdl->v_cap = 0; }
+        GMB_CUDA(gmb_dmalloc(ctx, &mdl->dV, sizeof(double) * mdl->ldq * ncol));
         GMB_CUDA(cudaMemsetAsync(mdl->dV, 0, sizeof(double) * mdl->ldq * ncol, ctx->stream));
         mdl->v_cap = ncol;
     }

@@ -93,6 +93,28 @@ int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, dou
     p.warmup = warmup; p.nsamp = nsamp; p.max_steps = max_steps; p.adapt = adapt; p.C = C;
     p.chain_offset = chain_offset; p.seed = seed; p.dV_out = dV_out; p.cs_out = d_cs;
     p.scratch = d_cs + gmb_hmc_fused_cs_doubles(C);
+    p.timing = nullptr;
+#ifdef GMB_FUSED_TIMING
+    {
+        static long long* d_tim = nullptr;
+        const int ctas = (C + CB - 1) / CB * cs;
+        if (!d_tim) GMB_CUDA(cudaMalloc(&d_tim, sizeof(long long) * 8 * 4096));
+        GMB_CUDA(cudaMemsetAsync(d_tim, 0, sizeof(long long) * 8 * 4096, ctx->stream));
+        p.timing = d_tim;
+        struct Dump { long long* d; int ctas; cudaStream_t st; };
+        static Dump last; last = {d_tim, ctas, ctx->stream};
+        // the caller synchronises the stream; print the previous launch's counters on the next call or at exit
+        static bool reg = false;
+        if (!reg) { reg = true; atexit([] {
+            std::vector<long long> h(8 * 4096); cudaMemcpy(h.data(), last.d, sizeof(long long) * 8 * last.ctas, cudaMemcpyDeviceToHost);
+            long long tot[8] = {0}; for (int b = 0; b < last.ctas; b++) for (int i = 0; i < 8; i++) tot[i] += h[b * 8 + i];
+            long long all = 0; for (int i = 0; i < 8; i++) all += tot[i];
+            const char* nm[8] = {"update+proposal", "tiles", "slots+local sum", "exchange stores", "barrier", "fragment read", "-", "-"};
+            fprintf(stderr, "[GMB_FUSED_TIMING] last launch, %d CTAs, mean cycles per CTA:\n", last.ctas);
+            for (int i = 0; i < 6; i++) fprintf(stderr, "  %-18s %12.0f  %5.1f%%\n", nm[i], (double)tot[i] / last.ctas, 100.0 * tot[i] / (all ? all : 1));
+        }); }
+    }
+#endif
     const size_t smem = fused_smem_bytes(p.n8, p.ld, cs, mdl->flink);
     switch (mdl->flink) {
     case 1: return gmb_fused_launch_fl1(ctx, p, smem, cs);

@@ -46,7 +46,16 @@ struct FusedParams {
     uint32_t chain_offset; unsigned long long seed;
     double* dV_out; double* cs_out;
     double* scratch;                               // [grid][8 chains][2 parities][v | grad][ld] : state at the last accepted proposal
+    long long* timing;                             // GMB_FUSED_TIMING builds only
 };
+
+// Optional per-phase cycle counters (build with EXTRA=-DGMB_FUSED_TIMING): thread 0 of every CTA accumulates clock64()
+// differences per phase of a leapfrog step into FusedParams::timing[blockIdx.x * 8 + phase] (tools/hmc_phase_timing.py).
+#ifdef GMB_FUSED_TIMING
+#define GMB_TICK(i) do { if (tid == 0) { const long long now__ = clock64(); tim_acc[i] += now__ - tim_last; tim_last = now__; } } while (0)
+#else
+#define GMB_TICK(i) do { } while (0)
+#endif
 
 namespace {
 
@@ -321,6 +330,9 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     if (CL) cg::this_cluster().sync();                // every CTA's shared memory is initialised before any remote store
     else __syncthreads();
 
+#ifdef GMB_FUSED_TIMING
+    long long tim_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tim_last = clock64();
+#endif
     // One evaluation of the gradient at the v' held in vp[], for the 8 chains of the group.
     // s = leapfrog step index; st0 / st1 = step counts of chains 2 fk and 2 fk + 1 (the accumulator columns of this lane):
     // the log-likelihood of a chain is accumulated on its last step (with_ll: some chain of the group is on its last step).
@@ -364,6 +376,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, 16); ll1 += __shfl_xor_sync(0xffffffffu, ll1, 16);
             if (fr == 0) { sLL[warp * CB + 2 * fk] = ll0; sLL[warp * CB + 2 * fk + 1] = ll1; }
         }
+        GMB_TICK(1);                                   // tile phase
         // ---- deterministic cross-warp sum of the partial gradients (C-fragment layout -> [q][chain] slots) ----
         double gsum[QT32];                            // this CTA's partial for chain `warp`, q = lane + 32 k
 #pragma unroll
@@ -412,6 +425,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
                 }
             }
         }
+        GMB_TICK(2);                                   // slot stores, barrier(s), local sums
         // ---- hand this CTA's partial (chain `warp`) to every CTA of the cluster; barrier; read it back in fragment layout ----
 #pragma unroll
         for (int k = 0; k < QT32; k++) {
@@ -430,8 +444,10 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
 #pragma unroll
             for (int rk = 0; rk < CS; rk++) xll_of[rk][off] = l;
         }
+        GMB_TICK(3);                                   // exchange stores
         if (CL) cg::this_cluster().sync();
         else __syncthreads();
+        GMB_TICK(4);                                   // cluster barrier
 #pragma unroll
         for (int j = 0; j < KS; j++) {
             double gs = sXch[((par * CS + 0) * CB + fr) * LD + 4 * j + fk];
@@ -446,6 +462,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
             llnew = l;
         }
         if (CL) par ^= 1;
+        GMB_TICK(5);                                   // fragment read
     };
 
     // gradient and log-likelihood at the initial state (carried over between proposals instead of recomputed, mhmcmc.h:64,82)
@@ -502,6 +519,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         // ---- leapfrog integrator, :73-78 ----
         for (int s = 0; s < smax; s++) {
             const bool any_last = __any_sync(0xffffffffu, s == steps - 1);   // some chain needs its log-likelihood on this step
+            GMB_TICK(0);                               // leapfrog update (and, once per proposal, everything outside the step loop)
             grad_eval(s, any_last, st0, st1);
             if (s < steps) {
                 const bool more = s < steps - 1;
@@ -561,6 +579,9 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         p.cs_out[FS_LLCUR * C + chain] = llcur; p.cs_out[FS_K0 * C + chain] = 0.0; p.cs_out[FS_ACCEPT * C + chain] = (double)accept;
         p.cs_out[FS_TOTSTEPS * C + chain] = totsteps; p.cs_out[FS_LASTPROB * C + chain] = lastprob;
     }
+#ifdef GMB_FUSED_TIMING
+    if (tid == 0 && p.timing) for (int i = 0; i < 8; i++) p.timing[blockIdx.x * 8 + i] = tim_acc[i];
+#endif
     if (CL) cg::this_cluster().sync();                // no CTA may exit while a peer can still store into its shared memory
 }
 

@@ -36,8 +36,8 @@ int upload_params(gmb_model* mdl, const double* beta, int count) {
     gmb_ctx* ctx = mdl->ctx;
     if ((size_t)count > ctx->pinned_doubles / 2) return gmb_set_error(GMB_EINVAL, "too many parameter values in one call (%d)", count);
     if (count > mdl->beta_cap) {
-        if (mdl->dbeta) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); GMB_CUDA(cudaFree(mdl->dbeta)); mdl->dbeta = nullptr; }
-        GMB_CUDA(cudaMalloc(&mdl->dbeta, sizeof(double) * count));
+        if (mdl->dbeta) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, mdl->dbeta); mdl->dbeta = nullptr; }
+        GMB_CUDA(gmb_dmalloc(ctx, &mdl->dbeta, sizeof(double) * count));
         mdl->beta_cap = count;
     }
     // the pinned staging area is reused by every call: make sure the previous copy has been consumed
@@ -68,7 +68,7 @@ extern "C" int gmb_model_create(gmb_ctx* ctx, int n, int P, int Q, const double*
     cudaError_t e = cudaSuccess;
     auto alloc0 = [&](double** p, size_t doubles) {
         if (e != cudaSuccess) return;
-        e = cudaMalloc(p, doubles * sizeof(double));
+        e = gmb_dmalloc(ctx, p, doubles * sizeof(double));
         if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, doubles * sizeof(double), ctx->stream);
     };
     alloc0(&mdl->dX, ldn * P); alloc0(&mdl->dZ, ldn * Q); alloc0(&mdl->dy, ldn); alloc0(&mdl->drowc, ldn); alloc0(&mdl->dxb, ldn);
@@ -89,9 +89,9 @@ extern "C" void gmb_model_destroy(gmb_model* mdl) {
     if (!mdl) return;
     cudaSetDevice(mdl->ctx->device);
     cudaStreamSynchronize(mdl->ctx->stream);
-    cudaFree(mdl->dX); cudaFree(mdl->dZ); cudaFree(mdl->dy); cudaFree(mdl->drowc); cudaFree(mdl->dxb); cudaFree(mdl->dbeta);
-    cudaFree(mdl->dU); cudaFree(mdl->dzd); cudaFree(mdl->dZL); cudaFree(mdl->dL);
-    cudaFree(mdl->dV); cudaFree(mdl->hmc_work);
+    gmb_dfree(mdl->ctx, mdl->dX); gmb_dfree(mdl->ctx, mdl->dZ); gmb_dfree(mdl->ctx, mdl->dy); gmb_dfree(mdl->ctx, mdl->drowc); gmb_dfree(mdl->ctx, mdl->dxb); gmb_dfree(mdl->ctx, mdl->dbeta);
+    gmb_dfree(mdl->ctx, mdl->dU); gmb_dfree(mdl->ctx, mdl->dzd); gmb_dfree(mdl->ctx, mdl->dZL); gmb_dfree(mdl->ctx, mdl->dL);
+    gmb_dfree(mdl->ctx, mdl->dV); gmb_dfree(mdl->ctx, mdl->hmc_work);
     delete mdl;
 }
 
@@ -102,12 +102,12 @@ int gmb_model_reserve_samples(gmb_model* mdl, int m) {
     gmb_ctx* ctx = mdl->ctx;
     if (m <= mdl->m_cap) return GMB_OK;
     GMB_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (mdl->dU) { cudaFree(mdl->dU); mdl->dU = nullptr; }
-    if (mdl->dzd) { cudaFree(mdl->dzd); mdl->dzd = nullptr; }
+    if (mdl->dU) { gmb_dfree(ctx, mdl->dU); mdl->dU = nullptr; }
+    if (mdl->dzd) { gmb_dfree(ctx, mdl->dzd); mdl->dzd = nullptr; }
     mdl->m_cap = 0;
     size_t cap = (size_t)m;
-    GMB_CUDA(cudaMalloc(&mdl->dU, sizeof(double) * mdl->ldq * cap));
-    GMB_CUDA(cudaMalloc(&mdl->dzd, sizeof(double) * mdl->ldn * cap));
+    GMB_CUDA(gmb_dmalloc(ctx, &mdl->dU, sizeof(double) * mdl->ldq * cap));
+    GMB_CUDA(gmb_dmalloc(ctx, &mdl->dzd, sizeof(double) * mdl->ldn * cap));
     // padding rows must hold finite values: the streaming kernels load them (and mask the result)
     GMB_CUDA(cudaMemsetAsync(mdl->dU, 0, sizeof(double) * mdl->ldq * cap, ctx->stream));
     GMB_CUDA(cudaMemsetAsync(mdl->dzd, 0, sizeof(double) * mdl->ldn * cap, ctx->stream));
