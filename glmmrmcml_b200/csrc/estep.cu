@@ -124,11 +124,21 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
         if (!two) r1.mask = 0.0;
         const double* col = zd + i0;
         int j = j0 + threadIdx.y;
-        // 4 independent 16-byte loads in flight per thread
-        for (; j + 3 * TY < j1; j += 4 * TY) {
-            double2 z[4];
+        // 4 independent 16-byte loads per group of columns, and the next group's loads are issued before the current group's
+        // arithmetic (register double buffer): 128 bytes in flight per thread while the FP64 chains run
+        double2 z[4], zn[4];
+        bool have = j + 3 * TY < j1;
+        if (have) {
 #pragma unroll
             for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const double2*>(col + (size_t)(j + u * TY) * ldn);
+        }
+        while (have) {
+            const int jn = j + 4 * TY;
+            const bool have_n = jn + 3 * TY < j1;
+            if (have_n) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) zn[u] = *reinterpret_cast<const double2*>(col + (size_t)(jn + u * TY) * ldn);
+            }
             double prod = 1.0, a1 = 0.0;
             int kmax = -(1 << 30);
 #pragma unroll
@@ -146,6 +156,9 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
                     acc -= log(prod);
                 }
             } else if (two) acc += a1;
+#pragma unroll
+            for (int u = 0; u < 4; u++) z[u] = zn[u];
+            j = jn; have = have_n;
         }
         for (; j < j1; j += TY) {
             double2 z = *reinterpret_cast<const double2*>(col + (size_t)j * ldn);
@@ -241,12 +254,22 @@ __global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int nco
             yr[2 * k + v] = ok[2 * k + v] ? y[i] : 0.0;
             wacc[2 * k + v] = 0.0; sacc[2 * k + v] = 0.0;
         }
-    for (int j = j0 + warp; j < j1; j += 8) {
-        const double* col = zd + (size_t)j * ldn + rbase + 2 * lane;
-        double2 z[4];
+    // the next column's loads are issued before the current column's arithmetic (register double buffer)
+    double2 z[4], zn[4];
+    bool inrow[4];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            z[k] = (rbase + 64 * k + 2 * lane < ldn) ? *reinterpret_cast<const double2*>(col + 64 * k) : make_double2(0.0, 0.0);
+    for (int k = 0; k < 4; k++) inrow[k] = rbase + 64 * k + 2 * lane < ldn;
+    int j = j0 + warp;
+    if (j < j1) {
+        const double* col = zd + (size_t)j * ldn + rbase + 2 * lane;
+#pragma unroll
+        for (int k = 0; k < 4; k++) z[k] = inrow[k] ? *reinterpret_cast<const double2*>(col + 64 * k) : make_double2(0.0, 0.0);
+    }
+    for (; j < j1; j += 8) {
+        if (j + 8 < j1) {
+            const double* coln = zd + (size_t)(j + 8) * ldn + rbase + 2 * lane;
+#pragma unroll
+            for (int k = 0; k < 4; k++) zn[k] = inrow[k] ? *reinterpret_cast<const double2*>(coln + 64 * k) : make_double2(0.0, 0.0);
         }
         double sr = 0.0, sr2 = 0.0;
 #pragma unroll
@@ -265,6 +288,8 @@ __global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int nco
             colpart[((size_t)blockIdx.x * 2 + 0) * ncols + j] = sr;
             colpart[((size_t)blockIdx.x * 2 + 1) * ncols + j] = sr2;
         }
+#pragma unroll
+        for (int k = 0; k < 4; k++) z[k] = zn[k];
     }
     // cross-warp reduction of the row accumulators
 #pragma unroll
@@ -290,16 +315,28 @@ __global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int nco
 }
 
 // K3 pass 2a: rows — sum the column-chunk partials;  2b: columns — sigma_j = sd(resid_j) (mcmloptim.h:216), summed.
-__global__ void mcnr_rows_kernel(int n, int ldn, int nchunks, const double* __restrict__ rowpart,
-                                 double* __restrict__ wsum, double* __restrict__ ssum) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+__global__ void __launch_bounds__(1024) mcnr_rows_kernel(int n, int ldn, int nchunks, const double* __restrict__ rowpart,
+                                                         double* __restrict__ wsum, double* __restrict__ ssum) {
+    // block (32 rows, 32 chunk lanes): thread (tx, ty) adds chunks ty, ty + 32, ... of row tx; thread (tx, 0) then adds the 32
+    // lane sums in order — a fixed order of addition, ~nchunks/32 dependent loads deep instead of nchunks
+    __shared__ double sa[32][33], sb[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.x * 32 + tx;
     double a = 0.0, b = 0.0;
-    for (int c = 0; c < nchunks; c++) {
-        a += rowpart[((size_t)c * 2 + 0) * ldn + i];
-        b += rowpart[((size_t)c * 2 + 1) * ldn + i];
+    if (i < n) {
+        for (int c = ty; c < nchunks; c += 32) {
+            a += rowpart[((size_t)c * 2 + 0) * ldn + i];
+            b += rowpart[((size_t)c * 2 + 1) * ldn + i];
+        }
     }
-    wsum[i] = a; ssum[i] = b;
+    sa[ty][tx] = a; sb[ty][tx] = b;
+    __syncthreads();
+    if (ty == 0 && i < n) {
+        double ta = 0.0, tb = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) { ta += sa[k][tx]; tb += sb[k][tx]; }
+        wsum[i] = ta; ssum[i] = tb;
+    }
 }
 
 __global__ void __launch_bounds__(256) mcnr_sigma_kernel(int n, int ncols, int ntiles, const double* __restrict__ colpart,
@@ -410,7 +447,7 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
     case 7: mcnr_pass1_kernel<7><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
     default: return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
     }
-    mcnr_rows_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ldn, CC, rowpart, wsum, ssum);
+    mcnr_rows_kernel<<<(n + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(n, ldn, CC, rowpart, wsum, ssum);
     mcnr_sigma_kernel<<<NSIG, 256, 0, ctx->stream>>>(n, ncols, RT, colpart, sigpart);
     mcnr_assemble_kernel<<<nout, 256, 0, ctx->stream>>>(n, P, ldn, mdl->dX, wsum, ssum, sigpart, NSIG, d_out);
     ctx->launches += 4;
