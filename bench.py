@@ -218,6 +218,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     from glmmrmcml_b200 import synth
     cfg = synth.config2(m=M_PER_GPU)
@@ -233,8 +240,9 @@ def main():
         import oracle
         oracle.build()
         vals, det = [], None
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         for it in range(args.warmup + args.steps):
-            t, det = cpu_reference_step(cfg, quick=args.quick)
+            t, det = cpu_reference_step(cfg, threads=ncores, quick=args.quick)   # torchrun exports OMP_NUM_THREADS=1: set it explicitly
             if it >= args.warmup:
                 vals.append(t)
         t_step = float(np.median(vals)) if vals else float("nan")
@@ -248,7 +256,7 @@ def main():
                                            "cannot be built here): 320 HMC proposals of one chain, 2 full log-lik evals, MCNR at m=192/384 "
                                            "(cost ~ m^2), 1 full mvn_ll eval; extrapolated to one full step", "detail": det},
                 "e2e": {"value": v, "unit": "u-samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ---------------- our arm ----------------
@@ -401,6 +409,11 @@ def main():
     ctx.timer_start(); [mdl.mcnr(beta, 1.0) for _ in range(16)]; t_n = ctx.timer_stop()
     extra["mcnr_steps_per_s"] = 16 / (t_n * 1e-3)
 
+    # every collective of this run is behind us: tear the process group down on all ranks together, before rank 0's solo work
+    barrier()
+    if dist is not None:
+        dist.destroy_process_group()
+        dist = None
     peaks, peak_src = load_peaks()
     roofline_estep = None
     if rank == 0:
@@ -408,13 +421,15 @@ def main():
         mbig = 250_000
         rngb = np.random.default_rng(5)
         Ubig = np.asfortranarray(cfg["L"] @ rngb.standard_normal((Q, mbig)))
-        mdl2 = g.Model(ctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+        # rank 0 only: on a context WITHOUT communicator (a collective issued by one rank alone would never return)
+        ctx1 = g.Context(local_rank) if world > 1 else ctx
+        mdl2 = g.Model(ctx1, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
         mdl2.set_u(Ubig)
         mdl2.log_likelihood_batch(Bst[:, :4], np.ones(4))
-        ctx.timer_start(); mdl2.log_likelihood_batch(Bst[:, :8], np.ones(8)); t_big = ctx.timer_stop() / 8
+        ctx1.timer_start(); mdl2.log_likelihood_batch(Bst[:, :8], np.ones(8)); t_big = ctx1.timer_stop() / 8
         bytes_ll = 8.0 * cfg["n"] * mbig + 16.0 * cfg["n"]
         mdl2.mcnr(beta, 1.0)
-        ctx.timer_start(); [mdl2.mcnr(beta, 1.0) for _ in range(4)]; t_nr = ctx.timer_stop() / 4
+        ctx1.timer_start(); [mdl2.mcnr(beta, 1.0) for _ in range(4)]; t_nr = ctx1.timer_stop() / 4
         bytes_nr = 8.0 * cfg["n"] * mbig + 8.0 * cfg["n"] * (P + 2)
         roofline_estep = {"kernel": "loglik_kernel<binomial-logit>", "bound": "hbm", "achieved": bytes_ll / (t_big * 1e-3) / 1e9,
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bytes_ll / (t_big * 1e-3) / 1e9 / peaks["hbm_gbs"],
@@ -426,7 +441,8 @@ def main():
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        t_cpu, det = cpu_reference_step(cfg, quick=args.quick)
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        t_cpu, det = cpu_reference_step(cfg, threads=ncores, quick=args.quick)
         cpu = {"value": M_PER_GPU / t_cpu, "unit": "u-samples/s", "cores": det["threads"], "kind": "port",
                "sample": "oracle FAITHFUL mode (reference loop structure incl. its redundant Z u GEMMs and per-sample Cholesky): 320 HMC "
                          "proposals of one chain, 2 full log-lik evals, MCNR at m=384/768 (cost ~ m^2), 1 full mvn_ll eval; "
@@ -446,9 +462,7 @@ def main():
                                         "MEASURED_PEAKS.json has no fp64 entry (bf16 tensor peak does not apply to an fp64 kernel)"},
             "roofline_estep": roofline_estep, "cpu_baseline": cpu}
     line.update(extra)
-    print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    emit(line)
 
 
 if __name__ == "__main__":
