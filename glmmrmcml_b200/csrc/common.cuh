@@ -124,6 +124,9 @@ struct gmb_cov {
     double* dU = nullptr; size_t dU_doubles = 0;
     // large-block workspace
     double* d_work = nullptr; size_t work_doubles = 0;
+    // inverses of the 64 x 64 diagonal blocks of the large blocks' factors (cov_large.cu), 64 x 64 col-major each
+    double* d_linv = nullptr; size_t linv_doubles = 0;
+    std::vector<long long> linv_off;     // per block: offset into d_linv (-1 for blocks that take the small / medium path)
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -286,6 +286,7 @@ extern "C" void gmb_cov_destroy(gmb_cov* cv) {
     gmb_dfree(cv->ctx, cv->d_logdet); gmb_dfree(cv->ctx, cv->d_status);
     if (cv->dU) gmb_dfree(cv->ctx, cv->dU);
     if (cv->d_work) gmb_dfree(cv->ctx, cv->d_work);
+    if (cv->d_linv) gmb_dfree(cv->ctx, cv->d_linv);
     delete cv;
 }
 

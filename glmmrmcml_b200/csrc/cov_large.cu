@@ -1,5 +1,5 @@
-// cov_large.cu — covariance blocks larger than a warp: blocked right-looking Cholesky and blocked forward
-// substitution with many right-hand sides, both built on the DMMA GEMM (gemm_f64.cu).
+// cov_large.cu — covariance blocks larger than a warp: two-level blocked right-looking Cholesky and two-level blocked
+// forward substitution with many right-hand sides, both built on the DMMA GEMM (gemm_f64.cu).
 //
 // Replaces, for one dense block (e.g. the fexp Gaussian-process block of configs C3/C5), glmmrBase
 // gen_block_mat(b, true, false) (unblocked Cholesky–Banachiewicz) and the per-sample
@@ -45,15 +45,23 @@ __global__ void build_block_kernel(CovBlock b, const CovFn* __restrict__ fns, co
     A[i + (size_t)j * ld] = v;
 }
 
-// unblocked Cholesky of the kb x kb diagonal block at (k0, k0), one CTA of 64 threads (thread = row), in shared memory
-__global__ void __launch_bounds__(NB) potf2_kernel(double* __restrict__ A, int ld, int k0, int kb, int row_offset, int* __restrict__ status) {
+// unblocked Cholesky of the kb x kb diagonal block at (k0, k0), one CTA of 64 threads (thread = row), in shared memory;
+// also writes the inverse of the factor (64 x 64 col-major, zero padded) to Linv: the panel solve of the factorisation and
+// the diagonal solves of the forward substitution then run as DMMA GEMMs instead of one serial recurrence per thread.
+__global__ void __launch_bounds__(NB) potf2_kernel(double* __restrict__ A, int ld, int k0, int kb, int row_offset, int* __restrict__ status,
+                                                   double* __restrict__ Linv) {
     __shared__ double s[NB][NB + 1];
     const int t = threadIdx.x;
-    if (t < kb) for (int j = 0; j <= t; j++) s[t][j] = A[(k0 + t) + (size_t)(k0 + j) * ld];
+    for (int j = 0; j < NB; j++) s[t][j] = (t < kb && j <= t && j < kb) ? A[(k0 + t) + (size_t)(k0 + j) * ld] : (t == j ? 1.0 : 0.0);
     __syncthreads();
     for (int j = 0; j < kb; j++) {
-        double sum = 0.0;
-        if (t >= j && t < kb) for (int k = 0; k < j; k++) sum += s[t][k] * s[j][k];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (t >= j && t < kb) {
+            int k = 0;
+            for (; k + 3 < j; k += 4) { s0 += s[t][k] * s[j][k]; s1 += s[t][k + 1] * s[j][k + 1]; s2 += s[t][k + 2] * s[j][k + 2]; s3 += s[t][k + 3] * s[j][k + 3]; }
+            for (; k < j; k++) s0 += s[t][k] * s[j][k];
+        }
+        const double sum = (s0 + s1) + (s2 + s3);
         __shared__ double djj;
         if (t == j) djj = s[j][j] - sum;
         __syncthreads();
@@ -64,23 +72,18 @@ __global__ void __launch_bounds__(NB) potf2_kernel(double* __restrict__ A, int l
         __syncthreads();
     }
     if (t < kb) for (int j = 0; j < kb; j++) A[(k0 + t) + (size_t)(k0 + j) * ld] = (j <= t) ? s[t][j] : 0.0;
-}
-
-// panel solve: rows r >= k0+kb of columns [k0, k0+kb) <- A[r, k0:k0+kb] * L_kk^{-T} ; thread = row
-__global__ void __launch_bounds__(128) trsm_panel_kernel(double* __restrict__ A, int ld, int n, int k0, int kb) {
-    __shared__ double Lkk[NB][NB + 1];
-    for (int e = threadIdx.x; e < kb * kb; e += blockDim.x) { int i = e % kb, j = e / kb; Lkk[i][j] = A[(k0 + i) + (size_t)(k0 + j) * ld]; }
-    __syncthreads();
-    int r = k0 + kb + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
+    // inverse: thread t solves L x = e_t (rows/cols >= kb form an identity block); every thread runs the same recurrence on
+    // broadcast reads of L, entries above the diagonal come out as exact zeros
     double x[NB];
-#pragma unroll 1
-    for (int j = 0; j < kb; j++) {
-        double v = A[r + (size_t)(k0 + j) * ld];
-        for (int k = 0; k < j; k++) v -= x[k] * Lkk[j][k];
-        x[j] = v / Lkk[j][j];
-        A[r + (size_t)(k0 + j) * ld] = x[j];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+        double a0 = (i == t) ? 1.0 : 0.0, a1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < i; k++) { if (k & 1) a1 -= s[i][k] * x[k]; else a0 -= s[i][k] * x[k]; }
+        x[i] = (a0 + a1) / s[i][i];
     }
+#pragma unroll
+    for (int i = 0; i < NB; i++) Linv[i + (size_t)t * NB] = (i >= t && i < kb && t < kb) ? x[i] : 0.0;
 }
 
 __global__ void logdet_diag_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ out) {
@@ -89,30 +92,6 @@ __global__ void logdet_diag_kernel(const double* __restrict__ A, int ld, int n, 
     for (int i = threadIdx.x; i < n; i += blockDim.x) c += 2.0 * log(A[i + (size_t)i * ld]);
     c = block_sum(c, red);
     if (threadIdx.x == 0) out[0] = c;
-}
-
-// diagonal-block solve for the blocked forward substitution: W[k0:k0+kb, j] <- L_kk^{-1} W[k0:k0+kb, j]; thread = column
-__global__ void __launch_bounds__(128) trsv_cols_kernel(const double* __restrict__ A, int ld, int k0, int kb,
-                                                        double* __restrict__ W, int ldw, int ncols) {
-    extern __shared__ double sm[];
-    double* Lkk = sm;                  // kb x kb (col-major), reciprocal diagonal
-    double* z = sm + NB * NB;          // [kb][128]
-    for (int e = threadIdx.x; e < kb * kb; e += blockDim.x) {
-        int i = e % kb, j = e / kb;
-        double v = A[(k0 + i) + (size_t)(k0 + j) * ld];
-        Lkk[e] = (i == j) ? 1.0 / v : v;
-    }
-    __syncthreads();
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= ncols) return;
-    double* w = W + (size_t)j * ldw + k0;
-    for (int i = 0; i < kb; i++) {
-        double lsum = 0.0;
-        for (int k = 0; k < i; k++) lsum += Lkk[i + k * kb] * z[k * 128 + threadIdx.x];
-        double zi = (w[i] - lsum) * Lkk[i + i * kb];
-        z[i * 128 + threadIdx.x] = zi;
-        w[i] = zi;
-    }
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ W, int ldw, int n, int ncols, double* __restrict__ partials) {
@@ -134,26 +113,66 @@ __global__ void copy_rows_kernel(const double* __restrict__ U, int ldu, int star
 
 }  // namespace
 
+// Two-level blocking.  Panels of NB = 64 columns are factorised in shared memory (potf2 + panel solve); their updates are
+// applied right away only INSIDE the current outer block of NBO = 256 columns, and the trailing matrix receives one
+// rank-256 update per outer block, split into block columns so that only the lower trapezoid is computed.  The rank-64
+// updates of the plain right-looking form ran the DMMA GEMM with a 4-iteration k loop (pipeline fill/drain dominated) and
+// computed the full square.
+constexpr int NBO = 256;   // outer block
+constexpr int NBC = 512;   // block-column width of the trailing update
+
+// storage for the inverted diagonal blocks of large block `bi` (allocated for all large blocks at first use)
+static int linv_buffer(gmb_cov* cv, int bi, double** out) {
+    gmb_ctx* ctx = cv->ctx;
+    if (cv->linv_off.empty()) {
+        long long off = 0;
+        cv->linv_off.assign(cv->blocks.size(), -1);
+        for (size_t k = 0; k < cv->blocks.size(); k++)
+            if (cv->blocks[k].n > GMB_COV_SMALL_MAX) { cv->linv_off[k] = off; off += (long long)((cv->blocks[k].n + NB - 1) / NB) * NB * NB; }
+        cv->linv_doubles = (size_t)off;
+        GMB_CUDA(gmb_dmalloc(ctx, &cv->d_linv, sizeof(double) * (off > 0 ? off : 1)));
+    }
+    if (cv->linv_off[bi] < 0) return gmb_set_error(GMB_ESTATE, "block %d has no inverse-diagonal storage", bi);
+    *out = cv->d_linv + cv->linv_off[bi];
+    return GMB_OK;
+}
+
 int gmb_cov_factor_large(gmb_cov* cv, int bi) {
     gmb_ctx* ctx = cv->ctx;
     const CovBlock& b = cv->blocks[bi];
     const int n = b.n, ld = gmb_cov_ld(n);
     double* A = cv->d_Lblk + b.l0;
+    double* linv = nullptr;
+    GMB_TRY(linv_buffer(cv, bi, &linv));
     dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8);
     build_block_kernel<<<grd, blk, 0, ctx->stream>>>(b, cv->d_fns, cv->d_data, cv->d_theta, A, ld);
     ctx->launches++;
-    for (int k0 = 0; k0 < n; k0 += NB) {
-        int kb = n - k0 < NB ? n - k0 : NB;
-        potf2_kernel<<<1, NB, 0, ctx->stream>>>(A, ld, k0, kb, b.start, cv->d_status);
-        ctx->launches++;
-        int rest = n - k0 - kb;
-        if (rest > 0) {
-            trsm_panel_kernel<<<(rest + 127) / 128, 128, 0, ctx->stream>>>(A, ld, n, k0, kb);
+    for (int K0 = 0; K0 < n; K0 += NBO) {
+        const int KB = n - K0 < NBO ? n - K0 : NBO;
+        const int Kend = K0 + KB;
+        for (int k0 = K0; k0 < Kend; k0 += NB) {
+            const int kb = Kend - k0 < NB ? Kend - k0 : NB;
+            double* Li = linv + (size_t)(k0 / NB) * NB * NB;
+            potf2_kernel<<<1, NB, 0, ctx->stream>>>(A, ld, k0, kb, b.start, cv->d_status, Li);
             ctx->launches++;
-            // trailing update A22 -= P P^T  (P = A[k0+kb:, k0:k0+kb]); full square, the upper part is never read
-            const double* Pm = A + (k0 + kb) + (size_t)k0 * ld;
-            double* A22 = A + (k0 + kb) + (size_t)(k0 + kb) * ld;
-            GMB_TRY(gmb_dgemm(ctx, 0, 1, rest, rest, kb, -1.0, Pm, ld, Pm, ld, 1.0, A22, ld));
+            const int rest = n - k0 - kb;
+            if (rest > 0) {
+                // panel solve P <- P L_kk^{-T}, in place: a CTA tile spans all kb <= 64 columns, so it only reads its own rows
+                double* Pp = A + (k0 + kb) + (size_t)k0 * ld;
+                GMB_TRY(gmb_dgemm(ctx, 0, 1, rest, kb, kb, 1.0, Pp, ld, Li, NB, 0.0, Pp, ld));
+                // inside the outer block: A[k0+kb:n, k0+kb:Kend] -= P Ptop^T, P = A[k0+kb:n, k0:k0+kb]
+                const int ncols_in = Kend - (k0 + kb);
+                if (ncols_in > 0) {
+                    const double* Pm = A + (k0 + kb) + (size_t)k0 * ld;
+                    GMB_TRY(gmb_dgemm(ctx, 0, 1, rest, ncols_in, kb, -1.0, Pm, ld, Pm, ld, 1.0, A + (k0 + kb) + (size_t)(k0 + kb) * ld, ld));
+                }
+            }
+        }
+        // trailing matrix: A[J:n, J:J+w] -= Pn[J:n, :] Pn[J:J+w, :]^T for block columns J, Pn = A[Kend:n, K0:Kend]
+        for (int J = Kend; J < n; J += NBC) {
+            const int w = n - J < NBC ? n - J : NBC;
+            const double* PJ = A + J + (size_t)K0 * ld;
+            GMB_TRY(gmb_dgemm(ctx, 0, 1, n - J, w, KB, -1.0, PJ, ld, PJ, ld, 1.0, A + J + (size_t)J * ld, ld));
         }
     }
     logdet_diag_kernel<<<1, 256, 0, ctx->stream>>>(A, ld, n, cv->d_logdet + bi);
@@ -179,22 +198,30 @@ int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols
         cv->work_doubles = need;
     }
     double* W = cv->d_work;
-    static bool configured = false;
-    size_t smem = (size_t)(NB * NB + NB * 128) * sizeof(double);
-    if (!configured) { GMB_CUDA(cudaFuncSetAttribute(trsv_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); configured = true; }
+    double* linv = nullptr;
+    GMB_TRY(linv_buffer(cv, bi, &linv));
     int nchunks = (ncols + chunk - 1) / chunk;
     int slots = 64 / nchunks; if (slots < 1) slots = 1;
     for (int c = 0; c < nchunks; c++) {
         int c0 = c * chunk, nc = ncols - c0 < chunk ? ncols - c0 : chunk;
         copy_rows_kernel<<<dim3((ldw + 255) / 256, nc), 256, 0, ctx->stream>>>(dU + (size_t)c0 * ldu, ldu, b.start, n, nc, W, ldw);
         ctx->launches++;
-        for (int k0 = 0; k0 < n; k0 += NB) {
-            int kb = n - k0 < NB ? n - k0 : NB;
-            trsv_cols_kernel<<<(nc + 127) / 128, 128, smem, ctx->stream>>>(A, ld, k0, kb, W, ldw, nc);
-            ctx->launches++;
-            int rest = n - k0 - kb;
-            if (rest > 0)   // W[k0+kb:, :] -= L[k0+kb:, k0:k0+kb] * W[k0:k0+kb, :]
-                GMB_TRY(gmb_dgemm(ctx, 0, 0, rest, nc, kb, -1.0, A + (k0 + kb) + (size_t)k0 * ld, ld, W + k0, ldw, 1.0, W + k0 + kb, ldw));
+        // blocked forward substitution, two levels: 64-row diagonal solves and rank-64 updates inside an outer block of 256
+        // rows, one rank-256 update of all rows below per outer block
+        for (int K0 = 0; K0 < n; K0 += NBO) {
+            const int KB = n - K0 < NBO ? n - K0 : NBO;
+            const int Kend = K0 + KB;
+            for (int k0 = K0; k0 < Kend; k0 += NB) {
+                const int kb = Kend - k0 < NB ? Kend - k0 : NB;
+                // diagonal solve W[k0:k0+kb, :] <- L_kk^{-1} W[k0:k0+kb, :], in place (a CTA tile spans all kb <= 64 rows)
+                GMB_TRY(gmb_dgemm(ctx, 0, 0, kb, nc, kb, 1.0, linv + (size_t)(k0 / NB) * NB * NB, NB, W + k0, ldw, 0.0, W + k0, ldw));
+                const int rows_in = Kend - (k0 + kb);
+                if (rows_in > 0)   // W[k0+kb:Kend, :] -= L[k0+kb:Kend, k0:k0+kb] W[k0:k0+kb, :]
+                    GMB_TRY(gmb_dgemm(ctx, 0, 0, rows_in, nc, kb, -1.0, A + (k0 + kb) + (size_t)k0 * ld, ld, W + k0, ldw, 1.0, W + k0 + kb, ldw));
+            }
+            const int rest = n - Kend;
+            if (rest > 0)          // W[Kend:, :] -= L[Kend:, K0:Kend] W[K0:Kend, :]
+                GMB_TRY(gmb_dgemm(ctx, 0, 0, rest, nc, KB, -1.0, A + Kend + (size_t)K0 * ld, ld, W + K0, ldw, 1.0, W + Kend, ldw));
         }
         if (c < 64) {
             int s0 = (c * slots) % 64;

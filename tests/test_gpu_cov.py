@@ -31,6 +31,8 @@ CASES = {
     "C3": lambda: synth.config3(nloc=250, m=250),
     "C4": lambda: synth.config4(ncl=100, nt=10, k=1, m=300),
     "C5": lambda: synth.config5(nloc=700, nobs=2, m=200),
+    # one dense block spanning several outer blocks (256) and trailing-update block columns (512) of the two-level Cholesky
+    "C3-1100": lambda: synth.config3(nloc=1100, m=130),
 }
 
 
@@ -41,7 +43,7 @@ def test_chol_and_mvn_ll(name, gctx, oracle):
     cv = g.Covariance(gctx, cfg["cov"], cfg["data"], cfg["eff_range"])
     assert (cv.B, cv.Q, cv.R) == oracle.cov_dims(cfg["cov"], cfg["data"])
     for scale in (1.0, 1.3):
-        theta = cfg["theta"] * np.array([scale, 1.0 / scale if name in ("C3", "C5") else min(0.95, scale * cfg["theta"][1]) / cfg["theta"][1]])[: cfg["theta"].size]
+        theta = cfg["theta"] * np.array([scale, 1.0 / scale if name in ("C3", "C5", "C3-1100") else min(0.95, scale * cfg["theta"][1]) / cfg["theta"][1]])[: cfg["theta"].size]
         Lw = oracle.genD(cfg["cov"], cfg["data"], cfg["eff_range"], theta, chol=True)
         Lg = cv.genD(theta, chol=True)
         assert np.max(np.abs(Lg - Lw)) <= 1e-11 * np.max(np.abs(Lw)) * max(1.0, np.linalg.cond(Lw))
