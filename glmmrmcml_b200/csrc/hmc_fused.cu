@@ -109,9 +109,9 @@ int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, dou
             std::vector<long long> h(8 * 4096); cudaMemcpy(h.data(), last.d, sizeof(long long) * 8 * last.ctas, cudaMemcpyDeviceToHost);
             long long tot[8] = {0}; for (int b = 0; b < last.ctas; b++) for (int i = 0; i < 8; i++) tot[i] += h[b * 8 + i];
             long long all = 0; for (int i = 0; i < 8; i++) all += tot[i];
-            const char* nm[8] = {"update+proposal", "tiles", "slots+local sum", "exchange stores", "barrier", "fragment read", "-", "-"};
+            const char* nm[8] = {"update+proposal", "tiles: eta", "slots+local sum", "exchange stores", "barrier", "fragment read", "tiles: residual", "tiles: gradient"};
             fprintf(stderr, "[GMB_FUSED_TIMING] last launch, %d CTAs, mean cycles per CTA:\n", last.ctas);
-            for (int i = 0; i < 6; i++) fprintf(stderr, "  %-18s %12.0f  %5.1f%%\n", nm[i], (double)tot[i] / last.ctas, 100.0 * tot[i] / (all ? all : 1));
+            for (int i = 0; i < 8; i++) fprintf(stderr, "  %-18s %12.0f  %5.1f%%\n", nm[i], (double)tot[i] / last.ctas, 100.0 * tot[i] / (all ? all : 1));
         }); }
     }
 #endif

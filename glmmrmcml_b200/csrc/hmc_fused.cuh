@@ -5,7 +5,8 @@
 //   for every tile of 8 observations (tiles interleaved over the 8 warps, up to 4 tiles in flight per warp)
 //     eta  = xb + (Z L) v'            DMMA m8n8k4, A = Z L rows from shared memory, B = v' fragments in registers
 //     res  = r(eta)                   family residual in the accumulator registers (table-driven exp + Newton reciprocal,
-//                                     branch free so that the 8 residuals of 4 tiles interleave on the FP64 pipe)
+//                                     branch free so that the 8 residuals of 4 tiles interleave on the FP64 pipe; interleaving
+//                                     them with the tensor instructions of other tiles by hand was measured and gave nothing)
 //     G   += (Z L)^T res              DMMA m8n8k4 again: the SAME shared-memory rows read transposed, res moved from
 //                                     accumulator to B-fragment layout with warp shuffles
 // so eta and res never exist in memory, Z L is read from shared memory only, and the two contractions of the
@@ -52,8 +53,10 @@ struct FusedParams {
 // Optional per-phase cycle counters (build with EXTRA=-DGMB_FUSED_TIMING): thread 0 of every CTA accumulates clock64()
 // differences per phase of a leapfrog step into FusedParams::timing[blockIdx.x * 8 + phase] (tools/hmc_phase_timing.py).
 #ifdef GMB_FUSED_TIMING
-#define GMB_TICK(i) do { if (tid == 0) { const long long now__ = clock64(); tim_acc[i] += now__ - tim_last; tim_last = now__; } } while (0)
+struct FusedTim { long long acc[8]; long long last; bool rec; };
+#define GMB_TICK(i) do { if (tim.rec) { const long long now__ = clock64(); tim.acc[i] += now__ - tim.last; tim.last = now__; } } while (0)
 #else
+struct FusedTim { };
 #define GMB_TICK(i) do { } while (0)
 #endif
 
@@ -86,7 +89,7 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
                                             const int (&r0)[NT], int nloc,
                                             const double* __restrict__ xb, const double* __restrict__ y, const double* __restrict__ rowc,
                                             double c0, double sigma, bool want0, bool want1, int fr, int fk,
-                                            double (&gacc)[(KS + 1) / 2][2], double& ll0, double& ll1) {
+                                            double (&gacc)[(KS + 1) / 2][2], double& ll0, double& ll1, FusedTim& tim) {
     constexpr int LD = 4 * KS, QT8 = (KS + 1) / 2;
     double a[NT][2], xbv[NT], yv[NT];
 #pragma unroll
@@ -102,6 +105,7 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
     for (int j = 0; j < KS; j++)
 #pragma unroll
         for (int t = 0; t < NT; t++) dmma884(a[t][0], a[t][1], sZL[(r0[t] + fr) * LD + 4 * j + fk], bf[j]);
+    GMB_TICK(1);                                       // eta products
     double res[NT][2];
 #pragma unroll
     for (int t = 0; t < NT; t++) {
@@ -118,6 +122,7 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
             if (want1 && ok) ll1 += l1;
         }
     }
+    GMB_TICK(6);                                       // residuals
 #pragma unroll
     for (int t = 0; t < NT; t++)
 #pragma unroll
@@ -132,90 +137,7 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
 #pragma unroll
             for (int i = 0; i < QT8; i++) dmma884(gacc[i][0], gacc[i][1], zt[8 * i], b);
         }
-}
-
-// Software-pipelined variant for NT = 2 or 4 full tiles (no masking, no log-likelihood): the tiles form two halves A and B;
-// the residual stages of A are placed between the eta products of B, and those of B between the gradient products of A,
-// so that the latency-bound scalar FP64 chains of one half overlap the tensor instructions of the other (all warps of a
-// CTA run the same phase at the same time after each barrier, so this overlap has to come from inside the warp).
-template <int FL, int KS, int NT, bool SMROW>
-__device__ __forceinline__ void fused_tiles_pipe(const double* __restrict__ sZL, const double* __restrict__ sTab, const double (&bf)[KS],
-                                                 const int (&r0)[NT], const double* __restrict__ xb, const double* __restrict__ y,
-                                                 int fr, int fk, double (&gacc)[(KS + 1) / 2][2]) {
-    constexpr int LD = 4 * KS, QT8 = (KS + 1) / 2, H = NT / 2;
-    double a[NT][2], xbv[NT], yv[NT];
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-        const int row = r0[t] + fr;
-        if (SMROW) { xbv[t] = xb[row]; yv[t] = y[row]; }
-        else { xbv[t] = __ldg(xb + row); yv[t] = __ldg(y + row); }
-        a[t][0] = a[t][1] = 0.0;
-    }
-    ResidStages<FL> st[NT][2];
-    double res[NT][2];
-    // eta(A)
-#pragma unroll
-    for (int j = 0; j < KS; j++)
-#pragma unroll
-        for (int t = 0; t < H; t++) dmma884(a[t][0], a[t][1], sZL[(r0[t] + fr) * LD + 4 * j + fk], bf[j]);
-    // eta(B) with the residual stages of A in between
-#pragma unroll
-    for (int j = 0; j < KS; j++) {
-#pragma unroll
-        for (int t = H; t < NT; t++) dmma884(a[t][0], a[t][1], sZL[(r0[t] + fr) * LD + 4 * j + fk], bf[j]);
-#pragma unroll
-        for (int sgi = 0; sgi < 4; sgi++) {
-            if (j == (sgi * KS) / 4) {
-#pragma unroll
-                for (int t = 0; t < H; t++)
-#pragma unroll
-                    for (int c = 0; c < 2; c++) {
-                        if (sgi == 0) st[t][c].s0(yv[t], xbv[t] + a[t][c], sTab);
-                        if (sgi == 1) st[t][c].s1();
-                        if (sgi == 2) st[t][c].s2();
-                        if (sgi == 3) res[t][c] = st[t][c].s3();
-                    }
-            }
-        }
-    }
-    // grad(A) with the residual stages of B in between, then grad(B)
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-#pragma unroll
-        for (int tt = 0; tt < H; tt++) {
-            const int t = half * H + tt;
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                // res is held as C fragment [row = lane/4][chain = 2(lane%4) + {0,1}]; the transposed product needs it as
-                // B fragment [k = row = 4h + lane%4][n = chain = lane/4]
-                const int src = 4 * (4 * h + fk) + (fr >> 1);
-                const double t0 = __shfl_sync(0xffffffffu, res[t][0], src);
-                const double t1 = __shfl_sync(0xffffffffu, res[t][1], src);
-                const double b = (fr & 1) ? t1 : t0;
-                const double* zt = sZL + (r0[t] + 4 * h + fk) * LD + fr;
-#pragma unroll
-                for (int i = 0; i < QT8; i++) dmma884(gacc[i][0], gacc[i][1], zt[8 * i], b);
-                if (half == 0) {
-                    // 2 H (tile, h) slots for the 4 stages of B
-                    const int slot = tt * 2 + h;
-#pragma unroll
-                    for (int sgi = 0; sgi < 4; sgi++) {
-                        if (slot == (sgi * 2 * H) / 4) {
-#pragma unroll
-                            for (int u = H; u < NT; u++)
-#pragma unroll
-                                for (int c = 0; c < 2; c++) {
-                                    if (sgi == 0) st[u][c].s0(yv[u], xbv[u] + a[u][c], sTab);
-                                    if (sgi == 1) st[u][c].s1();
-                                    if (sgi == 2) st[u][c].s2();
-                                    if (sgi == 3) res[u][c] = st[u][c].s3();
-                                }
-                        }
-                    }
-                }
-            }
-        }
-    }
+    GMB_TICK(7);                                       // gradient products
 }
 
 // Shared-memory carve-up (doubles), shared by the kernel and the host-side size computation.
@@ -329,9 +251,10 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     }
     if (CL) cg::this_cluster().sync();                // every CTA's shared memory is initialised before any remote store
     else __syncthreads();
-
+    FusedTim tim;
 #ifdef GMB_FUSED_TIMING
-    long long tim_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tim_last = clock64();
+    for (int i = 0; i < 8; i++) tim.acc[i] = 0;
+    tim.last = clock64(); tim.rec = (tid == 0);
 #endif
     // One evaluation of the gradient at the v' held in vp[], for the 8 chains of the group.
     // s = leapfrog step index; st0 / st1 = step counts of chains 2 fk and 2 fk + 1 (the accumulator columns of this lane):
@@ -348,35 +271,34 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         if (!with_ll) {
             for (; tile + 3 * NWARP < nfull; tile += 4 * NWARP) {
                 const int r0[4] = {tile * 8, (tile + NWARP) * 8, (tile + 2 * NWARP) * 8, (tile + 3 * NWARP) * 8};
-                fused_tiles_pipe<FL, KS, 4, CL>(sZL, sTab, vp, r0, rxb, ry, fr, fk, gacc);
+                fused_tiles<FL, KS, 4, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             for (; tile + NWARP < nfull; tile += 2 * NWARP) {
                 const int r0[2] = {tile * 8, (tile + NWARP) * 8};
-                fused_tiles_pipe<FL, KS, 2, CL>(sZL, sTab, vp, r0, rxb, ry, fr, fk, gacc);
+                fused_tiles<FL, KS, 2, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             for (; tile < nfull; tile += NWARP) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             if (has_tail && tile == nfull) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, true, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
         } else {
             for (; tile < nfull; tile += NWARP) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, true, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, false, true, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             if (has_tail && tile == nfull) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, true, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1);
+                fused_tiles<FL, KS, 1, true, true, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, 4);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 4);
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, 8);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 8);
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, 16); ll1 += __shfl_xor_sync(0xffffffffu, ll1, 16);
             if (fr == 0) { sLL[warp * CB + 2 * fk] = ll0; sLL[warp * CB + 2 * fk + 1] = ll1; }
         }
-        GMB_TICK(1);                                   // tile phase
         // ---- deterministic cross-warp sum of the partial gradients (C-fragment layout -> [q][chain] slots) ----
         double gsum[QT32];                            // this CTA's partial for chain `warp`, q = lane + 32 k
 #pragma unroll
@@ -580,7 +502,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         p.cs_out[FS_TOTSTEPS * C + chain] = totsteps; p.cs_out[FS_LASTPROB * C + chain] = lastprob;
     }
 #ifdef GMB_FUSED_TIMING
-    if (tid == 0 && p.timing) for (int i = 0; i < 8; i++) p.timing[blockIdx.x * 8 + i] = tim_acc[i];
+    if (tid == 0 && p.timing) for (int i = 0; i < 8; i++) p.timing[blockIdx.x * 8 + i] = tim.acc[i];
 #endif
     if (CL) cg::this_cluster().sync();                // no CTA may exit while a peer can still store into its shared memory
 }
@@ -615,15 +537,17 @@ int launch_fused_cs(gmb_ctx* ctx, const FusedParams& p, size_t smem, int cs) {
 template <int FL>
 int launch_fused_ks(gmb_ctx* ctx, const FusedParams& p, size_t smem, int cs) {
     switch (p.ks) {      // ld / 4; ld = 4 (mod 16)
+    case 13: return launch_fused_cs<FL, 13>(ctx, p, smem, cs);
+#ifndef GMB_FUSED_DEV    /* development builds (EXTRA=-DGMB_FUSED_DEV) instantiate Q <= 52 only: seconds instead of minutes */
     case 1: return launch_fused_cs<FL, 1>(ctx, p, smem, cs);
     case 5: return launch_fused_cs<FL, 5>(ctx, p, smem, cs);
     case 9: return launch_fused_cs<FL, 9>(ctx, p, smem, cs);
-    case 13: return launch_fused_cs<FL, 13>(ctx, p, smem, cs);
     case 17: return launch_fused_cs<FL, 17>(ctx, p, smem, cs);
     case 21: return launch_fused_cs<FL, 21>(ctx, p, smem, cs);
     case 25: return launch_fused_cs<FL, 25>(ctx, p, smem, cs);
     case 29: return launch_fused_cs<FL, 29>(ctx, p, smem, cs);
     case 33: return launch_fused_cs<FL, 33>(ctx, p, smem, cs);
+#endif
     }
     return gmb_set_error(GMB_EINVAL, "no on-chip sampler instantiation for Q = %d", p.Q);
 }
