@@ -33,7 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 M_PER_GPU = 10_000
-N_CHAINS = 500            # per GPU; 20 post-warm-up samples each
+N_CHAINS = 250            # per GPU; 40 columns each (39 post-warm-up draws + the state after warm-up): 32 groups of 8 chains, each
+                          # on a cluster of 4 SMs = 128 CTAs, one wave (the sampler picks the cluster size per run)
 HMC = dict(warmup=500, lam=5.0, max_steps=100, target_accept=0.95, adapt=100)
 N_D_EVALS = 64            # mvn_ll evaluations of one d_optim (BOBYQA over 2 parameters takes 40-80)
 N_HESS = 256              # 4 k^2, k = P + R = 8

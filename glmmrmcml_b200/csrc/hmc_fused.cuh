@@ -73,6 +73,33 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
         : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// ---- cluster exchange primitives: mbarrier with transaction count + st.async (the remote store itself signals the receiver) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, int rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+// 8-byte store into the shared memory of a CTA of the cluster that also signals 8 bytes on that CTA's mbarrier
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                 :: "r"(remote_addr), "l"(__double_as_longlong(v)), "r"(remote_bar) : "memory");
+}
+
 // sum over the 4 lanes that share fr (the 4 k-positions of a fragment)
 __device__ __forceinline__ double quad_sum(double v) {
     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -142,7 +169,7 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
 
 // Shared-memory carve-up (doubles), shared by the kernel and the host-side size computation.
 struct FusedLayout {
-    int zl, tab, rowv, slot, ll, xch, xll, total;   // offsets in doubles
+    int zl, tab, rowv, slot, ll, xch, xll, mbar, total;   // offsets in doubles
 };
 __host__ __device__ inline FusedLayout fused_layout(int n8, int ld, int cs, int fl) {
     const int qp8 = ((ld / 4 + 1) / 2) * 8;
@@ -156,6 +183,7 @@ __host__ __device__ inline FusedLayout fused_layout(int n8, int ld, int cs, int 
     L.ll = o;    o += NWARP * CB;                         // per-warp partial log-likelihoods
     L.xch = o;   o += npar * cs * CB * ld;                // [parity][rank][chain][q] partial gradients of every CTA of the cluster
     L.xll = o;   o += npar * cs * CB;                     // [parity][rank][chain] partial log-likelihoods
+    L.mbar = o;  o += 2;                                  // one mbarrier per parity (cluster variant)
     L.total = o;
     return L;
 }
@@ -179,6 +207,8 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     double* sLL = sm + lay.ll;                        // [NWARP][CB]
     double* sXch = sm + lay.xch;                      // [parities][CS][CB][LD]
     double* sXll = sm + lay.xll;                      // [parities][CS][CB]
+    unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sm + lay.mbar);   // [2]
+    constexpr uint32_t TX_BYTES = (uint32_t)CS * NWARP * (LD + 1) * 8;   // bytes every CTA receives per gradient exchange
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
@@ -198,6 +228,10 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     // ---- stage this CTA's rows of Z L (global: n x Q column-major) into shared memory, row-major, zero padded ----
     for (int idx = tid; idx < p.n8 * LD + 8; idx += THREADS) sZL[idx] = 0.0;
     if (tid < 64) sTab[tid] = GMB_EXP2_TAB[tid];
+    if (CL && tid == 0) {
+        mbar_init(smem_u32(&sBar[0]), 1); mbar_init(smem_u32(&sBar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     for (int idx = tid; idx < nloc * Q; idx += THREADS) {
         const int row = idx % nloc, q = idx / nloc;
@@ -214,19 +248,17 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     const double* rxb = CL ? sXB : p.xb;
     const double* ry = CL ? sY : p.y;
     const double* rrc = CL ? sRC : p.rowc;
-    // remote views of the exchange buffers of every CTA of the cluster (distributed shared memory)
-    double* xch_of[CS];
-    double* xll_of[CS];
+    // shared::cluster addresses of the exchange buffers and mbarriers of every CTA of the cluster (distributed shared memory)
+    uint32_t xch_of[CS], xll_of[CS], bar_of[CS];
     if (CL) {
-        cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
         for (int rk = 0; rk < CS; rk++) {
-            xch_of[rk] = cluster.map_shared_rank(sXch, rk);
-            xll_of[rk] = cluster.map_shared_rank(sXll, rk);
+            xch_of[rk] = mapa_u32(smem_u32(sXch), rk);
+            xll_of[rk] = mapa_u32(smem_u32(sXll), rk);
+            bar_of[rk] = mapa_u32(smem_u32(&sBar[0]), rk);
         }
-    } else {
-        xch_of[0] = sXch; xll_of[0] = sXll;
     }
+    uint32_t phase = 0;                               // bit p: phase parity to wait for on mbarrier p
     int par = 0;                                      // parity of the exchange buffer in use (cluster variant)
 
     const double sigma = p.var_par;
@@ -348,28 +380,41 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
             }
         }
         GMB_TICK(2);                                   // slot stores, barrier(s), local sums
-        // ---- hand this CTA's partial (chain `warp`) to every CTA of the cluster; barrier; read it back in fragment layout ----
+        // ---- hand this CTA's partial (chain `warp`) to every CTA of the cluster and read the sum back in fragment layout.
+        //      Cluster variant: one st.async per element and destination; the store signals the destination's mbarrier
+        //      (complete_tx), so a step needs neither a cluster-wide barrier nor a memory fence ----
+        if (CL && tid == 0) mbar_arrive_expect_tx(smem_u32(&sBar[par]), TX_BYTES);
 #pragma unroll
         for (int k = 0; k < QT32; k++) {
             const int q = lane + 32 * k;
             if (q < LD) {
                 const int off = ((par * CS + crank) * CB + warp) * LD + q;
+                if (CL) {
 #pragma unroll
-                for (int rk = 0; rk < CS; rk++) xch_of[rk][off] = gsum[k];
+                    for (int rk = 0; rk < CS; rk++) st_async_f64(xch_of[rk] + 8u * off, gsum[k], bar_of[rk] + 8u * par);
+                } else {
+                    sXch[off] = gsum[k];
+                }
             }
         }
-        if (with_ll && lane == 0) {
+        if (lane == 0 && (CL || with_ll)) {
             double l = 0.0;
+            if (with_ll) {
 #pragma unroll
-            for (int w = 0; w < NWARP; w++) l += sLL[w * CB + warp];
+                for (int w = 0; w < NWARP; w++) l += sLL[w * CB + warp];
+            }
             const int off = (par * CS + crank) * CB + warp;
+            if (CL) {
 #pragma unroll
-            for (int rk = 0; rk < CS; rk++) xll_of[rk][off] = l;
+                for (int rk = 0; rk < CS; rk++) st_async_f64(xll_of[rk] + 8u * off, l, bar_of[rk] + 8u * par);
+            } else {
+                sXll[off] = l;
+            }
         }
         GMB_TICK(3);                                   // exchange stores
-        if (CL) cg::this_cluster().sync();
+        if (CL) { mbar_wait(smem_u32(&sBar[par]), (phase >> par) & 1u); phase ^= 1u << par; }
         else __syncthreads();
-        GMB_TICK(4);                                   // cluster barrier
+        GMB_TICK(4);                                   // exchange completion
 #pragma unroll
         for (int j = 0; j < KS; j++) {
             double gs = sXch[((par * CS + 0) * CB + fr) * LD + 4 * j + fk];
