@@ -39,6 +39,9 @@ HMC = dict(warmup=500, lam=5.0, max_steps=100, target_accept=0.95, adapt=100)
 N_D_EVALS = 64            # mvn_ll evaluations of one d_optim (BOBYQA over 2 parameters takes 40-80)
 N_HESS = 256              # 4 k^2, k = P + R = 8
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: profiles/r01_microbench_fp64.txt (tools/microbench_fp64.cu)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` captures (profiles/r01_ncu_raw_extract_final.txt):
+SAMPLER_DRAM_BYTES_PER_LAUNCH = 446976.0            # hmc_fused_kernel<3,13,4>: Z L, xb, y are read once, the chain runs out of shared memory
+LOGLIK_DRAM_BYTES_PER_LAUNCH = 1.000278e9 + 3.865e6  # loglik_kernel<3> on 1 GB of zd (algorithmic bytes: 1.000008e9)
 
 
 def load_peaks():
@@ -417,6 +420,7 @@ def main():
         dist = None
     peaks, peak_src = load_peaks()
     roofline_estep = None
+    roofline_sat = None
     if rank == 0:
         # HBM roofline probe of the E-step kernels: same model, 1 GB of zd (> 4 x L2), 8 evaluations in one batch
         mbig = 250_000
@@ -434,9 +438,22 @@ def main():
         bytes_nr = 8.0 * cfg["n"] * mbig + 8.0 * cfg["n"] * (P + 2)
         roofline_estep = {"kernel": "loglik_kernel<binomial-logit>", "bound": "hbm", "achieved": bytes_ll / (t_big * 1e-3) / 1e9,
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bytes_ll / (t_big * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                          "bytes_per_launch": bytes_ll, "ms": t_big, "zd_bytes": 8.0 * cfg["n"] * mbig, "peak_source": peak_src,
+                          "bytes_per_launch": bytes_ll, "traffic": LOGLIK_DRAM_BYTES_PER_LAUNCH, "ms": t_big, "zd_bytes": 8.0 * cfg["n"] * mbig, "peak_source": peak_src,
                           "mcnr": {"achieved": bytes_nr / (t_nr * 1e-3) / 1e9, "frac": bytes_nr / (t_nr * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": t_nr}}
         mdl2.close()
+        # the sampler kernel with every SM busy on 8 tiles per warp (1184 chains = 148 groups, one CTA each): what the kernel
+        # reaches when the job offers enough chains; the timed step above runs 250 chains on clusters of 4 SMs, which is faster
+        # for m = 10^4 (the warm-up bounds the chain length) but spends a larger share of each leapfrog step in the exchange
+        mdl3 = g.Model(ctx1, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+        for rep in range(2):
+            r3 = mdl3.hmc_sample(L, beta, 1.0, warmup=100, nsamp_per_chain=4, lam=HMC["lam"], max_steps=HMC["max_steps"],
+                                 target_accept=HMC["target_accept"], adapt=HMC["adapt"], n_chains=1184, seed=seed0 + 99, keep_on_device=True,
+                                 want_u=False)
+        s3 = r3["stats"]
+        sat_tflops = s3["leapfrog_total"] * 4.0 * cfg["n"] * Q / (s3["kernel_ms"] * 1e-3) / 1e12
+        roofline_sat = {"chains": 1184, "ms": s3["kernel_ms"], "achieved": sat_tflops, "frac": sat_tflops / FP64_DMMA_PEAK_TFLOPS,
+                        "note": "same kernel, 1184 chains (148 CTAs x 8 chains, no cluster split), 104 proposals: kernel capability, not the timed step"}
+        mdl3.close()
 
     if rank != 0:
         return
@@ -458,7 +475,7 @@ def main():
             "roofline": {"kernel": "hmc_fused_kernel<binomial-logit, KS=13> (on-chip sampler: eta = ZL v and grad = ZL^T r(eta) as FP64 DMMA)",
                          "bound": "tensor",
                          "achieved": hmc_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": hmc_tflops / FP64_DMMA_PEAK_TFLOPS,
-                         "traffic": None, "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q,
+                         "traffic": SAMPLER_DRAM_BYTES_PER_LAUNCH, "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q, "saturated": roofline_sat,
                          "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_microbench_fp64.txt); "
                                         "MEASURED_PEAKS.json has no fp64 entry (bf16 tensor peak does not apply to an fp64 kernel)"},
             "roofline_estep": roofline_estep, "cpu_baseline": cpu}

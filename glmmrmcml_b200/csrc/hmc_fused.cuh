@@ -87,6 +87,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
 }
+// (.acquire.cluster is required: with the default CTA scope the st.async data of a peer CTA were observed stale — the chain
+// parity test fails; the price is one CCTL.IVALL, an L1 invalidation, per wait: profiles/r01_ncu_source_hmc_fused_final.txt)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;
     do {

@@ -7,6 +7,6 @@ from glmmrmcml_b200 import synth
 nch = int(sys.argv[1]) if len(sys.argv) > 1 else 500
 ctx = g.Context(0); cfg = synth.config2(m=64)
 mdl = g.Model(ctx, cfg["X"], cfg["Z"], cfg["y"], "binomial", "logit")
-out = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=110, nsamp_per_chain=2, lam=5.0, max_steps=100, target_accept=0.95,
+out = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=60, nsamp_per_chain=2, lam=5.0, max_steps=100, target_accept=0.95,
                      n_chains=nch, seed=3, keep_on_device=True, want_u=False)
 print("fused", out["stats"])
