@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "libref.so")
+SO_OMP = os.path.join(_HERE, "_ref", "libref_omp.so")   # same sources with the reference's OpenMP pragmas on: timing only
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _LIB = None
@@ -20,11 +21,22 @@ def available() -> bool:
     return os.path.exists(SO)
 
 
+def timing_available() -> bool:
+    return os.path.exists(SO_OMP)
+
+
+def use_timing_build():
+    """Route every call of this module to libref_omp.so (bench.py's reference arm; results of mcnr are not reproducible there)."""
+    global _LIB, SO
+    SO = SO_OMP
+    _LIB = None
+
+
 def lib():
     global _LIB
     if _LIB is None:
         L = C.CDLL(SO)
-        for nm in ("ref_family_ll", "ref_log_factorial_approx", "ref_loglik", "ref_log_prob", "ref_mvn_loglik", "ref_logdet"):
+        for nm in ("ref_family_ll", "ref_log_factorial_approx", "ref_loglik", "ref_loglik_reps", "ref_log_prob", "ref_mvn_loglik", "ref_logdet"):
             getattr(L, nm).restype = C.c_double
         L.ref_family_ll.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
         L.ref_log_factorial_approx.argtypes = [C.c_double]
@@ -76,6 +88,13 @@ def loglik(X, Z, U, y, beta, var_par, family, link):
     X = _f(X); Z = _f(Z); U = _f(U); y = _v(y); beta = _v(beta)
     n, P = X.shape; Q, m = U.shape
     return lib().ref_loglik(n, P, Q, m, _d(X), _d(Z), _d(U), _d(y), _d(beta), C.c_double(var_par), family.encode(), link.encode())
+
+
+def loglik_reps(X, Z, U, y, beta, var_par, family, link, reps):
+    """model built once, log_likelihood() evaluated `reps` times (timing helper)."""
+    X = _f(X); Z = _f(Z); U = _f(U); y = _v(y); beta = _v(beta)
+    n, P = X.shape; Q, m = U.shape
+    return lib().ref_loglik_reps(n, P, Q, m, _d(X), _d(Z), _d(U), _d(y), _d(beta), C.c_double(var_par), family.encode(), link.encode(), int(reps))
 
 
 def log_prob(X, Z, L, y, beta, var_par, family, link, v):

@@ -98,6 +98,17 @@ REF_API double ref_loglik(int n, int P, int Q, int m, const double* X, const dou
     return model.log_likelihood();
 }
 
+// the same model, log_likelihood() called `reps` times (what an optimiser does between two sample draws); returns the last value.
+// Used by bench.py's reference arm to time one objective evaluation without the model construction.
+REF_API double ref_loglik_reps(int n, int P, int Q, int m, const double* X, const double* Z, const double* U, const double* y,
+                               const double* beta, double var_par, const char* family, const char* link, int reps) {
+    Eigen::MatrixXd Xm = mat(X, n, P), Zm = mat(Z, n, Q), u = mat(U, Q, m);
+    glmmr::mcmlModel model(Zm, nullptr, Xm, vec(y, n), &u, vec(beta, P), var_par, family, link);
+    double v = 0.0;
+    for (int r = 0; r < reps; r++) v = model.log_likelihood();
+    return v;
+}
+
 // log_prob / log_grad with L given — as src/mcml_full.cpp:332
 REF_API double ref_log_prob(int n, int P, int Q, const double* X, const double* Z, const double* L, const double* y,
                             const double* beta, double var_par, const char* family, const char* link, const double* v) {

@@ -82,7 +82,7 @@ public:
     }
     // dense block, or its Cholesky factor by Cholesky–Banachiewicz (lower, or its transpose when upper)
     Eigen::MatrixXd gen_block_mat(int b, bool chol, bool upper) {
-        data_->subdata(b);
+        if (data_->b_ != b) data_->subdata(b);   // MCMLDmatrix::loglik calls this from an OpenMP loop after selecting b itself: no write then
         const int n = data_->n_dim();
         Eigen::MatrixXd L = Eigen::MatrixXd::Zero(n, n);
         if (!chol) { for (int j = 0; j < n; j++) for (int i = 0; i < n; i++) L(i, j) = get_val(i, j); return L; }
