@@ -1,0 +1,93 @@
+"""Size-independent properties at BASELINE.json's full C2 size (n = 500, Q = 50, m = 10^4) and on a zd larger than L2,
+where the CPU oracle is too slow to be the checker: additivity over column splits (the E-step quantities are means of
+per-sample terms), determinism, agreement of the sampler's cluster variants, Monte-Carlo agreement across seeds."""
+import numpy as np
+import pytest
+
+from glmmrmcml_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2(gctx):
+    import glmmrmcml_b200 as g
+    cfg = synth.config2(m=10_000)
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    cv = g.Covariance(gctx, cfg["cov"], cfg["data"], cfg["eff_range"])
+    yield cfg, mdl, cv
+    mdl.close(); cv.close()
+
+
+def test_estep_is_additive_over_column_splits(c2):
+    cfg, mdl, cv = c2
+    U = cfg["U"]; m = U.shape[1]; cut = 3777
+    beta = cfg["beta"] * 1.05
+    vals = {}
+    for name, cols in (("all", slice(0, m)), ("a", slice(0, cut)), ("b", slice(cut, m))):
+        Us = np.asfortranarray(U[:, cols])
+        mdl.set_u(Us)
+        nr = mdl.mcnr(beta, 1.0)
+        vals[name] = (mdl.log_likelihood(beta, 1.0), nr["xtwx"], nr["score"], nr["sigma"], cv.loglik(cfg["theta"], Us), Us.shape[1])
+    la, lb, lall = vals["a"], vals["b"], vals["all"]
+    wa, wb = la[5] / m, lb[5] / m
+    assert abs(wa * la[0] + wb * lb[0] - lall[0]) <= 1e-12 * abs(lall[0])
+    assert np.max(np.abs(wa * la[1] + wb * lb[1] - lall[1])) <= 1e-12 * np.max(np.abs(lall[1]))
+    assert np.max(np.abs(wa * la[2] + wb * lb[2] - lall[2])) <= 1e-11 * max(1.0, np.max(np.abs(lall[2])))
+    assert abs(wa * la[3] + wb * lb[3] - lall[3]) <= 1e-12 * lall[3]
+    assert abs(wa * la[4] + wb * lb[4] - lall[4]) <= 1e-12 * abs(lall[4])
+
+
+def test_estep_stream_larger_than_l2_is_additive_and_deterministic(gctx):
+    """1 GB of zd (the roofline probe's size): two halves add up to the whole, repeated evaluations are bitwise equal."""
+    import glmmrmcml_b200 as g
+    cfg = synth.config2(m=64)
+    rng = np.random.default_rng(7)
+    m = 250_000
+    U = np.asfortranarray(cfg["L"] @ rng.standard_normal((cfg["Q"], m)))
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    mdl.set_u(U)
+    full = mdl.log_likelihood(cfg["beta"], 1.0)
+    assert mdl.log_likelihood(cfg["beta"], 1.0) == full
+    mdl.set_u(np.asfortranarray(U[:, :100_000])); a = mdl.log_likelihood(cfg["beta"], 1.0)
+    mdl.set_u(np.asfortranarray(U[:, 100_000:])); b = mdl.log_likelihood(cfg["beta"], 1.0)
+    assert abs(0.4 * a + 0.6 * b - full) <= 1e-12 * abs(full)
+    mdl.close()
+
+
+def test_sampler_cluster_variants_agree_at_bench_size(c2):
+    """250 chains, the bench's proposal settings (shortened): cluster sizes 1, 2 and 4 follow the same chains (summation order of the
+    gradient differs, so states agree to rounding amplified by the leapfrog map, and the accept decisions are identical)."""
+    import glmmrmcml_b200 as g
+    cfg, mdl, cv = c2
+    outs = {}
+    try:
+        for cs in (1, 2, 4):
+            g.hmc_set_cluster_size(cs)
+            outs[cs] = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=30, nsamp_per_chain=3, lam=5.0, max_steps=100, target_accept=0.95,
+                                      n_chains=250, seed=20221208, want_u=False, want_v=True)
+    finally:
+        g.hmc_set_cluster_size(0)
+    for cs in (2, 4):
+        assert np.max(np.abs(outs[cs]["v"] - outs[1]["v"])) <= 1e-8
+        assert outs[cs]["stats"]["accept_rate"] == outs[1]["stats"]["accept_rate"]
+    # same seed, same variant: bitwise reproducible
+    again = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=30, nsamp_per_chain=3, lam=5.0, max_steps=100, target_accept=0.95,
+                           n_chains=250, seed=20221208, want_u=False, want_v=True)
+    assert np.array_equal(again["v"], outs[4]["v"]) or np.array_equal(again["v"], outs[2]["v"]) or np.array_equal(again["v"], outs[1]["v"])
+
+
+def test_sampler_posterior_means_agree_across_seeds_at_bench_size(c2):
+    """Full bench draw (250 chains x 40 columns after a 500-iteration warm-up): the posterior mean of every random effect from two
+    seeds agrees within 6 Monte-Carlo standard errors (chains are independent, so the error comes from per-chain means)."""
+    cfg, mdl, cv = c2
+    means, ses = [], []
+    for seed in (5, 6):
+        out = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=500, nsamp_per_chain=39, lam=5.0, max_steps=100, target_accept=0.95,
+                             n_chains=250, seed=seed, want_u=True)
+        assert 0.9 < out["stats"]["accept_rate"] <= 1.0
+        Uc = out["u"].reshape(cfg["Q"], 250, 40, order="F")[:, :, 1:]
+        cm = Uc.mean(axis=2)
+        means.append(cm.mean(axis=1)); ses.append(cm.std(axis=1, ddof=1) / np.sqrt(250))
+    z = np.abs(means[0] - means[1]) / np.sqrt(ses[0] ** 2 + ses[1] ** 2)
+    assert np.max(z) < 6.0, np.max(z)
