@@ -448,7 +448,8 @@ def main():
                          seed=seed0 + 7, keep_on_device=True, want_u=True)
     st = res["stats"]
     hmc_ms = st["kernel_ms"]
-    Uall = res["u"].reshape(Q, N_CHAINS, per, order="F")[:, :, 1:]           # drop each chain's column 0 (warm-up end state)
+    # columns are chain-major (column = chain * per + draw): [q, draw, chain] in Fortran order -> [q, chain, draw]
+    Uall = res["u"].reshape(Q, per, N_CHAINS, order="F").transpose(0, 2, 1)[:, :, 1:]   # drop each chain's column 0 (warm-up end state)
     ess = np.array([ess_geyer(Uall[q]) for q in range(Q)])
     n_post = N_CHAINS * (per - 1)
     extra["hmc"] = {"u_samples_per_s": sum_over_ranks(N_CHAINS * per / (hmc_ms * 1e-3)),

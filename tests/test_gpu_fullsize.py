@@ -86,7 +86,7 @@ def test_sampler_posterior_means_agree_across_seeds_at_bench_size(c2):
         out = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=500, nsamp_per_chain=39, lam=5.0, max_steps=100, target_accept=0.95,
                              n_chains=250, seed=seed, want_u=True)
         assert 0.9 < out["stats"]["accept_rate"] <= 1.0
-        Uc = out["u"].reshape(cfg["Q"], 250, 40, order="F")[:, :, 1:]
+        Uc = out["u"].reshape(cfg["Q"], 40, 250, order="F").transpose(0, 2, 1)[:, :, 1:]    # columns are chain-major: [q, chain, draw]
         cm = Uc.mean(axis=2)
         means.append(cm.mean(axis=1)); ses.append(cm.std(axis=1, ddof=1) / np.sqrt(250))
     z = np.abs(means[0] - means[1]) / np.sqrt(ses[0] ** 2 + ses[1] ** 2)

@@ -94,7 +94,7 @@ def test_gaussian_posterior_moments(gctx):
     nch, ns = 256, 40
     out = mdl.hmc_sample(cfg["L"], cfg["beta"], sigma, warmup=150, nsamp_per_chain=ns, lam=1.5, max_steps=50,
                          target_accept=0.9, n_chains=nch, seed=99, want_u=False, want_v=True)
-    V = out["v"].reshape(cfg["Q"], nch, ns + 1, order="F")[:, :, 1:]
+    V = out["v"].reshape(cfg["Q"], ns + 1, nch, order="F").transpose(0, 2, 1)[:, :, 1:]   # columns are chain-major: [q, chain, draw]
     # chains are independent: use per-chain means to get an honest Monte-Carlo standard error
     cm = V.mean(axis=2)
     est = cm.mean(axis=1); se = cm.std(axis=1, ddof=1) / np.sqrt(nch)
