@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import GmbError, HmcStats, lib, check  # noqa: F401
 
 __all__ = ["Context", "Model", "Covariance", "mvn_ll", "mcmc_sample", "mcml_optim", "mcml_simlik", "mcml_hess",
-           "aic_mcml", "mcml_full", "ModelMCML", "GmbError", "version"]
+           "aic_mcml", "mcml_full", "mcml_la", "mcml_la_nr", "ModelMCML", "GmbError", "version"]
 
 
 def _f(a):
@@ -360,6 +360,38 @@ def mcml_full(cov, data, eff_range, Z, X, y, family, link, start, mcnr=False, m=
                               int(trace), int(refresh), int(maxsteps), float(target_accept), int(n_chains), int(seed),
                               _d(beta), _d(theta), C.byref(sigma), C.byref(conv), C.byref(it), _d(u)))
     return dict(beta=beta, theta=theta, sigma=sigma.value, converged=bool(conv.value), iter=it.value, u=u)
+
+
+def _la(fn, cov, data, eff_range, Z, X, y, family, link, start, usehess, tol, verbose, trace, maxiter):
+    keep, cargs = _covargs(cov, data, eff_range)
+    Z = _f(Z); X = _f(X); y = _v(y); start = _v(start)
+    n, P = X.shape; Q = Z.shape[1]; R = _cov_R(cov)
+    beta = np.zeros(P); theta = np.zeros(R); sigma = C.c_double(); se = np.zeros(start.size); u = np.zeros(Q); it = C.c_int()
+    check(fn(*cargs, _d(Z), _d(X), _d(y), n, P, Q, family.encode(), link.encode(), _d(start), start.size, int(bool(usehess)),
+             float(tol), int(bool(verbose)), int(trace), int(maxiter), _d(beta), _d(theta), C.byref(sigma), _d(se), _d(u), C.byref(it)))
+    return dict(beta=beta, theta=theta, sigma=sigma.value, se=se, u=u.reshape(Q, 1), iter=it.value)
+
+
+def mcml_la(cov, data, eff_range, Z, X, y, family, link, start, usehess=False, tol=1e-3, verbose=True, trace=0, maxiter=10):
+    """src/mcml_la.cpp:28-155 — list(beta, theta, sigma, se, u): Laplace-approximation fit, derivative-free (beta, v) step."""
+    return _la(lib().gmb_mcml_la, cov, data, eff_range, Z, X, y, family, link, start, usehess, tol, verbose, trace, maxiter)
+
+
+def mcml_la_nr(cov, data, eff_range, Z, X, y, family, link, start, usehess=False, tol=1e-3, verbose=True, trace=0, maxiter=10):
+    """src/mcml_la.cpp:178-290 — the same with the Newton-Raphson step mcnr_b for (beta, v)."""
+    return _la(lib().gmb_mcml_la_nr, cov, data, eff_range, Z, X, y, family, link, start, usehess, tol, verbose, trace, maxiter)
+
+
+def la_objectives(cov, data, eff_range, Z, X, y, family, link, beta, theta, v, sigma=1.0, w_use_l=False, newton=True):
+    """Parity hook (gmb_la_objectives): the three Laplace objectives of likelihood.h:112-230 at one state and one mcnr_b step."""
+    keep, cargs = _covargs(cov, data, eff_range)
+    Z = _f(Z); X = _f(X); y = _v(y); beta = _v(beta); theta = _v(theta); v = _v(v)
+    n, P = X.shape; Q = Z.shape[1]
+    out3 = np.zeros(3); bn = np.zeros(P); vn = np.zeros(Q); sn = C.c_double()
+    check(lib().gmb_la_objectives(*cargs, _d(Z), _d(X), _d(y), n, P, Q, family.encode(), link.encode(), _d(beta), _d(theta), theta.size,
+                                  _d(v), float(sigma), int(bool(w_use_l)), _d(out3), _d(bn) if newton else None, _d(vn) if newton else None,
+                                  C.byref(sn)))
+    return dict(la=out3[0], la_cov=out3[1], la_btheta=out3[2], beta_nr=bn, v_nr=vn, sigma_nr=sn.value)
 
 
 def _wrap_objective(fun, n):

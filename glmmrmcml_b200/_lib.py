@@ -83,6 +83,12 @@ PROTOTYPES = {
                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                             C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64,
                                             dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int), dp]),
+    "gmb_mcml_la": (C.c_int, _cov_args + [dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, dp, C.c_int,
+                                          C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]),
+    "gmb_mcml_la_nr": (C.c_int, _cov_args + [dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, dp, C.c_int,
+                                             C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]),
+    "gmb_la_objectives": (C.c_int, _cov_args + [dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, dp, dp, C.c_int, dp,
+                                                C.c_double, C.c_int, dp, dp, dp, dp]),
 }
 
 OBJECTIVE = C.CFUNCTYPE(C.c_int, dp, C.c_int, C.c_int, dp, C.c_void_p)

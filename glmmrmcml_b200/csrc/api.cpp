@@ -204,6 +204,8 @@ int default_chains(int m) {
 
 }  // namespace
 
+int gmb_default_ctx(gmb_ctx** out) { return default_ctx(out); }   // for laplace.cu
+
 // DData::n_cov_pars() and the total block dimension from the cov matrix alone (host arithmetic; lets an adapter size
 // its theta output before calling an entry point).  Parameter counts per function id: R/R6ModelExtMCML.R:430.
 extern "C" int gmb_cov_shape(const int32_t* cov, int rows, int* B_out, int* Q_out, int* R_out) {

@@ -139,11 +139,15 @@ int gmb_dgemm(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double 
 // estep.cu
 int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb);
 int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, double* d_out /* 1 double: sum over local cols */);
+int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par, const double* d_zd, int ncols, double* d_out);
 int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* d_out /* P*P + P + 1 doubles: local sums */);
 
 // cov.cu
 int gmb_cov_factor(gmb_cov* cv, const double* theta);   // builds + factorises all blocks on the device
 int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_out /* 1 double: sum_j sum_b l_b(u_j) */);
+int gmb_cov_gen_device(gmb_cov* cv, const double* theta, int chol, double* d_out, int ld);   // dense D(theta) or chol D on the device
+// cov_large.cu: in-place blocked Cholesky of a raw device matrix (see the definition)
+int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet);
 
 // model.cu
 int gmb_model_reserve_samples(gmb_model* mdl, int m);

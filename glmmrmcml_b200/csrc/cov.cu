@@ -380,6 +380,23 @@ int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_ou
     return GMB_OK;
 }
 
+// dense Q x Q D(theta) (chol = 0) or its lower Cholesky factor (chol = 1) into a device matrix with leading dimension ld
+// (zero outside the blocks).  Returns GMB_ENOTPD when a block is not positive definite.
+int gmb_cov_gen_device(gmb_cov* cv, const double* theta, int chol, double* d_out, int ld) {
+    gmb_ctx* ctx = cv->ctx;
+    if (chol) GMB_TRY(gmb_cov_factor(cv, theta));
+    else {
+        for (int r = 0; r < cv->R; r++) ctx->h_pinned[r] = theta[r];
+        GMB_CUDA(cudaMemcpyAsync(cv->d_theta, ctx->h_pinned, sizeof(double) * cv->R, cudaMemcpyHostToDevice, ctx->stream));
+        cv->factor_valid = false;
+    }
+    GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)ld * cv->Q, ctx->stream));
+    expand_blocks_kernel<<<cv->B, 256, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_Lblk, chol, d_out, ld);
+    ctx->launches++;
+    GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}
+
 extern "C" int gmb_cov_gen(gmb_cov* cv, const double* theta, int chol, double* L_out) {
     if (!cv || !theta) return gmb_set_error(GMB_EINVAL, "gmb_cov_gen: bad arguments");
     gmb_ctx* ctx = cv->ctx;

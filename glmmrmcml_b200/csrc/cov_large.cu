@@ -137,23 +137,17 @@ static int linv_buffer(gmb_cov* cv, int bi, double** out) {
     return GMB_OK;
 }
 
-int gmb_cov_factor_large(gmb_cov* cv, int bi) {
-    gmb_ctx* ctx = cv->ctx;
-    const CovBlock& b = cv->blocks[bi];
-    const int n = b.n, ld = gmb_cov_ld(n);
-    double* A = cv->d_Lblk + b.l0;
-    double* linv = nullptr;
-    GMB_TRY(linv_buffer(cv, bi, &linv));
-    dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8);
-    build_block_kernel<<<grd, blk, 0, ctx->stream>>>(b, cv->d_fns, cv->d_data, cv->d_theta, A, ld);
-    ctx->launches++;
+// in-place lower Cholesky of the n x n device matrix A (lower triangle read; the strict upper triangle of the 64 x 64 diagonal
+// blocks is zeroed, the rest of the upper triangle is left as scratch).  linv: ceil(n/64) * 64 * 64 doubles (inverted diagonal
+// blocks), status: first non-PD pivot + 1 + row_offset (0 if fine), d_logdet: sum of 2 log L_ii.
+int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet) {
     for (int K0 = 0; K0 < n; K0 += NBO) {
         const int KB = n - K0 < NBO ? n - K0 : NBO;
         const int Kend = K0 + KB;
         for (int k0 = K0; k0 < Kend; k0 += NB) {
             const int kb = Kend - k0 < NB ? Kend - k0 : NB;
             double* Li = linv + (size_t)(k0 / NB) * NB * NB;
-            potf2_kernel<<<1, NB, 0, ctx->stream>>>(A, ld, k0, kb, b.start, cv->d_status, Li);
+            potf2_kernel<<<1, NB, 0, ctx->stream>>>(A, ld, k0, kb, row_offset, d_status, Li);
             ctx->launches++;
             const int rest = n - k0 - kb;
             if (rest > 0) {
@@ -175,10 +169,25 @@ int gmb_cov_factor_large(gmb_cov* cv, int bi) {
             GMB_TRY(gmb_dgemm(ctx, 0, 1, n - J, w, KB, -1.0, PJ, ld, PJ, ld, 1.0, A + J + (size_t)J * ld, ld));
         }
     }
-    logdet_diag_kernel<<<1, 256, 0, ctx->stream>>>(A, ld, n, cv->d_logdet + bi);
-    ctx->launches++;
+    if (d_logdet) {
+        logdet_diag_kernel<<<1, 256, 0, ctx->stream>>>(A, ld, n, d_logdet);
+        ctx->launches++;
+    }
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;
+}
+
+int gmb_cov_factor_large(gmb_cov* cv, int bi) {
+    gmb_ctx* ctx = cv->ctx;
+    const CovBlock& b = cv->blocks[bi];
+    const int n = b.n, ld = gmb_cov_ld(n);
+    double* A = cv->d_Lblk + b.l0;
+    double* linv = nullptr;
+    GMB_TRY(linv_buffer(cv, bi, &linv));
+    dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8);
+    build_block_kernel<<<grd, blk, 0, ctx->stream>>>(b, cv->d_fns, cv->d_data, cv->d_theta, A, ld);
+    ctx->launches++;
+    return gmb_chol_blocked(ctx, A, ld, n, b.start, cv->d_status, linv, cv->d_logdet + bi);
 }
 
 // d_partial: 64 doubles (zeroed by the caller); receives partial sums of ||L^{-1} u_j||^2 over the columns

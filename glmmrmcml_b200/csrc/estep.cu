@@ -389,8 +389,13 @@ int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb) {
 }
 
 int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, double* d_out) {
+    return gmb_launch_loglik_cols(mdl, d_beta, var_par, mdl->dzd, mdl->niter_local, d_out);
+}
+
+// the same sum over an explicit block of columns of a zd-like matrix (ldn x ncols); the Laplace objectives use single columns
+int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par, const double* d_zd, int ncols, double* d_out) {
     gmb_ctx* ctx = mdl->ctx;
-    const int n = mdl->n, ncols = mdl->niter_local;
+    const int n = mdl->n;
     if (ncols <= 0) { GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream)); return GMB_OK; }
     int half = (n + 1) / 2;
     int TX = 32; while (TX < 256 && TX < half) TX <<= 1;
@@ -409,9 +414,9 @@ int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, doub
     unsigned int* counter = ctx->d_counter;   // zeroed at ctx creation and re-zeroed by the last CTA
     dim3 grid(RT, CC), block(TX, TY);
     switch (mdl->flink) {
-    case 1: loglik_kernel<1><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dzd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
-    case 3: loglik_kernel<3><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dzd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
-    case 7: loglik_kernel<7><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dzd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 1: loglik_kernel<1><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 3: loglik_kernel<3><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 7: loglik_kernel<7><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
     default: return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
     }
     ctx->launches++;

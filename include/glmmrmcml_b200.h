@@ -29,6 +29,7 @@ extern "C" {
 #define GMB_ENCCL     5   /* NCCL failure */
 #define GMB_ESTATE    6   /* call order (e.g. loglik before set_u) */
 #define GMB_ECOV      7   /* unsupported covariance function id */
+#define GMB_ENUMERIC  8   /* singular system in a Newton step */
 
 typedef struct gmb_ctx   gmb_ctx;     /* one per process: device, streams, scratch, optional NCCL communicator */
 typedef struct gmb_model gmb_model;   /* replaces glmmr::mcmlModel (inst/include/glmmrmcml/mcmlmodel.h:28-307) */
@@ -220,6 +221,26 @@ int gmb_mcml_full(const int32_t* cov, int cov_rows, const double* data, int n_da
                   int refresh, int maxsteps, double target_accept, int n_chains, uint64_t seed,
                   double* beta_out, double* theta_out, double* sigma_out, int* converged_out, int* iter_out,
                   double* u_out);
+
+/* mcml_la, src/mcml_la.cpp:28-155: Laplace-approximation fit (la_optim over (beta, v), la_optim_cov over theta, final joint
+ * la_optim_bcov; optional finite-difference standard errors, hess_la).  start holds (beta, theta, sigma), n_start >= P + R + 1.
+ * se_out: n_start values (zeros unless usehess), u_out: Q values (u = L v).  m = 1: not a throughput path. */
+int gmb_mcml_la(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
+                const double* Z, const double* X, const double* y, int n, int P, int Q, const char* family, const char* link,
+                const double* start, int n_start, int usehess, double tol, int verbose, int trace, int maxiter,
+                double* beta_out, double* theta_out, double* sigma_out, double* se_out, double* u_out, int* iter_out);
+/* mcml_la_nr, src/mcml_la.cpp:178-290: the same loop with the Newton-Raphson step mcnr_b (mcmloptim.h:238-293) for (beta, v). */
+int gmb_mcml_la_nr(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
+                   const double* Z, const double* X, const double* y, int n, int P, int Q, const char* family, const char* link,
+                   const double* start, int n_start, int usehess, double tol, int verbose, int trace, int maxiter,
+                   double* beta_out, double* theta_out, double* sigma_out, double* se_out, double* u_out, int* iter_out);
+/* Parity hook for the Laplace path: out3 = (LA_likelihood(beta, v), LA_likelihood_cov(theta[, sigma]), LA_likelihood_btheta(beta, theta
+ * [, sigma])) of likelihood.h:112-230 at the given state, with W formed at xb + Z v (w_use_l = 0, update_W()) or xb + Z L v
+ * (w_use_l = 1); beta_nr / v_nr / sigma_nr (may be NULL) receive the state after one mcnr_b step (mcmloptim.h:238-293). */
+int gmb_la_objectives(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
+                      const double* Z, const double* X, const double* y, int n, int P, int Q, const char* family, const char* link,
+                      const double* beta, const double* theta, int R, const double* v, double sigma, int w_use_l,
+                      double* out3, double* beta_nr, double* v_nr, double* sigma_nr);
 
 #ifdef __cplusplus
 }

@@ -144,6 +144,17 @@ def objectives(cov, data, eff, X, Z, U, y, family, link, par, fix_var_par=1.0):
     return out
 
 
+def la_objectives(cov, data, eff, X, Z, y, family, link, beta, theta, v, sigma=1.0, w_use_l=False):
+    """LA_likelihood / LA_likelihood_cov / LA_likelihood_btheta (likelihood.h:112-230) at one state + one mcnr_b step."""
+    keep, a = _cov(cov, data, eff)
+    X = _f(X); Z = _f(Z); y = _v(y); beta = _v(beta); theta = _v(theta); v = _v(v)
+    n, P = X.shape; Q = Z.shape[1]
+    out3 = np.zeros(3); bn = np.zeros(P); vn = np.zeros(Q); sn = C.c_double()
+    lib().ref_la_objectives(*a, n, P, Q, _d(X), _d(Z), _d(y), family.encode(), link.encode(), _d(beta), _d(theta), theta.size, _d(v),
+                            C.c_double(sigma), int(bool(w_use_l)), _d(out3), _d(bn), _d(vn), C.byref(sn))
+    return dict(la=out3[0], la_cov=out3[1], la_btheta=out3[2], beta_nr=bn, v_nr=vn, sigma_nr=sn.value)
+
+
 def mcmc_sample(X, Z, L, y, beta, family, link, warmup, nsamp, lam, var_par, maxsteps, target_accept, seed, chain=0):
     """mcmc_sample (src/mcml_full.cpp:314-338) driven by the shared Philox stream; returns (Q x (nsamp+1) u-samples, stats)."""
     X = _f(X); Z = _f(Z); L = _f(L); y = _v(y); beta = _v(beta)

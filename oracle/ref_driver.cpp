@@ -176,6 +176,47 @@ REF_API void ref_objectives(const int32_t* cov, int rows, const double* data, in
     out3[0] = ll(pb); out3[1] = dl(pt); out3[2] = fl(pf);
 }
 
+// Laplace path: the three functors of likelihood.h:112-230 at one state and one mcmloptim::mcnr_b step (mcmloptim.h:238-293), on a model
+// built as in src/mcml_la.cpp:42-52 with theta as the initial covariance parameters (so D_ = D(theta)) and u = v.
+// w_use_l selects update_W(0, true) (mcml_la_nr) or update_W() (mcml_la).  out3 = (LA_likelihood, LA_likelihood_cov, LA_likelihood_btheta).
+REF_API void ref_la_objectives(const int32_t* cov, int rows, const double* data, int n_data, const double* eff, int n_eff,
+                               int n, int P, int Q, const double* X, const double* Z, const double* y, const char* family, const char* link,
+                               const double* beta, const double* theta, int R, const double* v, double sigma, int w_use_l,
+                               double* out3, double* beta_nr, double* v_nr, double* sigma_nr) {
+    glmmr::DData dat(covmat(cov, rows), arrd(data, n_data), arrd(eff, n_eff));
+    const bool gaussian = std::string(family) == "gaussian";
+    Eigen::ArrayXd st(P + R + 1);
+    for (int i = 0; i < P; i++) st(i) = beta[i];
+    for (int i = 0; i < R; i++) st(P + i) = theta[i];
+    st(P + R) = sigma;
+    glmmr::MCMLDmatrix dmat(&dat, arrd(theta, R));
+    Eigen::MatrixXd Xm = mat(X, n, P), Zm = mat(Z, n, Q), u = mat(v, Q, 1);
+    Eigen::MatrixXd L = dmat.genD(0, true, false);
+    glmmr::mcmlModel model(Zm, &L, Xm, vec(y, n), &u, vec(beta, P), gaussian ? sigma : 1.0, family, link);
+    glmmr::mcmloptim<glmmr::MCMLDmatrix> mc(&dmat, &model, st, 0);
+    model.update_W(0, w_use_l != 0);
+    std::vector<double> pbv(beta, beta + P), pt(theta, theta + R), pbt(beta, beta + P);
+    pbv.insert(pbv.end(), v, v + Q);
+    pbt.insert(pbt.end(), theta, theta + R);
+    if (gaussian) { pt.push_back(sigma); pbt.push_back(sigma); }
+    glmmr::likelihood::LA_likelihood<glmmr::MCMLDmatrix> la(&model, &dmat);
+    glmmr::likelihood::LA_likelihood_cov<glmmr::MCMLDmatrix> lc(&model, &dmat);
+    glmmr::likelihood::LA_likelihood_btheta<glmmr::MCMLDmatrix> lb(&model, &dmat);
+    out3[0] = la(pbv);
+    out3[1] = lc(pt);
+    out3[2] = lb(pbt);
+    if (beta_nr && v_nr) {
+        for (int q = 0; q < Q; q++) u(q, 0) = v[q];
+        model.update_beta(vec(beta, P));
+        model.update_W(0, w_use_l != 0);
+        mc.mcnr_b();
+        Eigen::VectorXd b = mc.get_beta();
+        std::memcpy(beta_nr, b.data(), sizeof(double) * P);
+        for (int q = 0; q < Q; q++) v_nr[q] = u(q, 0);
+        if (sigma_nr) *sigma_nr = mc.get_sigma();
+    }
+}
+
 // mcmc_sample(Z, L, X, y, beta, family, link, warmup, nsamp, lambda, var_par, 0, refresh, maxsteps, target_accept)
 // — src/mcml_full.cpp:329-337 — driven by the Philox stream (seed, chain).  out is Q x (nsamp+1).
 // stats: accept_/(warmup+nsamp), e_, ebar_, steps_ of the last proposal.
