@@ -86,6 +86,8 @@ struct gmb_model {
     // samples (this rank's columns)
     double* dU = nullptr;        // ldq x m_cap
     double* dzd = nullptr;       // ldn x m_cap
+    double* dF = nullptr;        // ldn x m_cap, binomial/logit only: exp(s_i zd_ij), s_i = -1 (y_i = 1) / +1 (y_i = 0); see estep.cu
+    bool f_valid = false;
     int m_cap = 0;
     int m_local = 0, niter_local = 0, m_total = 0, niter_total = 0;
     bool zd_valid = false;
@@ -141,6 +143,7 @@ int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb);
 int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, double* d_out /* 1 double: sum over local cols */);
 int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par, const double* d_zd, int ncols, double* d_out);
 int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* d_out /* P*P + P + 1 doubles: local sums */);
+int gmb_launch_build_factor(gmb_model* mdl, int ncols);
 
 // cov.cu
 int gmb_cov_factor(gmb_cov* cv, const double* theta);   // builds + factorises all blocks on the device

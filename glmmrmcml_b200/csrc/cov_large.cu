@@ -106,8 +106,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ W
 }
 
 __global__ void copy_rows_kernel(const double* __restrict__ U, int ldu, int start, int n, int ncols, double* __restrict__ W, int ldw) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y;
+    int i = blockIdx.y * blockDim.x + threadIdx.x;      // grid.x runs over the columns (no 65535 limit)
+    int j = blockIdx.x;
     if (i < ldw && j < ncols) W[(size_t)j * ldw + i] = (i < n) ? U[(size_t)j * ldu + start + i] : 0.0;
 }
 
@@ -213,7 +213,7 @@ int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols
     int slots = 64 / nchunks; if (slots < 1) slots = 1;
     for (int c = 0; c < nchunks; c++) {
         int c0 = c * chunk, nc = ncols - c0 < chunk ? ncols - c0 : chunk;
-        copy_rows_kernel<<<dim3((ldw + 255) / 256, nc), 256, 0, ctx->stream>>>(dU + (size_t)c0 * ldu, ldu, b.start, n, nc, W, ldw);
+        copy_rows_kernel<<<dim3(nc, (ldw + 255) / 256), 256, 0, ctx->stream>>>(dU + (size_t)c0 * ldu, ldu, b.start, n, nc, W, ldw);
         ctx->launches++;
         // blocked forward substitution, two levels: 64-row diagonal solves and rank-64 updates inside an outer block of 256
         // rows, one rank-256 update of all rows below per outer block

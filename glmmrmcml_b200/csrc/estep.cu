@@ -87,6 +87,125 @@ __device__ __forceinline__ double ll_direct(const RowTerm<FL>& r, double z) {
     return r.mask != 0.0 ? -log(1.0 + exp(x)) : 0.0;
 }
 
+// deterministic grid-wide sum: per-CTA partials, the last CTA to arrive adds them in a fixed order (bitwise reproducible)
+__device__ __forceinline__ void grid_sum_finish(double acc, int TX, double* __restrict__ partials, unsigned int* __restrict__ counter,
+                                                double* __restrict__ out, double* red, bool* is_last) {
+    double v = warp_sum(acc);
+    const int t = threadIdx.y * TX + threadIdx.x;
+    const int w = t >> 5, l = t & 31;
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    const int nblocks = gridDim.x * gridDim.y;
+    if (w == 0) {
+        v = (l < 8) ? red[l] : 0.0;
+        v = warp_sum(v);
+        if (l == 0) {
+            partials[bid] = v;
+            __threadfence();
+            unsigned int done = atomicAdd(counter, 1u);
+            *is_last = (done == (unsigned)nblocks - 1);
+        }
+    }
+    __syncthreads();
+    if (*is_last) {
+        __threadfence();
+        double s = 0.0;
+        for (int k = t; k < nblocks; k += 256) s += partials[k];
+        s = warp_sum(s);
+        __syncthreads();
+        if (l == 0) red[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            s = (l < 8) ? red[l] : 0.0;
+            s = warp_sum(s);
+            if (l == 0) { out[0] = s; *counter = 0u; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2, binomial/logit on the FACTOR matrix.  The sample matrix is fixed while the M-step evaluates the objective hundreds of times
+// (l_optim, f_hess), and exp(s eta) = exp(s xb_i) exp(s zd_ij) with the sign s fixed by y_i: F_ij = exp(s_i zd_ij) is built once per
+// sample matrix (build_factor_kernel, next to zd), after which an evaluation needs one exp per ROW and per element
+//     prod *= 1 + A_i F_ij          (A_i = exp(s_i xb_i); A_i = 0 drops rows whose y is neither 0 nor 1)
+// i.e. two FP64 instructions instead of a 20-instruction exp, and one log per 8 elements: the kernel streams at the rate of the
+// Gaussian one instead of being issue bound.  A group whose product leaves the finite range is redone term by term.
+// ---------------------------------------------------------------------------------------------------
+__global__ void build_factor_kernel(int n, int ldn, int ncols, const double* __restrict__ zd, const double* __restrict__ y,
+                                    double* __restrict__ F) {
+    const int i = blockIdx.y * blockDim.x + threadIdx.x;          // grid.x (up to 2^31 - 1) runs over the columns
+    const int j = blockIdx.x;
+    if (i >= ldn || j >= ncols) return;
+    double f = 1.0;
+    if (i < n) {
+        const double yi = y[i];
+        const double z = zd[i + (size_t)j * ldn];
+        f = (yi == 1.0) ? exp(-1.0 * z) : exp(z);
+    }
+    F[i + (size_t)j * ldn] = f;
+}
+
+__global__ void __launch_bounds__(256) loglik_logit_factor_kernel(int n, int P, int ldn, int ncols, int cols_per_cta,
+                                                                  const double* __restrict__ F, const double* __restrict__ X,
+                                                                  const double* __restrict__ beta, const double* __restrict__ y,
+                                                                  double* __restrict__ partials, unsigned int* __restrict__ counter,
+                                                                  double* __restrict__ out) {
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const int TX = blockDim.x, TY = blockDim.y;
+    const int i0 = 2 * (blockIdx.x * TX + threadIdx.x);
+    const int j0 = blockIdx.y * cols_per_cta;
+    const int j1 = min(j0 + cols_per_cta, ncols);
+    double acc = 0.0;
+    if (i0 < n) {
+        const bool two = (i0 + 1 < n);
+        double xb0 = 0.0, xb1 = 0.0;
+        for (int p = 0; p < P; p++) {                                // same order as xb_kernel
+            const double b = beta[p];
+            xb0 += X[i0 + (size_t)p * ldn] * b;
+            if (two) xb1 += X[i0 + 1 + (size_t)p * ldn] * b;
+        }
+        const double y0 = y[i0], y1 = two ? y[i0 + 1] : -1.0;
+        const double A0 = (y0 == 1.0) ? exp(-1.0 * xb0) : ((y0 == 0.0) ? exp(xb0) : 0.0);
+        const double A1 = (y1 == 1.0) ? exp(-1.0 * xb1) : ((y1 == 0.0) ? exp(xb1) : 0.0);
+        const double* col = F + i0;
+        int j = j0 + threadIdx.y;
+        double2 z[4], zn[4];
+        bool have = j + 3 * TY < j1;
+        if (have) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const double2*>(col + (size_t)(j + u * TY) * ldn);
+        }
+        while (have) {
+            const int jn = j + 4 * TY;
+            const bool have_n = jn + 3 * TY < j1;
+            if (have_n) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) zn[u] = *reinterpret_cast<const double2*>(col + (size_t)(jn + u * TY) * ldn);
+            }
+            double p0 = 1.0, p1 = 1.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) { p0 *= fma(A0, z[u].x, 1.0); p1 *= fma(A1, z[u].y, 1.0); }
+            const double prod = p0 * p1;
+            if (prod <= 1e300) {
+                acc -= log(prod);
+            } else {                                                  // overflow (or NaN): term by term
+#pragma unroll
+                for (int u = 0; u < 4; u++) acc -= log(fma(A0, z[u].x, 1.0)) + log(fma(A1, z[u].y, 1.0));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) z[u] = zn[u];
+            j = jn; have = have_n;
+        }
+        for (; j < j1; j += TY) {
+            const double2 zz = *reinterpret_cast<const double2*>(col + (size_t)j * ldn);
+            acc -= log(fma(A0, zz.x, 1.0)) + log(fma(A1, zz.y, 1.0));
+        }
+    }
+    grid_sum_finish(acc, TX, partials, counter, out, red, &is_last);
+}
+
 template <int FL>
 __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int ncols, int cols_per_cta,
                                                      const double* __restrict__ zd, const double* __restrict__ X,
@@ -172,40 +291,7 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
             } else if (two) acc += a1;
         }
     }
-    // flatten thread index for the block reduction
-    double v = warp_sum(acc);
-    const int t = threadIdx.y * TX + threadIdx.x;
-    const int w = t >> 5, l = t & 31;
-    if (l == 0) red[w] = v;
-    __syncthreads();
-    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-    const int nblocks = gridDim.x * gridDim.y;
-    if (w == 0) {
-        v = (l < 8) ? red[l] : 0.0;
-        v = warp_sum(v);
-        if (l == 0) {
-            partials[bid] = v;
-            __threadfence();
-            unsigned int done = atomicAdd(counter, 1u);
-            is_last = (done == (unsigned)nblocks - 1);
-        }
-    }
-    __syncthreads();
-    if (is_last) {
-        // the last CTA sums the per-CTA partials in a fixed order -> bitwise reproducible result
-        __threadfence();
-        double s = 0.0;
-        for (int k = t; k < nblocks; k += 256) s += partials[k];
-        s = warp_sum(s);
-        __syncthreads();
-        if (l == 0) red[w] = s;
-        __syncthreads();
-        if (w == 0) {
-            s = (l < 8) ? red[l] : 0.0;
-            s = warp_sum(s);
-            if (l == 0) { out[0] = s; *counter = 0u; }
-        }
-    }
+    grid_sum_finish(acc, TX, partials, counter, out, red, &is_last);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -413,12 +499,31 @@ int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par,
     double* partials = ctx->d_scratch;
     unsigned int* counter = ctx->d_counter;   // zeroed at ctx creation and re-zeroed by the last CTA
     dim3 grid(RT, CC), block(TX, TY);
+    if (mdl->flink == 3 && mdl->f_valid && d_zd >= mdl->dzd && d_zd < mdl->dzd + (size_t)mdl->ldn * mdl->m_cap) {
+        const double* d_f = mdl->dF + (d_zd - mdl->dzd);              // the same block of columns of the factor matrix
+        loglik_logit_factor_kernel<<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_f, mdl->dX, d_beta, mdl->dy,
+                                                                   partials, counter, d_out);
+        ctx->launches++;
+        GMB_CUDA(cudaGetLastError());
+        return GMB_OK;
+    }
     switch (mdl->flink) {
     case 1: loglik_kernel<1><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
     case 3: loglik_kernel<3><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
     case 7: loglik_kernel<7><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
     default: return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
     }
+    ctx->launches++;
+    GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}
+
+// F = exp(s zd) for the first ncols columns (binomial/logit models; called by gmb_model_build_zd)
+int gmb_launch_build_factor(gmb_model* mdl, int ncols) {
+    gmb_ctx* ctx = mdl->ctx;
+    if (ncols <= 0) return GMB_OK;
+    dim3 grid(ncols, (mdl->ldn + 255) / 256);
+    build_factor_kernel<<<grid, 256, 0, ctx->stream>>>(mdl->n, mdl->ldn, ncols, mdl->dzd, mdl->dy, mdl->dF);
     ctx->launches++;
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;

@@ -69,6 +69,7 @@ struct LaFit {
         ctx = c; D = d; M = m; n = m->n; P = m->P; Q = m->Q; ldn = m->ldn; ldq = m->ldq; hX = X; hy = y;
         int B;
         GMB_TRY(gmb_cov_dims(d, &B, &Q, &R));
+        if (Q > 65535) return gmb_set_error(GMB_EINVAL, "Laplace path: Q = %d exceeds 65535", Q);
         gaussian = std::string(family ? family : "") == "gaussian";
         if (n_start < P + R) return gmb_set_error(GMB_EINVAL, "start has %d values, needs P + R = %d", n_start, P + R);
         beta.assign(start, start + P);

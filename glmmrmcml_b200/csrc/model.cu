@@ -90,7 +90,7 @@ extern "C" void gmb_model_destroy(gmb_model* mdl) {
     cudaSetDevice(mdl->ctx->device);
     cudaStreamSynchronize(mdl->ctx->stream);
     gmb_dfree(mdl->ctx, mdl->dX); gmb_dfree(mdl->ctx, mdl->dZ); gmb_dfree(mdl->ctx, mdl->dy); gmb_dfree(mdl->ctx, mdl->drowc); gmb_dfree(mdl->ctx, mdl->dxb); gmb_dfree(mdl->ctx, mdl->dbeta);
-    gmb_dfree(mdl->ctx, mdl->dU); gmb_dfree(mdl->ctx, mdl->dzd); gmb_dfree(mdl->ctx, mdl->dZL); gmb_dfree(mdl->ctx, mdl->dL);
+    gmb_dfree(mdl->ctx, mdl->dU); gmb_dfree(mdl->ctx, mdl->dzd); gmb_dfree(mdl->ctx, mdl->dF); gmb_dfree(mdl->ctx, mdl->dZL); gmb_dfree(mdl->ctx, mdl->dL);
     gmb_dfree(mdl->ctx, mdl->dV); gmb_dfree(mdl->ctx, mdl->hmc_work);
     delete mdl;
 }
@@ -104,10 +104,13 @@ int gmb_model_reserve_samples(gmb_model* mdl, int m) {
     GMB_CUDA(cudaStreamSynchronize(ctx->stream));
     if (mdl->dU) { gmb_dfree(ctx, mdl->dU); mdl->dU = nullptr; }
     if (mdl->dzd) { gmb_dfree(ctx, mdl->dzd); mdl->dzd = nullptr; }
+    if (mdl->dF) { gmb_dfree(ctx, mdl->dF); mdl->dF = nullptr; }
+    mdl->f_valid = false;
     mdl->m_cap = 0;
     size_t cap = (size_t)m;
     GMB_CUDA(gmb_dmalloc(ctx, &mdl->dU, sizeof(double) * mdl->ldq * cap));
     GMB_CUDA(gmb_dmalloc(ctx, &mdl->dzd, sizeof(double) * mdl->ldn * cap));
+    if (mdl->flink == 3) GMB_CUDA(gmb_dmalloc(ctx, &mdl->dF, sizeof(double) * mdl->ldn * cap));
     // padding rows must hold finite values: the streaming kernels load them (and mask the result)
     GMB_CUDA(cudaMemsetAsync(mdl->dU, 0, sizeof(double) * mdl->ldq * cap, ctx->stream));
     GMB_CUDA(cudaMemsetAsync(mdl->dzd, 0, sizeof(double) * mdl->ldn * cap, ctx->stream));
@@ -119,6 +122,11 @@ int gmb_model_reserve_samples(gmb_model* mdl, int m) {
 int gmb_model_build_zd(gmb_model* mdl) {
     if (mdl->m_local > 0)
         GMB_TRY(gmb_dgemm(mdl->ctx, 0, 0, mdl->n, mdl->m_local, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dU, mdl->ldq, 0.0, mdl->dzd, mdl->ldn));
+    mdl->f_valid = false;
+    if (mdl->flink == 3 && mdl->dF && mdl->m_local > 0) {        // factor matrix of the binomial/logit E-step (estep.cu)
+        GMB_TRY(gmb_launch_build_factor(mdl, mdl->m_local));
+        mdl->f_valid = true;
+    }
     mdl->zd_valid = true;
     return GMB_OK;
 }
