@@ -314,7 +314,9 @@ __device__ __forceinline__ void mcnr_terms(double y, double eta, double inv_phi,
     }
 }
 
-template <int FL>
+// FACTOR (binomial/logit only): zd points to the factor matrix F = exp(s zd) (see loglik_logit_factor_kernel) and the row constant
+// is A_i = exp(s_i xb_i): 1/(1 + A F) is 1 - p or p, so the element costs a Newton reciprocal instead of an exp and a division.
+template <int FL, bool FACTOR>
 __global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int ncols, int cols_per_cta,
                                                          const double* __restrict__ zd, const double* __restrict__ xb,
                                                          const double* __restrict__ y, double inv_phi,
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int nco
             ok[2 * k + v] = i < n;
             xbr[2 * k + v] = ok[2 * k + v] ? xb[i] : 0.0;
             yr[2 * k + v] = ok[2 * k + v] ? y[i] : 0.0;
+            if (FACTOR) xbr[2 * k + v] = (yr[2 * k + v] == 1.0) ? exp(-1.0 * xbr[2 * k + v]) : exp(xbr[2 * k + v]);   // A_i
             wacc[2 * k + v] = 0.0; sacc[2 * k + v] = 0.0;
         }
     // the next column's loads are issued before the current column's arithmetic (register double buffer)
@@ -365,7 +368,13 @@ __global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int nco
                 int e = 2 * k + v;
                 if (ok[e]) {
                     double w, wu, r;
-                    mcnr_terms<FL>(yr[e], xbr[e] + (v ? z[k].y : z[k].x), inv_phi, stab, w, wu, r);
+                    if (FACTOR) {
+                        const double rc = dev_rcp_fast(fma(xbr[e], (v ? z[k].y : z[k].x), 1.0));   // 1/(1 + A F): p (y = 1) or 1 - p
+                        const double p = (yr[e] == 1.0) ? rc : 1.0 - rc;
+                        r = yr[e] - p; w = fma(-rc, rc, rc); wu = r;                                // p (1 - p) = rc - rc^2
+                    } else {
+                        mcnr_terms<FL>(yr[e], xbr[e] + (v ? z[k].y : z[k].x), inv_phi, stab, w, wu, r);
+                    }
                     wacc[e] += w; sacc[e] += wu; sr += r; sr2 += r * r;
                 }
             }
@@ -552,9 +561,12 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
     dim3 grid(RT, CC);
     size_t smem = 8 * 2 * 256 * sizeof(double);
     switch (mdl->flink) {
-    case 1: mcnr_pass1_kernel<1><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
-    case 3: mcnr_pass1_kernel<3><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
-    case 7: mcnr_pass1_kernel<7><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
+    case 1: mcnr_pass1_kernel<1, false><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
+    case 3:
+        if (mdl->f_valid) mcnr_pass1_kernel<3, true><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dF, d_xb, mdl->dy, inv_phi, rowpart, colpart);
+        else mcnr_pass1_kernel<3, false><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart);
+        break;
+    case 7: mcnr_pass1_kernel<7, false><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
     default: return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
     }
     mcnr_rows_kernel<<<(n + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(n, ldn, CC, rowpart, wsum, ssum);
