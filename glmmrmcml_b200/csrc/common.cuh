@@ -88,6 +88,8 @@ struct gmb_model {
     double* dzd = nullptr;       // ldn x m_cap
     double* dF = nullptr;        // ldn x m_cap, binomial/logit only: exp(s_i zd_ij), s_i = -1 (y_i = 1) / +1 (y_i = 0); see estep.cu
     bool f_valid = false;
+    double* dstat = nullptr;     // 2 x ldn row statistics of zd for the poisson / gaussian E-step (estep.cu: ensure_rowstats)
+    bool stat_valid = false; int stat_cols = 0;
     int m_cap = 0;
     int m_local = 0, niter_local = 0, m_total = 0, niter_total = 0;
     bool zd_valid = false;
@@ -144,6 +146,7 @@ int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, doub
 int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par, const double* d_zd, int ncols, double* d_out);
 int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* d_out /* P*P + P + 1 doubles: local sums */);
 int gmb_launch_build_factor(gmb_model* mdl, int ncols);
+int gmb_estep_rowstats_enabled();
 
 // cov.cu
 int gmb_cov_factor(gmb_cov* cv, const double* theta);   // builds + factorises all blocks on the device

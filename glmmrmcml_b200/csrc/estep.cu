@@ -295,6 +295,69 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K2 for poisson/log and gaussian/identity through ROW STATISTICS of the sample matrix.  With zd fixed,
+//   poisson : sum_j [y eta_ij - exp(eta_ij) - lf(y)] = y (m xb_i + T_i) - exp(xb_i) S_i - m lf(y_i),   S_i = sum_j exp(zd_ij), T_i = sum_j zd_ij
+//   gaussian: sum_j [c0 - (y - eta_ij)^2 / (2 s^2)]  = m c0 - [m d_i^2 - 2 d_i T_i + T2_i] / (2 s^2),  d_i = y_i - xb_i,    T2_i = sum_j zd_ij^2
+// so one evaluation costs O(n) once (S, T) or (T, T2) are known; they are built by ONE stream over zd per sample matrix (rowstat_kernel,
+// cached per (sample matrix, niter)) instead of one stream per evaluation.  Same sums as mcmlmodel.h:295-300, different order.
+// ---------------------------------------------------------------------------------------------------
+template <int FL>
+__global__ void __launch_bounds__(256) rowstat_kernel(int n, int ldn, int ncols, int cols_per_cta, const double* __restrict__ zd,
+                                                      double* __restrict__ rowpart /* [gridDim.y][2][ldn] */) {
+    extern __shared__ double sm[];           // [TY][2][2 TX]
+    const int TX = blockDim.x, TY = blockDim.y;
+    const int i0 = 2 * (blockIdx.x * TX + threadIdx.x);
+    const int j0 = blockIdx.y * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;       // (S or T2, T) of rows i0, i0 + 1
+    if (i0 < ldn) {
+        const double* col = zd + i0;
+        for (int j = j0 + threadIdx.y; j < j1; j += TY) {
+            const double2 z = *reinterpret_cast<const double2*>(col + (size_t)j * ldn);
+            if (FL == 1) { a0 += exp(z.x); a1 += exp(z.y); }
+            else { a0 = fma(z.x, z.x, a0); a1 = fma(z.y, z.y, a1); }
+            b0 += z.x; b1 += z.y;
+        }
+    }
+    double* s = sm + (size_t)threadIdx.y * 4 * TX;
+    s[2 * threadIdx.x] = a0; s[2 * threadIdx.x + 1] = a1;
+    s[2 * TX + 2 * threadIdx.x] = b0; s[2 * TX + 2 * threadIdx.x + 1] = b1;
+    __syncthreads();
+    if (threadIdx.y == 0 && i0 < ldn) {
+        for (int k = 1; k < TY; k++) {
+            const double* sk = sm + (size_t)k * 4 * TX;
+            a0 += sk[2 * threadIdx.x]; a1 += sk[2 * threadIdx.x + 1]; b0 += sk[2 * TX + 2 * threadIdx.x]; b1 += sk[2 * TX + 2 * threadIdx.x + 1];
+        }
+        double* ra = rowpart + ((size_t)blockIdx.y * 2 + 0) * ldn, * rb = rowpart + ((size_t)blockIdx.y * 2 + 1) * ldn;
+        ra[i0] = a0; rb[i0] = b0;
+        if (i0 + 1 < ldn) { ra[i0 + 1] = a1; rb[i0 + 1] = b1; }
+    }
+}
+
+template <int FL>
+__global__ void __launch_bounds__(256) loglik_rowstat_kernel(int n, int P, int ldn, double ncols, const double* __restrict__ statA,
+                                                             const double* __restrict__ statT, const double* __restrict__ X,
+                                                             const double* __restrict__ beta, const double* __restrict__ y,
+                                                             const double* __restrict__ rowc, double sigma, double* __restrict__ partials,
+                                                             unsigned int* __restrict__ counter, double* __restrict__ out) {
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0.0;
+    if (i < n) {
+        double xb = 0.0;
+        for (int p = 0; p < P; p++) xb += X[i + (size_t)p * ldn] * beta[p];
+        if (FL == 1) {
+            acc = y[i] * (ncols * xb + statT[i]) - exp(xb) * statA[i] - ncols * rowc[i];
+        } else {
+            const double c0 = -1.0 * log(sigma) - 0.5 * log(2 * GMB_PI_FAMILY);
+            const double d = y[i] - xb;
+            acc = ncols * c0 - 0.5 * (ncols * d * d - 2.0 * d * statT[i] + statA[i]) / (sigma * sigma);
+        }
+    }
+    grid_sum_finish(acc, blockDim.x, partials, counter, out, red, &is_last);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K3 pass 1.  CTA = 8 warps, row tile of 256 rows (lane owns rows 64k + 2 lane + {0,1}, k = 0..3), warp w walks
 // columns j0 + w, j0 + w + 8, ...  Per element: IRLS weight w_ij, score term wu_ij, residual r_ij.
 // Emits per-(column-chunk) row partial sums and per-(row-tile) column sums of r and r^2.
@@ -475,6 +538,11 @@ __global__ void __launch_bounds__(256) mcnr_assemble_kernel(int n, int P, int ld
 
 }  // namespace
 
+// 1 = poisson/gaussian evaluations go through the row statistics (default); 0 = always stream zd (roofline probes, parity tests of the stream)
+static int g_rowstats = 1;
+int gmb_estep_rowstats_enabled() { return g_rowstats; }
+extern "C" int gmb_estep_set_rowstats(int on) { g_rowstats = on ? 1 : 0; return GMB_OK; }
+
 int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb) {
     gmb_ctx* ctx = mdl->ctx;
     xb_kernel<<<(mdl->n + 255) / 256, 256, 0, ctx->stream>>>(mdl->n, mdl->P, mdl->ldn, mdl->dX, d_beta, d_xb);
@@ -483,7 +551,51 @@ int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb) {
     return GMB_OK;
 }
 
+// row statistics of the model's zd over its first niter_local columns (poisson: S, T; gaussian: T2, T), cached
+static int ensure_rowstats(gmb_model* mdl) {
+    gmb_ctx* ctx = mdl->ctx;
+    const int n = mdl->n, ldn = mdl->ldn, ncols = mdl->niter_local;
+    if (mdl->stat_valid && mdl->stat_cols == ncols) return GMB_OK;
+    if (!mdl->dstat) GMB_CUDA(gmb_dmalloc(ctx, &mdl->dstat, sizeof(double) * 2 * ldn));
+    const int half = (ldn + 1) / 2;
+    int TX = 32; while (TX < 128 && TX < half) TX <<= 1;
+    const int TY = 256 / TX;
+    const int RT = (half + TX - 1) / TX;
+    int CC = (ctx->sms * 4 + RT - 1) / RT;
+    const int max_cc = (ncols + 4 * TY - 1) / (4 * TY);
+    if (CC > max_cc) CC = max_cc;
+    if (CC < 1) CC = 1;
+    int cols_per_cta = (ncols + CC - 1) / CC;
+    CC = (ncols + cols_per_cta - 1) / cols_per_cta;
+    GMB_TRY(gmb_ctx_scratch(ctx, (size_t)CC * 2 * ldn));
+    double* rowpart = ctx->d_scratch;
+    dim3 grid(RT, CC), block(TX, TY);
+    const size_t smem = sizeof(double) * 4 * TX * TY;
+    if (mdl->flink == 1) rowstat_kernel<1><<<grid, block, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, rowpart);
+    else rowstat_kernel<7><<<grid, block, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, rowpart);
+    mcnr_rows_kernel<<<(n + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(n, ldn, CC, rowpart, mdl->dstat, mdl->dstat + ldn);
+    ctx->launches += 2;
+    GMB_CUDA(cudaGetLastError());
+    mdl->stat_valid = true; mdl->stat_cols = ncols;
+    return GMB_OK;
+}
+
 int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, double* d_out) {
+    gmb_ctx* ctx = mdl->ctx;
+    if ((mdl->flink == 1 || mdl->flink == 7) && mdl->niter_local > 0 && gmb_estep_rowstats_enabled()) {
+        GMB_TRY(ensure_rowstats(mdl));
+        const int n = mdl->n, nb = (n + 255) / 256;
+        GMB_TRY(gmb_ctx_scratch(ctx, (size_t)nb));
+        if (mdl->flink == 1)
+            loglik_rowstat_kernel<1><<<nb, 256, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, (double)mdl->niter_local, mdl->dstat, mdl->dstat + mdl->ldn, mdl->dX,
+                                                                  d_beta, mdl->dy, mdl->drowc, var_par, ctx->d_scratch, ctx->d_counter, d_out);
+        else
+            loglik_rowstat_kernel<7><<<nb, 256, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, (double)mdl->niter_local, mdl->dstat, mdl->dstat + mdl->ldn, mdl->dX,
+                                                                  d_beta, mdl->dy, mdl->drowc, var_par, ctx->d_scratch, ctx->d_counter, d_out);
+        ctx->launches++;
+        GMB_CUDA(cudaGetLastError());
+        return GMB_OK;
+    }
     return gmb_launch_loglik_cols(mdl, d_beta, var_par, mdl->dzd, mdl->niter_local, d_out);
 }
 

@@ -90,6 +90,7 @@ extern "C" void gmb_model_destroy(gmb_model* mdl) {
     cudaSetDevice(mdl->ctx->device);
     cudaStreamSynchronize(mdl->ctx->stream);
     gmb_dfree(mdl->ctx, mdl->dX); gmb_dfree(mdl->ctx, mdl->dZ); gmb_dfree(mdl->ctx, mdl->dy); gmb_dfree(mdl->ctx, mdl->drowc); gmb_dfree(mdl->ctx, mdl->dxb); gmb_dfree(mdl->ctx, mdl->dbeta);
+    gmb_dfree(mdl->ctx, mdl->dstat);
     gmb_dfree(mdl->ctx, mdl->dU); gmb_dfree(mdl->ctx, mdl->dzd); gmb_dfree(mdl->ctx, mdl->dF); gmb_dfree(mdl->ctx, mdl->dZL); gmb_dfree(mdl->ctx, mdl->dL);
     gmb_dfree(mdl->ctx, mdl->dV); gmb_dfree(mdl->ctx, mdl->hmc_work);
     delete mdl;
@@ -123,6 +124,7 @@ int gmb_model_build_zd(gmb_model* mdl) {
     if (mdl->m_local > 0)
         GMB_TRY(gmb_dgemm(mdl->ctx, 0, 0, mdl->n, mdl->m_local, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dU, mdl->ldq, 0.0, mdl->dzd, mdl->ldn));
     mdl->f_valid = false;
+    mdl->stat_valid = false;
     if (mdl->flink == 3 && mdl->dF && mdl->m_local > 0) {        // factor matrix of the binomial/logit E-step (estep.cu)
         GMB_TRY(gmb_launch_build_factor(mdl, mdl->m_local));
         mdl->f_valid = true;

@@ -146,6 +146,10 @@ int gmb_hmc_set_variant(int variant);
  * distributed shared memory.  All settings follow the same chain arithmetic and random streams. */
 int gmb_hmc_set_cluster_size(int cs);
 
+/* E-step evaluation strategy for poisson/log and gaussian/identity: 1 (default) = O(n) evaluations from row statistics of zd built once per
+ * sample matrix; 0 = stream zd on every evaluation (used by the roofline probes and the parity tests of the streaming kernel). */
+int gmb_estep_set_rowstats(int on);
+
 /* mcmlModel::log_prob / log_grad (mcmlmodel.h:138-153, 156-279, usezl = true) for C whitened states V (Q x C):
  * lp[C], grad (Q x C).  Either output may be NULL.  Used by the parity tests and by mcml_la. */
 int gmb_model_logprob_grad(gmb_model* mdl, const double* L, const double* beta, double var_par,

@@ -102,3 +102,26 @@ def test_errors(gctx):
         mdl.log_likelihood(cfg["beta"])          # no samples yet
     assert e.value.code == 6
     mdl.close()
+
+
+def test_rowstat_evaluation_equals_the_stream(gctx, oracle):
+    """poisson / gaussian: the O(n) evaluation from row statistics of zd (default) and the streaming kernel give the same value to
+    rounding, for several beta / sigma on the same sample matrix and with the niter quirk (fewer columns used than stored)."""
+    import glmmrmcml_b200 as g
+    for cfg, fam, link in ((synth.config4(ncl=40, nt=10, k=2, m=700), "poisson", "log"), (synth.config3(nloc=150, m=500), "gaussian", "identity")):
+        mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], fam, link)
+        fl = oracle.flink(fam, link)
+        rng = np.random.default_rng(1)
+        for niter in (None, cfg["U"].shape[1] - 7):
+            mdl.set_u(cfg["U"], niter_total=niter)
+            for k in range(3):
+                beta = cfg["beta"] + 0.05 * rng.standard_normal(cfg["P"]); sg = 0.7 + 0.2 * k
+                try:
+                    g.estep_set_rowstats(False); a = mdl.log_likelihood(beta, sg)
+                finally:
+                    g.estep_set_rowstats(True)
+                b = mdl.log_likelihood(beta, sg)
+                want = oracle.loglik_faithful(cfg["X"], cfg["Z"], cfg["U"], cfg["y"], beta, sg, fl, niter=niter)
+                assert abs(a - want) <= 1e-10 * abs(want)
+                assert abs(b - want) <= 1e-10 * abs(want), (a, b, want)
+        mdl.close()
