@@ -33,8 +33,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 M_PER_GPU = 10_000
-N_CHAINS = 250            # per GPU; 40 columns each (39 post-warm-up draws + the state after warm-up): 32 groups of 8 chains, each
-                          # on a cluster of 4 SMs = 128 CTAs, one wave (the sampler picks the cluster size per run)
+N_CHAINS = 1000           # per GPU; 10 columns each (9 post-warm-up draws + the state after warm-up): 125 groups of 8 chains, one CTA
+                          # each (the sampler aggregates the 500 observations into their 50 distinct rows of [X | Z] and picks the
+                          # cluster size per run: aggregate.cu, hmc_fused.cu)
 HMC = dict(warmup=500, lam=5.0, max_steps=100, target_accept=0.95, adapt=100)
 N_D_EVALS = 64            # mvn_ll evaluations of one d_optim (BOBYQA over 2 parameters takes 40-80)
 N_HESS = 256              # 4 k^2, k = P + R = 8
@@ -460,6 +461,7 @@ def main():
                     "leapfrog_per_s": sum_over_ranks(st["leapfrog_total"] / (hmc_ms * 1e-3))}
     hmc_flops = st["leapfrog_total"] * 4.0 * cfg["n"] * Q                     # 4 n Q per leapfrog step per chain
     hmc_tflops = hmc_flops / (hmc_ms * 1e-3) / 1e12
+    hmc_exec_tflops = st["leapfrog_total"] * 4.0 * st["rows_used"] * Q / (hmc_ms * 1e-3) / 1e12   # on the rows the kernel ran on
     mdl.use_device_u()
     # E-step evaluations/s on the step's own zd (40 MB, L2-resident between evaluations) and cold (L2 flushed before each)
     ctx.timer_start(); mdl.log_likelihood_batch(Bst, np.ones(N_HESS)); t_b = ctx.timer_stop()
@@ -502,9 +504,9 @@ def main():
                           "bytes_per_launch": bytes_ll, "traffic": LOGLIK_DRAM_BYTES_PER_LAUNCH, "ms": t_big, "zd_bytes": 8.0 * cfg["n"] * mbig, "peak_source": peak_src,
                           "mcnr": {"achieved": bytes_nr / (t_nr * 1e-3) / 1e9, "frac": bytes_nr / (t_nr * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": t_nr}}
         mdl2.close()
-        # the sampler kernel with every SM busy on 8 tiles per warp (1184 chains = 148 groups, one CTA each): what the kernel
-        # reaches when the job offers enough chains; the timed step above runs 250 chains on clusters of 4 SMs, which is faster
-        # for m = 10^4 (the warm-up bounds the chain length) but spends a larger share of each leapfrog step in the exchange
+        # the sampler kernel as a dense tensor kernel: row aggregation off, every SM busy on 8 tiles per warp (1184 chains = 148 groups,
+        # one CTA each) — what the DMMA path reaches on a model without repeated rows
+        g.hmc_set_row_aggregation(False)
         mdl3 = g.Model(ctx1, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
         for rep in range(2):
             r3 = mdl3.hmc_sample(L, beta, 1.0, warmup=100, nsamp_per_chain=4, lam=HMC["lam"], max_steps=HMC["max_steps"],
@@ -513,8 +515,10 @@ def main():
         s3 = r3["stats"]
         sat_tflops = s3["leapfrog_total"] * 4.0 * cfg["n"] * Q / (s3["kernel_ms"] * 1e-3) / 1e12
         roofline_sat = {"chains": 1184, "ms": s3["kernel_ms"], "achieved": sat_tflops, "frac": sat_tflops / FP64_DMMA_PEAK_TFLOPS,
-                        "note": "same kernel, 1184 chains (148 CTAs x 8 chains, no cluster split), 104 proposals: kernel capability, not the timed step"}
+                        "note": "same kernel without row aggregation, 1184 chains (148 CTAs x 8 chains, no cluster split), 104 proposals: the dense "
+                                "DMMA path on all 500 rows, not the timed step"}
         mdl3.close()
+        g.hmc_set_row_aggregation(True)
 
     if rank != 0:
         return
@@ -534,7 +538,12 @@ def main():
             "roofline": {"kernel": "hmc_fused_kernel<binomial-logit, KS=13> (on-chip sampler: eta = ZL v and grad = ZL^T r(eta) as FP64 DMMA)",
                          "bound": "tensor",
                          "achieved": hmc_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": hmc_tflops / FP64_DMMA_PEAK_TFLOPS,
-                         "traffic": SAMPLER_DRAM_BYTES_PER_LAUNCH, "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q, "saturated": roofline_sat,
+                         "traffic": SAMPLER_DRAM_BYTES_PER_LAUNCH, "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q,
+                         "rows_used": st["rows_used"], "executed_tflops": hmc_exec_tflops,
+                         "note": "achieved = ALGORITHMIC flops (4 n Q per leapfrog step and chain, n = 500 observations, SURVEY 8d) / kernel time; the kernel "
+                                 "aggregates observations that share their row of [X | Z] (500 -> rows_used distinct rows) and executes executed_tflops of "
+                                 "tensor work; at that size a step is bound by its reduction/update latency, not by the DMMA pipe",
+                         "saturated": roofline_sat,
                          "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_microbench_fp64.txt); "
                                         "MEASURED_PEAKS.json has no fp64 entry (bf16 tensor peak does not apply to an fp64 kernel)"},
             "roofline_estep": roofline_estep, "cpu_baseline": cpu}

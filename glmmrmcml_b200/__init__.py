@@ -49,6 +49,11 @@ def hmc_set_cluster_size(cs: int):
     check(lib().gmb_hmc_set_cluster_size(int(cs)))
 
 
+def hmc_set_row_aggregation(on: bool):
+    """On-chip sampler: True (default) = aggregate observations that share their row of [X | Z]; False = one row per observation."""
+    check(lib().gmb_hmc_set_row_aggregation(int(bool(on))))
+
+
 def estep_set_rowstats(on: bool):
     """poisson / gaussian E-step: True (default) = O(n) evaluations from row statistics, False = stream zd every time."""
     check(lib().gmb_estep_set_rowstats(int(bool(on))))

@@ -26,7 +26,7 @@ class GmbError(RuntimeError):
 class HmcStats(C.Structure):
     _fields_ = [("accept_rate", C.c_double), ("step_size_mean", C.c_double), ("steps_mean", C.c_double),
                 ("leapfrog_total", C.c_double), ("kernel_ms", C.c_double), ("n_chains", C.c_int),
-                ("nsamp_per_chain", C.c_int)]
+                ("nsamp_per_chain", C.c_int), ("rows_used", C.c_int), ("kernel_variant", C.c_int)]
 
 
 GMB_OK, GMB_EINVAL, GMB_EFAMILY, GMB_ECUDA, GMB_ENOTPD, GMB_ENCCL, GMB_ESTATE, GMB_ECOV = range(8)
@@ -70,6 +70,7 @@ PROTOTYPES = {
     "gmb_hmc_set_variant": (C.c_int, [C.c_int]),
     "gmb_hmc_set_cluster_size": (C.c_int, [C.c_int]),
     "gmb_estep_set_rowstats": (C.c_int, [C.c_int]),
+    "gmb_hmc_set_row_aggregation": (C.c_int, [C.c_int]),
     "gmb_model_logprob_grad": (C.c_int, [vp, dp, dp, C.c_double, dp, C.c_int, dp, dp]),
     "gmb_set_default_ctx": (C.c_int, [vp]),
     "gmb_cov_shape": (C.c_int, [ip, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

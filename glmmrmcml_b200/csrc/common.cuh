@@ -71,6 +71,17 @@ void gmb_dfree(gmb_ctx* ctx, void* p);                // no-op for NULL
 template <class T> static inline cudaError_t gmb_dmalloc(gmb_ctx* ctx, T** p, size_t bytes) { return gmb_dmalloc_raw(ctx, reinterpret_cast<void**>(p), bytes); }
 int gmb_comm_allreduce_dev(gmb_ctx* ctx, double* dbuf, int count);   // in place on ctx->stream; no-op if world==1
 
+// the on-chip sampler's view of a model: distinct rows of [X | Z] with weights (aggregate.cu); identity view when rows are distinct
+struct gmb_agg {
+    bool built = false, active = false, zl_valid = false;
+    int flag = -1;               // gmb_agg_enabled() at build time
+    int ng = 0, ldn = 0;         // rows of the view and their padded leading dimension
+    double *dX = nullptr, *dZ = nullptr, *dZL = nullptr, *dxb = nullptr;   // aggregated copies (active only)
+    double* dvec = nullptr;      // 6 x ldn: the arrays below
+    double *dcnt = nullptr, *dys = nullptr;                               // residual: observations per row, response term
+    double *dlcnt = nullptr, *dlys = nullptr, *dlsq = nullptr, *dlrc = nullptr;   // log-likelihood: count, response sum / mean, within-row SS, sum of lf(y)
+};
+
 struct gmb_model {
     gmb_ctx* ctx = nullptr;
     int n = 0, P = 0, Q = 0, flink = 0;
@@ -99,6 +110,7 @@ struct gmb_model {
     bool zl_valid = false;
     double* dV = nullptr;        // whitened samples of the last gmb_hmc_sample, ldq x v_cap
     size_t v_cap = 0;
+    gmb_agg agg;                 // row aggregation for the on-chip sampler
     double* hmc_work = nullptr;  // chain state + work buffers of the sampler
     size_t hmc_work_doubles = 0;
 };
@@ -162,6 +174,10 @@ int gmb_solve_small(int P, const double* A, const double* b, double* x);
 
 // hmc.cu
 int gmb_hmc_prepare(gmb_model* mdl, const double* L_host);   // uploads L and forms ZL = Z L
+// aggregate.cu
+int gmb_agg_ensure(gmb_model* mdl);
+void gmb_agg_free(gmb_model* mdl);
+int gmb_agg_enabled();
 
 // optim.cpp: gmb_minimize_bounded / gmb_fd_gradient / gmb_fd_hessian are declared in the public header
 
@@ -358,6 +374,32 @@ __device__ __forceinline__ double dev_family_resid(double y, double eta) {
         if (FL == 3) return 1.0 / (exp(eta) + 1.0) + y - 1.0;
     }
     return y - eta;
+}
+
+// Row-aggregated forms (aggregate.cu): a row stands for c observations that share eta; ys is the response term of the residual
+// (binomial: sum y - c, others: sum y).  With c = 1 these are the per-observation formulas of mcmlmodel.h:170-175, :184-193, :233-238.
+template <int FL>
+__device__ __forceinline__ double dev_family_resid_w(double c, double ys, double eta, const double* __restrict__ tab) {
+    if (FL == 1) return fma(-c, dev_exp_tab(eta, tab), ys);
+    if (FL == 3) return fma(c, dev_rcp_fast(dev_exp_tab(eta, tab) + 1.0), ys);
+    return fma(-c, eta, ys);
+}
+// log-density of a row: lc observations counted, lys = sum of y (poisson, binomial) or their mean (gaussian), lsq = within-row sum of
+// squares (gaussian), lrc = sum of lf(y) (poisson).  With lc = 1: dev_family_ll.
+template <int FL>
+__device__ __forceinline__ double dev_family_ll_w(double lc, double lys, double lsq, double lrc, double eta, double c0, double sigma) {
+    if (FL == 1) {
+        return lys * eta - lc * exp(eta) - lrc;
+    } else if (FL == 3) {
+        const double p = 1.0 / (1.0 + exp(-1.0 * eta));
+        double r = 0.0;
+        if (lys != 0.0) r += lys * log(p);
+        if (lc - lys != 0.0) r += (lc - lys) * log(1.0 - p);
+        return r;
+    } else {
+        const double z = (lys - eta) / sigma;
+        return lc * c0 - 0.5 * (lsq / (sigma * sigma) + lc * z * z);
+    }
 }
 
 // Philox4x32-10; counter = (idx, iteration, chain, stream), key = seed.  Must match oracle/oracle.cpp.

@@ -387,6 +387,19 @@ static int set_xb(gmb_model* mdl, const double* beta) {
     GMB_CUDA(cudaMemcpyAsync(mdl->dbeta, ctx->h_pinned, sizeof(double) * mdl->P, cudaMemcpyHostToDevice, ctx->stream));
     xb_kernel2<<<(mdl->n + 255) / 256, 256, 0, ctx->stream>>>(mdl->n, mdl->P, mdl->ldn, mdl->dX, mdl->dbeta, mdl->dxb);
     ctx->launches++;
+    if (mdl->agg.built && mdl->agg.active) {       // the sampler's aggregated view (aggregate.cu)
+        xb_kernel2<<<(mdl->agg.ng + 255) / 256, 256, 0, ctx->stream>>>(mdl->agg.ng, mdl->P, mdl->agg.ldn, mdl->agg.dX, mdl->dbeta, mdl->agg.dxb);
+        ctx->launches++;
+    }
+    return GMB_OK;
+}
+
+// Z L of the sampler's aggregated view, from the factor the model currently holds
+static int agg_update_zl(gmb_model* mdl) {
+    gmb_agg& a = mdl->agg;
+    if (!a.built || !a.active || a.zl_valid) return GMB_OK;
+    GMB_TRY(gmb_dgemm(mdl->ctx, 0, 0, a.ng, mdl->Q, mdl->Q, 1.0, a.dZ, a.ldn, mdl->dL, mdl->ldq, 0.0, a.dZL, a.ldn));
+    a.zl_valid = true;
     return GMB_OK;
 }
 
@@ -402,7 +415,9 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     if (mdl->flink == 7 && !(var_par > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0");
     gmb_ctx* ctx = mdl->ctx;
     GMB_CUDA(cudaSetDevice(ctx->device));
-    if (L) GMB_TRY(gmb_hmc_prepare(mdl, L));
+    if (g_hmc_variant != 1) GMB_TRY(gmb_agg_ensure(mdl));       // row view of the on-chip sampler (not used by the two-GEMM variant)
+    if (L) { GMB_TRY(gmb_hmc_prepare(mdl, L)); mdl->agg.zl_valid = false; }
+    GMB_TRY(agg_update_zl(mdl));
     GMB_TRY(set_xb(mdl, beta));
     const int C = n_chains, cols = nsamp_per_chain + 1;
     const size_t ncol = (size_t)C * cols;
@@ -434,6 +449,9 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
         stats->kernel_ms = ms;
         stats->n_chains = C;
         stats->nsamp_per_chain = nsamp_per_chain;
+        const bool fused = fits && g_hmc_variant != 1;
+        stats->kernel_variant = fused ? 2 : 1;
+        stats->rows_used = (fused && mdl->agg.built) ? mdl->agg.ng : mdl->n;
     }
     if (V_out)
         GMB_CUDA(cudaMemcpy2DAsync(V_out, mdl->Q * sizeof(double), mdl->dV, mdl->ldq * sizeof(double), mdl->Q * sizeof(double), ncol,

@@ -25,6 +25,9 @@ int tiles_per_cta(int n, int cs) {
     return (tiles + cs - 1) / cs;
 }
 
+// rows of the sampler's view of a model (after row aggregation, aggregate.cu); the model's own n before the view is built
+int view_rows(const gmb_model* mdl) { return mdl->agg.built ? mdl->agg.ng : mdl->n; }
+
 bool fused_fits(int n, int Q, int cs, int fl) {
     const int ld = fused_ld(Q);
     if (ld / 4 > 33) return false;
@@ -43,14 +46,15 @@ int forced_cs() {
 // state update and barriers); a cluster launch keeps 148 (CS = 2) or 132 (CS = 4) SMs busy (B300_MICROARCH.md).
 int choose_cs(const gmb_model* mdl, int C) {
     const int f = forced_cs();
-    if (f == 1 || f == 2 || f == 4) return fused_fits(mdl->n, mdl->Q, f, mdl->flink) ? f : 0;
+    const int n = view_rows(mdl);
+    if (f == 1 || f == 2 || f == 4) return fused_fits(n, mdl->Q, f, mdl->flink) ? f : 0;
     const int groups = (C + CB - 1) / CB, sms = mdl->ctx->sms;
     int best = 0; double best_cost = 0.0;
     for (int cs = 1; cs <= 4; cs *= 2) {
-        if (!fused_fits(mdl->n, mdl->Q, cs, mdl->flink)) continue;
+        if (!fused_fits(n, mdl->Q, cs, mdl->flink)) continue;
         const int usable = cs == 4 ? (sms / 4 * 4 * 132) / 148 : sms / cs * cs;
         const int waves = (groups * cs + usable - 1) / (usable > 0 ? usable : 1);
-        const int tpw = (tiles_per_cta(mdl->n, cs) + NWARP - 1) / NWARP;
+        const int tpw = (tiles_per_cta(n, cs) + NWARP - 1) / NWARP;
         const double cost = waves * (tpw + 2.0 + (cs > 1 ? 0.75 : 0.0));
         if (!best || cost < best_cost) { best = cs; best_cost = cost; }
     }
@@ -83,12 +87,15 @@ int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, dou
                       int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs) {
     gmb_ctx* ctx = mdl->ctx;
     const int cs = choose_cs(mdl, C);
-    if (!cs) return gmb_set_error(GMB_EINVAL, "Z L (%d x %d) does not fit the on-chip sampler", mdl->n, mdl->Q);
+    if (!cs) return gmb_set_error(GMB_EINVAL, "Z L (%d x %d) does not fit the on-chip sampler", view_rows(mdl), mdl->Q);
+    const gmb_agg& a = mdl->agg;
+    if (!a.built) return gmb_set_error(GMB_ESTATE, "on-chip sampler: the row view of the model has not been built");
     FusedParams p;
-    p.n = mdl->n; p.Q = mdl->Q; p.ld = fused_ld(mdl->Q); p.ks = p.ld / 4; p.qt8 = (mdl->Q + 7) / 8;
-    p.ldn = mdl->ldn; p.ldq = mdl->ldq;
-    p.tiles_per_cta = tiles_per_cta(mdl->n, cs); p.n8 = p.tiles_per_cta * 8;
-    p.ZL = mdl->dZL; p.xb = mdl->dxb; p.y = mdl->dy; p.rowc = mdl->drowc;
+    p.n = a.ng; p.Q = mdl->Q; p.ld = fused_ld(mdl->Q); p.ks = p.ld / 4; p.qt8 = (mdl->Q + 7) / 8;
+    p.ldn = a.ldn; p.ldq = mdl->ldq;
+    p.tiles_per_cta = tiles_per_cta(a.ng, cs); p.n8 = p.tiles_per_cta * 8;
+    p.ZL = a.active ? a.dZL : mdl->dZL; p.xb = a.active ? a.dxb : mdl->dxb;
+    p.cnt = a.dcnt; p.ys = a.dys; p.lcnt = a.dlcnt; p.lys = a.dlys; p.lsq = a.dlsq; p.lrc = a.dlrc;
     p.var_par = var_par; p.lambda = lambda; p.target_accept = target_accept;
     p.warmup = warmup; p.nsamp = nsamp; p.max_steps = max_steps; p.adapt = adapt; p.C = C;
     p.chain_offset = chain_offset; p.seed = seed; p.dV_out = dV_out; p.cs_out = d_cs;

@@ -26,7 +26,7 @@
 // free.
 //
 // Thread-block clusters (CS = 2 or 4 CTAs per group of 8 chains): the observations are split over the CTAs of a
-// cluster, each keeps only its rows of Z L (and of xb, y) in shared memory and computes a partial gradient; the
+// cluster, each keeps only its rows of Z L (and of xb and the row weights) in shared memory and computes a partial gradient; the
 // partials are exchanged through distributed shared memory (one remote store per gradient element, double buffered)
 // and one cluster barrier per leapfrog step, after which every CTA of the cluster sums them in rank order and advances
 // an identical replica of the chain state.  That (i) lets a group of 8 chains use CS SMs, so that a sampling run with
@@ -41,7 +41,9 @@ namespace cg = cooperative_groups;
 struct FusedParams {
     int n, Q, ld, ks, qt8, ldn, ldq, n8;          // n8: rows of Z L one CTA holds (tiles_per_cta * 8)
     int tiles_per_cta;
-    const double* ZL; const double* xb; const double* y; const double* rowc;
+    const double* ZL; const double* xb;            // the sampler's view of the model: n rows (distinct rows of [X | Z], aggregate.cu)
+    const double* cnt; const double* ys;           // residual weights of the view's rows
+    const double* lcnt; const double* lys; const double* lsq; const double* lrc;   // log-likelihood weights
     double var_par, lambda, target_accept;
     int warmup, nsamp, max_steps, adapt, C;
     uint32_t chain_offset; unsigned long long seed;
@@ -112,21 +114,23 @@ __device__ __forceinline__ double quad_sum(double v) {
 // Gradient contributions of `NT` (1, 2 or 4) tiles of 8 observations, local rows r0[t] .. r0[t]+7, for the 8 chains of the group.
 // MASK: rows >= nloc exist in the tile (only the last tile of a CTA whose row count is not a multiple of 8).
 // LL: also accumulate the family log-likelihood of the chains that are on their last leapfrog step.
-// SMROW: xb / y / rowc point to shared memory (cluster variant) instead of global memory.
+// SMROW: xb / cnt / ys point to shared memory (cluster variant) instead of global memory.  lw: the log-likelihood weights of this
+// CTA's rows in global memory (read on the last leapfrog step of a chain only).
+struct LLRows { const double* cnt; const double* ys; const double* sq; const double* rc; };
 template <int FL, int KS, int NT, bool MASK, bool LL, bool SMROW>
 __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, const double* __restrict__ sTab, const double (&bf)[KS],
                                             const int (&r0)[NT], int nloc,
-                                            const double* __restrict__ xb, const double* __restrict__ y, const double* __restrict__ rowc,
-                                            double c0, double sigma, bool want0, bool want1, int fr, int fk,
+                                            const double* __restrict__ xb, const double* __restrict__ cnt, const double* __restrict__ ys,
+                                            const LLRows lw, double c0, double sigma, bool want0, bool want1, int fr, int fk,
                                             double (&gacc)[(KS + 1) / 2][2], double& ll0, double& ll1, FusedTim& tim) {
     constexpr int LD = 4 * KS, QT8 = (KS + 1) / 2;
-    double a[NT][2], xbv[NT], yv[NT];
+    double a[NT][2], xbv[NT], cv[NT], yv[NT];
 #pragma unroll
     for (int t = 0; t < NT; t++) {
         const int row = r0[t] + fr;
         const bool ok = !MASK || row < nloc;
-        if (SMROW) { xbv[t] = ok ? xb[row] : 0.0; yv[t] = ok ? y[row] : 0.0; }
-        else { xbv[t] = ok ? __ldg(xb + row) : 0.0; yv[t] = ok ? __ldg(y + row) : 0.0; }
+        if (SMROW) { xbv[t] = ok ? xb[row] : 0.0; cv[t] = ok ? cnt[row] : 0.0; yv[t] = ok ? ys[row] : 0.0; }
+        else { xbv[t] = ok ? __ldg(xb + row) : 0.0; cv[t] = ok ? __ldg(cnt + row) : 0.0; yv[t] = ok ? __ldg(ys + row) : 0.0; }
         a[t][0] = a[t][1] = 0.0;
     }
     // eta tiles: rows x 8 chains; NT independent accumulator chains
@@ -139,16 +143,19 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
 #pragma unroll
     for (int t = 0; t < NT; t++) {
         const double eta0 = xbv[t] + a[t][0], eta1 = xbv[t] + a[t][1];
-        res[t][0] = dev_family_resid_tab<FL>(yv[t], eta0, sTab);
-        res[t][1] = dev_family_resid_tab<FL>(yv[t], eta1, sTab);
+        res[t][0] = dev_family_resid_w<FL>(cv[t], yv[t], eta0, sTab);
+        res[t][1] = dev_family_resid_w<FL>(cv[t], yv[t], eta1, sTab);
         if (MASK) { const bool ok = r0[t] + fr < nloc; if (!ok) { res[t][0] = 0.0; res[t][1] = 0.0; } }
         if (LL) {
             const bool ok = !MASK || r0[t] + fr < nloc;
-            double rc = 0.0;
-            if (FL == 1 && ok) rc = SMROW ? rowc[r0[t] + fr] : __ldg(rowc + r0[t] + fr);
-            const double l0 = dev_family_ll<FL>(yv[t], eta0, rc, c0, sigma), l1 = dev_family_ll<FL>(yv[t], eta1, rc, c0, sigma);
-            if (want0 && ok) ll0 += l0;
-            if (want1 && ok) ll1 += l1;
+            if (ok) {
+                const int row = r0[t] + fr;
+                const double lc = __ldg(lw.cnt + row), ly = __ldg(lw.ys + row);
+                const double lq = (FL == 7) ? __ldg(lw.sq + row) : 0.0, lr = (FL == 1) ? __ldg(lw.rc + row) : 0.0;
+                const double l0 = dev_family_ll_w<FL>(lc, ly, lq, lr, eta0, c0, sigma), l1 = dev_family_ll_w<FL>(lc, ly, lq, lr, eta1, c0, sigma);
+                if (want0) ll0 += l0;
+                if (want1) ll1 += l1;
+            }
         }
     }
     GMB_TICK(6);                                       // residuals
@@ -180,7 +187,7 @@ __host__ __device__ inline FusedLayout fused_layout(int n8, int ld, int cs, int 
     int o = 0;
     L.zl = o;    o += n8 * ld + 8;                        // Z L rows of this CTA (+8 spill-over doubles for the padded q-tile reads)
     L.tab = o;   o += 64;                                 // 2^(j/64)
-    L.rowv = o;  o += (cs > 1) ? (fl == 1 ? 3 : 2) * n8 : 0;   // xb, y (, rowc) of this CTA's rows (cluster variant)
+    L.rowv = o;  o += (cs > 1) ? 3 * n8 : 0;               // xb, cnt, ys of this CTA's rows (cluster variant)
     L.slot = o;  o += ((cs > 1) ? NWARP : NWARP / 2) * qp8 * 9;   // per-warp partial gradients
     L.ll = o;    o += NWARP * CB;                         // per-warp partial log-likelihoods
     L.xch = o;   o += npar * cs * CB * ld;                // [parity][rank][chain][q] partial gradients of every CTA of the cluster
@@ -203,8 +210,8 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     double* sZL = sm + lay.zl;
     double* sTab = sm + lay.tab;
     double* sXB = sm + lay.rowv;                      // cluster variant only
-    double* sY = sXB + p.n8;
-    double* sRC = sY + p.n8;
+    double* sCN = sXB + p.n8;
+    double* sYS = sCN + p.n8;
     double* sSlot = sm + lay.slot;                    // [slots][QP8][9]
     double* sLL = sm + lay.ll;                        // [NWARP][CB]
     double* sXch = sm + lay.xch;                      // [parities][CS][CB][LD]
@@ -243,13 +250,14 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         for (int idx = tid; idx < p.n8; idx += THREADS) {
             const bool ok = idx < nloc;
             sXB[idx] = ok ? p.xb[row0 + idx] : 0.0;
-            sY[idx] = ok ? p.y[row0 + idx] : 0.0;
-            if (FL == 1) sRC[idx] = ok ? p.rowc[row0 + idx] : 0.0;
+            sCN[idx] = ok ? p.cnt[row0 + idx] : 0.0;
+            sYS[idx] = ok ? p.ys[row0 + idx] : 0.0;
         }
     }
     const double* rxb = CL ? sXB : p.xb;
-    const double* ry = CL ? sY : p.y;
-    const double* rrc = CL ? sRC : p.rowc;
+    const double* rcn = CL ? sCN : p.cnt;
+    const double* rys = CL ? sYS : p.ys;
+    const LLRows lw = {p.lcnt + row0, p.lys + row0, p.lsq + row0, p.lrc + row0};
     // shared::cluster addresses of the exchange buffers and mbarriers of every CTA of the cluster (distributed shared memory)
     uint32_t xch_of[CS], xll_of[CS], bar_of[CS];
     if (CL) {
@@ -305,28 +313,28 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         if (!with_ll) {
             for (; tile + 3 * NWARP < nfull; tile += 4 * NWARP) {
                 const int r0[4] = {tile * 8, (tile + NWARP) * 8, (tile + 2 * NWARP) * 8, (tile + 3 * NWARP) * 8};
-                fused_tiles<FL, KS, 4, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
+                fused_tiles<FL, KS, 4, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, rcn, rys, lw, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             for (; tile + NWARP < nfull; tile += 2 * NWARP) {
                 const int r0[2] = {tile * 8, (tile + NWARP) * 8};
-                fused_tiles<FL, KS, 2, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
+                fused_tiles<FL, KS, 2, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, rcn, rys, lw, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             for (; tile < nfull; tile += NWARP) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
+                fused_tiles<FL, KS, 1, false, false, CL>(sZL, sTab, vp, r0, nloc, rxb, rcn, rys, lw, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             if (has_tail && tile == nfull) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, false, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
+                fused_tiles<FL, KS, 1, true, false, CL>(sZL, sTab, vp, r0, nloc, rxb, rcn, rys, lw, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
         } else {
             for (; tile < nfull; tile += NWARP) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, false, true, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
+                fused_tiles<FL, KS, 1, false, true, CL>(sZL, sTab, vp, r0, nloc, rxb, rcn, rys, lw, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             if (has_tail && tile == nfull) {
                 const int r0[1] = {tile * 8};
-                fused_tiles<FL, KS, 1, true, true, CL>(sZL, sTab, vp, r0, nloc, rxb, ry, rrc, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
+                fused_tiles<FL, KS, 1, true, true, CL>(sZL, sTab, vp, r0, nloc, rxb, rcn, rys, lw, c0, sigma, want0, want1, fr, fk, gacc, ll0, ll1, tim);
             }
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, 4);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 4);
             ll0 += __shfl_xor_sync(0xffffffffu, ll0, 8);  ll1 += __shfl_xor_sync(0xffffffffu, ll1, 8);

@@ -121,6 +121,8 @@ typedef struct gmb_hmc_stats {
     double kernel_ms;        /* device time of the sampling kernel(s) */
     int    n_chains;
     int    nsamp_per_chain;
+    int    rows_used;        /* rows the sampler ran on: n, or the number of distinct rows of [X | Z] when aggregated */
+    int    kernel_variant;   /* 1 = two-GEMM, 2 = on-chip */
 } gmb_hmc_stats;
 
 /* Runs n_chains independent copies of mcmcRunHMC::sample(warmup, .) (mhmcmc.h:121-157), each with its own
@@ -149,6 +151,10 @@ int gmb_hmc_set_cluster_size(int cs);
 /* E-step evaluation strategy for poisson/log and gaussian/identity: 1 (default) = O(n) evaluations from row statistics of zd built once per
  * sample matrix; 0 = stream zd on every evaluation (used by the roofline probes and the parity tests of the streaming kernel). */
 int gmb_estep_set_rowstats(int on);
+
+/* On-chip sampler: 1 (default) = observations that share their row of [X | Z] (hence their linear predictor) are aggregated into one
+ * weighted row (aggregate.cu; config C2: 500 rows -> 50), 0 = one row per observation.  Same sums in a different order. */
+int gmb_hmc_set_row_aggregation(int on);
 
 /* mcmlModel::log_prob / log_grad (mcmlmodel.h:138-153, 156-279, usezl = true) for C whitened states V (Q x C):
  * lp[C], grad (Q x C).  Either output may be NULL.  Used by the parity tests and by mcml_la. */

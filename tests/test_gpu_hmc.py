@@ -119,3 +119,47 @@ def test_mcmc_sample_shape_and_reference_quirk(gctx):
     s2 = g.mcmc_sample(cfg["Z"], cfg["L"], cfg["X"], cfg["y"], cfg["beta"], "binomial", "logit", warmup=10, nsamp=21, lam=0.05,
                        n_chains=1, seed=5)
     assert np.array_equal(s, s2)
+
+
+def test_row_aggregation_is_exact_and_active(gctx, oracle):
+    """Observations that share their row of [X | Z] are aggregated for the on-chip sampler (aggregate.cu): C2 has 500 rows but 50
+    distinct ones.  Chains with and without aggregation agree to rounding, both follow the oracle chain, and a model whose rows are
+    all distinct runs on the identity view."""
+    import glmmrmcml_b200 as g
+    cfg = synth.config2(m=4)
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    ZL = cfg["Z"] @ cfg["L"]; xb = cfg["X"] @ cfg["beta"]
+    outs = {}
+    try:
+        for on in (True, False):
+            g.hmc_set_row_aggregation(on)
+            mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+            outs[on] = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=15, nsamp_per_chain=5, lam=2.0, max_steps=40, target_accept=0.8,
+                                      n_chains=10, seed=99, want_u=False, want_v=True)
+            mdl.close()
+    finally:
+        g.hmc_set_row_aggregation(True)
+    assert outs[True]["stats"]["rows_used"] == 50 and outs[False]["stats"]["rows_used"] == 500
+    assert outs[True]["stats"]["kernel_variant"] == 2
+    assert np.max(np.abs(outs[True]["v"] - outs[False]["v"])) <= 1e-8
+    assert outs[True]["stats"]["accept_rate"] == outs[False]["stats"]["accept_rate"]
+    for c in (0, 7):
+        ref = oracle.hmc_chain(ZL, cfg["L"], xb, cfg["y"], 1.0, fl, 15, 5, 2.0, 40, 0.8, 99, chain=c)
+        assert np.max(np.abs(outs[True]["v"][:, c * 6:(c + 1) * 6] - ref["v"])) <= 1e-7
+    # gaussian with repeated rows (two observations per location): the within-row sum of squares enters the log-density
+    c5 = synth.config5(nloc=20, nobs=3, m=4)
+    rng = np.random.default_rng(2)
+    yg = c5["X"] @ c5["beta"] + c5["Z"] @ c5["U"][:, 0] + 0.5 * rng.standard_normal(c5["n"])
+    mdl = g.Model(gctx, c5["X"][:, :1], c5["Z"], yg, "gaussian", "identity")
+    out = mdl.hmc_sample(c5["L"], c5["beta"][:1], 0.7, warmup=12, nsamp_per_chain=4, lam=0.5, max_steps=20, target_accept=0.8, n_chains=3, seed=5,
+                         want_u=False, want_v=True)
+    assert out["stats"]["rows_used"] == 20
+    ref = oracle.hmc_chain(c5["Z"] @ c5["L"], c5["L"], c5["X"][:, :1] @ c5["beta"][:1], yg, 0.7, 7, 12, 4, 0.5, 20, 0.8, 5, chain=1)
+    assert np.max(np.abs(out["v"][:, 5:10] - ref["v"])) <= 1e-7
+    mdl.close()
+    # all rows distinct (C3: Z = I): identity view
+    c3 = synth.config3(nloc=40, m=4)
+    mdl = g.Model(gctx, c3["X"], c3["Z"], c3["y"], "gaussian", "identity")
+    out = mdl.hmc_sample(c3["L"], c3["beta"], 1.0, warmup=5, nsamp_per_chain=2, lam=0.5, max_steps=10, n_chains=2, seed=1, want_u=False, want_v=True)
+    assert out["stats"]["rows_used"] == 40
+    mdl.close()
