@@ -16,8 +16,8 @@ int fused_ld(int Q) {
 
 constexpr size_t SMEM_LIMIT = (size_t)227 * 1024;
 
-size_t fused_smem_bytes(int n8, int ld, int cs, int fl) {
-    return sizeof(double) * (size_t)fused_layout(n8, ld, cs, fl).total + 16;
+size_t fused_smem_bytes(int n8, int ld, int cs, int fl, int slots8) {
+    return sizeof(double) * (size_t)fused_layout(n8, ld, cs, fl, slots8).total + 16;
 }
 
 int tiles_per_cta(int n, int cs) {
@@ -31,7 +31,7 @@ int view_rows(const gmb_model* mdl) { return mdl->agg.built ? mdl->agg.ng : mdl-
 bool fused_fits(int n, int Q, int cs, int fl) {
     const int ld = fused_ld(Q);
     if (ld / 4 > 33) return false;
-    return fused_smem_bytes(tiles_per_cta(n, cs) * 8, ld, cs, fl) <= SMEM_LIMIT;
+    return fused_smem_bytes(tiles_per_cta(n, cs) * 8, ld, cs, fl, 0) <= SMEM_LIMIT;
 }
 
 // forced cluster size (0 = choose): gmb_hmc_set_cluster_size or the environment variable GMB_FUSED_CS
@@ -105,24 +105,26 @@ int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, dou
     {
         static long long* d_tim = nullptr;
         const int ctas = (C + CB - 1) / CB * cs;
-        if (!d_tim) GMB_CUDA(cudaMalloc(&d_tim, sizeof(long long) * 8 * 4096));
-        GMB_CUDA(cudaMemsetAsync(d_tim, 0, sizeof(long long) * 8 * 4096, ctx->stream));
+        if (!d_tim) GMB_CUDA(cudaMalloc(&d_tim, sizeof(long long) * 12 * 4096));
+        GMB_CUDA(cudaMemsetAsync(d_tim, 0, sizeof(long long) * 12 * 4096, ctx->stream));
         p.timing = d_tim;
         struct Dump { long long* d; int ctas; cudaStream_t st; };
         static Dump last; last = {d_tim, ctas, ctx->stream};
         // the caller synchronises the stream; print the previous launch's counters on the next call or at exit
         static bool reg = false;
         if (!reg) { reg = true; atexit([] {
-            std::vector<long long> h(8 * 4096); cudaMemcpy(h.data(), last.d, sizeof(long long) * 8 * last.ctas, cudaMemcpyDeviceToHost);
-            long long tot[8] = {0}; for (int b = 0; b < last.ctas; b++) for (int i = 0; i < 8; i++) tot[i] += h[b * 8 + i];
-            long long all = 0; for (int i = 0; i < 8; i++) all += tot[i];
-            const char* nm[8] = {"update+proposal", "tiles: eta", "slots+local sum", "exchange stores", "barrier", "fragment read", "tiles: residual", "tiles: gradient"};
+            std::vector<long long> h(12 * 4096); cudaMemcpy(h.data(), last.d, sizeof(long long) * 12 * last.ctas, cudaMemcpyDeviceToHost);
+            long long tot[12] = {0}; for (int b = 0; b < last.ctas; b++) for (int i = 0; i < 12; i++) tot[i] += h[b * 12 + i];
+            long long all = 0; for (int i = 0; i < 12; i++) all += tot[i];
+            const char* nm[12] = {"leapfrog update", "tiles: eta", "slots+local sum", "exchange stores", "barrier", "fragment read", "tiles: residual", "tiles: gradient",
+                                  "proposal setup", "metropolis+store", "-", "-"};
             fprintf(stderr, "[GMB_FUSED_TIMING] last launch, %d CTAs, mean cycles per CTA:\n", last.ctas);
-            for (int i = 0; i < 8; i++) fprintf(stderr, "  %-18s %12.0f  %5.1f%%\n", nm[i], (double)tot[i] / last.ctas, 100.0 * tot[i] / (all ? all : 1));
+            for (int i = 0; i < 10; i++) fprintf(stderr, "  %-18s %12.0f  %5.1f%%\n", nm[i], (double)tot[i] / last.ctas, 100.0 * tot[i] / (all ? all : 1));
         }); }
     }
 #endif
-    const size_t smem = fused_smem_bytes(p.n8, p.ld, cs, mdl->flink);
+    p.slots8 = (cs == 1 && fused_smem_bytes(p.n8, p.ld, cs, mdl->flink, 1) <= SMEM_LIMIT) ? 1 : 0;
+    const size_t smem = fused_smem_bytes(p.n8, p.ld, cs, mdl->flink, p.slots8);
     switch (mdl->flink) {
     case 1: return gmb_fused_launch_fl1(ctx, p, smem, cs);
     case 3: return gmb_fused_launch_fl3(ctx, p, smem, cs);

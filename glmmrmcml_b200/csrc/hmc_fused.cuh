@@ -41,6 +41,7 @@ namespace cg = cooperative_groups;
 struct FusedParams {
     int n, Q, ld, ks, qt8, ldn, ldq, n8;          // n8: rows of Z L one CTA holds (tiles_per_cta * 8)
     int tiles_per_cta;
+    int slots8;                                    // 1: one gradient slot per warp also without a cluster (the model is small enough)
     const double* ZL; const double* xb;            // the sampler's view of the model: n rows (distinct rows of [X | Z], aggregate.cu)
     const double* cnt; const double* ys;           // residual weights of the view's rows
     const double* lcnt; const double* lys; const double* lsq; const double* lrc;   // log-likelihood weights
@@ -55,7 +56,7 @@ struct FusedParams {
 // Optional per-phase cycle counters (build with EXTRA=-DGMB_FUSED_TIMING): thread 0 of every CTA accumulates clock64()
 // differences per phase of a leapfrog step into FusedParams::timing[blockIdx.x * 8 + phase] (tools/hmc_phase_timing.py).
 #ifdef GMB_FUSED_TIMING
-struct FusedTim { long long acc[8]; long long last; bool rec; };
+struct FusedTim { long long acc[12]; long long last; bool rec; };
 #define GMB_TICK(i) do { if (tim.rec) { const long long now__ = clock64(); tim.acc[i] += now__ - tim.last; tim.last = now__; } } while (0)
 #else
 struct FusedTim { };
@@ -133,7 +134,8 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
         else { xbv[t] = ok ? __ldg(xb + row) : 0.0; cv[t] = ok ? __ldg(cnt + row) : 0.0; yv[t] = ok ? __ldg(ys + row) : 0.0; }
         a[t][0] = a[t][1] = 0.0;
     }
-    // eta tiles: rows x 8 chains; NT independent accumulator chains
+    // eta tiles: rows x 8 chains; NT independent accumulator chains (splitting a tile's k range over several partial accumulators when
+    // NT < 4 was measured: slower)
 #pragma unroll
     for (int j = 0; j < KS; j++)
 #pragma unroll
@@ -180,7 +182,7 @@ __device__ __forceinline__ void fused_tiles(const double* __restrict__ sZL, cons
 struct FusedLayout {
     int zl, tab, rowv, slot, ll, xch, xll, mbar, total;   // offsets in doubles
 };
-__host__ __device__ inline FusedLayout fused_layout(int n8, int ld, int cs, int fl) {
+__host__ __device__ inline FusedLayout fused_layout(int n8, int ld, int cs, int fl, int slots8) {
     const int qp8 = ((ld / 4 + 1) / 2) * 8;
     const int npar = cs > 1 ? 2 : 1;
     FusedLayout L;
@@ -188,7 +190,7 @@ __host__ __device__ inline FusedLayout fused_layout(int n8, int ld, int cs, int 
     L.zl = o;    o += n8 * ld + 8;                        // Z L rows of this CTA (+8 spill-over doubles for the padded q-tile reads)
     L.tab = o;   o += 64;                                 // 2^(j/64)
     L.rowv = o;  o += (cs > 1) ? 3 * n8 : 0;               // xb, cnt, ys of this CTA's rows (cluster variant)
-    L.slot = o;  o += ((cs > 1) ? NWARP : NWARP / 2) * qp8 * 9;   // per-warp partial gradients
+    L.slot = o;  o += ((cs > 1 || slots8) ? NWARP : NWARP / 2) * qp8 * 9;   // per-warp partial gradients
     L.ll = o;    o += NWARP * CB;                         // per-warp partial log-likelihoods
     L.xch = o;   o += npar * cs * CB * ld;                // [parity][rank][chain][q] partial gradients of every CTA of the cluster
     L.xll = o;   o += npar * cs * CB;                     // [parity][rank][chain] partial log-likelihoods
@@ -206,7 +208,8 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     constexpr bool CL = CS > 1;
     extern __shared__ __align__(16) double sm[];
     const int Q = p.Q;
-    const FusedLayout lay = fused_layout(p.n8, LD, CS, FL);
+    const FusedLayout lay = fused_layout(p.n8, LD, CS, FL, p.slots8);
+    const bool slots8 = CL || p.slots8;              // one slot per warp (one barrier) when shared memory allows, else 4 slots in two phases
     double* sZL = sm + lay.zl;
     double* sTab = sm + lay.tab;
     double* sXB = sm + lay.rowv;                      // cluster variant only
@@ -295,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     else __syncthreads();
     FusedTim tim;
 #ifdef GMB_FUSED_TIMING
-    for (int i = 0; i < 8; i++) tim.acc[i] = 0;
+    for (int i = 0; i < 12; i++) tim.acc[i] = 0;
     tim.last = clock64(); tim.rec = (tid == 0);
 #endif
     // One evaluation of the gradient at the v' held in vp[], for the 8 chains of the group.
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         double gsum[QT32];                            // this CTA's partial for chain `warp`, q = lane + 32 k
 #pragma unroll
         for (int k = 0; k < QT32; k++) gsum[k] = 0.0;
-        if (!CL) {
+        if (!slots8) {
             // warps 4-7 -> 4 slots, warps 0-3 add, then warp c sums the 4 slots of chain c
             double* slot = sSlot + (warp & 3) * QP8 * 9;
             if (warp >= 4) {
@@ -458,6 +461,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
     }
 
     for (int t = 0; t < total; t++) {
+        GMB_TICK(9);                                   // Metropolis test, adaptation, sample store (previous proposal)
         __syncthreads();                               // the owners' scratch stores of the previous proposal are visible
         // ---- new_proposal, mhmcmc.h:61-75 ----
         double k0 = 0.0, pv = 0.0;
@@ -493,6 +497,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, 8));
         smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, 16));
         const int st0 = __shfl_sync(0xffffffffu, steps, 8 * fk), st1 = __shfl_sync(0xffffffffu, steps, 8 * fk + 4);
+        GMB_TICK(8);                                   // proposal: momentum draw, first half step
         // ---- leapfrog integrator, :73-78 ----
         for (int s = 0; s < smax; s++) {
             const bool any_last = __any_sync(0xffffffffu, s == steps - 1);   // some chain needs its log-likelihood on this step
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(THREADS, 1) hmc_fused_kernel(const FusedParams
         p.cs_out[FS_TOTSTEPS * C + chain] = totsteps; p.cs_out[FS_LASTPROB * C + chain] = lastprob;
     }
 #ifdef GMB_FUSED_TIMING
-    if (tid == 0 && p.timing) for (int i = 0; i < 8; i++) p.timing[blockIdx.x * 8 + i] = tim.acc[i];
+    if (tid == 0 && p.timing) for (int i = 0; i < 12; i++) p.timing[blockIdx.x * 12 + i] = tim.acc[i];
 #endif
     if (CL) cg::this_cluster().sync();                // no CTA may exit while a peer can still store into its shared memory
 }
