@@ -49,6 +49,11 @@ def hmc_set_cluster_size(cs: int):
     check(lib().gmb_hmc_set_cluster_size(int(cs)))
 
 
+def cov_set_gram(on: bool):
+    """mvn_ll on a model's samples: True (default) = Gram-matrix path for small blocks, False = stream the samples every time."""
+    check(lib().gmb_cov_set_gram(int(bool(on))))
+
+
 def hmc_set_row_aggregation(on: bool):
     """On-chip sampler: True (default) = aggregate observations that share their row of [X | Z]; False = one row per observation."""
     check(lib().gmb_hmc_set_row_aggregation(int(bool(on))))

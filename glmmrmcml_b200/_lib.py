@@ -71,6 +71,7 @@ PROTOTYPES = {
     "gmb_hmc_set_cluster_size": (C.c_int, [C.c_int]),
     "gmb_estep_set_rowstats": (C.c_int, [C.c_int]),
     "gmb_hmc_set_row_aggregation": (C.c_int, [C.c_int]),
+    "gmb_cov_set_gram": (C.c_int, [C.c_int]),
     "gmb_model_logprob_grad": (C.c_int, [vp, dp, dp, C.c_double, dp, C.c_int, dp, dp]),
     "gmb_set_default_ctx": (C.c_int, [vp]),
     "gmb_cov_shape": (C.c_int, [ip, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

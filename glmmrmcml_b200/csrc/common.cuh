@@ -104,6 +104,7 @@ struct gmb_model {
     int m_cap = 0;
     int m_local = 0, niter_local = 0, m_total = 0, niter_total = 0;
     bool zd_valid = false;
+    unsigned long long u_version = 1;   // bumped whenever dU changes (caches keyed on the sample matrix: cov.cu Gram matrices)
     // sampler state
     double* dZL = nullptr;       // ldn x Q   (Z L)
     double* dL = nullptr;        // ldq x Q
@@ -143,6 +144,8 @@ struct gmb_cov {
     // inverses of the 64 x 64 diagonal blocks of the large blocks' factors (cov_large.cu), 64 x 64 col-major each
     double* d_linv = nullptr; size_t linv_doubles = 0;
     std::vector<long long> linv_off;     // per block: offset into d_linv (-1 for blocks that take the small / medium path)
+    // Gram matrices of a model's samples (cov.cu: cov_ensure_gram), laid out like d_Lblk
+    double* d_gram = nullptr; const gmb_model* gram_model = nullptr; unsigned long long gram_version = 0; int gram_cols = 0;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -186,6 +186,137 @@ __global__ void __launch_bounds__(128) quad_medium_kernel(CovBlock b, const doub
     if (threadIdx.x == 0) partials[blockIdx.x] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K5 through sufficient statistics (all blocks <= 16).  The samples are fixed while d_optim / f_hess evaluate mvn_ll at many theta
+// (likelihood.h:40-45), and sum_j ||L_b^-1 u_bj||^2 = tr(D_b^-1 S_b) with the Gram matrix S_b = sum_j u_bj u_bj'.  S_b is built by ONE
+// stream over U per sample matrix (gram_small_kernel + gram_reduce_kernel, cached per (model, sample version)); an evaluation is then a
+// single launch that builds D_b(theta), factorises it, forms row k of L_b^-1 by back substitution and accumulates x' S_b x — independent
+// of the number of samples.  Same sums as mcmldmatrix.h:23-78 in a different order (relative error ~ kappa(D_b) eps).
+// ---------------------------------------------------------------------------------------------------
+constexpr int GRAM_WARPS = 8;
+
+__global__ void __launch_bounds__(GRAM_WARPS * 32) gram_small_kernel(int B, const CovBlock* __restrict__ blocks, const double* __restrict__ U,
+                                                                      int ldu, int ncols, int cols_per_cta, long long gram_doubles,
+                                                                      double* __restrict__ part /* [gridDim.y][gram_doubles] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bi = blockIdx.x * GRAM_WARPS + warp;
+    if (bi >= B) return;
+    const CovBlock b = blocks[bi];
+    const int n = b.n, nn = n * n;
+    const int j0 = blockIdx.y * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
+    double acc[8];
+    int ei[8], ej[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) { const int e = lane + 32 * t; acc[t] = 0.0; ei[t] = e < nn ? e % n : 0; ej[t] = e < nn ? e / n : 0; }
+    for (int j = j0; j < j1; j++) {
+        const double* u = U + (size_t)j * ldu + b.start;
+#pragma unroll
+        for (int t = 0; t < 8; t++) if (lane + 32 * t < nn) acc[t] = fma(u[ei[t]], u[ej[t]], acc[t]);
+    }
+    double* out = part + (size_t)blockIdx.y * gram_doubles + b.l0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) if (lane + 32 * t < nn) out[lane + 32 * t] = acc[t];
+}
+
+__global__ void gram_reduce_kernel(long long gram_doubles, int nchunks, const double* __restrict__ part, double* __restrict__ gram) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= gram_doubles) return;
+    double s = 0.0;
+    for (int c = 0; c < nchunks; c++) s += part[(size_t)c * gram_doubles + e];
+    gram[e] = s;
+}
+
+__global__ void __launch_bounds__(FACT_WARPS * 32) mvn_gram_kernel(int B, const CovBlock* __restrict__ blocks, const CovFn* __restrict__ fns,
+                                                                    const double* __restrict__ data, const double* __restrict__ theta,
+                                                                    const double* __restrict__ gram, double ncols, double* __restrict__ Lblk,
+                                                                    double* __restrict__ logdet, int* __restrict__ status,
+                                                                    double* __restrict__ partials, unsigned int* __restrict__ counter,
+                                                                    double* __restrict__ out) {
+    __shared__ double sL[FACT_WARPS][QUAD_SMALL_MAX][QUAD_SMALL_MAX + 1];
+    __shared__ double sS[FACT_WARPS][QUAD_SMALL_MAX][QUAD_SMALL_MAX + 1];
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bi = blockIdx.x * FACT_WARPS + warp;
+    double contrib = 0.0;
+    if (bi < B) {
+        const CovBlock b = blocks[bi];
+        const int n = b.n;
+        double (*L)[QUAD_SMALL_MAX + 1] = sL[warp];
+        double (*S)[QUAD_SMALL_MAX + 1] = sS[warp];
+        if (lane < n) for (int j = 0; j <= lane; j++) L[lane][j] = block_val(b, fns, data, theta, lane, j);
+        for (int e = lane; e < n * n; e += 32) S[e % n][e / n] = gram[b.l0 + e];
+        __syncwarp();
+        bool bad = false;
+        for (int j = 0; j < n; j++) {                   // Cholesky–Banachiewicz, as factor_small_kernel
+            double s = 0.0;
+            if (lane >= j && lane < n) for (int k = 0; k < j; k++) s += L[lane][k] * L[j][k];
+            double djj = __shfl_sync(0xffffffffu, L[j][j] - s, j);
+            if (!(djj > 0.0)) { bad = true; if (lane == 0) atomicCAS(status, 0, b.start + j + 1); break; }
+            double d = sqrt(djj);
+            __syncwarp();
+            if (lane == j) L[j][j] = d;
+            else if (lane > j && lane < n) L[lane][j] = (L[lane][j] - s) / d;
+            __syncwarp();
+        }
+        if (bad) {
+            contrib = nan("");
+            if (lane == 0) logdet[bi] = nan("");
+        } else {
+            double ld = (lane < n) ? 2.0 * log(L[lane][lane]) : 0.0;
+            ld = warp_sum(ld);
+            if (lane == 0) logdet[bi] = ld;
+            for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; Lblk[b.l0 + e] = (j <= i) ? L[i][j] : 0.0; }
+            // lane k: x = row k of L^-1 (solve L' x = e_k by back substitution), q_k = x' S x
+            double q = 0.0;
+            if (lane < n) {
+                double x[QUAD_SMALL_MAX];
+                const int k = lane;
+#pragma unroll
+                for (int i = QUAD_SMALL_MAX - 1; i >= 0; i--) {
+                    double v = 0.0;
+                    if (i < n && i <= k) {
+                        double s = (i == k) ? 1.0 : 0.0;
+#pragma unroll
+                        for (int j = i + 1; j < QUAD_SMALL_MAX; j++) if (j <= k && j < n) s -= L[j][i] * x[j];
+                        v = s / L[i][i];
+                    }
+                    x[i] = v;
+                }
+#pragma unroll
+                for (int i = 0; i < QUAD_SMALL_MAX; i++) {
+                    if (i < n) {
+                        double t = 0.0;
+#pragma unroll
+                        for (int j = 0; j < QUAD_SMALL_MAX; j++) if (j < n) t = fma(S[i][j], x[j], t);
+                        q = fma(x[i], t, q);
+                    }
+                }
+            }
+            q = warp_sum(q);
+            contrib = ncols * (-0.5 * n * log(2 * 3.14159265358979323846) - 0.5 * ld) - 0.5 * q;   // mcmldmatrix.h:63,75 (M_PI)
+        }
+    }
+    // deterministic grid sum: lane 0 of each warp holds its block's contribution
+    if (lane == 0) red[warp] = (bi < B) ? contrib : 0.0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < FACT_WARPS; w++) v += red[w];
+        partials[blockIdx.x] = v;
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double s = 0.0;
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) s += partials[k];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) { out[0] = s; *counter = 0u; }
+    }
+}
+
 // final: out[0] = ncols * sum_b (-0.5 n_b log(2 pi) - 0.5 logdet_b) - 0.5 * sum(partials)   (mcmldmatrix.h:63,75: M_PI)
 __global__ void __launch_bounds__(256) mvn_finish_kernel(int B, const CovBlock* __restrict__ blocks, const double* __restrict__ logdet,
                                                          const double* __restrict__ partials, int npart, int ncols,
@@ -287,6 +418,7 @@ extern "C" void gmb_cov_destroy(gmb_cov* cv) {
     if (cv->dU) gmb_dfree(cv->ctx, cv->dU);
     if (cv->d_work) gmb_dfree(cv->ctx, cv->d_work);
     if (cv->d_linv) gmb_dfree(cv->ctx, cv->d_linv);
+    if (cv->d_gram) gmb_dfree(cv->ctx, cv->d_gram);
     delete cv;
 }
 
@@ -445,6 +577,34 @@ static int cov_finish_ll(gmb_cov* cv, double* d_out, int m_total, double* out) {
     return GMB_OK;
 }
 
+// 1 = mvn_ll on a model's samples goes through the Gram matrices when every block is <= 16 (default); 0 = always stream U
+static int g_cov_gram = 1;
+extern "C" int gmb_cov_set_gram(int on) { g_cov_gram = on ? 1 : 0; return GMB_OK; }
+
+// Gram matrices S_b = sum_j u_bj u_bj' of the model's local sample columns, cached per (model, sample version)
+static int cov_ensure_gram(gmb_cov* cv, gmb_model* mdl) {
+    gmb_ctx* ctx = cv->ctx;
+    if (cv->gram_model == mdl && cv->gram_version == mdl->u_version && cv->gram_cols == mdl->m_local && cv->d_gram) return GMB_OK;
+    const long long gd = cv->lblk_doubles;
+    if (!cv->d_gram) GMB_CUDA(gmb_dmalloc(ctx, &cv->d_gram, sizeof(double) * (gd > 0 ? gd : 1)));
+    const int ncols = mdl->m_local;
+    const int gx = (cv->B + GRAM_WARPS - 1) / GRAM_WARPS;
+    int CC = (ctx->sms * 8 + gx - 1) / gx;
+    const int max_cc = (ncols + 63) / 64;
+    if (CC > max_cc) CC = max_cc;
+    if (CC < 1) CC = 1;
+    const int cols_per_cta = (ncols + CC - 1) / CC;
+    CC = (ncols + cols_per_cta - 1) / cols_per_cta;
+    GMB_TRY(gmb_ctx_scratch(ctx, (size_t)CC * gd));
+    GMB_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(double) * (size_t)CC * gd, ctx->stream));
+    gram_small_kernel<<<dim3(gx, CC), GRAM_WARPS * 32, 0, ctx->stream>>>(cv->B, cv->d_blocks, mdl->dU, mdl->ldq, ncols, cols_per_cta, gd, ctx->d_scratch);
+    gram_reduce_kernel<<<(unsigned)((gd + 255) / 256), 256, 0, ctx->stream>>>(gd, CC, ctx->d_scratch, cv->d_gram);
+    ctx->launches += 2;
+    GMB_CUDA(cudaGetLastError());
+    cv->gram_model = mdl; cv->gram_version = mdl->u_version; cv->gram_cols = ncols;
+    return GMB_OK;
+}
+
 extern "C" int gmb_cov_mvn_ll(gmb_cov* cv, const double* theta, const double* U, int Q, int m_local, int m_total, double* out) {
     if (!cv || !theta || !out || (m_local > 0 && !U)) return gmb_set_error(GMB_EINVAL, "gmb_cov_mvn_ll: bad arguments");
     if (Q != cv->Q) return gmb_set_error(GMB_EINVAL, "u has %d rows, covariance has %d", Q, cv->Q);
@@ -462,6 +622,32 @@ extern "C" int gmb_cov_mvn_ll_model(gmb_cov* cv, const double* theta, gmb_model*
     if (mdl->Q != cv->Q) return gmb_set_error(GMB_EINVAL, "model has Q=%d, covariance has %d", mdl->Q, cv->Q);
     if (!mdl->dU || mdl->m_local < 0) return gmb_set_error(GMB_ESTATE, "the model holds no samples (call gmb_model_set_u or gmb_hmc_sample first)");
     cudaSetDevice(cv->ctx->device);
+    if (cv->max_n <= QUAD_SMALL_MAX && g_cov_gram && mdl->m_local > 0) {
+        // sufficient-statistics path: Gram matrices of the model's samples (cached), one launch per evaluation
+        gmb_ctx* ctx = cv->ctx;
+        for (int r = 0; r < cv->R; r++) if (!(theta[r] == theta[r])) return gmb_set_error(GMB_ENOTPD, "D(theta) is not positive definite: theta is NaN");
+        GMB_TRY(cov_ensure_gram(cv, mdl));
+        GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int r = 0; r < cv->R; r++) ctx->h_pinned[r] = theta[r];
+        GMB_CUDA(cudaMemcpyAsync(cv->d_theta, ctx->h_pinned, sizeof(double) * cv->R, cudaMemcpyHostToDevice, ctx->stream));
+        GMB_CUDA(cudaMemsetAsync(cv->d_status, 0, sizeof(int), ctx->stream));
+        const int ctas = (cv->B + FACT_WARPS - 1) / FACT_WARPS;
+        GMB_TRY(gmb_ctx_scratch(ctx, (size_t)ctas));
+        mvn_gram_kernel<<<ctas, FACT_WARPS * 32, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_gram,
+                                                                  (double)mdl->m_local, cv->d_Lblk, cv->d_logdet, cv->d_status, ctx->d_scratch,
+                                                                  ctx->d_counter, ctx->d_result);
+        ctx->launches++;
+        GMB_CUDA(cudaGetLastError());
+        cv->theta_cached.assign(theta, theta + cv->R); cv->factor_valid = true;      // Lblk / logdet now hold this theta's factor
+        GMB_TRY(gmb_comm_allreduce_dev(ctx, ctx->d_result, 1));
+        int* hstat = reinterpret_cast<int*>(ctx->h_pinned + 64);
+        GMB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        GMB_CUDA(cudaMemcpyAsync(hstat, cv->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (*hstat != 0) { cv->factor_valid = false; return gmb_set_error(GMB_ENOTPD, "D(theta) is not positive definite: pivot %d", *hstat - 1); }
+        *out = ctx->h_pinned[0] / (ncols_total > 0 ? ncols_total : mdl->m_total);   // mcmldmatrix.h:40
+        return GMB_OK;
+    }
     GMB_TRY(gmb_cov_factor(cv, theta));
     GMB_TRY(gmb_cov_quad(cv, mdl->dU, mdl->ldq, mdl->m_local, cv->ctx->d_result));
     return cov_finish_ll(cv, cv->ctx->d_result, ncols_total > 0 ? ncols_total : mdl->m_total, out);

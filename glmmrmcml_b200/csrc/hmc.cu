@@ -459,6 +459,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     if (U_out || keep_on_device) {
         // u = L v (mhmcmc.h:155) straight into the model's sample matrix
         mdl->zd_valid = false;
+        mdl->u_version++;
         GMB_TRY(gmb_model_reserve_samples(mdl, (int)ncol));
         GMB_TRY(gmb_dgemm(ctx, 0, 0, mdl->Q, (int)ncol, mdl->Q, 1.0, mdl->dL, mdl->ldq, mdl->dV, mdl->ldq, 0.0, mdl->dU, mdl->ldq));
         mdl->m_local = (int)ncol; mdl->m_total = (int)ncol * ctx->world; mdl->niter_local = mdl->m_local; mdl->niter_total = mdl->m_total;

@@ -163,6 +163,7 @@ extern "C" int gmb_model_set_u(gmb_model* mdl, const double* U, int Q, int m_loc
     GMB_TRY(set_counts(mdl, m_local, m_total, niter_total));
     GMB_TRY(gmb_model_reserve_samples(mdl, m_local > 0 ? m_local : 1));
     GMB_TRY(upload_matrix(ctx, mdl->dU, mdl->ldq, U, Q, m_local));
+    mdl->u_version++;
     GMB_TRY(gmb_model_build_zd(mdl));
     GMB_CUDA(cudaStreamSynchronize(ctx->stream));   // U is a caller buffer: do not return before it has been read
     return GMB_OK;

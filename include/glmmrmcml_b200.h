@@ -152,6 +152,10 @@ int gmb_hmc_set_cluster_size(int cs);
  * sample matrix; 0 = stream zd on every evaluation (used by the roofline probes and the parity tests of the streaming kernel). */
 int gmb_estep_set_rowstats(int on);
 
+/* mvn_ll on a model's device-resident samples when every covariance block is <= 16: 1 (default) = through the Gram matrices of the samples
+ * (built once per sample matrix, each evaluation independent of the number of samples), 0 = stream the samples on every evaluation. */
+int gmb_cov_set_gram(int on);
+
 /* On-chip sampler: 1 (default) = observations that share their row of [X | Z] (hence their linear predictor) are aggregated into one
  * weighted row (aggregate.cu; config C2: 500 rows -> 50), 0 = one row per observation.  Same sums in a different order. */
 int gmb_hmc_set_row_aggregation(int on);

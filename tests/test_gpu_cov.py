@@ -95,3 +95,32 @@ def test_not_positive_definite(gctx):
         g.Covariance(gctx, np.array([[0, 3, 5, 1, 0]], dtype=np.int32), np.zeros(3), None)   # matern: not supported
     assert e.value.code == 7
     cv.close()
+
+
+@pytest.mark.parametrize("name", ["C1", "C2", "C4"])
+def test_gram_path_equals_stream_and_oracle(name, gctx, oracle):
+    """mvn_ll on a model's device-resident samples: the Gram-matrix evaluation (default for blocks <= 16) and the streaming evaluation
+    agree with the oracle at several theta on the same samples; the Gram matrices are rebuilt when the samples change."""
+    import glmmrmcml_b200 as g
+    cfg = CASES[name]()
+    cv = g.Covariance(gctx, cfg["cov"], cfg["data"], cfg["eff_range"])
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    rng = np.random.default_rng(4)
+    for rep in range(2):
+        U = np.asfortranarray(cfg["U"] * (1.0 + 0.3 * rep) + 0.01 * rng.standard_normal(cfg["U"].shape))
+        mdl.set_u(U)
+        for scale in (1.0, 0.8, 1.15):
+            theta = cfg["theta"] * np.array([scale, min(0.95, scale * cfg["theta"][1]) / cfg["theta"][1]])[: cfg["theta"].size]
+            want = oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], theta, U)
+            got = cv.loglik_model(theta, mdl)
+            try:
+                g.cov_set_gram(False); stream = cv.loglik_model(theta, mdl)
+            finally:
+                g.cov_set_gram(True)
+            assert abs(stream - want) <= 1e-10 * abs(want)
+            assert abs(got - want) <= 1e-10 * abs(want), (got, stream, want)
+            assert abs(cv.logdet(theta) - oracle.logdet(cfg["cov"], cfg["data"], cfg["eff_range"], theta)) <= 1e-10 * max(1.0, abs(want))
+    if name != "C1":
+        with pytest.raises(g.GmbError):
+            cv.loglik_model(np.array([0.3, 1.2]), mdl)          # ar1 parameter > 1: not positive definite
+    mdl.close(); cv.close()
