@@ -8,12 +8,12 @@ python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench.
 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches_bench_${TAG}.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 echo "launch list rc=$?"
-python tools/profile_hmc.py 250 > gpurun_out/plain_hmc.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:hmc_fused -c 1 -o gpurun_out/prof_hmc_${TAG} -f \
-    python tools/profile_hmc.py 250 > gpurun_out/ncu_hmc.log 2>&1
+python tools/profile_hmc.py > gpurun_out/plain_hmc.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:hmc_fused -c 2 -o gpurun_out/prof_hmc_${TAG} -f \
+    python tools/profile_hmc.py > gpurun_out/ncu_hmc.log 2>&1
 echo "hmc full rc=$?"
 python tools/profile_kernels.py estep > gpurun_out/plain_prof.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'loglik_kernel|mcnr_pass1' -c 4 -o gpurun_out/prof_estep_${TAG} -f \
+ncu --set full --clock-control none --import-source on -k regex:'loglik|mcnr_pass1' -c 5 -o gpurun_out/prof_estep_${TAG} -f \
     python tools/profile_kernels.py estep > gpurun_out/ncu_prof.log 2>&1
 echo "estep full rc=$?"
 tail -n 2 gpurun_out/plain_hmc.log gpurun_out/plain_prof.log
