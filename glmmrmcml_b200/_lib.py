@@ -26,7 +26,7 @@ class GmbError(RuntimeError):
 class HmcStats(C.Structure):
     _fields_ = [("accept_rate", C.c_double), ("step_size_mean", C.c_double), ("steps_mean", C.c_double),
                 ("leapfrog_total", C.c_double), ("kernel_ms", C.c_double), ("n_chains", C.c_int),
-                ("nsamp_per_chain", C.c_int), ("rows_used", C.c_int), ("kernel_variant", C.c_int)]
+                ("nsamp_per_chain", C.c_int), ("rows_used", C.c_int), ("kernel_variant", C.c_int), ("zl_nonzeros", C.c_double)]
 
 
 GMB_OK, GMB_EINVAL, GMB_EFAMILY, GMB_ECUDA, GMB_ENOTPD, GMB_ENCCL, GMB_ESTATE, GMB_ECOV = range(8)

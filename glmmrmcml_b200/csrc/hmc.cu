@@ -287,6 +287,8 @@ int gmb_hmc_prepare(gmb_model* mdl, const double* L_host) {
     GMB_TRY(gmb_dgemm(ctx, 0, 0, mdl->n, mdl->Q, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dL, mdl->ldq, 0.0, mdl->dZL, mdl->ldn));
     if (L_host) GMB_CUDA(cudaStreamSynchronize(ctx->stream));
     mdl->zl_valid = true;
+    mdl->agg.zl_valid = false;
+    mdl->ell.checked = mdl->ell.valid = false;
     return GMB_OK;
 }
 
@@ -346,25 +348,33 @@ size_t gmb_hmc_fused_scratch_doubles(const gmb_model* mdl, int C);
 int gmb_hmc_run_fused(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                       int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs);
 
-// 0 = choose (on-chip variant when the model fits one SM's shared memory), 1 = force the two-GEMM variant, 2 = force on-chip
+// hmc_sparse.cu
+bool gmb_hmc_sparse_applicable(const gmb_model* mdl);
+size_t gmb_hmc_sparse_work_doubles(const gmb_model* mdl, int C);
+int gmb_hmc_run_sparse(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
+                       int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs);
+
+// 0 = choose (structure-aware kernels when Z L is sparse enough, else the on-chip variant when the model fits one SM's shared memory,
+// else two GEMMs per step), 1 = force the two-GEMM variant, 2 = force on-chip, 3 = force structure-aware
 static int g_hmc_variant = 0;
 extern "C" int gmb_hmc_set_variant(int variant) {
-    if (variant < 0 || variant > 2) return gmb_set_error(GMB_EINVAL, "variant must be 0 (auto), 1 (two-GEMM) or 2 (on-chip)");
+    if (variant < 0 || variant > 3) return gmb_set_error(GMB_EINVAL, "variant must be 0 (auto), 1 (two-GEMM), 2 (on-chip) or 3 (structure-aware)");
     g_hmc_variant = variant;
     return GMB_OK;
 }
 
-static int hmc_run_fused_timed(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
+static int hmc_run_fused_timed(gmb_model* mdl, bool sparse, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                                int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, std::vector<double>* host_cs, float* ms) {
     gmb_ctx* ctx = mdl->ctx;
-    const size_t need = gmb_hmc_fused_cs_doubles(C) + gmb_hmc_fused_scratch_doubles(mdl, C);
+    const size_t need = sparse ? gmb_hmc_sparse_work_doubles(mdl, C) : gmb_hmc_fused_cs_doubles(C) + gmb_hmc_fused_scratch_doubles(mdl, C);
     if (need > mdl->hmc_work_doubles) {
         if (mdl->hmc_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, mdl->hmc_work); mdl->hmc_work = nullptr; mdl->hmc_work_doubles = 0; }
         GMB_CUDA(gmb_dmalloc(ctx, &mdl->hmc_work, need * sizeof(double)));
         mdl->hmc_work_doubles = need;
     }
     GMB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    GMB_TRY(gmb_hmc_run_fused(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
+    if (sparse) GMB_TRY(gmb_hmc_run_sparse(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
+    else GMB_TRY(gmb_hmc_run_fused(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
     GMB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     if (host_cs) {
         host_cs->resize((size_t)CS_COUNT * C);
@@ -416,8 +426,10 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     gmb_ctx* ctx = mdl->ctx;
     GMB_CUDA(cudaSetDevice(ctx->device));
     if (g_hmc_variant != 1) GMB_TRY(gmb_agg_ensure(mdl));       // row view of the on-chip sampler (not used by the two-GEMM variant)
-    if (L) { GMB_TRY(gmb_hmc_prepare(mdl, L)); mdl->agg.zl_valid = false; }
+    if (L) GMB_TRY(gmb_hmc_prepare(mdl, L));
     GMB_TRY(agg_update_zl(mdl));
+    const bool try_sparse = g_hmc_variant == 0 || g_hmc_variant == 3;
+    if (try_sparse) GMB_TRY(gmb_ell_ensure(mdl));
     GMB_TRY(set_xb(mdl, beta));
     const int C = n_chains, cols = nsamp_per_chain + 1;
     const size_t ncol = (size_t)C * cols;
@@ -430,10 +442,13 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     }
     std::vector<double> hcs;
     float ms = 0.f;
-    const bool fits = gmb_hmc_fused_applicable(mdl, C);
+    const bool sparse = try_sparse && gmb_hmc_sparse_applicable(mdl);
+    if (g_hmc_variant == 3 && !sparse)
+        return gmb_set_error(GMB_EINVAL, "the structure-aware sampler variant was forced but does not fit: Z L (%d x %d) is not sparse enough", mdl->agg.ng, mdl->Q);
+    const bool fits = !sparse && g_hmc_variant != 3 && gmb_hmc_fused_applicable(mdl, C);
     if (g_hmc_variant == 2 && !fits) return gmb_set_error(GMB_EINVAL, "the on-chip sampler variant was forced but Z L (%d x %d) does not fit in shared memory", mdl->n, mdl->Q);
-    if (fits && g_hmc_variant != 1)
-        GMB_TRY(hmc_run_fused_timed(mdl, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
+    if (sparse || (fits && g_hmc_variant != 1))
+        GMB_TRY(hmc_run_fused_timed(mdl, sparse, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
                                     mdl->dV, stats ? &hcs : nullptr, &ms));
     else
         GMB_TRY(hmc_run(mdl, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
@@ -450,8 +465,9 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
         stats->n_chains = C;
         stats->nsamp_per_chain = nsamp_per_chain;
         const bool fused = fits && g_hmc_variant != 1;
-        stats->kernel_variant = fused ? 2 : 1;
-        stats->rows_used = (fused && mdl->agg.built) ? mdl->agg.ng : mdl->n;
+        stats->kernel_variant = sparse ? 3 : (fused ? 2 : 1);
+        stats->rows_used = ((sparse || fused) && mdl->agg.built) ? mdl->agg.ng : mdl->n;
+        stats->zl_nonzeros = sparse ? (double)mdl->ell.nnz : (double)stats->rows_used * mdl->Q;
     }
     if (V_out)
         GMB_CUDA(cudaMemcpy2DAsync(V_out, mdl->Q * sizeof(double), mdl->dV, mdl->ldq * sizeof(double), mdl->Q * sizeof(double), ncol,

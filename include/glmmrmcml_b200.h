@@ -122,7 +122,8 @@ typedef struct gmb_hmc_stats {
     int    n_chains;
     int    nsamp_per_chain;
     int    rows_used;        /* rows the sampler ran on: n, or the number of distinct rows of [X | Z] when aggregated */
-    int    kernel_variant;   /* 1 = two-GEMM, 2 = on-chip */
+    int    kernel_variant;   /* 1 = two-GEMM, 2 = on-chip, 3 = structure-aware (sparse Z L) */
+    double zl_nonzeros;      /* entries of Z L the kernel works on per leapfrog step and chain: non-zeros (variant 3) or rows_used * Q */
 } gmb_hmc_stats;
 
 /* Runs n_chains independent copies of mcmcRunHMC::sample(warmup, .) (mhmcmc.h:121-157), each with its own
@@ -137,9 +138,10 @@ int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* beta, double v
                    int n_chains, uint32_t chain_offset, uint64_t seed, int keep_on_device,
                    double* U_out, double* V_out, gmb_hmc_stats* stats);
 
-/* Sampler kernel selection: 0 = automatic (the on-chip kernel, Z L resident in shared memory, when the model fits one
- * SM; otherwise two fused-epilogue GEMMs per leapfrog step), 1 = force the two-GEMM variant, 2 = force the on-chip one.
- * Both variants follow the same chain arithmetic and the same random streams. */
+/* Sampler kernel selection: 0 = automatic (the structure-aware kernels when Z L is sparse enough — indicator Z, block-diagonal D;
+ * else the on-chip kernel, Z L resident in shared memory, when the model fits one SM; otherwise two fused-epilogue GEMMs per
+ * leapfrog step), 1 = force the two-GEMM variant, 2 = force the on-chip one, 3 = force the structure-aware one.
+ * All variants follow the same chain arithmetic and the same random streams. */
 int gmb_hmc_set_variant(int variant);
 
 /* On-chip sampler: CTAs per group of 8 chains.  0 = automatic (per run: the cluster size with the shortest estimated

@@ -42,8 +42,8 @@ def test_log_prob_and_grad(case, oracle):
         assert np.max(np.abs(G[:, c] - gw)) <= 1e-10 * max(np.max(np.abs(gw)), 1.0)
 
 
-@pytest.mark.parametrize("variant,cluster", [(1, 0), (2, 1), (2, 2), (2, 4), (0, 0)],
-                         ids=["two-gemm", "on-chip", "on-chip-cluster2", "on-chip-cluster4", "auto"])
+@pytest.mark.parametrize("variant,cluster", [(1, 0), (2, 1), (2, 2), (2, 4), (3, 0), (0, 0)],
+                         ids=["two-gemm", "on-chip", "on-chip-cluster2", "on-chip-cluster4", "structure-aware", "auto"])
 def test_chain_follows_oracle(case, oracle, variant, cluster):
     """Same seed, same counter-based RNG: the device chains must reproduce the oracle chains' states (to the accuracy
     the leapfrog map preserves), acceptance rate, step size and step count — for both sampler kernels and for every
@@ -55,8 +55,8 @@ def test_chain_follows_oracle(case, oracle, variant, cluster):
     try:
         _chain_follows_oracle(cfg, mdl, oracle)
     except g.GmbError as e:
-        if variant == 2 and "does not fit" in str(e):
-            pytest.skip("model too large for the on-chip variant at this cluster size")
+        if variant in (2, 3) and "does not fit" in str(e):
+            pytest.skip("model too large for the on-chip variant at this cluster size / Z L not sparse enough")
         raise
     finally:
         g.hmc_set_variant(0)
@@ -140,7 +140,8 @@ def test_row_aggregation_is_exact_and_active(gctx, oracle):
     finally:
         g.hmc_set_row_aggregation(True)
     assert outs[True]["stats"]["rows_used"] == 50 and outs[False]["stats"]["rows_used"] == 500
-    assert outs[True]["stats"]["kernel_variant"] == 2
+    assert outs[True]["stats"]["kernel_variant"] == 3 and outs[False]["stats"]["kernel_variant"] == 3   # C2's Z L is sparse: 150 non-zeros
+    assert outs[True]["stats"]["zl_nonzeros"] == 150 and outs[False]["stats"]["zl_nonzeros"] == 1500
     assert np.max(np.abs(outs[True]["v"] - outs[False]["v"])) <= 1e-8
     assert outs[True]["stats"]["accept_rate"] == outs[False]["stats"]["accept_rate"]
     for c in (0, 7):
@@ -162,4 +163,80 @@ def test_row_aggregation_is_exact_and_active(gctx, oracle):
     mdl = g.Model(gctx, c3["X"], c3["Z"], c3["y"], "gaussian", "identity")
     out = mdl.hmc_sample(c3["L"], c3["beta"], 1.0, warmup=5, nsamp_per_chain=2, lam=0.5, max_steps=10, n_chains=2, seed=1, want_u=False, want_v=True)
     assert out["stats"]["rows_used"] == 40
+    mdl.close()
+
+
+SPARSE_CASES = {
+    # name: (config, kernel the dispatcher must pick — hmc_sparse.cu sparse_plan)
+    "C1-warp-regs": (lambda: synth.config1(m=4), "binomial"),
+    "C2-warp-regs": (lambda: synth.config2(m=4), "binomial"),
+    "wide-blocks-warp-smem-ell": (lambda: synth.config4(ncl=5, nt=12, k=2, m=4), "poisson"),       # 12 x 12 blocks: ELL width 12 > 8
+    "ragged-warp-4-per-lane": (lambda: synth.config4(ncl=13, nt=7, k=3, m=4), "poisson"),          # Q = 91
+    "C4-cta128": (lambda: synth.config4(ncl=30, nt=10, k=2, m=4), "poisson"),                      # Q = 300
+    "C4-cta512": (lambda: synth.config4(ncl=110, nt=10, k=1, m=4), "poisson"),                     # Q = 1100
+}
+
+
+@pytest.mark.parametrize("name", list(SPARSE_CASES))
+def test_structure_aware_sampler_follows_oracle(gctx, oracle, name):
+    """The structure-aware kernels (sparse Z L in ELL form, hmc_sparse.cu) in every size class: the dispatcher picks them without being
+    asked, they work on the non-zeros only, and the chains reproduce the oracle's dense chains under the same Philox stream."""
+    import glmmrmcml_b200 as g
+    cfg = SPARSE_CASES[name][0]()
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    ZL = cfg["Z"] @ cfg["L"]; xb = cfg["X"] @ cfg["beta"]
+    warm, ns, lam, ms, ta, seed, nch = 14, 5, 0.03, 30, 0.85, 777, 9
+    out = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=warm, nsamp_per_chain=ns, lam=lam, max_steps=ms, target_accept=ta,
+                         n_chains=nch, chain_offset=2, seed=seed, want_u=True, want_v=True)
+    st = out["stats"]
+    assert st["kernel_variant"] == 3
+    rows = np.unique(np.hstack([cfg["X"], cfg["Z"]]), axis=0).shape[0]
+    assert st["rows_used"] == min(rows, cfg["n"]) or st["rows_used"] == cfg["n"]
+    ZLv = ZL if st["rows_used"] == cfg["n"] else np.unique(np.hstack([cfg["X"], ZL]), axis=0)[:, cfg["X"].shape[1]:]
+    assert st["zl_nonzeros"] == np.count_nonzero(ZLv)
+    acc = []
+    for c in (0, 4, 8):
+        ref = oracle.hmc_chain(ZL, cfg["L"], xb, cfg["y"], 1.0, fl, warm, ns, lam, ms, ta, seed, chain=2 + c)
+        vg = out["v"][:, c * (ns + 1):(c + 1) * (ns + 1)]
+        ug = out["u"][:, c * (ns + 1):(c + 1) * (ns + 1)]
+        assert np.max(np.abs(vg - ref["v"])) <= 1e-7 * max(1.0, np.max(np.abs(ref["v"])))
+        assert np.max(np.abs(ug - ref["u"])) <= 1e-7 * max(1.0, np.max(np.abs(ref["u"])))
+    # the dense on-chip kernel / two-GEMM kernels on the same model give the same chains
+    g.hmc_set_variant(1)
+    try:
+        dense = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, warmup=warm, nsamp_per_chain=ns, lam=lam, max_steps=ms, target_accept=ta,
+                               n_chains=nch, chain_offset=2, seed=seed, want_u=False, want_v=True)
+    finally:
+        g.hmc_set_variant(0)
+    assert dense["stats"]["kernel_variant"] == 1
+    assert np.max(np.abs(dense["v"] - out["v"])) <= 1e-7 * max(1.0, np.max(np.abs(out["v"])))
+    assert dense["stats"]["accept_rate"] == st["accept_rate"]
+    mdl.close()
+
+
+def test_structure_aware_sampler_gaussian_and_dense_fallback(gctx, oracle):
+    """Gaussian-identity through the structure-aware kernel (aggregated rows: within-row sum of squares), and a dense Z L (C3: Z = I,
+    one dense block) stays on the dense kernels; forcing the structure-aware variant there is an error."""
+    import glmmrmcml_b200 as g
+    cfg = synth.config4(ncl=12, nt=6, k=3, m=4)
+    rng = np.random.default_rng(8)
+    yg = cfg["X"] @ cfg["beta"] + cfg["Z"] @ cfg["U"][:, 0] + 0.4 * rng.standard_normal(cfg["n"])
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], yg, "gaussian", "identity")
+    out = mdl.hmc_sample(cfg["L"], cfg["beta"], 0.6, warmup=10, nsamp_per_chain=4, lam=0.4, max_steps=20, target_accept=0.8, n_chains=5, seed=3,
+                         want_u=False, want_v=True)
+    assert out["stats"]["kernel_variant"] == 3 and out["stats"]["rows_used"] == 72
+    ref = oracle.hmc_chain(cfg["Z"] @ cfg["L"], cfg["L"], cfg["X"] @ cfg["beta"], yg, 0.6, 7, 10, 4, 0.4, 20, 0.8, 3, chain=4)
+    assert np.max(np.abs(out["v"][:, 20:25] - ref["v"])) <= 1e-7
+    mdl.close()
+    c3 = synth.config3(nloc=40, m=4)
+    mdl = g.Model(gctx, c3["X"], c3["Z"], c3["y"], "gaussian", "identity")
+    out = mdl.hmc_sample(c3["L"], c3["beta"], 1.0, warmup=5, nsamp_per_chain=2, lam=0.5, max_steps=10, n_chains=2, seed=1, want_u=False, want_v=True)
+    assert out["stats"]["kernel_variant"] == 2
+    g.hmc_set_variant(3)
+    try:
+        with pytest.raises(g.GmbError, match="not sparse enough"):
+            mdl.hmc_sample(c3["L"], c3["beta"], 1.0, warmup=5, nsamp_per_chain=2, lam=0.5, max_steps=10, n_chains=2, seed=1, want_u=False, want_v=True)
+    finally:
+        g.hmc_set_variant(0)
     mdl.close()
