@@ -33,15 +33,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 M_PER_GPU = 10_000
-N_CHAINS = 1000           # per GPU; 10 columns each (9 post-warm-up draws + the state after warm-up): 125 groups of 8 chains, one CTA
-                          # each (the sampler aggregates the 500 observations into their 50 distinct rows of [X | Z] and picks the
-                          # cluster size per run: aggregate.cu, hmc_fused.cu)
+N_CHAINS = 1000           # per GPU; 10 columns each (9 post-warm-up draws + the state after warm-up).  The sampler aggregates the 500
+                          # observations into their 50 distinct rows of [X | Z] (aggregate.cu) and, Z L being sparse (150 non-zeros),
+                          # runs the structure-aware kernel, one warp per chain (hmc_sparse.cu)
 HMC = dict(warmup=500, lam=5.0, max_steps=100, target_accept=0.95, adapt=100)
 N_D_EVALS = 64            # mvn_ll evaluations of one d_optim (BOBYQA over 2 parameters takes 40-80)
 N_HESS = 256              # 4 k^2, k = P + R = 8
+D_BATCH = 5               # 2 R + 1: the central-difference stencil the optimiser evaluates as one batch (optim.cpp)
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: profiles/r01_microbench_fp64.txt (tools/microbench_fp64.cu)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` captures (profiles/r01_ncu_raw_extract_final.txt):
-SAMPLER_DRAM_BYTES_PER_LAUNCH = 446976.0            # hmc_fused_kernel<3,13,4>: Z L, xb, y are read once, the chain runs out of shared memory
+SAMPLER_DRAM_BYTES_PER_LAUNCH = {2: 446976.0,       # hmc_fused_kernel<3,13,4>: Z L, xb, y are read once, the chain runs out of shared memory
+                                 3: None}            # hmc_sparse_kernel<3,32,2,6>: filled in from the ncu capture of this round
+# FP64 operations per leapfrog step and chain that the structure-aware kernel executes (FMA = 2): 4 per non-zero of Z L (eta and gradient),
+# per row the residual (table exp 18 + Newton reciprocal 9 + 2 for binomial-logit; 20 poisson; 2 gaussian), per column 8 (gradient, leapfrog)
+SPARSE_ROW_FLOPS = {"binomial": 29.0, "poisson": 20.0, "gaussian": 2.0}
 LOGLIK_DRAM_BYTES_PER_LAUNCH = 1.000278e9 + 3.865e6  # loglik_kernel<3> on 1 GB of zd (algorithmic bytes: 1.000008e9)
 
 
@@ -51,6 +56,36 @@ def load_peaks():
             return json.load(f), "measured"
     except Exception:
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def sampler_roofline(st, exec_tflops, algo_tflops, exec_per_step, cfg, Q, dense_probe):
+    """roofline object of the sampler launch of the timed step (the step's dominant kernel)."""
+    kv = st["kernel_variant"]
+    common = {"achieved": exec_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": exec_tflops / FP64_DMMA_PEAK_TFLOPS,
+              "algorithmic_tflops": algo_tflops, "frac_algorithmic": algo_tflops / FP64_DMMA_PEAK_TFLOPS,
+              "traffic": SAMPLER_DRAM_BYTES_PER_LAUNCH.get(kv), "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q,
+              "executed_flops_per_leapfrog_per_chain": exec_per_step, "rows_used": st["rows_used"], "zl_nonzeros": st["zl_nonzeros"],
+              "peak_source": "FP64 pipe peak measured on this pool's B200 (profiles/r01_microbench_fp64.txt: DMMA 37.1, DFMA 36.8 TFLOP/s, the same "
+                             "pipe); MEASURED_PEAKS.json has no fp64 entry (the bf16 tensor peak does not apply to an fp64 kernel)"}
+    if kv == 3:
+        common.update({
+            "kernel": "hmc_sparse_kernel<%s> (structure-aware sampler: Z L in ELL form, one warp per chain, state and ELL entries in registers)" % cfg["family"],
+            "bound": "fp64",
+            "note": "achieved = FP64 flops the kernel EXECUTES per leapfrog step and chain (4 per non-zero of Z L + residual per distinct row + "
+                    "leapfrog update per column; FMA = 2) / kernel time, against the FP64 pipe peak.  SURVEY 8d's algorithmic figure for the dense "
+                    "contraction (4 n Q = 1e5 per step and chain) is `algorithmic_tflops`: the kernel does the same arithmetic on the 150 non-zeros "
+                    "of the 50 distinct rows instead of 500 x 50 entries, so that figure exceeds the pipe peak.  With 1000 chains (1.7 warps per "
+                    "scheduler) a leapfrog step is bound by its dependent chain (shared-memory exchange + exp + reciprocal, ~750 cycles), not by "
+                    "pipe throughput; `dense_kernel` is the DMMA kernel a model with a dense Z L runs",
+            "dense_kernel": dense_probe})
+    else:
+        common.update({
+            "kernel": "hmc_fused_kernel<%s> (on-chip sampler: eta = ZL v and grad = ZL^T r(eta) as FP64 DMMA)" % cfg["family"] if kv == 2
+                      else "dgemm_kernel<EpiResid/EpiLeapfrog> (two fused-epilogue DMMA GEMMs per leapfrog step)",
+            "bound": "tensor",
+            "note": "achieved = tensor flops the kernel executes (4 rows_used Q per leapfrog step and chain) / kernel time",
+            "saturated": dense_probe})
+    return common
 
 
 def stencil_points(rng, P, R, beta, theta, npts, h=1e-5):
@@ -369,10 +404,10 @@ def main():
         first["done"] = True
         mdl.use_device_u()                                   # 2. zd = Z u
         nr = mdl.mcnr(beta, 1.0)                             # 3.
-        for k in range(N_D_EVALS):                           # 4.
-            cv.loglik_model(Td[:, k], mdl)
-        ll = mdl.log_likelihood_batch(Bst, np.ones(N_HESS))  # 5.
-        dl = [cv.loglik_model(Tst[:, k], mdl) for k in range(N_HESS)]
+        for k in range(0, N_D_EVALS, D_BATCH):               # 4. theta update: batches of 2R + 1 stencil points, as the optimiser issues them
+            cv.loglik_model_batch(Td[:, k:k + D_BATCH], mdl)
+        ll = mdl.log_likelihood_batch(Bst, np.ones(N_HESS))  # 5. Hessian stencil: one batch each
+        dl = cv.loglik_model_batch(Tst, mdl)
         return nr, ll, dl
 
     for i in range(args.warmup):
@@ -449,7 +484,11 @@ def main():
                     "leapfrog_per_s": sum_over_ranks(st["leapfrog_total"] / (hmc_ms * 1e-3))}
     hmc_flops = st["leapfrog_total"] * 4.0 * cfg["n"] * Q                     # 4 n Q per leapfrog step per chain
     hmc_tflops = hmc_flops / (hmc_ms * 1e-3) / 1e12
-    hmc_exec_tflops = st["leapfrog_total"] * 4.0 * st["rows_used"] * Q / (hmc_ms * 1e-3) / 1e12   # on the rows the kernel ran on
+    if st["kernel_variant"] == 3:
+        exec_per_step = 4.0 * st["zl_nonzeros"] + SPARSE_ROW_FLOPS[cfg["family"]] * st["rows_used"] + 8.0 * Q
+    else:
+        exec_per_step = 4.0 * st["rows_used"] * Q                             # dense contraction on the rows the kernel ran on
+    hmc_exec_tflops = st["leapfrog_total"] * exec_per_step / (hmc_ms * 1e-3) / 1e12
     mdl.use_device_u()
     # E-step evaluations/s on the step's own zd (40 MB, L2-resident between evaluations) and cold (L2 flushed before each)
     ctx.timer_start(); mdl.log_likelihood_batch(Bst, np.ones(N_HESS)); t_b = ctx.timer_stop()
@@ -461,6 +500,8 @@ def main():
                       "m": M_PER_GPU * world, "note": "m=10^4 x n=500: 40 MB, below launch latency; see roofline_estep for the streaming rate"}
     ctx.timer_start(); [cv.loglik_model(Tst[:, k], mdl) for k in range(64)]; t_d = ctx.timer_stop()
     extra["mvn_ll_evals_per_s"] = 64 / (t_d * 1e-3)
+    ctx.timer_start(); cv.loglik_model_batch(Tst, mdl); t_db = ctx.timer_stop()
+    extra["mvn_ll_evals_per_s_batched"] = N_HESS / (t_db * 1e-3)
     ctx.timer_start(); [mdl.mcnr(beta, 1.0) for _ in range(16)]; t_n = ctx.timer_stop()
     extra["mcnr_steps_per_s"] = 16 / (t_n * 1e-3)
 
@@ -495,6 +536,7 @@ def main():
         # the sampler kernel as a dense tensor kernel: row aggregation off, every SM busy on 8 tiles per warp (1184 chains = 148 groups,
         # one CTA each) — what the DMMA path reaches on a model without repeated rows
         g.hmc_set_row_aggregation(False)
+        g.hmc_set_variant(2)
         mdl3 = g.Model(ctx1, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
         for rep in range(2):
             r3 = mdl3.hmc_sample(L, beta, 1.0, warmup=100, nsamp_per_chain=4, lam=HMC["lam"], max_steps=HMC["max_steps"],
@@ -503,9 +545,12 @@ def main():
         s3 = r3["stats"]
         sat_tflops = s3["leapfrog_total"] * 4.0 * cfg["n"] * Q / (s3["kernel_ms"] * 1e-3) / 1e12
         roofline_sat = {"chains": 1184, "ms": s3["kernel_ms"], "achieved": sat_tflops, "frac": sat_tflops / FP64_DMMA_PEAK_TFLOPS,
-                        "note": "same kernel without row aggregation, 1184 chains (148 CTAs x 8 chains, no cluster split), 104 proposals: the dense "
-                                "DMMA path on all 500 rows, not the timed step"}
+                        "kernel": "hmc_fused_kernel<binomial-logit, KS=13> (dense on-chip sampler: eta = ZL v and grad = ZL^T r(eta) as FP64 DMMA)",
+                        "note": "the DENSE on-chip kernel (forced; the dispatcher picks the structure-aware one for this model) without row aggregation, "
+                                "1184 chains (148 CTAs x 8 chains, no cluster split), 104 proposals: the DMMA path on all 500 rows, 4 n Q flop per leapfrog "
+                                "step and chain against the measured DMMA peak — what a model with a dense Z L gets; not the timed step"}
         mdl3.close()
+        g.hmc_set_variant(0)
         g.hmc_set_row_aggregation(True)
 
     if rank != 0:
@@ -523,19 +568,7 @@ def main():
                     "calls": "gmb_mcmc_sample + gmb_mcml_optim(mcnr) + gmb_mcml_hess with host buffers", "s_per_step": e2e_s,
                     "parts_s": {k: float(np.mean(v)) for k, v in e2e_parts.items()}},
             "gpu_launches": int(launches), "clocks": clk, "wall_s": wall,
-            "roofline": {"kernel": "hmc_fused_kernel<binomial-logit, KS=13> (on-chip sampler: eta = ZL v and grad = ZL^T r(eta) as FP64 DMMA)",
-                         "bound": "tensor",
-                         "achieved": hmc_exec_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": hmc_exec_tflops / FP64_DMMA_PEAK_TFLOPS,
-                         "algorithmic_tflops": hmc_tflops,
-                         "traffic": SAMPLER_DRAM_BYTES_PER_LAUNCH, "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q,
-                         "rows_used": st["rows_used"], "executed_tflops": hmc_exec_tflops,
-                         "note": "achieved = tensor flops the kernel EXECUTES (4 rows_used Q per leapfrog step and chain) / kernel time: it aggregates the "
-                                 "500 observations into rows_used distinct rows of [X | Z], a tenth of SURVEY 8d's algorithmic 4 n Q (algorithmic_tflops "
-                                 "counts those); at that size a leapfrog step is bound by its reduction/update latency, not by the DMMA pipe — "
-                                 "`saturated` is the same kernel as a dense tensor kernel",
-                         "saturated": roofline_sat,
-                         "peak_source": "FP64 DMMA peak measured on this pool's B200 (profiles/r01_microbench_fp64.txt); "
-                                        "MEASURED_PEAKS.json has no fp64 entry (bf16 tensor peak does not apply to an fp64 kernel)"},
+            "roofline": sampler_roofline(st, hmc_exec_tflops, hmc_tflops, exec_per_step, cfg, Q, roofline_sat),
             "roofline_estep": roofline_estep, "cpu_baseline": cpu}
     line.update(extra)
     emit(line)

@@ -269,6 +269,14 @@ class Covariance:
         check(lib().gmb_cov_mvn_ll_model(self._h, _d(theta), model._h, int(ncols_total), C.byref(out)))
         return out.value
 
+    def loglik_model_batch(self, thetas, model: Model, ncols_total=0) -> np.ndarray:
+        """mvn_ll at the columns of thetas (R x k) on the model's samples: one launch, one synchronisation (-inf where D is not PD)."""
+        thetas = _f(np.asarray(thetas, dtype=np.float64).reshape(self.R, -1))
+        k = thetas.shape[1]
+        out = np.zeros(k)
+        check(lib().gmb_cov_mvn_ll_model_batch(self._h, _d(thetas), k, model._h, int(ncols_total), _d(out)))
+        return out
+
     def logdet(self, theta) -> float:
         theta = _v(theta)
         out = C.c_double()

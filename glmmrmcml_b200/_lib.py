@@ -64,6 +64,7 @@ PROTOTYPES = {
     "gmb_cov_gen": (C.c_int, [vp, dp, C.c_int, dp]),
     "gmb_cov_mvn_ll": (C.c_int, [vp, dp, dp, C.c_int, C.c_int, C.c_int, dp]),
     "gmb_cov_mvn_ll_model": (C.c_int, [vp, dp, vp, C.c_int, dp]),
+    "gmb_cov_mvn_ll_model_batch": (C.c_int, [vp, dp, C.c_int, vp, C.c_int, dp]),
     "gmb_cov_logdet": (C.c_int, [vp, dp, dp]),
     "gmb_hmc_sample": (C.c_int, [vp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                  C.c_int, C.c_uint32, C.c_uint64, C.c_int, dp, dp, C.POINTER(HmcStats)]),

@@ -96,6 +96,34 @@ struct Fit {
         return rc;
     }
 
+    // the same for k parameter columns (theta at X + c * stride + offset): points not seen before go to the device as one batch
+    int eval_d_batch(const double* X, int stride, int offset, int k, double* out) {
+        std::vector<int> todo;
+        std::vector<double> T;
+        std::vector<std::vector<double>> keys(k);
+        for (int c = 0; c < k; c++) {
+            const double* th = X + (size_t)c * stride + offset;
+            keys[c].assign(th, th + R);
+            auto itf = memo_d.find(keys[c]);
+            if (itf != memo_d.end()) { out[c] = itf->second; continue; }
+            bool nan_par = false;
+            for (int r = 0; r < R; r++) nan_par |= !(th[r] == th[r]);
+            if (nan_par) { out[c] = -kInf; continue; }
+            bool dup = false;
+            for (int t : todo) if (keys[t] == keys[c]) { dup = true; break; }
+            if (!dup) { todo.push_back(c); T.insert(T.end(), th, th + R); }
+            out[c] = std::numeric_limits<double>::quiet_NaN();
+        }
+        if (!todo.empty()) {
+            std::vector<double> res(todo.size());
+            GMB_TRY(gmb_cov_mvn_ll_model_batch(D, T.data(), (int)todo.size(), M, d_cols_total, res.data()));
+            for (size_t t = 0; t < todo.size(); t++) memo_d[keys[todo[t]]] = res[t];
+            nfev_d += (int)todo.size();
+        }
+        for (int c = 0; c < k; c++) if (out[c] != out[c]) { auto itf = memo_d.find(keys[c]); if (itf != memo_d.end()) out[c] = itf->second; }
+        return GMB_OK;
+    }
+
     // ---- objectives (likelihood.h) ----
     static int L_obj(const double* X, int n, int k, double* f, void* user) {      // L_likelihood, likelihood.h:57-64
         Fit* self = static_cast<Fit*>(user);
@@ -105,7 +133,8 @@ struct Fit {
     }
     static int D_obj(const double* X, int n, int k, double* f, void* user) {      // D_likelihood, likelihood.h:40-45
         Fit* self = static_cast<Fit*>(user);
-        for (int c = 0; c < k; c++) { double v; GMB_TRY(self->eval_d(X + (size_t)c * n, &v)); f[c] = -1 * v; }
+        GMB_TRY(self->eval_d_batch(X, n, 0, k, f));
+        for (int c = 0; c < k; c++) f[c] = -1 * f[c];
         return GMB_OK;
     }
     struct FArgs { Fit* self; bool importance; double fix_var_par; double denomD; };
@@ -114,9 +143,10 @@ struct Fit {
         Fit* self = a->self;
         std::vector<double> ll(k);
         GMB_TRY(self->eval_ll(X, n, k, false, a->fix_var_par, ll.data()));
+        std::vector<double> dl(k);
+        GMB_TRY(self->eval_d_batch(X, n, self->P, k, dl.data()));
         for (int c = 0; c < k; c++) {
-            double logl;
-            GMB_TRY(self->eval_d(X + (size_t)c * n + self->P, &logl));
+            const double logl = dl[c];
             // importance: -log(exp(ll + logl) / exp(denomD)) evaluated in log space (the reference form underflows)
             f[c] = a->importance ? -1.0 * (ll[c] + logl - a->denomD) : -1.0 * (ll[c] + logl);
         }

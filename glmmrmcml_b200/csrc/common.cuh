@@ -159,6 +159,7 @@ struct gmb_cov {
     double* d_linv = nullptr; size_t linv_doubles = 0;
     std::vector<long long> linv_off;     // per block: offset into d_linv (-1 for blocks that take the small / medium path)
     // Gram matrices of a model's samples (cov.cu: cov_ensure_gram), laid out like d_Lblk
+    double* d_batch = nullptr; size_t batch_bytes = 0;     // work area of gmb_cov_mvn_ll_model_batch
     double* d_gram = nullptr; const gmb_model* gram_model = nullptr; unsigned long long gram_version = 0; int gram_cols = 0;
 };
 

@@ -9,6 +9,7 @@
 // factorised once per theta; the per-sample work is only the forward substitution, which for small blocks is an
 // HBM stream of u (8 Q m bytes) and for large blocks a blocked TRSM on the DMMA GEMM.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -226,12 +227,15 @@ __global__ void gram_reduce_kernel(long long gram_doubles, int nchunks, const do
     gram[e] = s;
 }
 
+// blockIdx.y = evaluation e of a batch: theta, status, partials, counter and out are indexed by e (R parameters per evaluation); Lblk /
+// logdet (the factor cache of a single evaluation) may be NULL.
 __global__ void __launch_bounds__(FACT_WARPS * 32) mvn_gram_kernel(int B, const CovBlock* __restrict__ blocks, const CovFn* __restrict__ fns,
-                                                                    const double* __restrict__ data, const double* __restrict__ theta,
+                                                                    const double* __restrict__ data, const double* __restrict__ theta, int R,
                                                                     const double* __restrict__ gram, double ncols, double* __restrict__ Lblk,
                                                                     double* __restrict__ logdet, int* __restrict__ status,
                                                                     double* __restrict__ partials, unsigned int* __restrict__ counter,
                                                                     double* __restrict__ out) {
+    theta += (size_t)blockIdx.y * R; status += blockIdx.y; partials += (size_t)blockIdx.y * gridDim.x; counter += blockIdx.y; out += blockIdx.y;
     __shared__ double sL[FACT_WARPS][QUAD_SMALL_MAX][QUAD_SMALL_MAX + 1];
     __shared__ double sS[FACT_WARPS][QUAD_SMALL_MAX][QUAD_SMALL_MAX + 1];
     __shared__ double red[32];
@@ -261,12 +265,12 @@ __global__ void __launch_bounds__(FACT_WARPS * 32) mvn_gram_kernel(int B, const 
         }
         if (bad) {
             contrib = nan("");
-            if (lane == 0) logdet[bi] = nan("");
+            if (lane == 0 && logdet) logdet[bi] = nan("");
         } else {
             double ld = (lane < n) ? 2.0 * log(L[lane][lane]) : 0.0;
             ld = warp_sum(ld);
-            if (lane == 0) logdet[bi] = ld;
-            for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; Lblk[b.l0 + e] = (j <= i) ? L[i][j] : 0.0; }
+            if (lane == 0 && logdet) logdet[bi] = ld;
+            if (Lblk) for (int e = lane; e < n * n; e += 32) { const int i = e % n, j = e / n; Lblk[b.l0 + e] = (j <= i) ? L[i][j] : 0.0; }
             // lane k: x = row k of L^-1 (solve L' x = e_k by back substitution), q_k = x' S x
             double q = 0.0;
             if (lane < n) {
@@ -419,6 +423,7 @@ extern "C" void gmb_cov_destroy(gmb_cov* cv) {
     if (cv->d_work) gmb_dfree(cv->ctx, cv->d_work);
     if (cv->d_linv) gmb_dfree(cv->ctx, cv->d_linv);
     if (cv->d_gram) gmb_dfree(cv->ctx, cv->d_gram);
+    if (cv->d_batch) gmb_dfree(cv->ctx, cv->d_batch);
     delete cv;
 }
 
@@ -633,7 +638,7 @@ extern "C" int gmb_cov_mvn_ll_model(gmb_cov* cv, const double* theta, gmb_model*
         GMB_CUDA(cudaMemsetAsync(cv->d_status, 0, sizeof(int), ctx->stream));
         const int ctas = (cv->B + FACT_WARPS - 1) / FACT_WARPS;
         GMB_TRY(gmb_ctx_scratch(ctx, (size_t)ctas));
-        mvn_gram_kernel<<<ctas, FACT_WARPS * 32, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_gram,
+        mvn_gram_kernel<<<ctas, FACT_WARPS * 32, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->R, cv->d_gram,
                                                                   (double)mdl->m_local, cv->d_Lblk, cv->d_logdet, cv->d_status, ctx->d_scratch,
                                                                   ctx->d_counter, ctx->d_result);
         ctx->launches++;
@@ -651,6 +656,55 @@ extern "C" int gmb_cov_mvn_ll_model(gmb_cov* cv, const double* theta, gmb_model*
     GMB_TRY(gmb_cov_factor(cv, theta));
     GMB_TRY(gmb_cov_quad(cv, mdl->dU, mdl->ldq, mdl->m_local, cv->ctx->d_result));
     return cov_finish_ll(cv, cv->ctx->d_result, ncols_total > 0 ? ncols_total : mdl->m_total, out);
+}
+
+// k evaluations at the columns of thetas (R x k) with one launch and one synchronisation (sufficient-statistics path); otherwise one
+// after the other.  An evaluation whose D(theta) is not positive definite yields -inf instead of an error.
+extern "C" int gmb_cov_mvn_ll_model_batch(gmb_cov* cv, const double* thetas, int k, gmb_model* mdl, int ncols_total, double* out) {
+    if (!cv || !thetas || !mdl || !out || k < 0) return gmb_set_error(GMB_EINVAL, "gmb_cov_mvn_ll_model_batch: bad arguments");
+    if (k == 0) return GMB_OK;
+    const int R = cv->R;
+    if (!(cv->max_n <= QUAD_SMALL_MAX && g_cov_gram && mdl->dU && mdl->m_local > 0 && mdl->Q == cv->Q)) {
+        for (int e = 0; e < k; e++) {
+            int rc = gmb_cov_mvn_ll_model(cv, thetas + (size_t)e * R, mdl, ncols_total, out + e);
+            if (rc == GMB_ENOTPD) { out[e] = -INFINITY; rc = GMB_OK; }
+            GMB_TRY(rc);
+        }
+        return GMB_OK;
+    }
+    gmb_ctx* ctx = cv->ctx;
+    cudaSetDevice(ctx->device);
+    GMB_TRY(cov_ensure_gram(cv, mdl));
+    const int ctas = (cv->B + FACT_WARPS - 1) / FACT_WARPS;
+    const double denom = (double)(ncols_total > 0 ? ncols_total : mdl->m_total);
+    for (int off = 0; off < k; off += 2048) {
+        const int kb = std::min(2048, k - off);
+        // device layout: theta [R kb] | out [kb] | partials [ctas kb] | status [kb] ints | counters [kb] uints
+        const size_t nd = (size_t)R * kb + kb + (size_t)ctas * kb, need = nd * sizeof(double) + (size_t)kb * 8;
+        if (need > cv->batch_bytes) {
+            if (cv->d_batch) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, cv->d_batch); cv->d_batch = nullptr; cv->batch_bytes = 0; }
+            GMB_CUDA(gmb_dmalloc(ctx, &cv->d_batch, need));
+            cv->batch_bytes = need;
+        }
+        if ((size_t)(R + 1) * kb + kb > ctx->pinned_doubles) return gmb_set_error(GMB_EINVAL, "batch too large");
+        double* d_th = cv->d_batch; double* d_out = d_th + (size_t)R * kb; double* d_part = d_out + kb;
+        int* d_stat = reinterpret_cast<int*>(d_part + (size_t)ctas * kb); unsigned int* d_cnt = reinterpret_cast<unsigned int*>(d_stat + kb);
+        GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(ctx->h_pinned, thetas + (size_t)off * R, sizeof(double) * R * kb);
+        GMB_CUDA(cudaMemcpyAsync(d_th, ctx->h_pinned, sizeof(double) * R * kb, cudaMemcpyHostToDevice, ctx->stream));
+        GMB_CUDA(cudaMemsetAsync(d_stat, 0, (size_t)kb * 8, ctx->stream));
+        mvn_gram_kernel<<<dim3(ctas, kb), FACT_WARPS * 32, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, d_th, R, cv->d_gram,
+                                                                             (double)mdl->m_local, nullptr, nullptr, d_stat, d_part, d_cnt, d_out);
+        ctx->launches++;
+        GMB_CUDA(cudaGetLastError());
+        GMB_TRY(gmb_comm_allreduce_dev(ctx, d_out, kb));
+        double* h_out = ctx->h_pinned + (size_t)R * kb; int* h_stat = reinterpret_cast<int*>(h_out + kb);
+        GMB_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * kb, cudaMemcpyDeviceToHost, ctx->stream));
+        GMB_CUDA(cudaMemcpyAsync(h_stat, d_stat, sizeof(int) * kb, cudaMemcpyDeviceToHost, ctx->stream));
+        GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int e = 0; e < kb; e++) out[off + e] = (h_stat[e] != 0 || !(h_out[e] == h_out[e])) ? -INFINITY : h_out[e] / denom;   // mcmldmatrix.h:40
+    }
+    return GMB_OK;
 }
 
 extern "C" int gmb_cov_logdet(gmb_cov* cv, const double* theta, double* out) {

@@ -109,6 +109,9 @@ int gmb_cov_mvn_ll(gmb_cov* cv, const double* theta, const double* U, int Q, int
 /* Same on the device-resident samples of a model (set by gmb_model_set_u / gmb_hmc_sample); ncols_total = how many
  * leading columns to average (m+1 in mcml_full, mcmldmatrix.h:24,40). */
 int gmb_cov_mvn_ll_model(gmb_cov* cv, const double* theta, gmb_model* mdl, int ncols_total, double* out);
+/* The same at the k columns of thetas (R x k): one launch and one synchronisation for the whole batch when every block is <= 16 (the
+ * optimiser's stencils and the optimhess points of mcml_hess arrive as batches).  out[e] = -inf where D(theta_e) is not positive definite. */
+int gmb_cov_mvn_ll_model_batch(gmb_cov* cv, const double* thetas, int k, gmb_model* mdl, int ncols_total, double* out);
 /* MCMLDmatrix::logdet, mcmldmatrix.h:43-54. */
 int gmb_cov_logdet(gmb_cov* cv, const double* theta, double* out);
 

@@ -120,7 +120,26 @@ def test_gram_path_equals_stream_and_oracle(name, gctx, oracle):
             assert abs(stream - want) <= 1e-10 * abs(want)
             assert abs(got - want) <= 1e-10 * abs(want), (got, stream, want)
             assert abs(cv.logdet(theta) - oracle.logdet(cfg["cov"], cfg["data"], cfg["eff_range"], theta)) <= 1e-10 * max(1.0, abs(want))
+    # batched evaluation (one launch for all points): bitwise the single evaluations; -inf where D(theta) is not positive definite
+    R = cfg["theta"].size
+    pts = np.asfortranarray(np.stack([cfg["theta"] * s for s in (1.0, 0.7, 0.9, 1.1, 1.0)], axis=1))
     if name != "C1":
+        pts[:, 2] = [0.3, 1.2]                                   # ar1 parameter > 1
+    single = []
+    for k in range(pts.shape[1]):
+        try:
+            single.append(cv.loglik_model(pts[:, k], mdl))
+        except g.GmbError:
+            single.append(-np.inf)
+    batch = cv.loglik_model_batch(pts, mdl)
+    assert np.array_equal(batch, np.array(single))
+    try:
+        g.cov_set_gram(False)
+        assert np.allclose(cv.loglik_model_batch(pts, mdl), batch, rtol=1e-10, atol=0)     # falls back to single streaming evaluations
+    finally:
+        g.cov_set_gram(True)
+    if name != "C1":
+        assert batch[2] == -np.inf
         with pytest.raises(g.GmbError):
             cv.loglik_model(np.array([0.3, 1.2]), mdl)          # ar1 parameter > 1: not positive definite
     mdl.close(); cv.close()

@@ -9,7 +9,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-fi
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 echo "launch list rc=$?"
 python tools/profile_hmc.py > gpurun_out/plain_hmc.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:hmc_fused -c 2 -o gpurun_out/prof_hmc_${TAG} -f \
+ncu --set full --clock-control none --import-source on -k regex:"hmc_fused|hmc_sparse" -c 2 -o gpurun_out/prof_hmc_${TAG} -f \
     python tools/profile_hmc.py > gpurun_out/ncu_hmc.log 2>&1
 echo "hmc full rc=$?"
 python tools/profile_kernels.py estep > gpurun_out/plain_prof.log 2>&1 &&
