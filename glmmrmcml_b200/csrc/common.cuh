@@ -405,62 +405,6 @@ __device__ __forceinline__ double dev_family_resid_w(double c, double ys, double
     if (FL == 3) return fma(c, dev_rcp_fast(dev_exp_tab(eta, tab) + 1.0), ys);
     return fma(-c, eta, ys);
 }
-// The same for N rows at once, written stage by stage across the rows so that their dependent chains overlap (the sparse sampler runs one or
-// two warps per scheduler: nothing else hides the ~20 dependent FP64 operations of exp + reciprocal).  Per row: the operations of
-// dev_family_resid_w in the same order, hence the same bits.
-template <int FL, int N>
-__device__ __forceinline__ void dev_family_resid_w_vec(const double (&c)[N], const double (&ys)[N], const double (&eta)[N],
-                                                       const double* __restrict__ tab, double (&out)[N]) {
-    if (FL == 7) {
-#pragma unroll
-        for (int k = 0; k < N; k++) out[k] = fma(-c[k], eta[k], ys[k]);
-        return;
-    }
-    double t[N], r[N], T[N], q[N], e[N];
-    int kk[N];
-#pragma unroll
-    for (int k = 0; k < N; k++) t[k] = fma(eta[k], 92.33248261689366, 6755399441055744.0);
-#pragma unroll
-    for (int k = 0; k < N; k++) { kk[k] = __double2loint(t[k]); t[k] -= 6755399441055744.0; }
-#pragma unroll
-    for (int k = 0; k < N; k++) { T[k] = tab[kk[k] & 63]; r[k] = fma(t[k], -0.010830424667801708, eta[k]); }
-#pragma unroll
-    for (int k = 0; k < N; k++) r[k] = fma(t[k], -2.8447437476627285e-11, r[k]);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = fma(r[k], 1.0 / 120.0, 1.0 / 24.0);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = fma(q[k], r[k], 1.0 / 6.0);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = fma(q[k], r[k], 0.5);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = fma(q[k], r[k], 1.0);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = q[k] * r[k];
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-        const double m = fma(T[k], q[k], T[k]);
-        const int ks = min(max(kk[k], -64512), 64512);
-        e[k] = __hiloint2double(__double2hiint(m) + ((ks >> 6) << 20), __double2loint(m));
-    }
-    if (FL == 1) {
-#pragma unroll
-        for (int k = 0; k < N; k++) out[k] = fma(-c[k], e[k], ys[k]);
-        return;
-    }
-    double d[N], y[N], f[N];
-#pragma unroll
-    for (int k = 0; k < N; k++) { d[k] = e[k] + 1.0; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(d[k])); }
-#pragma unroll
-    for (int k = 0; k < N; k++) f[k] = fma(-d[k], y[k], 1.0);
-#pragma unroll
-    for (int k = 0; k < N; k++) y[k] = fma(y[k], f[k], y[k]);
-#pragma unroll
-    for (int k = 0; k < N; k++) f[k] = fma(-d[k], y[k], 1.0);
-#pragma unroll
-    for (int k = 0; k < N; k++) y[k] = fma(y[k], f[k], y[k]);
-#pragma unroll
-    for (int k = 0; k < N; k++) out[k] = fma(c[k], y[k], ys[k]);
-}
 // log-density of a row: lc observations counted, lys = sum of y (poisson, binomial) or their mean (gaussian), lsq = within-row sum of
 // squares (gaussian), lrc = sum of lf(y) (poisson).  With lc = 1: dev_family_ll.
 template <int FL>

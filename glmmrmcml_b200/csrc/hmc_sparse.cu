@@ -18,6 +18,7 @@
 // accumulate even and odd ELL positions separately to halve the dependent chain).
 #include "common.cuh"
 #include <algorithm>
+#include <type_traits>
 
 namespace {
 
@@ -91,6 +92,73 @@ __global__ void ell_fill_cols_kernel(int ng, int Q, int qp, int ld, int wc, cons
         }
     }
     for (int w = base + lane; w < wc; w += 32) { cv[(size_t)w * qp + j] = 0.0; cr[(size_t)w * qp + j] = first; }
+}
+
+// dev_family_resid_w (common.cuh) for N rows at once, written stage by stage across the rows so that their dependent chains overlap (the sparse sampler runs one or
+// two warps per scheduler: nothing else hides the ~20 dependent FP64 operations of exp + reciprocal).  Per row: the operations of
+// dev_family_resid_w in the same order, hence the same bits.
+// Constants come from the constant bank as direct DFMA operands (literals cost two UMOV each per use inside the step loop: 8 % of the
+// issued instructions in the first profile of this kernel).
+static __constant__ double SP_EXPC[10] = {
+    92.33248261689366,              // 0: 64 / ln2
+    6755399441055744.0,             // 1: 1.5 * 2^52 (round to nearest integer by addition)
+    -0.010830424667801708,          // 2: -ln2/64 high part
+    -2.8447437476627285e-11,        // 3: -ln2/64 low part
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0,   // 4..8
+    0.0};
+template <int FL, int N>
+__device__ __forceinline__ void dev_family_resid_w_vec(const double (&c)[N], const double (&ys)[N], const double (&eta)[N],
+                                                       const double* __restrict__ tab, double (&out)[N]) {
+    if (FL == 7) {
+#pragma unroll
+        for (int k = 0; k < N; k++) out[k] = fma(-c[k], eta[k], ys[k]);
+        return;
+    }
+    const double* cc = SP_EXPC;
+    double t[N], r[N], T[N], q[N], e[N];
+    int kk[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) t[k] = fma(eta[k], cc[0], cc[1]);
+#pragma unroll
+    for (int k = 0; k < N; k++) { kk[k] = __double2loint(t[k]); t[k] -= cc[1]; }
+#pragma unroll
+    for (int k = 0; k < N; k++) { T[k] = tab[kk[k] & 63]; r[k] = fma(t[k], cc[2], eta[k]); }
+#pragma unroll
+    for (int k = 0; k < N; k++) r[k] = fma(t[k], cc[3], r[k]);
+#pragma unroll
+    for (int k = 0; k < N; k++) q[k] = fma(r[k], cc[4], cc[5]);
+#pragma unroll
+    for (int k = 0; k < N; k++) q[k] = fma(q[k], r[k], cc[6]);
+#pragma unroll
+    for (int k = 0; k < N; k++) q[k] = fma(q[k], r[k], cc[7]);
+#pragma unroll
+    for (int k = 0; k < N; k++) q[k] = fma(q[k], r[k], cc[8]);
+#pragma unroll
+    for (int k = 0; k < N; k++) q[k] = q[k] * r[k];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        const double m = fma(T[k], q[k], T[k]);
+        const int ks = min(max(kk[k], -64512), 64512);
+        e[k] = __hiloint2double(__double2hiint(m) + ((ks >> 6) << 20), __double2loint(m));
+    }
+    if (FL == 1) {
+#pragma unroll
+        for (int k = 0; k < N; k++) out[k] = fma(-c[k], e[k], ys[k]);
+        return;
+    }
+    double d[N], y[N], f[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) { d[k] = e[k] + cc[8]; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(d[k])); }
+#pragma unroll
+    for (int k = 0; k < N; k++) f[k] = fma(-d[k], y[k], cc[8]);
+#pragma unroll
+    for (int k = 0; k < N; k++) y[k] = fma(y[k], f[k], y[k]);
+#pragma unroll
+    for (int k = 0; k < N; k++) f[k] = fma(-d[k], y[k], cc[8]);
+#pragma unroll
+    for (int k = 0; k < N; k++) y[k] = fma(y[k], f[k], y[k]);
+#pragma unroll
+    for (int k = 0; k < N; k++) out[k] = fma(c[k], y[k], ys[k]);
 }
 
 // ---- the sampler ----
@@ -192,7 +260,9 @@ __global__ void __launch_bounds__(TPC == 32 ? 32 * SP_CPB : TPC) hmc_sparse_kern
     double totsteps = 0.0, lastprob = 0.0;
 
     // gradient of the log-density at the v' in s_vp (visible to the whole chain) -> g; with_ll: llnew = family log-likelihood there
-    auto grad_eval = [&](bool with_ll) {
+    // (with_ll is a compile-time tag: the steps of a trajectory before the last one carry no log-likelihood code and no branch)
+    auto grad_eval = [&](auto ll_tag) {
+        constexpr bool with_ll = decltype(ll_tag)::value;
         double ll = 0.0;
         if constexpr (REGELL) {
             // straight-line code for all slots of the lane (padding rows / columns carry zero weights, zero ELL values and offset 0), written
@@ -283,7 +353,7 @@ __global__ void __launch_bounds__(TPC == 32 ? 32 * SP_CPB : TPC) hmc_sparse_kern
         }
     }
     chain_sync();
-    grad_eval(true);
+    grad_eval(std::true_type{});
     llcur = llnew;
 #pragma unroll
     for (int k = 0; k < KQ; k++) {
@@ -330,19 +400,19 @@ __global__ void __launch_bounds__(TPC == 32 ? 32 * SP_CPB : TPC) hmc_sparse_kern
         }
         chain_sync();
         // ---- leapfrog integrator, :73-78 ----
-        for (int s = 0; s < steps; s++) {
-            const bool more = s < steps - 1;
-            grad_eval(!more);
+        auto leap = [&](auto more_tag) {
+            constexpr bool more = decltype(more_tag)::value;
+            grad_eval(std::integral_constant<bool, !more>{});
             if constexpr (REGELL) {
-                // branch free (padding columns: g = r = v' = 0 throughout); after a chain's last step v' stays and the store repeats it
+                // straight-line (padding columns: g = r = v' = 0 throughout)
 #pragma unroll
                 for (int k = 0; k < NE; k++) {
                     double rr = r_reg[k] + (eps / 2) * g_reg[k];                                    // :77
-                    const double rn = rr + (eps / 2) * g_reg[k];                                    // :74 of the next step
-                    rr = more ? rn : rr;
-                    const double vn = vp_reg[k] + eps * rr;                                         // :75
-                    vp_reg[k] = more ? vn : vp_reg[k];
-                    my_vp[k * TPC] = vp_reg[k];
+                    if (more) {
+                        rr = rr + (eps / 2) * g_reg[k];                                             // :74 of the next step
+                        vp_reg[k] = vp_reg[k] + eps * rr;                                           // :75
+                        my_vp[k * TPC] = vp_reg[k];
+                    }
                     r_reg[k] = rr;
                 }
             } else {
@@ -363,7 +433,9 @@ __global__ void __launch_bounds__(TPC == 32 ? 32 * SP_CPB : TPC) hmc_sparse_kern
                 }
             }
             chain_sync();                                          // the new v' is visible; every read of r(eta) is done
-        }
+        };
+        for (int s = 0; s + 1 < steps; s++) leap(std::true_type{});
+        leap(std::false_type{});
         // ---- Metropolis test and adaptation, :80-117 ----
         double k1 = 0.0, pvp = 0.0;
 #pragma unroll
