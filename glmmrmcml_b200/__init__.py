@@ -39,6 +39,11 @@ def _covargs(cov, data, eff_range):
     return (cov, data, eff), [cov.ctypes.data_as(_lib.ip), cov.shape[0], _d(data), data.size, _d(eff), eff.size]
 
 
+def estep_set_multi(on: bool):
+    """Batched binomial/logit evaluations share their pass over the factor matrix (default) or run one launch each (gmb_estep_set_multi)."""
+    check(lib().gmb_estep_set_multi(int(bool(on))))
+
+
 def hmc_set_variant(variant: int):
     """0 = automatic, 1 = two-GEMM sampler kernels, 2 = on-chip sampler kernel (see gmb_hmc_set_variant)."""
     check(lib().gmb_hmc_set_variant(int(variant)))

@@ -69,6 +69,7 @@ PROTOTYPES = {
     "gmb_hmc_sample": (C.c_int, [vp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int,
                                  C.c_int, C.c_uint32, C.c_uint64, C.c_int, dp, dp, C.POINTER(HmcStats)]),
     "gmb_hmc_set_variant": (C.c_int, [C.c_int]),
+    "gmb_estep_set_multi": (C.c_int, [C.c_int]),
     "gmb_hmc_set_cluster_size": (C.c_int, [C.c_int]),
     "gmb_estep_set_rowstats": (C.c_int, [C.c_int]),
     "gmb_hmc_set_row_aggregation": (C.c_int, [C.c_int]),

@@ -176,6 +176,8 @@ int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, doub
 int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par, const double* d_zd, int ncols, double* d_out);
 int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* d_out /* P*P + P + 1 doubles: local sums */);
 int gmb_launch_build_factor(gmb_model* mdl, int ncols);
+#define GMB_LOGLIK_NB 8
+int gmb_launch_loglik_multi(gmb_model* mdl, const double* d_beta, int n_eval, double* d_out, int* done);
 int gmb_estep_rowstats_enabled();
 
 // cov.cu

@@ -206,6 +206,127 @@ __global__ void __launch_bounds__(256) loglik_logit_factor_kernel(int n, int P, 
     grid_sum_finish(acc, TX, partials, counter, out, red, &is_last);
 }
 
+// The same for a whole batch of parameter vectors in ONE launch (the optimiser's stencils and the 4 k^2 optimhess points arrive as batches):
+// blockIdx.z selects a group of NB evaluations, a thread keeps the NB row constants A_i of its two rows in registers and applies them to every
+// element it loads, and the grid is sized for one wave over all groups — so F is read once per NB evaluations and the per-thread set-up (x'beta,
+// two exp per evaluation) and the grid reduction are amortised over hundreds of columns instead of a dozen.  At C2 (n = 500: one row tile) a
+// single evaluation is bound by launch + set-up + reduction latency (14.6 us for 5 10^6 elements); the batch is bound by its FP64 work.
+// Deterministic (fixed partition per problem size and batch), but the partition differs from the single evaluation's: values agree to rounding,
+// not bit for bit.  beta: P x n_eval; group z covers evaluations min(z NB, n_eval - NB) .. + NB - 1 (a short last group overlaps the one
+// before); partials: [group][NB][blocks]; counters: one per group, zero on entry; out: n_eval values.
+template <int NB>
+__global__ void __launch_bounds__(256) loglik_logit_factor_multi_kernel(int n, int P, int ldn, int ncols, int cols_per_cta, int n_eval,
+                                                                        const double* __restrict__ F, const double* __restrict__ X,
+                                                                        const double* __restrict__ beta, const double* __restrict__ y,
+                                                                        double* __restrict__ partials, unsigned int* __restrict__ counter,
+                                                                        double* __restrict__ out) {
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const int TX = blockDim.x, TY = blockDim.y;
+    {
+        const int e_start = min((int)blockIdx.z * NB, n_eval - NB);
+        beta += (size_t)e_start * P; out += e_start;
+        partials += (size_t)blockIdx.z * NB * gridDim.x * gridDim.y; counter += blockIdx.z;
+    }
+    const int i0 = 2 * (blockIdx.x * TX + threadIdx.x);
+    const int j0 = blockIdx.y * cols_per_cta;
+    const int j1 = min(j0 + cols_per_cta, ncols);
+    double acc[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) acc[b] = 0.0;
+    if (i0 < n) {
+        const bool two = (i0 + 1 < n);
+        const double y0 = y[i0], y1 = two ? y[i0 + 1] : -1.0;
+        double A0[NB], A1[NB];
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            double xb0 = 0.0, xb1 = 0.0;
+            for (int p = 0; p < P; p++) {                            // same order as xb_kernel
+                const double bb = beta[p + (size_t)b * P];
+                xb0 += X[i0 + (size_t)p * ldn] * bb;
+                if (two) xb1 += X[i0 + 1 + (size_t)p * ldn] * bb;
+            }
+            A0[b] = (y0 == 1.0) ? exp(-1.0 * xb0) : ((y0 == 0.0) ? exp(xb0) : 0.0);
+            A1[b] = (y1 == 1.0) ? exp(-1.0 * xb1) : ((y1 == 0.0) ? exp(xb1) : 0.0);
+        }
+        const double* col = F + i0;
+        int j = j0 + threadIdx.y;
+        double2 z[4], zn[4];
+        bool have = j + 3 * TY < j1;
+        if (have) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const double2*>(col + (size_t)(j + u * TY) * ldn);
+        }
+        while (have) {
+            const int jn = j + 4 * TY;
+            const bool have_n = jn + 3 * TY < j1;
+            if (have_n) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) zn[u] = *reinterpret_cast<const double2*>(col + (size_t)(jn + u * TY) * ldn);
+            }
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                double p0 = 1.0, p1 = 1.0;
+#pragma unroll
+                for (int u = 0; u < 4; u++) { p0 *= fma(A0[b], z[u].x, 1.0); p1 *= fma(A1[b], z[u].y, 1.0); }
+                const double prod = p0 * p1;
+                if (prod <= 1e300) {
+                    acc[b] -= log(prod);
+                } else {                                              // overflow (or NaN): term by term
+#pragma unroll
+                    for (int u = 0; u < 4; u++) acc[b] -= log(fma(A0[b], z[u].x, 1.0)) + log(fma(A1[b], z[u].y, 1.0));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) z[u] = zn[u];
+            j = jn; have = have_n;
+        }
+        for (; j < j1; j += TY) {
+            const double2 zz = *reinterpret_cast<const double2*>(col + (size_t)j * ldn);
+#pragma unroll
+            for (int b = 0; b < NB; b++) acc[b] -= log(fma(A0[b], zz.x, 1.0)) + log(fma(A1[b], zz.y, 1.0));
+        }
+    }
+    // per evaluation: the deterministic grid sum of grid_sum_finish (per-CTA partial, last CTA sums the partials in index order)
+    const int t = threadIdx.y * TX + threadIdx.x, w = t >> 5, l = t & 31;
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x, nblocks = gridDim.x * gridDim.y;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        double v = warp_sum(acc[b]);
+        __syncthreads();
+        if (l == 0) red[w] = v;
+        __syncthreads();
+        if (w == 0) {
+            v = (l < 8) ? red[l] : 0.0;
+            v = warp_sum(v);
+            if (l == 0) partials[(size_t)b * nblocks + bid] = v;
+        }
+    }
+    if (t == 0) {
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == (unsigned)nblocks - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            double s = 0.0;
+            for (int k = t; k < nblocks; k += 256) s += partials[(size_t)b * nblocks + k];
+            s = warp_sum(s);
+            __syncthreads();
+            if (l == 0) red[w] = s;
+            __syncthreads();
+            if (w == 0) {
+                s = (l < 8) ? red[l] : 0.0;
+                s = warp_sum(s);
+                if (l == 0) out[b] = s;
+            }
+        }
+        if (t == 0) *counter = 0u;
+    }
+}
+
 template <int FL>
 __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int ncols, int cols_per_cta,
                                                      const double* __restrict__ zd, const double* __restrict__ X,
@@ -636,6 +757,40 @@ int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par,
     }
     ctx->launches++;
     GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}
+
+// n_eval (>= GMB_LOGLIK_NB) evaluations of the binomial/logit objective on the model's factor matrix in one launch; d_beta: P x n_eval,
+// d_out: n_eval values.  Sets *done = 0 (and launches nothing) when the factor path does not apply.
+int gmb_launch_loglik_multi(gmb_model* mdl, const double* d_beta, int n_eval, double* d_out, int* done) {
+    gmb_ctx* ctx = mdl->ctx;
+    *done = 0;
+    const int n = mdl->n, ncols = mdl->niter_local;
+    if (!(mdl->flink == 3 && mdl->f_valid && ncols > 0 && n_eval >= GMB_LOGLIK_NB)) return GMB_OK;
+    const int groups = (n_eval + GMB_LOGLIK_NB - 1) / GMB_LOGLIK_NB;
+    if (groups > 65535) return GMB_OK;
+    int half = (n + 1) / 2;
+    int TX = 32; while (TX < 256 && TX < half) TX <<= 1;
+    int TY = 256 / TX;
+    int RT = (half + TX - 1) / TX;
+    // one wave of 2 CTAs per SM over all groups, at least 4 TY columns per CTA
+    int want_cc = (ctx->sms * 2) / (RT * groups); if (want_cc < 1) want_cc = 1;
+    int max_cc = (ncols + 4 * TY - 1) / (4 * TY);
+    int CC = want_cc < max_cc ? want_cc : max_cc; if (CC < 1) CC = 1;
+    int cols_per_cta = (ncols + CC - 1) / CC;
+    cols_per_cta = round_up(cols_per_cta, TY);
+    CC = (ncols + cols_per_cta - 1) / cols_per_cta;
+    const size_t nblocks = (size_t)RT * CC;
+    const size_t part = nblocks * GMB_LOGLIK_NB * groups;
+    GMB_TRY(gmb_ctx_scratch(ctx, part + (size_t)(groups + 1) / 2 + 1));
+    unsigned int* counters = reinterpret_cast<unsigned int*>(ctx->d_scratch + part);
+    GMB_CUDA(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * groups, ctx->stream));
+    dim3 grid(RT, CC, groups), block(TX, TY);
+    loglik_logit_factor_multi_kernel<GMB_LOGLIK_NB><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, n_eval, mdl->dF, mdl->dX,
+                                                                                      d_beta, mdl->dy, ctx->d_scratch, counters, d_out);
+    ctx->launches++;
+    GMB_CUDA(cudaGetLastError());
+    *done = 1;
     return GMB_OK;
 }
 

@@ -186,6 +186,10 @@ static int check_ready(gmb_model* mdl, const double* beta) {
     return GMB_OK;
 }
 
+// 1 (default): batched binomial/logit evaluations share their pass over the factor matrix (estep.cu: loglik_logit_factor_multi_kernel)
+static int g_loglik_multi = 1;
+extern "C" int gmb_estep_set_multi(int on) { g_loglik_multi = on ? 1 : 0; return GMB_OK; }
+
 extern "C" int gmb_model_loglik_batch(gmb_model* mdl, const double* beta_mat, const double* var_par, int n_eval, double* out) {
     GMB_TRY(check_ready(mdl, beta_mat));
     if (!var_par || !out || n_eval <= 0) return gmb_set_error(GMB_EINVAL, "gmb_model_loglik_batch: bad arguments");
@@ -194,7 +198,14 @@ extern "C" int gmb_model_loglik_batch(gmb_model* mdl, const double* beta_mat, co
     GMB_CUDA(cudaSetDevice(ctx->device));
     if (mdl->flink == 7) for (int e = 0; e < n_eval; e++) if (!(var_par[e] > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0 (got %g)", var_par[e]);
     GMB_TRY(upload_params(mdl, beta_mat, mdl->P * n_eval));
-    for (int e = 0; e < n_eval; e++)
+    int e0 = 0;
+    if (n_eval >= GMB_LOGLIK_NB && g_loglik_multi) {
+        // binomial/logit on the factor matrix: the whole batch in one launch, GMB_LOGLIK_NB evaluations per pass over F
+        int done = 0;
+        GMB_TRY(gmb_launch_loglik_multi(mdl, mdl->dbeta, n_eval, ctx->d_result, &done));
+        if (done) e0 = n_eval;
+    }
+    for (int e = e0; e < n_eval; e++)
         GMB_TRY(gmb_launch_loglik(mdl, mdl->dbeta + (size_t)e * mdl->P, var_par[e], ctx->d_result + e));
     GMB_TRY(gmb_comm_allreduce_dev(ctx, ctx->d_result, n_eval));
     double* hres = ctx->h_pinned + ctx->pinned_doubles / 2;

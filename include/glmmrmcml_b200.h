@@ -157,6 +157,11 @@ int gmb_hmc_set_cluster_size(int cs);
  * sample matrix; 0 = stream zd on every evaluation (used by the roofline probes and the parity tests of the streaming kernel). */
 int gmb_estep_set_rowstats(int on);
 
+/* Batched binomial/logit evaluations (gmb_model_loglik_batch, batches of >= 8): 1 (default) = one launch for the whole batch, 8 parameter
+ * vectors share each pass over the factor matrix; 0 = one launch per evaluation.  Both deterministic; they partition the sum differently, so
+ * values agree to rounding (1e-13 relative), not bit for bit. */
+int gmb_estep_set_multi(int on);
+
 /* mvn_ll on a model's device-resident samples when every covariance block is <= 16: 1 (default) = through the Gram matrices of the samples
  * (built once per sample matrix, each evaluation independent of the number of samples), 0 = stream the samples on every evaluation. */
 int gmb_cov_set_gram(int on);

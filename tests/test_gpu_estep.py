@@ -49,6 +49,33 @@ def test_loglik_matches_oracle(case, oracle):
         assert abs(got - want) <= RTOL * abs(want), (got, want)
 
 
+@pytest.mark.parametrize("k", [2, 8, 19, 256])
+def test_loglik_multi_kernel_equals_single_kernel(gctx, oracle, k):
+    """Batched binomial/logit evaluations run as one launch, 8 parameter vectors per pass over the factor matrix (estep.cu:
+    loglik_logit_factor_multi_kernel); batches shorter than, equal to and not a multiple of 8, with a parameter vector large enough to
+    push groups of factors past the overflow guard.  Same sums in another partition: 1e-13 relative against the single-launch kernel,
+    1e-10 against the oracle, and bitwise reproducible."""
+    import glmmrmcml_b200 as g
+    cfg = synth.config2(m=1500)
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    mdl.set_u(cfg["U"])
+    rng = np.random.default_rng(5)
+    betas = np.asfortranarray(cfg["beta"][:, None] + 0.2 * rng.standard_normal((cfg["P"], k)))
+    betas[:, k - 1] *= 150.0                       # |eta| ~ 100: products of 8 factors overflow, term-by-term path
+    try:
+        g.estep_set_multi(False); single = mdl.log_likelihood_batch(betas, np.ones(k))
+    finally:
+        g.estep_set_multi(True)
+    multi = mdl.log_likelihood_batch(betas, np.ones(k))
+    assert np.all(np.isfinite(multi)) and rel(multi, single) <= 1e-13 and np.max(np.abs(multi / single - 1)) <= 1e-13
+    assert np.array_equal(multi, mdl.log_likelihood_batch(betas, np.ones(k)))
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    for e in (0, k - 1):
+        want = oracle.loglik_faithful(cfg["X"], cfg["Z"], cfg["U"], cfg["y"], betas[:, e], 1.0, fl)
+        assert abs(multi[e] - want) <= RTOL * abs(want)
+    mdl.close()
+
+
 def test_loglik_batch_equals_single(case):
     cfg, mdl = case
     rng = np.random.default_rng(11)
@@ -56,7 +83,10 @@ def test_loglik_batch_equals_single(case):
     sig = 1.0 + 0.1 * np.arange(9)
     b = mdl.log_likelihood_batch(betas, sig)
     s = np.array([mdl.log_likelihood(betas[:, k], sig[k]) for k in range(9)])
-    assert np.array_equal(b, s)          # same kernel, deterministic reduction -> bitwise equal
+    if cfg["family"] == "binomial":      # batches of >= 8 take the one-launch kernel (another partition of the same sum)
+        assert rel(b, s) <= 1e-13
+    else:
+        assert np.array_equal(b, s)      # same kernel, deterministic reduction -> bitwise equal
 
 
 def test_loglik_is_deterministic(case):
