@@ -139,7 +139,19 @@ class Context:
 
     def make_default(self):
         """Route the reference-named entry points (mcml_full, ...) through this context."""
+        global _DEFAULT_CTX
         check(lib().gmb_set_default_ctx(self._h))
+        _DEFAULT_CTX = self
+
+
+_DEFAULT_CTX = None
+
+
+def default_context() -> "Context":
+    """The context behind the reference-named entry points (created on device 0 the first time it is needed)."""
+    if _DEFAULT_CTX is None:
+        Context(0).make_default()
+    return _DEFAULT_CTX
 
 
 class Model:
@@ -459,11 +471,14 @@ def fd_hessian(fun, x, ndeps, lower=None, upper=None, usebounds=False):
 
 
 class ModelMCML:
-    """Mirror of the R6 class ``ModelMCML`` (R/R6ModelExtMCML.R) for the internal-sampler path (``usestan = FALSE``).
+    """Mirror of the R6 class ``ModelMCML`` (R/R6ModelExtMCML.R).
 
     Holds what ``Model$new(covariance, mean.function, family)`` holds in R: the design matrices, the covariance in
-    ``get_D_data()`` form, the family and starting parameters.  ``MCML(y)`` runs ``mcml_full`` (R/R6ModelExtMCML.R:399-419)
-    and optionally the Hessian standard errors (``mcml_hess``, :448-474) and the conditional AIC (``aic_mcml``, :542-553).
+    ``get_D_data()`` form, the family and starting parameters.  ``MCML(y, usestan=False)`` runs ``mcml_full``
+    (R/R6ModelExtMCML.R:399-419); ``MCML(y, usestan=True)`` runs the R-level loop of :238-329 with the Stan call (``mod$sample``,
+    :248-255) replaced by the native sampler (``mcmc_sample``) — sample, ``mcml_optim``, refresh the Cholesky factor — and the
+    optional simulated-likelihood step (``mcml_simlik``, :335-373).  Both then take the Hessian standard errors
+    (``mcml_hess``, :448-474) and the conditional AIC (``aic_mcml``, :542-553).
     """
 
     def __init__(self, cov, data, eff_range, Z, X, family, link, beta_start, theta_start, var_par=1.0):
@@ -474,21 +489,66 @@ class ModelMCML:
         # R/R6ModelExtMCML.R:867-872
         self.mcmc_options = dict(warmup=500, samps=250, lam=5.0, refresh=500, maxsteps=100, target_accept=0.95)
 
+    def chol_D(self, theta):
+        """``self$covariance$get_chol_D(theta)``: dense lower Cholesky factor of D(theta)."""
+        cv = Covariance(default_context(), self.cov, self.data, self.eff_range)
+        try:
+            return cv.genD(_v(theta), chol=True)
+        finally:
+            cv.close()
+
+    def _mcml_stan_branch(self, y, start, tol, max_iter, method, sim_lik_step, verbose, n_chains, seed):
+        """R/R6ModelExtMCML.R:238-373 with `mod$sample` (cmdstanr, inst/stan/*.stan: gamma ~ N(0, I), y | Xb + Z L gamma) replaced by the
+        native sampler on the same target; `dsamps` = L gamma for the `samps` post-warm-up draws."""
+        P = self.X.shape[1]; R = _cov_R(self.cov)
+        gaussian = self.family == "gaussian"
+        o = self.mcmc_options
+        theta = _v(start).copy()                                  # (beta, cov pars, sigma)
+        thetanew = np.ones_like(theta)                            # :182
+        ib, ic, isg = slice(0, P), slice(P, P + R), P + R
+        act = slice(0, P + R + 1) if gaussian else slice(0, P + R)   # all_pars, :165,:177
+        L = self.chol_D(self.theta)                               # :199 get_chol_D() at the covariance's own parameters
+        it = 0
+        dsamps = None
+        while np.any(np.abs(theta[act] - thetanew[act]) > tol) and it <= max_iter:   # :238
+            it += 1
+            thetanew = theta.copy()
+            s = mcmc_sample(self.Z, L, self.X, y, thetanew[ib], self.family, self.link, o["warmup"], o["samps"], o["lam"],
+                            var_par=thetanew[isg], refresh=o["refresh"], maxsteps=o["maxsteps"], target_accept=o["target_accept"],
+                            n_chains=max(1, n_chains), seed=seed + it)
+            dsamps = np.asfortranarray(s[:, 1:])                  # iter_sampling draws (column 0 is the post-warm-up state), :256-258
+            fit = mcml_optim(self.cov, self.data, self.eff_range, self.Z, self.X, y, dsamps, self.family, self.link, theta,
+                             trace=0, mcnr=(method == "mcnr"))    # :293-306
+            theta[ib] = fit["beta"]
+            if gaussian:
+                theta[isg] = fit["sigma"]
+            theta[ic] = fit["theta"]
+            L = self.chol_D(thetanew[ic])                         # :315 — the PREVIOUS iterate's covariance parameters, as the reference
+            if verbose:
+                print(f"Iter {it}: beta {theta[ib]} theta {theta[ic]} max diff {np.max(np.abs(theta[act] - thetanew[act])):.3g}")
+        not_conv = it >= max_iter or bool(np.any(np.abs(theta[act] - thetanew[act]) > tol))   # :331
+        if sim_lik_step:                                          # :335-373
+            nt = mcml_simlik(self.cov, self.data, self.eff_range, self.Z, self.X, y, dsamps, self.family, self.link, theta)
+            theta[ib] = nt["beta"]; theta[ic] = nt["theta"]
+            if gaussian:
+                theta[isg] = nt["sigma"]
+        return dict(beta=theta[ib].copy(), theta=theta[ic].copy(), sigma=float(theta[isg]), converged=not not_conv, iter=it, u=dsamps)
+
     def MCML(self, y, start=None, se_theta=True, verbose=True, tol=1e-2, max_iter=30, method="mcnr", usestan=False,
-             n_chains=0, seed=1):
-        if usestan:
-            raise NotImplementedError("the Stan programs of inst/stan are replaced by the native sampler on this path; "
-                                      "call MCML(..., usestan=False)")
+             sim_lik_step=False, n_chains=0, seed=1):
         if method not in ("mcem", "mcnr"):
             raise ValueError("method must be 'mcem' or 'mcnr'")
         P = self.X.shape[1]
         if start is None:                                         # R/R6ModelExtMCML.R:159-179
             start = np.concatenate([self.beta, self.theta, [self.var_par if self.family == "gaussian" else 1.0]])
         o = self.mcmc_options
-        fit = mcml_full(self.cov, self.data, self.eff_range, self.Z, self.X, y, self.family, self.link, start,
-                        mcnr=(method == "mcnr"), m=o["samps"], maxiter=max_iter, warmup=o["warmup"], tol=tol,
-                        verbose=verbose, lam=o["lam"], trace=0, refresh=o["refresh"], maxsteps=o["maxsteps"],
-                        target_accept=o["target_accept"], n_chains=n_chains, seed=seed)
+        if usestan:
+            fit = self._mcml_stan_branch(y, start, tol, max_iter, method, sim_lik_step, verbose, n_chains, seed)
+        else:
+            fit = mcml_full(self.cov, self.data, self.eff_range, self.Z, self.X, y, self.family, self.link, start,
+                            mcnr=(method == "mcnr"), m=o["samps"], maxiter=max_iter, warmup=o["warmup"], tol=tol,
+                            verbose=verbose, lam=o["lam"], trace=0, refresh=o["refresh"], maxsteps=o["maxsteps"],
+                            target_accept=o["target_accept"], n_chains=n_chains, seed=seed)
         out = dict(fit)
         pars = np.concatenate([fit["beta"], fit["theta"]])
         if se_theta:

@@ -134,3 +134,22 @@ def test_model_mcml_class_runs_the_reference_call_sequence(gctx):
     k = cfg["P"] + 2
     assert out["hessian"].shape == (k, k) and np.isfinite(out["aic"])
     assert out["u"].shape == (cfg["Q"], 501)
+
+
+def test_model_mcml_usestan_branch_runs_on_the_native_sampler(gctx):
+    """ModelMCML$MCML(y, usestan = TRUE) (R/R6ModelExtMCML.R:238-373): the R-level loop — sample, mcml_optim, refresh L from the previous
+    iterate — with the Stan call replaced by the native sampler, then the simulated-likelihood step; the estimates agree with the
+    usestan = FALSE path (mcml_full) within Monte-Carlo error and the sample matrix has `samps` columns like Stan's draws."""
+    import glmmrmcml_b200 as g
+    gctx.make_default()
+    cfg = small_rct(m=8)
+    mod = g.ModelMCML(cfg["cov"], cfg["data"], cfg["eff_range"], cfg["Z"], cfg["X"], cfg["family"], cfg["link"], cfg["beta"], cfg["theta"])
+    mod.mcmc_options.update(warmup=100, samps=2000, lam=1.0, maxsteps=30)
+    a = mod.MCML(cfg["y"], verbose=False, tol=5e-2, max_iter=10, method="mcnr", usestan=True, sim_lik_step=True, n_chains=50, seed=3)
+    b = mod.MCML(cfg["y"], verbose=False, tol=5e-2, max_iter=10, method="mcnr", usestan=False, n_chains=50, seed=3)
+    assert a["u"].shape == (cfg["Q"], 2000) and b["u"].shape == (cfg["Q"], 2001)
+    assert a["iter"] >= 2 and np.all(np.isfinite(a["beta"])) and np.all(a["theta"] > 0)
+    assert np.max(np.abs(a["beta"] - b["beta"])) <= 0.25
+    assert a["hessian"].shape == (cfg["P"] + 2, cfg["P"] + 2) and np.isfinite(a["aic"])
+    L = mod.chol_D(cfg["theta"])
+    assert np.allclose(L, synth.dense_chol_D(cfg["cov"], cfg["data"], cfg["theta"]), rtol=1e-10, atol=1e-12)

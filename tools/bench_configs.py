@@ -70,6 +70,11 @@ def run(name):
     out["loglik"] = {"stream_ms": t_ll, "stream_evals_per_s": 1e3 / t_ll, "GBps": by / t_ll / 1e6, "frac_hbm": by / t_ll / 1e6 / HBM_PEAK,
                      "default_path_ms": t_def, "default_path_evals_per_s": 1e3 / t_def,
                      "default_path": "factor matrix stream" if cfg["family"] == "binomial" else "row statistics, O(n) per evaluation"}
+    # batched evaluations (what the optimiser and the Hessian stencil issue): 64 parameter vectors per call
+    B64 = np.asfortranarray(beta[:, None] * (1 + 1e-6 * np.arange(64))[None, :])
+    mdl.log_likelihood_batch(B64, np.full(64, sig)); ctx.sync()
+    ctx.timer_start(); mdl.log_likelihood_batch(B64, np.full(64, sig)); t_b = ctx.timer_stop()
+    out["loglik"]["batched_evals_per_s"] = 64e3 / t_b
     # K3
     mdl.mcnr(beta, sig); ts = []
     for r in range(3):
@@ -97,9 +102,25 @@ def run(name):
     res = mdl.hmc_sample(None, beta, sig, warmup=hw, nsamp_per_chain=hn, lam=0.05, max_steps=10, target_accept=0.9, n_chains=chains, seed=2,
                          keep_on_device=True, want_u=False)
     st = res["stats"]; fl_h = st["leapfrog_total"] * 4.0 * n * Q
-    out["hmc"] = {"chains": chains, "ms": st["kernel_ms"], "leapfrog_per_s": st["leapfrog_total"] / st["kernel_ms"] * 1e3,
-                  "TFLOPs": fl_h / st["kernel_ms"] / 1e9, "frac_fp64": fl_h / st["kernel_ms"] / 1e9 / FP64_PEAK,
-                  "accept": st["accept_rate"], "steps_mean": st["steps_mean"]}
+    names = {1: "two-GEMM (K6')", 2: "on-chip dense (K6)", 3: "structure-aware (K6s)"}
+    out["hmc"] = {"kernel": names[st["kernel_variant"]], "chains": chains, "ms": st["kernel_ms"], "rows_used": st["rows_used"], "zl_nonzeros": st["zl_nonzeros"],
+                  "leapfrog_per_s": st["leapfrog_total"] / st["kernel_ms"] * 1e3,
+                  "algorithmic_TFLOPs": fl_h / st["kernel_ms"] / 1e9, "accept": st["accept_rate"], "steps_mean": st["steps_mean"]}
+    if st["kernel_variant"] != 3:
+        out["hmc"]["frac_fp64"] = fl_h / st["kernel_ms"] / 1e9 / FP64_PEAK
+    else:
+        # the dense kernel on the same model, for reference (fewer proposals: it is orders of magnitude slower here)
+        g.hmc_set_variant(1)
+        try:
+            rd = mdl.hmc_sample(None, beta, sig, warmup=1, nsamp_per_chain=1, lam=0.05, max_steps=10, target_accept=0.9, n_chains=chains, seed=2,
+                                keep_on_device=True, want_u=False)["stats"]
+        finally:
+            g.hmc_set_variant(0)
+        fd = rd["leapfrog_total"] * 4.0 * n * Q
+        out["hmc"]["dense_kernel"] = {"kernel": names[rd["kernel_variant"]], "ms": rd["kernel_ms"], "leapfrog_per_s": rd["leapfrog_total"] / rd["kernel_ms"] * 1e3,
+                                      "TFLOPs": fd / rd["kernel_ms"] / 1e9, "frac_fp64": fd / rd["kernel_ms"] / 1e9 / FP64_PEAK}
+        res = mdl.hmc_sample(None, beta, sig, warmup=hw, nsamp_per_chain=hn, lam=0.05, max_steps=10, target_accept=0.9, n_chains=chains, seed=2,
+                             keep_on_device=True, want_u=False)
     # K1: zd = Z u for the sampler's device-resident draws (chains * (hn + 1) columns)
     mh = chains * (hn + 1)
     ctx.sync(); ctx.timer_start(); mdl.use_device_u(); t = ctx.timer_stop()
