@@ -44,6 +44,11 @@ def estep_set_multi(on: bool):
     check(lib().gmb_estep_set_multi(int(bool(on))))
 
 
+def hmc_set_components(on: bool):
+    """Large sparse models: trajectory decomposed over the connected components of Z L (default) or one CTA per chain (gmb_hmc_set_components)."""
+    check(lib().gmb_hmc_set_components(int(bool(on))))
+
+
 def hmc_set_variant(variant: int):
     """0 = automatic, 1 = two-GEMM sampler kernels, 2 = on-chip sampler kernel (see gmb_hmc_set_variant)."""
     check(lib().gmb_hmc_set_variant(int(variant)))

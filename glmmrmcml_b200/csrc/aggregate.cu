@@ -74,7 +74,7 @@ int gmb_agg_ensure(gmb_model* mdl) {
     gmb_agg& a = mdl->agg;
     if (a.built && a.flag == gmb_agg_enabled()) return GMB_OK;
     if (a.built) gmb_agg_free(mdl);
-    mdl->ell.checked = mdl->ell.valid = false;      // the sparse form describes the view
+    gmb_sparse_invalidate(mdl);                      // the sparse forms describe the view
     a.flag = gmb_agg_enabled();
     gmb_ctx* ctx = mdl->ctx;
     const int n = mdl->n, P = mdl->P, Q = mdl->Q, ldn = mdl->ldn, fl = mdl->flink;

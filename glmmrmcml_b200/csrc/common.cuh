@@ -95,6 +95,14 @@ struct gmb_ell {
     int* dcnt = nullptr; size_t cnt_cap = 0;     // per-row / per-column counts
 };
 
+// connected components of the view's Z L packed into groups of <= 32 rows / columns (hmc_comp.cu)
+struct gmb_comp {
+    bool checked = false, valid = false;
+    int G = 0, W = 0, ncomp = 0;
+    int* dint = nullptr; size_t int_cap = 0;     // grow | gcol | lrc | lcr
+    double* dval = nullptr; size_t val_cap = 0;  // lrv | lcv
+};
+
 struct gmb_model {
     gmb_ctx* ctx = nullptr;
     int n = 0, P = 0, Q = 0, flink = 0;
@@ -126,6 +134,7 @@ struct gmb_model {
     size_t v_cap = 0;
     gmb_agg agg;                 // row aggregation for the on-chip sampler
     gmb_ell ell;                 // sparse form of the view's Z L (structure-aware sampler)
+    gmb_comp comp;               // its connected components (large sparse models)
     double* hmc_work = nullptr;  // chain state + work buffers of the sampler
     size_t hmc_work_doubles = 0;
 };
@@ -201,6 +210,11 @@ int gmb_agg_enabled();
 // hmc_sparse.cu
 void gmb_ell_free(gmb_model* mdl);
 int gmb_ell_ensure(gmb_model* mdl);
+// hmc_comp.cu
+void gmb_comp_free(gmb_model* mdl);
+int gmb_comp_ensure(gmb_model* mdl);
+// the sparse forms describe the view's current Z L: call whenever it changes
+static inline void gmb_sparse_invalidate(gmb_model* mdl) { mdl->ell.checked = mdl->ell.valid = false; mdl->comp.checked = mdl->comp.valid = false; }
 
 // optim.cpp: gmb_minimize_bounded / gmb_fd_gradient / gmb_fd_hessian are declared in the public header
 

@@ -288,7 +288,7 @@ int gmb_hmc_prepare(gmb_model* mdl, const double* L_host) {
     if (L_host) GMB_CUDA(cudaStreamSynchronize(ctx->stream));
     mdl->zl_valid = true;
     mdl->agg.zl_valid = false;
-    mdl->ell.checked = mdl->ell.valid = false;
+    gmb_sparse_invalidate(mdl);
     return GMB_OK;
 }
 
@@ -354,6 +354,15 @@ size_t gmb_hmc_sparse_work_doubles(const gmb_model* mdl, int C);
 int gmb_hmc_run_sparse(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                        int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs);
 
+// hmc_comp.cu
+bool gmb_hmc_comp_applicable(const gmb_model* mdl);
+size_t gmb_hmc_comp_work_doubles(const gmb_model* mdl, int C);
+int gmb_hmc_run_comp(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
+                     int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* work);
+// 1 (default) = large sparse models run the component-decomposed kernels (hmc_comp.cu), 0 = the CTA-per-chain kernel (hmc_sparse.cu)
+static int g_hmc_components = 1;
+extern "C" int gmb_hmc_set_components(int on) { g_hmc_components = on ? 1 : 0; return GMB_OK; }
+
 // 0 = choose (structure-aware kernels when Z L is sparse enough, else the on-chip variant when the model fits one SM's shared memory,
 // else two GEMMs per step), 1 = force the two-GEMM variant, 2 = force on-chip, 3 = force structure-aware
 static int g_hmc_variant = 0;
@@ -366,14 +375,17 @@ extern "C" int gmb_hmc_set_variant(int variant) {
 static int hmc_run_fused_timed(gmb_model* mdl, bool sparse, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                                int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, std::vector<double>* host_cs, float* ms) {
     gmb_ctx* ctx = mdl->ctx;
-    const size_t need = sparse ? gmb_hmc_sparse_work_doubles(mdl, C) : gmb_hmc_fused_cs_doubles(C) + gmb_hmc_fused_scratch_doubles(mdl, C);
+    const bool comp = sparse && g_hmc_components && gmb_hmc_comp_applicable(mdl);
+    const size_t need = comp ? gmb_hmc_comp_work_doubles(mdl, C)
+                             : (sparse ? gmb_hmc_sparse_work_doubles(mdl, C) : gmb_hmc_fused_cs_doubles(C) + gmb_hmc_fused_scratch_doubles(mdl, C));
     if (need > mdl->hmc_work_doubles) {
         if (mdl->hmc_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, mdl->hmc_work); mdl->hmc_work = nullptr; mdl->hmc_work_doubles = 0; }
         GMB_CUDA(gmb_dmalloc(ctx, &mdl->hmc_work, need * sizeof(double)));
         mdl->hmc_work_doubles = need;
     }
     GMB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (sparse) GMB_TRY(gmb_hmc_run_sparse(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
+    if (comp) GMB_TRY(gmb_hmc_run_comp(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
+    else if (sparse) GMB_TRY(gmb_hmc_run_sparse(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
     else GMB_TRY(gmb_hmc_run_fused(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
     GMB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     if (host_cs) {
@@ -429,7 +441,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     if (L) GMB_TRY(gmb_hmc_prepare(mdl, L));
     GMB_TRY(agg_update_zl(mdl));
     const bool try_sparse = g_hmc_variant == 0 || g_hmc_variant == 3;
-    if (try_sparse) GMB_TRY(gmb_ell_ensure(mdl));
+    if (try_sparse) { GMB_TRY(gmb_ell_ensure(mdl)); GMB_TRY(gmb_comp_ensure(mdl)); }
     GMB_TRY(set_xb(mdl, beta));
     const int C = n_chains, cols = nsamp_per_chain + 1;
     const size_t ncol = (size_t)C * cols;
@@ -468,6 +480,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
         stats->kernel_variant = sparse ? 3 : (fused ? 2 : 1);
         stats->rows_used = ((sparse || fused) && mdl->agg.built) ? mdl->agg.ng : mdl->n;
         stats->zl_nonzeros = sparse ? (double)mdl->ell.nnz : (double)stats->rows_used * mdl->Q;
+        stats->component_groups = (sparse && g_hmc_components && gmb_hmc_comp_applicable(mdl)) ? mdl->comp.G : 0;
     }
     if (V_out)
         GMB_CUDA(cudaMemcpy2DAsync(V_out, mdl->Q * sizeof(double), mdl->dV, mdl->ldq * sizeof(double), mdl->Q * sizeof(double), ncol,

@@ -16,13 +16,12 @@
 //
 // Sums run over the non-zeros in ascending column (row) order — the dense contraction without its zero terms (the register variants
 // accumulate even and odd ELL positions separately to halve the dependent chain).
-#include "common.cuh"
+#include "hmc_sparse_common.cuh"
 #include <algorithm>
 #include <type_traits>
 
 namespace {
 
-enum { SP_EPS = 0, SP_EBAR, SP_H, SP_LLCUR, SP_K0, SP_ACCEPT, SP_TOTSTEPS, SP_LASTPROB, SP_COUNT };   // = CS_* of hmc.cu
 
 constexpr int SP_CPB = 4;        // chains (warps) per CTA, warp-per-chain variants
 constexpr int SP_MAXW = 8;       // ELL width up to which the entries of a lane's rows / columns are kept in registers
@@ -92,73 +91,6 @@ __global__ void ell_fill_cols_kernel(int ng, int Q, int qp, int ld, int wc, cons
         }
     }
     for (int w = base + lane; w < wc; w += 32) { cv[(size_t)w * qp + j] = 0.0; cr[(size_t)w * qp + j] = first; }
-}
-
-// dev_family_resid_w (common.cuh) for N rows at once, written stage by stage across the rows so that their dependent chains overlap (the sparse sampler runs one or
-// two warps per scheduler: nothing else hides the ~20 dependent FP64 operations of exp + reciprocal).  Per row: the operations of
-// dev_family_resid_w in the same order, hence the same bits.
-// Constants come from the constant bank as direct DFMA operands (literals cost two UMOV each per use inside the step loop: 8 % of the
-// issued instructions in the first profile of this kernel).
-static __constant__ double SP_EXPC[10] = {
-    92.33248261689366,              // 0: 64 / ln2
-    6755399441055744.0,             // 1: 1.5 * 2^52 (round to nearest integer by addition)
-    -0.010830424667801708,          // 2: -ln2/64 high part
-    -2.8447437476627285e-11,        // 3: -ln2/64 low part
-    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0,   // 4..8
-    0.0};
-template <int FL, int N>
-__device__ __forceinline__ void dev_family_resid_w_vec(const double (&c)[N], const double (&ys)[N], const double (&eta)[N],
-                                                       const double* __restrict__ tab, double (&out)[N]) {
-    if (FL == 7) {
-#pragma unroll
-        for (int k = 0; k < N; k++) out[k] = fma(-c[k], eta[k], ys[k]);
-        return;
-    }
-    const double* cc = SP_EXPC;
-    double t[N], r[N], T[N], q[N], e[N];
-    int kk[N];
-#pragma unroll
-    for (int k = 0; k < N; k++) t[k] = fma(eta[k], cc[0], cc[1]);
-#pragma unroll
-    for (int k = 0; k < N; k++) { kk[k] = __double2loint(t[k]); t[k] -= cc[1]; }
-#pragma unroll
-    for (int k = 0; k < N; k++) { T[k] = tab[kk[k] & 63]; r[k] = fma(t[k], cc[2], eta[k]); }
-#pragma unroll
-    for (int k = 0; k < N; k++) r[k] = fma(t[k], cc[3], r[k]);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = fma(r[k], cc[4], cc[5]);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = fma(q[k], r[k], cc[6]);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = fma(q[k], r[k], cc[7]);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = fma(q[k], r[k], cc[8]);
-#pragma unroll
-    for (int k = 0; k < N; k++) q[k] = q[k] * r[k];
-#pragma unroll
-    for (int k = 0; k < N; k++) {
-        const double m = fma(T[k], q[k], T[k]);
-        const int ks = min(max(kk[k], -64512), 64512);
-        e[k] = __hiloint2double(__double2hiint(m) + ((ks >> 6) << 20), __double2loint(m));
-    }
-    if (FL == 1) {
-#pragma unroll
-        for (int k = 0; k < N; k++) out[k] = fma(-c[k], e[k], ys[k]);
-        return;
-    }
-    double d[N], y[N], f[N];
-#pragma unroll
-    for (int k = 0; k < N; k++) { d[k] = e[k] + cc[8]; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[k]) : "d"(d[k])); }
-#pragma unroll
-    for (int k = 0; k < N; k++) f[k] = fma(-d[k], y[k], cc[8]);
-#pragma unroll
-    for (int k = 0; k < N; k++) y[k] = fma(y[k], f[k], y[k]);
-#pragma unroll
-    for (int k = 0; k < N; k++) f[k] = fma(-d[k], y[k], cc[8]);
-#pragma unroll
-    for (int k = 0; k < N; k++) y[k] = fma(y[k], f[k], y[k]);
-#pragma unroll
-    for (int k = 0; k < N; k++) out[k] = fma(c[k], y[k], ys[k]);
 }
 
 // ---- the sampler ----

@@ -127,6 +127,7 @@ typedef struct gmb_hmc_stats {
     int    rows_used;        /* rows the sampler ran on: n, or the number of distinct rows of [X | Z] when aggregated */
     int    kernel_variant;   /* 1 = two-GEMM, 2 = on-chip, 3 = structure-aware (sparse Z L) */
     double zl_nonzeros;      /* entries of Z L the kernel works on per leapfrog step and chain: non-zeros (variant 3) or rows_used * Q */
+    int    component_groups; /* variant 3 on a large model: groups of connected components of Z L the trajectory is decomposed into (else 0) */
 } gmb_hmc_stats;
 
 /* Runs n_chains independent copies of mcmcRunHMC::sample(warmup, .) (mhmcmc.h:121-157), each with its own
@@ -146,6 +147,10 @@ int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* beta, double v
  * leapfrog step), 1 = force the two-GEMM variant, 2 = force the on-chip one, 3 = force the structure-aware one.
  * All variants follow the same chain arithmetic and the same random streams. */
 int gmb_hmc_set_variant(int variant);
+
+/* Structure-aware sampler on large models: 1 (default) = decompose the trajectory over the connected components of Z L (one warp per chain and
+ * group of components, two launches per proposal), 0 = one CTA per chain streaming the sparse Z L on every leapfrog step. */
+int gmb_hmc_set_components(int on);
 
 /* On-chip sampler: CTAs per group of 8 chains.  0 = automatic (per run: the cluster size with the shortest estimated
  * leapfrog step among those whose share of Z L fits one SM's shared memory), 1 = one CTA per group, 2 / 4 = the

@@ -172,17 +172,29 @@ SPARSE_CASES = {
     "C2-warp-regs": (lambda: synth.config2(m=4), "binomial"),
     "wide-blocks-warp-smem-ell": (lambda: synth.config4(ncl=5, nt=12, k=2, m=4), "poisson"),       # 12 x 12 blocks: ELL width 12 > 8
     "ragged-warp-4-per-lane": (lambda: synth.config4(ncl=13, nt=7, k=3, m=4), "poisson"),          # Q = 91
-    "C4-cta128": (lambda: synth.config4(ncl=30, nt=10, k=2, m=4), "poisson"),                      # Q = 300
-    "C4-cta512": (lambda: synth.config4(ncl=110, nt=10, k=1, m=4), "poisson"),                     # Q = 1100
+    "C4-cta128": (lambda: synth.config4(ncl=30, nt=10, k=2, m=4), "poisson"),                      # Q = 300, one CTA per chain
+    "C4-cta512": (lambda: synth.config4(ncl=110, nt=10, k=1, m=4), "poisson"),                     # Q = 1100, one CTA per chain
+    "C4-components": (lambda: synth.config4(ncl=30, nt=10, k=2, m=4), "poisson"),                  # Q = 300: 30 components in 10 groups
+    "C4-components-ragged": (lambda: synth.config4(ncl=57, nt=7, k=1, m=4), "poisson"),            # Q = 399: 57 components of 7, groups of 4
+    "C1-like-components": (lambda: synth.config1(m=4, ncl=40, nt=5, nind=3), "binomial"),          # Q = 240: components of 5 rows x 6 columns
 }
 
 
 @pytest.mark.parametrize("name", list(SPARSE_CASES))
 def test_structure_aware_sampler_follows_oracle(gctx, oracle, name):
-    """The structure-aware kernels (sparse Z L in ELL form, hmc_sparse.cu) in every size class: the dispatcher picks them without being
-    asked, they work on the non-zeros only, and the chains reproduce the oracle's dense chains under the same Philox stream."""
+    """The structure-aware kernels (sparse Z L in ELL form, hmc_sparse.cu; trajectories decomposed over the connected components of Z L,
+    hmc_comp.cu) in every size class: the dispatcher picks them without being asked, they work on the non-zeros only, and the chains
+    reproduce the oracle's dense chains under the same Philox stream."""
     import glmmrmcml_b200 as g
     cfg = SPARSE_CASES[name][0]()
+    g.hmc_set_components("components" in name)
+    try:
+        _structure_aware_case(gctx, oracle, g, cfg, "components" in name)
+    finally:
+        g.hmc_set_components(True)
+
+
+def _structure_aware_case(gctx, oracle, g, cfg, want_components):
     fl = oracle.flink(cfg["family"], cfg["link"])
     mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
     ZL = cfg["Z"] @ cfg["L"]; xb = cfg["X"] @ cfg["beta"]
@@ -191,6 +203,7 @@ def test_structure_aware_sampler_follows_oracle(gctx, oracle, name):
                          n_chains=nch, chain_offset=2, seed=seed, want_u=True, want_v=True)
     st = out["stats"]
     assert st["kernel_variant"] == 3
+    assert (st["component_groups"] >= 2) == want_components
     rows = np.unique(np.hstack([cfg["X"], cfg["Z"]]), axis=0).shape[0]
     assert st["rows_used"] == min(rows, cfg["n"]) or st["rows_used"] == cfg["n"]
     ZLv = ZL if st["rows_used"] == cfg["n"] else np.unique(np.hstack([cfg["X"], ZL]), axis=0)[:, cfg["X"].shape[1]:]
