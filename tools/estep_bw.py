@@ -21,9 +21,10 @@ for fam in fams:
     mdl.set_u(U)
     B = np.asfortranarray(np.repeat(cfg["beta"][:, None], 8, axis=1) + 1e-6 * np.arange(8)[None, :])
     g.estep_set_rowstats(False)                      # the stream itself (poisson / gaussian default to O(n) row-statistic evaluations)
+    g.estep_set_multi(False)                         # ... one launch per evaluation (binomial batches default to 8 evaluations per pass)
     mdl.log_likelihood_batch(B[:, :4], np.ones(4))
     ctx.timer_start(); mdl.log_likelihood_batch(B, np.ones(8)); t = ctx.timer_stop() / 8
-    g.estep_set_rowstats(True)
+    g.estep_set_rowstats(True); g.estep_set_multi(True)
     mdl.log_likelihood_batch(B[:, :4], np.ones(4))
     ctx.timer_start(); mdl.log_likelihood_batch(B, np.ones(8)); t_default = ctx.timer_stop() / 8
     by = 8.0 * n * mbig + 16.0 * n

@@ -13,7 +13,7 @@ ncu --set full --clock-control none --import-source on -k regex:"hmc_fused|hmc_s
     python tools/profile_hmc.py > gpurun_out/ncu_hmc.log 2>&1
 echo "hmc full rc=$?"
 python tools/profile_kernels.py estep > gpurun_out/plain_prof.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:'loglik|mcnr_pass1' -c 5 -o gpurun_out/prof_estep_${TAG} -f \
+ncu --set full --clock-control none --import-source on -k regex:'loglik|mcnr_pass1' -c 6 -o gpurun_out/prof_estep_${TAG} -f \
     python tools/profile_kernels.py estep > gpurun_out/ncu_prof.log 2>&1
 echo "estep full rc=$?"
 tail -n 2 gpurun_out/plain_hmc.log gpurun_out/plain_prof.log

@@ -23,6 +23,8 @@ if which in ("all", "estep"):
         mdl.log_likelihood(cfg["beta"], 1.0)
     for _ in range(2):
         mdl.mcnr(cfg["beta"], 1.0)
+    B = np.asfortranarray(np.repeat(cfg["beta"][:, None], 16, axis=1) * (1 + 1e-6 * np.arange(16))[None, :])
+    mdl.log_likelihood_batch(B, np.ones(16))        # the batched kernel: 16 evaluations in one launch, 8 per pass over the matrix
     mdl.close()
 if which in ("all", "hmc"):
     mdl = g.Model(ctx, cfg["X"], cfg["Z"], cfg["y"], "binomial", "logit")
