@@ -49,6 +49,11 @@ def hmc_set_components(on: bool):
     check(lib().gmb_hmc_set_components(int(bool(on))))
 
 
+def hmc_set_factored(on: bool):
+    """Two-GEMM sampler: apply a sparse Z and the dense factor L separately (default) or contract with the dense Z L (gmb_hmc_set_factored)."""
+    check(lib().gmb_hmc_set_factored(int(bool(on))))
+
+
 def hmc_set_variant(variant: int):
     """0 = automatic, 1 = two-GEMM sampler kernels, 2 = on-chip sampler kernel (see gmb_hmc_set_variant)."""
     check(lib().gmb_hmc_set_variant(int(variant)))

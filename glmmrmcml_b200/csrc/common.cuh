@@ -135,6 +135,7 @@ struct gmb_model {
     gmb_agg agg;                 // row aggregation for the on-chip sampler
     gmb_ell ell;                 // sparse form of the view's Z L (structure-aware sampler)
     gmb_comp comp;               // its connected components (large sparse models)
+    gmb_ell zell;                // sparse form of Z itself (factored sampler: Z sparse, L dense)
     double* hmc_work = nullptr;  // chain state + work buffers of the sampler
     size_t hmc_work_doubles = 0;
 };
@@ -210,6 +211,7 @@ int gmb_agg_enabled();
 // hmc_sparse.cu
 void gmb_ell_free(gmb_model* mdl);
 int gmb_ell_ensure(gmb_model* mdl);
+int gmb_zell_ensure(gmb_model* mdl);
 // hmc_comp.cu
 void gmb_comp_free(gmb_model* mdl);
 int gmb_comp_ensure(gmb_model* mdl);

@@ -18,6 +18,10 @@
 // 2 = momentum (:62-63), 3 = accept uniform (:85).  Reproducible, unlike std::random_device at :55.
 #include "gemm_f64.cuh"
 
+// 1 (default) = the factored variant of the two-contraction sampler when Z is sparse, Z L is not and n >= 2 Q; 0 = always contract with the dense Z L
+static int g_hmc_factored = 1;
+extern "C" int gmb_hmc_set_factored(int on) { g_hmc_factored = on ? 1 : 0; return GMB_OK; }
+
 namespace {
 
 // per-chain scalar state, stored as rows of a [CS_COUNT][C] double array
@@ -214,18 +218,67 @@ __global__ void xb_kernel2(int n, int P, int ldn, const double* __restrict__ X, 
     xb[i] = s;
 }
 
+// ---- factored variant: Z sparse, L dense (Z L is dense but n >> Q, config C5: Z = indicator of the location, L a dense 5000 x 5000 factor) ----
+// eta = xb + Z (L v') and grad = -v' + s L^T (Z^T r(eta)): the two dense contractions shrink from n x Q to Q x Q (W = L V', G = L^T T) and Z is
+// applied by two gather kernels on its ELL form (by rows for eta and the residual, by columns for T = Z^T RES).
+constexpr int ZSP_CH = 4;        // chains per thread of the row kernel
+template <int FL>
+__global__ void __launch_bounds__(256) zsp_resid_kernel(int n, int ngp, int wr, int C, int ldn, int ldq, const double* __restrict__ rv,
+                                                        const int* __restrict__ rc, const double* __restrict__ W, const double* __restrict__ xb,
+                                                        const double* __restrict__ y, const double* __restrict__ rowc, double* __restrict__ RES,
+                                                        const int* __restrict__ steps, int s, double c0, double sigma, double* __restrict__ llpart) {
+    __shared__ double red[32];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const bool ok = i < n;
+    const double xbi = ok ? xb[i] : 0.0, yi = ok ? y[i] : 0.0, rci = (ok && FL == 1) ? rowc[i] : 0.0;
+    for (int cc = 0; cc < ZSP_CH; cc++) {
+        const int c = blockIdx.y * ZSP_CH + cc;
+        if (c >= C) break;
+        const bool active = steps == nullptr || s < steps[c], want_ll = steps == nullptr || s == steps[c] - 1;   // as EpiResid
+        if (!active) continue;                                       // block-uniform
+        double ll = 0.0;
+        if (ok) {
+            double eta = xbi;
+            for (int w = 0; w < wr; w++) eta = fma(rv[(size_t)w * ngp + i], W[rc[(size_t)w * ngp + i] + (size_t)c * ldq], eta);
+            RES[i + (size_t)c * ldn] = dev_family_resid<FL>(yi, eta);
+            if (want_ll) ll = dev_family_ll<FL>(yi, eta, rci, c0, sigma);
+        }
+        if (want_ll) {
+            ll = block_sum(ll, red);
+            if (threadIdx.x == 0) llpart[(size_t)blockIdx.x * C + c] = ll;
+            __syncthreads();
+        }
+    }
+}
+// T = Z^T RES for the active chains
+__global__ void __launch_bounds__(256) zsp_gather_kernel(int Q, int qp, int wc, int ldn, int ldq, const double* __restrict__ cv,
+                                                         const int* __restrict__ cr, const double* __restrict__ RES, double* __restrict__ T,
+                                                         const int* __restrict__ steps, int s) {
+    const int q = blockIdx.x * 256 + threadIdx.x, c = blockIdx.y;
+    if (q >= Q || !(steps == nullptr || s < steps[c])) return;
+    double t = 0.0;
+    for (int w = 0; w < wc; w++) t = fma(cv[(size_t)w * qp + q], RES[cr[(size_t)w * qp + q] + (size_t)c * ldn], t);
+    T[q + (size_t)c * ldq] = t;
+}
+
 struct HmcBuffers {
-    double *V, *VP, *R, *G, *GC, *RES, *llpart, *cs;
+    double *V, *VP, *R, *G, *GC, *RES, *llpart, *cs, *W, *T;
     int *steps, *max_seen;
     int row_tiles;
+    bool factored;
 };
+
+static bool factored_applicable(const gmb_model* mdl) {
+    return g_hmc_factored && mdl->zell.checked && mdl->zell.valid && mdl->n >= 2 * mdl->Q && mdl->dL != nullptr;
+}
 
 int hmc_layout(gmb_model* mdl, int C, HmcBuffers& b) {
     gmb_ctx* ctx = mdl->ctx;
     const size_t ldq = mdl->ldq, ldn = mdl->ldn;
     const int rt = gmbgemm::row_tile(ctx, mdl->n, C);
-    b.row_tiles = (mdl->n + rt - 1) / rt;
-    size_t need = 5 * ldq * C + ldn * C + (size_t)b.row_tiles * C + (size_t)CS_COUNT * C + (size_t)C /*steps as ints*/ + 16;
+    b.factored = factored_applicable(mdl);
+    b.row_tiles = b.factored ? (mdl->n + 255) / 256 : (mdl->n + rt - 1) / rt;
+    size_t need = 7 * ldq * C + ldn * C + (size_t)b.row_tiles * C + (size_t)CS_COUNT * C + (size_t)C /*steps as ints*/ + 16;
     if (need > mdl->hmc_work_doubles) {
         if (mdl->hmc_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, mdl->hmc_work); mdl->hmc_work = nullptr; mdl->hmc_work_doubles = 0; }
         GMB_CUDA(gmb_dmalloc(ctx, &mdl->hmc_work, need * sizeof(double)));
@@ -234,6 +287,7 @@ int hmc_layout(gmb_model* mdl, int C, HmcBuffers& b) {
     GMB_CUDA(cudaMemsetAsync(mdl->hmc_work, 0, need * sizeof(double), ctx->stream));
     double* p = mdl->hmc_work;
     b.V = p; p += ldq * C; b.VP = p; p += ldq * C; b.R = p; p += ldq * C; b.G = p; p += ldq * C; b.GC = p; p += ldq * C;
+    b.W = p; p += ldq * C; b.T = p; p += ldq * C;
     b.RES = p; p += ldn * C; b.llpart = p; p += (size_t)b.row_tiles * C; b.cs = p; p += (size_t)CS_COUNT * C;
     b.steps = reinterpret_cast<int*>(p); p += (C + 1) / 2 + 1;
     b.max_seen = reinterpret_cast<int*>(p);
@@ -250,7 +304,29 @@ int launch_resid(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, con
     return gmbgemm::dispatch<false, true>(mdl->ctx, mdl->n, C, mdl->Q, mdl->dZL, mdl->ldn, b.VP, mdl->ldq, epi);
 }
 
+template <int FL>
+int launch_resid_factored(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, const int* steps, int s) {
+    gmb_ctx* ctx = mdl->ctx;
+    const gmb_ell& e = mdl->zell;
+    GMB_TRY(gmb_dgemm(ctx, 0, 0, mdl->Q, C, mdl->Q, 1.0, mdl->dL, mdl->ldq, b.VP, mdl->ldq, 0.0, b.W, mdl->ldq));      // W = L V'
+    const double c0 = (FL == 7) ? (-1.0 * log(var_par) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
+    zsp_resid_kernel<FL><<<dim3((mdl->n + 255) / 256, (C + ZSP_CH - 1) / ZSP_CH), 256, 0, ctx->stream>>>(
+        mdl->n, e.ngp, e.wr, C, mdl->ldn, mdl->ldq, e.rv, e.rc, b.W, mdl->dxb, mdl->dy, mdl->drowc, b.RES, steps, s, c0, var_par, b.llpart);
+    zsp_gather_kernel<<<dim3((mdl->Q + 255) / 256, C), 256, 0, ctx->stream>>>(mdl->Q, e.qp, e.wc, mdl->ldn, mdl->ldq, e.cv, e.cr, b.RES, b.T, steps, s);
+    ctx->launches += 2;
+    GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}
+
 int launch_resid_fl(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, const int* steps, int s) {
+    if (b.factored) {
+        switch (mdl->flink) {
+        case 1: return launch_resid_factored<1>(mdl, C, b, var_par, steps, s);
+        case 3: return launch_resid_factored<3>(mdl, C, b, var_par, steps, s);
+        case 7: return launch_resid_factored<7>(mdl, C, b, var_par, steps, s);
+        }
+        return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
+    }
     switch (mdl->flink) {
     case 1: return launch_resid<1>(mdl, C, b, var_par, steps, s);
     case 3: return launch_resid<3>(mdl, C, b, var_par, steps, s);
@@ -263,6 +339,8 @@ int launch_leap(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, int 
     EpiLeapfrog epi;
     epi.VP = b.VP; epi.R = b.R; epi.G = b.G; epi.ldq = mdl->ldq; epi.steps = b.steps; epi.eps = b.cs + (size_t)CS_EPS * C;
     epi.s = s; epi.sc = (mdl->flink == 7) ? 1.0 / (var_par * var_par) : 1.0; epi.init = init;
+    if (b.factored)     // G = -V' + s L^T T, T = Z^T RES
+        return gmbgemm::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->Q, mdl->dL, mdl->ldq, b.T, mdl->ldq, epi);
     return gmbgemm::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->n, mdl->dZL, mdl->ldn, b.RES, mdl->ldn, epi);
 }
 
@@ -462,9 +540,11 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     if (sparse || (fits && g_hmc_variant != 1))
         GMB_TRY(hmc_run_fused_timed(mdl, sparse, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
                                     mdl->dV, stats ? &hcs : nullptr, &ms));
-    else
+    else {
+        if (g_hmc_factored && mdl->n >= 2 * mdl->Q) GMB_TRY(gmb_zell_ensure(mdl));
         GMB_TRY(hmc_run(mdl, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
                         mdl->dV, stats ? &hcs : nullptr, &ms));
+    }
     if (stats) {
         double acc = 0, eps = 0, tot = 0;
         for (int c = 0; c < C; c++) { acc += hcs[(size_t)CS_ACCEPT * C + c]; eps += hcs[(size_t)CS_EPS * C + c]; tot += hcs[(size_t)CS_TOTSTEPS * C + c]; }
@@ -480,6 +560,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
         stats->kernel_variant = sparse ? 3 : (fused ? 2 : 1);
         stats->rows_used = ((sparse || fused) && mdl->agg.built) ? mdl->agg.ng : mdl->n;
         stats->zl_nonzeros = sparse ? (double)mdl->ell.nnz : (double)stats->rows_used * mdl->Q;
+        stats->factored = (!sparse && !fused && factored_applicable(mdl)) ? 1 : 0;
         stats->component_groups = (sparse && g_hmc_components && gmb_hmc_comp_applicable(mdl)) ? mdl->comp.G : 0;
     }
     if (V_out)

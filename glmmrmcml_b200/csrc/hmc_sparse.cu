@@ -19,6 +19,7 @@
 #include "hmc_sparse_common.cuh"
 #include <algorithm>
 #include <type_traits>
+#include <initializer_list>
 
 namespace {
 
@@ -496,23 +497,17 @@ int ensure_cap(gmb_ctx* ctx, T** ptr, size_t* cap, size_t need) {
 }  // namespace
 
 void gmb_ell_free(gmb_model* mdl) {
-    gmb_ell& e = mdl->ell;
     gmb_ctx* ctx = mdl->ctx;
-    gmb_dfree(ctx, e.rv); gmb_dfree(ctx, e.rc); gmb_dfree(ctx, e.cv); gmb_dfree(ctx, e.cr); gmb_dfree(ctx, e.dcnt);
-    e = gmb_ell();
+    for (gmb_ell* e : {&mdl->ell, &mdl->zell}) {
+        gmb_dfree(ctx, e->rv); gmb_dfree(ctx, e->rc); gmb_dfree(ctx, e->cv); gmb_dfree(ctx, e->cr); gmb_dfree(ctx, e->dcnt);
+        *e = gmb_ell();
+    }
 }
 
-// Sparse form of the sampler's view of Z L (rebuilt whenever the factor changes).  The structure-aware kernels apply when few enough
+// Sparse (ELL) form of a dense device matrix; gmb_ell_ensure: of the sampler's view of Z L (rebuilt whenever the factor changes).  The structure-aware kernels apply when few enough
 // entries of the view are non-zero and the ELL padding stays within a small multiple of the non-zeros (no dense row or column).
-int gmb_ell_ensure(gmb_model* mdl) {
-    gmb_ell& e = mdl->ell;
-    if (e.checked) return GMB_OK;
-    gmb_ctx* ctx = mdl->ctx;
-    const gmb_agg& a = mdl->agg;
+int gmb_ell_build(gmb_ctx* ctx, const double* A, int ld, int ng, int Q, gmb_ell& e) {
     e.valid = false;
-    if (!a.built) return gmb_set_error(GMB_ESTATE, "structure-aware sampler: the row view of the model has not been built");
-    const double* A = a.active ? a.dZL : mdl->dZL;
-    const int ng = a.ng, ld = a.ldn, Q = mdl->Q;
     e.ng = ng; e.Q = Q; e.ngp = round_up(ng, 32); e.qp = round_up(Q, 32);
     // two slots of run-time widths per thread in the register variants need zero-filled padding rows / columns up to 64
     if (std::max(ng, Q) <= 64) { e.ngp = 64; e.qp = 64; }
@@ -545,6 +540,22 @@ int gmb_ell_ensure(gmb_model* mdl) {
     GMB_CUDA(cudaGetLastError());
     e.valid = true;
     return GMB_OK;
+}
+
+int gmb_ell_ensure(gmb_model* mdl) {
+    gmb_ell& e = mdl->ell;
+    if (e.checked) return GMB_OK;
+    const gmb_agg& a = mdl->agg;
+    e.valid = false;
+    if (!a.built) return gmb_set_error(GMB_ESTATE, "structure-aware sampler: the row view of the model has not been built");
+    return gmb_ell_build(mdl->ctx, a.active ? a.dZL : mdl->dZL, a.ldn, a.ng, mdl->Q, e);
+}
+
+// sparse form of Z itself (all n rows; Z never changes): the factored two-contraction sampler of hmc.cu applies Z and L separately
+int gmb_zell_ensure(gmb_model* mdl) {
+    gmb_ell& e = mdl->zell;
+    if (e.checked) return GMB_OK;
+    return gmb_ell_build(mdl->ctx, mdl->dZ, mdl->ldn, mdl->n, mdl->Q, e);
 }
 
 // true when the structure-aware kernels can run the model's current Z L (gmb_ell_ensure must have been called)

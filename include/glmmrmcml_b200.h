@@ -128,6 +128,7 @@ typedef struct gmb_hmc_stats {
     int    kernel_variant;   /* 1 = two-GEMM, 2 = on-chip, 3 = structure-aware (sparse Z L) */
     double zl_nonzeros;      /* entries of Z L the kernel works on per leapfrog step and chain: non-zeros (variant 3) or rows_used * Q */
     int    component_groups; /* variant 3 on a large model: groups of connected components of Z L the trajectory is decomposed into (else 0) */
+    int    factored;         /* variant 1 with Z applied in sparse form and L as the dense operand (Q x Q contractions instead of n x Q) */
 } gmb_hmc_stats;
 
 /* Runs n_chains independent copies of mcmcRunHMC::sample(warmup, .) (mhmcmc.h:121-157), each with its own
@@ -151,6 +152,10 @@ int gmb_hmc_set_variant(int variant);
 /* Structure-aware sampler on large models: 1 (default) = decompose the trajectory over the connected components of Z L (one warp per chain and
  * group of components, two launches per proposal), 0 = one CTA per chain streaming the sparse Z L on every leapfrog step. */
 int gmb_hmc_set_components(int on);
+
+/* Two-GEMM sampler: 1 (default) = when Z is sparse, Z L is dense and n >= 2 Q, apply Z and L separately (W = L V', gather by the rows of Z,
+ * residual, gather by its columns, G = L^T T: contractions of size Q x Q instead of n x Q); 0 = always contract with the dense n x Q matrix Z L. */
+int gmb_hmc_set_factored(int on);
 
 /* On-chip sampler: CTAs per group of 8 chains.  0 = automatic (per run: the cluster size with the shortest estimated
  * leapfrog step among those whose share of Z L fits one SM's shared memory), 1 = one CTA per group, 2 / 4 = the

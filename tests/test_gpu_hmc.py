@@ -253,3 +253,52 @@ def test_structure_aware_sampler_gaussian_and_dense_fallback(gctx, oracle):
     finally:
         g.hmc_set_variant(0)
     mdl.close()
+
+
+def test_factored_two_contraction_sampler(gctx, oracle):
+    """Z sparse, L dense (C5: Z = indicator of the location, one dense covariance block, n = nobs * Q): the two-GEMM sampler applies Z in ELL
+    form and contracts with the Q x Q factor instead of the n x Q matrix Z L.  Same chains as the dense contraction and as the oracle."""
+    import glmmrmcml_b200 as g
+    cfg = synth.config5(nloc=70, nobs=4, m=4)                       # n = 280, Q = 70
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    ZL = cfg["Z"] @ cfg["L"]; xb = cfg["X"] @ cfg["beta"]
+    kw = dict(warmup=10, nsamp_per_chain=4, lam=0.05, max_steps=20, target_accept=0.85, n_chains=7, chain_offset=1, seed=31, want_u=False, want_v=True)
+    outs = {}
+    g.hmc_set_variant(1)
+    try:
+        for on in (True, False):
+            g.hmc_set_factored(on)
+            outs[on] = mdl.hmc_sample(cfg["L"], cfg["beta"], 1.0, **kw)
+    finally:
+        g.hmc_set_factored(True); g.hmc_set_variant(0)
+    assert outs[True]["stats"]["kernel_variant"] == 1 and outs[True]["stats"]["factored"] == 1 and outs[False]["stats"]["factored"] == 0
+    assert np.max(np.abs(outs[True]["v"] - outs[False]["v"])) <= 1e-8
+    assert outs[True]["stats"]["accept_rate"] == outs[False]["stats"]["accept_rate"]
+    for c in (0, 6):
+        ref = oracle.hmc_chain(ZL, cfg["L"], xb, cfg["y"], 1.0, fl, 10, 4, 0.05, 20, 0.85, 31, chain=1 + c)
+        assert np.max(np.abs(outs[True]["v"][:, c * 5:(c + 1) * 5] - ref["v"])) <= 1e-7
+    # log_prob / log_grad through the same contractions
+    rng = np.random.default_rng(3)
+    V = np.asfortranarray(0.5 * rng.standard_normal((cfg["Q"], 5)))
+    g.hmc_set_variant(1)
+    try:
+        lp, G = mdl.log_prob_grad(cfg["L"], cfg["beta"], 1.0, V)
+    finally:
+        g.hmc_set_variant(0)
+    for c in range(5):
+        want = oracle.log_prob(ZL, xb, cfg["y"], 1.0, fl, V[:, c])
+        assert abs(lp[c] - want) <= 1e-10 * abs(want)
+        gw = oracle.log_grad(ZL, xb, cfg["y"], 1.0, fl, V[:, c])
+        assert np.max(np.abs(G[:, c] - gw)) <= 1e-10 * max(np.max(np.abs(gw)), 1.0)
+    mdl.close()
+    # Z = I (C3): n = Q, nothing to gain — the dense contraction stays
+    c3 = synth.config3(nloc=150, m=4)
+    mdl = g.Model(gctx, c3["X"], c3["Z"], c3["y"], "gaussian", "identity")
+    g.hmc_set_variant(1)
+    try:
+        out = mdl.hmc_sample(c3["L"], c3["beta"], 1.0, warmup=3, nsamp_per_chain=2, lam=0.5, max_steps=5, n_chains=3, seed=1, want_u=False)
+    finally:
+        g.hmc_set_variant(0)
+    assert out["stats"]["factored"] == 0
+    mdl.close()

@@ -106,7 +106,23 @@ def run(name):
     out["hmc"] = {"kernel": names[st["kernel_variant"]], "chains": chains, "ms": st["kernel_ms"], "rows_used": st["rows_used"], "zl_nonzeros": st["zl_nonzeros"],
                   "leapfrog_per_s": st["leapfrog_total"] / st["kernel_ms"] * 1e3,
                   "algorithmic_TFLOPs": fl_h / st["kernel_ms"] / 1e9, "accept": st["accept_rate"], "steps_mean": st["steps_mean"]}
-    if st["kernel_variant"] != 3:
+    out["hmc"]["factored"] = st["factored"]; out["hmc"]["component_groups"] = st["component_groups"]
+    if st["kernel_variant"] != 3 and st["factored"]:
+        # Z sparse, L dense: the contractions are Q x Q; the dense n x Q contraction on the same model for reference
+        out["hmc"]["executed_TFLOPs"] = st["leapfrog_total"] * 4.0 * Q * Q / st["kernel_ms"] / 1e9
+        out["hmc"]["frac_fp64_executed"] = out["hmc"]["executed_TFLOPs"] / FP64_PEAK
+        g.hmc_set_factored(False)
+        try:
+            rd = mdl.hmc_sample(None, beta, sig, warmup=1, nsamp_per_chain=1, lam=0.05, max_steps=10, target_accept=0.9, n_chains=chains, seed=2,
+                                keep_on_device=True, want_u=False)["stats"]
+        finally:
+            g.hmc_set_factored(True)
+        fd = rd["leapfrog_total"] * 4.0 * n * Q
+        out["hmc"]["dense_kernel"] = {"kernel": names[rd["kernel_variant"]], "ms": rd["kernel_ms"], "leapfrog_per_s": rd["leapfrog_total"] / rd["kernel_ms"] * 1e3,
+                                      "TFLOPs": fd / rd["kernel_ms"] / 1e9, "frac_fp64": fd / rd["kernel_ms"] / 1e9 / FP64_PEAK}
+        res = mdl.hmc_sample(None, beta, sig, warmup=hw, nsamp_per_chain=hn, lam=0.05, max_steps=10, target_accept=0.9, n_chains=chains, seed=2,
+                             keep_on_device=True, want_u=False)
+    elif st["kernel_variant"] != 3:
         out["hmc"]["frac_fp64"] = fl_h / st["kernel_ms"] / 1e9 / FP64_PEAK
     else:
         # the dense kernel on the same model, for reference (fewer proposals: it is orders of magnitude slower here)
