@@ -49,6 +49,11 @@ def hmc_set_components(on: bool):
     check(lib().gmb_hmc_set_components(int(bool(on))))
 
 
+def estep_set_sparse_zd(on: bool):
+    """zd = Z u by gathering through the sparse form of Z (default, when Z is sparse) or always by the dense contraction (gmb_estep_set_sparse_zd)."""
+    check(lib().gmb_estep_set_sparse_zd(int(bool(on))))
+
+
 def hmc_set_factored(on: bool):
     """Two-GEMM sampler: apply a sparse Z and the dense factor L separately (default) or contract with the dense Z L (gmb_hmc_set_factored)."""
     check(lib().gmb_hmc_set_factored(int(bool(on))))

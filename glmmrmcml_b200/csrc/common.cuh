@@ -130,6 +130,7 @@ struct gmb_model {
     double* dZL = nullptr;       // ldn x Q   (Z L)
     double* dL = nullptr;        // ldq x Q
     bool zl_valid = false;
+    bool l_lower = false;        // the factor uploaded last is lower triangular (verified on the host): its zero k tiles are skipped in the contractions
     double* dV = nullptr;        // whitened samples of the last gmb_hmc_sample, ldq x v_cap
     size_t v_cap = 0;
     gmb_agg agg;                 // row aggregation for the on-chip sampler
@@ -179,6 +180,8 @@ struct gmb_cov {
 // gemm_f64.cu : C (M x N, ldc) = alpha * op(A) * B + beta * C ; A is M x K col-major (transA=0) or K x M (transA=1)
 int gmb_dgemm(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
               const double* B, int ldb, double beta, double* C, int ldc);
+int gmb_dgemm_tri(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+                  const double* B, int ldb, double beta, double* C, int ldc, int lower_a);
 
 // estep.cu
 int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb);

@@ -30,7 +30,21 @@ struct EpiAxpby {
 
 int gmb_dgemm(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
               const double* B, int ldb, double beta, double* C, int ldc) {
+    return gmb_dgemm_tri(ctx, transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, 0);
+}
+
+// lower_a != 0: A (before op) is a lower-triangular M x M factor (K = M); the k tiles above (transA = 0) or below (transA = 1) the
+// diagonal of each row tile are skipped
+int gmb_dgemm_tri(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
+                  const double* B, int ldb, double beta, double* C, int ldc, int lower_a) {
     EpiAxpby epi{alpha, beta, C, ldc};
+    const int tri = (lower_a && M == K) ? (transA ? 2 : 1) : 0;
+    if (tri) {
+        if (!transA && !transB) return gmbgemm::dispatch<false, true>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+        if (!transA && transB) return gmbgemm::dispatch<false, false>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+        if (transA && !transB) return gmbgemm::dispatch<true, true>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+        return gmbgemm::dispatch<true, false>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+    }
     // A is k-contiguous when transposed; B is k-contiguous when NOT transposed
     if (!transA && !transB) return gmbgemm::dispatch<false, true>(ctx, M, N, K, A, lda, B, ldb, epi);
     if (!transA && transB) return gmbgemm::dispatch<false, false>(ctx, M, N, K, A, lda, B, ldb, epi);

@@ -81,7 +81,7 @@ struct OperandTile {
 
 template <int BM, int BN, int WM, int WN, bool A_KCONT, bool B_KCONT, class Epi>
 __global__ void __launch_bounds__(THREADS) dgemm_kernel(int M, int N, int K, const double* __restrict__ A, int lda,
-                                                        const double* __restrict__ B, int ldb, Epi epi) {
+                                                        const double* __restrict__ B, int ldb, Epi epi, int tri) {
     using TA = OperandTile<BM, A_KCONT>;
     using TB = OperandTile<BN, B_KCONT>;
     constexpr int WTM = BM / WM, WTN = BN / WN;       // warp tile
@@ -95,6 +95,10 @@ __global__ void __launch_bounds__(THREADS) dgemm_kernel(int M, int N, int K, con
     const int wm = warp % WM, wn = warp / WM;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int KT = (K + BK - 1) / BK;
+    // triangular operand (a Cholesky factor): tri = 1: op(A)(m, k) = 0 for k > m ; tri = 2: op(A)(m, k) = 0 for k < m (the factor read transposed).
+    // The k tiles that hold only zeros for this row tile are skipped — the same sums without their zero terms.
+    const int kt0 = (tri == 2) ? min(m0 / BK, KT) : 0;
+    const int kt1 = (tri == 1) ? min(KT, (m0 + BM + BK - 1) / BK) : KT;
 
     {   // skip tiles whose columns are all inactive (chains that finished their trajectory)
         int act = 0;
@@ -110,28 +114,28 @@ __global__ void __launch_bounds__(THREADS) dgemm_kernel(int M, int N, int K, con
 
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++) {
-        if (s < KT) {
-            TA::load(sA + s * TA::DOUBLES, A, lda, m0, s * BK, M, K, tid);
-            TB::load(sB + s * TB::DOUBLES, B, ldb, n0, s * BK, N, K, tid);
+        if (kt0 + s < kt1) {
+            TA::load(sA + s * TA::DOUBLES, A, lda, m0, (kt0 + s) * BK, M, K, tid);
+            TB::load(sB + s * TB::DOUBLES, B, ldb, n0, (kt0 + s) * BK, N, K, tid);
         }
         cp_async_commit();
     }
 
     const int fr = lane >> 2, fk = lane & 3;   // fragment row (m or n) and k within the k4 step
-    for (int kt = 0; kt < KT; kt++) {
+    for (int kt = kt0; kt < kt1; kt++) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
             int nk = kt + STAGES - 1;
-            if (nk < KT) {
-                int s = nk % STAGES;
+            if (nk < kt1) {
+                int s = (nk - kt0) % STAGES;
                 TA::load(sA + s * TA::DOUBLES, A, lda, m0, nk * BK, M, K, tid);
                 TB::load(sB + s * TB::DOUBLES, B, ldb, n0, nk * BK, N, K, tid);
             }
             cp_async_commit();
         }
-        const double* a = sA + (kt % STAGES) * TA::DOUBLES;
-        const double* b = sB + (kt % STAGES) * TB::DOUBLES;
+        const double* a = sA + ((kt - kt0) % STAGES) * TA::DOUBLES;
+        const double* b = sB + ((kt - kt0) % STAGES) * TB::DOUBLES;
 #pragma unroll
         for (int ks = 0; ks < BK; ks += 4) {
             double af[MT], bf[NT];
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(THREADS) dgemm_kernel(int M, int N, int K, con
 }
 
 template <int BM, int BN, int WM, int WN, bool AK, bool BKC, class Epi>
-int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi) {
+int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi, int tri = 0) {
     using TA = OperandTile<BM, AK>;
     using TB = OperandTile<BN, BKC>;
     size_t smem = (size_t)STAGES * (TA::DOUBLES + TB::DOUBLES) * sizeof(double);
@@ -206,7 +210,7 @@ int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const do
         configured = true;
     }
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-    kern<<<grid, THREADS, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, epi);
+    kern<<<grid, THREADS, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, epi, tri);
     ctx->launches++;
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;
@@ -219,13 +223,13 @@ inline int row_tile(gmb_ctx* ctx, int M, int N) {
 }
 
 template <bool AK, bool BKC, class Epi>
-int dispatch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi) {
+int dispatch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi, int tri = 0) {
     if (M <= 0 || N <= 0) return GMB_OK;
     if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 1) || (ldb & 1))
         return gmb_set_error(GMB_EINVAL, "dgemm: operands must be 16-byte aligned with even leading dimensions");
     // big tiles when they fill the machine, otherwise 64x64 tiles for more CTAs
-    if (row_tile(ctx, M, N) == 128) return launch<128, 128, 2, 4, AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi);
-    return launch<64, 64, 2, 4, AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi);
+    if (row_tile(ctx, M, N) == 128) return launch<128, 128, 2, 4, AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+    return launch<64, 64, 2, 4, AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
 }
 
 }  // namespace gmbgemm

@@ -269,7 +269,9 @@ struct HmcBuffers {
 };
 
 static bool factored_applicable(const gmb_model* mdl) {
-    return g_hmc_factored && mdl->zell.checked && mdl->zell.valid && mdl->n >= 2 * mdl->Q && mdl->dL != nullptr;
+    // worth it when the Q x Q contractions are at most half the n x Q ones: n >= 2 Q, or n >= Q with a triangular factor (its zero tiles are skipped)
+    return g_hmc_factored && mdl->zell.checked && mdl->zell.valid && mdl->dL != nullptr &&
+           (mdl->n >= 2 * mdl->Q || (mdl->l_lower && mdl->n >= mdl->Q));
 }
 
 int hmc_layout(gmb_model* mdl, int C, HmcBuffers& b) {
@@ -308,7 +310,7 @@ template <int FL>
 int launch_resid_factored(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, const int* steps, int s) {
     gmb_ctx* ctx = mdl->ctx;
     const gmb_ell& e = mdl->zell;
-    GMB_TRY(gmb_dgemm(ctx, 0, 0, mdl->Q, C, mdl->Q, 1.0, mdl->dL, mdl->ldq, b.VP, mdl->ldq, 0.0, b.W, mdl->ldq));      // W = L V'
+    GMB_TRY(gmb_dgemm_tri(ctx, 0, 0, mdl->Q, C, mdl->Q, 1.0, mdl->dL, mdl->ldq, b.VP, mdl->ldq, 0.0, b.W, mdl->ldq, mdl->l_lower ? 1 : 0));   // W = L V'
     const double c0 = (FL == 7) ? (-1.0 * log(var_par) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
     zsp_resid_kernel<FL><<<dim3((mdl->n + 255) / 256, (C + ZSP_CH - 1) / ZSP_CH), 256, 0, ctx->stream>>>(
         mdl->n, e.ngp, e.wr, C, mdl->ldn, mdl->ldq, e.rv, e.rc, b.W, mdl->dxb, mdl->dy, mdl->drowc, b.RES, steps, s, c0, var_par, b.llpart);
@@ -340,7 +342,7 @@ int launch_leap(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, int 
     epi.VP = b.VP; epi.R = b.R; epi.G = b.G; epi.ldq = mdl->ldq; epi.steps = b.steps; epi.eps = b.cs + (size_t)CS_EPS * C;
     epi.s = s; epi.sc = (mdl->flink == 7) ? 1.0 / (var_par * var_par) : 1.0; epi.init = init;
     if (b.factored)     // G = -V' + s L^T T, T = Z^T RES
-        return gmbgemm::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->Q, mdl->dL, mdl->ldq, b.T, mdl->ldq, epi);
+        return gmbgemm::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->Q, mdl->dL, mdl->ldq, b.T, mdl->ldq, epi, mdl->l_lower ? 2 : 0);
     return gmbgemm::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->n, mdl->dZL, mdl->ldn, b.RES, mdl->ldn, epi);
 }
 
@@ -361,6 +363,12 @@ int gmb_hmc_prepare(gmb_model* mdl, const double* L_host) {
     if (L_host) {
         GMB_CUDA(cudaMemcpy2DAsync(mdl->dL, ldq * sizeof(double), L_host, Q * sizeof(double), Q * sizeof(double), Q,
                                    cudaMemcpyHostToDevice, ctx->stream));
+        bool lower = true;                                       // a Cholesky factor is; any other square root of D takes the full contractions
+        for (size_t c = 1; c < Q && lower; c++)
+            for (size_t r = 0; r < c; r++) if (L_host[r + c * Q] != 0.0) { lower = false; break; }
+        mdl->l_lower = lower;
+    } else {
+        mdl->l_lower = false;                                    // factor written on the device by the caller: not verified
     }
     GMB_TRY(gmb_dgemm(ctx, 0, 0, mdl->n, mdl->Q, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dL, mdl->ldq, 0.0, mdl->dZL, mdl->ldn));
     if (L_host) GMB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -541,7 +549,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
         GMB_TRY(hmc_run_fused_timed(mdl, sparse, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
                                     mdl->dV, stats ? &hcs : nullptr, &ms));
     else {
-        if (g_hmc_factored && mdl->n >= 2 * mdl->Q) GMB_TRY(gmb_zell_ensure(mdl));
+        if (g_hmc_factored && mdl->n >= mdl->Q) GMB_TRY(gmb_zell_ensure(mdl));
         GMB_TRY(hmc_run(mdl, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
                         mdl->dV, stats ? &hcs : nullptr, &ms));
     }
@@ -571,7 +579,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
         mdl->zd_valid = false;
         mdl->u_version++;
         GMB_TRY(gmb_model_reserve_samples(mdl, (int)ncol));
-        GMB_TRY(gmb_dgemm(ctx, 0, 0, mdl->Q, (int)ncol, mdl->Q, 1.0, mdl->dL, mdl->ldq, mdl->dV, mdl->ldq, 0.0, mdl->dU, mdl->ldq));
+        GMB_TRY(gmb_dgemm_tri(ctx, 0, 0, mdl->Q, (int)ncol, mdl->Q, 1.0, mdl->dL, mdl->ldq, mdl->dV, mdl->ldq, 0.0, mdl->dU, mdl->ldq, mdl->l_lower ? 1 : 0));
         mdl->m_local = (int)ncol; mdl->m_total = (int)ncol * ctx->world; mdl->niter_local = mdl->m_local; mdl->niter_total = mdl->m_total;
         if (U_out)
             GMB_CUDA(cudaMemcpy2DAsync(U_out, mdl->Q * sizeof(double), mdl->dU, mdl->ldq * sizeof(double), mdl->Q * sizeof(double), ncol,

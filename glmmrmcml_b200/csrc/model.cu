@@ -6,6 +6,7 @@
 //   mcmlmodel.h:286, and m times per mcnr() call, mcmloptim.h:213 -> mcmlmodel.h:121).
 // The dense n x n weight matrix W_ (mcmlmodel.h:36,62) is never materialised.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -123,8 +124,37 @@ int gmb_model_reserve_samples(gmb_model* mdl, int m) {
 }
 
 // zd = Z u for the first m_local columns of dU (mcmlmodel.h:286 / :117, hoisted)
+// zd = Z u with Z in ELL form (indicator designs: one or two non-zeros per row): a gather instead of a 2 n Q m flop contraction
+__global__ void __launch_bounds__(256) zd_sparse_kernel(int n, int ldn, int ngp, int wr, int ldq, const double* __restrict__ rv, const int* __restrict__ rc,
+                                                        const double* __restrict__ U, double* __restrict__ zd) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const size_t j = blockIdx.y;
+    if (i >= ldn) return;
+    double s = 0.0;
+    if (i < n) for (int w = 0; w < wr; w++) s = fma(rv[(size_t)w * ngp + i], U[rc[(size_t)w * ngp + i] + j * ldq], s);
+    zd[i + j * ldn] = s;
+}
+
+// 1 (default) = build zd by gathering when Z is sparse (same criterion as the samplers' sparse forms), 0 = always the dense contraction
+static int g_zd_sparse = 1;
+extern "C" int gmb_estep_set_sparse_zd(int on) { g_zd_sparse = on ? 1 : 0; return GMB_OK; }
+
 int gmb_model_build_zd(gmb_model* mdl) {
-    if (mdl->m_local > 0)
+    bool sparse = false;
+    if (mdl->m_local > 0 && g_zd_sparse && mdl->Q >= 64) {
+        GMB_TRY(gmb_zell_ensure(mdl));
+        sparse = mdl->zell.valid && mdl->m_local <= 65535 * 16;
+    }
+    if (sparse) {
+        const gmb_ell& e = mdl->zell;
+        for (int j0 = 0; j0 < mdl->m_local; j0 += 65535) {
+            const int nc = std::min(65535, mdl->m_local - j0);
+            zd_sparse_kernel<<<dim3((mdl->ldn + 255) / 256, nc), 256, 0, mdl->ctx->stream>>>(mdl->n, mdl->ldn, e.ngp, e.wr, mdl->ldq, e.rv, e.rc,
+                                                                                           mdl->dU + (size_t)j0 * mdl->ldq, mdl->dzd + (size_t)j0 * mdl->ldn);
+            mdl->ctx->launches++;
+        }
+        GMB_CUDA(cudaGetLastError());
+    } else if (mdl->m_local > 0)
         GMB_TRY(gmb_dgemm(mdl->ctx, 0, 0, mdl->n, mdl->m_local, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dU, mdl->ldq, 0.0, mdl->dzd, mdl->ldn));
     mdl->f_valid = false;
     mdl->stat_valid = false;

@@ -167,6 +167,9 @@ int gmb_hmc_set_cluster_size(int cs);
  * sample matrix; 0 = stream zd on every evaluation (used by the roofline probes and the parity tests of the streaming kernel). */
 int gmb_estep_set_rowstats(int on);
 
+/* zd = Z u: 1 (default) = gather through the sparse form of Z when Z is sparse (indicator designs) and Q >= 64, 0 = always the dense contraction. */
+int gmb_estep_set_sparse_zd(int on);
+
 /* Batched binomial/logit evaluations (gmb_model_loglik_batch, batches of >= 8): 1 (default) = one launch for the whole batch, 8 parameter
  * vectors share each pass over the factor matrix; 0 = one launch per evaluation.  Both deterministic; they partition the sum differently, so
  * values agree to rounding (1e-13 relative), not bit for bit. */

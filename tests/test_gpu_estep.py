@@ -155,3 +155,27 @@ def test_rowstat_evaluation_equals_the_stream(gctx, oracle):
                 assert abs(a - want) <= 1e-10 * abs(want)
                 assert abs(b - want) <= 1e-10 * abs(want), (a, b, want)
         mdl.close()
+
+
+@pytest.mark.parametrize("name", ["C4", "C5"])
+def test_sparse_zd_build_equals_dense_contraction(gctx, oracle, name):
+    """zd = Z u through the sparse form of Z (indicator designs, Q >= 64) against the dense DMMA contraction and the oracle: same sums
+    without the zero terms."""
+    import glmmrmcml_b200 as g
+    cfg = CASES[name]()
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    vals = {}
+    try:
+        for on in (True, False):
+            g.estep_set_sparse_zd(on)
+            mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+            mdl.set_u(cfg["U"])
+            nr = mdl.mcnr(cfg["beta"], 1.0)
+            vals[on] = (mdl.log_likelihood(cfg["beta"], 1.0), nr["xtwx"], nr["score"])
+            mdl.close()
+    finally:
+        g.estep_set_sparse_zd(True)
+    want = oracle.loglik_faithful(cfg["X"], cfg["Z"], cfg["U"], cfg["y"], cfg["beta"], 1.0, fl)
+    assert abs(vals[True][0] - want) <= RTOL * abs(want)
+    assert abs(vals[True][0] - vals[False][0]) <= 1e-12 * abs(want)
+    assert rel(vals[True][1], vals[False][1]) <= 1e-12 and rel(vals[True][2], vals[False][2]) <= 1e-10

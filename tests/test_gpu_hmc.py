@@ -292,13 +292,22 @@ def test_factored_two_contraction_sampler(gctx, oracle):
         gw = oracle.log_grad(ZL, xb, cfg["y"], 1.0, fl, V[:, c])
         assert np.max(np.abs(G[:, c] - gw)) <= 1e-10 * max(np.max(np.abs(gw)), 1.0)
     mdl.close()
-    # Z = I (C3): n = Q, nothing to gain — the dense contraction stays
+    # Z = I (C3): n = Q — factored only because the Cholesky factor is triangular (its zero k tiles are skipped); with a full square root
+    # of D (here L P for a permutation P: same D = L L') the dense contraction stays, and both follow the oracle
     c3 = synth.config3(nloc=150, m=4)
     mdl = g.Model(gctx, c3["X"], c3["Z"], c3["y"], "gaussian", "identity")
+    perm = np.random.default_rng(1).permutation(c3["Q"])
+    Lfull = np.asfortranarray(c3["L"][:, perm])
+    kw3 = dict(warmup=6, nsamp_per_chain=3, lam=0.5, max_steps=8, target_accept=0.8, n_chains=3, seed=1, want_u=True, want_v=True)
     g.hmc_set_variant(1)
     try:
-        out = mdl.hmc_sample(c3["L"], c3["beta"], 1.0, warmup=3, nsamp_per_chain=2, lam=0.5, max_steps=5, n_chains=3, seed=1, want_u=False)
+        a = mdl.hmc_sample(c3["L"], c3["beta"], 1.0, **kw3)
+        b = mdl.hmc_sample(Lfull, c3["beta"], 1.0, **kw3)
     finally:
         g.hmc_set_variant(0)
-    assert out["stats"]["factored"] == 0
+    assert a["stats"]["factored"] == 1 and b["stats"]["factored"] == 0
+    for out, Lm in ((a, c3["L"]), (b, Lfull)):
+        ref = oracle.hmc_chain(c3["Z"] @ Lm, Lm, c3["X"] @ c3["beta"], c3["y"], 1.0, 7, 6, 3, 0.5, 8, 0.8, 1, chain=2)
+        assert np.max(np.abs(out["v"][:, 8:12] - ref["v"])) <= 1e-7
+        assert np.max(np.abs(out["u"][:, 8:12] - ref["u"])) <= 1e-7
     mdl.close()

@@ -17,3 +17,7 @@ ncu --set full --clock-control none --import-source on -k regex:'loglik|mcnr_pas
     python tools/profile_kernels.py estep > gpurun_out/ncu_prof.log 2>&1
 echo "estep full rc=$?"
 tail -n 2 gpurun_out/plain_hmc.log gpurun_out/plain_prof.log
+# summaries are extracted here, on the box (the reports exceed gpurun's 64 MiB return limit): profiles/ -> gpurun_out/profiles_out/
+bash tools/make_profiles.sh ${TAG} > gpurun_out/make_profiles.log 2>&1
+mkdir -p gpurun_out/profiles_out && cp profiles/${TAG}_ncu_raw_extract_final.txt profiles/${TAG}_ncu_source_*_final.txt profiles/${TAG}_launches_bench.csv gpurun_out/profiles_out/
+rm -f gpurun_out/prof_*_${TAG}.ncu-rep gpurun_out/launches_bench_${TAG}.csv
