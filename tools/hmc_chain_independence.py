@@ -16,7 +16,7 @@ def run(seed, variant=0, cs=0, nch=250, ns=39, warm=500):
     Uc = out["u"].reshape(Q, ns + 1, nch, order="F").transpose(0, 2, 1)[:, :, 1:]
     cm = Uc.mean(axis=2)
     return cm.mean(axis=1), cm.std(axis=1, ddof=1) / np.sqrt(nch), out["stats"], cm
-for label, kw in (("fused auto", dict()), ("fused cs1", dict(cs=1)), ("two-gemm", dict(variant=1, nch=64, ns=20, warm=200))):
+for label, kw in (("auto (structure-aware)", dict()), ("on-chip dense", dict(variant=2)), ("on-chip dense cs1", dict(variant=2, cs=1)), ("two-gemm", dict(variant=1, nch=64, ns=20, warm=200))):
     ms, ss = [], []
     for seed in range(1, 7):
         m_, s_, st, cm = run(seed, **kw)

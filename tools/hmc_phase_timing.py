@@ -6,6 +6,7 @@ The counters of the last launch are printed to stderr at exit."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import glmmrmcml_b200 as g
+g.hmc_set_variant(2)        # this tool studies the dense on-chip kernel (the dispatcher alone picks the structure-aware one for C2)
 from glmmrmcml_b200 import synth
 nch = int(sys.argv[1]) if len(sys.argv) > 1 else 500
 cs = int(sys.argv[2]) if len(sys.argv) > 2 else 0

@@ -8,6 +8,7 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import glmmrmcml_b200 as g
+g.hmc_set_variant(2)        # this tool studies the dense on-chip kernel (the dispatcher alone picks the structure-aware one for C2)
 from glmmrmcml_b200 import synth
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
