@@ -292,6 +292,11 @@ extern "C" int gmb_mcmc_sample(const double* Z, const double* L, const double* X
     int C = n_chains > 0 ? n_chains : default_chains(nsamp);
     if (C > want) C = want;
     const int per = (want + C - 1) / C;                          // columns per chain (k + 1)
+    if ((size_t)C * per == (size_t)want) {                       // the chains' columns fill the result exactly: straight into the caller's buffer
+        GMB_TRY(gmb_hmc_sample(h.mdl, L, beta, var_par, warmup, per - 1, lambda, maxsteps, target_accept, 100, C, 0u, seed, 0,
+                               samples_out, nullptr, nullptr));
+        return GMB_OK;
+    }
     std::vector<double> U((size_t)Q * C * per);
     GMB_TRY(gmb_hmc_sample(h.mdl, L, beta, var_par, warmup, per - 1, lambda, maxsteps, target_accept, 100, C, 0u, seed, 0,
                            U.data(), nullptr, nullptr));

@@ -93,7 +93,9 @@ __global__ void __launch_bounds__(THREADS) dgemm_kernel(int M, int N, int K, con
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WM, wn = warp / WM;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    // tri = 1: the last row tiles carry the longest k ranges — start them first (CTAs are scheduled in index order)
+    const int bx = (tri == 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
+    const int m0 = bx * BM, n0 = blockIdx.y * BN;
     const int KT = (K + BK - 1) / BK;
     // triangular operand (a Cholesky factor): tri = 1: op(A)(m, k) = 0 for k > m ; tri = 2: op(A)(m, k) = 0 for k < m (the factor read transposed).
     // The k tiles that hold only zeros for this row tile are skipped — the same sums without their zero terms.
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(THREADS) dgemm_kernel(int M, int N, int K, con
                 double x = 0.0;
 #pragma unroll
                 for (int w = 0; w < WM; w++) x += scol[w * BN + c];
-                epi.colsum_out(blockIdx.x, n, x);
+                epi.colsum_out(bx, n, x);
             }
         }
     }
