@@ -35,7 +35,11 @@ sys.path.insert(0, ROOT)
 M_PER_GPU = 10_000
 N_CHAINS = 1000           # per GPU; 10 columns each (9 post-warm-up draws + the state after warm-up).  The sampler aggregates the 500
                           # observations into their 50 distinct rows of [X | Z] (aggregate.cu) and, Z L being sparse (150 non-zeros),
-                          # runs the structure-aware kernel, one warp per chain (hmc_sparse.cu)
+                          # runs the structure-aware kernel, one warp per chain (hmc_sparse.cu).  Chain count: a draw costs (warm-up +
+                          # columns per chain) x ~95 leapfrog steps in sequence, 280 ns each up to one warp per scheduler (592), 350 ns
+                          # with 1000 chains.  500 chains x 20 columns give more columns per second (13.7 ms per draw against 16.9 ms)
+                          # but fewer effective samples per second (median ESS/s 74 k against 93 k: consecutive draws of a chain are
+                          # correlated) — tools/hmc_chain_count_sweep.py; the E-step integrates over these columns, so ESS/s decides
 HMC = dict(warmup=500, lam=5.0, max_steps=100, target_accept=0.95, adapt=100)
 N_D_EVALS = 64            # mvn_ll evaluations of one d_optim (BOBYQA over 2 parameters takes 40-80)
 N_HESS = 256              # 4 k^2, k = P + R = 8
@@ -58,7 +62,7 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
 
 
-def sampler_roofline(st, exec_tflops, algo_tflops, exec_per_step, cfg, Q, dense_probe):
+def sampler_roofline(st, exec_tflops, algo_tflops, exec_per_step, cfg, Q, dense_probe, many_probe=None):
     """roofline object of the sampler launch of the timed step (the step's dominant kernel)."""
     kv = st["kernel_variant"]
     common = {"achieved": exec_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": exec_tflops / FP64_DMMA_PEAK_TFLOPS,
@@ -75,9 +79,15 @@ def sampler_roofline(st, exec_tflops, algo_tflops, exec_per_step, cfg, Q, dense_
                     "leapfrog update per column; FMA = 2) / kernel time, against the FP64 pipe peak.  SURVEY 8d's algorithmic figure for the dense "
                     "contraction (4 n Q = 1e5 per step and chain) is `algorithmic_tflops`: the kernel does the same arithmetic on the 150 non-zeros "
                     "of the 50 distinct rows instead of 500 x 50 entries, so that figure exceeds the pipe peak.  With 1000 chains (1.7 warps per "
-                    "scheduler) a leapfrog step is bound by its dependent chain (shared-memory exchange + exp + reciprocal, ~750 cycles), not by "
+                    "scheduler) a leapfrog step is bound by its dependent chain (shared-memory exchange + exp + reciprocal: 550 cycles alone, ~700 shared), not by "
                     "pipe throughput; `dense_kernel` is the DMMA kernel a model with a dense Z L runs",
             "dense_kernel": dense_probe})
+        if many_probe and many_probe.get("kernel_variant") == 3:
+            t = many_probe["leapfrog_per_s"] * exec_per_step / 1e12
+            common["saturated"] = {"chains": many_probe["chains"], "ms": many_probe["ms"], "leapfrog_per_s": many_probe["leapfrog_per_s"],
+                                   "achieved": t, "frac": t / FP64_DMMA_PEAK_TFLOPS,
+                                   "note": "the same kernel with 4000 chains (several warps per scheduler, 104 proposals): bound by the shared-memory "
+                                           "pipe (ncu: 69 % busy already at 1000 chains), not by latency; not the timed step"}
     else:
         common.update({
             "kernel": "hmc_fused_kernel<%s> (on-chip sampler: eta = ZL v and grad = ZL^T r(eta) as FP64 DMMA)" % cfg["family"] if kv == 2
@@ -513,6 +523,7 @@ def main():
     peaks, peak_src = load_peaks()
     roofline_estep = None
     roofline_sat = None
+    roofline_many = None
     if rank == 0:
         # HBM roofline probe of the E-step kernels: same model, 1 GB of zd (> 4 x L2), 8 evaluations in one batch
         mbig = 250_000
@@ -542,6 +553,16 @@ def main():
                                               "(algorithmic bytes / 8 per evaluation), bound by FP64 work"},
                           "mcnr": {"achieved": bytes_nr / (t_nr * 1e-3) / 1e9, "frac": bytes_nr / (t_nr * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": t_nr}}
         mdl2.close()
+        # the timed step's sampler kernel with every scheduler holding several warps (4000 chains): its throughput regime
+        mdl4 = g.Model(ctx1, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+        for rep in range(2):
+            r4 = mdl4.hmc_sample(L, beta, 1.0, warmup=100, nsamp_per_chain=4, lam=HMC["lam"], max_steps=HMC["max_steps"],
+                                 target_accept=HMC["target_accept"], adapt=HMC["adapt"], n_chains=4000, seed=seed0 + 98, keep_on_device=True,
+                                 want_u=False)
+        s4 = r4["stats"]
+        roofline_many = {"chains": 4000, "ms": s4["kernel_ms"], "leapfrog_per_s": s4["leapfrog_total"] / (s4["kernel_ms"] * 1e-3),
+                         "kernel_variant": s4["kernel_variant"]}
+        mdl4.close()
         # the sampler kernel as a dense tensor kernel: row aggregation off, every SM busy on 8 tiles per warp (1184 chains = 148 groups,
         # one CTA each) — what the DMMA path reaches on a model without repeated rows
         g.hmc_set_row_aggregation(False)
@@ -577,7 +598,7 @@ def main():
                     "calls": "gmb_mcmc_sample + gmb_mcml_optim(mcnr) + gmb_mcml_hess with host buffers", "s_per_step": e2e_s,
                     "parts_s": {k: float(np.mean(v)) for k, v in e2e_parts.items()}},
             "gpu_launches": int(launches), "clocks": clk, "wall_s": wall,
-            "roofline": sampler_roofline(st, hmc_exec_tflops, hmc_tflops, exec_per_step, cfg, Q, roofline_sat),
+            "roofline": sampler_roofline(st, hmc_exec_tflops, hmc_tflops, exec_per_step, cfg, Q, roofline_sat, roofline_many),
             "roofline_estep": roofline_estep, "cpu_baseline": cpu}
     line.update(extra)
     emit(line)
