@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) loglik_logit_factor_kernel(int n, int P, 
 // not bit for bit.  beta: P x n_eval; group z covers evaluations min(z NB, n_eval - NB) .. + NB - 1 (a short last group overlaps the one
 // before); partials: [group][NB][blocks]; counters: one per group, zero on entry; out: n_eval values.
 template <int NB>
-__global__ void __launch_bounds__(256) loglik_logit_factor_multi_kernel(int n, int P, int ldn, int ncols, int cols_per_cta, int n_eval,
+__global__ void __launch_bounds__(256, 2) loglik_logit_factor_multi_kernel(int n, int P, int ldn, int ncols, int cols_per_cta, int n_eval,
                                                                         const double* __restrict__ F, const double* __restrict__ X,
                                                                         const double* __restrict__ beta, const double* __restrict__ y,
                                                                         double* __restrict__ partials, unsigned int* __restrict__ counter,
