@@ -45,10 +45,10 @@ struct CompParams {
 // mode 0: initial state (mhmcmc.h:48-49), its gradient and log-likelihood; mode 1: proposal `it` (:61-78)
 template <int FL, int W>
 __global__ void __launch_bounds__(32 * CP_WPB) comp_traj_kernel(const CompParams p, int mode, int it) {
-    __shared__ double sTab[64];
+    __shared__ double sTab[16];                  // 2^(j/16): the conflict-free table of dev_family_resid_w_vec16
     __shared__ double sX[CP_WPB][2][CP_CAP];     // v' and r(eta) of the warp's group
     const int tid = threadIdx.x, t = tid & 31, w = tid >> 5;
-    if (tid < 64) sTab[tid] = GMB_EXP2_TAB[tid];
+    if (tid < 16) sTab[tid] = GMB_EXP2_TAB[4 * tid];
     __syncthreads();
     const long long wg = (long long)blockIdx.x * CP_WPB + w;
     if (wg >= (long long)p.C * p.G) return;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(32 * CP_WPB) comp_traj_kernel(const CompParams
         eta[0] += eo;
         const double cn1[1] = {cn}, ys1[1] = {ysv};
         double res[1];
-        dev_family_resid_w_vec<FL, 1>(cn1, ys1, eta, sTab, res);
+        dev_family_resid_w_vec16<FL, 1>(cn1, ys1, eta, sTab, res);
         s_res[t] = res[0];
         if (with_ll) {
             ll = 0.0;

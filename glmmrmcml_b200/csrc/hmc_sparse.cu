@@ -98,7 +98,7 @@ __global__ void ell_fill_cols_kernel(int ng, int Q, int qp, int ld, int wc, cons
 // TPC threads per chain: 32 = one warp per chain, SP_CPB chains per CTA; otherwise one CTA of TPC threads per chain.
 // NPT > 0: every thread owns at most NPT rows and NPT columns and keeps their state in registers (NPT == 0: run-time counts, state
 // in shared / global memory).  W > 0: the ELL entries of those rows and columns are in registers too, padded to the compile-time
-// width W (even, <= SP_MAXW) — the leapfrog step is then straight-line code.
+// width W (<= SP_MAXW) — the leapfrog step is then straight-line code.
 template <int FL, int TPC, int NPT, int W>
 __global__ void __launch_bounds__(TPC == 32 ? 32 * SP_CPB : TPC) hmc_sparse_kernel(const SparseParams p) {
     constexpr bool WARP = (TPC == 32);
@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(TPC == 32 ? 32 * SP_CPB : TPC) hmc_sparse_kern
     constexpr int CPB = WARP ? SP_CPB : 1;
     constexpr int NR = NPT > 0 ? NPT : 1;
     constexpr int NE = REGELL ? NPT : 1, NW = REGELL ? W : 2;
-    static_assert(W % 2 == 0, "register ELL width must be even");
     static_assert(W == 0 || NPT > 0, "register ELL needs a compile-time row count");
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x;
@@ -120,7 +119,8 @@ __global__ void __launch_bounds__(TPC == 32 ? 32 * SP_CPB : TPC) hmc_sparse_kern
     double* s_red = sm + 64 + (size_t)CPB * (qp + ngp);          // 32 doubles (CTA-per-chain reductions)
     // ELL arrays: global memory, or staged in shared memory behind s_red (small models without register ELL)
     const double* rv = p.rv; const int* rc = p.rc; const double* cv = p.cv; const int* cr = p.cr;
-    if (tid < 64) sTab[tid] = GMB_EXP2_TAB[tid];
+    if (REGELL) { if (tid < 16) sTab[tid] = GMB_EXP2_TAB[4 * tid]; }           // 2^(j/16): the conflict-free 128-byte table of dev_family_resid_w_vec16
+    else if (tid < 64) sTab[tid] = GMB_EXP2_TAB[tid];
     if (WARP && !REGELL && p.ell_smem) {
         double* s_rv = s_red + 32; double* s_cv = s_rv + (size_t)wr * ngp;
         int* s_rc = reinterpret_cast<int*>(s_cv + (size_t)wc * qp); int* s_cr = s_rc + (size_t)wr * ngp;
@@ -204,16 +204,20 @@ __global__ void __launch_bounds__(TPC == 32 ? 32 * SP_CPB : TPC) hmc_sparse_kern
 #pragma unroll
             for (int k = 0; k < NE; k++) { eta[k] = xb_reg[k]; eo[k] = 0.0; }
 #pragma unroll
-            for (int w = 0; w < NW; w += 2)
+            for (int w = 0; w + 1 < NW; w += 2)
 #pragma unroll
                 for (int k = 0; k < NE; k++) {
                     eta[k] = fma(erv[k][w], *reinterpret_cast<const double*>(s_vp_b + erc[k][w]), eta[k]);
                     eo[k] = fma(erv[k][w + 1], *reinterpret_cast<const double*>(s_vp_b + erc[k][w + 1]), eo[k]);
                 }
+            if (NW & 1) {
+#pragma unroll
+                for (int k = 0; k < NE; k++) eta[k] = fma(erv[k][NW - 1], *reinterpret_cast<const double*>(s_vp_b + erc[k][NW - 1]), eta[k]);
+            }
 #pragma unroll
             for (int k = 0; k < NE; k++) eta[k] += eo[k];
             double res[NE];
-            dev_family_resid_w_vec<FL, NE>(cn_reg, ys_reg, eta, sTab, res);
+            dev_family_resid_w_vec16<FL, NE>(cn_reg, ys_reg, eta, sTab, res);
 #pragma unroll
             for (int k = 0; k < NE; k++) my_res[k * TPC] = res[k];
             if (with_ll) {
@@ -231,12 +235,16 @@ __global__ void __launch_bounds__(TPC == 32 ? 32 * SP_CPB : TPC) hmc_sparse_kern
 #pragma unroll
             for (int k = 0; k < NE; k++) gs[k] = go[k] = 0.0;
 #pragma unroll
-            for (int w = 0; w < NW; w += 2)
+            for (int w = 0; w + 1 < NW; w += 2)
 #pragma unroll
                 for (int k = 0; k < NE; k++) {
                     gs[k] = fma(ecv[k][w], *reinterpret_cast<const double*>(s_res_b + ecr[k][w]), gs[k]);
                     go[k] = fma(ecv[k][w + 1], *reinterpret_cast<const double*>(s_res_b + ecr[k][w + 1]), go[k]);
                 }
+            if (NW & 1) {
+#pragma unroll
+                for (int k = 0; k < NE; k++) gs[k] = fma(ecv[k][NW - 1], *reinterpret_cast<const double*>(s_res_b + ecr[k][NW - 1]), gs[k]);
+            }
 #pragma unroll
             for (int k = 0; k < NE; k++) g_reg[k] = -1.0 * vp_reg[k] + sc * (gs[k] + go[k]);       // mcmlmodel.h:163 + :173/:191/:235
         } else {
@@ -441,7 +449,7 @@ SparsePlan sparse_plan(const gmb_ell& e) {
     const int big = std::max(e.ng, e.Q);
     if (big <= 128) {
         const size_t base = sizeof(double) * (64 + SP_CPB * per_chain + 32);
-        if (big <= 64 && e.wr <= SP_MAXW && e.wc <= SP_MAXW) { pl.kind = 1; pl.w = std::max(2, (std::max(e.wr, e.wc) + 1) / 2 * 2); pl.smem = base; return pl; }
+        if (big <= 64 && e.wr <= SP_MAXW && e.wc <= SP_MAXW) { pl.kind = 1; pl.w = std::max(1, std::max(e.wr, e.wc)); pl.smem = base; return pl; }
         const size_t ell = (size_t)12 * ((size_t)e.wr * e.ngp + (size_t)e.wc * e.qp) + 16;
         pl.kind = big <= 64 ? 2 : 3;
         pl.ell_smem = base + ell <= 96 * 1024 ? 1 : 0;
@@ -471,9 +479,13 @@ int launch_sparse_kind(gmb_ctx* ctx, const SparseParams& p, const SparsePlan& pl
     switch (pl.kind) {
     case 1:
         switch (pl.w) {
+        case 1: return launch_sparse<FL, 32, 2, 1>(ctx, p, pl.smem);
         case 2: return launch_sparse<FL, 32, 2, 2>(ctx, p, pl.smem);
+        case 3: return launch_sparse<FL, 32, 2, 3>(ctx, p, pl.smem);
         case 4: return launch_sparse<FL, 32, 2, 4>(ctx, p, pl.smem);
+        case 5: return launch_sparse<FL, 32, 2, 5>(ctx, p, pl.smem);
         case 6: return launch_sparse<FL, 32, 2, 6>(ctx, p, pl.smem);
+        case 7: return launch_sparse<FL, 32, 2, 7>(ctx, p, pl.smem);
         case 8: return launch_sparse<FL, 32, 2, 8>(ctx, p, pl.smem);
         }
         break;
