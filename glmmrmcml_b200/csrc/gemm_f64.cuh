@@ -19,6 +19,7 @@
 //   __device__ void colsum_out(int row_tile, int n, double v) const; (COLSUM only; one call per (row tile, column))
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 namespace gmbgemm {
 
@@ -220,8 +221,10 @@ int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const do
 
 // number of row tiles the dispatcher below will use (callers size their column-sum buffers with it)
 inline int row_tile(gmb_ctx* ctx, int M, int N) {
+    // 128 x 128 tiles when they make at least GMB_GEMM_WAVES waves of CTAs (one per SM); fewer, larger tiles lose the tail of the last wave
+    static const int waves = [] { const char* e = getenv("GMB_GEMM_WAVES"); return e ? atoi(e) : 4; }();
     long tiles128 = (long)((M + 127) / 128) * ((N + 127) / 128);
-    return tiles128 >= ctx->sms ? 128 : 64;
+    return tiles128 >= (long)waves * ctx->sms ? 128 : 64;
 }
 
 template <bool AK, bool BKC, class Epi>
