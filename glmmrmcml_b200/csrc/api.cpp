@@ -286,8 +286,10 @@ extern "C" int gmb_mcmc_sample(const double* Z, const double* L, const double* X
     if (!Z || !L || !X || !y || !beta || !samples_out) return gmb_set_error(GMB_EINVAL, "gmb_mcmc_sample: NULL argument");
     if (nsamp < 0) return gmb_set_error(GMB_EINVAL, "nsamp must be >= 0");
     gmb_ctx* ctx; GMB_TRY(default_ctx(&ctx));
+    GmbPhase ph(ctx->stream);
     Handles h;
     GMB_TRY(gmb_model_create(ctx, n, P, Q, X, Z, y, family, link, &h.mdl));
+    ph.mark("mcmc_sample: model upload");
     const int want = nsamp + 1;                                  // Q x (nsamp + 1), mhmcmc.h:126
     int C = n_chains > 0 ? n_chains : default_chains(nsamp);
     if (C > want) C = want;
@@ -312,14 +314,18 @@ extern "C" int gmb_mcml_optim(const int32_t* cov, int cov_rows, const double* da
     (void)trace;
     if (!start) return gmb_set_error(GMB_EINVAL, "start is NULL");
     gmb_ctx* ctx; GMB_TRY(default_ctx(&ctx));
+    GmbPhase ph(ctx->stream);
     Handles h;
     GMB_TRY(setup_fixed_u(ctx, cov, cov_rows, data, n_data, eff_range, n_eff, Z, X, y, u, n, P, Q, m, family, link, h));
+    ph.mark("optim: objects, upload u, zd");
     Fit mc;
     GMB_TRY(mc.init(ctx, h.cv, h.mdl, start, n_start, family));
     mc.model_var_par = 1.0;                                       // :52
     mc.d_cols_total = h.m_total;
     if (!mcnr) GMB_TRY(mc.l_optim()); else GMB_TRY(mc.mcnr());    // :55-59
+    ph.mark("optim: beta step");
     GMB_TRY(mc.d_optim());                                        // :60
+    ph.mark("optim: theta step");
     if (beta_out) memcpy(beta_out, mc.beta.data(), sizeof(double) * P);
     if (theta_out) memcpy(theta_out, mc.theta.data(), sizeof(double) * mc.R);
     if (sigma_out) *sigma_out = mc.sigma;

@@ -38,6 +38,22 @@ int gmb_set_error(int code, const char* fmt, ...);
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
+// Host-side phase timer for the entry points: with GMB_TRACE=1 in the environment every GMB_PHASE("name") prints the milliseconds since the
+// previous one to stderr (the stream is synchronised first, so the cost lands on the phase that issued it); without it, one branch.
+#include <chrono>
+#include <cstdlib>
+struct GmbPhase {
+    bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0;
+    explicit GmbPhase(cudaStream_t s) : st(s) { static const bool e = getenv("GMB_TRACE") != nullptr; on = e; if (on) { cudaStreamSynchronize(st); t0 = std::chrono::steady_clock::now(); } }
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gmb trace] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // ------------------------------------------------------------------------------------------------
 // host-side objects
 // ------------------------------------------------------------------------------------------------

@@ -523,11 +523,15 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     if (mdl->flink == 7 && !(var_par > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0");
     gmb_ctx* ctx = mdl->ctx;
     GMB_CUDA(cudaSetDevice(ctx->device));
+    GmbPhase ph(ctx->stream);
     if (g_hmc_variant != 1) GMB_TRY(gmb_agg_ensure(mdl));       // row view of the on-chip sampler (not used by the two-GEMM variant)
+    ph.mark("hmc: row aggregation");
     if (L) GMB_TRY(gmb_hmc_prepare(mdl, L));
     GMB_TRY(agg_update_zl(mdl));
+    ph.mark("hmc: upload L, Z L");
     const bool try_sparse = g_hmc_variant == 0 || g_hmc_variant == 3;
     if (try_sparse) { GMB_TRY(gmb_ell_ensure(mdl)); GMB_TRY(gmb_comp_ensure(mdl)); }
+    ph.mark("hmc: sparse forms");
     GMB_TRY(set_xb(mdl, beta));
     const int C = n_chains, cols = nsamp_per_chain + 1;
     const size_t ncol = (size_t)C * cols;
@@ -553,6 +557,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
         GMB_TRY(hmc_run(mdl, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
                         mdl->dV, stats ? &hcs : nullptr, &ms));
     }
+    ph.mark("hmc: sampler kernels");
     if (stats) {
         double acc = 0, eps = 0, tot = 0;
         for (int c = 0; c < C; c++) { acc += hcs[(size_t)CS_ACCEPT * C + c]; eps += hcs[(size_t)CS_EPS * C + c]; tot += hcs[(size_t)CS_TOTSTEPS * C + c]; }
@@ -586,6 +591,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
                                        cudaMemcpyDeviceToHost, ctx->stream));
     }
     GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ph.mark("hmc: u = L v, copies out");
     return GMB_OK;
 }
 

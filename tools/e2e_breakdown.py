@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import glmmrmcml_b200 as g
 from glmmrmcml_b200 import synth
 
-M, NCH = 10_000, 500
+M, NCH = 10_000, 1000
 cfg = synth.config2(m=M)
 ctx = g.Context(0); ctx.make_default()
 cv = g.Covariance(ctx, cfg["cov"], cfg["data"], cfg["eff_range"])
