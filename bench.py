@@ -47,7 +47,7 @@ D_BATCH = 5               # 2 R + 1: the central-difference stencil the optimise
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: profiles/r01_microbench_fp64.txt (tools/microbench_fp64.cu)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` captures (profiles/r01_ncu_raw_extract_final.txt):
 SAMPLER_DRAM_BYTES_PER_LAUNCH = {2: 446976.0,       # hmc_fused_kernel<3,13,4>: Z L, xb, y are read once, the chain runs out of shared memory
-                                 3: 80384.0}         # hmc_sparse_kernel<3,32,2,6>: ELL arrays, xb and row weights are read once; the samples stay in L2
+                                 3: 80384.0}         # hmc_sparse_kernel<3,32,2,5>: ELL arrays, xb and row weights are read once; the samples stay in L2
 # FP64 operations per leapfrog step and chain that the structure-aware kernel executes (FMA = 2): 4 per non-zero of Z L (eta and gradient),
 # per row the residual (table exp 18 + Newton reciprocal 9 + 2 for binomial-logit; 20 poisson; 2 gaussian), per column 8 (gradient, leapfrog)
 SPARSE_ROW_FLOPS = {"binomial": 29.0, "poisson": 20.0, "gaussian": 2.0}
