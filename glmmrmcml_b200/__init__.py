@@ -528,10 +528,15 @@ class ModelMCML:
         while np.any(np.abs(theta[act] - thetanew[act]) > tol) and it <= max_iter:   # :238
             it += 1
             thetanew = theta.copy()
-            s = mcmc_sample(self.Z, L, self.X, y, thetanew[ib], self.family, self.link, o["warmup"], o["samps"], o["lam"],
+            # C chains deliver `per` columns each, chain-major, column 0 of every chain being its state after warm-up (mhmcmc.h:142):
+            # ask for exactly C * per columns so that none is truncated, and drop every chain's column 0
+            Cn = max(1, min(n_chains, o["samps"]))
+            per = -(-o["samps"] // Cn) + 1
+            s = mcmc_sample(self.Z, L, self.X, y, thetanew[ib], self.family, self.link, o["warmup"], Cn * per - 1, o["lam"],
                             var_par=thetanew[isg], refresh=o["refresh"], maxsteps=o["maxsteps"], target_accept=o["target_accept"],
-                            n_chains=max(1, n_chains), seed=seed + it)
-            dsamps = np.asfortranarray(s[:, 1:])                  # iter_sampling draws (column 0 is the post-warm-up state), :256-258
+                            n_chains=Cn, seed=seed + it)
+            Qd = s.shape[0]
+            dsamps = np.asfortranarray(s.reshape(Qd, per, Cn, order="F")[:, 1:, :].reshape(Qd, -1, order="F")[:, :o["samps"]])   # iter_sampling draws, :256-258
             fit = mcml_optim(self.cov, self.data, self.eff_range, self.Z, self.X, y, dsamps, self.family, self.link, theta,
                              trace=0, mcnr=(method == "mcnr"))    # :293-306
             theta[ib] = fit["beta"]
@@ -567,7 +572,9 @@ class ModelMCML:
         out = dict(fit)
         pars = np.concatenate([fit["beta"], fit["theta"]])
         if se_theta:
-            H = mcml_hess(self.cov, self.data, self.eff_range, self.Z, self.X, y, fit["u"], self.family, self.link, pars)
+            # `start = theta` in R carries sigma behind the covariance parameters (R/R6ModelExtMCML.R:464-474): f_hess holds it fixed
+            hstart = np.concatenate([pars, [fit["sigma"]]]) if self.family == "gaussian" else pars
+            H = mcml_hess(self.cov, self.data, self.eff_range, self.Z, self.X, y, fit["u"], self.family, self.link, hstart)
             out["hessian"] = H
             try:
                 out["se"] = np.sqrt(np.diag(np.linalg.inv(H)))

@@ -395,6 +395,7 @@ extern "C" int gmb_cov_create(gmb_ctx* ctx, const int32_t* cov, int rows, const 
         if (b.n > cv->max_n) cv->max_n = b.n;
     }
     if (off > n_data) { delete cv; return gmb_set_error(GMB_EINVAL, "covariance data has %d values, %lld required", n_data, off); }
+    if (cv->R > 64) { const int R = cv->R; delete cv; return gmb_set_error(GMB_EINVAL, "%d covariance parameters exceed the staging area (64)", R); }
     cv->Q = start;
     cv->lblk_doubles = loff;
     cudaSetDevice(ctx->device);

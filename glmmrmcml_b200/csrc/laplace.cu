@@ -70,6 +70,9 @@ struct LaFit {
         int B;
         GMB_TRY(gmb_cov_dims(d, &B, &Q, &R));
         if (Q > 65535) return gmb_set_error(GMB_EINVAL, "Laplace path: Q = %d exceeds 65535", Q);
+        // pinned staging layout of this file: beta at [0, P), v at [1024, 1024 + Q), results from pinned_doubles / 2
+        if (P > 1024 || (size_t)Q + 1024 > ctx->pinned_doubles / 2)
+            return gmb_set_error(GMB_EINVAL, "Laplace path: P = %d / Q = %d exceed the staging area (P <= 1024, Q <= %zu)", P, Q, ctx->pinned_doubles / 2 - 1024);
         gaussian = std::string(family ? family : "") == "gaussian";
         if (n_start < P + R) return gmb_set_error(GMB_EINVAL, "start has %d values, needs P + R = %d", n_start, P + R);
         beta.assign(start, start + P);
@@ -366,10 +369,13 @@ int run_la(int nr, const int32_t* cov, int cov_rows, const double* data, int n_d
         if (maxdiff < tol) converged = true;                                       // :77
         beta = newbeta; theta = newtheta; var_par = new_var_par;
         if (!converged) {                                                          // :83-91 / :236-244
+            // the reference refreshes W BEFORE Z L: mcml_la forms it at xb + Z v with the previous var_par_ (:90-93), mcml_la_nr at
+            // xb + (Z L_old) v with the new one (:239-243); the new factor only enters with update_L() afterwards
+            GMB_TRY(mc.upload_beta(beta.data()));
+            if (nr) mc.var_par = new_var_par;
+            GMB_TRY(mc.update_W(nr != 0));
             mc.var_par = new_var_par;
             GMB_TRY(mc.set_L(theta.data(), true));
-            GMB_TRY(mc.upload_beta(beta.data()));
-            GMB_TRY(mc.update_W(nr != 0));
         }
         if (verbose) {
             fprintf(stderr, "Iter %d  beta:", iter);

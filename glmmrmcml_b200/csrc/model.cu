@@ -221,13 +221,9 @@ static int check_ready(gmb_model* mdl, const double* beta) {
 static int g_loglik_multi = 1;
 extern "C" int gmb_estep_set_multi(int on) { g_loglik_multi = on ? 1 : 0; return GMB_OK; }
 
-extern "C" int gmb_model_loglik_batch(gmb_model* mdl, const double* beta_mat, const double* var_par, int n_eval, double* out) {
-    GMB_TRY(check_ready(mdl, beta_mat));
-    if (!var_par || !out || n_eval <= 0) return gmb_set_error(GMB_EINVAL, "gmb_model_loglik_batch: bad arguments");
-    if (n_eval > GMB_RESULT_DOUBLES) return gmb_set_error(GMB_EINVAL, "at most %d evaluations per batch", GMB_RESULT_DOUBLES);
+// one chunk of a batch: at most GMB_RESULT_DOUBLES evaluations whose parameters fit the pinned staging area
+static int loglik_chunk(gmb_model* mdl, const double* beta_mat, const double* var_par, int n_eval, double* out) {
     gmb_ctx* ctx = mdl->ctx;
-    GMB_CUDA(cudaSetDevice(ctx->device));
-    if (mdl->flink == 7) for (int e = 0; e < n_eval; e++) if (!(var_par[e] > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0 (got %g)", var_par[e]);
     GMB_TRY(upload_params(mdl, beta_mat, mdl->P * n_eval));
     int e0 = 0;
     if (n_eval >= GMB_LOGLIK_NB && g_loglik_multi) {
@@ -243,6 +239,24 @@ extern "C" int gmb_model_loglik_batch(gmb_model* mdl, const double* beta_mat, co
     GMB_CUDA(cudaMemcpyAsync(hres, ctx->d_result, sizeof(double) * n_eval, cudaMemcpyDeviceToHost, ctx->stream));
     GMB_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int e = 0; e < n_eval; e++) out[e] = hres[e] / mdl->niter_total;   // mcmlmodel.h:303 ll.mean()
+    return GMB_OK;
+}
+
+extern "C" int gmb_model_loglik_batch(gmb_model* mdl, const double* beta_mat, const double* var_par, int n_eval, double* out) {
+    GMB_TRY(check_ready(mdl, beta_mat));
+    if (!var_par || !out || n_eval <= 0) return gmb_set_error(GMB_EINVAL, "gmb_model_loglik_batch: bad arguments");
+    gmb_ctx* ctx = mdl->ctx;
+    GMB_CUDA(cudaSetDevice(ctx->device));
+    if (mdl->flink == 7 || mdl->flink == 8) for (int e = 0; e < n_eval; e++) if (!(var_par[e] > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0 (got %g)", var_par[e]);
+    // any batch size: chunks bounded by the result buffer and by the pinned staging area (P values per evaluation; the reference
+    // has no limit on P or on the number of optimhess points, mcmloptim.h:333-355)
+    size_t cmax = (ctx->pinned_doubles / 2) / (size_t)mdl->P;
+    if (cmax > GMB_RESULT_DOUBLES) cmax = GMB_RESULT_DOUBLES;
+    if (cmax < 1) return gmb_set_error(GMB_EINVAL, "P = %d exceeds the parameter staging area", mdl->P);
+    for (int off = 0; off < n_eval; off += (int)cmax) {
+        const int nb = n_eval - off < (int)cmax ? n_eval - off : (int)cmax;
+        GMB_TRY(loglik_chunk(mdl, beta_mat + (size_t)off * mdl->P, var_par + off, nb, out + off));
+    }
     return GMB_OK;
 }
 

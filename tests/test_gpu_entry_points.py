@@ -153,3 +153,41 @@ def test_model_mcml_usestan_branch_runs_on_the_native_sampler(gctx):
     assert a["hessian"].shape == (cfg["P"] + 2, cfg["P"] + 2) and np.isfinite(a["aic"])
     L = mod.chol_D(cfg["theta"])
     assert np.allclose(L, synth.dense_chol_D(cfg["cov"], cfg["data"], cfg["theta"]), rtol=1e-10, atol=1e-12)
+
+
+def test_model_mcml_gaussian_takes_hessian_ses(gctx):
+    """Gaussian family through ModelMCML$MCML with se_theta = TRUE: mcml_hess receives (beta, theta, sigma) like `start = theta` in
+    R/R6ModelExtMCML.R:464-474 (mcmloptim ctor needs P + R + 1 values for gaussian models, mcmloptim.h:30)."""
+    import glmmrmcml_b200 as g
+    gctx.make_default()
+    cfg = synth.config3(nloc=40, m=8)
+    mod = g.ModelMCML(cfg["cov"], cfg["data"], cfg["eff_range"], cfg["Z"], cfg["X"], "gaussian", "identity", cfg["beta"], cfg["theta"], var_par=1.0)
+    mod.mcmc_options.update(warmup=100, samps=400, lam=1.0, maxsteps=30)
+    out = mod.MCML(cfg["y"], verbose=False, tol=5e-2, max_iter=4, method="mcem", n_chains=40, seed=5)
+    k = cfg["P"] + 2
+    assert out["hessian"].shape == (k, k) and np.all(np.isfinite(out["hessian"])) and np.isfinite(out["aic"])
+    assert out["sigma"] > 0
+
+
+def test_mcml_hess_with_many_fixed_effects(gctx, oracle):
+    """P = 25: the optimhess stencil has 4 (P + R)^2 = 2916 points, more parameter values than one staging buffer holds — the batch is
+    chunked inside the library (the reference has no limit, mcmloptim.h:333-355)."""
+    import glmmrmcml_b200 as g
+    gctx.make_default()
+    cfg = small_rct(m=64)
+    rng = np.random.default_rng(3)
+    Xw = np.asfortranarray(np.column_stack([cfg["X"], 0.3 * rng.standard_normal((cfg["n"], 25 - cfg["P"]))]))
+    beta = np.concatenate([cfg["beta"], 0.1 * rng.standard_normal(25 - cfg["P"])])
+    x0 = np.concatenate([beta, cfg["theta"]])
+    H = g.mcml_hess(cfg["cov"], cfg["data"], cfg["eff_range"], cfg["Z"], Xw, cfg["y"], cfg["U"], cfg["family"], cfg["link"], x0, 1e-3, 0)
+    assert H.shape == (27, 27) and np.all(np.isfinite(H))
+    nr = oracle.mcnr(Xw, cfg["Z"], cfg["U"], cfg["y"], beta, 1.0, oracle.flink(cfg["family"], cfg["link"]))
+    assert np.max(np.abs(H[:25, :25] - nr["xtwx"])) <= 1e-4 * np.max(np.abs(nr["xtwx"]))
+    # and directly: one batch of 40 000 parameter vectors (> 32 768 / P per chunk, > the 16 384-value result buffer)
+    mdl = g.Model(gctx, Xw, cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+    mdl.set_u(cfg["U"])
+    B = np.asfortranarray(beta[:, None] + 1e-3 * rng.standard_normal((25, 40000)))
+    ll = mdl.log_likelihood_batch(B, np.ones(40000))
+    for k in (0, 17, 16384, 39999):
+        assert abs(ll[k] - mdl.log_likelihood(B[:, k], 1.0)) <= 1e-12 * abs(ll[k])
+    mdl.close()
