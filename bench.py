@@ -173,136 +173,136 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# CPU baseline: the oracle's FAITHFUL restatement of the reference CPU path, bounded sample, extrapolated to one step
+# CPU arm: the reference's CPU path (oracle FAITHFUL mode = the reference's loop structure) on a BOUNDED SAMPLE of the step,
+# every piece executed for real — nothing is extrapolated into the arm's value
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(cfg, threads=None, quick=False):
-    """Times the reference's CPU path (oracle FAITHFUL mode) on a bounded sample of the C2 step and extrapolates to the
-    full step.  Returns (seconds for one full step, detail dict)."""
+CPU_SAMPLE_M = 2500       # Monte-Carlo samples of the bounded CPU sample (the GPU arm's step has 10^4)
+
+
+def cpu_reference_sample(cfg, threads=None, m_s=CPU_SAMPLE_M, quick=False):
+    """One pass of the C2 step at m_s samples on the host cores, as the reference runs it (src/mcml_full.cpp:83-126 with Hessian SEs):
+    a single HMC chain of warmup + m_s proposals (mhmcmc.h:121-157), one MCNR step whose update_W(i) redoes the Z u GEMM for every sample
+    (mcmloptim.h:213), N_D_EVALS + N_HESS mvn_ll evaluations that re-factorise every block per sample (mcmldmatrix.h:33-36) and N_HESS
+    log-likelihood evaluations that redo the Z u GEMM (mcmlmodel.h:286).  Returns (seconds, detail); value = m_s / seconds."""
     import oracle
     oracle.build()
     if threads:
         oracle.set_threads(threads)
     nthr = oracle.max_threads() if not threads else threads
+    if quick:
+        m_s = min(m_s, 300)
     fl = oracle.flink(cfg["family"], cfg["link"])
-    X, Z, y, U, beta, theta = cfg["X"], cfg["Z"], cfg["y"], cfg["U"], cfg["beta"], cfg["theta"]
-    m = U.shape[1]
+    X, Z, y, beta, theta = cfg["X"], cfg["Z"], cfg["y"], cfg["beta"], cfg["theta"]
+    U = np.asfortranarray(cfg["U"][:, :m_s])
     ZL = Z @ cfg["L"]
     xb = X @ beta
-    d = {}
-    # 1. sampler: single sequential chain as in the reference; time post-adaptation proposals
-    wu, ns = (100, 60) if quick else (120, 200)
+    P, R = cfg["P"], theta.size
+    rng = np.random.default_rng(99)
+    Bst, Tst = stencil_points(rng, P, R, beta, theta, N_HESS)
+    _, Td = stencil_points(rng, P, R, beta, theta, N_D_EVALS, h=1e-3)
+    d = {"m_sample": m_s, "threads": nthr}
+    warm = 100 if quick else HMC["warmup"]
     t0 = time.perf_counter()
-    ch = oracle.hmc_chain(ZL, cfg["L"], xb, y, 1.0, fl, wu, ns, HMC["lam"], HMC["max_steps"], HMC["target_accept"], 12345, want_u=False)
-    t_h = time.perf_counter() - t0
-    per_prop = t_h / (wu + ns)
-    d["hmc_s_per_proposal"] = per_prop
-    d["hmc_steps_per_proposal"] = ch["total_steps"] / (wu + ns)
-    t_hmc = per_prop * (HMC["warmup"] + m)
-    # 2+5a. E-step log-likelihood, Z u GEMM recomputed per evaluation (mcmlmodel.h:286)
-    reps = 1 if quick else 2
+    ch = oracle.hmc_chain(ZL, cfg["L"], xb, y, 1.0, fl, warm, m_s, HMC["lam"], HMC["max_steps"], HMC["target_accept"], 12345, want_u=False)
+    d["hmc_s"] = time.perf_counter() - t0
+    d["hmc_proposals"] = warm + m_s
+    d["hmc_steps_per_proposal"] = ch["total_steps"] / (warm + m_s)
     t0 = time.perf_counter()
-    for _ in range(reps):
-        oracle.loglik_faithful(X, Z, U, y, beta, 1.0, fl)
-    t_ll = (time.perf_counter() - t0) / reps
-    d["loglik_s_per_eval"] = t_ll
-    # 3. MCNR: Z u GEMM recomputed for EVERY sample (mcmloptim.h:213 -> mcmlmodel.h:121) => O(m^2); time at reduced m
-    ms1, ms2 = (192, 384) if quick else (384, 768)
-    ts = []
-    for msub in (ms1, ms2):
-        best = np.inf
-        for _ in range(2):
-            t0 = time.perf_counter()
-            oracle.mcnr(X, Z, U[:, :msub], y, beta, 1.0, fl, faithful=True)
-            best = min(best, time.perf_counter() - t0)
-        ts.append(best)
-    expo = np.log(ts[1] / ts[0]) / np.log(ms2 / ms1)
-    d["mcnr_scaling_exponent"] = float(expo)
-    t_mcnr = ts[1] * (m / ms2) ** 2
-    d["mcnr_s_extrapolated"] = float(t_mcnr)
-    # 4+5b. mvn_ll with the block Cholesky re-done per sample (mcmldmatrix.h:33-36)
+    oracle.mcnr(X, Z, U, y, beta, 1.0, fl, faithful=True)
+    d["mcnr_s"] = time.perf_counter() - t0
+    n_ll = 16 if quick else N_HESS
     t0 = time.perf_counter()
-    oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], theta, U, faithful=True)
-    t_d = time.perf_counter() - t0
-    d["mvn_ll_s_per_eval"] = t_d
-    total = t_hmc + t_mcnr + N_HESS * t_ll + (N_D_EVALS + N_HESS) * t_d
-    d.update(hmc_s=t_hmc, estep_s=N_HESS * t_ll, mvn_s=(N_D_EVALS + N_HESS) * t_d, threads=nthr)
-    # the same step with the redundant work hoisted (stronger CPU baseline, reported beside the faithful one)
-    zd = oracle.gemm(Z, U)
+    for k in range(n_ll):
+        oracle.loglik_faithful(X, Z, U, y, Bst[:, k], 1.0, fl)
+    d["estep_s"] = (time.perf_counter() - t0) * (N_HESS / n_ll)
+    n_d = 16 if quick else N_D_EVALS + N_HESS
+    Tall = np.concatenate([Td, Tst], axis=1)
     t0 = time.perf_counter()
-    oracle.loglik_zd(zd, xb, y, 1.0, fl)
-    t_llh = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], theta, U, faithful=False)
-    t_dh = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    oracle.mcnr(X, Z, U, y, beta, 1.0, fl, faithful=False)
-    t_mh = time.perf_counter() - t0
-    d["hoisted_step_s"] = float(t_hmc + t_mh + N_HESS * t_llh + (N_D_EVALS + N_HESS) * t_dh)
-    d["hoisted_loglik_s_per_eval"] = t_llh
+    for k in range(n_d):
+        oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], Tall[:, k], U, faithful=True)
+    d["mvn_s"] = (time.perf_counter() - t0) * ((N_D_EVALS + N_HESS) / n_d)
+    total = d["hmc_s"] + d["mcnr_s"] + d["estep_s"] + d["mvn_s"]
     return float(total), d
 
 
-def cpu_reference_step_ref(cfg, threads=None, quick=False):
-    """The same bounded sample on oracle/_ref/libref_omp.so: the reference's own headers (inst/include/glmmrmcml/*.h, compiled where
-    they lie against the stand-in Eigen/Rcpp/glmmrBase headers of oracle/shim, OpenMP pragmas on).  Returns (seconds per full step, detail)."""
+def cpu_hoisted_and_full_m(cfg, det, threads=None, quick=False):
+    """Beside the arm's value: (i) the same sample with the reference's redundant work hoisted (zd built once, one factorisation per theta)
+    — a stronger CPU baseline; (ii) what the faithful step costs at the GPU arm's full m = 10^4, from the measured pieces: sampler and
+    evaluations scale linearly in m, MCNR with the exponent measured here on two sample sizes (labelled an estimate, not the arm's value)."""
     import oracle
-    from oracle import ref
-    oracle.build()
-    if threads:
-        oracle.set_threads(threads)          # one libgomp per process: this also sets the team size of libref_omp.so
-    ref.use_timing_build()
-    nthr = oracle.max_threads() if not threads else threads
-    X, Z, y, U, beta, theta, L = cfg["X"], cfg["Z"], cfg["y"], cfg["U"], cfg["beta"], cfg["theta"], cfg["L"]
-    fam, link = cfg["family"], cfg["link"]
-    m = U.shape[1]
-    d = {}
-    wu, ns = (100, 60) if quick else (120, 200)
-    t0 = time.perf_counter()
-    _, st = ref.mcmc_sample(X, Z, L, y, beta, fam, link, wu, ns, HMC["lam"], 1.0, HMC["max_steps"], HMC["target_accept"], 12345)
-    per_prop = (time.perf_counter() - t0) / (wu + ns)
-    d["hmc_s_per_proposal"] = per_prop
-    t_hmc = per_prop * (HMC["warmup"] + m)
-    t0 = time.perf_counter(); ref.loglik_reps(X, Z, U, y, beta, 1.0, fam, link, 1); t1 = time.perf_counter() - t0
-    r2 = 2 if quick else 3
-    t0 = time.perf_counter(); ref.loglik_reps(X, Z, U, y, beta, 1.0, fam, link, 1 + r2); t2 = time.perf_counter() - t0
-    t_ll = max(t2 - t1, 1e-9) / r2           # one log_likelihood() on an existing model (mcmlmodel.h:284-304, Z u GEMM included)
-    d["loglik_s_per_eval"] = t_ll
-    ms1, ms2 = (96, 192) if quick else (192, 384)
-    start = np.concatenate([beta, theta, [1.0]])
-    ts = []
-    for msub in (ms1, ms2):
-        t0 = time.perf_counter()
-        ref.mcnr(cfg["cov"], cfg["data"], cfg["eff_range"], X, Z, U[:, :msub], y, fam, link, start)
-        ts.append(time.perf_counter() - t0)
-    d["mcnr_scaling_exponent"] = float(np.log(ts[1] / ts[0]) / np.log(ms2 / ms1))
-    t_mcnr = ts[1] * (m / ms2) ** 2          # update_W(i) redoes the Z u GEMM for every sample (mcmloptim.h:213): cost ~ m^2
-    d["mcnr_s_extrapolated"] = float(t_mcnr)
-    t0 = time.perf_counter(); ref.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], theta, U); t_d = time.perf_counter() - t0
-    d["mvn_ll_s_per_eval"] = t_d
-    total = t_hmc + t_mcnr + N_HESS * t_ll + (N_D_EVALS + N_HESS) * t_d
-    d.update(hmc_s=t_hmc, estep_s=N_HESS * t_ll, mvn_s=(N_D_EVALS + N_HESS) * t_d, threads=nthr)
-    return float(total), d
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    X, Z, y, beta, theta = cfg["X"], cfg["Z"], cfg["y"], cfg["beta"], cfg["theta"]
+    m_s = det["m_sample"]
+    U = np.asfortranarray(cfg["U"][:, :m_s])
+    xb = X @ beta
+    zd = oracle.gemm(Z, U)
+    t0 = time.perf_counter(); oracle.loglik_zd(zd, xb, y, 1.0, fl); t_llh = time.perf_counter() - t0
+    t0 = time.perf_counter(); oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], theta, U, faithful=False); t_dh = time.perf_counter() - t0
+    t0 = time.perf_counter(); oracle.mcnr(X, Z, U, y, beta, 1.0, fl, faithful=False); t_mh = time.perf_counter() - t0
+    hoisted = det["hmc_s"] + t_mh + N_HESS * t_llh + (N_D_EVALS + N_HESS) * t_dh
+    m_half = max(64, m_s // 2)
+    t0 = time.perf_counter(); oracle.mcnr(X, Z, np.asfortranarray(U[:, :m_half]), y, beta, 1.0, fl, faithful=True); t_half = time.perf_counter() - t0
+    expo = float(np.log(det["mcnr_s"] / t_half) / np.log(m_s / m_half))
+    f = M_PER_GPU / m_s
+    per_prop = det["hmc_s"] / det["hmc_proposals"]
+    full = per_prop * (HMC["warmup"] + M_PER_GPU) + det["mcnr_s"] * f ** expo + (det["estep_s"] + det["mvn_s"]) * f
+    return {"hoisted_step_s": float(hoisted), "hoisted_value": m_s / hoisted, "hoisted_loglik_s_per_eval": t_llh,
+            "mcnr_scaling_exponent_measured": expo,
+            "full_m_estimate": {"m": M_PER_GPU, "step_s": float(full), "value": M_PER_GPU / full,
+                                "how": "sampler, log-likelihood and mvn_ll pieces x m / m_sample; MCNR x (m / m_sample)^exponent with the exponent measured in this run"}}
 
 
 def cpu_arm(cfg, threads, quick):
-    """(seconds per step, detail, kind, sample description) of the CPU arm.
-
-    The arm's VALUE is the oracle's FAITHFUL port (the reference's loop structure on plain OpenMP loops, close to what Eigen without a vendor
-    BLAS does).  When oracle/_ref holds the OpenMP build of the reference's own headers, the same sample is also timed on it and reported
-    beside the port (`reference_headers`): those headers run on the stand-in Eigen of oracle/shim, whose eagerly evaluated plain-loop matrix
-    kernels are several times slower than the port, so taking that number as the baseline would flatter the GPU arm."""
-    t, det = cpu_reference_step(cfg, threads=threads, quick=quick)
-    sample = ("oracle FAITHFUL (the reference's loop structure incl. its redundant Z u GEMMs and per-sample Cholesky): 320 HMC proposals of one "
-              "chain, 2 full log-lik evals, MCNR at m=384/768 (cost ~ m^2), 1 full mvn_ll eval; extrapolated to one full step")
-    try:
-        from oracle import ref
-        if ref.timing_available():
-            t_ref, det_ref = cpu_reference_step_ref(cfg, threads=threads, quick=True)
-            det["reference_headers"] = {"value": M_PER_GPU / t_ref, "step_s": t_ref, "detail": det_ref,
-                                        "what": "oracle/_ref/libref_omp.so: inst/include/glmmrmcml/*.h compiled where they lie against oracle/shim"}
-    except Exception as e:      # the port's number stands on its own
-        det["reference_headers"] = {"unavailable": str(e)[:200]}
+    """(seconds per bounded sample, detail, kind, sample description) of the CPU arm."""
+    t, det = cpu_reference_sample(cfg, threads=threads, quick=quick)
+    sample = ("oracle FAITHFUL (the reference's loop structure incl. its redundant Z u GEMMs and per-sample Cholesky) on m_sample = %d of the step's "
+              "10^4 samples, every piece run for real: one HMC chain of %d proposals, 1 MCNR step, %d log-likelihood and %d mvn_ll evaluations; "
+              "value = m_sample / time (the reference's MCNR cost grows faster than m, so the smaller sample FAVOURS the CPU arm)"
+              % (det["m_sample"], det["hmc_proposals"], N_HESS, N_D_EVALS + N_HESS))
     return t, det, "port", sample
+
+
+def check_step_against_oracle(cfg, mdl, out, Bst, Tst, m_per_gpu, world, sum_over_ranks, n_pts=4):
+    """The outputs of the timed step (MCNR sums, the first Hessian-stencil log-likelihoods and mvn_ll values) against the oracle on the
+    sample columns the step drew.  Every rank evaluates the oracle on ITS columns; the sums are added over ranks like the device sums."""
+    import oracle
+    oracle.build()
+    nr, ll, dl = out
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    U = mdl.get_u(0, m_per_gpu)
+    zd = oracle.gemm(cfg["Z"], U)
+    m_tot = m_per_gpu * world
+    X = cfg["X"]
+    w, wu, sg = oracle.mcnr_sums_zd(zd, X @ cfg["beta"], cfg["y"], 1.0, fl)
+    w = sum_over_ranks(w); wu = sum_over_ranks(wu); sg = sum_over_ranks(float(sg))
+    xtwx = X.T @ (w[:, None] * X) / m_tot
+    score = X.T @ wu / m_tot
+    res = {"mcnr_xtwx_rel_err": float(np.max(np.abs(nr["xtwx"] - xtwx)) / np.max(np.abs(xtwx))),
+           "mcnr_score_abs_err_over_xtwx": float(np.max(np.abs(nr["score"] - score)) / np.max(np.abs(xtwx))),
+           "mcnr_sigma_rel_err": float(abs(nr["sigma"] - sg / m_tot) / (sg / m_tot))}
+    e_ll, e_d = 0.0, 0.0
+    for k in range(n_pts):
+        _, ps = oracle.loglik_zd(zd, X @ Bst[:, k], cfg["y"], 1.0, fl, per_sample=True)
+        ref = sum_over_ranks(float(np.sum(ps))) / m_tot
+        e_ll = max(e_ll, abs(ll[k] - ref) / abs(ref))
+        ref_d = sum_over_ranks(oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], Tst[:, k], U) * m_per_gpu) / m_tot
+        e_d = max(e_d, abs(dl[k] - ref_d) / abs(ref_d))
+    res.update(loglik_rel_err=float(e_ll), mvn_ll_rel_err=float(e_d), points=n_pts, tol=1e-10, ranks=world)
+    res["ok"] = bool(max(res["mcnr_xtwx_rel_err"], res["mcnr_score_abs_err_over_xtwx"], res["mcnr_sigma_rel_err"], e_ll, e_d) <= 1e-10)
+    return res
+
+
+def vendor_comparators():
+    """cuBLAS Dgemm / cuSOLVER Dpotrf / cuBLAS Dtrsm on the same GPU (tools/vendor_fp64, a stand-alone binary: tools only, the product
+    library never links or calls the vendor BLAS).  None when the binary is missing."""
+    exe = os.path.join(ROOT, "tools", "vendor_fp64")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+        return json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:
+        return {"error": str(e)[:300]}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -314,6 +314,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="smaller CPU samples (for tests)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the large configurations C3 / C4 / C5")
+    ap.add_argument("--configs-size", default="full", choices=["full", "small"], help="size of the large configurations (small: for tests)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -343,11 +345,14 @@ def main():
         vals, det = [], None
         ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         for it in range(args.warmup + args.steps):
-            t, det, kind, sample = cpu_arm(cfg, ncores, args.quick)   # torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly
+            # warm-up steps run a small sample (page-in, thread pool start); torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly
+            t, d, kind, smp = cpu_arm(cfg, ncores, args.quick or it < args.warmup)
             if it >= args.warmup:
-                vals.append(t)
+                vals.append(t); det = d; sample = smp
         t_step = float(np.median(vals)) if vals else float("nan")
-        v = M_PER_GPU / t_step
+        v = det["m_sample"] / t_step
+        if not args.quick:
+            det.update(cpu_hoisted_and_full_m(cfg, det, ncores))
         line = {"metric": "u-samples/s through sampler + E-step", "value": v, "unit": "u-samples/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
@@ -392,6 +397,8 @@ def main():
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(ids[0], rank, world)
     ctx.make_default()
+    from tools import bench_configs as bc
+    env = bc.Env(g, ctx, rank, world, dist, hbm_gbs=load_peaks()[0]["hbm_gbs"])      # rank / world and array reductions for the oracle checks
 
     P, Q, R = cfg["P"], cfg["Q"], cfg["theta"].size
     beta, theta = cfg["beta"], cfg["theta"]
@@ -439,7 +446,9 @@ def main():
     launches = sum_over_ranks(ctx.launch_count - l0)
     ms_step = max_over_ranks(ms) / args.steps
     value = M_PER_GPU * world / (ms_step * 1e-3)
-    assert np.all(np.isfinite(out[1])) and np.all(np.isfinite(out[2]))
+    # the timed step's own outputs against the oracle on the samples it drew (all ranks: local oracle sums, summed like the device sums)
+    step_parity = check_step_against_oracle(cfg, mdl, out, Bst, Tst, M_PER_GPU, world, env.sum)
+    assert step_parity["ok"], step_parity
 
     # ---- end to end through the reference-named C-ABI entry points with host buffers (what the R loop calls) ----
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
@@ -515,6 +524,22 @@ def main():
     ctx.timer_start(); [mdl.mcnr(beta, 1.0) for _ in range(16)]; t_n = ctx.timer_stop()
     extra["mcnr_steps_per_s"] = 16 / (t_n * 1e-3)
 
+    # ---- BASELINE.json's large configurations at their stated size, with in-run oracle parity (tools/bench_configs.py) ----
+    configs = None
+    if not args.no_configs:
+        import oracle as orc
+        orc.build()
+        if world > 1:
+            orc.set_threads(max(1, (os.cpu_count() or world) // world))      # torchrun exports OMP_NUM_THREADS=1; the checker may use this rank's share
+        configs = {"scaling": "strong: m (sample columns) and chains are split over the ranks; C3 (m = 250) does not shard and runs at N = 1 only",
+                   "size": args.configs_size}
+        for nm in (["C3"] if world == 1 else []) + ["C4", "C5"]:
+            t0c = time.perf_counter()
+            configs[nm] = bc.run_config(nm, env, size=args.configs_size, oracle=orc)
+            configs[nm]["wall_s"] = round(time.perf_counter() - t0c, 1)
+            if rank == 0:
+                print("[bench] %s done in %.1f s, parity ok = %s" % (nm, configs[nm]["wall_s"], configs[nm]["parity"]["ok"]), file=sys.stderr, flush=True)
+
     # every collective of this run is behind us: tear the process group down on all ranks together, before rank 0's solo work
     barrier()
     if dist is not None:
@@ -586,11 +611,15 @@ def main():
     if rank != 0:
         return
     cpu = None
+    comparators = None
     if world == 1 and not args.no_cpu_baseline:
         ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         t_cpu, det, kind, sample = cpu_arm(cfg, ncores, args.quick)
-        cpu = {"value": M_PER_GPU / t_cpu, "unit": "u-samples/s", "cores": det["threads"], "kind": kind, "sample": sample, "step_s": t_cpu,
-               "hoisted_value": M_PER_GPU / det["hoisted_step_s"], "detail": det}
+        if not args.quick:
+            det.update(cpu_hoisted_and_full_m(cfg, det, ncores))
+        cpu = {"value": det["m_sample"] / t_cpu, "unit": "u-samples/s", "cores": det["threads"], "kind": kind, "sample": sample, "sample_s": t_cpu,
+               "hoisted_value": det.get("hoisted_value"), "detail": det}
+        comparators = vendor_comparators()
     line = {"metric": "u-samples/s through sampler + E-step", "value": value, "unit": "u-samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
@@ -599,7 +628,8 @@ def main():
                     "parts_s": {k: float(np.mean(v)) for k, v in e2e_parts.items()}},
             "gpu_launches": int(launches), "clocks": clk, "wall_s": wall,
             "roofline": sampler_roofline(st, hmc_exec_tflops, hmc_tflops, exec_per_step, cfg, Q, roofline_sat, roofline_many),
-            "roofline_estep": roofline_estep, "cpu_baseline": cpu}
+            "roofline_estep": roofline_estep, "cpu_baseline": cpu, "step_parity": step_parity, "configs": configs,
+            "vendor_fp64_comparators": comparators}
     line.update(extra)
     emit(line)
 

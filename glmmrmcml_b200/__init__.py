@@ -205,6 +205,14 @@ class Model:
     def use_device_u(self, niter_total=0):
         check(lib().gmb_model_use_device_u(self._h, int(niter_total)))
 
+    def get_u(self, col0=0, ncols=None):
+        """Columns [col0, col0 + ncols) of this rank's device-resident sample matrix (gmb_model_get_u)."""
+        if ncols is None:
+            raise ValueError("ncols is required")
+        out = np.zeros((self.Q, int(ncols)), order="F")
+        check(lib().gmb_model_get_u(self._h, int(col0), int(ncols), _d(out)))
+        return out
+
     def log_likelihood(self, beta, var_par=1.0) -> float:
         """mcmlModel::log_likelihood after update_beta (mcmlmodel.h:100-102, 284-304)."""
         beta = _v(beta)

@@ -347,8 +347,9 @@ __global__ void expand_blocks_kernel(int B, const CovBlock* __restrict__ blocks,
                                      const double* __restrict__ data, const double* __restrict__ theta,
                                      const double* __restrict__ Lblk, int chol, double* __restrict__ out, int ld) {
     const CovBlock b = blocks[blockIdx.x];
-    for (int e = threadIdx.x; e < b.n * b.n; e += blockDim.x) {
-        int i = e % b.n, j = e / b.n;
+    const long long nn = (long long)b.n * b.n;
+    for (long long e = (long long)blockIdx.y * blockDim.x + threadIdx.x; e < nn; e += (long long)gridDim.y * blockDim.x) {
+        const int i = (int)(e % b.n), j = (int)(e / b.n);
         double v = chol ? ((j <= i) ? Lblk[b.l0 + i + (size_t)j * gmb_cov_ld(b.n)] : 0.0) : block_val(b, fns, data, theta, i, j);
         out[(size_t)(b.start + j) * ld + b.start + i] = v;
     }
@@ -518,6 +519,12 @@ int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_ou
     return GMB_OK;
 }
 
+// CTAs per block of expand_blocks_kernel: one for small blocks, enough to fill the machine for a large one
+static int expand_chunks(const gmb_cov* cv) {
+    const long long per = ((long long)cv->max_n * cv->max_n + 256 * 8 - 1) / (256 * 8);
+    return (int)std::max<long long>(1, std::min<long long>(per, 2048));
+}
+
 // dense Q x Q D(theta) (chol = 0) or its lower Cholesky factor (chol = 1) into a device matrix with leading dimension ld
 // (zero outside the blocks).  Returns GMB_ENOTPD when a block is not positive definite.
 int gmb_cov_gen_device(gmb_cov* cv, const double* theta, int chol, double* d_out, int ld) {
@@ -529,7 +536,7 @@ int gmb_cov_gen_device(gmb_cov* cv, const double* theta, int chol, double* d_out
         cv->factor_valid = false;
     }
     GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)ld * cv->Q, ctx->stream));
-    expand_blocks_kernel<<<cv->B, 256, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_Lblk, chol, d_out, ld);
+    expand_blocks_kernel<<<dim3(cv->B, expand_chunks(cv)), 256, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_Lblk, chol, d_out, ld);
     ctx->launches++;
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;
@@ -550,7 +557,7 @@ extern "C" int gmb_cov_gen(gmb_cov* cv, const double* theta, int chol, double* L
     double* dense = nullptr;
     GMB_CUDA(gmb_dmalloc(ctx, &dense, sizeof(double) * Q * Q));
     GMB_CUDA(cudaMemsetAsync(dense, 0, sizeof(double) * Q * Q, ctx->stream));
-    expand_blocks_kernel<<<cv->B, 256, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_Lblk, chol, dense, (int)Q);
+    expand_blocks_kernel<<<dim3(cv->B, expand_chunks(cv)), 256, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->d_Lblk, chol, dense, (int)Q);
     ctx->launches++;
     cudaError_t e = cudaMemcpyAsync(L_out, dense, sizeof(double) * Q * Q, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);

@@ -210,6 +210,17 @@ extern "C" int gmb_model_use_device_u(gmb_model* mdl, int niter_total) {
     return GMB_OK;
 }
 
+extern "C" int gmb_model_get_u(gmb_model* mdl, int col0, int ncols, double* U_out) {
+    if (!mdl || !U_out || col0 < 0 || ncols < 0) return gmb_set_error(GMB_EINVAL, "gmb_model_get_u: bad arguments");
+    if (!mdl->dU || col0 + ncols > mdl->m_local) return gmb_set_error(GMB_ESTATE, "the model holds %d sample columns, asked for [%d, %d)", mdl->dU ? mdl->m_local : 0, col0, col0 + ncols);
+    if (ncols == 0) return GMB_OK;
+    GMB_CUDA(cudaSetDevice(mdl->ctx->device));
+    GMB_CUDA(cudaMemcpy2DAsync(U_out, (size_t)mdl->Q * sizeof(double), mdl->dU + (size_t)col0 * mdl->ldq, (size_t)mdl->ldq * sizeof(double),
+                               (size_t)mdl->Q * sizeof(double), ncols, cudaMemcpyDeviceToHost, mdl->ctx->stream));
+    GMB_CUDA(cudaStreamSynchronize(mdl->ctx->stream));
+    return GMB_OK;
+}
+
 static int check_ready(gmb_model* mdl, const double* beta) {
     if (!mdl || !beta) return gmb_set_error(GMB_EINVAL, "model or beta is NULL");
     if (!mdl->zd_valid) return gmb_set_error(GMB_ESTATE, "no samples set: call gmb_model_set_u (or gmb_hmc_sample + gmb_model_use_device_u) first");

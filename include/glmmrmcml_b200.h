@@ -80,6 +80,10 @@ int gmb_model_set_u(gmb_model* mdl, const double* U, int Q, int m_local, int m_t
 /* Same, but the samples are already on the device from gmb_hmc_sample(..., keep_on_device=1). */
 int gmb_model_use_device_u(gmb_model* mdl, int niter_total);
 
+/* Copies `ncols` columns, starting at column col0, of this rank's device-resident sample matrix u (Q x m_local: what gmb_model_set_u
+ * uploaded or gmb_hmc_sample(..., keep_on_device) left behind) into U_out (Q x ncols, column-major). */
+int gmb_model_get_u(gmb_model* mdl, int col0, int ncols, double* U_out);
+
 /* E-step objective, mcmlModel::log_likelihood mcmlmodel.h:284-304 after update_beta(beta) (:100-102):
  * mean_j sum_i l(y_i, (X beta)_i + zd_ij ; var_par).  All-reduced over ranks. */
 int gmb_model_loglik(gmb_model* mdl, const double* beta, double var_par, double* out);

@@ -46,6 +46,7 @@ def lib():
         _LIB.orc_loglik_zd.restype = C.c_double
         _LIB.orc_loglik_faithful.restype = C.c_double
         _LIB.orc_mvn_loglik.restype = C.c_double
+        _LIB.orc_mcnr_sums_zd.restype = C.c_double
         _LIB.orc_logdet.restype = C.c_double
         _LIB.orc_log_prob.restype = C.c_double
         _LIB.orc_rng_uniform.restype = C.c_double
@@ -117,6 +118,15 @@ def mcnr(X, Z, U, y, beta, var_par, fl, niter=None, faithful=False):
     rc = lib().orc_mcnr(n, P, Q, niter, _d(X), _d(Z), _d(U), _d(y), _d(beta), C.c_double(var_par), int(fl),
                         int(bool(faithful)), _d(xtwx), _d(score), _d(incr), C.byref(sigma))
     return dict(xtwx=xtwx, score=score, beta_incr=incr, sigma=sigma.value, rc=rc)
+
+
+def mcnr_sums_zd(zd, xb, y, var_par, fl):
+    """Raw MCNR sums over the columns of zd (mcmloptim.h:210-223): (wsum[n], wusum[n], sum_j sd(resid_j)); see orc_mcnr_sums_zd."""
+    zd = _f(zd); n, m = zd.shape
+    xb = np.ascontiguousarray(xb, dtype=np.float64); y = np.ascontiguousarray(y, dtype=np.float64)
+    w = np.zeros(n); wu = np.zeros(n)
+    sg = lib().orc_mcnr_sums_zd(n, m, _d(zd), _d(xb), _d(y), C.c_double(var_par), int(fl), _d(w), _d(wu))
+    return w, wu, sg
 
 
 def cov_dims(cov, data):

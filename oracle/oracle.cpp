@@ -148,17 +148,24 @@ static void gemm_nn(int M, int N, int K, const double* A, const double* B, doubl
     }
 }
 
-// y = A (M x K) * x
+// y = A (M x K) * x.  Large products are split over row chunks (each row's sum keeps its order in k: same bits as the serial loop).
 static void gemv_n(int M, int K, const double* A, const double* x, double* y) {
-    for (int i = 0; i < M; i++) y[i] = 0;
-    for (int k = 0; k < K; k++) {
-        const double* a = A + (size_t)k * M; double xv = x[k];
-        for (int i = 0; i < M; i++) y[i] += a[i] * xv;
+    const bool big = (size_t)M * K > ((size_t)1 << 22);
+#pragma omp parallel for schedule(static) if (big)
+    for (int i0 = 0; i0 < M; i0 += 1024) {
+        const int i1 = std::min(M, i0 + 1024);
+        for (int i = i0; i < i1; i++) y[i] = 0;
+        for (int k = 0; k < K; k++) {
+            const double* a = A + (size_t)k * M; double xv = x[k];
+            for (int i = i0; i < i1; i++) y[i] += a[i] * xv;
+        }
     }
 }
 
 // y = A^T (K x M from A M x K) * x  (x length M, y length K)
 static void gemv_t(int M, int K, const double* A, const double* x, double* y) {
+    const bool big = (size_t)M * K > ((size_t)1 << 22);
+#pragma omp parallel for schedule(static) if (big)
     for (int k = 0; k < K; k++) {
         const double* a = A + (size_t)k * M; double s = 0;
         for (int i = 0; i < M; i++) s += a[i] * x[i];
@@ -318,6 +325,48 @@ ORC_API int orc_mcnr(int n, int P, int Q, int niter, const double* X, const doub
     std::memcpy(xtwx, XtWX.data(), sizeof(double) * P * P);
     std::memcpy(score, sc.data(), sizeof(double) * P);
     return solve_spd_or_lu(P, XtWX, sc, beta_incr);                         // :230,232
+}
+
+// The same per-sample terms on a caller-supplied zd (n x m), summed over its m columns WITHOUT the final division, so that a caller can
+// walk a large sample matrix in column chunks: wsum_i = sum_j W_j,ii ; wusum_i = sum_j Wu_ij ; returns sum_j sd(resid_j).
+// mean_j X^T W_j X = X^T diag(wsum / m) X (mcmloptim.h:217,227-229: the same sums in a different order).  OpenMP over samples with
+// per-thread row accumulators added in thread order.
+ORC_API double orc_mcnr_sums_zd(int n, int m, const double* zd, const double* xb, const double* y, double var_par, int flink,
+                                double* wsum, double* wusum) {
+    int fam, lnk; flink_to_family_link(flink, &fam, &lnk);
+    if (fam < 0) return NAN;
+    double nvar_par = 1.0;
+    if (fam == 2) nvar_par *= var_par * var_par;
+    const int T = omp_get_max_threads();
+    std::vector<double> wacc((size_t)T * n, 0.0), uacc((size_t)T * n, 0.0), sg(T, 0.0);
+#pragma omp parallel
+    {
+        const int t = omp_get_thread_num();
+        double* wa = wacc.data() + (size_t)t * n; double* ua = uacc.data() + (size_t)t * n;
+        std::vector<double> resid(n);
+#pragma omp for schedule(static)
+        for (int j = 0; j < m; j++) {
+            const double* z = zd + (size_t)j * n;
+            double mean = 0;
+            for (int i = 0; i < n; i++) { resid[i] = y[i] - inv_link(xb[i] + z[i], lnk); mean += resid[i]; }
+            mean /= n;
+            double ss = 0;
+            for (int i = 0; i < n; i++) {
+                ss += (resid[i] - mean) * (resid[i] - mean);
+                const double W = 1 / (dhdmu(xb[i] + z[i], fam, lnk) * nvar_par);
+                wa[i] += W;
+                ua[i] += W * detadmu(xb[i] + z[i], lnk) * resid[i];
+            }
+            sg[t] += std::sqrt(ss / (n - 1));
+        }
+    }
+    double s = 0;
+    for (int i = 0; i < n; i++) { wsum[i] = 0; wusum[i] = 0; }
+    for (int t = 0; t < T; t++) {
+        s += sg[t];
+        for (int i = 0; i < n; i++) { wsum[i] += wacc[(size_t)t * n + i]; wusum[i] += uacc[(size_t)t * n + i]; }
+    }
+    return s;
 }
 
 // ----------------------------------------------------------------------------------------------

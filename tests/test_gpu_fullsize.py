@@ -1,6 +1,9 @@
-"""Size-independent properties at BASELINE.json's full C2 size (n = 500, Q = 50, m = 10^4) and on a zd larger than L2,
-where the CPU oracle is too slow to be the checker: additivity over column splits (the E-step quantities are means of
-per-sample terms), determinism, agreement of the sampler's cluster variants, Monte-Carlo agreement across seeds."""
+"""BASELINE.json's configurations at their FULL stated size.
+
+C2 (n = 500, Q = 50, m = 10^4): the oracle checks every E-step quantity directly (it needs milliseconds at this size), plus
+size-independent properties — additivity over column splits, determinism, agreement of the sampler's kernel variants, Monte-Carlo
+agreement across seeds.  C3 (n = Q = 10^4), C4 (m = 10^5) and C5 (n = 5 10^4, Q = 5 10^3, m = 10^4): tools/bench_configs.run_config,
+the block bench.py emits, whose `parity` object compares the GPU with the oracle (LAPACK for the one dense 10^4 block) on the same inputs."""
 import numpy as np
 import pytest
 
@@ -101,3 +104,47 @@ def test_sampler_posterior_means_agree_across_seeds_at_bench_size(c2):
         means.append(cm.mean(axis=1)); ses.append(cm.std(axis=1, ddof=1) / np.sqrt(250))
     z = np.abs(means[0] - means[1]) / np.sqrt(ses[0] ** 2 + ses[1] ** 2)
     assert np.max(z) < 6.0, np.max(z)
+
+
+def test_c2_full_size_against_the_oracle(c2, oracle):
+    """m = 10^4: log-likelihood (single, batched), MCNR sums and mvn_ll against the oracle at 1e-10."""
+    cfg, mdl, cv = c2
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    mdl.set_u(cfg["U"])
+    zd = oracle.gemm(cfg["Z"], cfg["U"])
+    rng = np.random.default_rng(2)
+    B = np.asfortranarray(cfg["beta"][:, None] + 1e-2 * rng.standard_normal((cfg["P"], 16)))
+    llb = mdl.log_likelihood_batch(B, np.ones(16))
+    for k in range(16):
+        ref = oracle.loglik_zd(zd, cfg["X"] @ B[:, k], cfg["y"], 1.0, fl)
+        assert abs(llb[k] - ref) <= 1e-10 * abs(ref)
+        if k < 3:
+            assert abs(mdl.log_likelihood(B[:, k], 1.0) - ref) <= 1e-10 * abs(ref)
+    nr = mdl.mcnr(cfg["beta"], 1.0)
+    ref = oracle.mcnr(cfg["X"], cfg["Z"], cfg["U"], cfg["y"], cfg["beta"], 1.0, fl)
+    assert np.max(np.abs(nr["xtwx"] - ref["xtwx"])) <= 1e-10 * np.max(np.abs(ref["xtwx"]))
+    assert np.max(np.abs(nr["score"] - ref["score"])) <= 1e-10 * np.max(np.abs(ref["xtwx"]))
+    assert abs(nr["sigma"] - ref["sigma"]) <= 1e-10 * ref["sigma"]
+    for th in (cfg["theta"], cfg["theta"] * np.array([1.3, 0.9])):
+        r = oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], th, cfg["U"])
+        assert abs(cv.loglik_model(th, mdl) - r) <= 1e-10 * abs(r)
+        assert abs(cv.loglik(th, cfg["U"]) - r) <= 1e-10 * abs(r)
+
+
+@pytest.mark.parametrize("name", ["C3", "C4", "C5"])
+def test_large_configs_full_size_parity(gctx, oracle, name):
+    """C3 at n = Q = 10^4 (Cholesky + solves of one 10^4 block, factored sampler), C4 at m = 10^5 (8 GB of samples, component sampler),
+    C5 at n = 5 10^4, Q = 5 10^3, m = 10^4 — every parity field of the bench block within its tolerance."""
+    import glmmrmcml_b200 as g
+    from tools import bench_configs as bc
+    out = bc.run_config(name, bc.Env(g, gctx), size="full", oracle=oracle)
+    p = out["parity"]
+    assert p["loglik"]["rel_err"] <= 1e-10 and p["loglik"]["rel_err_default_path"] <= 1e-10, p
+    assert max(p["mcnr"]["xtwx_rel_err"], p["mcnr"]["score_rel_err"], p["mcnr"]["sigma_rel_err"]) <= 1e-10, p
+    assert p["mvn_ll"]["rel_err"] <= 1e-10, p
+    assert p["loglik_on_sampled_u"]["rel_err"] <= 1e-10, p
+    assert p["log_prob"]["rel_err"] <= 1e-10 and p["log_grad"]["rel_err"] <= 1e-10, p
+    assert p["chain"]["max_abs_err"] <= 1e-7 and p["chain"]["same_kernel_as_timed_run"], p
+    if "chol" in p:
+        assert p["chol"]["ok"], p
+    assert p["ok"]
