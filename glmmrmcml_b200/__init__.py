@@ -84,6 +84,12 @@ def estep_set_rowstats(on: bool):
     check(lib().gmb_estep_set_rowstats(int(bool(on))))
 
 
+def mcml_set_importance_form(reference_form: bool):
+    """mcml_simlik's importance-weighted objective: False (default) = log space, True = the reference's -log(exp(ll + logl) / exp(denomD))
+    (likelihood.h:101-105), which underflows for all but small models (gmb_mcml_set_importance_form)."""
+    check(lib().gmb_mcml_set_importance_form(int(bool(reference_form))))
+
+
 def version() -> str:
     return lib().gmb_version().decode()
 
@@ -185,7 +191,8 @@ class Model:
 
     def close(self):
         if self._h:
-            lib().gmb_model_destroy(self._h)
+            if self.ctx._h:                       # a handle that outlives its context is dropped, not destroyed (the context owned its memory pool)
+                lib().gmb_model_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):
@@ -278,7 +285,8 @@ class Covariance:
 
     def close(self):
         if self._h:
-            lib().gmb_cov_destroy(self._h)
+            if self.ctx._h:
+                lib().gmb_cov_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "gmb_cov_set_gram": (C.c_int, [C.c_int]),
     "gmb_model_logprob_grad": (C.c_int, [vp, dp, dp, C.c_double, dp, C.c_int, dp, dp]),
     "gmb_set_default_ctx": (C.c_int, [vp]),
+    "gmb_mcml_set_importance_form": (C.c_int, [C.c_int]),
     "gmb_cov_shape": (C.c_int, [ip, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gmb_mvn_ll": (C.c_int, _cov_args + [dp, C.c_int, dp, C.c_int, C.c_int, dp]),
     "gmb_mcmc_sample": (C.c_int, [dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int,

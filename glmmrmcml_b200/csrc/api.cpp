@@ -25,6 +25,7 @@ int default_ctx(gmb_ctx** out) {
 }
 
 const double kInf = std::numeric_limits<double>::infinity();
+int g_importance_reference_form = 0;     // gmb_mcml_set_importance_form
 
 struct Fit {
     gmb_ctx* ctx = nullptr;
@@ -147,8 +148,12 @@ struct Fit {
         GMB_TRY(self->eval_d_batch(X, n, self->P, k, dl.data()));
         for (int c = 0; c < k; c++) {
             const double logl = dl[c];
-            // importance: -log(exp(ll + logl) / exp(denomD)) evaluated in log space (the reference form underflows)
-            f[c] = a->importance ? -1.0 * (ll[c] + logl - a->denomD) : -1.0 * (ll[c] + logl);
+            if (!a->importance) f[c] = -1.0 * (ll[c] + logl);
+            else if (g_importance_reference_form) {                  // likelihood.h:101-105 as written: du = exp(ll + logl) / exp(denomD); -log(du)
+                const double du = std::exp(ll[c] + logl) / std::exp(a->denomD);
+                f[c] = -1.0 * std::log(du);
+            } else f[c] = -1.0 * (ll[c] + logl - a->denomD);          // the same quantity in log space (default: the written form underflows to
+                                                                      // -log(0 / 0) once |ll + logl| exceeds ~745)
         }
         return GMB_OK;
     }
@@ -235,6 +240,8 @@ int default_chains(int m) {
 }  // namespace
 
 int gmb_default_ctx(gmb_ctx** out) { return default_ctx(out); }   // for laplace.cu
+
+extern "C" int gmb_mcml_set_importance_form(int reference_form) { g_importance_reference_form = reference_form ? 1 : 0; return GMB_OK; }
 
 // DData::n_cov_pars() and the total block dimension from the cov matrix alone (host arithmetic; lets an adapter size
 // its theta output before calling an entry point).  Parameter counts per function id: R/R6ModelExtMCML.R:430.

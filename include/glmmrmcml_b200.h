@@ -241,6 +241,11 @@ int gmb_mcml_simlik(const int32_t* cov, int cov_rows, const double* data, int n_
                     const char* family, const char* link, const double* start, int n_start, int trace,
                     double* beta_out, double* theta_out, double* sigma_out);
 
+/* Importance-weighted objective of mcml_simlik (F_likelihood with importance = true, likelihood.h:101-105): 0 (default) = evaluated in
+ * log space, -(ll + logl - denomD); 1 = exactly as the reference writes it, -log(exp(ll + logl) / exp(denomD)), which is the same number
+ * while exp() stays in range and -log(0 / 0) = NaN beyond (|ll + logl| > ~745: any model with more than a few hundred observations). */
+int gmb_mcml_set_importance_form(int reference_form);
+
 /* mcml_hess, src/mcml_optim.cpp:263-285: (P+R) x (P+R) finite-difference Hessian of F_likelihood (optimhess stencil). */
 int gmb_mcml_hess(const int32_t* cov, int cov_rows, const double* data, int n_data, const double* eff_range, int n_eff,
                   const double* Z, const double* X, const double* y, const double* u, int n, int P, int Q, int m,

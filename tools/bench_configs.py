@@ -291,7 +291,7 @@ def run_config(name, env, size="full", oracle=None, check=True):
             Lg = cv.genD(th1, chol=True)
             import scipy.linalg.lapack as lap
             anorm = float(np.max(np.sum(np.abs(D1), axis=0)))
-            rcond, info = lap.dpocon(Lh, anorm, lower=1)
+            rcond, info = lap.dpocon(Lh, anorm, uplo='L')
             kappa = 1.0 / rcond if rcond > 0 else float("inf")
             err = float(np.max(np.abs(Lg - Lh)) / np.max(np.abs(Lh)))
             parity["chol"] = {"max_rel_err": err, "kappa_1": kappa, "err_over_kappa_eps": err / (kappa * 2.220446049250313e-16), "tol": "1e-12 kappa",
