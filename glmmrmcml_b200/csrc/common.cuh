@@ -75,6 +75,8 @@ struct gmb_ctx {
     int rank = 0, world = 1;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // internal (sampler kernel time)
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;   // gmb_ctx_timer_start / _stop
+    cudaStream_t stream2 = nullptr;             // high-priority side stream: panel factorisations running ahead of the trailing updates (cov_large.cu)
+    cudaEvent_t evp = nullptr, evn = nullptr, evj = nullptr;   // panel-ready / narrow-update-done / join events of that look-ahead
     void* d_flush = nullptr; int flush_val = 0; // gmb_ctx_flush_l2
 };
 
@@ -198,6 +200,8 @@ int gmb_dgemm(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double 
               const double* B, int ldb, double beta, double* C, int ldc);
 int gmb_dgemm_tri(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
                   const double* B, int ldb, double beta, double* C, int ldc, int lower_a);
+int gmb_dgemm_rowpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias A
+int gmb_dgemm_colpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias B
 
 // estep.cu
 int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb);
@@ -401,27 +405,62 @@ __device__ __forceinline__ double dev_log_factorial_approx(double n) {
     return n * log(n) - n + log(n * (1 + 4 * n * (1 + 2 * n))) / 6 + log(GMB_PI_FAMILY) / 2;
 }
 
-// Per-observation log-density with the reference's algebra (moremaths.h:26-102), in-scope cases.
-//   FL 1: poisson/log   : y*eta - exp(eta) - rowc        (rowc = log_factorial_approx(y), hoisted per row)
-//   FL 3: binomial/logit: y==1: log(1/(1+exp(-eta))) ; y==0: log(1 - 1/(1+exp(-eta)))
-//   FL 7: gaussian/id   : c0 - 0.5*((y-eta)*inv_sigma)^2  (c0 = -log(sigma) - 0.5*log(2*3.141593))
+// family/link codes with device kernels (mcmlmodel.h:74-87): 1 poisson/log, 2 poisson/identity, 3 binomial/logit, 4 binomial/log,
+// 5 binomial/identity, 6 binomial/probit, 7 gaussian/identity, 8 gaussian/log.  1, 3 and 7 (the north-star's) run on every kernel family;
+// the others on the general kernels (streaming E-step, two-contraction sampler).
+__host__ __device__ static inline bool gmb_flink_supported(int fl) { return fl >= 1 && fl <= 8; }
+__host__ __device__ static inline bool gmb_flink_core(int fl) { return fl == 1 || fl == 3 || fl == 7; }
+__host__ __device__ static inline bool gmb_flink_gaussian(int fl) { return fl == 7 || fl == 8; }
+
+// Per-observation log-density with the reference's algebra (moremaths.h:26-102).
+//   FL 1: poisson/log      : y*eta - exp(eta) - rowc          (rowc = log_factorial_approx(y), hoisted per row)
+//   FL 2: poisson/identity : y*log(eta) - eta - rowc
+//   FL 3: binomial/logit   : y==1: log(1/(1+exp(-eta))) ; y==0: log(1 - 1/(1+exp(-eta)))
+//   FL 4: binomial/log     : y==1: eta ; y==0: log(1 - exp(eta))
+//   FL 5: binomial/identity: y==1: log(eta) ; y==0: log(1 - eta)
+//   FL 6: binomial/probit  : y==1: log Phi(eta) ; y==0: log(1 - Phi(eta))      (R::pnorm, :69-75)
+//   FL 7: gaussian/identity: c0 - 0.5*((y-eta)/sigma)^2         (c0 = -log(sigma) - 0.5*log(2*3.141593))
+//   FL 8: gaussian/log     : c0 - 0.5*((log(y)-eta)/sigma)^2    (y here is what the model stores: the constructor already replaced it
+//                            by log y, mcmlmodel.h:90-92, so the reference takes the logarithm twice, moremaths.h:81 — kept as is)
+// Binomial codes leave responses other than 0 / 1 out of the sum (the reference leaves logl unset there).
 template <int FL>
 __device__ __forceinline__ double dev_family_ll(double y, double eta, double rowc, double c0, double sigma) {
     if (FL == 1) {
         return y * eta - exp(eta) - rowc;
+    } else if (FL == 2) {
+        return y * log(eta) - eta - rowc;
     } else if (FL == 3) {
         double p = 1.0 / (1.0 + exp(-1.0 * eta));
         double r = 0.0;
         if (y == 1.0) r = log(p);
         else if (y == 0.0) r = log(1.0 - p);
         return r;
-    } else {
+    } else if (FL == 4) {
+        double r = 0.0;
+        if (y == 1.0) r = eta;
+        else if (y == 0.0) r = log(1.0 - exp(eta));
+        return r;
+    } else if (FL == 5) {
+        double r = 0.0;
+        if (y == 1.0) r = log(eta);
+        else if (y == 0.0) r = log(1.0 - eta);
+        return r;
+    } else if (FL == 6) {
+        double r = 0.0;
+        if (y == 1.0) r = log(normcdf(eta));
+        else if (y == 0.0) r = log(1.0 - normcdf(eta));
+        return r;
+    } else if (FL == 7) {
         double z = (y - eta) / sigma;
+        return c0 - 0.5 * z * z;
+    } else {
+        double z = (log(y) - eta) / sigma;
         return c0 - 0.5 * z * z;
     }
 }
 
-// gradient residual r(eta) of mcmlmodel.h:170-175 (FL 1), :184-193 (FL 3), :233-238 (FL 7, without the 1/sigma^2)
+// gradient residual r(eta) of mcmlmodel.h:170-175 (FL 1), :176-183 (2), :184-193 (3), :194-206 (4), :207-219 (5), :220-232 (6), :233-244 (7, 8:
+// without the 1/sigma^2).  Codes 4-6 as the reference writes them (e.g. the y == 0 branch of code 4 carries the reference's sign).
 template <int FL, bool FAST = false>
 __device__ __forceinline__ double dev_family_resid(double y, double eta) {
     if (FAST) {
@@ -430,6 +469,15 @@ __device__ __forceinline__ double dev_family_resid(double y, double eta) {
     } else {
         if (FL == 1) return y - exp(eta);
         if (FL == 3) return 1.0 / (exp(eta) + 1.0) + y - 1.0;
+    }
+    if (FL == 2) return y * (1.0 / eta) - 1.0;
+    if (FL == 4) { if (y == 1.0) return 1.0; if (y == 0.0) return exp(eta) / (1.0 - exp(eta)); return eta; }
+    if (FL == 5) { if (y == 1.0) return 1.0 / eta; if (y == 0.0) return -1.0 / (1.0 - eta); return eta; }
+    if (FL == 6) {
+        const double pdf = 0.3989422804014327 * exp(-0.5 * eta * eta);      // R::dnorm(eta, 0, 1)
+        if (y == 1.0) return pdf / normcdf(eta);
+        if (y == 0.0) return -1.0 * pdf / (1.0 - normcdf(eta));
+        return eta;
     }
     return y - eta;
 }
@@ -458,6 +506,25 @@ __device__ __forceinline__ double dev_family_ll_w(double lc, double lys, double 
         const double z = (lys - eta) / sigma;
         return lc * c0 - 0.5 * (lsq / (sigma * sigma) + lc * z * z);
     }
+}
+
+// Covariance kernel functions (glmmrBase DSubMatrix::get_val; SURVEY.md App. C.2 — reconstructed, the table lives here for the device side and
+// in oracle/oracle.cpp cov_fn for the oracle): entry = prod_k f_k(dist_k; theta), eff = the function's effective range (compact support).
+//   1 gr  2 fexp0  3 ar1  4 sqexp  7 wend0  8 wend1  9 wend2  13 fexp  14 sqexp0
+__host__ __device__ static inline bool gmb_cov_fn_supported(int id) { return id == 1 || id == 2 || id == 3 || id == 4 || id == 7 || id == 8 || id == 9 || id == 13 || id == 14; }
+__device__ __forceinline__ double dev_cov_fn(int id, double d, const double* th, double eff) {
+    switch (id) {
+    case 1:  return d == 0.0 ? th[0] * th[0] : 0.0;                 // gr
+    case 2:  return exp(-d / th[0]);                                // fexp0
+    case 3:  return pow(th[0], d);                                  // ar1
+    case 4:  return th[0] * exp(-d * d / (th[1] * th[1]));          // sqexp
+    case 7:  { const double x = d / eff; return x < 1.0 ? th[0] * pow(1.0 - x, th[1]) : 0.0; }                                                   // wend0
+    case 8:  { const double x = d / eff; return x < 1.0 ? th[0] * (1.0 + th[1] * x) * pow(1.0 - x, th[1]) : 0.0; }                               // wend1
+    case 9:  { const double x = d / eff; return x < 1.0 ? th[0] * (1.0 + th[1] * x + (th[1] * th[1] - 1.0) * (1.0 / 3.0) * x * x) * pow(1.0 - x, th[1]) : 0.0; }   // wend2
+    case 13: return th[0] * exp(-d / th[1]);                        // fexp
+    case 14: return exp(-d * d / (th[0] * th[0]));                  // sqexp0
+    }
+    return nan("");
 }
 
 // Philox4x32-10; counter = (idx, iteration, chain, stream), key = seed.  Must match oracle/oracle.cpp.

@@ -37,6 +37,14 @@ extern "C" int gmb_ctx_create(int device, gmb_ctx** out) {
         unsigned long long keep = ~0ull;
         GMB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
+    {
+        int lo = 0, hi = 0;
+        GMB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        GMB_CUDA(cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, hi));
+        GMB_CUDA(cudaEventCreateWithFlags(&ctx->evp, cudaEventDisableTiming));
+        GMB_CUDA(cudaEventCreateWithFlags(&ctx->evn, cudaEventDisableTiming));
+        GMB_CUDA(cudaEventCreateWithFlags(&ctx->evj, cudaEventDisableTiming));
+    }
     GMB_CUDA(cudaEventCreate(&ctx->ev0));
     GMB_CUDA(cudaEventCreate(&ctx->ev1));
     GMB_CUDA(cudaEventCreate(&ctx->ev2));
@@ -217,6 +225,10 @@ extern "C" void gmb_ctx_destroy(gmb_ctx* ctx) {
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
+    if (ctx->evp) cudaEventDestroy(ctx->evp);
+    if (ctx->evn) cudaEventDestroy(ctx->evn);
+    if (ctx->evj) cudaEventDestroy(ctx->evj);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

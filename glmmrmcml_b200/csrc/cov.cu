@@ -19,19 +19,7 @@ __host__ __device__ inline int cov_fn_npar(int id) {
     switch (id) { case 1: case 2: case 3: case 6: case 14: return 1; case 4: case 5: case 7: case 8: case 9: case 10: case 11: case 12: case 13: return 2; }
     return 0;
 }
-__host__ __device__ inline bool cov_fn_supported(int id) { return id == 1 || id == 2 || id == 3 || id == 4 || id == 13 || id == 14; }
-
-__device__ __forceinline__ double cov_fn_eval(int id, double d, const double* th) {
-    switch (id) {
-    case 1:  return d == 0.0 ? th[0] * th[0] : 0.0;                 // gr
-    case 2:  return exp(-d / th[0]);                                // fexp0
-    case 3:  return pow(th[0], d);                                  // ar1
-    case 4:  return th[0] * exp(-d * d / (th[1] * th[1]));          // sqexp
-    case 13: return th[0] * exp(-d / th[1]);                        // fexp
-    case 14: return exp(-d * d / (th[0] * th[0]));                  // sqexp0
-    }
-    return nan("");
-}
+__host__ __device__ inline bool cov_fn_supported(int id) { return gmb_cov_fn_supported(id); }
 
 // DSubMatrix::get_val(i, j)
 __device__ __forceinline__ double block_val(const CovBlock& b, const CovFn* __restrict__ fns, const double* __restrict__ data,
@@ -45,7 +33,7 @@ __device__ __forceinline__ double block_val(const CovBlock& b, const CovFn* __re
             double di = dat[i + (size_t)(fn.col0 + k) * b.n] - dat[j + (size_t)(fn.col0 + k) * b.n];
             d2 += di * di;
         }
-        v *= cov_fn_eval(fn.id, sqrt(d2), theta + fn.par0);
+        v *= dev_cov_fn(fn.id, sqrt(d2), theta + fn.par0, fn.eff);
     }
     return v;
 }
@@ -375,13 +363,15 @@ extern "C" int gmb_cov_create(gmb_ctx* ctx, const int32_t* cov, int rows, const 
     // rows of one block are expected to be contiguous (that is how get_D_data() emits them)
     for (int r = 0; r < rows; r++) {
         int b = cov[r], nb = cov[r + rows], id = cov[r + 2 * rows], nv = cov[r + 3 * rows], p0 = cov[r + 4 * rows];
-        if (!cov_fn_supported(id)) { delete cv; return gmb_set_error(GMB_ECOV, "covariance function id %d is not supported (supported: 1 gr, 2 fexp0, 3 ar1, 4 sqexp, 13 fexp, 14 sqexp0)", id); }
+        if (!cov_fn_supported(id)) { delete cv; return gmb_set_error(GMB_ECOV, "covariance function id %d is not supported (supported: 1 gr, 2 fexp0, 3 ar1, 4 sqexp, 7-9 wend0/1/2, 13 fexp, 14 sqexp0)", id); }
         if (nb <= 0 || nv < 0 || p0 < 0) { delete cv; return gmb_set_error(GMB_EINVAL, "bad covariance row %d", r); }
         CovBlock& blk = cv->blocks[b];
         if (blk.fn0 < 0) blk.fn0 = (int)cv->fns.size();
         else if (blk.fn0 + blk.nfn != (int)cv->fns.size()) { delete cv; return gmb_set_error(GMB_EINVAL, "rows of block %d are not contiguous", b); }
         blk.n = nb;
-        cv->fns.push_back(CovFn{id, nv, p0, blk.ncol, (eff_range && r < n_eff) ? eff_range[r] : 0.0});
+        const double eff = (eff_range && r < n_eff) ? eff_range[r] : 0.0;
+        if (id >= 7 && id <= 9 && !(eff > 0.0)) { delete cv; return gmb_set_error(GMB_EINVAL, "covariance row %d: the compact-support function %d needs eff_range > 0", r, id); }
+        cv->fns.push_back(CovFn{id, nv, p0, blk.ncol, eff});
         blk.nfn++; blk.ncol += nv;
         if (id != 1) blk.all_gr = 0;
         if (p0 + cov_fn_npar(id) > cv->R) cv->R = p0 + cov_fn_npar(id);

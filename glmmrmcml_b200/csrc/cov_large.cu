@@ -8,19 +8,7 @@
 
 namespace {
 
-constexpr int NB = 64;   // panel width
-
-__device__ __forceinline__ double cov_fn_eval_l(int id, double d, const double* th) {
-    switch (id) {
-    case 1:  return d == 0.0 ? th[0] * th[0] : 0.0;
-    case 2:  return exp(-d / th[0]);
-    case 3:  return pow(th[0], d);
-    case 4:  return th[0] * exp(-d * d / (th[1] * th[1]));
-    case 13: return th[0] * exp(-d / th[1]);
-    case 14: return exp(-d * d / (th[0] * th[0]));
-    }
-    return nan("");
-}
+constexpr int NB = 128;   // panel width
 
 // fill the lower triangle of the block with D_b(i,j) (upper triangle zero)
 __global__ void build_block_kernel(CovBlock b, const CovFn* __restrict__ fns, const double* __restrict__ data,
@@ -39,51 +27,134 @@ __global__ void build_block_kernel(CovBlock b, const CovFn* __restrict__ fns, co
                 double di = dat[i + (size_t)(fn.col0 + k) * b.n] - dat[j + (size_t)(fn.col0 + k) * b.n];
                 d2 += di * di;
             }
-            v *= cov_fn_eval_l(fn.id, sqrt(d2), theta + fn.par0);
+            v *= dev_cov_fn(fn.id, sqrt(d2), theta + fn.par0, fn.eff);
         }
     }
     A[i + (size_t)j * ld] = v;
 }
 
-// unblocked Cholesky of the kb x kb diagonal block at (k0, k0), one CTA of 64 threads (thread = row), in shared memory;
-// also writes the inverse of the factor (64 x 64 col-major, zero padded) to Linv: the panel solve of the factorisation and
-// the diagonal solves of the forward substitution then run as DMMA GEMMs instead of one serial recurrence per thread.
-__global__ void __launch_bounds__(NB) potf2_kernel(double* __restrict__ A, int ld, int k0, int kb, int row_offset, int* __restrict__ status,
-                                                   double* __restrict__ Linv) {
-    __shared__ double s[NB][NB + 1];
-    const int t = threadIdx.x;
-    for (int j = 0; j < NB; j++) s[t][j] = (t < kb && j <= t && j < kb) ? A[(k0 + t) + (size_t)(k0 + j) * ld] : (t == j ? 1.0 : 0.0);
-    __syncthreads();
-    for (int j = 0; j < kb; j++) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (t >= j && t < kb) {
-            int k = 0;
-            for (; k + 3 < j; k += 4) { s0 += s[t][k] * s[j][k]; s1 += s[t][k + 1] * s[j][k + 1]; s2 += s[t][k + 2] * s[j][k + 2]; s3 += s[t][k + 3] * s[j][k + 3]; }
-            for (; k < j; k++) s0 += s[t][k] * s[j][k];
+// Cholesky factor AND its inverse of one kb x kb (kb <= 128) diagonal block at (k0, k0): one CTA of 256 threads, the block in registers.
+// Thread (tx, ty) = (tid % 16, tid / 16) owns the 8 x 8 elements (r, c) = (tx + 16 i, ty + 16 jj) — the interleaving keeps every thread busy
+// while the active trailing block shrinks.  Phase 1, right-looking elimination: at step j the owners of column j publish it through shared
+// memory, every thread scales the entries of its rows / columns by 1/sqrt(pivot) and applies the rank-1 update to its tile (one block barrier
+// per step, buffers double-buffered).  Phase 2, the inverse by the same elimination applied to the identity (row k of L^-1 is finished at step
+// k and eliminated from the rows below), with L read from shared memory.  The panel solve of the factorisation and the diagonal solves of the
+// forward substitution then run as DMMA GEMMs with the inverse instead of one serial recurrence per row.
+// Rows / columns >= kb are padded with the identity.  A: the lower triangle is read; L is written to the lower triangle, the strict upper
+// triangle of the block is zeroed.  Linv: 128 x 128 column-major, zero outside the kb x kb lower triangle.
+constexpr int DIAG_SMEM_DOUBLES = NB * (NB + 1) + 4 * NB;
+__global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int kb, int row_offset, int* __restrict__ status,
+                                                         double* __restrict__ Linv) {
+    extern __shared__ double sm[];
+    double* Ls = sm;                              // [128][129]
+    double* colbuf = sm + NB * (NB + 1);          // 2 x 128
+    double* rowbuf = colbuf + 2 * NB;             // 2 x 128
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    double a[8][8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = tx + 16 * i, c = ty + 16 * jj;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < kb && c < kb) v = (r >= c) ? A[(size_t)(k0 + r) + (size_t)(k0 + c) * ld] : A[(size_t)(k0 + c) + (size_t)(k0 + r) * ld];
+            a[i][jj] = v;
         }
-        const double sum = (s0 + s1) + (s2 + s3);
-        __shared__ double djj;
-        if (t == j) djj = s[j][j] - sum;
-        __syncthreads();
-        if (!(djj > 0.0)) { if (t == 0) atomicCAS(status, 0, row_offset + k0 + j + 1); return; }
-        double d = sqrt(djj);
-        if (t == j) s[j][j] = d;
-        else if (t > j && t < kb) s[t][j] = (s[t][j] - sum) / d;
-        __syncthreads();
+    // ---- phase 1: L ----
+#pragma unroll
+    for (int jq = 0; jq < 8; jq++) {
+        for (int js = 0; js < 16; js++) {
+            const int j = 16 * jq + js;
+            double* buf = colbuf + (j & 1) * NB;
+            if (ty == js) {                       // owners of column j
+#pragma unroll
+                for (int i = 0; i < 8; i++) buf[tx + 16 * i] = a[i][jq];
+            }
+            __syncthreads();
+            const double d = buf[j];
+            if (!(d > 0.0)) { if (tid == 0) atomicCAS(status, 0, row_offset + k0 + j + 1); return; }    // uniform: every thread reads the same pivot
+            const double inv = 1.0 / sqrt(d);
+            double lr[8], lc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { lr[i] = buf[tx + 16 * i] * inv; lc[i] = buf[ty + 16 * i] * inv; }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (i < jq) continue;
+                const bool rok = (i > jq) || (tx > js);
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) {
+                    if (jj < jq) continue;
+                    const bool cok = (jj > jq) || (ty > js);
+                    if (rok && cok) a[i][jj] = fma(-lr[i], lc[jj], a[i][jj]);
+                }
+            }
+            if (ty == js) {                       // final values of column j
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (i < jq) continue;
+                    if (i > jq || tx > js) a[i][jq] = lr[i];
+                    else if (tx == js) a[i][jq] = d * inv;
+                }
+            }
+        }
     }
-    if (t < kb) for (int j = 0; j < kb; j++) A[(k0 + t) + (size_t)(k0 + j) * ld] = (j <= t) ? s[t][j] : 0.0;
-    // inverse: thread t solves L x = e_t (rows/cols >= kb form an identity block); every thread runs the same recurrence on
-    // broadcast reads of L, entries above the diagonal come out as exact zeros
-    double x[NB];
+    // L to global (strict upper triangle of the block zeroed) and to shared memory
 #pragma unroll
-    for (int i = 0; i < NB; i++) {
-        double a0 = (i == t) ? 1.0 : 0.0, a1 = 0.0;
+    for (int jj = 0; jj < 8; jj++)
 #pragma unroll
-        for (int k = 0; k < i; k++) { if (k & 1) a1 -= s[i][k] * x[k]; else a0 -= s[i][k] * x[k]; }
-        x[i] = (a0 + a1) / s[i][i];
+        for (int i = 0; i < 8; i++) {
+            const int r = tx + 16 * i, c = ty + 16 * jj;
+            const double v = (r >= c) ? a[i][jj] : 0.0;
+            Ls[r * (NB + 1) + c] = v;
+            if (r < kb && c < kb) A[(size_t)(k0 + r) + (size_t)(k0 + c) * ld] = v;
+        }
+    // ---- phase 2: X = L^-1 ----
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i][jj] = (tx + 16 * i == ty + 16 * jj) ? 1.0 : 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int kq = 0; kq < 8; kq++) {
+        for (int ks = 0; ks < 16; ks++) {
+            const int k = 16 * kq + ks;
+            double* buf = rowbuf + (k & 1) * NB;
+            if (tx == ks) {                       // owners of row k
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) buf[ty + 16 * jj] = a[kq][jj];
+            }
+            __syncthreads();
+            const double dinv = 1.0 / Ls[k * (NB + 1) + k];
+            double xc[8], lr[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) xc[jj] = buf[ty + 16 * jj] * dinv;
+#pragma unroll
+            for (int i = 0; i < 8; i++) lr[i] = Ls[(tx + 16 * i) * (NB + 1) + k];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (i < kq) continue;
+                const bool rok = (i > kq) || (tx > ks);
+                if (rok) {
+#pragma unroll
+                    for (int jj = 0; jj < 8; jj++) {
+                        if (jj > kq) continue;    // row k of the inverse is zero right of the diagonal
+                        a[i][jj] = fma(-lr[i], xc[jj], a[i][jj]);
+                    }
+                }
+            }
+            if (tx == ks) {
+#pragma unroll
+                for (int jj = 0; jj < 8; jj++) a[kq][jj] = xc[jj];
+            }
+        }
     }
 #pragma unroll
-    for (int i = 0; i < NB; i++) Linv[i + (size_t)t * NB] = (i >= t && i < kb && t < kb) ? x[i] : 0.0;
+    for (int jj = 0; jj < 8; jj++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = tx + 16 * i, c = ty + 16 * jj;
+            Linv[r + (size_t)c * NB] = (r >= c && r < kb && c < kb) ? a[i][jj] : 0.0;
+        }
 }
 
 __global__ void logdet_diag_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ out) {
@@ -113,13 +184,20 @@ __global__ void copy_rows_kernel(const double* __restrict__ U, int ldu, int star
 
 }  // namespace
 
-// Two-level blocking.  Panels of NB = 64 columns are factorised in shared memory (potf2 + panel solve); their updates are
-// applied right away only INSIDE the current outer block of NBO = 256 columns, and the trailing matrix receives one
-// rank-256 update per outer block, split into block columns so that only the lower trapezoid is computed.  The rank-64
-// updates of the plain right-looking form ran the DMMA GEMM with a 4-iteration k loop (pipeline fill/drain dominated) and
-// computed the full square.
-constexpr int NBO = 256;   // outer block
-constexpr int NBC = 512;   // block-column width of the trailing update
+// Two-level blocking with look-ahead.  Panels of NB = 128 columns: potrf_diag_kernel factorises and inverts the diagonal block, the rows
+// below are solved as one GEMM with the inverse, and the panel's rank-128 update is applied right away only INSIDE the current outer block of
+// NBO = 512 columns.  The trailing matrix receives one rank-512 update per outer block (long k loops for the DMMA GEMM), restricted to the
+// lower trapezoid by block columns — split in two: the NARROW part (the next outer block's columns) first, then the WIDE rest.  The panel
+// chain of the next outer block — a sequence of small dependent kernels — runs on the context's high-priority side stream as soon as the
+// narrow part is done, underneath the wide update on the main stream: the latency of the chain is hidden instead of being paid per panel
+// (the round-1 version ran 79 panels x 4 serial launches at n = 5000: 10 ms at 4 TFLOP/s).
+constexpr int NBO = 512;   // outer block
+
+struct StreamSwap {       // run the library's launchers on another stream for the lifetime of this object (host code is single threaded)
+    gmb_ctx* c; cudaStream_t saved;
+    StreamSwap(gmb_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { c->stream = s; }
+    ~StreamSwap() { c->stream = saved; }
+};
 
 // storage for the inverted diagonal blocks of large block `bi` (allocated for all large blocks at first use)
 static int linv_buffer(gmb_cov* cv, int bi, double** out) {
@@ -137,36 +215,51 @@ static int linv_buffer(gmb_cov* cv, int bi, double** out) {
     return GMB_OK;
 }
 
-// in-place lower Cholesky of the n x n device matrix A (lower triangle read; the strict upper triangle of the 64 x 64 diagonal
-// blocks is zeroed, the rest of the upper triangle is left as scratch).  linv: ceil(n/64) * 64 * 64 doubles (inverted diagonal
-// blocks), status: first non-PD pivot + 1 + row_offset (0 if fine), d_logdet: sum of 2 log L_ii.
-int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet) {
-    for (int K0 = 0; K0 < n; K0 += NBO) {
-        const int KB = n - K0 < NBO ? n - K0 : NBO;
-        const int Kend = K0 + KB;
-        for (int k0 = K0; k0 < Kend; k0 += NB) {
-            const int kb = Kend - k0 < NB ? Kend - k0 : NB;
-            double* Li = linv + (size_t)(k0 / NB) * NB * NB;
-            potf2_kernel<<<1, NB, 0, ctx->stream>>>(A, ld, k0, kb, row_offset, d_status, Li);
-            ctx->launches++;
-            const int rest = n - k0 - kb;
-            if (rest > 0) {
-                // panel solve P <- P L_kk^{-T}, in place: a CTA tile spans all kb <= 64 columns, so it only reads its own rows
-                double* Pp = A + (k0 + kb) + (size_t)k0 * ld;
-                GMB_TRY(gmb_dgemm(ctx, 0, 1, rest, kb, kb, 1.0, Pp, ld, Li, NB, 0.0, Pp, ld));
-                // inside the outer block: A[k0+kb:n, k0+kb:Kend] -= P Ptop^T, P = A[k0+kb:n, k0:k0+kb]
-                const int ncols_in = Kend - (k0 + kb);
-                if (ncols_in > 0) {
-                    const double* Pm = A + (k0 + kb) + (size_t)k0 * ld;
-                    GMB_TRY(gmb_dgemm(ctx, 0, 1, rest, ncols_in, kb, -1.0, Pm, ld, Pm, ld, 1.0, A + (k0 + kb) + (size_t)(k0 + kb) * ld, ld));
-                }
-            }
+// the panel chain of the outer block [K0, Kend): diagonal factor + inverse, panel solve, update inside the outer block
+static int chol_outer_block(gmb_ctx* ctx, double* A, int ld, int n, int K0, int Kend, int row_offset, int* d_status, double* linv) {
+    static bool configured = false;
+    if (!configured) { GMB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DIAG_SMEM_DOUBLES * sizeof(double)))); configured = true; }
+    for (int k0 = K0; k0 < Kend; k0 += NB) {
+        const int kb = Kend - k0 < NB ? Kend - k0 : NB;
+        double* Li = linv + (size_t)(k0 / NB) * NB * NB;
+        potrf_diag_kernel<<<1, 256, DIAG_SMEM_DOUBLES * sizeof(double), ctx->stream>>>(A, ld, k0, kb, row_offset, d_status, Li);
+        ctx->launches++;
+        const int rest = n - k0 - kb;
+        if (rest > 0) {
+            double* Pp = A + (k0 + kb) + (size_t)k0 * ld;                       // panel solve P <- P L_kk^-T, in place
+            GMB_TRY(gmb_dgemm_rowpanel(ctx, rest, kb, kb, 1.0, Pp, ld, Li, NB, Pp, ld));
+            const int ncols_in = Kend - (k0 + kb);
+            if (ncols_in > 0)                                                   // A[k0+kb:n, k0+kb:Kend] -= P Ptop^T
+                GMB_TRY(gmb_dgemm(ctx, 0, 1, rest, ncols_in, kb, -1.0, Pp, ld, Pp, ld, 1.0, A + (k0 + kb) + (size_t)(k0 + kb) * ld, ld));
         }
-        // trailing matrix: A[J:n, J:J+w] -= Pn[J:n, :] Pn[J:J+w, :]^T for block columns J, Pn = A[Kend:n, K0:Kend]
-        for (int J = Kend; J < n; J += NBC) {
-            const int w = n - J < NBC ? n - J : NBC;
+    }
+    return GMB_OK;
+}
+
+// in-place lower Cholesky of the n x n device matrix A (lower triangle read; the strict upper triangle of the 128 x 128 diagonal blocks is
+// zeroed, the rest of the upper triangle is left as scratch).  linv: ceil(n/128) * 128 * 128 doubles (inverted diagonal blocks), status:
+// first non-PD pivot + 1 + row_offset (0 if fine), d_logdet: sum of 2 log L_ii.  Work is issued on ctx->stream and ctx->stream2 and joined
+// back on ctx->stream before returning.
+int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet) {
+    cudaStream_t M = ctx->stream, P = ctx->stream2;
+    GMB_CUDA(cudaEventRecord(ctx->evn, M));                                     // everything issued so far (the block build) precedes the first panel
+    for (int K0 = 0; K0 < n; K0 += NBO) {
+        const int Kend = K0 + NBO < n ? K0 + NBO : n, KB = Kend - K0;
+        {   // side stream: the panel chain of this outer block, once the narrow update of its columns is done
+            StreamSwap sw(ctx, P);
+            GMB_CUDA(cudaStreamWaitEvent(P, ctx->evn, 0));
+            GMB_TRY(chol_outer_block(ctx, A, ld, n, K0, Kend, row_offset, d_status, linv));
+            GMB_CUDA(cudaEventRecord(ctx->evp, P));
+        }
+        GMB_CUDA(cudaStreamWaitEvent(M, ctx->evp, 0));
+        if (Kend >= n) break;
+        // main stream: rank-KB update of the trailing matrix by Pn = A[Kend:n, K0:Kend], block column by block column (lower trapezoid)
+        bool first = true;
+        for (int J = Kend; J < n; J += NBO) {
+            const int w = n - J < NBO ? n - J : NBO;
             const double* PJ = A + J + (size_t)K0 * ld;
             GMB_TRY(gmb_dgemm(ctx, 0, 1, n - J, w, KB, -1.0, PJ, ld, PJ, ld, 1.0, A + J + (size_t)J * ld, ld));
+            if (first) { GMB_CUDA(cudaEventRecord(ctx->evn, M)); first = false; }      // narrow part done: the next panel chain may start
         }
     }
     if (d_logdet) {
@@ -211,26 +304,38 @@ int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols
     GMB_TRY(linv_buffer(cv, bi, &linv));
     int nchunks = (ncols + chunk - 1) / chunk;
     int slots = 64 / nchunks; if (slots < 1) slots = 1;
+    cudaStream_t M = ctx->stream, P = ctx->stream2;
     for (int c = 0; c < nchunks; c++) {
         int c0 = c * chunk, nc = ncols - c0 < chunk ? ncols - c0 : chunk;
         copy_rows_kernel<<<dim3(nc, (ldw + 255) / 256), 256, 0, ctx->stream>>>(dU + (size_t)c0 * ldu, ldu, b.start, n, nc, W, ldw);
         ctx->launches++;
-        // blocked forward substitution, two levels: 64-row diagonal solves and rank-64 updates inside an outer block of 256
-        // rows, one rank-256 update of all rows below per outer block
+        // blocked forward substitution with the same two levels and the same look-ahead as the factorisation: 128-row diagonal solves (GEMMs
+        // with the inverted diagonal blocks) and rank-128 updates inside an outer block of 512 rows on the side stream; per outer block one
+        // rank-512 update of the rows below on the main stream — its first 512 rows (all the next outer block needs) first
+        GMB_CUDA(cudaEventRecord(ctx->evn, M));
         for (int K0 = 0; K0 < n; K0 += NBO) {
-            const int KB = n - K0 < NBO ? n - K0 : NBO;
-            const int Kend = K0 + KB;
-            for (int k0 = K0; k0 < Kend; k0 += NB) {
-                const int kb = Kend - k0 < NB ? Kend - k0 : NB;
-                // diagonal solve W[k0:k0+kb, :] <- L_kk^{-1} W[k0:k0+kb, :], in place (a CTA tile spans all kb <= 64 rows)
-                GMB_TRY(gmb_dgemm(ctx, 0, 0, kb, nc, kb, 1.0, linv + (size_t)(k0 / NB) * NB * NB, NB, W + k0, ldw, 0.0, W + k0, ldw));
-                const int rows_in = Kend - (k0 + kb);
-                if (rows_in > 0)   // W[k0+kb:Kend, :] -= L[k0+kb:Kend, k0:k0+kb] W[k0:k0+kb, :]
-                    GMB_TRY(gmb_dgemm(ctx, 0, 0, rows_in, nc, kb, -1.0, A + (k0 + kb) + (size_t)k0 * ld, ld, W + k0, ldw, 1.0, W + k0 + kb, ldw));
+            const int Kend = K0 + NBO < n ? K0 + NBO : n, KB = Kend - K0;
+            {
+                StreamSwap sw(ctx, P);
+                GMB_CUDA(cudaStreamWaitEvent(P, ctx->evn, 0));
+                for (int k0 = K0; k0 < Kend; k0 += NB) {
+                    const int kb = Kend - k0 < NB ? Kend - k0 : NB;
+                    // diagonal solve W[k0:k0+kb, :] <- L_kk^{-1} W[k0:k0+kb, :], in place
+                    GMB_TRY(gmb_dgemm_colpanel(ctx, kb, nc, kb, 1.0, linv + (size_t)(k0 / NB) * NB * NB, NB, W + k0, ldw, W + k0, ldw));
+                    const int rows_in = Kend - (k0 + kb);
+                    if (rows_in > 0)   // W[k0+kb:Kend, :] -= L[k0+kb:Kend, k0:k0+kb] W[k0:k0+kb, :]
+                        GMB_TRY(gmb_dgemm(ctx, 0, 0, rows_in, nc, kb, -1.0, A + (k0 + kb) + (size_t)k0 * ld, ld, W + k0, ldw, 1.0, W + k0 + kb, ldw));
+                }
+                GMB_CUDA(cudaEventRecord(ctx->evp, P));
             }
-            const int rest = n - Kend;
-            if (rest > 0)          // W[Kend:, :] -= L[Kend:, K0:Kend] W[K0:Kend, :]
-                GMB_TRY(gmb_dgemm(ctx, 0, 0, rest, nc, KB, -1.0, A + Kend + (size_t)K0 * ld, ld, W + K0, ldw, 1.0, W + Kend, ldw));
+            GMB_CUDA(cudaStreamWaitEvent(M, ctx->evp, 0));
+            if (Kend >= n) break;
+            const int nar = n - Kend < NBO ? n - Kend : NBO;          // W[Kend:Kend+nar, :] -= L[Kend:Kend+nar, K0:Kend] W[K0:Kend, :]
+            GMB_TRY(gmb_dgemm(ctx, 0, 0, nar, nc, KB, -1.0, A + Kend + (size_t)K0 * ld, ld, W + K0, ldw, 1.0, W + Kend, ldw));
+            GMB_CUDA(cudaEventRecord(ctx->evn, M));
+            const int rest = n - Kend - nar;
+            if (rest > 0)
+                GMB_TRY(gmb_dgemm(ctx, 0, 0, rest, nc, KB, -1.0, A + Kend + nar + (size_t)K0 * ld, ld, W + K0, ldw, 1.0, W + Kend + nar, ldw));
         }
         if (c < 64) {
             int s0 = (c * slots) % 64;

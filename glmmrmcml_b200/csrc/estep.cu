@@ -73,9 +73,11 @@ __device__ __forceinline__ void ll_accum(const RowTerm<FL>& r, double z, double 
         const int kc = min(max(k, -64512), 64512);
         const double e = __hiloint2double(__double2hiint(m) + ((kc >> 6) << 20), __double2loint(m));
         prod *= fma(e, r.mask, 1.0);
-    } else {
+    } else if (FL == 7) {
         const double zz = (r.y - eta) * inv_sigma;                   // moremaths.h:75-78
         acc += c0 - 0.5 * zz * zz;
+    } else {                                                          // codes 2, 4, 5, 6, 8: the generic per-observation term
+        acc += dev_family_ll<FL>(r.y, eta, r.rowc, c0, 1.0 / inv_sigma);
     }
 }
 
@@ -346,8 +348,8 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
     const int i0 = 2 * (blockIdx.x * TX + threadIdx.x);
     const int j0 = blockIdx.y * cols_per_cta;
     const int j1 = min(j0 + cols_per_cta, ncols);
-    const double c0 = (FL == 7) ? (-1.0 * log(sigma) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
-    const double inv_sigma = (FL == 7) ? 1.0 / sigma : 1.0;
+    const double c0 = (FL == 7 || FL == 8) ? (-1.0 * log(sigma) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
+    const double inv_sigma = (FL == 7 || FL == 8) ? 1.0 / sigma : 1.0;
 
     double acc = 0.0;
     if (i0 < n) {
@@ -359,9 +361,11 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
             if (two) xb1 += X[i0 + 1 + (size_t)p * ldn] * b;
         }
         RowTerm<FL> r0, r1;
-        r0.init(xb0, y[i0], (FL == 1) ? rowc[i0] : 0.0);
-        r1.init(xb1, two ? y[i0 + 1] : 0.0, (FL == 1 && two) ? rowc[i0 + 1] : 0.0);
+        r0.init(xb0, y[i0], (FL == 1 || FL == 2) ? rowc[i0] : 0.0);
+        r1.init(xb1, two ? y[i0 + 1] : 0.0, ((FL == 1 || FL == 2) && two) ? rowc[i0 + 1] : 0.0);
         if (!two) r1.mask = 0.0;
+        if ((FL == 4 || FL == 5 || FL == 6) && !two) r1.y = -1.0;      // neither 0 nor 1: the generic binomial terms contribute nothing
+        if ((FL == 2 || FL == 8) && !two) { r1.y = 1.0; r1.xb = 1.0; }  // finite dummy, discarded below
         const double* col = zd + i0;
         int j = j0 + threadIdx.y;
         // 4 independent 16-byte loads per group of columns, and the next group's loads are issued before the current group's
@@ -493,8 +497,17 @@ __device__ __forceinline__ void mcnr_terms(double y, double eta, double inv_phi,
         const double rc = dev_rcp_fast(1.0 + e);
         const double p = e * rc;
         r = y - p; w = p * rc; wu = r;                   // p (1 - p) = e / (1 + e)^2
-    } else {                     // gaussian/identity : W = 1/sigma^2
+    } else if (FL == 7) {        // gaussian/identity : W = 1/sigma^2
         r = y - eta; w = inv_phi; wu = inv_phi * r;
+    } else if (FL == 2) {        // poisson/identity : dhdmu = eta, detadmu = 1
+        r = y - eta; w = 1.0 / eta; wu = w * r;
+    } else if (FL == 4) {        // binomial/log : dhdmu = (1 - p)/p with p = e^eta, detadmu = e^-eta
+        const double p = exp(eta);
+        r = y - p; w = 1.0 / ((1.0 - p) / p); wu = w * exp(-1.0 * eta) * r;
+    } else if (FL == 5) {        // binomial/identity : dhdmu = eta (1 - eta), detadmu = 1
+        r = y - eta; w = 1.0 / (eta * (1.0 - eta)); wu = w * r;
+    } else {                     // gaussian/log (8) : dhdmu = 1 (gaussian), W = 1/sigma^2, h^-1 = e^eta, detadmu = e^-eta
+        r = y - exp(eta); w = inv_phi; wu = w * exp(-1.0 * eta) * r;
     }
 }
 
@@ -775,6 +788,9 @@ int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par,
     case 1: loglik_kernel<1><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
     case 3: loglik_kernel<3><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
     case 7: loglik_kernel<7><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+#define GMB_LL_CASE(F) case F: loglik_kernel<F><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    GMB_LL_CASE(2) GMB_LL_CASE(4) GMB_LL_CASE(5) GMB_LL_CASE(6) GMB_LL_CASE(8)
+#undef GMB_LL_CASE
     default: return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
     }
     ctx->launches++;
@@ -846,7 +862,7 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
     double* wsum = colpart + (size_t)RT * 2 * ncols;
     double* ssum = wsum + ldn;
     double* sigpart = ssum + ldn;
-    double inv_phi = (mdl->flink == 7) ? 1.0 / (var_par * var_par) : 1.0;   // mcmlmodel.h:123-133
+    double inv_phi = gmb_flink_gaussian(mdl->flink) ? 1.0 / (var_par * var_par) : 1.0;   // mcmlmodel.h:123-133
     dim3 grid(RT, CC);
     size_t smem = 8 * MCNR_STAGES * 256 * sizeof(double);     // 64 KB: the column rings (the row-reduction buffer aliases them)
     {   // per device and cheap: set on every call
@@ -862,6 +878,11 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
         else mcnr_pass1_kernel<3, false><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart);
         break;
     case 7: mcnr_pass1_kernel<7, false><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
+#define GMB_NR_CASE(F) case F: GMB_CUDA(cudaFuncSetAttribute(mcnr_pass1_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        mcnr_pass1_kernel<F, false><<<grid, 256, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, d_xb, mdl->dy, inv_phi, rowpart, colpart); break;
+    GMB_NR_CASE(2) GMB_NR_CASE(4) GMB_NR_CASE(5) GMB_NR_CASE(8)
+#undef GMB_NR_CASE
+    case 6: return gmb_set_error(GMB_EFAMILY, "MCNR for binomial/probit needs glmmrBase's dhdmu, which is not part of the reference tree (use method = 'mcem')");
     default: return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
     }
     mcnr_rows_kernel<<<(n + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(n, ldn, CC, rowpart, wsum, ssum);

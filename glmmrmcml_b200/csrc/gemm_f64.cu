@@ -51,3 +51,18 @@ int gmb_dgemm_tri(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, dou
     if (transA && !transB) return gmbgemm::dispatch<true, true>(ctx, M, N, K, A, lda, B, ldb, epi);
     return gmbgemm::dispatch<true, false>(ctx, M, N, K, A, lda, B, ldb, epi);
 }
+
+// In-place products with a 128 x 128 operand (the inverted diagonal blocks of cov_large.cu): the CTA tile spans the whole 128-wide side, so a
+// CTA reads only locations it alone writes, and it writes them after its last read.
+//   gmb_dgemm_rowpanel: C (M x 128) = alpha * A (M x 128) * B^T, B stored 128 x 128 (n contiguous), C may alias A
+//   gmb_dgemm_colpanel: C (128 x N) = alpha * A (128 x 128) * B (128 x N), C may alias B
+int gmb_dgemm_rowpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc) {
+    if (N > 128 || M <= 0) return M <= 0 ? GMB_OK : gmb_set_error(GMB_EINVAL, "gmb_dgemm_rowpanel: N must be <= 128");
+    EpiAxpby epi{alpha, 0.0, C, ldc};
+    return gmbgemm::launch<64, 128, 2, 4, false, false, EpiAxpby>(ctx, M, N, K, A, lda, B, ldb, epi, 0);
+}
+int gmb_dgemm_colpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc) {
+    if (M > 128 || N <= 0) return N <= 0 ? GMB_OK : gmb_set_error(GMB_EINVAL, "gmb_dgemm_colpanel: M must be <= 128");
+    EpiAxpby epi{alpha, 0.0, C, ldc};
+    return gmbgemm::launch<128, 64, 4, 2, false, true, EpiAxpby>(ctx, M, N, K, A, lda, B, ldb, epi, 0);
+}

@@ -44,7 +44,7 @@ struct EpiResid {
     }
     __device__ __forceinline__ double colterm(int m, int n, double acc) const {
         if (!wants_ll(n)) return 0.0;
-        return dev_family_ll<FL>(y[m], xb[m] + acc, (FL == 1) ? rowc[m] : 0.0, c0, sigma);
+        return dev_family_ll<FL>(y[m], xb[m] + acc, (FL == 1 || FL == 2) ? rowc[m] : 0.0, c0, sigma);
     }
     __device__ __forceinline__ void colsum_out(int rt, int n, double v) const {
         if (wants_ll(n)) llpart[(size_t)rt * C + n] = v;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(256) zsp_resid_kernel(int n, int ngp, int wr, 
     __shared__ double red[32];
     const int i = blockIdx.x * 256 + threadIdx.x;
     const bool ok = i < n;
-    const double xbi = ok ? xb[i] : 0.0, yi = ok ? y[i] : 0.0, rci = (ok && FL == 1) ? rowc[i] : 0.0;
+    const double xbi = ok ? xb[i] : 0.0, yi = ok ? y[i] : 0.0, rci = (ok && (FL == 1 || FL == 2)) ? rowc[i] : 0.0;
     for (int cc = 0; cc < ZSP_CH; cc++) {
         const int c = blockIdx.y * ZSP_CH + cc;
         if (c >= C) break;
@@ -301,7 +301,7 @@ int launch_resid(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, con
     EpiResid<FL> epi;
     epi.xb = mdl->dxb; epi.y = mdl->dy; epi.rowc = mdl->drowc; epi.RES = b.RES; epi.ldr = mdl->ldn;
     epi.steps = steps; epi.s = s;
-    epi.c0 = (FL == 7) ? (-1.0 * log(var_par) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
+    epi.c0 = (FL == 7 || FL == 8) ? (-1.0 * log(var_par) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
     epi.sigma = var_par; epi.llpart = b.llpart; epi.C = C;
     return gmbgemm::dispatch<false, true>(mdl->ctx, mdl->n, C, mdl->Q, mdl->dZL, mdl->ldn, b.VP, mdl->ldq, epi);
 }
@@ -311,7 +311,7 @@ int launch_resid_factored(gmb_model* mdl, int C, const HmcBuffers& b, double var
     gmb_ctx* ctx = mdl->ctx;
     const gmb_ell& e = mdl->zell;
     GMB_TRY(gmb_dgemm_tri(ctx, 0, 0, mdl->Q, C, mdl->Q, 1.0, mdl->dL, mdl->ldq, b.VP, mdl->ldq, 0.0, b.W, mdl->ldq, mdl->l_lower ? 1 : 0));   // W = L V'
-    const double c0 = (FL == 7) ? (-1.0 * log(var_par) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
+    const double c0 = (FL == 7 || FL == 8) ? (-1.0 * log(var_par) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
     zsp_resid_kernel<FL><<<dim3((mdl->n + 255) / 256, (C + ZSP_CH - 1) / ZSP_CH), 256, 0, ctx->stream>>>(
         mdl->n, e.ngp, e.wr, C, mdl->ldn, mdl->ldq, e.rv, e.rc, b.W, mdl->dxb, mdl->dy, mdl->drowc, b.RES, steps, s, c0, var_par, b.llpart);
     zsp_gather_kernel<<<dim3((mdl->Q + 255) / 256, C), 256, 0, ctx->stream>>>(mdl->Q, e.qp, e.wc, mdl->ldn, mdl->ldq, e.cv, e.cr, b.RES, b.T, steps, s);
@@ -326,6 +326,11 @@ int launch_resid_fl(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, 
         case 1: return launch_resid_factored<1>(mdl, C, b, var_par, steps, s);
         case 3: return launch_resid_factored<3>(mdl, C, b, var_par, steps, s);
         case 7: return launch_resid_factored<7>(mdl, C, b, var_par, steps, s);
+        case 2: return launch_resid_factored<2>(mdl, C, b, var_par, steps, s);
+        case 4: return launch_resid_factored<4>(mdl, C, b, var_par, steps, s);
+        case 5: return launch_resid_factored<5>(mdl, C, b, var_par, steps, s);
+        case 6: return launch_resid_factored<6>(mdl, C, b, var_par, steps, s);
+        case 8: return launch_resid_factored<8>(mdl, C, b, var_par, steps, s);
         }
         return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
     }
@@ -333,6 +338,11 @@ int launch_resid_fl(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, 
     case 1: return launch_resid<1>(mdl, C, b, var_par, steps, s);
     case 3: return launch_resid<3>(mdl, C, b, var_par, steps, s);
     case 7: return launch_resid<7>(mdl, C, b, var_par, steps, s);
+    case 2: return launch_resid<2>(mdl, C, b, var_par, steps, s);
+    case 4: return launch_resid<4>(mdl, C, b, var_par, steps, s);
+    case 5: return launch_resid<5>(mdl, C, b, var_par, steps, s);
+    case 6: return launch_resid<6>(mdl, C, b, var_par, steps, s);
+    case 8: return launch_resid<8>(mdl, C, b, var_par, steps, s);
     }
     return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
 }
@@ -340,7 +350,7 @@ int launch_resid_fl(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, 
 int launch_leap(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, int s, int init) {
     EpiLeapfrog epi;
     epi.VP = b.VP; epi.R = b.R; epi.G = b.G; epi.ldq = mdl->ldq; epi.steps = b.steps; epi.eps = b.cs + (size_t)CS_EPS * C;
-    epi.s = s; epi.sc = (mdl->flink == 7) ? 1.0 / (var_par * var_par) : 1.0; epi.init = init;
+    epi.s = s; epi.sc = gmb_flink_gaussian(mdl->flink) ? 1.0 / (var_par * var_par) : 1.0; epi.init = init;
     if (b.factored)     // G = -V' + s L^T T, T = Z^T RES
         return gmbgemm::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->Q, mdl->dL, mdl->ldq, b.T, mdl->ldq, epi, mdl->l_lower ? 2 : 0);
     return gmbgemm::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->n, mdl->dZL, mdl->ldn, b.RES, mdl->ldn, epi);
@@ -520,16 +530,20 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     if (warmup < 0 || nsamp_per_chain < 0 || n_chains <= 0 || max_steps < 1 || !(lambda > 0.0))
         return gmb_set_error(GMB_EINVAL, "gmb_hmc_sample: bad sampler settings (warmup=%d nsamp=%d chains=%d max_steps=%d lambda=%g)",
                              warmup, nsamp_per_chain, n_chains, max_steps, lambda);
-    if (mdl->flink == 7 && !(var_par > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0");
+    if (gmb_flink_gaussian(mdl->flink) && !(var_par > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0");
     gmb_ctx* ctx = mdl->ctx;
     GMB_CUDA(cudaSetDevice(ctx->device));
     GmbPhase ph(ctx->stream);
-    if (g_hmc_variant != 1) GMB_TRY(gmb_agg_ensure(mdl));       // row view of the on-chip sampler (not used by the two-GEMM variant)
+    // family/link codes beyond the north-star's three run on the general two-contraction kernels only
+    const bool core = gmb_flink_core(mdl->flink);
+    if (!core && (g_hmc_variant == 2 || g_hmc_variant == 3))
+        return gmb_set_error(GMB_EFAMILY, "family/link code %d runs on the two-contraction sampler only (variant 0 or 1)", mdl->flink);
+    if (g_hmc_variant != 1 && core) GMB_TRY(gmb_agg_ensure(mdl));       // row view of the on-chip sampler (not used by the two-GEMM variant)
     ph.mark("hmc: row aggregation");
     if (L) GMB_TRY(gmb_hmc_prepare(mdl, L));
     GMB_TRY(agg_update_zl(mdl));
     ph.mark("hmc: upload L, Z L");
-    const bool try_sparse = g_hmc_variant == 0 || g_hmc_variant == 3;
+    const bool try_sparse = core && (g_hmc_variant == 0 || g_hmc_variant == 3);
     if (try_sparse) { GMB_TRY(gmb_ell_ensure(mdl)); GMB_TRY(gmb_comp_ensure(mdl)); }
     ph.mark("hmc: sparse forms");
     GMB_TRY(set_xb(mdl, beta));
@@ -547,7 +561,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     const bool sparse = try_sparse && gmb_hmc_sparse_applicable(mdl);
     if (g_hmc_variant == 3 && !sparse)
         return gmb_set_error(GMB_EINVAL, "the structure-aware sampler variant was forced but does not fit: Z L (%d x %d) is not sparse enough", mdl->agg.ng, mdl->Q);
-    const bool fits = !sparse && g_hmc_variant != 3 && gmb_hmc_fused_applicable(mdl, C);
+    const bool fits = core && !sparse && g_hmc_variant != 3 && gmb_hmc_fused_applicable(mdl, C);
     if (g_hmc_variant == 2 && !fits) return gmb_set_error(GMB_EINVAL, "the on-chip sampler variant was forced but Z L (%d x %d) does not fit in shared memory", mdl->n, mdl->Q);
     if (sparse || (fits && g_hmc_variant != 1))
         GMB_TRY(hmc_run_fused_timed(mdl, sparse, var_par, warmup, nsamp_per_chain, lambda, max_steps, target_accept, adapt, C, chain_offset, seed,
@@ -600,7 +614,7 @@ extern "C" int gmb_model_logprob_grad(gmb_model* mdl, const double* L, const dou
                                       const double* V, int C, double* lp, double* grad) {
     if (!mdl || !beta || !V || C <= 0) return gmb_set_error(GMB_EINVAL, "gmb_model_logprob_grad: bad arguments");
     if (!L && !mdl->zl_valid) return gmb_set_error(GMB_ESTATE, "gmb_model_logprob_grad: L is NULL and the model holds no factor yet");
-    if (mdl->flink == 7 && !(var_par > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0");
+    if (gmb_flink_gaussian(mdl->flink) && !(var_par > 0.0)) return gmb_set_error(GMB_EINVAL, "gaussian var_par must be > 0");
     gmb_ctx* ctx = mdl->ctx;
     GMB_CUDA(cudaSetDevice(ctx->device));
     if (L) GMB_TRY(gmb_hmc_prepare(mdl, L));

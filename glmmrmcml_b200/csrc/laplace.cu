@@ -70,6 +70,7 @@ struct LaFit {
         int B;
         GMB_TRY(gmb_cov_dims(d, &B, &Q, &R));
         if (Q > 65535) return gmb_set_error(GMB_EINVAL, "Laplace path: Q = %d exceeds 65535", Q);
+        if (!gmb_flink_core(m->flink)) return gmb_set_error(GMB_EFAMILY, "Laplace path: family/link code %d is not implemented (poisson/log, binomial/logit, gaussian/identity)", m->flink);
         // pinned staging layout of this file: beta at [0, P), v at [1024, 1024 + Q), results from pinned_doubles / 2
         if (P > 1024 || (size_t)Q + 1024 > ctx->pinned_doubles / 2)
             return gmb_set_error(GMB_EINVAL, "Laplace path: P = %d / Q = %d exceed the staging area (P <= 1024, Q <= %zu)", P, Q, ctx->pinned_doubles / 2 - 1024);

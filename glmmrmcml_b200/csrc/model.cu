@@ -23,7 +23,13 @@ int flink_from_strings(const char* family, const char* link) {
 __global__ void rowc_kernel(int n, int flink, const double* __restrict__ y, double* __restrict__ rowc) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    rowc[i] = (flink == 1) ? dev_log_factorial_approx(y[i]) : 0.0;   // moremaths.h:34-39
+    rowc[i] = (flink == 1 || flink == 2) ? dev_log_factorial_approx(y[i]) : 0.0;   // moremaths.h:34-39, :43
+}
+
+// gaussian/log: the constructor replaces y by log y (mcmlmodel.h:90-92)
+__global__ void logy_kernel(int n, double* __restrict__ y) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = log(y[i]);
 }
 
 int upload_matrix(gmb_ctx* ctx, double* dst, int ld, const double* src, int rows, int cols) {
@@ -58,9 +64,9 @@ extern "C" int gmb_model_create(gmb_ctx* ctx, int n, int P, int Q, const double*
     if (fl == 0)
         return gmb_set_error(GMB_EFAMILY, "unknown family/link '%s'/'%s' (mcmlmodel.h:74-87 lists the valid pairs)",
                              family ? family : "", link ? link : "");
-    if (fl != 1 && fl != 3 && fl != 7)
-        return gmb_set_error(GMB_EFAMILY, "family/link '%s'/'%s' (code %d) has no device kernel; in scope: poisson/log, "
-                             "binomial/logit, gaussian/identity", family, link, fl);
+    if (!gmb_flink_supported(fl))
+        return gmb_set_error(GMB_EFAMILY, "family/link '%s'/'%s' (code %d) has no device kernel (supported: codes 1-8; the Gamma codes are "
+                             "unreachable in the reference, whose family string is 'Gamma', and beta/logit is not implemented)", family, link, fl);
     GMB_CUDA(cudaSetDevice(ctx->device));
     gmb_model* mdl = new gmb_model();
     mdl->ctx = ctx; mdl->n = n; mdl->P = P; mdl->Q = Q; mdl->flink = fl;
@@ -80,6 +86,7 @@ extern "C" int gmb_model_create(gmb_ctx* ctx, int n, int P, int Q, const double*
     if (rc) { gmb_model_destroy(mdl); return rc; }
     rowc_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, fl, mdl->dy, mdl->drowc);
     ctx->launches++;
+    if (fl == 8) { logy_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, mdl->dy); ctx->launches++; }
     e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { gmb_model_destroy(mdl); return gmb_set_error(GMB_ECUDA, "gmb_model_create: %s", cudaGetErrorString(e)); }
     *out = mdl;

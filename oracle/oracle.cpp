@@ -418,12 +418,16 @@ static int parse_cov(const int32_t* cov, int rows, const double* data, int n_dat
 }
 
 // kernel functions
-static inline double cov_fn(int id, double d, const double* th) {
+static inline double cov_fn(int id, double d, const double* th, double eff) {
     switch (id) {
     case 1:  return d == 0 ? th[0] * th[0] : 0.0;            // gr
     case 2:  return std::exp(-d / th[0]);                     // fexp0
     case 3:  return std::pow(th[0], d);                       // ar1
     case 4:  return th[0] * std::exp(-d * d / (th[1] * th[1]));   // sqexp
+    // Wendland compact-support functions (x = d / eff_range, zero beyond it); reconstructed like the rest of this table
+    case 7:  { double x = d / eff; return x < 1 ? th[0] * std::pow(1 - x, th[1]) : 0.0; }                                   // wend0
+    case 8:  { double x = d / eff; return x < 1 ? th[0] * (1 + th[1] * x) * std::pow(1 - x, th[1]) : 0.0; }                 // wend1
+    case 9:  { double x = d / eff; return x < 1 ? th[0] * (1 + th[1] * x + (th[1] * th[1] - 1) * (1.0 / 3.0) * x * x) * std::pow(1 - x, th[1]) : 0.0; }   // wend2
     case 13: return th[0] * std::exp(-d / th[1]);             // fexp
     case 14: return std::exp(-d * d / (th[0] * th[0]));       // sqexp0
     }
@@ -440,7 +444,7 @@ static inline double block_val(const CovSpec& cs, const CovSpec::Block& b, const
             double di = dat[i + (size_t)(f.col0 + k) * b.n] - dat[j + (size_t)(f.col0 + k) * b.n];
             d2 += di * di;
         }
-        v *= cov_fn(f.id, std::sqrt(d2), theta + f.par0);
+        v *= cov_fn(f.id, std::sqrt(d2), theta + f.par0, f.eff);
     }
     return v;
 }
@@ -590,6 +594,10 @@ static void log_grad(int n, int Q, const double* ZL, const double* xb, const dou
     case 3: for (int i = 0; i < n; i++) mu[i] = 1 / (std::exp(mu[i]) + 1) + y[i] - 1; break;   // :184-193
     case 4: for (int i = 0; i < n; i++) { if (y[i] == 1) mu[i] = 1; else if (y[i] == 0) mu[i] = std::exp(mu[i]) / (1 - std::exp(mu[i])); } break;   // :194-206
     case 5: for (int i = 0; i < n; i++) { if (y[i] == 1) mu[i] = 1 / mu[i]; else if (y[i] == 0) mu[i] = -1 / (1 - mu[i]); } break;                    // :207-219
+    case 6: for (int i = 0; i < n; i++) {                                                // :220-232 (R::dnorm / R::pnorm)
+                const double pdf = std::exp(-0.5 * mu[i] * mu[i]) / std::sqrt(2 * M_PI);
+                if (y[i] == 1) mu[i] = pdf / pnorm_std(mu[i]); else if (y[i] == 0) mu[i] = -1.0 * pdf / (1 - pnorm_std(mu[i]));
+            } break;
     case 7: case 8: for (int i = 0; i < n; i++) mu[i] = (y[i] - mu[i]); break;           // :233-244 (scaled below)
     default: for (int i = 0; i < n; i++) mu[i] = NAN;
     }

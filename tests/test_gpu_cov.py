@@ -143,3 +143,28 @@ def test_gram_path_equals_stream_and_oracle(name, gctx, oracle):
         with pytest.raises(g.GmbError):
             cv.loglik_model(np.array([0.3, 1.2]), mdl)          # ar1 parameter > 1: not positive definite
     mdl.close(); cv.close()
+
+
+@pytest.mark.parametrize("fid", [7, 8, 9])
+def test_wendland_compact_support_blocks(gctx, oracle, fid):
+    """Covariance function ids 7-9 (wend0 / wend1 / wend2, compact support through eff_range; SURVEY App. C.2 reconstruction, N4): D(theta), its
+    Cholesky factor and mvn_ll against the oracle, small (warp) and large (blocked) blocks."""
+    import glmmrmcml_b200 as g
+    rng = np.random.default_rng(40 + fid)
+    for nloc, m in ((12, 64), (150, 40)):
+        xy = rng.random((nloc, 2))
+        cov = np.array([[0, nloc, fid, 2, 0]], dtype=np.int32)
+        data = np.concatenate([xy[:, 0], xy[:, 1]])
+        eff = np.array([0.45])
+        theta = np.array([0.8, 3.0 + fid])                      # smoothness large enough for positive definiteness in 2-D
+        cv = g.Covariance(gctx, cov, data, eff)
+        D = cv.genD(theta, chol=False); L = cv.genD(theta, chol=True)
+        Do = oracle.genD(cov, data, eff, theta, chol=False); Lo = oracle.genD(cov, data, eff, theta, chol=True)
+        assert np.count_nonzero(Do == 0.0) > 0                  # compact support: exact zeros beyond eff_range
+        assert np.max(np.abs(D - Do)) <= 1e-14 and np.max(np.abs(L - Lo)) <= 1e-11
+        U = np.asfortranarray(Lo @ rng.standard_normal((nloc, m)))
+        r = oracle.mvn_loglik(cov, data, eff, theta, U)
+        assert abs(cv.loglik(theta, U) - r) <= 1e-10 * abs(r)
+        cv.close()
+    with pytest.raises(g.GmbError):                             # compact support needs its range
+        g.Covariance(gctx, cov, data, np.array([0.0]))
