@@ -200,6 +200,7 @@ int gmb_dgemm(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double 
               const double* B, int ldb, double beta, double* C, int ldc);
 int gmb_dgemm_tri(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
                   const double* B, int ldb, double beta, double* C, int ldc, int lower_a);
+int gmb_dsyrk_lower_sub(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc, int c0, int c1);   // C[:, c0:c1) -= P P^T, lower tiles
 int gmb_dgemm_rowpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias A
 int gmb_dgemm_colpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias B
 

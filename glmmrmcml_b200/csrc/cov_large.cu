@@ -33,118 +33,75 @@ __global__ void build_block_kernel(CovBlock b, const CovFn* __restrict__ fns, co
     A[i + (size_t)j * ld] = v;
 }
 
-// Cholesky factor AND its inverse of one kb x kb (kb <= 128) diagonal block at (k0, k0): one CTA of 256 threads, the block in registers.
-// Thread (tx, ty) = (tid % 16, tid / 16) owns the 8 x 8 elements (r, c) = (tx + 16 i, ty + 16 jj) — the interleaving keeps every thread busy
-// while the active trailing block shrinks.  Phase 1, right-looking elimination: at step j the owners of column j publish it through shared
-// memory, every thread scales the entries of its rows / columns by 1/sqrt(pivot) and applies the rank-1 update to its tile (one block barrier
-// per step, buffers double-buffered).  Phase 2, the inverse by the same elimination applied to the identity (row k of L^-1 is finished at step
-// k and eliminated from the rows below), with L read from shared memory.  The panel solve of the factorisation and the diagonal solves of the
-// forward substitution then run as DMMA GEMMs with the inverse instead of one serial recurrence per row.
-// Rows / columns >= kb are padded with the identity.  A: the lower triangle is read; L is written to the lower triangle, the strict upper
-// triangle of the block is zeroed.  Linv: 128 x 128 column-major, zero outside the kb x kb lower triangle.
-constexpr int DIAG_SMEM_DOUBLES = NB * (NB + 1) + 4 * NB;
+// Cholesky factor AND its inverse of one kb x kb (kb <= 128) diagonal block at (k0, k0): one CTA of 256 threads, both matrices in registers.
+// Thread (tx, ty) = (tid % 16, tid / 16) owns the elements (r, c) = (tx + 16 i, ty + 16 jj) of the LOWER triangles (i >= jj: 36 of the 64
+// index pairs) of A and of B = L^-1 (B starts as the identity) — the interleaving keeps every thread busy while the active part of A shrinks
+// and the active part of B grows.  One right-looking elimination produces both: at step j the owners of column j of A and of row j of B publish
+// them through (double-buffered) shared memory — one block barrier per step —, every thread scales by rsqrt(pivot), column j of L is final,
+// row j of L^-1 is final, and the rank-1 updates A[r, c] -= l_r l_c (r, c > j) and B[r, c] -= l_r x_c (r > j, c <= j) are applied to its tiles.
+// The panel solve of the factorisation and the diagonal solves of the forward substitution then run as DMMA GEMMs with the inverse instead of
+// one serial recurrence per row.  Rows / columns >= kb are padded with the identity.  A: the lower triangle is read; L is written to the lower
+// triangle, the strict upper triangle of the block is zeroed.  Linv: 128 x 128 column-major, zero outside the kb x kb lower triangle.
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int kb, int row_offset, int* __restrict__ status,
                                                          double* __restrict__ Linv) {
-    extern __shared__ double sm[];
-    double* Ls = sm;                              // [128][129]
-    double* colbuf = sm + NB * (NB + 1);          // 2 x 128
-    double* rowbuf = colbuf + 2 * NB;             // 2 x 128
+    __shared__ double colbuf[2][NB], rowbuf[2][NB];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    double a[8][8];
+    double a[8][8], bm[8][8];                     // only the entries with i >= jj are ever touched (the others are never materialised)
 #pragma unroll
     for (int jj = 0; jj < 8; jj++)
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = jj; i < 8; i++) {
             const int r = tx + 16 * i, c = ty + 16 * jj;
             double v = (r == c) ? 1.0 : 0.0;
-            if (r < kb && c < kb) v = (r >= c) ? A[(size_t)(k0 + r) + (size_t)(k0 + c) * ld] : A[(size_t)(k0 + c) + (size_t)(k0 + r) * ld];
+            if (r < kb && c < kb && r >= c) v = A[(size_t)(k0 + r) + (size_t)(k0 + c) * ld];
             a[i][jj] = v;
+            bm[i][jj] = (r == c) ? 1.0 : 0.0;
         }
-    // ---- phase 1: L ----
 #pragma unroll
     for (int jq = 0; jq < 8; jq++) {
         for (int js = 0; js < 16; js++) {
             const int j = 16 * jq + js;
-            double* buf = colbuf + (j & 1) * NB;
-            if (ty == js) {                       // owners of column j
+            double* cb = colbuf[j & 1];
+            double* rb = rowbuf[j & 1];
+            if (ty == js) {                       // owners of column j of A: rows r >= j live in slots i >= jq
 #pragma unroll
-                for (int i = 0; i < 8; i++) buf[tx + 16 * i] = a[i][jq];
+                for (int i = jq; i < 8; i++) cb[tx + 16 * i] = a[i][jq];
+            }
+            if (tx == js) {                       // owners of row j of B: columns c <= j live in slots jj <= jq
+#pragma unroll
+                for (int jj = 0; jj <= jq; jj++) rb[ty + 16 * jj] = bm[jq][jj];
             }
             __syncthreads();
-            const double d = buf[j];
+            const double d = cb[j];
             if (!(d > 0.0)) { if (tid == 0) atomicCAS(status, 0, row_offset + k0 + j + 1); return; }    // uniform: every thread reads the same pivot
-            const double inv = 1.0 / sqrt(d);
-            double lr[8], lc[8];
+            const double inv = rsqrt(d);
+            double lr[8], lc[8], xc[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) { lr[i] = buf[tx + 16 * i] * inv; lc[i] = buf[ty + 16 * i] * inv; }
+            for (int i = jq; i < 8; i++) { lr[i] = cb[tx + 16 * i] * inv; lc[i] = cb[ty + 16 * i] * inv; }
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (i < jq) continue;
-                const bool rok = (i > jq) || (tx > js);
+            for (int jj = 0; jj <= jq; jj++) xc[jj] = rb[ty + 16 * jj] * inv;
 #pragma unroll
-                for (int jj = 0; jj < 8; jj++) {
-                    if (jj < jq) continue;
-                    const bool cok = (jj > jq) || (ty > js);
-                    if (rok && cok) a[i][jj] = fma(-lr[i], lc[jj], a[i][jj]);
+            for (int i = jq; i < 8; i++) {
+                const bool rok = (i > jq) || (tx > js);           // r > j
+                if (rok) {
+#pragma unroll
+                    for (int jj = jq; jj <= i; jj++)               // A: columns c > j of the lower triangle
+                        if ((jj > jq) || (ty > js)) a[i][jj] = fma(-lr[i], lc[jj], a[i][jj]);
+#pragma unroll
+                    for (int jj = 0; jj <= jq; jj++)               // B: columns c <= j (entries right of the diagonal of row j are zero)
+                        bm[i][jj] = fma(-lr[i], xc[jj], bm[i][jj]);
                 }
             }
-            if (ty == js) {                       // final values of column j
+            if (ty == js) {                       // column j of L
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (i < jq) continue;
+                for (int i = jq; i < 8; i++) {
                     if (i > jq || tx > js) a[i][jq] = lr[i];
                     else if (tx == js) a[i][jq] = d * inv;
                 }
             }
-        }
-    }
-    // L to global (strict upper triangle of the block zeroed) and to shared memory
+            if (tx == js) {                       // row j of L^-1
 #pragma unroll
-    for (int jj = 0; jj < 8; jj++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int r = tx + 16 * i, c = ty + 16 * jj;
-            const double v = (r >= c) ? a[i][jj] : 0.0;
-            Ls[r * (NB + 1) + c] = v;
-            if (r < kb && c < kb) A[(size_t)(k0 + r) + (size_t)(k0 + c) * ld] = v;
-        }
-    // ---- phase 2: X = L^-1 ----
-#pragma unroll
-    for (int jj = 0; jj < 8; jj++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) a[i][jj] = (tx + 16 * i == ty + 16 * jj) ? 1.0 : 0.0;
-    __syncthreads();
-#pragma unroll
-    for (int kq = 0; kq < 8; kq++) {
-        for (int ks = 0; ks < 16; ks++) {
-            const int k = 16 * kq + ks;
-            double* buf = rowbuf + (k & 1) * NB;
-            if (tx == ks) {                       // owners of row k
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++) buf[ty + 16 * jj] = a[kq][jj];
-            }
-            __syncthreads();
-            const double dinv = 1.0 / Ls[k * (NB + 1) + k];
-            double xc[8], lr[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; jj++) xc[jj] = buf[ty + 16 * jj] * dinv;
-#pragma unroll
-            for (int i = 0; i < 8; i++) lr[i] = Ls[(tx + 16 * i) * (NB + 1) + k];
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (i < kq) continue;
-                const bool rok = (i > kq) || (tx > ks);
-                if (rok) {
-#pragma unroll
-                    for (int jj = 0; jj < 8; jj++) {
-                        if (jj > kq) continue;    // row k of the inverse is zero right of the diagonal
-                        a[i][jj] = fma(-lr[i], xc[jj], a[i][jj]);
-                    }
-                }
-            }
-            if (tx == ks) {
-#pragma unroll
-                for (int jj = 0; jj < 8; jj++) a[kq][jj] = xc[jj];
+                for (int jj = 0; jj <= jq; jj++) bm[jq][jj] = xc[jj];
             }
         }
     }
@@ -153,7 +110,9 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int r = tx + 16 * i, c = ty + 16 * jj;
-            Linv[r + (size_t)c * NB] = (r >= c && r < kb && c < kb) ? a[i][jj] : 0.0;
+            const bool low = (i > jj) || (i == jj && r >= c);
+            if (r < kb && c < kb) A[(size_t)(k0 + r) + (size_t)(k0 + c) * ld] = (i >= jj && low) ? a[i >= jj ? i : jj][jj] : 0.0;
+            Linv[r + (size_t)c * NB] = (i >= jj && low && r < kb && c < kb) ? bm[i >= jj ? i : jj][jj] : 0.0;
         }
 }
 
@@ -217,12 +176,10 @@ static int linv_buffer(gmb_cov* cv, int bi, double** out) {
 
 // the panel chain of the outer block [K0, Kend): diagonal factor + inverse, panel solve, update inside the outer block
 static int chol_outer_block(gmb_ctx* ctx, double* A, int ld, int n, int K0, int Kend, int row_offset, int* d_status, double* linv) {
-    static bool configured = false;
-    if (!configured) { GMB_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DIAG_SMEM_DOUBLES * sizeof(double)))); configured = true; }
     for (int k0 = K0; k0 < Kend; k0 += NB) {
         const int kb = Kend - k0 < NB ? Kend - k0 : NB;
         double* Li = linv + (size_t)(k0 / NB) * NB * NB;
-        potrf_diag_kernel<<<1, 256, DIAG_SMEM_DOUBLES * sizeof(double), ctx->stream>>>(A, ld, k0, kb, row_offset, d_status, Li);
+        potrf_diag_kernel<<<1, 256, 0, ctx->stream>>>(A, ld, k0, kb, row_offset, d_status, Li);
         ctx->launches++;
         const int rest = n - k0 - kb;
         if (rest > 0) {
@@ -254,12 +211,14 @@ int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int
         GMB_CUDA(cudaStreamWaitEvent(M, ctx->evp, 0));
         if (Kend >= n) break;
         // main stream: rank-KB update of the trailing matrix by Pn = A[Kend:n, K0:Kend], block column by block column (lower trapezoid)
-        bool first = true;
-        for (int J = Kend; J < n; J += NBO) {
-            const int w = n - J < NBO ? n - J : NBO;
-            const double* PJ = A + J + (size_t)K0 * ld;
-            GMB_TRY(gmb_dgemm(ctx, 0, 1, n - J, w, KB, -1.0, PJ, ld, PJ, ld, 1.0, A + J + (size_t)J * ld, ld));
-            if (first) { GMB_CUDA(cudaEventRecord(ctx->evn, M)); first = false; }      // narrow part done: the next panel chain may start
+        // (lower tile pairs only, one launch for all of them: equal work per CTA, no tile of the upper triangle)
+        {
+            const int Mt = n - Kend;
+            const double* Pn = A + Kend + (size_t)K0 * ld;
+            double* Ct = A + Kend + (size_t)Kend * ld;
+            GMB_TRY(gmb_dsyrk_lower_sub(ctx, Mt, KB, Pn, ld, Ct, ld, 0, NBO < Mt ? NBO : Mt));       // narrow part: the next outer block's columns
+            GMB_CUDA(cudaEventRecord(ctx->evn, M));                                                    // ... done: the next panel chain may start
+            if (Mt > NBO) GMB_TRY(gmb_dsyrk_lower_sub(ctx, Mt, KB, Pn, ld, Ct, ld, NBO, Mt));          // wide rest
         }
     }
     if (d_logdet) {

@@ -8,6 +8,7 @@
 // 16-byte loads that are contiguous across the warp, xb/y held in registers, column loop unrolled for
 // memory-level parallelism, deterministic two-level reduction (no floating-point atomics).
 #include "common.cuh"
+#include "gemm_tma.cuh"    // mbarrier / TMA helpers and the tensor-map encoder
 
 namespace {
 
@@ -628,6 +629,243 @@ __global__ void __launch_bounds__(256) mcnr_pass1_kernel(int n, int ldn, int nco
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K3 pass 1, TMA version (poisson/log, binomial/logit on the factor matrix, gaussian/identity).
+// The cp.async version above issues ~37 instructions per element (per-lane copies with their predicates and addresses, selects, a 10-shuffle
+// warp reduction per column): it is ISSUE bound at 55-64 % of the HBM rate.  Here
+//   * the sample columns arrive as TMA boxes of 256 rows x 8 columns (16 KB, one column per warp) in a ring of MCNR_TMA_STAGES stages: one
+//     elected thread arms the stage's mbarrier and issues one cp.async.bulk.tensor per stage; rows beyond n and columns beyond the matrix are
+//     zero-filled by the TMA unit, and the per-row constants are chosen so that zero-filled entries contribute exactly nothing (no masks);
+//   * the arithmetic works on sums that need no per-element select: binomial t = 1/(1 + A F) (p or 1 - p by the sign folded into F and A),
+//     u = 1 - t, w = t u, residual r = c + s u with per-row constants (c, s) — the row sums kept are sum(t u) and sum(u); poisson mu = A e^z
+//     with A = e^xb hoisted, row sum kept is sum(mu); gaussian r = d - z, row sum kept is sum(z);
+//   * the per-column sums of r and r^2 of FOUR columns are reduced together: an 8-value fold (16, 8, 4 lanes) followed by two butterfly steps —
+//     9 shuffles for 4 columns instead of 40.
+// Outputs as mcnr_pass1_kernel: rowpart [gridDim.y][2][ldn] (sum_j w, sum_j wu) and colpart [gridDim.x][2][ncols] (sum_i r, sum_i r^2).
+// ---------------------------------------------------------------------------------------------------
+constexpr int MCNR_TMA_STAGES = 6;
+constexpr int MCNR_TMA_COLS = 8;                 // columns per stage = warps per CTA
+constexpr size_t MCNR_TMA_SMEM = (size_t)MCNR_TMA_STAGES * 256 * MCNR_TMA_COLS * sizeof(double) + 1024 + 128;
+
+// cubic-convergence reciprocal for d >= 1: hardware seed (about 20 bits) and one third-order step, error ~ e^3 (<= 1 ulp)
+__device__ __forceinline__ double dev_rcp_cubic(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    const double e = fma(-d, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
+}
+
+template <int FL>
+__global__ void __launch_bounds__(256, 2) mcnr_tma_kernel(const __grid_constant__ CUtensorMap tm, int n, int ldn, int ncols, int cols_per_cta,
+                                                          const double* __restrict__ xb, const double* __restrict__ y, double inv_phi,
+                                                          double* __restrict__ rowpart, double* __restrict__ colpart) {
+    extern __shared__ unsigned char smraw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
+    double* ring = reinterpret_cast<double*>(base);                                  // [stage][col][256]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + MCNR_TMA_STAGES * 256 * MCNR_TMA_COLS);
+    uint64_t* empty = full + MCNR_TMA_STAGES;
+    __shared__ double stab[64];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) stab[tid] = GMB_EXP2_TAB[tid];
+    if (tid == 0) {
+        for (int s = 0; s < MCNR_TMA_STAGES; s++) { gmbtma::mbar_init(&full[s], 1); gmbtma::mbar_init(&empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int rbase = blockIdx.x * 256;
+    const int j0 = blockIdx.y * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
+    const int ntile = (j1 - j0 + MCNR_TMA_COLS - 1) / MCNR_TMA_COLS;
+
+    // per-row constants of the lane's 8 rows (rbase + lane + 32 k); rows beyond n get constants that make a zero-filled entry contribute nothing
+    double ca[8], cb[8], cs[8];      // FL 3: A, c, s ; FL 1: A = e^xb, y ; FL 7: d = y - xb
+    double acc0[8], acc1[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int i = rbase + lane + 32 * k;
+        const bool ok = i < n;
+        const double xbi = ok ? xb[i] : 0.0, yi = ok ? y[i] : 0.0;
+        if (FL == 3) {
+            ca[k] = ok ? ((yi == 1.0) ? exp(-1.0 * xbi) : exp(xbi)) : 0.0;          // F is zero-filled there: t = 1, u = 0
+            cs[k] = (yi == 1.0) ? 1.0 : -1.0;
+            cb[k] = (yi == 1.0) ? 0.0 : yi;                                           // r = y - p: y = 1: u ; otherwise y - u
+        } else if (FL == 1) {
+            ca[k] = ok ? exp(xbi) : 0.0; cb[k] = yi; cs[k] = 0.0;
+        } else {
+            ca[k] = yi - xbi; cb[k] = 0.0; cs[k] = 0.0;
+        }
+        acc0[k] = 0.0; acc1[k] = 0.0;
+    }
+    auto produce = [&](int t) {
+        const int s = t % MCNR_TMA_STAGES;
+        if (t >= MCNR_TMA_STAGES) gmbtma::mbar_wait(&empty[s], ((t / MCNR_TMA_STAGES) - 1) & 1);
+        gmbtma::mbar_expect_tx(&full[s], 256 * MCNR_TMA_COLS * sizeof(double));
+        gmbtma::tma_load_2d(ring + (size_t)s * 256 * MCNR_TMA_COLS, &tm, &full[s], rbase, j0 + t * MCNR_TMA_COLS);
+    };
+    if (tid == 0) for (int t = 0; t < MCNR_TMA_STAGES - 1 && t < ntile; t++) produce(t);
+
+    // (sum r, sum r^2) of 4 columns of this warp (4 successive stages) are reduced together: value index q = 2 * slot + (0: sum r, 1: sum r^2)
+    for (int t4 = 0; t4 < ntile; t4 += 4) {
+        double cv[8];
+        int cols[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            cv[2 * q] = 0.0; cv[2 * q + 1] = 0.0; cols[q] = -1;
+            const int t = t4 + q;
+            if (t >= ntile) continue;                                                // block-uniform
+            const int s = t % MCNR_TMA_STAGES;
+            if (tid == 0 && t + MCNR_TMA_STAGES - 1 < ntile) produce(t + MCNR_TMA_STAGES - 1);
+            __syncwarp();
+            gmbtma::mbar_wait(&full[s], (t / MCNR_TMA_STAGES) & 1);
+            const int j = j0 + t * MCNR_TMA_COLS + warp;
+            if (j < j1) {                                                            // warp-uniform
+                const double* col = ring + ((size_t)s * MCNR_TMA_COLS + warp) * 256 + lane;
+                double z[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) z[k] = col[32 * k];
+                double sr = 0.0, sr2 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    double r;
+                    if (FL == 3) {
+                        const double tt = dev_rcp_cubic(fma(ca[k], z[k], 1.0));       // p (y = 1) or 1 - p
+                        const double u = 1.0 - tt;
+                        acc0[k] = fma(tt, u, acc0[k]);                                // sum_j p (1 - p)
+                        acc1[k] += u;
+                        r = fma(cs[k], u, cb[k]);
+                    } else if (FL == 1) {
+                        const double mu = ca[k] * dev_exp_tab(z[k], stab);
+                        acc0[k] += mu;
+                        r = cb[k] - mu;
+                    } else {
+                        acc0[k] += z[k];
+                        r = ca[k] - z[k];
+                    }
+                    sr += r; sr2 = fma(r, r, sr2);
+                }
+                cv[2 * q] = sr; cv[2 * q + 1] = sr2; cols[q] = j;
+            }
+            __syncwarp();
+            if (lane == 0) gmbtma::mbar_arrive(&empty[s]);
+        }
+        // fold the 8 values over the warp: 16-, 8- and 4-lane halves keep one half of the values each, then two butterfly steps
+        double v4[4], v2[2], v1;
+        const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const double send = hi16 ? cv[q] : cv[q + 4], keep = hi16 ? cv[q + 4] : cv[q];
+            v4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const double send = hi8 ? v4[q] : v4[q + 2], keep = hi8 ? v4[q + 2] : v4[q];
+            v2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const double send = hi4 ? v2[0] : v2[1], keep = hi4 ? v2[1] : v2[0];
+            v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        // lane l holds the total of value index 4 * bit4(l) + 2 * bit3(l) + bit2(l)
+        const int qi = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+        int cj = cols[0];
+        if ((qi >> 1) == 1) cj = cols[1]; else if ((qi >> 1) == 2) cj = cols[2]; else if ((qi >> 1) == 3) cj = cols[3];
+        if ((lane & 3) == 0 && cj >= 0) colpart[((size_t)blockIdx.x * 2 + (qi & 1)) * ncols + cj] = v1;
+    }
+    __syncthreads();                                   // every warp is done with the ring: reuse it for the cross-warp row reduction
+    double* red = ring;                                // [8 warps][2][256]
+    const double nc = (double)(j1 - j0);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int r = lane + 32 * k;
+        red[(warp * 2 + 0) * 256 + r] = acc0[k];
+        red[(warp * 2 + 1) * 256 + r] = acc1[k];
+    }
+    __syncthreads();
+    {
+        const int r = tid, i = rbase + r;              // 256 threads <-> 256 rows
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; w++) { a += red[(w * 2 + 0) * 256 + r]; b += red[(w * 2 + 1) * 256 + r]; }
+        if (i < n) {
+            const double xbi = xb[i], yi = y[i];
+            double wsum, ssum;
+            if (FL == 3) { wsum = a; ssum = (yi == 1.0) ? b : fma(nc, yi, -b); }     // sum_j (y - p)
+            else if (FL == 1) { wsum = a; ssum = fma(nc, yi, -a); }                  // W = mu, Wu = y - mu
+            else { wsum = nc * inv_phi; ssum = inv_phi * fma(nc, yi - xbi, -a); }    // W = 1/sigma^2, Wu = (y - eta)/sigma^2
+            rowpart[((size_t)blockIdx.y * 2 + 0) * ldn + i] = wsum;
+            rowpart[((size_t)blockIdx.y * 2 + 1) * ldn + i] = ssum;
+        }
+    }
+}
+
+// K3 tail in ONE launch: CTAs [0, RT) reduce the row partials of their 256-row tile over the column chunks and assemble the tile's share of
+// X' diag(w) X and X' s (one warp per output entry, fixed order); CTAs [RT, RT + NSIG) turn the column partials into sum_j sd(resid_j)
+// (mcmloptim.h:216); the last CTA to finish adds the per-CTA partials in index order -> out [P*P + P + 1].  Deterministic.
+__global__ void __launch_bounds__(256) mcnr_tail_kernel(int n, int P, int ldn, int ncols, int RT, int CC, int NSIG, const double* __restrict__ X,
+                                                        const double* __restrict__ rowpart, const double* __restrict__ colpart,
+                                                        double* __restrict__ part /* [RT][P*P+P] then [NSIG] */, unsigned int* __restrict__ counter,
+                                                        double* __restrict__ out) {
+    __shared__ double sw[256], ss[256];
+    __shared__ double red[32];
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nout = P * P + P;
+    if ((int)blockIdx.x < RT) {
+        const int i = blockIdx.x * 256 + tid;
+        double a = 0.0, b = 0.0;
+        if (i < n) for (int c = 0; c < CC; c++) { a += rowpart[((size_t)c * 2 + 0) * ldn + i]; b += rowpart[((size_t)c * 2 + 1) * ldn + i]; }
+        sw[tid] = a; ss[tid] = b;
+        __syncthreads();
+        double* dst = part + (size_t)blockIdx.x * nout;
+        for (int e = warp; e < nout; e += 8) {
+            double acc = 0.0;
+            if (e < P * P) {
+                const int pa = e % P, pb = e / P;
+                for (int r = lane; r < 256; r += 32) { const int ii = blockIdx.x * 256 + r; if (ii < n) acc += X[ii + (size_t)pa * ldn] * sw[r] * X[ii + (size_t)pb * ldn]; }
+            } else {
+                const int pa = e - P * P;
+                for (int r = lane; r < 256; r += 32) { const int ii = blockIdx.x * 256 + r; if (ii < n) acc += X[ii + (size_t)pa * ldn] * ss[r]; }
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) dst[e] = acc;
+        }
+    } else {
+        const int b = blockIdx.x - RT;
+        double acc = 0.0;
+        for (int j = b * 256 + tid; j < ncols; j += NSIG * 256) {
+            double sr = 0.0, sr2 = 0.0;
+            for (int t = 0; t < RT; t++) { sr += colpart[((size_t)t * 2 + 0) * ncols + j]; sr2 += colpart[((size_t)t * 2 + 1) * ncols + j]; }
+            const double mean = sr / n;
+            const double q = sr2 - n * mean * mean;
+            acc += sqrt(fmax(q, 0.0) / (n - 1));
+        }
+        acc = block_sum(acc, red);
+        if (tid == 0) part[(size_t)RT * nout + b] = acc;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        is_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int e = tid; e < nout; e += 256) {
+            double s = 0.0;
+            for (int t = 0; t < RT; t++) s += part[(size_t)t * nout + e];
+            out[e] = s;
+        }
+        if (tid == 0) {
+            double s = 0.0;
+            for (int b = 0; b < NSIG; b++) s += part[(size_t)RT * nout + b];
+            out[nout] = s;
+            *counter = 0u;
+        }
+    }
+}
+
 // K3 pass 2a: rows — sum the column-chunk partials;  2b: columns — sigma_j = sd(resid_j) (mcmloptim.h:216), summed.
 __global__ void __launch_bounds__(1024) mcnr_rows_kernel(int n, int ldn, int nchunks, const double* __restrict__ rowpart,
                                                          double* __restrict__ wsum, double* __restrict__ ssum) {
@@ -693,6 +931,9 @@ __global__ void __launch_bounds__(256) mcnr_assemble_kernel(int n, int P, int ld
 }
 
 }  // namespace
+
+// 1 (default) = MCNR pass 1 through the TMA kernel where it applies; 0 = the cp.async kernel (GMB_MCNR_TMA=0; parity tests compare both)
+static int g_mcnr_tma = [] { const char* e = getenv("GMB_MCNR_TMA"); return e ? atoi(e) : 1; }();
 
 // 1 = poisson/gaussian evaluations go through the row statistics (default); 0 = always stream zd (roofline probes, parity tests of the stream)
 static int g_rowstats = 1;
@@ -853,6 +1094,7 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
     int max_cc = (ncols + 31) / 32;
     int CC = want_cc < max_cc ? want_cc : max_cc; if (CC < 1) CC = 1;
     int cols_per_cta = (ncols + CC - 1) / CC;
+    cols_per_cta = round_up(cols_per_cta, 32);              // whole TMA boxes (8 columns) and whole 4-column reduction groups per warp
     CC = (ncols + cols_per_cta - 1) / cols_per_cta;
     const int NSIG = 64;
     size_t need = (size_t)CC * 2 * ldn + (size_t)RT * 2 * ncols + 2 * (size_t)ldn + NSIG;
@@ -864,6 +1106,31 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
     double* sigpart = ssum + ldn;
     double inv_phi = gmb_flink_gaussian(mdl->flink) ? 1.0 / (var_par * var_par) : 1.0;   // mcmlmodel.h:123-133
     dim3 grid(RT, CC);
+    const int fl = mdl->flink;
+    if (g_mcnr_tma && gmbtma::get_encode() && (fl == 1 || fl == 7 || (fl == 3 && mdl->f_valid))) {
+        // TMA pass + one tail launch
+        CUtensorMap tm;
+        const double* src = (fl == 3) ? mdl->dF : mdl->dzd;
+        GMB_TRY(gmbtma::make_map(&tm, src, n, ncols, ldn, 256, MCNR_TMA_COLS, false));
+        const size_t npart = (size_t)RT * (P * P + P) + NSIG;
+        GMB_TRY(gmb_ctx_scratch(ctx, (size_t)CC * 2 * ldn + (size_t)RT * 2 * ncols + npart));
+        rowpart = ctx->d_scratch; colpart = rowpart + (size_t)CC * 2 * ldn;
+        double* part = colpart + (size_t)RT * 2 * ncols;
+        static bool configured = false;
+        if (!configured) {
+            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
+            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
+            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
+            configured = true;
+        }
+        if (fl == 1) mcnr_tma_kernel<1><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart);
+        else if (fl == 3) mcnr_tma_kernel<3><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart);
+        else mcnr_tma_kernel<7><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart);
+        mcnr_tail_kernel<<<RT + NSIG, 256, 0, ctx->stream>>>(n, P, ldn, ncols, RT, CC, NSIG, mdl->dX, rowpart, colpart, part, ctx->d_counter, d_out);
+        ctx->launches += 2;
+        GMB_CUDA(cudaGetLastError());
+        return GMB_OK;
+    }
     size_t smem = 8 * MCNR_STAGES * 256 * sizeof(double);     // 64 KB: the column rings (the row-reduction buffer aliases them)
     {   // per device and cheap: set on every call
         GMB_CUDA(cudaFuncSetAttribute(mcnr_pass1_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -6,7 +6,7 @@
 // C (M x N, ldc) = alpha * op(A) * op(B) + beta * C, all column-major:
 //   transA = 0: A is M x K (m contiguous) ; transA = 1: A is K x M (k contiguous)
 //   transB = 0: B is K x N (k contiguous) ; transB = 1: B is N x K (n contiguous)
-#include "gemm_f64.cuh"
+#include "gemm_tma.cuh"
 
 namespace {
 
@@ -40,16 +40,16 @@ int gmb_dgemm_tri(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, dou
     EpiAxpby epi{alpha, beta, C, ldc};
     const int tri = (lower_a && M == K) ? (transA ? 2 : 1) : 0;
     if (tri) {
-        if (!transA && !transB) return gmbgemm::dispatch<false, true>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
-        if (!transA && transB) return gmbgemm::dispatch<false, false>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
-        if (transA && !transB) return gmbgemm::dispatch<true, true>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
-        return gmbgemm::dispatch<true, false>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+        if (!transA && !transB) return gmbtma::dispatch<false, true>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+        if (!transA && transB) return gmbtma::dispatch<false, false>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+        if (transA && !transB) return gmbtma::dispatch<true, true>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+        return gmbtma::dispatch<true, false>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
     }
     // A is k-contiguous when transposed; B is k-contiguous when NOT transposed
-    if (!transA && !transB) return gmbgemm::dispatch<false, true>(ctx, M, N, K, A, lda, B, ldb, epi);
-    if (!transA && transB) return gmbgemm::dispatch<false, false>(ctx, M, N, K, A, lda, B, ldb, epi);
-    if (transA && !transB) return gmbgemm::dispatch<true, true>(ctx, M, N, K, A, lda, B, ldb, epi);
-    return gmbgemm::dispatch<true, false>(ctx, M, N, K, A, lda, B, ldb, epi);
+    if (!transA && !transB) return gmbtma::dispatch<false, true>(ctx, M, N, K, A, lda, B, ldb, epi);
+    if (!transA && transB) return gmbtma::dispatch<false, false>(ctx, M, N, K, A, lda, B, ldb, epi);
+    if (transA && !transB) return gmbtma::dispatch<true, true>(ctx, M, N, K, A, lda, B, ldb, epi);
+    return gmbtma::dispatch<true, false>(ctx, M, N, K, A, lda, B, ldb, epi);
 }
 
 // In-place products with a 128 x 128 operand (the inverted diagonal blocks of cov_large.cu): the CTA tile spans the whole 128-wide side, so a
@@ -65,4 +65,10 @@ int gmb_dgemm_colpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const do
     if (M > 128 || N <= 0) return N <= 0 ? GMB_OK : gmb_set_error(GMB_EINVAL, "gmb_dgemm_colpanel: M must be <= 128");
     EpiAxpby epi{alpha, 0.0, C, ldc};
     return gmbgemm::launch<128, 64, 4, 2, false, true, EpiAxpby>(ctx, M, N, K, A, lda, B, ldb, epi, 0);
+}
+
+// C[:, c0:c1) -= P P^T on the lower tiles of the M x M matrix C (P: M x K, m contiguous): the trailing update of the blocked Cholesky
+int gmb_dsyrk_lower_sub(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc, int c0, int c1) {
+    EpiAxpby epi{-1.0, 1.0, C, ldc};
+    return gmbtma::dispatch_syrk_lower(ctx, M, K, Pm, ldp, epi, c0, c1);
 }

@@ -95,8 +95,17 @@ __global__ void __launch_bounds__(THREADS) dgemm_kernel(int M, int N, int K, con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp % WM, wn = warp / WM;
     // tri = 1: the last row tiles carry the longest k ranges — start them first (CTAs are scheduled in index order)
-    const int bx = (tri == 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-    const int m0 = bx * BM, n0 = blockIdx.y * BN;
+    // tri & 0xff = 3: symmetric rank-k update, lower tiles only (BM == BN): blockIdx.x enumerates the tile pairs (ti >= tj) of the tile columns
+    // tj >= tri >> 8, column by column — every CTA has the same amount of work and no tile of the upper triangle is computed
+    int bx = (tri == 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, by = blockIdx.y;
+    if ((tri & 0xff) == 3) {
+        const int T = (M + BM - 1) / BM;
+        int rem = blockIdx.x, tj = tri >> 8;
+        while (rem >= T - tj) { rem -= T - tj; tj++; }
+        bx = tj + rem; by = tj;
+        tri = 0;
+    }
+    const int m0 = bx * BM, n0 = by * BN;
     const int KT = (K + BK - 1) / BK;
     // triangular operand (a Cholesky factor): tri = 1: op(A)(m, k) = 0 for k > m ; tri = 2: op(A)(m, k) = 0 for k < m (the factor read transposed).
     // The k tiles that hold only zeros for this row tile are skipped — the same sums without their zero terms.
@@ -201,6 +210,9 @@ __global__ void __launch_bounds__(THREADS) dgemm_kernel(int M, int N, int K, con
     }
 }
 
+// lower tile pairs (ti >= tj) with tj in [c0, c1) of a T x T tile grid
+inline int syrk_tiles(int T, int c0, int c1) { int c = 0; for (int tj = c0; tj < c1 && tj < T; tj++) c += T - tj; return c; }
+
 template <int BM, int BN, int WM, int WN, bool AK, bool BKC, class Epi>
 int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi, int tri = 0) {
     using TA = OperandTile<BM, AK>;
@@ -213,28 +225,11 @@ int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const do
         configured = true;
     }
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+    if ((tri & 0xff) == 3) grid = dim3(syrk_tiles((M + BM - 1) / BM, tri >> 8, (N + BN - 1) / BN), 1);
     kern<<<grid, THREADS, smem, ctx->stream>>>(M, N, K, A, lda, B, ldb, epi, tri);
     ctx->launches++;
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;
-}
-
-// number of row tiles the dispatcher below will use (callers size their column-sum buffers with it)
-inline int row_tile(gmb_ctx* ctx, int M, int N) {
-    // 128 x 128 tiles when they make at least GMB_GEMM_WAVES waves of CTAs (one per SM); fewer, larger tiles lose the tail of the last wave
-    static const int waves = [] { const char* e = getenv("GMB_GEMM_WAVES"); return e ? atoi(e) : 4; }();
-    long tiles128 = (long)((M + 127) / 128) * ((N + 127) / 128);
-    return tiles128 >= (long)waves * ctx->sms ? 128 : 64;
-}
-
-template <bool AK, bool BKC, class Epi>
-int dispatch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi, int tri = 0) {
-    if (M <= 0 || N <= 0) return GMB_OK;
-    if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 1) || (ldb & 1))
-        return gmb_set_error(GMB_EINVAL, "dgemm: operands must be 16-byte aligned with even leading dimensions");
-    // big tiles when they fill the machine, otherwise 64x64 tiles for more CTAs
-    if (row_tile(ctx, M, N) == 128) return launch<128, 128, 2, 4, AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
-    return launch<64, 64, 2, 4, AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
 }
 
 }  // namespace gmbgemm

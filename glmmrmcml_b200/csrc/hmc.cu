@@ -16,7 +16,7 @@
 //
 // RNG: Philox4x32-10, counter (idx, iteration, chain, stream), key = seed; stream 0 = initial state (:48-49),
 // 2 = momentum (:62-63), 3 = accept uniform (:85).  Reproducible, unlike std::random_device at :55.
-#include "gemm_f64.cuh"
+#include "gemm_tma.cuh"
 
 // 1 (default) = the factored variant of the two-contraction sampler when Z is sparse, Z L is not and n >= 2 Q; 0 = always contract with the dense Z L
 static int g_hmc_factored = 1;
@@ -277,7 +277,7 @@ static bool factored_applicable(const gmb_model* mdl) {
 int hmc_layout(gmb_model* mdl, int C, HmcBuffers& b) {
     gmb_ctx* ctx = mdl->ctx;
     const size_t ldq = mdl->ldq, ldn = mdl->ldn;
-    const int rt = gmbgemm::row_tile(ctx, mdl->n, C);
+    const int rt = gmbtma::row_tile(ctx, mdl->n, C, mdl->Q);
     b.factored = factored_applicable(mdl);
     b.row_tiles = b.factored ? (mdl->n + 255) / 256 : (mdl->n + rt - 1) / rt;
     size_t need = 7 * ldq * C + ldn * C + (size_t)b.row_tiles * C + (size_t)CS_COUNT * C + (size_t)C /*steps as ints*/ + 16;
@@ -303,7 +303,7 @@ int launch_resid(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, con
     epi.steps = steps; epi.s = s;
     epi.c0 = (FL == 7 || FL == 8) ? (-1.0 * log(var_par) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;
     epi.sigma = var_par; epi.llpart = b.llpart; epi.C = C;
-    return gmbgemm::dispatch<false, true>(mdl->ctx, mdl->n, C, mdl->Q, mdl->dZL, mdl->ldn, b.VP, mdl->ldq, epi);
+    return gmbtma::dispatch<false, true>(mdl->ctx, mdl->n, C, mdl->Q, mdl->dZL, mdl->ldn, b.VP, mdl->ldq, epi);
 }
 
 template <int FL>
@@ -352,8 +352,8 @@ int launch_leap(gmb_model* mdl, int C, const HmcBuffers& b, double var_par, int 
     epi.VP = b.VP; epi.R = b.R; epi.G = b.G; epi.ldq = mdl->ldq; epi.steps = b.steps; epi.eps = b.cs + (size_t)CS_EPS * C;
     epi.s = s; epi.sc = gmb_flink_gaussian(mdl->flink) ? 1.0 / (var_par * var_par) : 1.0; epi.init = init;
     if (b.factored)     // G = -V' + s L^T T, T = Z^T RES
-        return gmbgemm::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->Q, mdl->dL, mdl->ldq, b.T, mdl->ldq, epi, mdl->l_lower ? 2 : 0);
-    return gmbgemm::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->n, mdl->dZL, mdl->ldn, b.RES, mdl->ldn, epi);
+        return gmbtma::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->Q, mdl->dL, mdl->ldq, b.T, mdl->ldq, epi, mdl->l_lower ? 2 : 0);
+    return gmbtma::dispatch<true, true>(mdl->ctx, mdl->Q, C, mdl->n, mdl->dZL, mdl->ldn, b.RES, mdl->ldn, epi);
 }
 
 }  // namespace

@@ -1,0 +1,18 @@
+"""Profiling driver: one large-block factorisation (+ one mvn_ll) at n = NLOC, for `ncu --metrics gpu__time_duration.sum`."""
+import sys, os, numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import glmmrmcml_b200 as g
+nloc = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
+m = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+rng = np.random.default_rng(1)
+xy = rng.random((nloc, 2))
+cov = np.array([[0, nloc, 13, 2, 0]], dtype=np.int32); data = np.concatenate([xy[:, 0], xy[:, 1]])
+ctx = g.Context(0)
+cv = g.Covariance(ctx, cov, data, np.zeros(1))
+th = np.array([0.25, 0.1])
+cv.logdet(th)
+ctx.sync(); ctx.timer_start(); cv.logdet(th * 1.001); print("factor ms", ctx.timer_stop())
+if m:
+    U = np.asfortranarray(rng.standard_normal((nloc, m)))
+    cv.loglik(th * 1.002, U)
+    ctx.timer_start(); cv.loglik(th * 1.003, U); print("mvn_ll (incl. H2D of U) ms", ctx.timer_stop())
