@@ -54,6 +54,11 @@ def estep_set_sparse_zd(on: bool):
     check(lib().gmb_estep_set_sparse_zd(int(bool(on))))
 
 
+def hmc_set_lane(on: bool):
+    """Small block-structured models: one lane per connected component of Z L (default) or one warp per chain (gmb_hmc_set_lane)."""
+    check(lib().gmb_hmc_set_lane(int(bool(on))))
+
+
 def hmc_set_factored(on: bool):
     """Two-GEMM sampler: apply a sparse Z and the dense factor L separately (default) or contract with the dense Z L (gmb_hmc_set_factored)."""
     check(lib().gmb_hmc_set_factored(int(bool(on))))

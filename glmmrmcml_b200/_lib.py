@@ -26,7 +26,7 @@ class GmbError(RuntimeError):
 class HmcStats(C.Structure):
     _fields_ = [("accept_rate", C.c_double), ("step_size_mean", C.c_double), ("steps_mean", C.c_double),
                 ("leapfrog_total", C.c_double), ("kernel_ms", C.c_double), ("n_chains", C.c_int),
-                ("nsamp_per_chain", C.c_int), ("rows_used", C.c_int), ("kernel_variant", C.c_int), ("zl_nonzeros", C.c_double), ("component_groups", C.c_int), ("factored", C.c_int)]
+                ("nsamp_per_chain", C.c_int), ("rows_used", C.c_int), ("kernel_variant", C.c_int), ("zl_nonzeros", C.c_double), ("component_groups", C.c_int), ("factored", C.c_int), ("lane_components", C.c_int)]
 
 
 GMB_OK, GMB_EINVAL, GMB_EFAMILY, GMB_ECUDA, GMB_ENOTPD, GMB_ENCCL, GMB_ESTATE, GMB_ECOV = range(8)
@@ -74,6 +74,7 @@ PROTOTYPES = {
     "gmb_estep_set_sparse_zd": (C.c_int, [C.c_int]),
     "gmb_hmc_set_components": (C.c_int, [C.c_int]),
     "gmb_hmc_set_factored": (C.c_int, [C.c_int]),
+    "gmb_hmc_set_lane": (C.c_int, [C.c_int]),
     "gmb_hmc_set_cluster_size": (C.c_int, [C.c_int]),
     "gmb_estep_set_rowstats": (C.c_int, [C.c_int]),
     "gmb_hmc_set_row_aggregation": (C.c_int, [C.c_int]),

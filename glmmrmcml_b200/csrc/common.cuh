@@ -121,6 +121,14 @@ struct gmb_comp {
     double* dval = nullptr; size_t val_cap = 0;  // lrv | lcv
 };
 
+// connected components of the view's Z L for the lane-per-component sampler (hmc_lane.cu): small block-structured models
+struct gmb_lane {
+    bool checked = false, valid = false;
+    bool tri = false; int ncomp = 0, L = 0, slots = 0;                // components; lanes per component; rows = columns owned by a lane                    // components (lanes per chain); padded rows = columns per component (4 or 6)
+    int* dint = nullptr; size_t int_cap = 0;     // rowid | colid
+    double* dval = nullptr; size_t val_cap = 0;  // dense blocks
+};
+
 struct gmb_model {
     gmb_ctx* ctx = nullptr;
     int n = 0, P = 0, Q = 0, flink = 0;
@@ -154,6 +162,7 @@ struct gmb_model {
     gmb_agg agg;                 // row aggregation for the on-chip sampler
     gmb_ell ell;                 // sparse form of the view's Z L (structure-aware sampler)
     gmb_comp comp;               // its connected components (large sparse models)
+    gmb_lane lane;               // ... and (small block-structured models)
     gmb_ell zell;                // sparse form of Z itself (factored sampler: Z sparse, L dense)
     double* hmc_work = nullptr;  // chain state + work buffers of the sampler
     size_t hmc_work_doubles = 0;
@@ -239,8 +248,13 @@ int gmb_zell_ensure(gmb_model* mdl);
 // hmc_comp.cu
 void gmb_comp_free(gmb_model* mdl);
 int gmb_comp_ensure(gmb_model* mdl);
+// hmc_lane.cu
+void gmb_lane_free(gmb_model* mdl);
+int gmb_lane_ensure(gmb_model* mdl);
 // the sparse forms describe the view's current Z L: call whenever it changes
-static inline void gmb_sparse_invalidate(gmb_model* mdl) { mdl->ell.checked = mdl->ell.valid = false; mdl->comp.checked = mdl->comp.valid = false; }
+static inline void gmb_sparse_invalidate(gmb_model* mdl) {
+    mdl->ell.checked = mdl->ell.valid = false; mdl->comp.checked = mdl->comp.valid = false; mdl->lane.checked = mdl->lane.valid = false;
+}
 
 // optim.cpp: gmb_minimize_bounded / gmb_fd_gradient / gmb_fd_hessian are declared in the public header
 

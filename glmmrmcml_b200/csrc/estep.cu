@@ -800,49 +800,66 @@ __global__ void __launch_bounds__(256, 2) mcnr_tma_kernel(const __grid_constant_
     }
 }
 
-// K3 tail in ONE launch: CTAs [0, RT) reduce the row partials of their 256-row tile over the column chunks and assemble the tile's share of
-// X' diag(w) X and X' s (one warp per output entry, fixed order); CTAs [RT, RT + NSIG) turn the column partials into sum_j sd(resid_j)
-// (mcmloptim.h:216); the last CTA to finish adds the per-CTA partials in index order -> out [P*P + P + 1].  Deterministic.
+// K3 tail in ONE launch.  CTAs [0, 8 RT): CTA (tile, sub) reduces the row partials of 32 rows of a 256-row tile over the column chunks (lane = row,
+// the 8 warps stride over the chunks, fixed-order combination through shared memory) and assembles those rows' share of X' diag(w) X and X' s
+// (one warp per output entry).  CTAs [8 RT, 8 RT + NSIG): 32 columns each per pass (lane = column, warps stride over the row tiles) -> their share
+// of sum_j sd(resid_j) (mcmloptim.h:216).  The last CTA to finish adds the per-CTA partials in index order -> out [P*P + P + 1].  Deterministic.
 __global__ void __launch_bounds__(256) mcnr_tail_kernel(int n, int P, int ldn, int ncols, int RT, int CC, int NSIG, const double* __restrict__ X,
                                                         const double* __restrict__ rowpart, const double* __restrict__ colpart,
-                                                        double* __restrict__ part /* [RT][P*P+P] then [NSIG] */, unsigned int* __restrict__ counter,
+                                                        double* __restrict__ part /* [8 RT][P*P+P] then [NSIG] */, unsigned int* __restrict__ counter,
                                                         double* __restrict__ out) {
-    __shared__ double sw[256], ss[256];
-    __shared__ double red[32];
+    __shared__ double sa[8][32], sb[8][32];
+    __shared__ double sw[32], ss[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nout = P * P + P;
-    if ((int)blockIdx.x < RT) {
-        const int i = blockIdx.x * 256 + tid;
+    const int nout = P * P + P, NR = 8 * RT;
+    if ((int)blockIdx.x < NR) {
+        const int i0 = ((int)blockIdx.x >> 3) * 256 + ((int)blockIdx.x & 7) * 32, i = i0 + lane;
         double a = 0.0, b = 0.0;
-        if (i < n) for (int c = 0; c < CC; c++) { a += rowpart[((size_t)c * 2 + 0) * ldn + i]; b += rowpart[((size_t)c * 2 + 1) * ldn + i]; }
-        sw[tid] = a; ss[tid] = b;
+        if (i < n) for (int c = warp; c < CC; c += 8) { a += rowpart[((size_t)c * 2 + 0) * ldn + i]; b += rowpart[((size_t)c * 2 + 1) * ldn + i]; }
+        sa[warp][lane] = a; sb[warp][lane] = b;
+        __syncthreads();
+        if (warp == 0) {
+            double ta = 0.0, tb = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { ta += sa[w][lane]; tb += sb[w][lane]; }
+            sw[lane] = ta; ss[lane] = tb;
+        }
         __syncthreads();
         double* dst = part + (size_t)blockIdx.x * nout;
+        const double wi = sw[lane], si = ss[lane];
         for (int e = warp; e < nout; e += 8) {
             double acc = 0.0;
-            if (e < P * P) {
-                const int pa = e % P, pb = e / P;
-                for (int r = lane; r < 256; r += 32) { const int ii = blockIdx.x * 256 + r; if (ii < n) acc += X[ii + (size_t)pa * ldn] * sw[r] * X[ii + (size_t)pb * ldn]; }
-            } else {
-                const int pa = e - P * P;
-                for (int r = lane; r < 256; r += 32) { const int ii = blockIdx.x * 256 + r; if (ii < n) acc += X[ii + (size_t)pa * ldn] * ss[r]; }
+            if (i < n) {
+                if (e < P * P) acc = X[i + (size_t)(e % P) * ldn] * wi * X[i + (size_t)(e / P) * ldn];
+                else acc = X[i + (size_t)(e - P * P) * ldn] * si;
             }
             acc = warp_sum(acc);
             if (lane == 0) dst[e] = acc;
         }
     } else {
-        const int b = blockIdx.x - RT;
-        double acc = 0.0;
-        for (int j = b * 256 + tid; j < ncols; j += NSIG * 256) {
+        const int b = blockIdx.x - NR;
+        double tot = 0.0;                                   // meaningful in warp 0
+        for (int j0 = b * 32; j0 < ncols; j0 += NSIG * 32) {
+            const int j = j0 + lane;
             double sr = 0.0, sr2 = 0.0;
-            for (int t = 0; t < RT; t++) { sr += colpart[((size_t)t * 2 + 0) * ncols + j]; sr2 += colpart[((size_t)t * 2 + 1) * ncols + j]; }
-            const double mean = sr / n;
-            const double q = sr2 - n * mean * mean;
-            acc += sqrt(fmax(q, 0.0) / (n - 1));
+            if (j < ncols) for (int t = warp; t < RT; t += 8) { sr += colpart[((size_t)t * 2 + 0) * ncols + j]; sr2 += colpart[((size_t)t * 2 + 1) * ncols + j]; }
+            __syncthreads();
+            sa[warp][lane] = sr; sb[warp][lane] = sr2;
+            __syncthreads();
+            if (warp == 0 && j < ncols) {
+                double r1 = 0.0, r2 = 0.0;
+#pragma unroll
+                for (int w = 0; w < 8; w++) { r1 += sa[w][lane]; r2 += sb[w][lane]; }
+                const double mean = r1 / n;
+                const double q = r2 - n * mean * mean;
+                tot += sqrt(fmax(q, 0.0) / (n - 1));
+            }
         }
-        acc = block_sum(acc, red);
-        if (tid == 0) part[(size_t)RT * nout + b] = acc;
+        if (warp == 0) {
+            tot = warp_sum(tot);
+            if (lane == 0) part[(size_t)NR * nout + b] = tot;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -854,12 +871,12 @@ __global__ void __launch_bounds__(256) mcnr_tail_kernel(int n, int P, int ldn, i
         __threadfence();
         for (int e = tid; e < nout; e += 256) {
             double s = 0.0;
-            for (int t = 0; t < RT; t++) s += part[(size_t)t * nout + e];
+            for (int t = 0; t < NR; t++) s += part[(size_t)t * nout + e];
             out[e] = s;
         }
         if (tid == 0) {
             double s = 0.0;
-            for (int b = 0; b < NSIG; b++) s += part[(size_t)RT * nout + b];
+            for (int b = 0; b < NSIG; b++) s += part[(size_t)NR * nout + b];
             out[nout] = s;
             *counter = 0u;
         }
@@ -1112,7 +1129,8 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
         CUtensorMap tm;
         const double* src = (fl == 3) ? mdl->dF : mdl->dzd;
         GMB_TRY(gmbtma::make_map(&tm, src, n, ncols, ldn, 256, MCNR_TMA_COLS, false));
-        const size_t npart = (size_t)RT * (P * P + P) + NSIG;
+        const int NSIG2 = (ncols + 31) / 32 < 512 ? (ncols + 31) / 32 : 512;
+        const size_t npart = (size_t)8 * RT * (P * P + P) + NSIG2;
         GMB_TRY(gmb_ctx_scratch(ctx, (size_t)CC * 2 * ldn + (size_t)RT * 2 * ncols + npart));
         rowpart = ctx->d_scratch; colpart = rowpart + (size_t)CC * 2 * ldn;
         double* part = colpart + (size_t)RT * 2 * ncols;
@@ -1126,7 +1144,7 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
         if (fl == 1) mcnr_tma_kernel<1><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart);
         else if (fl == 3) mcnr_tma_kernel<3><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart);
         else mcnr_tma_kernel<7><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart);
-        mcnr_tail_kernel<<<RT + NSIG, 256, 0, ctx->stream>>>(n, P, ldn, ncols, RT, CC, NSIG, mdl->dX, rowpart, colpart, part, ctx->d_counter, d_out);
+        mcnr_tail_kernel<<<8 * RT + NSIG2, 256, 0, ctx->stream>>>(n, P, ldn, ncols, RT, CC, NSIG2, mdl->dX, rowpart, colpart, part, ctx->d_counter, d_out);
         ctx->launches += 2;
         GMB_CUDA(cudaGetLastError());
         return GMB_OK;

@@ -450,6 +450,11 @@ size_t gmb_hmc_sparse_work_doubles(const gmb_model* mdl, int C);
 int gmb_hmc_run_sparse(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                        int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs);
 
+// hmc_lane.cu
+bool gmb_hmc_lane_applicable(const gmb_model* mdl);
+int gmb_hmc_run_lane(gmb_model* mdl, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
+                     int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, double* d_cs);
+
 // hmc_comp.cu
 bool gmb_hmc_comp_applicable(const gmb_model* mdl);
 size_t gmb_hmc_comp_work_doubles(const gmb_model* mdl, int C);
@@ -471,7 +476,8 @@ extern "C" int gmb_hmc_set_variant(int variant) {
 static int hmc_run_fused_timed(gmb_model* mdl, bool sparse, double var_par, int warmup, int nsamp, double lambda, int max_steps, double target_accept,
                                int adapt, int C, uint32_t chain_offset, uint64_t seed, double* dV_out, std::vector<double>* host_cs, float* ms) {
     gmb_ctx* ctx = mdl->ctx;
-    const bool comp = sparse && g_hmc_components && gmb_hmc_comp_applicable(mdl);
+    const bool lane = sparse && gmb_hmc_lane_applicable(mdl);
+    const bool comp = sparse && !lane && g_hmc_components && gmb_hmc_comp_applicable(mdl);
     const size_t need = comp ? gmb_hmc_comp_work_doubles(mdl, C)
                              : (sparse ? gmb_hmc_sparse_work_doubles(mdl, C) : gmb_hmc_fused_cs_doubles(C) + gmb_hmc_fused_scratch_doubles(mdl, C));
     if (need > mdl->hmc_work_doubles) {
@@ -480,7 +486,8 @@ static int hmc_run_fused_timed(gmb_model* mdl, bool sparse, double var_par, int 
         mdl->hmc_work_doubles = need;
     }
     GMB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (comp) GMB_TRY(gmb_hmc_run_comp(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
+    if (lane) GMB_TRY(gmb_hmc_run_lane(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
+    else if (comp) GMB_TRY(gmb_hmc_run_comp(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
     else if (sparse) GMB_TRY(gmb_hmc_run_sparse(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
     else GMB_TRY(gmb_hmc_run_fused(mdl, var_par, warmup, nsamp, lambda, max_steps, target_accept, adapt, C, chain_offset, seed, dV_out, mdl->hmc_work));
     GMB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -544,7 +551,7 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
     GMB_TRY(agg_update_zl(mdl));
     ph.mark("hmc: upload L, Z L");
     const bool try_sparse = core && (g_hmc_variant == 0 || g_hmc_variant == 3);
-    if (try_sparse) { GMB_TRY(gmb_ell_ensure(mdl)); GMB_TRY(gmb_comp_ensure(mdl)); }
+    if (try_sparse) { GMB_TRY(gmb_ell_ensure(mdl)); GMB_TRY(gmb_comp_ensure(mdl)); GMB_TRY(gmb_lane_ensure(mdl)); }
     ph.mark("hmc: sparse forms");
     GMB_TRY(set_xb(mdl, beta));
     const int C = n_chains, cols = nsamp_per_chain + 1;
@@ -588,7 +595,8 @@ extern "C" int gmb_hmc_sample(gmb_model* mdl, const double* L, const double* bet
         stats->rows_used = ((sparse || fused) && mdl->agg.built) ? mdl->agg.ng : mdl->n;
         stats->zl_nonzeros = sparse ? (double)mdl->ell.nnz : (double)stats->rows_used * mdl->Q;
         stats->factored = (!sparse && !fused && factored_applicable(mdl)) ? 1 : 0;
-        stats->component_groups = (sparse && g_hmc_components && gmb_hmc_comp_applicable(mdl)) ? mdl->comp.G : 0;
+        stats->lane_components = (sparse && gmb_hmc_lane_applicable(mdl)) ? mdl->lane.ncomp : 0;
+        stats->component_groups = (sparse && !stats->lane_components && g_hmc_components && gmb_hmc_comp_applicable(mdl)) ? mdl->comp.G : 0;
     }
     if (V_out)
         GMB_CUDA(cudaMemcpy2DAsync(V_out, mdl->Q * sizeof(double), mdl->dV, mdl->ldq * sizeof(double), mdl->Q * sizeof(double), ncol,

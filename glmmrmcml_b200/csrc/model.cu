@@ -102,6 +102,7 @@ extern "C" void gmb_model_destroy(gmb_model* mdl) {
     gmb_agg_free(mdl);
     gmb_ell_free(mdl);
     gmb_comp_free(mdl);
+    gmb_lane_free(mdl);
     gmb_dfree(mdl->ctx, mdl->dU); gmb_dfree(mdl->ctx, mdl->dzd); gmb_dfree(mdl->ctx, mdl->dF); gmb_dfree(mdl->ctx, mdl->dZL); gmb_dfree(mdl->ctx, mdl->dL);
     gmb_dfree(mdl->ctx, mdl->dV); gmb_dfree(mdl->ctx, mdl->hmc_work);
     delete mdl;

@@ -133,6 +133,7 @@ typedef struct gmb_hmc_stats {
     double zl_nonzeros;      /* entries of Z L the kernel works on per leapfrog step and chain: non-zeros (variant 3) or rows_used * Q */
     int    component_groups; /* variant 3 on a large model: groups of connected components of Z L the trajectory is decomposed into (else 0) */
     int    factored;         /* variant 1 with Z applied in sparse form and L as the dense operand (Q x Q contractions instead of n x Q) */
+    int    lane_components;  /* variant 3 on a small block-structured model: connected components of Z L, one lane each (else 0) */
 } gmb_hmc_stats;
 
 /* Runs n_chains independent copies of mcmcRunHMC::sample(warmup, .) (mhmcmc.h:121-157), each with its own
@@ -156,6 +157,11 @@ int gmb_hmc_set_variant(int variant);
 /* Structure-aware sampler on large models: 1 (default) = decompose the trajectory over the connected components of Z L (one warp per chain and
  * group of components, two launches per proposal), 0 = one CTA per chain streaming the sparse Z L on every leapfrog step. */
 int gmb_hmc_set_components(int on);
+
+/* Structure-aware sampler on small models: 1 (default) = when the view's Z L falls apart into at most 32 connected components of at most 6 rows
+ * and 6 columns (cluster designs: one per cluster), a lane integrates a whole component in registers and a leapfrog step needs no exchange
+ * between lanes (hmc_lane.cu); 0 = one warp per chain with the rows / columns spread over its lanes (hmc_sparse.cu). */
+int gmb_hmc_set_lane(int on);
 
 /* Two-GEMM sampler: 1 (default) = when Z is sparse, Z L is dense and n >= 2 Q, apply Z and L separately (W = L V', gather by the rows of Z,
  * residual, gather by its columns, G = L^T T: contractions of size Q x Q instead of n x Q); 0 = always contract with the dense n x Q matrix Z L. */

@@ -171,12 +171,18 @@ SPARSE_CASES = {
     "C1-warp-regs": (lambda: synth.config1(m=4), "binomial"),
     "C2-warp-regs": (lambda: synth.config2(m=4), "binomial"),
     "wide-blocks-warp-smem-ell": (lambda: synth.config4(ncl=5, nt=12, k=2, m=4), "poisson"),       # 12 x 12 blocks: ELL width 12 > 8
-    "ragged-warp-4-per-lane": (lambda: synth.config4(ncl=13, nt=7, k=3, m=4), "poisson"),          # Q = 91
+    "ragged-warp-4-per-thread": (lambda: synth.config4(ncl=13, nt=7, k=3, m=4), "poisson"),          # Q = 91
     "C4-cta128": (lambda: synth.config4(ncl=30, nt=10, k=2, m=4), "poisson"),                      # Q = 300, one CTA per chain
     "C4-cta512": (lambda: synth.config4(ncl=110, nt=10, k=1, m=4), "poisson"),                     # Q = 1100, one CTA per chain
     "C4-components": (lambda: synth.config4(ncl=30, nt=10, k=2, m=4), "poisson"),                  # Q = 300: 30 components in 10 groups
     "C4-components-ragged": (lambda: synth.config4(ncl=57, nt=7, k=1, m=4), "poisson"),            # Q = 399: 57 components of 7, groups of 4
     "C1-like-components": (lambda: synth.config1(m=4, ncl=40, nt=5, nind=3), "binomial"),          # Q = 240: components of 5 rows x 6 columns
+    # lane-per-component kernel (hmc_lane.cu): at most 32 components of at most 6 x 6
+    "C1-lane": (lambda: synth.config1(m=4), "binomial"),                                           # 10 components of 5 rows x 6 columns, 3 chains per warp
+    "C2-lane": (lambda: synth.config2(m=4), "binomial"),                                           # 10 components of 5 x 5
+    "blocks-of-4-lane": (lambda: synth.config2(m=4, ncl=7, nt=4, nind=5), "binomial"),            # 7 components of 4 x 4: 4 chains per warp
+    "poisson-30-lane": (lambda: synth.config4(ncl=30, nt=6, k=2, m=4), "poisson"),                 # 30 components of 6 x 6: one chain per warp
+    "poisson-17-lane": (lambda: synth.config4(ncl=17, nt=3, k=3, m=4), "poisson"),                 # 17 components of 3 x 3: one chain per warp, 15 idle lanes
 }
 
 
@@ -188,13 +194,15 @@ def test_structure_aware_sampler_follows_oracle(gctx, oracle, name):
     import glmmrmcml_b200 as g
     cfg = SPARSE_CASES[name][0]()
     g.hmc_set_components("components" in name)
+    g.hmc_set_lane(name.endswith("-lane"))
     try:
-        _structure_aware_case(gctx, oracle, g, cfg, "components" in name)
+        _structure_aware_case(gctx, oracle, g, cfg, "components" in name, name.endswith("-lane"))
     finally:
         g.hmc_set_components(True)
+        g.hmc_set_lane(True)
 
 
-def _structure_aware_case(gctx, oracle, g, cfg, want_components):
+def _structure_aware_case(gctx, oracle, g, cfg, want_components, want_lane=False):
     fl = oracle.flink(cfg["family"], cfg["link"])
     mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
     ZL = cfg["Z"] @ cfg["L"]; xb = cfg["X"] @ cfg["beta"]
@@ -204,6 +212,7 @@ def _structure_aware_case(gctx, oracle, g, cfg, want_components):
     st = out["stats"]
     assert st["kernel_variant"] == 3
     assert (st["component_groups"] >= 2) == want_components
+    assert (st["lane_components"] >= 1) == want_lane
     rows = np.unique(np.hstack([cfg["X"], cfg["Z"]]), axis=0).shape[0]
     assert st["rows_used"] == min(rows, cfg["n"]) or st["rows_used"] == cfg["n"]
     ZLv = ZL if st["rows_used"] == cfg["n"] else np.unique(np.hstack([cfg["X"], ZL]), axis=0)[:, cfg["X"].shape[1]:]
