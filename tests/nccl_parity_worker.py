@@ -67,13 +67,20 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     res["mcml_full"] = {"beta": float(np.max(np.abs(fm["beta"] - fs["beta"]))), "theta": float(np.max(np.abs(fm["theta"] - fs["theta"]))),
                         "iter": [fm["iter"], fs["iter"]], "u_max_abs": float(t.item())}
-    worst = max(max(v for k, v in res[nm].items()) for nm in cases)
-    res["worst_sum_rel_err"] = worst
-    res["ok"] = bool(worst <= 1e-12 and res["mcml_full"]["beta"] <= 1e-9 and res["mcml_full"]["theta"] <= 1e-9 and res["mcml_full"]["u_max_abs"] <= 1e-6
-                     and fm["iter"] == fs["iter"])
+    worst = max(max(v for k, v in res[nm].items() if k != "incr") for nm in cases)           # the all-reduced sums themselves
+    worst_incr = max(res[nm]["incr"] for nm in cases)                                          # Newton increment: the sums through a P x P solve
+    res["worst_sum_rel_err"] = worst; res["worst_incr_rel_err"] = worst_incr
+    res["ok"] = bool(worst <= 1e-12 and worst_incr <= 1e-9 and res["mcml_full"]["beta"] <= 1e-9 and res["mcml_full"]["theta"] <= 1e-7   # the theta step is an optimiser with xtol = 1e-8
+                     and res["mcml_full"]["u_max_abs"] <= 1e-6 and fm["iter"] == fs["iter"])
     dist.barrier()
     if rank == 0:
         print("NCCL_PARITY " + json.dumps(res), flush=True)
+        try:                                                      # keep the record next to the other GPU outputs
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "nccl_parity.json"), "w") as f:
+                json.dump(res, f, indent=1)
+        except OSError:
+            pass
     dist.destroy_process_group()
     sys.exit(0 if res["ok"] else 1)
 
