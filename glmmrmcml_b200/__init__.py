@@ -183,7 +183,10 @@ def default_context() -> "Context":
 class Model:
     """Device-resident replacement of glmmr::mcmlModel (inst/include/glmmrmcml/mcmlmodel.h:28-307)."""
 
-    def __init__(self, ctx: Context, X, Z, y, family: str, link: str):
+    def __init__(self, ctx: Context, X, Z, y, family: str, link: str, precision: str = "fp64"):
+        """precision: "fp64" (default) or "fp32" — storage of the streamed E-step matrices (gmb_model_create_prec)."""
+        if precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
         X = _f(X); Z = _f(Z); y = _v(y)
         n, P = X.shape
         if Z.shape[0] != n or y.size != n:
@@ -191,7 +194,9 @@ class Model:
         self.n, self.P, self.Q = n, P, Z.shape[1]
         self.ctx = ctx
         self._h = C.c_void_p()
-        check(lib().gmb_model_create(ctx._h, n, P, self.Q, _d(X), _d(Z), _d(y), family.encode(), link.encode(), C.byref(self._h)))
+        self.precision = precision
+        check(lib().gmb_model_create_prec(ctx._h, n, P, self.Q, _d(X), _d(Z), _d(y), family.encode(), link.encode(),
+                                          32 if precision == "fp32" else 64, C.byref(self._h)))
         self.flink = lib().gmb_model_flink(self._h)
 
     def close(self):

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "gmb_comm_allreduce_host": (C.c_int, [vp, dp, C.c_int]),
     "gmb_comm_bcast_host": (C.c_int, [vp, dp, C.c_int]),
     "gmb_model_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_char_p, C.c_char_p, C.POINTER(vp)]),
+    "gmb_model_create_prec": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, dp, dp, dp, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]),
     "gmb_model_destroy": (None, [vp]),
     "gmb_model_flink": (C.c_int, [vp]),
     "gmb_model_set_u": (C.c_int, [vp, dp, C.c_int, C.c_int, C.c_int, C.c_int]),

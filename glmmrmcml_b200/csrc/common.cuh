@@ -143,6 +143,9 @@ struct gmb_model {
     int beta_cap = 0;
     // samples (this rank's columns)
     double* dU = nullptr;        // ldq x m_cap
+    int prec = 64;               // 64: zd / F stored as double; 32 (gmb_model_create_prec): as float — half the E-step bytes, arithmetic stays fp64
+    float* dzd32 = nullptr;      // ldn x m_cap (fp32 mode)
+    float* dF32 = nullptr;
     double* dzd = nullptr;       // ldn x m_cap
     double* dF = nullptr;        // ldn x m_cap, binomial/logit only: exp(s_i zd_ij), s_i = -1 (y_i = 1) / +1 (y_i = 0); see estep.cu
     bool f_valid = false;

@@ -12,6 +12,15 @@
 
 namespace {
 
+// storage type of the streamed matrices (zd, F): double, or float in fp32 mode (values are widened on load; all arithmetic stays fp64)
+template <class T> struct Pair;
+template <> struct Pair<double> { typedef double2 type; };
+template <> struct Pair<float> { typedef float2 type; };
+template <class T> __device__ __forceinline__ double2 ld2(const T* p) {
+    const typename Pair<T>::type v = *reinterpret_cast<const typename Pair<T>::type*>(p);
+    return make_double2((double)v.x, (double)v.y);
+}
+
 __global__ void xb_kernel(int n, int P, int ldn, const double* __restrict__ X, const double* __restrict__ beta,
                           double* __restrict__ xb) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -135,22 +144,24 @@ __device__ __forceinline__ void grid_sum_finish(double acc, int TX, double* __re
 // i.e. two FP64 instructions instead of a 20-instruction exp, and one log per 8 elements: the kernel streams at the rate of the
 // Gaussian one instead of being issue bound.  A group whose product leaves the finite range is redone term by term.
 // ---------------------------------------------------------------------------------------------------
-__global__ void build_factor_kernel(int n, int ldn, int ncols, const double* __restrict__ zd, const double* __restrict__ y,
-                                    double* __restrict__ F) {
+template <class T>
+__global__ void build_factor_kernel(int n, int ldn, int ncols, const T* __restrict__ zd, const double* __restrict__ y,
+                                    T* __restrict__ F) {
     const int i = blockIdx.y * blockDim.x + threadIdx.x;          // grid.x (up to 2^31 - 1) runs over the columns
     const int j = blockIdx.x;
     if (i >= ldn || j >= ncols) return;
     double f = 1.0;
     if (i < n) {
         const double yi = y[i];
-        const double z = zd[i + (size_t)j * ldn];
+        const double z = (double)zd[i + (size_t)j * ldn];
         f = (yi == 1.0) ? exp(-1.0 * z) : exp(z);
     }
-    F[i + (size_t)j * ldn] = f;
+    F[i + (size_t)j * ldn] = (T)f;
 }
 
+template <class T>
 __global__ void __launch_bounds__(256) loglik_logit_factor_kernel(int n, int P, int ldn, int ncols, int cols_per_cta,
-                                                                  const double* __restrict__ F, const double* __restrict__ X,
+                                                                  const T* __restrict__ F, const double* __restrict__ X,
                                                                   const double* __restrict__ beta, const double* __restrict__ y,
                                                                   double* __restrict__ partials, unsigned int* __restrict__ counter,
                                                                   double* __restrict__ out) {
@@ -172,20 +183,20 @@ __global__ void __launch_bounds__(256) loglik_logit_factor_kernel(int n, int P, 
         const double y0 = y[i0], y1 = two ? y[i0 + 1] : -1.0;
         const double A0 = (y0 == 1.0) ? exp(-1.0 * xb0) : ((y0 == 0.0) ? exp(xb0) : 0.0);
         const double A1 = (y1 == 1.0) ? exp(-1.0 * xb1) : ((y1 == 0.0) ? exp(xb1) : 0.0);
-        const double* col = F + i0;
+        const T* col = F + i0;
         int j = j0 + threadIdx.y;
         double2 z[4], zn[4];
         bool have = j + 3 * TY < j1;
         if (have) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const double2*>(col + (size_t)(j + u * TY) * ldn);
+            for (int u = 0; u < 4; u++) z[u] = ld2(col + (size_t)(j + u * TY) * ldn);
         }
         while (have) {
             const int jn = j + 4 * TY;
             const bool have_n = jn + 3 * TY < j1;
             if (have_n) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) zn[u] = *reinterpret_cast<const double2*>(col + (size_t)(jn + u * TY) * ldn);
+                for (int u = 0; u < 4; u++) zn[u] = ld2(col + (size_t)(jn + u * TY) * ldn);
             }
             double p0 = 1.0, p1 = 1.0;
 #pragma unroll
@@ -202,7 +213,7 @@ __global__ void __launch_bounds__(256) loglik_logit_factor_kernel(int n, int P, 
             j = jn; have = have_n;
         }
         for (; j < j1; j += TY) {
-            const double2 zz = *reinterpret_cast<const double2*>(col + (size_t)j * ldn);
+            const double2 zz = ld2(col + (size_t)j * ldn);
             acc -= log(fma(A0, zz.x, 1.0)) + log(fma(A1, zz.y, 1.0));
         }
     }
@@ -330,9 +341,9 @@ __global__ void __launch_bounds__(256, 2) loglik_logit_factor_multi_kernel(int n
     }
 }
 
-template <int FL>
+template <int FL, class T>
 __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int ncols, int cols_per_cta,
-                                                     const double* __restrict__ zd, const double* __restrict__ X,
+                                                     const T* __restrict__ zd, const double* __restrict__ X,
                                                      const double* __restrict__ beta,
                                                      const double* __restrict__ y, const double* __restrict__ rowc,
                                                      double sigma, double* __restrict__ partials,
@@ -367,7 +378,7 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
         if (!two) r1.mask = 0.0;
         if ((FL == 4 || FL == 5 || FL == 6) && !two) r1.y = -1.0;      // neither 0 nor 1: the generic binomial terms contribute nothing
         if ((FL == 2 || FL == 8) && !two) { r1.y = 1.0; r1.xb = 1.0; }  // finite dummy, discarded below
-        const double* col = zd + i0;
+        const T* col = zd + i0;
         int j = j0 + threadIdx.y;
         // 4 independent 16-byte loads per group of columns, and the next group's loads are issued before the current group's
         // arithmetic (register double buffer): 128 bytes in flight per thread while the FP64 chains run
@@ -375,14 +386,14 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
         bool have = j + 3 * TY < j1;
         if (have) {
 #pragma unroll
-            for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const double2*>(col + (size_t)(j + u * TY) * ldn);
+            for (int u = 0; u < 4; u++) z[u] = ld2(col + (size_t)(j + u * TY) * ldn);
         }
         while (have) {
             const int jn = j + 4 * TY;
             const bool have_n = jn + 3 * TY < j1;
             if (have_n) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) zn[u] = *reinterpret_cast<const double2*>(col + (size_t)(jn + u * TY) * ldn);
+                for (int u = 0; u < 4; u++) zn[u] = ld2(col + (size_t)(jn + u * TY) * ldn);
             }
             double prod = 1.0, a1 = 0.0;
             int kmax = -(1 << 30);
@@ -406,7 +417,7 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
             j = jn; have = have_n;
         }
         for (; j < j1; j += TY) {
-            double2 z = *reinterpret_cast<const double2*>(col + (size_t)j * ldn);
+            double2 z = ld2(col + (size_t)j * ldn);
             double prod = 1.0, a1 = 0.0;
             int kmax = -(1 << 30);
             ll_accum<FL>(r0, z.x, c0, inv_sigma, stab, acc, prod, kmax);
@@ -427,8 +438,8 @@ __global__ void __launch_bounds__(256) loglik_kernel(int n, int P, int ldn, int 
 // so one evaluation costs O(n) once (S, T) or (T, T2) are known; they are built by ONE stream over zd per sample matrix (rowstat_kernel,
 // cached per (sample matrix, niter)) instead of one stream per evaluation.  Same sums as mcmlmodel.h:295-300, different order.
 // ---------------------------------------------------------------------------------------------------
-template <int FL>
-__global__ void __launch_bounds__(256) rowstat_kernel(int n, int ldn, int ncols, int cols_per_cta, const double* __restrict__ zd,
+template <int FL, class T>
+__global__ void __launch_bounds__(256) rowstat_kernel(int n, int ldn, int ncols, int cols_per_cta, const T* __restrict__ zd,
                                                       double* __restrict__ rowpart /* [gridDim.y][2][ldn] */) {
     extern __shared__ double sm[];           // [TY][2][2 TX]
     const int TX = blockDim.x, TY = blockDim.y;
@@ -436,9 +447,9 @@ __global__ void __launch_bounds__(256) rowstat_kernel(int n, int ldn, int ncols,
     const int j0 = blockIdx.y * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
     double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;       // (S or T2, T) of rows i0, i0 + 1
     if (i0 < ldn) {
-        const double* col = zd + i0;
+        const T* col = zd + i0;
         for (int j = j0 + threadIdx.y; j < j1; j += TY) {
-            const double2 z = *reinterpret_cast<const double2*>(col + (size_t)j * ldn);
+            const double2 z = ld2(col + (size_t)j * ldn);
             if (FL == 1) { a0 += exp(z.x); a1 += exp(z.y); }
             else { a0 = fma(z.x, z.x, a0); a1 = fma(z.y, z.y, a1); }
             b0 += z.x; b1 += z.y;
@@ -656,14 +667,14 @@ __device__ __forceinline__ double dev_rcp_cubic(double d) {
     return fma(y, t, y);
 }
 
-template <int FL>
+template <int FL, class T>
 __global__ void __launch_bounds__(256, 2) mcnr_tma_kernel(const __grid_constant__ CUtensorMap tm, int n, int ldn, int ncols, int cols_per_cta,
                                                           const double* __restrict__ xb, const double* __restrict__ y, double inv_phi,
                                                           double* __restrict__ rowpart, double* __restrict__ colpart) {
     extern __shared__ unsigned char smraw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
-    double* ring = reinterpret_cast<double*>(base);                                  // [stage][col][256]
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + MCNR_TMA_STAGES * 256 * MCNR_TMA_COLS);
+    T* ring = reinterpret_cast<T*>(base);                                            // [stage][col][256]
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)MCNR_TMA_STAGES * 256 * MCNR_TMA_COLS * sizeof(double));
     uint64_t* empty = full + MCNR_TMA_STAGES;
     __shared__ double stab[64];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -699,7 +710,7 @@ __global__ void __launch_bounds__(256, 2) mcnr_tma_kernel(const __grid_constant_
     auto produce = [&](int t) {
         const int s = t % MCNR_TMA_STAGES;
         if (t >= MCNR_TMA_STAGES) gmbtma::mbar_wait(&empty[s], ((t / MCNR_TMA_STAGES) - 1) & 1);
-        gmbtma::mbar_expect_tx(&full[s], 256 * MCNR_TMA_COLS * sizeof(double));
+        gmbtma::mbar_expect_tx(&full[s], 256 * MCNR_TMA_COLS * sizeof(T));
         gmbtma::tma_load_2d(ring + (size_t)s * 256 * MCNR_TMA_COLS, &tm, &full[s], rbase, j0 + t * MCNR_TMA_COLS);
     };
     if (tid == 0) for (int t = 0; t < MCNR_TMA_STAGES - 1 && t < ntile; t++) produce(t);
@@ -719,10 +730,10 @@ __global__ void __launch_bounds__(256, 2) mcnr_tma_kernel(const __grid_constant_
             gmbtma::mbar_wait(&full[s], (t / MCNR_TMA_STAGES) & 1);
             const int j = j0 + t * MCNR_TMA_COLS + warp;
             if (j < j1) {                                                            // warp-uniform
-                const double* col = ring + ((size_t)s * MCNR_TMA_COLS + warp) * 256 + lane;
+                const T* col = ring + ((size_t)s * MCNR_TMA_COLS + warp) * 256 + lane;
                 double z[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) z[k] = col[32 * k];
+                for (int k = 0; k < 8; k++) z[k] = (double)col[32 * k];
                 double sr = 0.0, sr2 = 0.0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
@@ -774,7 +785,7 @@ __global__ void __launch_bounds__(256, 2) mcnr_tma_kernel(const __grid_constant_
         if ((lane & 3) == 0 && cj >= 0) colpart[((size_t)blockIdx.x * 2 + (qi & 1)) * ncols + cj] = v1;
     }
     __syncthreads();                                   // every warp is done with the ring: reuse it for the cross-warp row reduction
-    double* red = ring;                                // [8 warps][2][256]
+    double* red = reinterpret_cast<double*>(base);     // [8 warps][2][256]
     const double nc = (double)(j1 - j0);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -985,12 +996,49 @@ static int ensure_rowstats(gmb_model* mdl) {
     double* rowpart = ctx->d_scratch;
     dim3 grid(RT, CC), block(TX, TY);
     const size_t smem = sizeof(double) * 4 * TX * TY;
-    if (mdl->flink == 1) rowstat_kernel<1><<<grid, block, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, rowpart);
-    else rowstat_kernel<7><<<grid, block, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, rowpart);
+    if (mdl->prec == 32) {
+        if (mdl->flink == 1) rowstat_kernel<1, float><<<grid, block, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd32, rowpart);
+        else rowstat_kernel<7, float><<<grid, block, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd32, rowpart);
+    } else {
+        if (mdl->flink == 1) rowstat_kernel<1, double><<<grid, block, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, rowpart);
+        else rowstat_kernel<7, double><<<grid, block, smem, ctx->stream>>>(n, ldn, ncols, cols_per_cta, mdl->dzd, rowpart);
+    }
     mcnr_rows_kernel<<<(n + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(n, ldn, CC, rowpart, mdl->dstat, mdl->dstat + ldn);
     ctx->launches += 2;
     GMB_CUDA(cudaGetLastError());
     mdl->stat_valid = true; mdl->stat_cols = ncols;
+    return GMB_OK;
+}
+
+// fp32 mode: the whole sample matrix of the model (float storage), one evaluation
+static int launch_loglik_f32(gmb_model* mdl, const double* d_beta, double var_par, int ncols, double* d_out) {
+    gmb_ctx* ctx = mdl->ctx;
+    const int n = mdl->n;
+    if (ncols <= 0) { GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream)); return GMB_OK; }
+    int half = (n + 1) / 2;
+    int TX = 32; while (TX < 256 && TX < half) TX <<= 1;
+    int TY = 256 / TX;
+    int RT = (half + TX - 1) / TX;
+    int want_cc = (ctx->sms * 6 + RT - 1) / RT;
+    int max_cc = (ncols + 4 * TY - 1) / (4 * TY);
+    int CC = want_cc < max_cc ? want_cc : max_cc; if (CC < 1) CC = 1;
+    int cols_per_cta = (ncols + CC - 1) / CC;
+    cols_per_cta = round_up(cols_per_cta, TY);
+    CC = (ncols + cols_per_cta - 1) / cols_per_cta;
+    GMB_TRY(gmb_ctx_scratch(ctx, (size_t)RT * CC));
+    double* partials = ctx->d_scratch;
+    unsigned int* counter = ctx->d_counter;
+    dim3 grid(RT, CC), block(TX, TY);
+    if (mdl->flink == 3 && mdl->f_valid)
+        loglik_logit_factor_kernel<float><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dF32, mdl->dX, d_beta, mdl->dy, partials, counter, d_out);
+    else switch (mdl->flink) {
+    case 1: loglik_kernel<1, float><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dzd32, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 3: loglik_kernel<3, float><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dzd32, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 7: loglik_kernel<7, float><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, mdl->dzd32, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    default: return gmb_set_error(GMB_EFAMILY, "fp32 mode: family/link code %d is not implemented (poisson/log, binomial/logit, gaussian/identity)", mdl->flink);
+    }
+    ctx->launches++;
+    GMB_CUDA(cudaGetLastError());
     return GMB_OK;
 }
 
@@ -1010,6 +1058,7 @@ int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, doub
         GMB_CUDA(cudaGetLastError());
         return GMB_OK;
     }
+    if (mdl->prec == 32) return launch_loglik_f32(mdl, d_beta, var_par, mdl->niter_local, d_out);
     return gmb_launch_loglik_cols(mdl, d_beta, var_par, mdl->dzd, mdl->niter_local, d_out);
 }
 
@@ -1036,17 +1085,17 @@ int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par,
     dim3 grid(RT, CC), block(TX, TY);
     if (mdl->flink == 3 && mdl->f_valid && d_zd >= mdl->dzd && d_zd < mdl->dzd + (size_t)mdl->ldn * mdl->m_cap) {
         const double* d_f = mdl->dF + (d_zd - mdl->dzd);              // the same block of columns of the factor matrix
-        loglik_logit_factor_kernel<<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_f, mdl->dX, d_beta, mdl->dy,
+        loglik_logit_factor_kernel<double><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_f, mdl->dX, d_beta, mdl->dy,
                                                                    partials, counter, d_out);
         ctx->launches++;
         GMB_CUDA(cudaGetLastError());
         return GMB_OK;
     }
     switch (mdl->flink) {
-    case 1: loglik_kernel<1><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
-    case 3: loglik_kernel<3><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
-    case 7: loglik_kernel<7><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
-#define GMB_LL_CASE(F) case F: loglik_kernel<F><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 1: loglik_kernel<1, double><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 3: loglik_kernel<3, double><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+    case 7: loglik_kernel<7, double><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
+#define GMB_LL_CASE(F) case F: loglik_kernel<F, double><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_zd, mdl->dX, d_beta, mdl->dy, mdl->drowc, var_par, partials, counter, d_out); break;
     GMB_LL_CASE(2) GMB_LL_CASE(4) GMB_LL_CASE(5) GMB_LL_CASE(6) GMB_LL_CASE(8)
 #undef GMB_LL_CASE
     default: return gmb_set_error(GMB_EFAMILY, "family/link code %d has no device kernel", mdl->flink);
@@ -1062,7 +1111,7 @@ int gmb_launch_loglik_multi(gmb_model* mdl, const double* d_beta, int n_eval, do
     gmb_ctx* ctx = mdl->ctx;
     *done = 0;
     const int n = mdl->n, ncols = mdl->niter_local;
-    if (!(mdl->flink == 3 && mdl->f_valid && ncols > 0 && n_eval >= GMB_LOGLIK_NB)) return GMB_OK;
+    if (!(mdl->flink == 3 && mdl->f_valid && ncols > 0 && n_eval >= GMB_LOGLIK_NB) || mdl->prec == 32) return GMB_OK;
     const int groups = (n_eval + GMB_LOGLIK_NB - 1) / GMB_LOGLIK_NB;
     if (groups > 65535) return GMB_OK;
     int half = (n + 1) / 2;
@@ -1095,7 +1144,8 @@ int gmb_launch_build_factor(gmb_model* mdl, int ncols) {
     gmb_ctx* ctx = mdl->ctx;
     if (ncols <= 0) return GMB_OK;
     dim3 grid(ncols, (mdl->ldn + 255) / 256);
-    build_factor_kernel<<<grid, 256, 0, ctx->stream>>>(mdl->n, mdl->ldn, ncols, mdl->dzd, mdl->dy, mdl->dF);
+    if (mdl->prec == 32) build_factor_kernel<float><<<grid, 256, 0, ctx->stream>>>(mdl->n, mdl->ldn, ncols, mdl->dzd32, mdl->dy, mdl->dF32);
+    else build_factor_kernel<double><<<grid, 256, 0, ctx->stream>>>(mdl->n, mdl->ldn, ncols, mdl->dzd, mdl->dy, mdl->dF);
     ctx->launches++;
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;
@@ -1124,11 +1174,14 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
     double inv_phi = gmb_flink_gaussian(mdl->flink) ? 1.0 / (var_par * var_par) : 1.0;   // mcmlmodel.h:123-133
     dim3 grid(RT, CC);
     const int fl = mdl->flink;
-    if (g_mcnr_tma && gmbtma::get_encode() && (fl == 1 || fl == 7 || (fl == 3 && mdl->f_valid))) {
+    if (mdl->prec == 32 && !(gmbtma::get_encode() && (fl == 1 || fl == 7 || (fl == 3 && mdl->f_valid))))
+        return gmb_set_error(GMB_EFAMILY, "fp32 mode: the MCNR step is implemented for poisson/log, binomial/logit and gaussian/identity");
+    if ((g_mcnr_tma || mdl->prec == 32) && gmbtma::get_encode() && (fl == 1 || fl == 7 || (fl == 3 && mdl->f_valid))) {
         // TMA pass + one tail launch
         CUtensorMap tm;
-        const double* src = (fl == 3) ? mdl->dF : mdl->dzd;
-        GMB_TRY(gmbtma::make_map(&tm, src, n, ncols, ldn, 256, MCNR_TMA_COLS, false));
+        const bool f32 = mdl->prec == 32;
+        const void* src = f32 ? (const void*)((fl == 3) ? mdl->dF32 : mdl->dzd32) : (const void*)((fl == 3) ? mdl->dF : mdl->dzd);
+        GMB_TRY(gmbtma::make_map(&tm, src, n, ncols, ldn, 256, MCNR_TMA_COLS, false, f32));
         const int NSIG2 = (ncols + 31) / 32 < 512 ? (ncols + 31) / 32 : 512;
         const size_t npart = (size_t)8 * RT * (P * P + P) + NSIG2;
         GMB_TRY(gmb_ctx_scratch(ctx, (size_t)CC * 2 * ldn + (size_t)RT * 2 * ncols + npart));
@@ -1136,14 +1189,18 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
         double* part = colpart + (size_t)RT * 2 * ncols;
         static bool configured = false;
         if (!configured) {
-            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
-            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
-            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
+            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<1, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
+            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<3, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
+            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<7, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
+            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
+            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<3, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
+            GMB_CUDA(cudaFuncSetAttribute(mcnr_tma_kernel<7, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCNR_TMA_SMEM));
             configured = true;
         }
-        if (fl == 1) mcnr_tma_kernel<1><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart);
-        else if (fl == 3) mcnr_tma_kernel<3><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart);
-        else mcnr_tma_kernel<7><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart);
+#define GMB_NR_TMA(F, TT) mcnr_tma_kernel<F, TT><<<grid, 256, MCNR_TMA_SMEM, ctx->stream>>>(tm, n, ldn, ncols, cols_per_cta, d_xb, mdl->dy, inv_phi, rowpart, colpart)
+        if (f32) { if (fl == 1) GMB_NR_TMA(1, float); else if (fl == 3) GMB_NR_TMA(3, float); else GMB_NR_TMA(7, float); }
+        else { if (fl == 1) GMB_NR_TMA(1, double); else if (fl == 3) GMB_NR_TMA(3, double); else GMB_NR_TMA(7, double); }
+#undef GMB_NR_TMA
         mcnr_tail_kernel<<<8 * RT + NSIG2, 256, 0, ctx->stream>>>(n, P, ldn, ncols, RT, CC, NSIG2, mdl->dX, rowpart, colpart, part, ctx->d_counter, d_out);
         ctx->launches += 2;
         GMB_CUDA(cudaGetLastError());

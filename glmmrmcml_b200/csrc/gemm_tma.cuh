@@ -236,14 +236,14 @@ inline encode_fn get_encode() {
 }
 
 // tensor map of a column-major fp64 operand: rows = extent of the contiguous dimension, cols = the other, ld in doubles
-inline int make_map(CUtensorMap* tm, const double* ptr, int rows, int cols, int ld, int box_rows, int box_cols, bool swizzle128 = true) {
+inline int make_map(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld, int box_rows, int box_cols, bool swizzle128 = true, bool f32 = false) {
     encode_fn enc = get_encode();
     if (!enc) return gmb_set_error(GMB_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? sizeof(float) : sizeof(double))};
     cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return gmb_set_error(GMB_ECUDA, "cuTensorMapEncodeTiled failed (%d) for a %d x %d operand, ld %d", (int)r, rows, cols, ld);
     return GMB_OK;

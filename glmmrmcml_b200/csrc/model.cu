@@ -58,18 +58,26 @@ int upload_params(gmb_model* mdl, const double* beta, int count) {
 
 extern "C" int gmb_model_create(gmb_ctx* ctx, int n, int P, int Q, const double* X, const double* Z, const double* y,
                                 const char* family, const char* link, gmb_model** out) {
+    return gmb_model_create_prec(ctx, n, P, Q, X, Z, y, family, link, 64, out);
+}
+
+extern "C" int gmb_model_create_prec(gmb_ctx* ctx, int n, int P, int Q, const double* X, const double* Z, const double* y,
+                                     const char* family, const char* link, int precision, gmb_model** out) {
+    if (precision != 64 && precision != 32) return gmb_set_error(GMB_EINVAL, "precision must be 64 or 32 (got %d)", precision);
     if (!ctx || !out || !X || !Z || !y || n <= 0 || P <= 0 || Q <= 0)
         return gmb_set_error(GMB_EINVAL, "gmb_model_create: bad arguments (n=%d P=%d Q=%d)", n, P, Q);
     int fl = flink_from_strings(family, link);
     if (fl == 0)
         return gmb_set_error(GMB_EFAMILY, "unknown family/link '%s'/'%s' (mcmlmodel.h:74-87 lists the valid pairs)",
                              family ? family : "", link ? link : "");
+    if (precision == 32 && !gmb_flink_core(fl))
+        return gmb_set_error(GMB_EFAMILY, "fp32 mode is implemented for poisson/log, binomial/logit and gaussian/identity (got code %d)", fl);
     if (!gmb_flink_supported(fl))
         return gmb_set_error(GMB_EFAMILY, "family/link '%s'/'%s' (code %d) has no device kernel (supported: codes 1-8; the Gamma codes are "
                              "unreachable in the reference, whose family string is 'Gamma', and beta/logit is not implemented)", family, link, fl);
     GMB_CUDA(cudaSetDevice(ctx->device));
     gmb_model* mdl = new gmb_model();
-    mdl->ctx = ctx; mdl->n = n; mdl->P = P; mdl->Q = Q; mdl->flink = fl;
+    mdl->ctx = ctx; mdl->n = n; mdl->P = P; mdl->Q = Q; mdl->flink = fl; mdl->prec = precision;
     mdl->ldn = round_up(n, 4); mdl->ldq = round_up(Q, 4);
     const size_t ldn = mdl->ldn;
     cudaError_t e = cudaSuccess;
@@ -103,6 +111,7 @@ extern "C" void gmb_model_destroy(gmb_model* mdl) {
     gmb_ell_free(mdl);
     gmb_comp_free(mdl);
     gmb_lane_free(mdl);
+    gmb_dfree(mdl->ctx, mdl->dzd32); gmb_dfree(mdl->ctx, mdl->dF32);
     gmb_dfree(mdl->ctx, mdl->dU); gmb_dfree(mdl->ctx, mdl->dzd); gmb_dfree(mdl->ctx, mdl->dF); gmb_dfree(mdl->ctx, mdl->dZL); gmb_dfree(mdl->ctx, mdl->dL);
     gmb_dfree(mdl->ctx, mdl->dV); gmb_dfree(mdl->ctx, mdl->hmc_work);
     delete mdl;
@@ -122,25 +131,40 @@ int gmb_model_reserve_samples(gmb_model* mdl, int m) {
     mdl->m_cap = 0;
     size_t cap = (size_t)m;
     GMB_CUDA(gmb_dmalloc(ctx, &mdl->dU, sizeof(double) * mdl->ldq * cap));
-    GMB_CUDA(gmb_dmalloc(ctx, &mdl->dzd, sizeof(double) * mdl->ldn * cap));
-    if (mdl->flink == 3) GMB_CUDA(gmb_dmalloc(ctx, &mdl->dF, sizeof(double) * mdl->ldn * cap));
+    if (mdl->dzd32) { gmb_dfree(ctx, mdl->dzd32); mdl->dzd32 = nullptr; }
+    if (mdl->dF32) { gmb_dfree(ctx, mdl->dF32); mdl->dF32 = nullptr; }
     // padding rows must hold finite values: the streaming kernels load them (and mask the result)
     GMB_CUDA(cudaMemsetAsync(mdl->dU, 0, sizeof(double) * mdl->ldq * cap, ctx->stream));
-    GMB_CUDA(cudaMemsetAsync(mdl->dzd, 0, sizeof(double) * mdl->ldn * cap, ctx->stream));
+    if (mdl->prec == 32) {
+        GMB_CUDA(gmb_dmalloc(ctx, &mdl->dzd32, sizeof(float) * mdl->ldn * cap));
+        if (mdl->flink == 3) GMB_CUDA(gmb_dmalloc(ctx, &mdl->dF32, sizeof(float) * mdl->ldn * cap));
+        GMB_CUDA(cudaMemsetAsync(mdl->dzd32, 0, sizeof(float) * mdl->ldn * cap, ctx->stream));
+    } else {
+        GMB_CUDA(gmb_dmalloc(ctx, &mdl->dzd, sizeof(double) * mdl->ldn * cap));
+        if (mdl->flink == 3) GMB_CUDA(gmb_dmalloc(ctx, &mdl->dF, sizeof(double) * mdl->ldn * cap));
+        GMB_CUDA(cudaMemsetAsync(mdl->dzd, 0, sizeof(double) * mdl->ldn * cap, ctx->stream));
+    }
     mdl->m_cap = m;
     return GMB_OK;
 }
 
 // zd = Z u for the first m_local columns of dU (mcmlmodel.h:286 / :117, hoisted)
 // zd = Z u with Z in ELL form (indicator designs: one or two non-zeros per row): a gather instead of a 2 n Q m flop contraction
+template <class T>
 __global__ void __launch_bounds__(256) zd_sparse_kernel(int n, int ldn, int ngp, int wr, int ldq, const double* __restrict__ rv, const int* __restrict__ rc,
-                                                        const double* __restrict__ U, double* __restrict__ zd) {
+                                                        const double* __restrict__ U, T* __restrict__ zd) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     const size_t j = blockIdx.y;
     if (i >= ldn) return;
     double s = 0.0;
     if (i < n) for (int w = 0; w < wr; w++) s = fma(rv[(size_t)w * ngp + i], U[rc[(size_t)w * ngp + i] + j * ldq], s);
-    zd[i + j * ldn] = s;
+    zd[i + j * ldn] = (T)s;
+}
+
+// fp32 mode, dense Z: a block of columns of the fp64 product, narrowed
+__global__ void narrow_kernel(size_t count, const double* __restrict__ src, float* __restrict__ dst) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < count) dst[e] = (float)src[e];
 }
 
 // 1 (default) = build zd by gathering when Z is sparse (same criterion as the samplers' sparse forms), 0 = always the dense contraction
@@ -157,16 +181,34 @@ int gmb_model_build_zd(gmb_model* mdl) {
         const gmb_ell& e = mdl->zell;
         for (int j0 = 0; j0 < mdl->m_local; j0 += 65535) {
             const int nc = std::min(65535, mdl->m_local - j0);
-            zd_sparse_kernel<<<dim3((mdl->ldn + 255) / 256, nc), 256, 0, mdl->ctx->stream>>>(mdl->n, mdl->ldn, e.ngp, e.wr, mdl->ldq, e.rv, e.rc,
-                                                                                           mdl->dU + (size_t)j0 * mdl->ldq, mdl->dzd + (size_t)j0 * mdl->ldn);
+            if (mdl->prec == 32)
+                zd_sparse_kernel<float><<<dim3((mdl->ldn + 255) / 256, nc), 256, 0, mdl->ctx->stream>>>(mdl->n, mdl->ldn, e.ngp, e.wr, mdl->ldq, e.rv, e.rc,
+                                                                                                      mdl->dU + (size_t)j0 * mdl->ldq, mdl->dzd32 + (size_t)j0 * mdl->ldn);
+            else
+                zd_sparse_kernel<double><<<dim3((mdl->ldn + 255) / 256, nc), 256, 0, mdl->ctx->stream>>>(mdl->n, mdl->ldn, e.ngp, e.wr, mdl->ldq, e.rv, e.rc,
+                                                                                                       mdl->dU + (size_t)j0 * mdl->ldq, mdl->dzd + (size_t)j0 * mdl->ldn);
             mdl->ctx->launches++;
+        }
+        GMB_CUDA(cudaGetLastError());
+    } else if (mdl->m_local > 0 && mdl->prec == 32) {
+        // dense Z in fp32 mode: the fp64 DMMA product in column chunks through the context's scratch area, narrowed to float
+        gmb_ctx* ctx = mdl->ctx;
+        const int chunk = std::max(1, std::min(mdl->m_local, (int)(((size_t)1 << 27) / (size_t)mdl->ldn)));
+        GMB_TRY(gmb_ctx_scratch(ctx, (size_t)mdl->ldn * chunk));
+        for (int j0 = 0; j0 < mdl->m_local; j0 += chunk) {
+            const int nc = std::min(chunk, mdl->m_local - j0);
+            GMB_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(double) * (size_t)mdl->ldn * nc, ctx->stream));
+            GMB_TRY(gmb_dgemm(ctx, 0, 0, mdl->n, nc, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dU + (size_t)j0 * mdl->ldq, mdl->ldq, 0.0, ctx->d_scratch, mdl->ldn));
+            const size_t cnt = (size_t)mdl->ldn * nc;
+            narrow_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(cnt, ctx->d_scratch, mdl->dzd32 + (size_t)j0 * mdl->ldn);
+            ctx->launches++;
         }
         GMB_CUDA(cudaGetLastError());
     } else if (mdl->m_local > 0)
         GMB_TRY(gmb_dgemm(mdl->ctx, 0, 0, mdl->n, mdl->m_local, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dU, mdl->ldq, 0.0, mdl->dzd, mdl->ldn));
     mdl->f_valid = false;
     mdl->stat_valid = false;
-    if (mdl->flink == 3 && mdl->dF && mdl->m_local > 0) {        // factor matrix of the binomial/logit E-step (estep.cu)
+    if (mdl->flink == 3 && (mdl->dF || mdl->dF32) && mdl->m_local > 0) {        // factor matrix of the binomial/logit E-step (estep.cu)
         GMB_TRY(gmb_launch_build_factor(mdl, mdl->m_local));
         mdl->f_valid = true;
     }
