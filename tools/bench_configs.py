@@ -299,6 +299,32 @@ def run_config(name, env, size="full", oracle=None, check=True):
             del Lg, D1
         parity["oracle_s"] = round(time.perf_counter() - t0, 2)
 
+    # ---- fp32 mode: the same E-step on float storage of zd / F (half the bytes), against the same fp64 oracle values at 1e-5 -------------
+    if fam in ("binomial", "poisson", "gaussian"):
+        m32 = g.Model(ctx, cfg["X"], cfg["Z"], cfg["y"], fam, link, precision="fp32")
+        m32.set_u(U, m_total=m_total)
+        ll32 = m32.log_likelihood(beta, sig)
+        nr32 = m32.mcnr(beta, sig)
+        by32 = 4.0 * n * m_local + 8.0 * n
+        g.estep_set_rowstats(False)
+        try:
+            m32.log_likelihood(beta, sig)
+            t32 = env.max(timed(ctx, lambda: m32.log_likelihood(beta, sig), reps=5, flush=True))
+        finally:
+            g.estep_set_rowstats(True)
+        t32n = env.max(timed(ctx, lambda: m32.mcnr(beta, sig), reps=3, flush=True))
+        out["fp32"] = {"dtype": "f32 storage of zd / F, f64 accumulation (gmb_model_create_prec(..., 32))",
+                       "estep_evals_per_s_stream_cold": 1e3 / t32, "speedup_vs_f64_stream": t_stream / t32,
+                       "mcnr_steps_per_s": 1e3 / t32n, "mcnr_speedup_vs_f64": t_nr / t32n,
+                       "roofline": {"bound": "hbm", "achieved": by32 / t32 / 1e6, "peak": env.hbm, "unit": "GB/s", "frac": by32 / t32 / 1e6 / env.hbm,
+                                    "bytes_per_launch": by32, "ms": t32},
+                       "mcnr_roofline": {"bound": "hbm", "achieved": (by32 + 8.0 * n * P) / t32n / 1e6, "peak": env.hbm, "unit": "GB/s",
+                                         "frac": (by32 + 8.0 * n * P) / t32n / 1e6 / env.hbm, "ms": t32n}}
+        if check:
+            parity["fp32"] = {"loglik_rel_err": abs(ll32 - ll_ref) / abs(ll_ref), "mcnr_xtwx_rel_err": rel(nr32["xtwx"], xtwx_ref),
+                              "mcnr_sigma_rel_err": abs(nr32["sigma"] - sg / m_total) / (sg / m_total), "tol": 1e-5}
+        m32.close()
+
     # ---- K6: sampler -------------------------------------------------------------------------------------------------------
     h = cfg["hmc"]
     C_local = max(1, cfg["chains_total"] // world)
@@ -365,7 +391,8 @@ def run_config(name, env, size="full", oracle=None, check=True):
         ok = (parity["loglik"]["rel_err"] <= 1e-10 and parity["loglik"]["rel_err_default_path"] <= 1e-10 and parity["mcnr"]["xtwx_rel_err"] <= 1e-10
               and parity["mcnr"]["score_rel_err"] <= 1e-10 and parity["mcnr"]["sigma_rel_err"] <= 1e-10 and parity["mvn_ll"]["rel_err"] <= 1e-10
               and parity["loglik_on_sampled_u"]["rel_err"] <= 1e-10 and parity["log_prob"]["rel_err"] <= 1e-10 and parity["log_grad"]["rel_err"] <= 1e-10
-              and parity["chain"]["max_abs_err"] <= 1e-7 and parity.get("chol", {"ok": True})["ok"])
+              and parity["chain"]["max_abs_err"] <= 1e-7 and parity.get("chol", {"ok": True})["ok"]
+              and max(parity.get("fp32", {"loglik_rel_err": 0.0})["loglik_rel_err"], parity.get("fp32", {"mcnr_xtwx_rel_err": 0.0})["mcnr_xtwx_rel_err"]) <= 1e-5)
         parity["ok"] = bool(ok)
     out["parity"] = parity if check else None
     mdl.close(); cv.close()
