@@ -44,6 +44,11 @@ def estep_set_multi(on: bool):
     check(lib().gmb_estep_set_multi(int(bool(on))))
 
 
+def estep_set_tf32(on: bool):
+    """fp32 mode, dense Z: zd = Z u on the tensor cores (tcgen05, 3xTF32; default) or as the fp64 product narrowed to float (gmb_estep_set_tf32)."""
+    check(lib().gmb_estep_set_tf32(int(bool(on))))
+
+
 def hmc_set_components(on: bool):
     """Large sparse models: trajectory decomposed over the connected components of Z L (default) or one CTA per chain (gmb_hmc_set_components)."""
     check(lib().gmb_hmc_set_components(int(bool(on))))

@@ -72,6 +72,7 @@ PROTOTYPES = {
                                  C.c_int, C.c_uint32, C.c_uint64, C.c_int, dp, dp, C.POINTER(HmcStats)]),
     "gmb_hmc_set_variant": (C.c_int, [C.c_int]),
     "gmb_estep_set_multi": (C.c_int, [C.c_int]),
+    "gmb_estep_set_tf32": (C.c_int, [C.c_int]),
     "gmb_estep_set_sparse_zd": (C.c_int, [C.c_int]),
     "gmb_hmc_set_components": (C.c_int, [C.c_int]),
     "gmb_hmc_set_factored": (C.c_int, [C.c_int]),

@@ -146,6 +146,8 @@ struct gmb_model {
     int prec = 64;               // 64: zd / F stored as double; 32 (gmb_model_create_prec): as float — half the E-step bytes, arithmetic stays fp64
     float* dzd32 = nullptr;      // ldn x m_cap (fp32 mode)
     float* dF32 = nullptr;
+    float *dZt_hi = nullptr, *dZt_lo = nullptr;   // fp32 mode, dense Z: K-major 3xTF32 split of Z (n rows of ldk floats), built once (gemm_tf32.cu)
+    float *dU_hi = nullptr, *dU_lo = nullptr; size_t u32_cap = 0;   // ... and of the current sample matrix (m rows of ldk floats)
     double* dzd = nullptr;       // ldn x m_cap
     double* dF = nullptr;        // ldn x m_cap, binomial/logit only: exp(s_i zd_ij), s_i = -1 (y_i = 1) / +1 (y_i = 0); see estep.cu
     bool f_valid = false;
@@ -215,6 +217,12 @@ int gmb_dgemm_tri(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, dou
 int gmb_dsyrk_lower_sub(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc, int c0, int c1);   // C[:, c0:c1) -= P P^T, lower tiles
 int gmb_dgemm_rowpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias A
 int gmb_dgemm_colpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias B
+
+// gemm_tf32.cu: tcgen05 (kind::tf32, 3xTF32 split) contraction of the fp32 mode
+bool gmb_tf32_enabled();
+int gmb_split_tf32(gmb_ctx* ctx, int rows, int cols, int ld, const double* src, int transpose, int ldo, float* hi, float* lo);
+int gmb_sgemm3_tf32(gmb_ctx* ctx, int M, int N, int K, const float* Ahi, const float* Alo, int lda, const float* Bhi, const float* Blo, int ldb,
+                    float* Cm, int ldc);
 
 // estep.cu
 int gmb_launch_xb(gmb_model* mdl, const double* d_beta, double* d_xb);

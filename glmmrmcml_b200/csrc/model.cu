@@ -112,6 +112,7 @@ extern "C" void gmb_model_destroy(gmb_model* mdl) {
     gmb_comp_free(mdl);
     gmb_lane_free(mdl);
     gmb_dfree(mdl->ctx, mdl->dzd32); gmb_dfree(mdl->ctx, mdl->dF32);
+    gmb_dfree(mdl->ctx, mdl->dZt_hi); gmb_dfree(mdl->ctx, mdl->dZt_lo); gmb_dfree(mdl->ctx, mdl->dU_hi); gmb_dfree(mdl->ctx, mdl->dU_lo);
     gmb_dfree(mdl->ctx, mdl->dU); gmb_dfree(mdl->ctx, mdl->dzd); gmb_dfree(mdl->ctx, mdl->dF); gmb_dfree(mdl->ctx, mdl->dZL); gmb_dfree(mdl->ctx, mdl->dL);
     gmb_dfree(mdl->ctx, mdl->dV); gmb_dfree(mdl->ctx, mdl->hmc_work);
     delete mdl;
@@ -190,6 +191,24 @@ int gmb_model_build_zd(gmb_model* mdl) {
             mdl->ctx->launches++;
         }
         GMB_CUDA(cudaGetLastError());
+    } else if (mdl->m_local > 0 && mdl->prec == 32 && gmb_tf32_enabled()) {
+        // dense Z in fp32 mode: tensor cores, tcgen05.mma kind::tf32 with the 3xTF32 split (gemm_tf32.cu)
+        gmb_ctx* ctx = mdl->ctx;
+        const int ldk = round_up(mdl->Q, 4);
+        if (!mdl->dZt_hi) {
+            GMB_CUDA(gmb_dmalloc(ctx, &mdl->dZt_hi, sizeof(float) * (size_t)mdl->n * ldk));
+            GMB_CUDA(gmb_dmalloc(ctx, &mdl->dZt_lo, sizeof(float) * (size_t)mdl->n * ldk));
+            GMB_TRY(gmb_split_tf32(ctx, mdl->n, mdl->Q, mdl->ldn, mdl->dZ, 1, ldk, mdl->dZt_hi, mdl->dZt_lo));
+        }
+        const size_t need = (size_t)mdl->m_local * ldk;
+        if (need > mdl->u32_cap) {
+            if (mdl->dU_hi) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, mdl->dU_hi); gmb_dfree(ctx, mdl->dU_lo); mdl->dU_hi = mdl->dU_lo = nullptr; }
+            GMB_CUDA(gmb_dmalloc(ctx, &mdl->dU_hi, sizeof(float) * need));
+            GMB_CUDA(gmb_dmalloc(ctx, &mdl->dU_lo, sizeof(float) * need));
+            mdl->u32_cap = need;
+        }
+        GMB_TRY(gmb_split_tf32(ctx, mdl->Q, mdl->m_local, mdl->ldq, mdl->dU, 0, ldk, mdl->dU_hi, mdl->dU_lo));
+        GMB_TRY(gmb_sgemm3_tf32(ctx, mdl->n, mdl->m_local, mdl->Q, mdl->dZt_hi, mdl->dZt_lo, ldk, mdl->dU_hi, mdl->dU_lo, ldk, mdl->dzd32, mdl->ldn));
     } else if (mdl->m_local > 0 && mdl->prec == 32) {
         // dense Z in fp32 mode: the fp64 DMMA product in column chunks through the context's scratch area, narrowed to float
         gmb_ctx* ctx = mdl->ctx;

@@ -186,6 +186,10 @@ int gmb_estep_set_rowstats(int on);
 /* zd = Z u: 1 (default) = gather through the sparse form of Z when Z is sparse (indicator designs) and Q >= 64, 0 = always the dense contraction. */
 int gmb_estep_set_sparse_zd(int on);
 
+/* fp32 mode with a dense Z: 1 (default) = zd = Z u on the tensor cores (tcgen05.mma kind::tf32, operands split 3xTF32, fp32 accumulation in
+ * tensor memory), 0 = the fp64 DMMA product narrowed to float. */
+int gmb_estep_set_tf32(int on);
+
 /* Batched binomial/logit evaluations (gmb_model_loglik_batch, batches of >= 8): 1 (default) = one launch for the whole batch, 8 parameter
  * vectors share each pass over the factor matrix; 0 = one launch per evaluation.  Both deterministic; they partition the sum differently, so
  * values agree to rounding (1e-13 relative), not bit for bit. */

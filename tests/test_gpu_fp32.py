@@ -64,3 +64,37 @@ def test_fp32_mode_rejects_what_it_does_not_implement(gctx):
     with pytest.raises(g.GmbError) as e:
         g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], "binomial", "probit", precision="fp32")
     assert e.value.code == 2
+
+
+@pytest.mark.parametrize("shape", [(700, 333, 500), (128, 64, 128), (130, 37, 259), (1500, 2049, 300)])
+def test_tcgen05_3xtf32_contraction_of_a_dense_z(gctx, oracle, shape):
+    """fp32 mode with a dense Z: zd = Z u runs on tcgen05.mma kind::tf32 with the 3xTF32 operand split, TMA staging and a TMEM accumulator
+    (gemm_tf32.cu).  The log-likelihood (a sum over all n x m entries of zd) and the MCNR sums agree with the fp64 oracle at the fp32 mode's
+    1e-5, with the same model run through the fp64 DMMA product narrowed to float, and plain TF32 would NOT (its 2^-11 operand rounding
+    gives ~1e-4): the split is doing its job.  Shapes cover partial tiles in M, N and K."""
+    import glmmrmcml_b200 as g
+    n, Q, m = shape
+    rng = np.random.default_rng(n + Q)
+    X = np.asfortranarray(np.column_stack([np.ones(n), rng.standard_normal(n)]))
+    Z = np.asfortranarray(rng.standard_normal((n, Q)) / np.sqrt(Q))
+    beta = np.array([0.3, -0.2])
+    U = np.asfortranarray(rng.standard_normal((Q, m)))
+    y = (rng.random(n) < 0.5).astype(float)
+    fl = oracle.flink("binomial", "logit")
+    want = oracle.loglik_faithful(X, Z, U, y, beta, 1.0, fl)
+    vals = {}
+    for on in (True, False):
+        g.estep_set_tf32(on)
+        try:
+            mdl = g.Model(gctx, X, Z, y, "binomial", "logit", precision="fp32")
+            mdl.set_u(U)
+            vals[on] = (mdl.log_likelihood(beta, 1.0), mdl.mcnr(beta, 1.0))
+            mdl.close()
+        finally:
+            g.estep_set_tf32(True)
+    for on in (True, False):
+        assert abs(vals[on][0] - want) <= TOL32 * abs(want), (on, vals[on][0], want)
+    ref = oracle.mcnr(X, Z, U, y, beta, 1.0, fl)
+    assert np.max(np.abs(vals[True][1]["xtwx"] - ref["xtwx"])) <= TOL32 * np.max(np.abs(ref["xtwx"]))
+    assert abs(vals[True][0] - vals[False][0]) <= 2e-6 * abs(want)
+    assert vals[True][0] != vals[False][0]                              # two different contractions
