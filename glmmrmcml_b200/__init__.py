@@ -227,6 +227,10 @@ class Model:
     def use_device_u(self, niter_total=0):
         check(lib().gmb_model_use_device_u(self._h, int(niter_total)))
 
+    def rebuild_zd(self):
+        """zd = Z u again from the device-resident samples (gmb_model_rebuild_zd; timing of the contraction without the upload)."""
+        check(lib().gmb_model_rebuild_zd(self._h))
+
     def get_u(self, col0=0, ncols=None):
         """Columns [col0, col0 + ncols) of this rank's device-resident sample matrix (gmb_model_get_u)."""
         if ncols is None:

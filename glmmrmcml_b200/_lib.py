@@ -57,6 +57,7 @@ PROTOTYPES = {
     "gmb_model_set_u": (C.c_int, [vp, dp, C.c_int, C.c_int, C.c_int, C.c_int]),
     "gmb_model_use_device_u": (C.c_int, [vp, C.c_int]),
     "gmb_model_get_u": (C.c_int, [vp, C.c_int, C.c_int, dp]),
+    "gmb_model_rebuild_zd": (C.c_int, [vp]),
     "gmb_model_loglik": (C.c_int, [vp, dp, C.c_double, dp]),
     "gmb_model_loglik_batch": (C.c_int, [vp, dp, dp, C.c_int, dp]),
     "gmb_model_mcnr": (C.c_int, [vp, dp, C.c_double, dp, dp, dp, dp]),

@@ -9,10 +9,11 @@
 // Kernel (one 128 x 128 output tile per CTA, 192 threads):
 //   warp 0, one thread   TMA producer: per k tile of 32 floats four boxes (A_hi, A_lo, B_hi, B_lo; 128 rows x 128 bytes each, 128-byte swizzle)
 //                        into a 3-stage ring, completion on the stage's `full` mbarrier
-//   warp 1               allocates 128 TMEM columns; one thread issues, per k tile, 4 k-steps x 3 tcgen05.mma (M 128, N 128, K 8) from shared-memory
-//                        descriptors and commits the stage's `empty` mbarrier (tcgen05.commit) — the accumulator never touches registers
-//   warps 2-5            epilogue: wait for the final commit, tcgen05.ld their 32-lane quadrant of the accumulator (32 columns at a time) and
-//                        store it as float into the column-major result
+//   warp 1               allocates 256 TMEM columns (two accumulators); one thread issues, per k tile, 4 k-steps x 3 tcgen05.mma (M 128, N 128, K 8) from
+//                        shared-memory descriptors and commits the stage's `empty` mbarrier (tcgen05.commit); after every 16 k tiles it commits the
+//                        accumulator's `full` mbarrier and switches to the other accumulator
+//   warps 2-5            epilogue: per chunk tcgen05.ld their 32-lane quadrant of the accumulator (32 columns at a time), add it to the thread's
+//                        row of fp32 sums, release the accumulator; finally store the row as float into the column-major result
 // Operands are K-major (k contiguous): B = u is stored that way (Q x m column-major); Z (n x Q column-major) is transposed by its split kernel.
 #include "common.cuh"
 #include "gemm_tma.cuh"
@@ -68,6 +69,12 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(gmbtma::smem_u32(bar)) : "memory");
 }
 
+// k tiles accumulated in TMEM before the partial sum is handed to the epilogue.  The tensor core accumulates in fp32 with truncation: the bias grows
+// linearly with the number of accumulation steps (measured: relative error of a log-likelihood 1.55e-9 K with one accumulator over the whole of K,
+// tools/tf32_error_sweep.py — 1.3e-5 at K = 8192, beyond the fp32 mode's tolerance).  Chunks of 512 are summed by the epilogue with rounded fp32
+// additions instead; two TMEM accumulators alternate so that the MMAs of the next chunk run while the epilogue drains the previous one.
+constexpr int KCHUNK_TILES = 16;
+
 __global__ void __launch_bounds__(192, 1) sgemm3_tf32_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__ CUtensorMap tmAl,
                                                             const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
                                                             int M, int N, int K, float* __restrict__ Cm, int ldc) {
@@ -75,18 +82,20 @@ __global__ void __launch_bounds__(192, 1) sgemm3_tf32_kernel(const __grid_consta
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)TST * STAGE_BYTES);
     uint64_t* empty = full + TST;
-    uint64_t* done = empty + TST;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    uint64_t* acc_full = empty + TST;                           // [2]: the chunk's MMAs are done
+    uint64_t* acc_empty = acc_full + 2;                         // [2]: the epilogue has drained the accumulator
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
     const int KT = (K + TK - 1) / TK;
+    const int NC = (KT + KCHUNK_TILES - 1) / KCHUNK_TILES;
     if (tid == 0) {
         for (int s = 0; s < TST; s++) { gmbtma::mbar_init(&full[s], 1); gmbtma::mbar_init(&empty[s], 1); }
-        gmbtma::mbar_init(done, 1);
+        for (int b = 0; b < 2; b++) { gmbtma::mbar_init(&acc_full[b], 1); gmbtma::mbar_init(&acc_empty[b], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {                                            // TMEM: 128 columns x 128 lanes of fp32 for the accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gmbtma::smem_u32(tmem_slot)), "r"(128) : "memory");
+    if (warp == 1) {                                            // TMEM: two accumulators of 128 columns x 128 lanes of fp32
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(gmbtma::smem_u32(tmem_slot)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -111,49 +120,66 @@ __global__ void __launch_bounds__(192, 1) sgemm3_tf32_kernel(const __grid_consta
         if (lane == 0) {
             // instruction descriptor: D fp32, A and B tf32, both K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-            for (int kt = 0; kt < KT; kt++) {
-                const int s = kt % TST;
-                gmbtma::mbar_wait(&full[s], (kt / TST) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = gmbtma::smem_u32(base + (size_t)s * STAGE_BYTES);
+            for (int c = 0; c < NC; c++) {
+                const int buf = c & 1;
+                if (c >= 2) { gmbtma::mbar_wait(&acc_empty[buf], ((c >> 1) - 1) & 1); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                const uint32_t tacc = tmem + (uint32_t)(buf * TN);
+                const int kt_end = min(KT, (c + 1) * KCHUNK_TILES);
+                for (int kt = c * KCHUNK_TILES; kt < kt_end; kt++) {
+                    const int s = kt % TST;
+                    gmbtma::mbar_wait(&full[s], (kt / TST) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = gmbtma::smem_u32(base + (size_t)s * STAGE_BYTES);
 #pragma unroll
-                for (int k8 = 0; k8 < TK / 8; k8++) {           // one instruction covers K = 8 tf32 = 32 bytes along the swizzled row
-                    const uint64_t ah = smem_desc(sa + k8 * 32), al = smem_desc(sa + OP_BYTES + k8 * 32);
-                    const uint64_t bh = smem_desc(sa + 2 * OP_BYTES + k8 * 32), bl = smem_desc(sa + 3 * OP_BYTES + k8 * 32);
-                    mma_tf32(tmem, ah, bh, idesc, (kt > 0 || k8 > 0) ? 1u : 0u);
-                    mma_tf32(tmem, ah, bl, idesc, 1u);
-                    mma_tf32(tmem, al, bh, idesc, 1u);
+                    for (int k8 = 0; k8 < TK / 8; k8++) {       // one instruction covers K = 8 tf32 = 32 bytes along the swizzled row
+                        const uint64_t ah = smem_desc(sa + k8 * 32), al = smem_desc(sa + OP_BYTES + k8 * 32);
+                        const uint64_t bh = smem_desc(sa + 2 * OP_BYTES + k8 * 32), bl = smem_desc(sa + 3 * OP_BYTES + k8 * 32);
+                        mma_tf32(tacc, ah, bh, idesc, (kt > c * KCHUNK_TILES || k8 > 0) ? 1u : 0u);
+                        mma_tf32(tacc, ah, bl, idesc, 1u);
+                        mma_tf32(tacc, al, bh, idesc, 1u);
+                    }
+                    mma_commit(&empty[s]);                      // arrives when the MMAs that read this stage are done
                 }
-                mma_commit(&empty[s]);                          // arrives when the MMAs that read this stage are done
+                mma_commit(&acc_full[buf]);
             }
-            mma_commit(done);
         }
     } else {
-        // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+        // epilogue warps 2..5: TMEM lane quadrant = warp % 4; the thread owns one row of the tile and sums the chunk results
         const int q = warp & 3;
-        gmbtma::mbar_wait(done, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int m = m0 + q * 32 + lane;
-#pragma unroll 1
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                           "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
-                           "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                         : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (m < M) {
+        float acc[TN];
 #pragma unroll
-                for (int j = 0; j < 32; j++) { const int n = n0 + c0 + j; if (n < N) Cm[(size_t)n * ldc + m] = __uint_as_float(v[j]); }
+        for (int j = 0; j < TN; j++) acc[j] = 0.f;
+        for (int c = 0; c < NC; c++) {
+            const int buf = c & 1;
+            gmbtma::mbar_wait(&acc_full[buf], (c >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c0 = 0; c0 < TN; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * TN + c0);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                               "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                               "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                             : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j++) acc[c0 + j] += __uint_as_float(v[j]);
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) gmbtma::mbar_arrive(&acc_empty[buf]);
+        }
+        if (m < M) {
+#pragma unroll
+            for (int j = 0; j < TN; j++) { const int n = n0 + j; if (n < N) Cm[(size_t)n * ldc + m] = acc[j]; }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256) : "memory");
 }
 
 int make_map_f32(CUtensorMap* tm, const float* ptr, int k_extent, int rows, int ldk) {

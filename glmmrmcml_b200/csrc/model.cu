@@ -279,6 +279,14 @@ extern "C" int gmb_model_use_device_u(gmb_model* mdl, int niter_total) {
     return GMB_OK;
 }
 
+// Re-forms zd = Z u (and the factor matrix) from the device-resident samples: what gmb_model_set_u does after its upload — exposed so that the
+// contraction can be timed without the host-to-device copy (benchmarks, profiles).
+extern "C" int gmb_model_rebuild_zd(gmb_model* mdl) {
+    if (!mdl || !mdl->dU || mdl->m_local <= 0) return gmb_set_error(GMB_ESTATE, "gmb_model_rebuild_zd: the model holds no samples");
+    GMB_CUDA(cudaSetDevice(mdl->ctx->device));
+    return gmb_model_build_zd(mdl);
+}
+
 extern "C" int gmb_model_get_u(gmb_model* mdl, int col0, int ncols, double* U_out) {
     if (!mdl || !U_out || col0 < 0 || ncols < 0) return gmb_set_error(GMB_EINVAL, "gmb_model_get_u: bad arguments");
     if (!mdl->dU || col0 + ncols > mdl->m_local) return gmb_set_error(GMB_ESTATE, "the model holds %d sample columns, asked for [%d, %d)", mdl->dU ? mdl->m_local : 0, col0, col0 + ncols);

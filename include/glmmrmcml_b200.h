@@ -90,6 +90,9 @@ int gmb_model_use_device_u(gmb_model* mdl, int niter_total);
  * uploaded or gmb_hmc_sample(..., keep_on_device) left behind) into U_out (Q x ncols, column-major). */
 int gmb_model_get_u(gmb_model* mdl, int col0, int ncols, double* U_out);
 
+/* Re-forms zd = Z u from the device-resident samples (the work gmb_model_set_u does after its upload); for timing the contraction alone. */
+int gmb_model_rebuild_zd(gmb_model* mdl);
+
 /* E-step objective, mcmlModel::log_likelihood mcmlmodel.h:284-304 after update_beta(beta) (:100-102):
  * mean_j sum_i l(y_i, (X beta)_i + zd_ij ; var_par).  All-reduced over ranks. */
 int gmb_model_loglik(gmb_model* mdl, const double* beta, double var_par, double* out);
