@@ -77,6 +77,8 @@ struct gmb_ctx {
     cudaEvent_t ev2 = nullptr, ev3 = nullptr;   // gmb_ctx_timer_start / _stop
     cudaStream_t stream2 = nullptr;             // high-priority side stream: panel factorisations running ahead of the trailing updates (cov_large.cu)
     cudaEvent_t evp = nullptr, evn = nullptr, evj = nullptr;   // panel-ready / narrow-update-done / join events of that look-ahead
+    cudaStream_t stream3 = nullptr;             // second high-priority stream: work of the panel chain that is off its critical path (block inverses)
+    cudaEvent_t evd[4] = {nullptr, nullptr, nullptr, nullptr}, evx = nullptr;   // diagonal-block-ready (per panel of an outer block) / inverse-ready
     void* d_flush = nullptr; int flush_val = 0; // gmb_ctx_flush_l2
 };
 
@@ -215,6 +217,9 @@ int gmb_dgemm(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double 
 int gmb_dgemm_tri(gmb_ctx* ctx, int transA, int transB, int M, int N, int K, double alpha, const double* A, int lda,
                   const double* B, int ldb, double beta, double* C, int ldc, int lower_a);
 int gmb_dsyrk_lower_sub(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc, int c0, int c1);   // C[:, c0:c1) -= P P^T, lower tiles
+int gmb_dsyrk_lower_rest(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc, int skip, int max_ctas);
+int gmb_dgemm_rtri(gmb_ctx* ctx, int M, int N, const double* A, int lda, const double* T, int ldt, double* C, int ldc);
+bool gmb_gemm_tma_available();
 int gmb_dgemm_rowpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias A
 int gmb_dgemm_colpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias B
 

@@ -44,6 +44,9 @@ extern "C" int gmb_ctx_create(int device, gmb_ctx** out) {
         GMB_CUDA(cudaEventCreateWithFlags(&ctx->evp, cudaEventDisableTiming));
         GMB_CUDA(cudaEventCreateWithFlags(&ctx->evn, cudaEventDisableTiming));
         GMB_CUDA(cudaEventCreateWithFlags(&ctx->evj, cudaEventDisableTiming));
+        GMB_CUDA(cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, hi));
+        for (int k = 0; k < 4; k++) GMB_CUDA(cudaEventCreateWithFlags(&ctx->evd[k], cudaEventDisableTiming));
+        GMB_CUDA(cudaEventCreateWithFlags(&ctx->evx, cudaEventDisableTiming));
     }
     GMB_CUDA(cudaEventCreate(&ctx->ev0));
     GMB_CUDA(cudaEventCreate(&ctx->ev1));
@@ -228,6 +231,9 @@ extern "C" void gmb_ctx_destroy(gmb_ctx* ctx) {
     if (ctx->evp) cudaEventDestroy(ctx->evp);
     if (ctx->evn) cudaEventDestroy(ctx->evn);
     if (ctx->evj) cudaEventDestroy(ctx->evj);
+    for (int k = 0; k < 4; k++) if (ctx->evd[k]) cudaEventDestroy(ctx->evd[k]);
+    if (ctx->evx) cudaEventDestroy(ctx->evx);
+    if (ctx->stream3) { cudaStreamSynchronize(ctx->stream3); cudaStreamDestroy(ctx->stream3); }
     if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

@@ -174,52 +174,101 @@ static int linv_buffer(gmb_cov* cv, int bi, double** out) {
     return GMB_OK;
 }
 
-// the panel chain of the outer block [K0, Kend): diagonal factor + inverse, panel solve, update inside the outer block
-static int chol_outer_block(gmb_ctx* ctx, double* A, int ld, int n, int K0, int Kend, int row_offset, int* d_status, double* linv) {
-    for (int k0 = K0; k0 < Kend; k0 += NB) {
+// the panel chain of the outer block [K0, Kend), confined to the block's own KB x KB diagonal part: per 128-column panel the diagonal factor +
+// inverse, the solve of the (at most 384) rows of the block below it and their rank-128 update (on the current stream).  With X != NULL also
+// the inverse of the whole KB x KB factor, block row by block row: X[j, 0:j] = -L_jj^-1 (L[j, 0:j] X[0:j, 0:j]), X[j, j] = L_jj^-1 (T: 128 x
+// KB scratch) — off the chain's critical path, on ctx->stream3 behind the event of panel j; ctx->evx is recorded when X is complete.
+static int chol_diag_chain(gmb_ctx* ctx, double* A, int ld, int K0, int Kend, int row_offset, int* d_status, double* linv, double* X, double* T) {
+    cudaStream_t S = ctx->stream, S3 = ctx->stream3;
+    for (int k0 = K0, j = 0; k0 < Kend; k0 += NB, j++) {
         const int kb = Kend - k0 < NB ? Kend - k0 : NB;
         double* Li = linv + (size_t)(k0 / NB) * NB * NB;
-        potrf_diag_kernel<<<1, 256, 0, ctx->stream>>>(A, ld, k0, kb, row_offset, d_status, Li);
+        potrf_diag_kernel<<<1, 256, 0, S>>>(A, ld, k0, kb, row_offset, d_status, Li);
         ctx->launches++;
-        const int rest = n - k0 - kb;
-        if (rest > 0) {
+        if (X) {
+            GMB_CUDA(cudaEventRecord(ctx->evd[j], S));
+            StreamSwap sw(ctx, S3);
+            GMB_CUDA(cudaStreamWaitEvent(S3, ctx->evd[j], 0));
+            const int j0 = k0 - K0;
+            GMB_CUDA(cudaMemcpy2DAsync(X + j0 + (size_t)j0 * NBO, sizeof(double) * NBO, Li, sizeof(double) * NB, sizeof(double) * NB, NB,
+                                       cudaMemcpyDeviceToDevice, S3));
+            if (j0 > 0) {
+                GMB_TRY(gmb_dgemm(ctx, 0, 0, NB, j0, j0, 1.0, A + k0 + (size_t)K0 * ld, ld, X, NBO, 0.0, T, NB));
+                GMB_TRY(gmb_dgemm(ctx, 0, 0, NB, j0, NB, -1.0, Li, NB, T, NB, 0.0, X + j0, NBO));
+            }
+        }
+        const int rows_in = Kend - (k0 + kb);
+        if (rows_in > 0) {
             double* Pp = A + (k0 + kb) + (size_t)k0 * ld;                       // panel solve P <- P L_kk^-T, in place
-            GMB_TRY(gmb_dgemm_rowpanel(ctx, rest, kb, kb, 1.0, Pp, ld, Li, NB, Pp, ld));
-            const int ncols_in = Kend - (k0 + kb);
-            if (ncols_in > 0)                                                   // A[k0+kb:n, k0+kb:Kend] -= P Ptop^T
-                GMB_TRY(gmb_dgemm(ctx, 0, 1, rest, ncols_in, kb, -1.0, Pp, ld, Pp, ld, 1.0, A + (k0 + kb) + (size_t)(k0 + kb) * ld, ld));
+            GMB_TRY(gmb_dgemm_rowpanel(ctx, rows_in, kb, kb, 1.0, Pp, ld, Li, NB, Pp, ld));
+            GMB_TRY(gmb_dgemm(ctx, 0, 1, rows_in, rows_in, kb, -1.0, Pp, ld, Pp, ld, 1.0, A + (k0 + kb) + (size_t)(k0 + kb) * ld, ld));
         }
     }
+    if (X) GMB_CUDA(cudaEventRecord(ctx->evx, S3));
     return GMB_OK;
 }
+
+static int g_chol_reserve = [] { const char* e = getenv("GMB_CHOL_RESERVE_SMS"); return e ? atoi(e) : 8; }();
 
 // in-place lower Cholesky of the n x n device matrix A (lower triangle read; the strict upper triangle of the 128 x 128 diagonal blocks is
 // zeroed, the rest of the upper triangle is left as scratch).  linv: ceil(n/128) * 128 * 128 doubles (inverted diagonal blocks), status:
 // first non-PD pivot + 1 + row_offset (0 if fine), d_logdet: sum of 2 log L_ii.  Work is issued on ctx->stream and ctx->stream2 and joined
 // back on ctx->stream before returning.
+//
+// Schedule per outer block K (512 columns), main stream M and high-priority side stream P:
+//   P: chain(K)   the block's 512 x 512 diagonal part only: 4 x (potrf_diag, solve and update of <= 384 rows) and the inverse X_K of the
+//                 512 x 512 factor — a chain of ~20 small dependent launches, but none of them touches more than 512 rows
+//   S3: the inverse X_K, block row j behind potrf_diag j of chain(K) (off the chain's critical path)
+//   M: solve(K)   W = A[below, K] X_K^T as a product over all rows below (tri = 4 skips the zero k tiles), out of place — the next outer
+//                 block's 512 rows first
+//   S3: copy W back into A (the factor's panel), under the update
+//   M: A[next diagonal block] -= W_top W_top^T (10 tiles), which releases chain(K + 1) on P
+//   M: rest of the trailing update, one PERSISTENT launch over all remaining lower tiles on (SMs - reserve) CTAs, so that chain(K + 1)
+//      always finds a free SM: the chain is hidden under the update as long as the update is the longer of the two.
 int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet) {
     cudaStream_t M = ctx->stream, P = ctx->stream2;
+    const int nouter = (n + NBO - 1) / NBO;
+    const bool tma = gmb_gemm_tma_available();
+    double *Wp = nullptr, *Xall = nullptr, *T = nullptr;
+    const int ldw = ld;
+    if (nouter > 1) {
+        if (!tma) return gmb_set_error(GMB_ECUDA, "the blocked Cholesky needs cuTensorMapEncodeTiled (TMA GEMM) for n > %d", NBO);
+        const size_t need = (size_t)ldw * NBO + (size_t)(nouter - 1) * NBO * NBO + (size_t)NB * NBO;
+        GMB_TRY(gmb_ctx_scratch(ctx, need));
+        Wp = ctx->d_scratch; Xall = Wp + (size_t)ldw * NBO; T = Xall + (size_t)(nouter - 1) * NBO * NBO;
+        GMB_CUDA(cudaMemsetAsync(Xall, 0, sizeof(double) * (size_t)(nouter - 1) * NBO * NBO, M));
+    }
+    int max_ctas = g_chol_reserve < 0 ? 0 : ctx->sms - g_chol_reserve;          // < 0: one CTA per tile (not persistent)
+    if (g_chol_reserve >= 0 && max_ctas < 1) max_ctas = 1;
     GMB_CUDA(cudaEventRecord(ctx->evn, M));                                     // everything issued so far (the block build) precedes the first panel
-    for (int K0 = 0; K0 < n; K0 += NBO) {
+    for (int K0 = 0, ko = 0; K0 < n; K0 += NBO, ko++) {
         const int Kend = K0 + NBO < n ? K0 + NBO : n, KB = Kend - K0;
-        {   // side stream: the panel chain of this outer block, once the narrow update of its columns is done
+        double* X = (Kend < n) ? Xall + (size_t)ko * NBO * NBO : nullptr;
+        {
             StreamSwap sw(ctx, P);
             GMB_CUDA(cudaStreamWaitEvent(P, ctx->evn, 0));
-            GMB_TRY(chol_outer_block(ctx, A, ld, n, K0, Kend, row_offset, d_status, linv));
+            GMB_TRY(chol_diag_chain(ctx, A, ld, K0, Kend, row_offset, d_status, linv, X, T));
             GMB_CUDA(cudaEventRecord(ctx->evp, P));
         }
         GMB_CUDA(cudaStreamWaitEvent(M, ctx->evp, 0));
         if (Kend >= n) break;
-        // main stream: rank-KB update of the trailing matrix by Pn = A[Kend:n, K0:Kend], block column by block column (lower trapezoid)
-        // (lower tile pairs only, one launch for all of them: equal work per CTA, no tile of the upper triangle)
-        {
-            const int Mt = n - Kend;
-            const double* Pn = A + Kend + (size_t)K0 * ld;
-            double* Ct = A + Kend + (size_t)Kend * ld;
-            GMB_TRY(gmb_dsyrk_lower_sub(ctx, Mt, KB, Pn, ld, Ct, ld, 0, NBO < Mt ? NBO : Mt));       // narrow part: the next outer block's columns
-            GMB_CUDA(cudaEventRecord(ctx->evn, M));                                                    // ... done: the next panel chain may start
-            if (Mt > NBO) GMB_TRY(gmb_dsyrk_lower_sub(ctx, Mt, KB, Pn, ld, Ct, ld, NBO, Mt));          // wide rest
-        }
+        const int Mt = n - Kend;
+        double* Pn = A + Kend + (size_t)K0 * ld;
+        double* Ct = A + Kend + (size_t)Kend * ld;
+        GMB_CUDA(cudaStreamWaitEvent(M, ctx->evx, 0));
+        const int nd = Mt < NBO ? Mt : NBO;
+        GMB_TRY(gmb_dgemm_rtri(ctx, nd, KB, Pn, ld, X, NBO, Wp, ldw));                          // solve(K), the next outer block's rows first
+        GMB_TRY(gmb_dsyrk_lower_sub(ctx, nd, KB, Wp, ldw, Ct, ld, 0, nd));                      // the next outer block's diagonal part
+        GMB_CUDA(cudaEventRecord(ctx->evn, M));
+        if (Mt > nd) GMB_TRY(gmb_dgemm_rtri(ctx, Mt - nd, KB, Pn + nd, ld, X, NBO, Wp + nd, ldw));
+        GMB_CUDA(cudaEventRecord(ctx->evj, M));
+        GMB_CUDA(cudaStreamWaitEvent(ctx->stream3, ctx->evj, 0));                               // the factor's panel goes back into A under the update
+        GMB_CUDA(cudaMemcpy2DAsync(Pn, sizeof(double) * ld, Wp, sizeof(double) * ldw, sizeof(double) * Mt, KB, cudaMemcpyDeviceToDevice, ctx->stream3));
+        if (Mt > nd) GMB_TRY(gmb_dsyrk_lower_rest(ctx, Mt, KB, Wp, ldw, Ct, ld, nd, max_ctas)); // everything else, under chain(K + 1)
+    }
+    if (nouter > 1) {                                                            // the last panel copy
+        GMB_CUDA(cudaEventRecord(ctx->evx, ctx->stream3));
+        GMB_CUDA(cudaStreamWaitEvent(M, ctx->evx, 0));
     }
     if (d_logdet) {
         logdet_diag_kernel<<<1, 256, 0, ctx->stream>>>(A, ld, n, d_logdet);

@@ -19,7 +19,8 @@ struct EpiAxpby {
     __device__ __forceinline__ void store(int m, int n, double acc) const {
         size_t o = (size_t)n * ldc + m;
         double r = alpha * acc;
-        if (beta != 0.0) r += beta * C[o];
+        if (beta == 1.0) { atomicAdd(C + o, r); return; }      // result unused: a RED (no load latency in the epilogue; one CTA owns the element,
+        if (beta != 0.0) r += beta * C[o];                     // so the sum is still a single deterministic addition)
         C[o] = r;
     }
     __device__ __forceinline__ double colterm(int, int, double) const { return 0.0; }
@@ -72,3 +73,16 @@ int gmb_dsyrk_lower_sub(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, d
     EpiAxpby epi{-1.0, 1.0, C, ldc};
     return gmbtma::dispatch_syrk_lower(ctx, M, K, Pm, ldp, epi, c0, c1);
 }
+// the same over ALL lower tiles except those of the leading skip x skip block (skip a multiple of 128), as one persistent launch on at most
+// max_ctas CTAs (0: one CTA per tile)
+int gmb_dsyrk_lower_rest(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc, int skip, int max_ctas) {
+    EpiAxpby epi{-1.0, 1.0, C, ldc};
+    return gmbtma::dispatch_syrk_lower(ctx, M, K, Pm, ldp, epi, 0, M, skip / 128, max_ctas);
+}
+// C (M x N) = A (M x K) * T^T for a lower-triangular N x N matrix T (K = N, column-major, zeros above the diagonal are NOT read):
+// the triangular solve X L^T = A as a product with T = L^-1
+int gmb_dgemm_rtri(gmb_ctx* ctx, int M, int N, const double* A, int lda, const double* T, int ldt, double* C, int ldc) {
+    EpiAxpby epi{1.0, 0.0, C, ldc};
+    return gmbtma::dispatch<false, false>(ctx, M, N, N, A, lda, T, ldt, epi, 4);
+}
+bool gmb_gemm_tma_available() { return gmbtma::gemm_tma_mode() != 0 && gmbtma::get_encode() != nullptr; }

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(THREADS) dgemm_kernel(int M, int N, int K, con
     // triangular operand (a Cholesky factor): tri = 1: op(A)(m, k) = 0 for k > m ; tri = 2: op(A)(m, k) = 0 for k < m (the factor read transposed).
     // The k tiles that hold only zeros for this row tile are skipped — the same sums without their zero terms.
     const int kt0 = (tri == 2) ? min(m0 / BK, KT) : 0;
-    const int kt1 = (tri == 1) ? min(KT, (m0 + BM + BK - 1) / BK) : KT;
+    const int kt1 = (tri == 1) ? min(KT, (m0 + BM + BK - 1) / BK) : (tri == 4) ? min(KT, (n0 + BN + BK - 1) / BK) : KT;   // tri = 4: B(n, k) = 0 for k > n
 
     {   // skip tiles whose columns are all inactive (chains that finished their trajectory)
         int act = 0;

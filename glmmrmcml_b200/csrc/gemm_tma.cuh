@@ -88,9 +88,11 @@ struct FragAddr {
 template <bool KCONT>
 __device__ __forceinline__ int frag_row(int t, int fr) { return KCONT ? 8 * t + rho_k(fr) : 16 * (t >> 1) + rho_mn(t & 1, fr); }
 
+constexpr int RASTER_GROUP = 16;
+
 template <bool A_KCONT, bool B_KCONT, class Epi>
 __global__ void __launch_bounds__(THREADS, 1) dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                               int M, int N, int K, Epi epi, int tri) {
+                                                               int M, int N, int K, Epi epi, int tri_arg, int ptiles) {
     constexpr int MT = 8, NT = 4;                          // warp tile 64 x 32: m8n8 fragment tiles per warp
     extern __shared__ unsigned char smraw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
@@ -100,34 +102,54 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_tma_kernel(const __grid_cons
     uint64_t* empty = full + STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int bx = (tri == 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, by = blockIdx.y;
-    if ((tri & 0xff) == 3) {                               // symmetric rank-k update, lower tile pairs only (see gemm_f64.cuh)
-        const int T = (M + BM - 1) / BM;
-        int rem = blockIdx.x, tj = tri >> 8;
-        while (rem >= T - tj) { rem -= T - tj; tj++; }
-        bx = tj + rem; by = tj;
-        tri = 0;
-    }
-    const int m0 = bx * BM, n0 = by * BN;
-    const int KT = (K + BK - 1) / BK;
-    const int kt0 = (tri == 2) ? min(m0 / BK, KT) : 0;
-    const int kt1 = (tri == 1) ? min(KT, (m0 + BM + BK - 1) / BK) : KT;
-
-    {   // skip tiles whose columns are all inactive (chains that finished their trajectory)
-        int act = 0;
-        for (int c = tid; c < BN; c += THREADS) if (n0 + c < N && epi.column_active(n0 + c)) act = 1;
-        if (!__syncthreads_or(act)) return;
-    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // ptiles > 0 (symmetric rank-k update only): PERSISTENT — gridDim.x CTAs walk the ptiles tile pairs with stride gridDim.x, the operand ring
+    // and its barrier phases running on across tiles (it_base).  The blocked Cholesky launches its trailing update on fewer CTAs than SMs so
+    // that the panel chain of the next outer block (high-priority side stream, tiny kernels) finds a free SM at once instead of waiting for a
+    // 128 x 128 x 512 tile (~70 us) to retire.
+    int it_base = 0;
+    for (int tile = blockIdx.x; ptiles == 0 || tile < ptiles; tile += gridDim.x) {
+    int tri = tri_arg;
+    int bx = (tri == 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, by = (tri == 4) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+    if (tri == 0 && gridDim.x > RASTER_GROUP) {
+        // grouped rasterisation: the CTAs resident at one time (one per SM, launched in linear order) cover RASTER_GROUP tile rows x ~9 tile
+        // columns instead of a full column of tiles x ~2, so a wave pulls (16 + 9) operand panels through L2 instead of (M/128 + 2): at
+        // 8192 x 16384 x 4096 the DRAM reads fall from 19x the algorithmic bytes (ncu, profiles/r02_ncu_gemm_dgemm_tma_ke.txt) to ~3x
+        const int pid = blockIdx.x + gridDim.x * blockIdx.y;
+        const int per_group = RASTER_GROUP * gridDim.y;
+        const int g = pid / per_group, first = g * RASTER_GROUP;
+        const int gm = min((int)gridDim.x - first, RASTER_GROUP);
+        const int r = pid - g * per_group;
+        bx = first + r % gm; by = r / gm;
+    }
+    if ((tri & 0xff) == 3) {                               // symmetric rank-k update, lower tile pairs only (see gemm_f64.cuh); tile column tj
+        const int T = (M + BM - 1) / BM;                   // holds the tile rows max(tj, rmin) .. T - 1
+        int rem = tile, tj = (tri >> 8) & 0xfff;
+        const int rmin = (tri >> 20) & 0xfff;
+        while (rem >= T - max(tj, rmin)) { rem -= T - max(tj, rmin); tj++; }
+        bx = max(tj, rmin) + rem; by = tj;
+        tri = 0;
+    }
+    const int m0 = bx * BM, n0 = by * BN;
+    const int KT = (K + BK - 1) / BK;
+    const int kt0 = (tri == 2) ? min(m0 / BK, KT) : 0;
+    // tri = 4: B is triangular, B(n, k) = 0 for k > n (the transposed inverse of a lower factor: a triangular solve as a product)
+    const int kt1 = (tri == 1) ? min(KT, (m0 + BM + BK - 1) / BK) : (tri == 4) ? min(KT, (n0 + BN + BK - 1) / BK) : KT;
+
+    if (ptiles == 0) {   // skip tiles whose columns are all inactive (chains that finished their trajectory)
+        int act = 0;
+        for (int c = tid; c < BN; c += THREADS) if (n0 + c < N && epi.column_active(n0 + c)) act = 1;
+        if (!__syncthreads_or(act)) return;
+    }
 
     // ---- producer: lane 0 of warp 0 feeds the ring, STAGES - 1 k tiles ahead of the arithmetic ----
     auto produce = [&](int kt) {
         constexpr uint32_t STAGE_BYTES = 2 * TILE_DOUBLES * sizeof(double);
-        const int it = kt - kt0, s = it % STAGES;
+        const int it = it_base + kt - kt0, s = it % STAGES;
         if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);      // all 8 warps have released the stage's previous tile
         mbar_expect_tx(&full[s], STAGE_BYTES);
         double* a = sA + s * TILE_DOUBLES;
@@ -158,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_tma_kernel(const __grid_cons
     FragAddr<B_KCONT> fb; fb.init(wn * 32, fr, fk);
 
     for (int kt = kt0; kt < kt1; kt++) {
-        const int it = kt - kt0, s = it % STAGES;
+        const int it = it_base + kt - kt0, s = it % STAGES;
         if (tid == 0 && kt + STAGES - 1 < kt1) produce(kt + STAGES - 1);
         __syncwarp();
         mbar_wait(&full[s], (it / STAGES) & 1);
@@ -220,6 +242,9 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_tma_kernel(const __grid_cons
             if (n < N) epi.colsum_out(bx, n, scol[c] + scol[BN + c]);
         }
     }
+    if (ptiles == 0) break;
+    it_base += max(kt1 - kt0, 0);
+    }   // tile loop
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -249,8 +274,11 @@ inline int make_map(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld
     return GMB_OK;
 }
 
+// lower tile pairs of the tile columns [c0, c1) of a T x T tile grid, tile column tj holding the tile rows max(tj, rmin) .. T - 1
+inline int syrk_tiles_rmin(int T, int c0, int c1, int rmin) { int c = 0; for (int tj = c0; tj < c1 && tj < T; tj++) c += T - (tj > rmin ? tj : rmin); return c; }
+
 template <bool AK, bool BKC, class Epi>
-int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi, int tri) {
+int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi, int tri, int max_ctas = 0) {
     CUtensorMap tmA, tmB;
     // contiguous dimension first: k for a K-contiguous operand (box 16 k x 128 rows), m / n otherwise (box 16 rows x BK k)
     if (AK) GMB_TRY(make_map(&tmA, A, K, M, lda, 16, 128)); else GMB_TRY(make_map(&tmA, A, M, K, lda, 16, BK));
@@ -262,8 +290,14 @@ int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const do
         configured = true;
     }
     dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-    if ((tri & 0xff) == 3) grid = dim3(gmbgemm::syrk_tiles((M + BM - 1) / BM, tri >> 8, (N + BN - 1) / BN), 1);
-    kern<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, M, N, K, epi, tri);
+    int ptiles = 0;
+    if ((tri & 0xff) == 3) {
+        const int tiles = syrk_tiles_rmin((M + BM - 1) / BM, (tri >> 8) & 0xfff, (N + BN - 1) / BN, (tri >> 20) & 0xfff);
+        if (tiles <= 0) return GMB_OK;
+        grid = dim3(tiles, 1);
+        if (max_ctas > 0) { ptiles = tiles; grid = dim3(tiles < max_ctas ? tiles : max_ctas, 1); }
+    }
+    kern<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, M, N, K, epi, tri, ptiles);
     ctx->launches++;
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;
@@ -290,13 +324,15 @@ int dispatch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const 
     if (M <= 0 || N <= 0) return GMB_OK;
     if (((uintptr_t)A & 15) || ((uintptr_t)B & 15) || (lda & 1) || (ldb & 1))
         return gmb_set_error(GMB_EINVAL, "dgemm: operands must be 16-byte aligned with even leading dimensions");
-    if (use_tma(ctx, M, N, K)) return launch<AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
+    // tri = 4 (a triangular solve as a product, the Cholesky's panel step): unequal tiles, heaviest first — worth the big tiles from half a wave on
+    const bool tri4_tma = tri == 4 && gemm_tma_mode() != 0 && get_encode() && K >= 64 && 2L * ((M + BM - 1) / BM) * ((N + BN - 1) / BN) >= ctx->sms;
+    if (use_tma(ctx, M, N, K) || tri4_tma) return launch<AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
     return gmbgemm::launch<64, 64, 2, 4, AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
 }
 
 // C[:, c0:c1) (lower tiles) = epi(P P^T) for the M x K matrix P (m contiguous): column range in elements, multiples of 128
 template <class Epi>
-int dispatch_syrk_lower(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, const Epi& epi, int c0, int c1) {
+int dispatch_syrk_lower(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, const Epi& epi, int c0, int c1, int rmin_tiles = 0, int max_ctas = 0) {
     if (M <= 0 || c1 <= c0) return GMB_OK;
     if (((uintptr_t)Pm & 15) || (ldp & 1)) return gmb_set_error(GMB_EINVAL, "dsyrk: operand must be 16-byte aligned with an even leading dimension");
     if ((c0 % 128) || (c1 % 128 && c1 < M)) return gmb_set_error(GMB_EINVAL, "dsyrk: the column range must be made of whole 128-column tiles");
@@ -304,7 +340,10 @@ int dispatch_syrk_lower(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, c
     const long tiles = gmbgemm::syrk_tiles((M + 127) / 128, c0 / 128, (N + 127) / 128);
     const long rounds = (tiles + ctx->sms - 1) / ctx->sms;
     const bool tma = gemm_tma_mode() != 0 && get_encode() && K >= 64 && (gemm_tma_mode() == 2 || tiles >= 6L * ctx->sms || (double)tiles >= 0.9 * (double)(rounds * ctx->sms));
-    if (tma) return launch<false, false, Epi>(ctx, M, N, K, Pm, ldp, Pm, ldp, epi, 3 | ((c0 / 128) << 8));
+    if (tma || rmin_tiles > 0 || max_ctas > 0) {
+        if (!get_encode()) return gmb_set_error(GMB_ECUDA, "dsyrk: the persistent update needs the TMA kernel");
+        return launch<false, false, Epi>(ctx, M, N, K, Pm, ldp, Pm, ldp, epi, 3 | ((c0 / 128) << 8) | (rmin_tiles << 20), max_ctas);
+    }
     return gmbgemm::launch<64, 64, 2, 4, false, false, Epi>(ctx, M, N, K, Pm, ldp, Pm, ldp, epi, 3 | ((c0 / 64) << 8));
 }
 
