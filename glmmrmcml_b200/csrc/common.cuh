@@ -220,6 +220,9 @@ int gmb_dsyrk_lower_sub(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, d
 int gmb_dsyrk_lower_rest(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc, int skip, int max_ctas);
 int gmb_dgemm_rtri(gmb_ctx* ctx, int M, int N, const double* A, int lda, const double* T, int ldt, double* C, int ldc);
 bool gmb_gemm_tma_available();
+int gmb_dgemm_rowpanel_small(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);
+int gmb_dgemm_nt_small(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc);
+int gmb_dsyrk_lower_small(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc);
 int gmb_dgemm_rowpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias A
 int gmb_dgemm_colpanel(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc);   // C may alias B
 

@@ -42,10 +42,108 @@ __global__ void build_block_kernel(CovBlock b, const CovFn* __restrict__ fns, co
 // The panel solve of the factorisation and the diagonal solves of the forward substitution then run as DMMA GEMMs with the inverse instead of
 // one serial recurrence per row.  Rows / columns >= kb are padded with the identity.  A: the lower triangle is read; L is written to the lower
 // triangle, the strict upper triangle of the block is zeroed.  Linv: 128 x 128 column-major, zero outside the kb x kb lower triangle.
+__device__ __forceinline__ unsigned pd_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pd_bar_arrive(uint64_t* bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(pd_smem(bar)) : "memory"); }
+__device__ __forceinline__ void pd_bar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok = 0;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(pd_smem(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// One elimination step j = 16 JQ + js.  JQN = slot of column / row j + 1 (JQ, or JQ + 1 when js = 15).  The entries of column j + 1 of A and
+// of row j + 1 of B are updated FIRST and published for step j + 1 (one mbarrier arrival per warp); the rest of the rank-1 update follows, off
+// the critical path: while it runs, the next pivot's rsqrt is already under way in the warps that are done.
+template <int JQ, int JQN>
+__device__ __forceinline__ bool potrf_step(int js, int tx, int ty, int lane, double (&a)[8][8], double (&bm)[8][8],
+                                           double (*colbuf)[NB], double (*rowbuf)[NB], uint64_t* bars, int* status, int pivot_id) {
+    const int j = 16 * JQ + js;
+    pd_bar_wait(&bars[j & 1], (j >> 1) & 1);
+    const double* cb = colbuf[j & 1];
+    const double* rb = rowbuf[j & 1];
+    const double d = cb[j];
+    if (!(d > 0.0)) { if (threadIdx.x == 0) atomicCAS(status, 0, pivot_id + j + 1); return false; }    // uniform: every thread reads the same pivot
+    const double inv = rsqrt(d);
+    double lr[8], lc[8], xc[8];
+#pragma unroll
+    for (int i = JQ; i < 8; i++) { lr[i] = cb[tx + 16 * i] * inv; lc[i] = cb[ty + 16 * i] * inv; }
+#pragma unroll
+    for (int jj = 0; jj <= JQ; jj++) xc[jj] = rb[ty + 16 * jj] * inv;
+    // rows r > j of slot i, columns c > j of slot jj
+#define PD_ROK(i) (((i) > JQ) || (tx > js))
+#define PD_COK(jj) (((jj) > JQ) || (ty > js))
+    if (JQN < 8) {
+        // ---- priority: column slot JQN of A (all its rows), row slot JQN of B ----
+#pragma unroll
+        for (int i = JQN; i < 8; i++)
+            if (PD_ROK(i) && PD_COK(JQN)) a[i][JQN] = fma(-lr[i], lc[JQN], a[i][JQN]);
+        if (PD_ROK(JQN)) {
+#pragma unroll
+            for (int jj = 0; jj <= JQ; jj++) bm[JQN][jj] = fma(-lr[JQN], xc[jj], bm[JQN][jj]);
+        }
+        const int jn = j + 1, jsn = jn & 15;
+        double* cbn = colbuf[jn & 1];
+        double* rbn = rowbuf[jn & 1];
+        if (ty == jsn) {                          // owners of column j + 1 of A: rows r >= j + 1 live in slots i >= JQN
+#pragma unroll
+            for (int i = JQN; i < 8; i++) cbn[tx + 16 * i] = a[i][JQN];
+        }
+        if (tx == jsn) {                          // owners of row j + 1 of B: columns c <= j + 1 live in slots jj <= JQN
+#pragma unroll
+            for (int jj = 0; jj <= JQN; jj++) rbn[ty + 16 * jj] = bm[JQN][jj];
+        }
+        __syncwarp();
+        if (lane == 0) pd_bar_arrive(&bars[jn & 1]);
+    }
+    // ---- the rest of the rank-1 update ----
+#pragma unroll
+    for (int i = JQ; i < 8; i++) {
+        if (PD_ROK(i)) {
+#pragma unroll
+            for (int jj = JQ; jj <= i; jj++)               // A: columns c > j of the lower triangle
+                if (jj != JQN && PD_COK(jj)) a[i][jj] = fma(-lr[i], lc[jj], a[i][jj]);
+            if (i != JQN) {
+#pragma unroll
+                for (int jj = 0; jj <= JQ; jj++)           // B: columns c <= j (entries right of the diagonal of row j are zero)
+                    bm[i][jj] = fma(-lr[i], xc[jj], bm[i][jj]);
+            }
+        }
+    }
+#undef PD_ROK
+#undef PD_COK
+    if (ty == js) {                               // column j of L
+#pragma unroll
+        for (int i = JQ; i < 8; i++) {
+            if (i > JQ || tx > js) a[i][JQ] = lr[i];
+            else if (tx == js) a[i][JQ] = d * inv;
+        }
+    }
+    if (tx == js) {                               // row j of L^-1
+#pragma unroll
+        for (int jj = 0; jj <= JQ; jj++) bm[JQ][jj] = xc[jj];
+    }
+    return true;
+}
+
+template <int JQ>
+__device__ __forceinline__ bool potrf_phase(int tx, int ty, int lane, double (&a)[8][8], double (&bm)[8][8], double (*colbuf)[NB], double (*rowbuf)[NB],
+                                            uint64_t* bars, int* status, int pivot_id) {
+#pragma unroll 1
+    for (int js = 0; js < 15; js++)
+        if (!potrf_step<JQ, JQ>(js, tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id)) return false;
+    return potrf_step<JQ, JQ + 1>(15, tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+}
+
 __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A, int ld, int k0, int kb, int row_offset, int* __restrict__ status,
                                                          double* __restrict__ Linv) {
     __shared__ double colbuf[2][NB], rowbuf[2][NB];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    __shared__ uint64_t bars[2];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pd_smem(&bars[0])), "r"(8));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pd_smem(&bars[1])), "r"(8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     double a[8][8], bm[8][8];                     // only the entries with i >= jj are ever touched (the others are never materialised)
 #pragma unroll
     for (int jj = 0; jj < 8; jj++)
@@ -57,54 +155,24 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
             a[i][jj] = v;
             bm[i][jj] = (r == c) ? 1.0 : 0.0;
         }
+    __syncthreads();                              // barriers initialised
+    if (ty == 0) {                                // column 0 of A, row 0 of B for step 0
 #pragma unroll
-    for (int jq = 0; jq < 8; jq++) {
-        for (int js = 0; js < 16; js++) {
-            const int j = 16 * jq + js;
-            double* cb = colbuf[j & 1];
-            double* rb = rowbuf[j & 1];
-            if (ty == js) {                       // owners of column j of A: rows r >= j live in slots i >= jq
-#pragma unroll
-                for (int i = jq; i < 8; i++) cb[tx + 16 * i] = a[i][jq];
-            }
-            if (tx == js) {                       // owners of row j of B: columns c <= j live in slots jj <= jq
-#pragma unroll
-                for (int jj = 0; jj <= jq; jj++) rb[ty + 16 * jj] = bm[jq][jj];
-            }
-            __syncthreads();
-            const double d = cb[j];
-            if (!(d > 0.0)) { if (tid == 0) atomicCAS(status, 0, row_offset + k0 + j + 1); return; }    // uniform: every thread reads the same pivot
-            const double inv = rsqrt(d);
-            double lr[8], lc[8], xc[8];
-#pragma unroll
-            for (int i = jq; i < 8; i++) { lr[i] = cb[tx + 16 * i] * inv; lc[i] = cb[ty + 16 * i] * inv; }
-#pragma unroll
-            for (int jj = 0; jj <= jq; jj++) xc[jj] = rb[ty + 16 * jj] * inv;
-#pragma unroll
-            for (int i = jq; i < 8; i++) {
-                const bool rok = (i > jq) || (tx > js);           // r > j
-                if (rok) {
-#pragma unroll
-                    for (int jj = jq; jj <= i; jj++)               // A: columns c > j of the lower triangle
-                        if ((jj > jq) || (ty > js)) a[i][jj] = fma(-lr[i], lc[jj], a[i][jj]);
-#pragma unroll
-                    for (int jj = 0; jj <= jq; jj++)               // B: columns c <= j (entries right of the diagonal of row j are zero)
-                        bm[i][jj] = fma(-lr[i], xc[jj], bm[i][jj]);
-                }
-            }
-            if (ty == js) {                       // column j of L
-#pragma unroll
-                for (int i = jq; i < 8; i++) {
-                    if (i > jq || tx > js) a[i][jq] = lr[i];
-                    else if (tx == js) a[i][jq] = d * inv;
-                }
-            }
-            if (tx == js) {                       // row j of L^-1
-#pragma unroll
-                for (int jj = 0; jj <= jq; jj++) bm[jq][jj] = xc[jj];
-            }
-        }
+        for (int i = 0; i < 8; i++) colbuf[0][tx + 16 * i] = a[i][0];
     }
+    if (tx == 0) rowbuf[0][ty] = bm[0][0];
+    __syncwarp();
+    if (lane == 0) pd_bar_arrive(&bars[0]);
+    const int pivot_id = row_offset + k0;
+    bool ok = potrf_phase<0>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase<1>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase<2>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase<3>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase<4>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase<5>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase<6>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase<7>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    if (!ok) return;
 #pragma unroll
     for (int jj = 0; jj < 8; jj++)
 #pragma unroll
@@ -200,8 +268,8 @@ static int chol_diag_chain(gmb_ctx* ctx, double* A, int ld, int K0, int Kend, in
         const int rows_in = Kend - (k0 + kb);
         if (rows_in > 0) {
             double* Pp = A + (k0 + kb) + (size_t)k0 * ld;                       // panel solve P <- P L_kk^-T, in place
-            GMB_TRY(gmb_dgemm_rowpanel(ctx, rows_in, kb, kb, 1.0, Pp, ld, Li, NB, Pp, ld));
-            GMB_TRY(gmb_dgemm(ctx, 0, 1, rows_in, rows_in, kb, -1.0, Pp, ld, Pp, ld, 1.0, A + (k0 + kb) + (size_t)(k0 + kb) * ld, ld));
+            GMB_TRY(gmb_dgemm_rowpanel_small(ctx, rows_in, kb, kb, 1.0, Pp, ld, Li, NB, Pp, ld));
+            GMB_TRY(gmb_dsyrk_lower_small(ctx, rows_in, kb, Pp, ld, A + (k0 + kb) + (size_t)(k0 + kb) * ld, ld));
         }
     }
     if (X) GMB_CUDA(cudaEventRecord(ctx->evx, S3));
@@ -258,7 +326,7 @@ int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int
         GMB_CUDA(cudaStreamWaitEvent(M, ctx->evx, 0));
         const int nd = Mt < NBO ? Mt : NBO;
         GMB_TRY(gmb_dgemm_rtri(ctx, nd, KB, Pn, ld, X, NBO, Wp, ldw));                          // solve(K), the next outer block's rows first
-        GMB_TRY(gmb_dsyrk_lower_sub(ctx, nd, KB, Wp, ldw, Ct, ld, 0, nd));                      // the next outer block's diagonal part
+        GMB_TRY(gmb_dsyrk_lower_small(ctx, nd, KB, Wp, ldw, Ct, ld));                           // the next outer block's diagonal part
         GMB_CUDA(cudaEventRecord(ctx->evn, M));
         if (Mt > nd) GMB_TRY(gmb_dgemm_rtri(ctx, Mt - nd, KB, Pn + nd, ld, X, NBO, Wp + nd, ldw));
         GMB_CUDA(cudaEventRecord(ctx->evj, M));

@@ -85,4 +85,23 @@ int gmb_dgemm_rtri(gmb_ctx* ctx, int M, int N, const double* A, int lda, const d
     EpiAxpby epi{1.0, 0.0, C, ldc};
     return gmbtma::dispatch<false, false>(ctx, M, N, N, A, lda, T, ldt, epi, 4);
 }
+// Small members of the Cholesky panel chain (at most 512 rows): tiles of 16 x 128 / 32 x 32 instead of 64 x 128 / 64 x 64, so that a
+// 384 x 128 x 128 product runs on 24-144 SMs for ~3 us instead of on 6-36 SMs for ~15 us — these launches are the chain's critical path.
+int gmb_dgemm_rowpanel_small(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double* C, int ldc) {
+    if (N > 128 || M <= 0) return M <= 0 ? GMB_OK : gmb_set_error(GMB_EINVAL, "gmb_dgemm_rowpanel_small: N must be <= 128");
+    EpiAxpby epi{alpha, 0.0, C, ldc};
+    return gmbgemm::launch<16, 128, 1, 8, false, false, EpiAxpby>(ctx, M, N, K, A, lda, B, ldb, epi, 0);
+}
+// C (M x N) = alpha A B^T + beta C, A: M x K and B: N x K, both m / n contiguous
+int gmb_dgemm_nt_small(gmb_ctx* ctx, int M, int N, int K, double alpha, const double* A, int lda, const double* B, int ldb, double beta, double* C, int ldc) {
+    if (M <= 0 || N <= 0) return GMB_OK;
+    EpiAxpby epi{alpha, beta, C, ldc};
+    return gmbgemm::launch<32, 32, 2, 4, false, false, EpiAxpby>(ctx, M, N, K, A, lda, B, ldb, epi, 0);
+}
+// C -= P P^T on the lower 32 x 32 tiles of the M x M matrix C (M <= 512 or so)
+int gmb_dsyrk_lower_small(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc) {
+    if (M <= 0) return GMB_OK;
+    EpiAxpby epi{-1.0, 1.0, C, ldc};
+    return gmbgemm::launch<32, 32, 2, 4, false, false, EpiAxpby>(ctx, M, M, K, Pm, ldp, Pm, ldp, epi, 3);
+}
 bool gmb_gemm_tma_available() { return gmbtma::gemm_tma_mode() != 0 && gmbtma::get_encode() != nullptr; }
