@@ -84,6 +84,16 @@ def cov_set_gram(on: bool):
     check(lib().gmb_cov_set_gram(int(bool(on))))
 
 
+def estep_set_row_aggregation(on: bool):
+    """E-step: True (default) = run on the distinct rows of [X | Z] when at most a quarter of the rows are distinct; False = every row."""
+    check(lib().gmb_estep_set_row_aggregation(int(bool(on))))
+
+
+def cov_set_block_classes(on: bool):
+    """Gram-matrix mvn_ll: True (default) = identical covariance blocks are factorised once per class; False = once per block."""
+    check(lib().gmb_cov_set_block_classes(int(bool(on))))
+
+
 def hmc_set_row_aggregation(on: bool):
     """On-chip sampler: True (default) = aggregate observations that share their row of [X | Z]; False = one row per observation."""
     check(lib().gmb_hmc_set_row_aggregation(int(bool(on))))
@@ -231,6 +241,12 @@ class Model:
         """zd = Z u again from the device-resident samples (gmb_model_rebuild_zd; timing of the contraction without the upload)."""
         check(lib().gmb_model_rebuild_zd(self._h))
 
+    def estep_rows(self) -> int:
+        """Rows of the zd matrix the model holds: n, or the number of distinct rows of [X | Z] when the E-step runs aggregated."""
+        r = C.c_int()
+        check(lib().gmb_model_estep_rows(self._h, C.byref(r)))
+        return r.value
+
     def get_u(self, col0=0, ncols=None):
         """Columns [col0, col0 + ncols) of this rank's device-resident sample matrix (gmb_model_get_u)."""
         if ncols is None:
@@ -301,6 +317,9 @@ class Covariance:
         B, Q, R = C.c_int(), C.c_int(), C.c_int()
         check(lib().gmb_cov_dims(self._h, C.byref(B), C.byref(Q), C.byref(R)))
         self.B, self.Q, self.R = B.value, Q.value, R.value
+        nc = C.c_int()
+        check(lib().gmb_cov_block_classes(self._h, C.byref(nc)))
+        self.block_classes = nc.value        # distinct blocks (size, functions, data): one factorisation each on the Gram path
 
     def close(self):
         if self._h:

@@ -64,7 +64,8 @@ void gmb_agg_free(gmb_model* mdl) {
     gmb_agg& a = mdl->agg;
     gmb_ctx* ctx = mdl->ctx;
     if (a.built && a.active) { gmb_dfree(ctx, a.dX); gmb_dfree(ctx, a.dZ); gmb_dfree(ctx, a.dZL); gmb_dfree(ctx, a.dxb); }
-    gmb_dfree(ctx, a.dvec);
+    gmb_dfree(ctx, a.dvec); gmb_dfree(ctx, a.dgid); gmb_dfree(ctx, a.drep);
+    mdl->eagg = false;
     a = gmb_agg();
 }
 
@@ -73,6 +74,7 @@ void gmb_agg_free(gmb_model* mdl) {
 int gmb_agg_ensure(gmb_model* mdl) {
     gmb_agg& a = mdl->agg;
     if (a.built && a.flag == gmb_agg_enabled()) return GMB_OK;
+    const bool rebuild_zd = a.built && mdl->eagg && mdl->zd_valid;   // the E-step's zd lives on the view that is about to change
     if (a.built) gmb_agg_free(mdl);
     gmb_sparse_invalidate(mdl);                      // the sparse forms describe the view
     a.flag = gmb_agg_enabled();
@@ -136,7 +138,8 @@ int gmb_agg_ensure(gmb_model* mdl) {
                 ctx->launches += 2;
                 GMB_CUDA(cudaStreamSynchronize(ctx->stream));
             }
-            gmb_dfree(ctx, d_gid); gmb_dfree(ctx, d_rep); gmb_dfree(ctx, d_bad);
+            if (want) { a.dgid = d_gid; a.drep = d_rep; } else { gmb_dfree(ctx, d_gid); gmb_dfree(ctx, d_rep); }
+            gmb_dfree(ctx, d_bad);
         }
     } else {
         GMB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -148,8 +151,8 @@ int gmb_agg_ensure(gmb_model* mdl) {
     a.active = want;
     // per-row weights and response sums, accumulated in row order on the host (deterministic)
     const int ng = a.ng, ldg = a.ldn;
-    std::vector<double> hv((size_t)6 * ldg, 0.0);
-    double *cnt = hv.data(), *ys = cnt + ldg, *lcnt = ys + ldg, *lys = lcnt + ldg, *lsq = lys + ldg, *lrc = lsq + ldg;
+    std::vector<double> hv((size_t)8 * ldg, 0.0);
+    double *cnt = hv.data(), *ys = cnt + ldg, *lcnt = ys + ldg, *lys = lcnt + ldg, *lsq = lys + ldg, *lrc = lsq + ldg, *eys = lrc + ldg, *ess = eys + ldg;
     std::vector<double> ysum(ng, 0.0);
     for (int i = 0; i < n; i++) { cnt[gid[i]] += 1.0; ysum[gid[i]] += y[i]; lrc[gid[i]] += rowc[i]; }
     for (int i = 0; i < n; i++) {                      // log-likelihood weights
@@ -164,13 +167,22 @@ int gmb_agg_ensure(gmb_model* mdl) {
         if (fl == 7) lys[g] = ysum[g] / cnt[g];                                                   // group mean
     }
     if (fl == 7) for (int i = 0; i < n; i++) { const double d = y[i] - lys[gid[i]]; lsq[gid[i]] += d * d; }   // within-group sum of squares
+    a.binary_ok = true;
+    for (int g = 0; g < ng; g++) eys[g] = ysum[g];
+    for (int i = 0; i < n; i++) {
+        const int g = gid[i];
+        const double d = y[i] - ysum[g] / cnt[g];
+        ess[g] += d * d;
+        if (fl == 3 && !(y[i] == 0.0 || y[i] == 1.0)) a.binary_ok = false;
+    }
     GMB_CUDA(gmb_dmalloc(ctx, &a.dvec, sizeof(double) * hv.size()));
     GMB_CUDA(cudaMemcpyAsync(a.dvec, hv.data(), sizeof(double) * hv.size(), cudaMemcpyHostToDevice, ctx->stream));
     GMB_CUDA(cudaStreamSynchronize(ctx->stream));
     a.dcnt = a.dvec; a.dys = a.dvec + ldg; a.dlcnt = a.dvec + 2 * (size_t)ldg; a.dlys = a.dvec + 3 * (size_t)ldg;
-    a.dlsq = a.dvec + 4 * (size_t)ldg; a.dlrc = a.dvec + 5 * (size_t)ldg;
+    a.dlsq = a.dvec + 4 * (size_t)ldg; a.dlrc = a.dvec + 5 * (size_t)ldg; a.deys = a.dvec + 6 * (size_t)ldg; a.dess = a.dvec + 7 * (size_t)ldg;
     if (!a.active) { a.dX = mdl->dX; a.dZ = mdl->dZ; a.dZL = nullptr; a.dxb = nullptr; }          // aliases: resolved by the accessors below
     a.built = true;
+    if (rebuild_zd) GMB_TRY(gmb_model_build_zd(mdl));
     return GMB_OK;
 }
 

@@ -100,6 +100,11 @@ struct gmb_agg {
     double* dvec = nullptr;      // 6 x ldn: the arrays below
     double *dcnt = nullptr, *dys = nullptr;                               // residual: observations per row, response term
     double *dlcnt = nullptr, *dlys = nullptr, *dlsq = nullptr, *dlrc = nullptr;   // log-likelihood: count, response sum / mean, within-row SS, sum of lf(y)
+    // E-step on the aggregated rows (estep.cu: *_agg kernels): response sum, within-row sum of squares about the row mean (every family),
+    // row of each observation / representative observation of each row; binary_ok: every response of a binomial model is 0 or 1
+    double *deys = nullptr, *dess = nullptr;
+    int *dgid = nullptr, *drep = nullptr;
+    bool binary_ok = true;
 };
 
 // sparse form of the sampler's Z L view (hmc_sparse.cu): row-wise and column-wise ELL, entry w of row i at [w * ngp + i]
@@ -167,6 +172,7 @@ struct gmb_model {
     double* dV = nullptr;        // whitened samples of the last gmb_hmc_sample, ldq x v_cap
     size_t v_cap = 0;
     gmb_agg agg;                 // row aggregation for the on-chip sampler
+    bool eagg = false;           // zd (and the E-step kernels) run on the agg.ng distinct rows of [X | Z], leading dimension agg.ldn (model.cu)
     gmb_ell ell;                 // sparse form of the view's Z L (structure-aware sampler)
     gmb_comp comp;               // its connected components (large sparse models)
     gmb_lane lane;               // ... and (small block-structured models)
@@ -206,6 +212,11 @@ struct gmb_cov {
     // Gram matrices of a model's samples (cov.cu: cov_ensure_gram), laid out like d_Lblk
     double* d_batch = nullptr; size_t batch_bytes = 0;     // work area of gmb_cov_mvn_ll_model_batch
     double* d_gram = nullptr; const gmb_model* gram_model = nullptr; unsigned long long gram_version = 0; int gram_cols = 0;
+    // classes of IDENTICAL blocks (same size, function rows and data: gr(cl)*ar1(t) repeats one block per cluster): the Gram
+    // path builds and factorises one block per class on the class's summed Gram matrix
+    int ncls = 0;
+    int *d_cls_rep = nullptr, *d_cls_ptr = nullptr, *d_cls_mem = nullptr;   // representative block / CSR member lists
+    double* d_gram_cls = nullptr;                                           // class sums, stored at the representative's l0
 };
 
 // ------------------------------------------------------------------------------------------------

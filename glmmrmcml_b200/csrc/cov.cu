@@ -9,6 +9,8 @@
 // factorised once per theta; the per-sample work is only the forward substitution, which for small blocks is an
 // HBM stream of u (8 Q m bytes) and for large blocks a blocked TRSM on the DMMA GEMM.
 #include "common.cuh"
+#include <map>
+#include <string>
 #include <algorithm>
 
 namespace {
@@ -215,6 +217,20 @@ __global__ void gram_reduce_kernel(long long gram_doubles, int nchunks, const do
     gram[e] = s;
 }
 
+// class sums of the Gram matrices: element e of class c = sum over the member blocks in list order (deterministic)
+__global__ void gram_class_kernel(int ncls, const CovBlock* __restrict__ blocks, const int* __restrict__ rep, const int* __restrict__ ptr,
+                                  const int* __restrict__ mem, const double* __restrict__ gram, double* __restrict__ gram_cls) {
+    const int c = blockIdx.x;
+    if (c >= ncls) return;
+    const CovBlock b = blocks[rep[c]];
+    const int nn = b.n * b.n;
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+        double s = 0.0;
+        for (int k = ptr[c]; k < ptr[c + 1]; k++) s += gram[blocks[mem[k]].l0 + e];
+        gram_cls[b.l0 + e] = s;
+    }
+}
+
 // blockIdx.y = evaluation e of a batch: theta, status, partials, counter and out are indexed by e (R parameters per evaluation); Lblk /
 // logdet (the factor cache of a single evaluation) may be NULL.
 __global__ void __launch_bounds__(FACT_WARPS * 32) mvn_gram_kernel(int B, const CovBlock* __restrict__ blocks, const CovFn* __restrict__ fns,
@@ -222,7 +238,9 @@ __global__ void __launch_bounds__(FACT_WARPS * 32) mvn_gram_kernel(int B, const 
                                                                     const double* __restrict__ gram, double ncols, double* __restrict__ Lblk,
                                                                     double* __restrict__ logdet, int* __restrict__ status,
                                                                     double* __restrict__ partials, unsigned int* __restrict__ counter,
-                                                                    double* __restrict__ out) {
+                                                                    double* __restrict__ out, const int* __restrict__ cls_rep,
+                                                                    const int* __restrict__ cls_ptr) {
+    // cls_rep != NULL: B counts CLASSES of identical blocks; `gram` holds the class sums and the log-determinant term counts once per member
     theta += (size_t)blockIdx.y * R; status += blockIdx.y; partials += (size_t)blockIdx.y * gridDim.x; counter += blockIdx.y; out += blockIdx.y;
     __shared__ double sL[FACT_WARPS][QUAD_SMALL_MAX][QUAD_SMALL_MAX + 1];
     __shared__ double sS[FACT_WARPS][QUAD_SMALL_MAX][QUAD_SMALL_MAX + 1];
@@ -232,7 +250,8 @@ __global__ void __launch_bounds__(FACT_WARPS * 32) mvn_gram_kernel(int B, const 
     const int bi = blockIdx.x * FACT_WARPS + warp;
     double contrib = 0.0;
     if (bi < B) {
-        const CovBlock b = blocks[bi];
+        const CovBlock b = blocks[cls_rep ? cls_rep[bi] : bi];
+        const double mult = cls_rep ? (double)(cls_ptr[bi + 1] - cls_ptr[bi]) : 1.0;
         const int n = b.n;
         double (*L)[QUAD_SMALL_MAX + 1] = sL[warp];
         double (*S)[QUAD_SMALL_MAX + 1] = sS[warp];
@@ -286,7 +305,7 @@ __global__ void __launch_bounds__(FACT_WARPS * 32) mvn_gram_kernel(int B, const 
                 }
             }
             q = warp_sum(q);
-            contrib = ncols * (-0.5 * n * log(2 * 3.14159265358979323846) - 0.5 * ld) - 0.5 * q;   // mcmldmatrix.h:63,75 (M_PI)
+            contrib = mult * ncols * (-0.5 * n * log(2 * 3.14159265358979323846) - 0.5 * ld) - 0.5 * q;   // mcmldmatrix.h:63,75 (M_PI)
         }
     }
     // deterministic grid sum: lane 0 of each warp holds its block's contribution
@@ -401,7 +420,58 @@ extern "C" int gmb_cov_create(gmb_ctx* ctx, const int32_t* cov, int rows, const 
     GMB_CUDA(cudaMemcpyAsync(cv->d_fns, cv->fns.data(), sizeof(CovFn) * cv->fns.size(), cudaMemcpyHostToDevice, ctx->stream));
     GMB_CUDA(cudaMemcpyAsync(cv->d_data, data, sizeof(double) * off, cudaMemcpyHostToDevice, ctx->stream));
     GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (cv->max_n <= QUAD_SMALL_MAX && cv->B > 1) {
+        // classes of identical blocks: exact comparison of size, function rows (id, variables, parameter offsets, effective range) and data differences
+        std::map<std::string, int> seen;
+        std::vector<int> rep, cls(cv->B);
+        for (int b = 0; b < cv->B; b++) {
+            const CovBlock& blk = cv->blocks[b];
+            std::string key(reinterpret_cast<const char*>(&blk.n), sizeof(int));
+            for (int f = 0; f < blk.nfn; f++) {
+                const CovFn& fn = cv->fns[blk.fn0 + f];
+                key.append(reinterpret_cast<const char*>(&fn.id), sizeof(int)); key.append(reinterpret_cast<const char*>(&fn.nvar), sizeof(int));
+                key.append(reinterpret_cast<const char*>(&fn.par0), sizeof(int)); key.append(reinterpret_cast<const char*>(&fn.col0), sizeof(int));
+                key.append(reinterpret_cast<const char*>(&fn.eff), sizeof(double));
+            }
+            // the functions see the data only through the differences dat[i] - dat[j] of each column (block_val): equal differences, computed
+            // exactly as the kernels compute them, give bitwise equal blocks — gr(cl) * ar1(t) carries a different label per cluster, same block
+            const double* dat = data + blk.data0;
+            for (int c = 0; c < blk.ncol; c++)
+                for (int i = 1; i < blk.n; i++)
+                    for (int j = 0; j < i; j++) {
+                        double di = dat[i + (size_t)c * blk.n] - dat[j + (size_t)c * blk.n];
+                        if (di == 0.0) di = 0.0;                               // -0.0
+                        key.append(reinterpret_cast<const char*>(&di), sizeof(double));
+                    }
+            auto it = seen.find(key);
+            if (it == seen.end()) { it = seen.emplace(std::move(key), (int)rep.size()).first; rep.push_back(b); }
+            cls[b] = it->second;
+        }
+        if ((int)rep.size() < cv->B) {
+            cv->ncls = (int)rep.size();
+            std::vector<int> ptr(cv->ncls + 1, 0), mem(cv->B);
+            for (int b = 0; b < cv->B; b++) ptr[cls[b] + 1]++;
+            for (int c = 0; c < cv->ncls; c++) ptr[c + 1] += ptr[c];
+            std::vector<int> fill(ptr.begin(), ptr.end() - 1);
+            for (int b = 0; b < cv->B; b++) mem[fill[cls[b]]++] = b;
+            GMB_CUDA(gmb_dmalloc(ctx, &cv->d_cls_rep, sizeof(int) * cv->ncls));
+            GMB_CUDA(gmb_dmalloc(ctx, &cv->d_cls_ptr, sizeof(int) * (cv->ncls + 1)));
+            GMB_CUDA(gmb_dmalloc(ctx, &cv->d_cls_mem, sizeof(int) * cv->B));
+            GMB_CUDA(cudaMemcpyAsync(cv->d_cls_rep, rep.data(), sizeof(int) * cv->ncls, cudaMemcpyHostToDevice, ctx->stream));
+            GMB_CUDA(cudaMemcpyAsync(cv->d_cls_ptr, ptr.data(), sizeof(int) * (cv->ncls + 1), cudaMemcpyHostToDevice, ctx->stream));
+            GMB_CUDA(cudaMemcpyAsync(cv->d_cls_mem, mem.data(), sizeof(int) * cv->B, cudaMemcpyHostToDevice, ctx->stream));
+            GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     *out = cv;
+    return GMB_OK;
+}
+
+static int g_cov_classes = 1;
+extern "C" int gmb_cov_set_block_classes(int on) { g_cov_classes = on ? 1 : 0; return GMB_OK; }
+extern "C" int gmb_cov_block_classes(gmb_cov* cv, int* ncls) {
+    if (!cv || !ncls) return gmb_set_error(GMB_EINVAL, "gmb_cov_block_classes: bad arguments");
+    *ncls = cv->ncls > 0 ? cv->ncls : cv->B;
     return GMB_OK;
 }
 
@@ -415,6 +485,8 @@ extern "C" void gmb_cov_destroy(gmb_cov* cv) {
     if (cv->d_work) gmb_dfree(cv->ctx, cv->d_work);
     if (cv->d_linv) gmb_dfree(cv->ctx, cv->d_linv);
     if (cv->d_gram) gmb_dfree(cv->ctx, cv->d_gram);
+    if (cv->d_gram_cls) gmb_dfree(cv->ctx, cv->d_gram_cls);
+    gmb_dfree(cv->ctx, cv->d_cls_rep); gmb_dfree(cv->ctx, cv->d_cls_ptr); gmb_dfree(cv->ctx, cv->d_cls_mem);
     if (cv->d_batch) gmb_dfree(cv->ctx, cv->d_batch);
     delete cv;
 }
@@ -603,6 +675,11 @@ static int cov_ensure_gram(gmb_cov* cv, gmb_model* mdl) {
     gram_small_kernel<<<dim3(gx, CC), GRAM_WARPS * 32, 0, ctx->stream>>>(cv->B, cv->d_blocks, mdl->dU, mdl->ldq, ncols, cols_per_cta, gd, ctx->d_scratch);
     gram_reduce_kernel<<<(unsigned)((gd + 255) / 256), 256, 0, ctx->stream>>>(gd, CC, ctx->d_scratch, cv->d_gram);
     ctx->launches += 2;
+    if (cv->ncls > 0) {
+        if (!cv->d_gram_cls) GMB_CUDA(gmb_dmalloc(ctx, &cv->d_gram_cls, sizeof(double) * (gd > 0 ? gd : 1)));
+        gram_class_kernel<<<cv->ncls, 128, 0, ctx->stream>>>(cv->ncls, cv->d_blocks, cv->d_cls_rep, cv->d_cls_ptr, cv->d_cls_mem, cv->d_gram, cv->d_gram_cls);
+        ctx->launches++;
+    }
     GMB_CUDA(cudaGetLastError());
     cv->gram_model = mdl; cv->gram_version = mdl->u_version; cv->gram_cols = ncols;
     return GMB_OK;
@@ -634,14 +711,19 @@ extern "C" int gmb_cov_mvn_ll_model(gmb_cov* cv, const double* theta, gmb_model*
         for (int r = 0; r < cv->R; r++) ctx->h_pinned[r] = theta[r];
         GMB_CUDA(cudaMemcpyAsync(cv->d_theta, ctx->h_pinned, sizeof(double) * cv->R, cudaMemcpyHostToDevice, ctx->stream));
         GMB_CUDA(cudaMemsetAsync(cv->d_status, 0, sizeof(int), ctx->stream));
-        const int ctas = (cv->B + FACT_WARPS - 1) / FACT_WARPS;
+        const bool by_class = cv->ncls > 0 && g_cov_classes;       // one factorisation per class of identical blocks
+        const int nb = by_class ? cv->ncls : cv->B;
+        const int ctas = (nb + FACT_WARPS - 1) / FACT_WARPS;
         GMB_TRY(gmb_ctx_scratch(ctx, (size_t)ctas));
-        mvn_gram_kernel<<<ctas, FACT_WARPS * 32, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->R, cv->d_gram,
-                                                                  (double)mdl->m_local, cv->d_Lblk, cv->d_logdet, cv->d_status, ctx->d_scratch,
-                                                                  ctx->d_counter, ctx->d_result);
+        mvn_gram_kernel<<<ctas, FACT_WARPS * 32, 0, ctx->stream>>>(nb, cv->d_blocks, cv->d_fns, cv->d_data, cv->d_theta, cv->R,
+                                                                  by_class ? cv->d_gram_cls : cv->d_gram, (double)mdl->m_local,
+                                                                  by_class ? nullptr : cv->d_Lblk, by_class ? nullptr : cv->d_logdet, cv->d_status,
+                                                                  ctx->d_scratch, ctx->d_counter, ctx->d_result, by_class ? cv->d_cls_rep : nullptr,
+                                                                  by_class ? cv->d_cls_ptr : nullptr);
         ctx->launches++;
         GMB_CUDA(cudaGetLastError());
-        cv->theta_cached.assign(theta, theta + cv->R); cv->factor_valid = true;      // Lblk / logdet now hold this theta's factor
+        if (by_class) cv->factor_valid = false;                                          // the per-block factor cache was not refreshed
+        else { cv->theta_cached.assign(theta, theta + cv->R); cv->factor_valid = true; }  // Lblk / logdet now hold this theta's factor
         GMB_TRY(gmb_comm_allreduce_dev(ctx, ctx->d_result, 1));
         int* hstat = reinterpret_cast<int*>(ctx->h_pinned + 64);
         GMB_CUDA(cudaMemcpyAsync(ctx->h_pinned, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -673,7 +755,9 @@ extern "C" int gmb_cov_mvn_ll_model_batch(gmb_cov* cv, const double* thetas, int
     gmb_ctx* ctx = cv->ctx;
     cudaSetDevice(ctx->device);
     GMB_TRY(cov_ensure_gram(cv, mdl));
-    const int ctas = (cv->B + FACT_WARPS - 1) / FACT_WARPS;
+    const bool by_class = cv->ncls > 0 && g_cov_classes;
+    const int nb = by_class ? cv->ncls : cv->B;
+    const int ctas = (nb + FACT_WARPS - 1) / FACT_WARPS;
     const double denom = (double)(ncols_total > 0 ? ncols_total : mdl->m_total);
     for (int off = 0; off < k; off += 2048) {
         const int kb = std::min(2048, k - off);
@@ -691,8 +775,10 @@ extern "C" int gmb_cov_mvn_ll_model_batch(gmb_cov* cv, const double* thetas, int
         memcpy(ctx->h_pinned, thetas + (size_t)off * R, sizeof(double) * R * kb);
         GMB_CUDA(cudaMemcpyAsync(d_th, ctx->h_pinned, sizeof(double) * R * kb, cudaMemcpyHostToDevice, ctx->stream));
         GMB_CUDA(cudaMemsetAsync(d_stat, 0, (size_t)kb * 8, ctx->stream));
-        mvn_gram_kernel<<<dim3(ctas, kb), FACT_WARPS * 32, 0, ctx->stream>>>(cv->B, cv->d_blocks, cv->d_fns, cv->d_data, d_th, R, cv->d_gram,
-                                                                             (double)mdl->m_local, nullptr, nullptr, d_stat, d_part, d_cnt, d_out);
+        mvn_gram_kernel<<<dim3(ctas, kb), FACT_WARPS * 32, 0, ctx->stream>>>(nb, cv->d_blocks, cv->d_fns, cv->d_data, d_th, R,
+                                                                             by_class ? cv->d_gram_cls : cv->d_gram, (double)mdl->m_local, nullptr, nullptr,
+                                                                             d_stat, d_part, d_cnt, d_out, by_class ? cv->d_cls_rep : nullptr,
+                                                                             by_class ? cv->d_cls_ptr : nullptr);
         ctx->launches++;
         GMB_CUDA(cudaGetLastError());
         GMB_TRY(gmb_comm_allreduce_dev(ctx, d_out, kb));

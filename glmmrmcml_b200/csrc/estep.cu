@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(256, 2) mcnr_tma_kernel(const __grid_constant_
 // the 8 warps stride over the chunks, fixed-order combination through shared memory) and assembles those rows' share of X' diag(w) X and X' s
 // (one warp per output entry).  CTAs [8 RT, 8 RT + NSIG): 32 columns each per pass (lane = column, warps stride over the row tiles) -> their share
 // of sum_j sd(resid_j) (mcmloptim.h:216).  The last CTA to finish adds the per-CTA partials in index order -> out [P*P + P + 1].  Deterministic.
-__global__ void __launch_bounds__(256) mcnr_tail_kernel(int n, int P, int ldn, int ncols, int RT, int CC, int NSIG, const double* __restrict__ X,
+__global__ void __launch_bounds__(256) mcnr_tail_kernel(int n, int nobs, int P, int ldn, int ncols, int RT, int RTC, int CC, int NSIG, const double* __restrict__ X,
                                                         const double* __restrict__ rowpart, const double* __restrict__ colpart,
                                                         double* __restrict__ part /* [8 RT][P*P+P] then [NSIG] */, unsigned int* __restrict__ counter,
                                                         double* __restrict__ out) {
@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(256) mcnr_tail_kernel(int n, int P, int ldn, i
         for (int j0 = b * 32; j0 < ncols; j0 += NSIG * 32) {
             const int j = j0 + lane;
             double sr = 0.0, sr2 = 0.0;
-            if (j < ncols) for (int t = warp; t < RT; t += 8) { sr += colpart[((size_t)t * 2 + 0) * ncols + j]; sr2 += colpart[((size_t)t * 2 + 1) * ncols + j]; }
+            if (j < ncols) for (int t = warp; t < RTC; t += 8) { sr += colpart[((size_t)t * 2 + 0) * ncols + j]; sr2 += colpart[((size_t)t * 2 + 1) * ncols + j]; }
             __syncthreads();
             sa[warp][lane] = sr; sb[warp][lane] = sr2;
             __syncthreads();
@@ -862,9 +862,9 @@ __global__ void __launch_bounds__(256) mcnr_tail_kernel(int n, int P, int ldn, i
                 double r1 = 0.0, r2 = 0.0;
 #pragma unroll
                 for (int w = 0; w < 8; w++) { r1 += sa[w][lane]; r2 += sb[w][lane]; }
-                const double mean = r1 / n;
-                const double q = r2 - n * mean * mean;
-                tot += sqrt(fmax(q, 0.0) / (n - 1));
+                const double mean = r1 / nobs;                 // nobs = observations (n, or more than n rows when the rows are aggregated)
+                const double q = r2 - nobs * mean * mean;
+                tot += sqrt(fmax(q, 0.0) / (nobs - 1));
             }
         }
         if (warp == 0) {
@@ -958,6 +958,97 @@ __global__ void __launch_bounds__(256) mcnr_assemble_kernel(int n, int P, int ld
     if (threadIdx.x == 0) out[e] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// E-step on AGGREGATED rows.  Observations that share their row of [X | Z] share eta = x'beta + z'u for every beta and u, so
+// zd is formed for the ng distinct rows only (model.cu) and a row carries the sufficient statistics of its c observations (aggregate.cu):
+//   log-likelihood   sum_i l(y_i, eta) = dev_family_ll_w(c, sum y | mean y, within-row SS, sum lf(y); eta)
+//   MCNR             W is a function of eta alone: sum_i w_i = c w;  the working residual is linear in y: sum_i wu_i = c wu(ybar);
+//                    sum_i r_i = c (ybar - mu),  sum_i r_i^2 = SS_within + c (ybar - mu)^2
+// — the sums of mcmlmodel.h:284-304 / mcmloptim.h:190-231 in a different order, on n / ng times fewer bytes (config C2: 500 -> 50 rows).
+// One warp spans 32 rows, the 8 warps of a CTA take every 8th column of the CTA's column chunk.
+// ---------------------------------------------------------------------------------------------------
+template <int FL, class T>
+__global__ void __launch_bounds__(256) loglik_agg_kernel(int ng, int P, int ldg, int ncols, int cols_per_cta, int CC, const T* __restrict__ zd,
+                                                         const double* __restrict__ Xg, const double* __restrict__ beta /* P x gridDim.y */,
+                                                         const double* __restrict__ lc, const double* __restrict__ lys, const double* __restrict__ lsq,
+                                                         const double* __restrict__ lrc, double var_par, double* __restrict__ partials /* [gridDim.y][gridDim.x] */) {
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rt = blockIdx.x / CC, cc = blockIdx.x % CC;
+    const int g = rt * 32 + lane;
+    const int j0 = cc * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
+    const double* b = beta + (size_t)blockIdx.y * P;
+    double acc = 0.0;
+    if (g < ng) {
+        double xb = 0.0;
+        for (int p = 0; p < P; p++) xb += Xg[g + (size_t)p * ldg] * b[p];          // same order as xb_kernel
+        const double c = lc[g], ys = lys[g], sq = (FL == 7) ? lsq[g] : 0.0, rc = (FL == 1) ? lrc[g] : 0.0;
+        const double c0 = (FL == 7) ? (-1.0 * log(var_par) - 0.5 * log(2 * GMB_PI_FAMILY)) : 0.0;   // as loglik_kernel
+        const T* col = zd + g;
+        for (int j = j0 + warp; j < j1; j += 8)
+            acc += dev_family_ll_w<FL>(c, ys, sq, rc, xb + (double)col[(size_t)j * ldg], c0, var_par);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
+// out[e] = sum of the nb partials of evaluation e, in a fixed order
+__global__ void __launch_bounds__(256) agg_finish_kernel(int nb, const double* __restrict__ partials, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < nb; k += 256) s += partials[(size_t)blockIdx.x * nb + k];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// MCNR pass 1 on the aggregated rows; writes the same partial sums as mcnr_pass1_kernel: rowpart[cc][2][ldg] (sum_j of c w and c wu per row),
+// colpart[rt][2][ncols] (sum over the tile's rows of sum_i r_i and sum_i r_i^2 per column), rt = tiles of 32 rows
+template <int FL, class T>
+__global__ void __launch_bounds__(256) mcnr_agg_kernel(int ng, int ldg, int ncols, int cols_per_cta, const T* __restrict__ zd,
+                                                       const double* __restrict__ xb /* per observation */, const int* __restrict__ rep,
+                                                       const double* __restrict__ cnt, const double* __restrict__ eys, const double* __restrict__ ess,
+                                                       double inv_phi, double* __restrict__ rowpart, double* __restrict__ colpart) {
+    __shared__ double stab[64];
+    __shared__ double sw[8][32], ss[8][32];
+    if (threadIdx.x < 64) stab[threadIdx.x] = GMB_EXP2_TAB[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = blockIdx.x * 32 + lane;
+    const int j0 = blockIdx.y * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
+    const bool ok = g < ng;
+    const double c = ok ? cnt[g] : 0.0;
+    const double ybar = ok ? eys[g] / c : 0.0, sq = ok ? ess[g] : 0.0, xbg = ok ? xb[rep[g]] : 0.0;
+    const T* col = zd + (ok ? g : 0);
+    double wacc = 0.0, sacc = 0.0;
+    for (int j = j0 + warp; j < j1; j += 8) {
+        double w = 0.0, wu = 0.0, r = 0.0;
+        if (ok) mcnr_terms<FL>(ybar, xbg + (double)col[(size_t)j * ldg], inv_phi, stab, w, wu, r);
+        wacc += w; sacc += wu;
+        const double sr = warp_sum(c * r), sr2 = warp_sum(ok ? fma(c * r, r, sq) : 0.0);
+        if (lane == 0) {
+            colpart[((size_t)blockIdx.x * 2 + 0) * ncols + j] = sr;
+            colpart[((size_t)blockIdx.x * 2 + 1) * ncols + j] = sr2;
+        }
+    }
+    sw[warp][lane] = c * wacc; ss[warp][lane] = c * sacc;
+    __syncthreads();
+    if (warp == 0 && ok) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { a += sw[k][lane]; b += ss[k][lane]; }
+        rowpart[((size_t)blockIdx.y * 2 + 0) * ldg + g] = a;
+        rowpart[((size_t)blockIdx.y * 2 + 1) * ldg + g] = b;
+    }
+}
+
+// row statistics of the aggregated rows -> per observation (rows of one group share zd, hence their statistics)
+__global__ void stat_expand_kernel(int n, int ldn, int ldg, const int* __restrict__ gid, const double* __restrict__ sg, double* __restrict__ st) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st[i] = sg[gid[i]];
+    st[ldn + i] = sg[ldg + gid[i]];
+}
+
 }  // namespace
 
 // 1 (default) = MCNR pass 1 through the TMA kernel where it applies; 0 = the cp.async kernel (GMB_MCNR_TMA=0; parity tests compare both)
@@ -982,6 +1073,36 @@ static int ensure_rowstats(gmb_model* mdl) {
     const int n = mdl->n, ldn = mdl->ldn, ncols = mdl->niter_local;
     if (mdl->stat_valid && mdl->stat_cols == ncols) return GMB_OK;
     if (!mdl->dstat) GMB_CUDA(gmb_dmalloc(ctx, &mdl->dstat, sizeof(double) * 2 * ldn));
+    if (mdl->eagg) {
+        // the statistics of the ng aggregated rows, then one copy per observation (the O(n) evaluation kernel is unchanged)
+        const gmb_agg& a = mdl->agg;
+        const int ng = a.ng, ldg = a.ldn, halfg = (ldg + 1) / 2;
+        int TXg = 32; while (TXg < 128 && TXg < halfg) TXg <<= 1;
+        const int TYg = 256 / TXg, RTg = (halfg + TXg - 1) / TXg;
+        int CCg = (ctx->sms * 4 + RTg - 1) / RTg;
+        const int max_ccg = (ncols + 4 * TYg - 1) / (4 * TYg);
+        if (CCg > max_ccg) CCg = max_ccg;
+        if (CCg < 1) CCg = 1;
+        int cpc = (ncols + CCg - 1) / CCg;
+        CCg = (ncols + cpc - 1) / cpc;
+        GMB_TRY(gmb_ctx_scratch(ctx, (size_t)CCg * 2 * ldg + 2 * (size_t)ldg));
+        double* rp = ctx->d_scratch; double* sg = rp + (size_t)CCg * 2 * ldg;
+        dim3 gridg(RTg, CCg), blockg(TXg, TYg);
+        const size_t smemg = sizeof(double) * 4 * TXg * TYg;
+        if (mdl->prec == 32) {
+            if (mdl->flink == 1) rowstat_kernel<1, float><<<gridg, blockg, smemg, ctx->stream>>>(ng, ldg, ncols, cpc, mdl->dzd32, rp);
+            else rowstat_kernel<7, float><<<gridg, blockg, smemg, ctx->stream>>>(ng, ldg, ncols, cpc, mdl->dzd32, rp);
+        } else {
+            if (mdl->flink == 1) rowstat_kernel<1, double><<<gridg, blockg, smemg, ctx->stream>>>(ng, ldg, ncols, cpc, mdl->dzd, rp);
+            else rowstat_kernel<7, double><<<gridg, blockg, smemg, ctx->stream>>>(ng, ldg, ncols, cpc, mdl->dzd, rp);
+        }
+        mcnr_rows_kernel<<<(ng + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(ng, ldg, CCg, rp, sg, sg + ldg);
+        stat_expand_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ldn, ldg, a.dgid, sg, mdl->dstat);
+        ctx->launches += 3;
+        GMB_CUDA(cudaGetLastError());
+        mdl->stat_valid = true; mdl->stat_cols = ncols;
+        return GMB_OK;
+    }
     const int half = (ldn + 1) / 2;
     int TX = 32; while (TX < 128 && TX < half) TX <<= 1;
     const int TY = 256 / TX;
@@ -1042,8 +1163,40 @@ static int launch_loglik_f32(gmb_model* mdl, const double* d_beta, double var_pa
     return GMB_OK;
 }
 
+// n_eval evaluations (d_beta: P x n_eval, one var_par) of the whole-model objective on the aggregated rows: two launches
+static int launch_loglik_agg(gmb_model* mdl, const double* d_beta, int n_eval, double var_par, double* d_out) {
+    gmb_ctx* ctx = mdl->ctx;
+    const gmb_agg& a = mdl->agg;
+    const int ng = a.ng, ldg = a.ldn, ncols = mdl->niter_local;
+    if (ncols <= 0) { GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n_eval, ctx->stream)); return GMB_OK; }
+    const int RT = (ng + 31) / 32;
+    for (int e0 = 0; e0 < n_eval; e0 += 32768) {
+        const int ne = std::min(32768, n_eval - e0);
+        int CC = (ctx->sms * 4 + RT * ne - 1) / (RT * ne);
+        const int max_cc = (ncols + 31) / 32;
+        if (CC > max_cc) CC = max_cc;
+        if (CC < 1) CC = 1;
+        int cpc = round_up((ncols + CC - 1) / CC, 8);
+        CC = (ncols + cpc - 1) / cpc;
+        const int nb = RT * CC;
+        GMB_TRY(gmb_ctx_scratch(ctx, (size_t)nb * ne));
+        dim3 grid(nb, ne);
+#define GMB_LLA(F, TT, ZD) loglik_agg_kernel<F, TT><<<grid, 256, 0, ctx->stream>>>(ng, mdl->P, ldg, ncols, cpc, CC, ZD, a.dX, d_beta + (size_t)e0 * mdl->P, a.dlcnt, \
+                                                                                  a.dlys, a.dlsq, a.dlrc, var_par, ctx->d_scratch)
+        if (mdl->prec == 32) { if (mdl->flink == 1) GMB_LLA(1, float, mdl->dzd32); else if (mdl->flink == 3) GMB_LLA(3, float, mdl->dzd32); else GMB_LLA(7, float, mdl->dzd32); }
+        else { if (mdl->flink == 1) GMB_LLA(1, double, mdl->dzd); else if (mdl->flink == 3) GMB_LLA(3, double, mdl->dzd); else GMB_LLA(7, double, mdl->dzd); }
+#undef GMB_LLA
+        agg_finish_kernel<<<ne, 256, 0, ctx->stream>>>(nb, ctx->d_scratch, d_out + e0);
+        ctx->launches += 2;
+    }
+    GMB_CUDA(cudaGetLastError());
+    return GMB_OK;
+}
+
 int gmb_launch_loglik(gmb_model* mdl, const double* d_beta, double var_par, double* d_out) {
     gmb_ctx* ctx = mdl->ctx;
+    if (mdl->eagg && !((mdl->flink == 1 || mdl->flink == 7) && mdl->niter_local > 0 && gmb_estep_rowstats_enabled()))
+        return launch_loglik_agg(mdl, d_beta, 1, var_par, d_out);
     if ((mdl->flink == 1 || mdl->flink == 7) && mdl->niter_local > 0 && gmb_estep_rowstats_enabled()) {
         GMB_TRY(ensure_rowstats(mdl));
         const int n = mdl->n, nb = (n + 255) / 256;
@@ -1111,6 +1264,11 @@ int gmb_launch_loglik_multi(gmb_model* mdl, const double* d_beta, int n_eval, do
     gmb_ctx* ctx = mdl->ctx;
     *done = 0;
     const int n = mdl->n, ncols = mdl->niter_local;
+    if (mdl->eagg && mdl->flink == 3 && ncols > 0) {             // aggregated rows: the whole batch in two launches (var_par plays no role)
+        GMB_TRY(launch_loglik_agg(mdl, d_beta, n_eval, 1.0, d_out));
+        *done = 1;
+        return GMB_OK;
+    }
     if (!(mdl->flink == 3 && mdl->f_valid && ncols > 0 && n_eval >= GMB_LOGLIK_NB) || mdl->prec == 32) return GMB_OK;
     const int groups = (n_eval + GMB_LOGLIK_NB - 1) / GMB_LOGLIK_NB;
     if (groups > 65535) return GMB_OK;
@@ -1174,6 +1332,31 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
     double inv_phi = gmb_flink_gaussian(mdl->flink) ? 1.0 / (var_par * var_par) : 1.0;   // mcmlmodel.h:123-133
     dim3 grid(RT, CC);
     const int fl = mdl->flink;
+    if (mdl->eagg) {
+        const gmb_agg& a = mdl->agg;
+        const int ng = a.ng, ldg = a.ldn;
+        const int RTC = (ng + 31) / 32, RTg = (ng + 255) / 256;
+        int CCg = (ctx->sms * 4 + RTC - 1) / RTC;
+        const int max_ccg = (ncols + 31) / 32;
+        if (CCg > max_ccg) CCg = max_ccg;
+        if (CCg < 1) CCg = 1;
+        const int cpc = round_up((ncols + CCg - 1) / CCg, 8);
+        CCg = (ncols + cpc - 1) / cpc;
+        const int NSIG2 = (ncols + 31) / 32 < 512 ? (ncols + 31) / 32 : 512;
+        const size_t npart = (size_t)8 * RTg * (P * P + P) + NSIG2;
+        GMB_TRY(gmb_ctx_scratch(ctx, (size_t)CCg * 2 * ldg + (size_t)RTC * 2 * ncols + npart));
+        rowpart = ctx->d_scratch; colpart = rowpart + (size_t)CCg * 2 * ldg;
+        double* part = colpart + (size_t)RTC * 2 * ncols;
+        dim3 gridg(RTC, CCg);
+#define GMB_NRA(F, TT, ZD) mcnr_agg_kernel<F, TT><<<gridg, 256, 0, ctx->stream>>>(ng, ldg, ncols, cpc, ZD, d_xb, a.drep, a.dcnt, a.deys, a.dess, inv_phi, rowpart, colpart)
+        if (mdl->prec == 32) { if (fl == 1) GMB_NRA(1, float, mdl->dzd32); else if (fl == 3) GMB_NRA(3, float, mdl->dzd32); else GMB_NRA(7, float, mdl->dzd32); }
+        else { if (fl == 1) GMB_NRA(1, double, mdl->dzd); else if (fl == 3) GMB_NRA(3, double, mdl->dzd); else GMB_NRA(7, double, mdl->dzd); }
+#undef GMB_NRA
+        mcnr_tail_kernel<<<8 * RTg + NSIG2, 256, 0, ctx->stream>>>(ng, n, P, ldg, ncols, RTg, RTC, CCg, NSIG2, a.dX, rowpart, colpart, part, ctx->d_counter, d_out);
+        ctx->launches += 2;
+        GMB_CUDA(cudaGetLastError());
+        return GMB_OK;
+    }
     if (mdl->prec == 32 && !(gmbtma::get_encode() && (fl == 1 || fl == 7 || (fl == 3 && mdl->f_valid))))
         return gmb_set_error(GMB_EFAMILY, "fp32 mode: the MCNR step is implemented for poisson/log, binomial/logit and gaussian/identity");
     if ((g_mcnr_tma || mdl->prec == 32) && gmbtma::get_encode() && (fl == 1 || fl == 7 || (fl == 3 && mdl->f_valid))) {
@@ -1201,7 +1384,7 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
         if (f32) { if (fl == 1) GMB_NR_TMA(1, float); else if (fl == 3) GMB_NR_TMA(3, float); else GMB_NR_TMA(7, float); }
         else { if (fl == 1) GMB_NR_TMA(1, double); else if (fl == 3) GMB_NR_TMA(3, double); else GMB_NR_TMA(7, double); }
 #undef GMB_NR_TMA
-        mcnr_tail_kernel<<<8 * RT + NSIG2, 256, 0, ctx->stream>>>(n, P, ldn, ncols, RT, CC, NSIG2, mdl->dX, rowpart, colpart, part, ctx->d_counter, d_out);
+        mcnr_tail_kernel<<<8 * RT + NSIG2, 256, 0, ctx->stream>>>(n, n, P, ldn, ncols, RT, RT, CC, NSIG2, mdl->dX, rowpart, colpart, part, ctx->d_counter, d_out);
         ctx->launches += 2;
         GMB_CUDA(cudaGetLastError());
         return GMB_OK;

@@ -153,12 +153,16 @@ int gmb_model_reserve_samples(gmb_model* mdl, int m) {
 // zd = Z u with Z in ELL form (indicator designs: one or two non-zeros per row): a gather instead of a 2 n Q m flop contraction
 template <class T>
 __global__ void __launch_bounds__(256) zd_sparse_kernel(int n, int ldn, int ngp, int wr, int ldq, const double* __restrict__ rv, const int* __restrict__ rc,
+                                                        const int* __restrict__ rowmap /* row of Z that output row i reads; NULL: i */,
                                                         const double* __restrict__ U, T* __restrict__ zd) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     const size_t j = blockIdx.y;
     if (i >= ldn) return;
     double s = 0.0;
-    if (i < n) for (int w = 0; w < wr; w++) s = fma(rv[(size_t)w * ngp + i], U[rc[(size_t)w * ngp + i] + j * ldq], s);
+    if (i < n) {
+        const int zi = rowmap ? rowmap[i] : i;
+        for (int w = 0; w < wr; w++) s = fma(rv[(size_t)w * ngp + zi], U[rc[(size_t)w * ngp + zi] + j * ldq], s);
+    }
     zd[i + j * ldn] = (T)s;
 }
 
@@ -172,26 +176,46 @@ __global__ void narrow_kernel(size_t count, const double* __restrict__ src, floa
 static int g_zd_sparse = 1;
 extern "C" int gmb_estep_set_sparse_zd(int on) { g_zd_sparse = on ? 1 : 0; return GMB_OK; }
 
+// 1 (default) = the E-step runs on the distinct rows of [X | Z] when at most a quarter of the rows are distinct (poisson/log, binomial/logit
+// with 0/1 responses, gaussian/identity); 0 = one row of zd per observation
+static int g_estep_agg = 1;
+extern "C" int gmb_estep_set_row_aggregation(int on) { g_estep_agg = on ? 1 : 0; return GMB_OK; }
+extern "C" int gmb_model_estep_rows(gmb_model* mdl, int* rows) {
+    if (!mdl || !rows) return gmb_set_error(GMB_EINVAL, "gmb_model_estep_rows: bad arguments");
+    *rows = (mdl->zd_valid && mdl->eagg) ? mdl->agg.ng : mdl->n;
+    return GMB_OK;
+}
+
 int gmb_model_build_zd(gmb_model* mdl) {
     bool sparse = false;
     if (mdl->m_local > 0 && g_zd_sparse && mdl->Q >= 64) {
         GMB_TRY(gmb_zell_ensure(mdl));
         sparse = mdl->zell.valid && mdl->m_local <= 65535 * 16;
     }
+    // rows that share [X | Z] share zd — form it (and run the E-step kernels, estep.cu) on the distinct rows only
+    mdl->eagg = false;
+    if (g_estep_agg && mdl->m_local > 0 && gmb_flink_core(mdl->flink) && gmb_agg_enabled()) {
+        GMB_TRY(gmb_agg_ensure(mdl));
+        const gmb_agg& a = mdl->agg;
+        mdl->eagg = a.active && (long long)a.ng * 4 <= mdl->n && (mdl->flink != 3 || a.binary_ok);
+    }
+    const int ne = mdl->eagg ? mdl->agg.ng : mdl->n, lde = mdl->eagg ? mdl->agg.ldn : mdl->ldn;
+    const double* Ze = mdl->eagg ? mdl->agg.dZ : mdl->dZ;
+    const int* rowmap = mdl->eagg ? mdl->agg.drep : nullptr;
     if (sparse) {
         const gmb_ell& e = mdl->zell;
         for (int j0 = 0; j0 < mdl->m_local; j0 += 65535) {
             const int nc = std::min(65535, mdl->m_local - j0);
             if (mdl->prec == 32)
-                zd_sparse_kernel<float><<<dim3((mdl->ldn + 255) / 256, nc), 256, 0, mdl->ctx->stream>>>(mdl->n, mdl->ldn, e.ngp, e.wr, mdl->ldq, e.rv, e.rc,
-                                                                                                      mdl->dU + (size_t)j0 * mdl->ldq, mdl->dzd32 + (size_t)j0 * mdl->ldn);
+                zd_sparse_kernel<float><<<dim3((lde + 255) / 256, nc), 256, 0, mdl->ctx->stream>>>(ne, lde, e.ngp, e.wr, mdl->ldq, e.rv, e.rc, rowmap,
+                                                                                                 mdl->dU + (size_t)j0 * mdl->ldq, mdl->dzd32 + (size_t)j0 * lde);
             else
-                zd_sparse_kernel<double><<<dim3((mdl->ldn + 255) / 256, nc), 256, 0, mdl->ctx->stream>>>(mdl->n, mdl->ldn, e.ngp, e.wr, mdl->ldq, e.rv, e.rc,
-                                                                                                       mdl->dU + (size_t)j0 * mdl->ldq, mdl->dzd + (size_t)j0 * mdl->ldn);
+                zd_sparse_kernel<double><<<dim3((lde + 255) / 256, nc), 256, 0, mdl->ctx->stream>>>(ne, lde, e.ngp, e.wr, mdl->ldq, e.rv, e.rc, rowmap,
+                                                                                                  mdl->dU + (size_t)j0 * mdl->ldq, mdl->dzd + (size_t)j0 * lde);
             mdl->ctx->launches++;
         }
         GMB_CUDA(cudaGetLastError());
-    } else if (mdl->m_local > 0 && mdl->prec == 32 && gmb_tf32_enabled()) {
+    } else if (mdl->m_local > 0 && mdl->prec == 32 && gmb_tf32_enabled() && !mdl->eagg) {
         // dense Z in fp32 mode: tensor cores, tcgen05.mma kind::tf32 with the 3xTF32 split (gemm_tf32.cu)
         gmb_ctx* ctx = mdl->ctx;
         const int ldk = round_up(mdl->Q, 4);
@@ -212,22 +236,24 @@ int gmb_model_build_zd(gmb_model* mdl) {
     } else if (mdl->m_local > 0 && mdl->prec == 32) {
         // dense Z in fp32 mode: the fp64 DMMA product in column chunks through the context's scratch area, narrowed to float
         gmb_ctx* ctx = mdl->ctx;
-        const int chunk = std::max(1, std::min(mdl->m_local, (int)(((size_t)1 << 27) / (size_t)mdl->ldn)));
-        GMB_TRY(gmb_ctx_scratch(ctx, (size_t)mdl->ldn * chunk));
+        const int chunk = std::max(1, std::min(mdl->m_local, (int)(((size_t)1 << 27) / (size_t)lde)));
+        GMB_TRY(gmb_ctx_scratch(ctx, (size_t)lde * chunk));
         for (int j0 = 0; j0 < mdl->m_local; j0 += chunk) {
             const int nc = std::min(chunk, mdl->m_local - j0);
-            GMB_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(double) * (size_t)mdl->ldn * nc, ctx->stream));
-            GMB_TRY(gmb_dgemm(ctx, 0, 0, mdl->n, nc, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dU + (size_t)j0 * mdl->ldq, mdl->ldq, 0.0, ctx->d_scratch, mdl->ldn));
-            const size_t cnt = (size_t)mdl->ldn * nc;
-            narrow_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(cnt, ctx->d_scratch, mdl->dzd32 + (size_t)j0 * mdl->ldn);
+            GMB_CUDA(cudaMemsetAsync(ctx->d_scratch, 0, sizeof(double) * (size_t)lde * nc, ctx->stream));
+            GMB_TRY(gmb_dgemm(ctx, 0, 0, ne, nc, mdl->Q, 1.0, Ze, lde, mdl->dU + (size_t)j0 * mdl->ldq, mdl->ldq, 0.0, ctx->d_scratch, lde));
+            const size_t cnt = (size_t)lde * nc;
+            narrow_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, ctx->stream>>>(cnt, ctx->d_scratch, mdl->dzd32 + (size_t)j0 * lde);
             ctx->launches++;
         }
         GMB_CUDA(cudaGetLastError());
-    } else if (mdl->m_local > 0)
-        GMB_TRY(gmb_dgemm(mdl->ctx, 0, 0, mdl->n, mdl->m_local, mdl->Q, 1.0, mdl->dZ, mdl->ldn, mdl->dU, mdl->ldq, 0.0, mdl->dzd, mdl->ldn));
+    } else if (mdl->m_local > 0) {
+        if (mdl->eagg) GMB_CUDA(cudaMemsetAsync(mdl->dzd, 0, sizeof(double) * (size_t)lde * mdl->m_local, mdl->ctx->stream));    // padding rows
+        GMB_TRY(gmb_dgemm(mdl->ctx, 0, 0, ne, mdl->m_local, mdl->Q, 1.0, Ze, lde, mdl->dU, mdl->ldq, 0.0, mdl->dzd, lde));
+    }
     mdl->f_valid = false;
     mdl->stat_valid = false;
-    if (mdl->flink == 3 && (mdl->dF || mdl->dF32) && mdl->m_local > 0) {        // factor matrix of the binomial/logit E-step (estep.cu)
+    if (mdl->flink == 3 && (mdl->dF || mdl->dF32) && mdl->m_local > 0 && !mdl->eagg) {        // factor matrix of the binomial/logit E-step (estep.cu)
         GMB_TRY(gmb_launch_build_factor(mdl, mdl->m_local));
         mdl->f_valid = true;
     }

@@ -202,6 +202,20 @@ int gmb_estep_set_multi(int on);
  * (built once per sample matrix, each evaluation independent of the number of samples), 0 = stream the samples on every evaluation. */
 int gmb_cov_set_gram(int on);
 
+/* Gram-matrix path: 1 (default) = blocks that are IDENTICAL (same size, same function rows, same data — gr(cl)*ar1(t) repeats one block per
+ * cluster; mcmldmatrix.h:26-36 loops over all of them) are built and factorised once per class, on the class's summed Gram matrix;
+ * 0 = one factorisation per block.  Same sums in a different order.  gmb_cov_block_classes: number of distinct classes found. */
+int gmb_cov_set_block_classes(int on);
+
+/* E-step (log-likelihood, MCNR sums) of poisson/log, binomial/logit (0/1 responses) and gaussian/identity models: 1 (default) = when at most
+ * a quarter of the rows of [X | Z] are distinct, zd = Z u is formed for the distinct rows only and every kernel runs on those rows with the
+ * sufficient statistics of their observations (config C2: 500 rows -> 50; R6ModelExtMCML.R:283,297 densifies); 0 = one row per observation.
+ * Same sums in a different order.  Needs the sampler's row view (gmb_hmc_set_row_aggregation(1), the default).
+ * gmb_model_estep_rows: rows of the zd the model currently holds. */
+int gmb_estep_set_row_aggregation(int on);
+int gmb_model_estep_rows(gmb_model* mdl, int* rows);
+int gmb_cov_block_classes(gmb_cov* cv, int* ncls);
+
 /* On-chip sampler: 1 (default) = observations that share their row of [X | Z] (hence their linear predictor) are aggregated into one
  * weighted row (aggregate.cu; config C2: 500 rows -> 50), 0 = one row per observation.  Same sums in a different order. */
 int gmb_hmc_set_row_aggregation(int on);

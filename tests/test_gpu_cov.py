@@ -168,3 +168,51 @@ def test_wendland_compact_support_blocks(gctx, oracle, fid):
         cv.close()
     with pytest.raises(g.GmbError):                             # compact support needs its range
         g.Covariance(gctx, cov, data, np.array([0.0]))
+
+
+def test_identical_blocks_are_factorised_once(gctx, oracle):
+    """gr(cl)*ar1(t) repeats ONE block per cluster (mcmldmatrix.h:26-36 loops over all of them).  The Gram path finds the classes
+    (here: 60 identical 10 x 10 blocks, 7 identical 4 x 4 blocks with another parameter set, 3 singletons), factorises one block per class on the
+    summed Gram matrix and agrees with the per-block evaluation and with the oracle."""
+    import glmmrmcml_b200 as g
+    rng = np.random.default_rng(11)
+    cov, data, b = [], [], 0
+    for c in range(60):                                   # gr(cl) * ar1(t), label differs per cluster
+        cov += [[b, 10, 1, 1, 0], [b, 10, 3, 1, 1]]; data += [c + 1.0] * 10 + list(np.arange(1.0, 11.0)); b += 1
+    for c in range(7):                                    # gr(cl2) * fexp0(x) on a shared design of 4 points
+        cov += [[b, 4, 1, 1, 2], [b, 4, 2, 1, 3]]; data += [100.0 + c] * 4 + [0.0, 0.5, 1.25, 2.0]; b += 1
+    for c in range(3):                                    # singletons: different point sets
+        x = rng.random(6)
+        cov += [[b, 6, 2, 1, 4]]; data += list(x); b += 1
+    cov = np.array(cov, dtype=np.int32); data = np.array(data); eff = np.zeros(len(cov))
+    theta = np.array([0.4, 0.6, 0.5, 0.8, 0.7])
+    cv = g.Covariance(gctx, cov, data, eff)
+    assert cv.B == 70 and cv.block_classes == 5
+    Q = cv.Q
+    n = 40
+    Z = np.zeros((n, Q), order="F"); Z[np.arange(n), rng.integers(0, Q, n)] = 1.0
+    mdl = g.Model(gctx, np.ones((n, 1), order="F"), Z, rng.poisson(2.0, n).astype(float), "poisson", "log")
+    L = cv.genD(theta, chol=True)
+    U = np.asfortranarray(L @ rng.standard_normal((Q, 777)))
+    mdl.set_u(U)
+    pts = np.asfortranarray(np.stack([theta * s for s in (1.0, 0.8, 1.1)], axis=1))
+    for k in range(3):
+        want = oracle.mvn_loglik(cov, data, eff, pts[:, k], U)
+        got = cv.loglik_model(pts[:, k], mdl)
+        try:
+            g.cov_set_block_classes(False); per_block = cv.loglik_model(pts[:, k], mdl)
+        finally:
+            g.cov_set_block_classes(True)
+        assert abs(got - want) <= 1e-10 * abs(want) and abs(per_block - want) <= 1e-10 * abs(want), (got, per_block, want)
+        assert abs(got - per_block) <= 1e-13 * abs(want)
+        assert abs(cv.logdet(pts[:, k]) - oracle.logdet(cov, data, eff, pts[:, k])) <= 1e-10 * abs(want)    # per-block factor cache still right
+    batch = cv.loglik_model_batch(pts, mdl)
+    assert np.array_equal(batch, np.array([cv.loglik_model(pts[:, k], mdl) for k in range(3)]))
+    bad = theta.copy(); bad[1] = 1.3                       # ar1 parameter > 1: the class's block is not positive definite
+    with pytest.raises(g.GmbError):
+        cv.loglik_model(bad, mdl)
+    # a second covariance object whose blocks all differ keeps the per-block path
+    cfg = synth.config3(nloc=12, m=10)
+    cv2 = g.Covariance(gctx, np.array([[0, 5, 13, 1, 0], [1, 5, 13, 1, 0]], dtype=np.int32), np.concatenate([rng.random(5), rng.random(5)]), np.zeros(2))
+    assert cv2.block_classes == 2
+    cv2.close(); mdl.close(); cv.close()

@@ -27,12 +27,20 @@ CASES = {
 }
 
 
-@pytest.fixture(scope="module", params=list(CASES))
+# C1 and C2 repeat every row of [X | Z] ten times: by default their E-step runs on the 50 distinct rows (estep.cu: *_agg kernels); the
+# "-dense" variants switch that off so that the per-observation kernels (factor matrix, TMA MCNR pass) stay covered on the same data
+@pytest.fixture(scope="module", params=list(CASES) + ["C1-dense", "C2-dense"])
 def case(request, gctx):
     import glmmrmcml_b200 as g
-    cfg = CASES[request.param]()
+    name = request.param
+    cfg = CASES[name.replace("-dense", "")]()
     mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
-    mdl.set_u(cfg["U"])
+    g.estep_set_row_aggregation(not name.endswith("-dense"))
+    try:
+        mdl.set_u(cfg["U"])
+    finally:
+        g.estep_set_row_aggregation(True)
+    assert mdl.estep_rows() == (50 if name in ("C1", "C2") else cfg["n"])
     yield cfg, mdl
     mdl.close()
 
@@ -58,7 +66,12 @@ def test_loglik_multi_kernel_equals_single_kernel(gctx, oracle, k):
     import glmmrmcml_b200 as g
     cfg = synth.config2(m=1500)
     mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
-    mdl.set_u(cfg["U"])
+    g.estep_set_row_aggregation(False)             # the factor-matrix kernels are the per-observation path
+    try:
+        mdl.set_u(cfg["U"])
+    finally:
+        g.estep_set_row_aggregation(True)
+    assert mdl.estep_rows() == cfg["n"]
     rng = np.random.default_rng(5)
     betas = np.asfortranarray(cfg["beta"][:, None] + 0.2 * rng.standard_normal((cfg["P"], k)))
     betas[:, k - 1] *= 150.0                       # |eta| ~ 100: products of 8 factors overflow, term-by-term path

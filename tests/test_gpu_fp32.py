@@ -20,14 +20,21 @@ CASES = {
 }
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(CASES) + ["C1-dense", "C2-dense"])
 def test_fp32_mode_estep_against_the_fp64_oracle(gctx, oracle, name):
     import glmmrmcml_b200 as g
+    dense = name.endswith("-dense")                # C1 / C2: E-step on every observation instead of on the 50 distinct rows
+    name = name.replace("-dense", "")
     cfg = CASES[name]()
     fl = oracle.flink(cfg["family"], cfg["link"])
     m32 = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"], precision="fp32")
     m64 = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
-    m32.set_u(cfg["U"]); m64.set_u(cfg["U"])
+    g.estep_set_row_aggregation(not dense)
+    try:
+        m32.set_u(cfg["U"]); m64.set_u(cfg["U"])
+    finally:
+        g.estep_set_row_aggregation(True)
+    assert m32.estep_rows() == (50 if (name in ("C1", "C2") and not dense) else cfg["n"])
     rng = np.random.default_rng(3)
     worst = 0.0
     for trial in range(3):
