@@ -45,13 +45,16 @@ N_D_EVALS = 64            # mvn_ll evaluations of one d_optim (BOBYQA over 2 par
 N_HESS = 256              # 4 k^2, k = P + R = 8
 D_BATCH = 5               # 2 R + 1: the central-difference stencil the optimiser evaluates as one batch (optim.cpp)
 FP64_DMMA_PEAK_TFLOPS = 37.1   # measured on this pool's B200: profiles/r01_microbench_fp64.txt (tools/microbench_fp64.cu)
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the round's `ncu --set full` captures (profiles/r01_ncu_raw_extract_final.txt):
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the `ncu --set full` captures (profiles/r02_ncu_hmc_hmc_lane.txt,
+# profiles/r01_ncu_raw_extract_final.txt):
 SAMPLER_DRAM_BYTES_PER_LAUNCH = {2: 446976.0,       # hmc_fused_kernel<3,13,4>: Z L, xb, y are read once, the chain runs out of shared memory
-                                 3: 80384.0}         # hmc_sparse_kernel<3,32,2,5>: ELL arrays, xb and row weights are read once; the samples stay in L2
+                                 3: 80384.0,         # hmc_sparse_kernel<3,32,2,5>: ELL arrays, xb and row weights are read once; the samples stay in L2
+                                 "lane": 128768.0}   # hmc_lane_kernel<3,1,5,5,1>: block of Z L, xb and row weights read once; state in registers, samples stay in L2
 # FP64 operations per leapfrog step and chain that the structure-aware kernel executes (FMA = 2): 4 per non-zero of Z L (eta and gradient),
 # per row the residual (table exp 18 + Newton reciprocal 9 + 2 for binomial-logit; 20 poisson; 2 gaussian), per column 8 (gradient, leapfrog)
 SPARSE_ROW_FLOPS = {"binomial": 29.0, "poisson": 20.0, "gaussian": 2.0}
-LOGLIK_DRAM_BYTES_PER_LAUNCH = 1.000278e9 + 3.865e6  # loglik_kernel<3> on 1 GB of zd (algorithmic bytes: 1.000008e9)
+LOGLIK_DRAM_BYTES_PER_LAUNCH = 1.000243e9 + 6.959e6  # loglik_logit_factor_kernel<double> on 1 GB of F (algorithmic bytes: 1.000008e9); profiles/r02_ncu_estep_loglik_logit.txt
+MCNR_DRAM_BYTES_PER_LAUNCH = 1.000088e9 + 14.16e6     # mcnr_tma_kernel<3, double> on the same matrix (same capture)
 
 
 def load_peaks():
@@ -65,13 +68,33 @@ def load_peaks():
 def sampler_roofline(st, exec_tflops, algo_tflops, exec_per_step, cfg, Q, dense_probe, many_probe=None):
     """roofline object of the sampler launch of the timed step (the step's dominant kernel)."""
     kv = st["kernel_variant"]
+    lane = kv == 3 and st.get("lane_components", 0) > 0
     common = {"achieved": exec_tflops, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": exec_tflops / FP64_DMMA_PEAK_TFLOPS,
               "algorithmic_tflops": algo_tflops, "frac_algorithmic": algo_tflops / FP64_DMMA_PEAK_TFLOPS,
-              "traffic": SAMPLER_DRAM_BYTES_PER_LAUNCH.get(kv), "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q,
+              "traffic": SAMPLER_DRAM_BYTES_PER_LAUNCH.get("lane" if lane else kv), "flops_per_leapfrog_per_chain": 4.0 * cfg["n"] * Q,
               "executed_flops_per_leapfrog_per_chain": exec_per_step, "rows_used": st["rows_used"], "zl_nonzeros": st["zl_nonzeros"],
               "peak_source": "FP64 pipe peak measured on this pool's B200 (profiles/r01_microbench_fp64.txt: DMMA 37.1, DFMA 36.8 TFLOP/s, the same "
                              "pipe); MEASURED_PEAKS.json has no fp64 entry (the bf16 tensor peak does not apply to an fp64 kernel)"}
-    if kv == 3:
+    if lane:
+        common.update({
+            "kernel": "hmc_lane_kernel<%s> (structure-aware sampler, lane per connected component: Z L is block diagonal in the aggregated rows, "
+                      "%d blocks per chain; one lane integrates a whole block — rows, columns, momentum, position, ELL entries in registers — "
+                      "with no exchange inside a trajectory; a warp-level sum per proposal for the accept test)" % (cfg["family"], st["lane_components"]),
+            "bound": "fp64",
+            "note": "achieved = FP64 flops the kernel EXECUTES per leapfrog step and chain (4 per non-zero of Z L + residual per distinct row + "
+                    "leapfrog update per column; FMA = 2) / kernel time, against the FP64 pipe peak.  SURVEY 8d's algorithmic figure for the dense "
+                    "contraction (4 n Q = 1e5 per step and chain) is `algorithmic_tflops`: the kernel does the same arithmetic on the 150 non-zeros "
+                    "of the 50 distinct rows instead of 500 x 50 entries, so that figure exceeds the pipe peak.  1000 chains x 10 blocks = 313 warps "
+                    "on 592 schedulers: every warp has a scheduler to itself and runs one dependent FP64 chain (ncu, profiles/r02_ncu_hmc_hmc_lane.txt: "
+                    "FP64 pipe 55 % busy on the active schedulers, 6 % of the warp slots) — bound by FP64 latency x trajectory length, not by pipe "
+                    "throughput; `dense_kernel` is the DMMA kernel a model with a dense Z L runs",
+            "dense_kernel": dense_probe})
+        if many_probe and many_probe.get("kernel_variant") == 3:
+            t = many_probe["leapfrog_per_s"] * exec_per_step / 1e12
+            common["saturated"] = {"chains": many_probe["chains"], "ms": many_probe["ms"], "leapfrog_per_s": many_probe["leapfrog_per_s"],
+                                   "achieved": t, "frac": t / FP64_DMMA_PEAK_TFLOPS,
+                                   "note": "the same kernel with 4000 chains (two warps per scheduler, 104 proposals): its throughput regime; not the timed step"}
+    elif kv == 3:
         common.update({
             "kernel": "hmc_sparse_kernel<%s> (structure-aware sampler: Z L in ELL form, one warp per chain, state and ELL entries in registers)" % cfg["family"],
             "bound": "fp64",
@@ -557,7 +580,13 @@ def main():
         # rank 0 only: on a context WITHOUT communicator (a collective issued by one rank alone would never return)
         ctx1 = g.Context(local_rank) if world > 1 else ctx
         mdl2 = g.Model(ctx1, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
-        mdl2.set_u(Ubig)
+        # the streaming kernels a design WITHOUT repeated rows runs (C3-C5): one row of zd per observation.  C2 itself repeats every row of
+        # [X | Z] ten times and its E-step runs on the 50 distinct rows by default (`aggregated` below: the same evaluations on a tenth of the bytes)
+        g.estep_set_row_aggregation(False)
+        try:
+            mdl2.set_u(Ubig)
+        finally:
+            g.estep_set_row_aggregation(True)
         g.estep_set_multi(False)                     # one launch per evaluation: every launch streams the whole 1 GB
         try:
             mdl2.log_likelihood_batch(Bst[:, :4], np.ones(4))
@@ -576,7 +605,21 @@ def main():
                           "batched": {"ms_per_eval": t_multi, "evals_per_s": 1e3 / t_multi,
                                       "note": "loglik_logit_factor_multi_kernel, 64 evaluations in one launch: the matrix is read once per 8 evaluations "
                                               "(algorithmic bytes / 8 per evaluation), bound by FP64 work"},
-                          "mcnr": {"achieved": bytes_nr / (t_nr * 1e-3) / 1e9, "frac": bytes_nr / (t_nr * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": t_nr}}
+                          "mcnr": {"achieved": bytes_nr / (t_nr * 1e-3) / 1e9, "frac": bytes_nr / (t_nr * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": t_nr,
+                                   "traffic": MCNR_DRAM_BYTES_PER_LAUNCH,
+                                   "note": "whole mcnr() call (x'beta, TMA pass, tail, 7 doubles back to the host); the TMA pass alone: 171 us = 5.83 TB/s under ncu"}}
+        mdl2.close()
+        # the same evaluations with the E-step on the 50 distinct rows (the default for this model): zd is 100 MB instead of 1 GB
+        mdl2 = g.Model(ctx1, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+        mdl2.set_u(Ubig)
+        rows_agg = mdl2.estep_rows()
+        mdl2.log_likelihood_batch(Bst[:, :64], np.ones(64))
+        ctx1.timer_start(); mdl2.log_likelihood_batch(Bst[:, :64], np.ones(64)); t_agg = ctx1.timer_stop() / 64
+        mdl2.mcnr(beta, 1.0)
+        ctx1.timer_start(); [mdl2.mcnr(beta, 1.0) for _ in range(4)]; t_nr_agg = ctx1.timer_stop() / 4
+        roofline_estep["aggregated"] = {"rows": rows_agg, "zd_bytes": 8.0 * rows_agg * mbig, "loglik_ms_per_eval_batched": t_agg, "mcnr_ms": t_nr_agg,
+                                        "speedup_loglik_vs_batched_dense": t_multi / t_agg, "speedup_mcnr": t_nr / t_nr_agg,
+                                        "note": "SURVEY 8f N2: observations sharing their row of [X | Z] share eta; zd and every E-step kernel run on the distinct rows"}
         mdl2.close()
         # the timed step's sampler kernel with every scheduler holding several warps (4000 chains): its throughput regime
         mdl4 = g.Model(ctx1, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])

@@ -152,7 +152,7 @@ __global__ void build_factor_kernel(int n, int ldn, int ncols, const T* __restri
     if (i >= ldn || j >= ncols) return;
     double f = 1.0;
     if (i < n) {
-        const double yi = y[i];
+        const double yi = y ? y[i] : 0.0;                 // y == NULL (aggregated rows): F = exp(zd) for every row
         const double z = (double)zd[i + (size_t)j * ldn];
         f = (yi == 1.0) ? exp(-1.0 * z) : exp(z);
     }
@@ -992,6 +992,83 @@ __global__ void __launch_bounds__(256) loglik_agg_kernel(int ng, int P, int ldg,
     if (threadIdx.x == 0) partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = acc;
 }
 
+// Binomial/logit on the aggregated rows, through the factor matrix F = exp(zd) (ng x m, built with zd): with c observations of which n1 are
+// ones in a row,   sum_i l_i = n1 eta - c log(1 + e^eta),   e^eta = A F,  A = exp(x'beta), so
+//     ll(beta) = sum_g n1_g (m xb_g + T_g) - sum_g c_g log prod_j (1 + A_g F_gj),        T_g = sum_j zd_gj (a row statistic of the sample matrix)
+// — per element one FMA and one multiply per evaluation and one log per 8 columns, as loglik_logit_factor_multi_kernel but with the product
+// running along a ROW (the weight c_g factors out of the log), on ng instead of n rows.  NB evaluations share each load; blockIdx.y = group of NB
+// evaluations (a short last group overlaps the one before).  partials: [gridDim.y][NB][gridDim.x].
+template <int NB, class T>
+__global__ void __launch_bounds__(256) loglik_logit_agg_kernel(int ng, int P, int ldg, int ncols, int cols_per_cta, int CC, int n_eval,
+                                                               const T* __restrict__ F, const double* __restrict__ Xg, const double* __restrict__ beta,
+                                                               const double* __restrict__ lc, const double* __restrict__ lys, const double* __restrict__ Tsum,
+                                                               double* __restrict__ partials) {
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rt = blockIdx.x / CC, cc = blockIdx.x % CC;
+    const int g = rt * 32 + lane;
+    const int j0 = cc * cols_per_cta, j1 = min(j0 + cols_per_cta, ncols);
+    const int e0 = min((int)blockIdx.y * NB, n_eval - NB);
+    double A[NB], acc[NB];
+#pragma unroll
+    for (int e = 0; e < NB; e++) { A[e] = 0.0; acc[e] = 0.0; }
+    if (g < ng) {
+        double lin[NB];
+#pragma unroll
+        for (int e = 0; e < NB; e++) {
+            const double* b = beta + (size_t)(e0 + e) * P;
+            double xb = 0.0;
+            for (int p = 0; p < P; p++) xb += Xg[g + (size_t)p * ldg] * b[p];      // same order as xb_kernel
+            A[e] = exp(xb);
+            lin[e] = (cc == 0 && warp == 0) ? lys[g] * ((double)ncols * xb + Tsum[g]) : 0.0;
+        }
+        const T* row = F + g;
+        int j = j0 + warp;
+        for (; j + 56 < j1; j += 64) {                 // 8 of this warp's columns per group
+            double f[8], pr[NB];
+#pragma unroll
+            for (int u = 0; u < 8; u++) f[u] = (double)row[(size_t)(j + 8 * u) * ldg];
+#pragma unroll
+            for (int e = 0; e < NB; e++) {
+                pr[e] = fma(A[e], f[0], 1.0);
+#pragma unroll
+                for (int u = 1; u < 8; u++) pr[e] *= fma(A[e], f[u], 1.0);
+            }
+#pragma unroll
+            for (int e = 0; e < NB; e++) {
+                if (pr[e] <= 1e300) acc[e] += log(pr[e]);
+                else {                                  // overflow (or NaN): term by term
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc[e] += log(fma(A[e], f[u], 1.0));
+                }
+            }
+        }
+        for (; j < j1; j += 8) {
+            const double f = (double)row[(size_t)j * ldg];
+#pragma unroll
+            for (int e = 0; e < NB; e++) acc[e] += log(fma(A[e], f, 1.0));
+        }
+        const double c = lc[g];
+#pragma unroll
+        for (int e = 0; e < NB; e++) acc[e] = lin[e] - c * acc[e];
+    }
+#pragma unroll
+    for (int e = 0; e < NB; e++) {
+        const double v = block_sum(acc[e], red);
+        if (threadIdx.x == 0) partials[((size_t)blockIdx.y * NB + e) * gridDim.x + blockIdx.x] = v;
+        __syncthreads();
+    }
+}
+
+// out[min(z NB, n_eval - NB) + e] = sum of the nb partials of (group z, evaluation e); block index = z NB + e
+__global__ void __launch_bounds__(256) agg_finish_groups_kernel(int nb, int NB, int n_eval, const double* __restrict__ partials, double* __restrict__ out) {
+    __shared__ double red[32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < nb; k += 256) s += partials[(size_t)blockIdx.x * nb + k];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) out[min((int)blockIdx.x / NB * NB, n_eval - NB) + (int)blockIdx.x % NB] = s;
+}
+
 // out[e] = sum of the nb partials of evaluation e, in a fixed order
 __global__ void __launch_bounds__(256) agg_finish_kernel(int nb, const double* __restrict__ partials, double* __restrict__ out) {
     __shared__ double red[32];
@@ -1096,8 +1173,12 @@ static int ensure_rowstats(gmb_model* mdl) {
             if (mdl->flink == 1) rowstat_kernel<1, double><<<gridg, blockg, smemg, ctx->stream>>>(ng, ldg, ncols, cpc, mdl->dzd, rp);
             else rowstat_kernel<7, double><<<gridg, blockg, smemg, ctx->stream>>>(ng, ldg, ncols, cpc, mdl->dzd, rp);
         }
-        mcnr_rows_kernel<<<(ng + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(ng, ldg, CCg, rp, sg, sg + ldg);
-        stat_expand_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ldn, ldg, a.dgid, sg, mdl->dstat);
+        if (mdl->flink == 3)      // binomial/logit: only T_g = sum_j zd_gj is used, by the aggregated rows themselves (loglik_logit_agg_kernel): dstat = [T2 | T] x ldg
+            mcnr_rows_kernel<<<(ng + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(ng, ldg, CCg, rp, mdl->dstat, mdl->dstat + ldg);
+        else {
+            mcnr_rows_kernel<<<(ng + 31) / 32, dim3(32, 32), 0, ctx->stream>>>(ng, ldg, CCg, rp, sg, sg + ldg);
+            stat_expand_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, ldn, ldg, a.dgid, sg, mdl->dstat);
+        }
         ctx->launches += 3;
         GMB_CUDA(cudaGetLastError());
         mdl->stat_valid = true; mdl->stat_cols = ncols;
@@ -1170,6 +1251,36 @@ static int launch_loglik_agg(gmb_model* mdl, const double* d_beta, int n_eval, d
     const int ng = a.ng, ldg = a.ldn, ncols = mdl->niter_local;
     if (ncols <= 0) { GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * n_eval, ctx->stream)); return GMB_OK; }
     const int RT = (ng + 31) / 32;
+    if (mdl->flink == 3 && mdl->f_valid) {
+        GMB_TRY(ensure_rowstats(mdl));                        // T_g
+        const bool f32 = mdl->prec == 32;
+        for (int e0 = 0; e0 < n_eval;) {
+            // batches of >= 8 evaluations: groups of 8 per pass over F; what is left (< 8): one evaluation per pass
+            const int NBk = (n_eval - e0 >= GMB_LOGLIK_NB) ? GMB_LOGLIK_NB : 1;
+            const int ne = NBk == 1 ? 1 : std::min(n_eval - e0, 8 * 32768);
+            const int groups = (ne + NBk - 1) / NBk;
+            int CC = (ctx->sms * 2 + RT * groups - 1) / (RT * groups);
+            const int max_cc = (ncols + 63) / 64;
+            if (CC > max_cc) CC = max_cc;
+            if (CC < 1) CC = 1;
+            const int cpc = round_up((ncols + CC - 1) / CC, 8);
+            CC = (ncols + cpc - 1) / cpc;
+            const int nb = RT * CC;
+            GMB_TRY(gmb_ctx_scratch(ctx, (size_t)nb * groups * NBk));
+            dim3 grid(nb, groups);
+            const double* bp = d_beta + (size_t)e0 * mdl->P;
+#define GMB_LFA(NBV, TT, FP) loglik_logit_agg_kernel<NBV, TT><<<grid, 256, 0, ctx->stream>>>(ng, mdl->P, ldg, ncols, cpc, CC, ne, FP, a.dX, bp, a.dlcnt, a.dlys, \
+                                                                                           mdl->dstat + ldg, ctx->d_scratch)
+            if (NBk == 1) { if (f32) GMB_LFA(1, float, mdl->dF32); else GMB_LFA(1, double, mdl->dF); }
+            else { if (f32) GMB_LFA(GMB_LOGLIK_NB, float, mdl->dF32); else GMB_LFA(GMB_LOGLIK_NB, double, mdl->dF); }
+#undef GMB_LFA
+            agg_finish_groups_kernel<<<groups * NBk, 256, 0, ctx->stream>>>(nb, NBk, ne, ctx->d_scratch, d_out + e0);
+            ctx->launches += 2;
+            e0 += ne;
+        }
+        GMB_CUDA(cudaGetLastError());
+        return GMB_OK;
+    }
     for (int e0 = 0; e0 < n_eval; e0 += 32768) {
         const int ne = std::min(32768, n_eval - e0);
         int CC = (ctx->sms * 4 + RT * ne - 1) / (RT * ne);
@@ -1236,7 +1347,7 @@ int gmb_launch_loglik_cols(gmb_model* mdl, const double* d_beta, double var_par,
     double* partials = ctx->d_scratch;
     unsigned int* counter = ctx->d_counter;   // zeroed at ctx creation and re-zeroed by the last CTA
     dim3 grid(RT, CC), block(TX, TY);
-    if (mdl->flink == 3 && mdl->f_valid && d_zd >= mdl->dzd && d_zd < mdl->dzd + (size_t)mdl->ldn * mdl->m_cap) {
+    if (mdl->flink == 3 && mdl->f_valid && !mdl->eagg && d_zd >= mdl->dzd && d_zd < mdl->dzd + (size_t)mdl->ldn * mdl->m_cap) {
         const double* d_f = mdl->dF + (d_zd - mdl->dzd);              // the same block of columns of the factor matrix
         loglik_logit_factor_kernel<double><<<grid, block, 0, ctx->stream>>>(n, mdl->P, mdl->ldn, ncols, cols_per_cta, d_f, mdl->dX, d_beta, mdl->dy,
                                                                    partials, counter, d_out);
@@ -1301,9 +1412,11 @@ int gmb_launch_loglik_multi(gmb_model* mdl, const double* d_beta, int n_eval, do
 int gmb_launch_build_factor(gmb_model* mdl, int ncols) {
     gmb_ctx* ctx = mdl->ctx;
     if (ncols <= 0) return GMB_OK;
-    dim3 grid(ncols, (mdl->ldn + 255) / 256);
-    if (mdl->prec == 32) build_factor_kernel<float><<<grid, 256, 0, ctx->stream>>>(mdl->n, mdl->ldn, ncols, mdl->dzd32, mdl->dy, mdl->dF32);
-    else build_factor_kernel<double><<<grid, 256, 0, ctx->stream>>>(mdl->n, mdl->ldn, ncols, mdl->dzd, mdl->dy, mdl->dF);
+    const int ne = mdl->eagg ? mdl->agg.ng : mdl->n, lde = mdl->eagg ? mdl->agg.ldn : mdl->ldn;
+    const double* ye = mdl->eagg ? nullptr : mdl->dy;
+    dim3 grid(ncols, (lde + 255) / 256);
+    if (mdl->prec == 32) build_factor_kernel<float><<<grid, 256, 0, ctx->stream>>>(ne, lde, ncols, mdl->dzd32, ye, mdl->dF32);
+    else build_factor_kernel<double><<<grid, 256, 0, ctx->stream>>>(ne, lde, ncols, mdl->dzd, ye, mdl->dF);
     ctx->launches++;
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;

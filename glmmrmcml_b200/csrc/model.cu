@@ -253,7 +253,7 @@ int gmb_model_build_zd(gmb_model* mdl) {
     }
     mdl->f_valid = false;
     mdl->stat_valid = false;
-    if (mdl->flink == 3 && (mdl->dF || mdl->dF32) && mdl->m_local > 0 && !mdl->eagg) {        // factor matrix of the binomial/logit E-step (estep.cu)
+    if (mdl->flink == 3 && (mdl->dF || mdl->dF32) && mdl->m_local > 0) {        // factor matrix of the binomial/logit E-step (estep.cu); aggregated rows: exp(zd)
         GMB_TRY(gmb_launch_build_factor(mdl, mdl->m_local));
         mdl->f_valid = true;
     }
