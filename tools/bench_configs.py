@@ -209,7 +209,7 @@ def run_config(name, env, size="full", oracle=None, check=True):
     byn = 8.0 * n * m_local + 8.0 * n * (P + 2)
     t_nr = env.max(timed(ctx, lambda: mdl.mcnr(beta, sig), reps=3, flush=True))
     out["mcnr"] = {"steps_per_s": 1e3 / t_nr,
-                   "roofline": {"bound": "hbm", "kernel": "mcnr_pass1_kernel + reductions (whole step incl. read-back)", "achieved": byn / t_nr / 1e6,
+                   "roofline": {"bound": "hbm", "kernel": "mcnr_tma_kernel + mcnr_tail_kernel (whole mcnr() call incl. x'beta and the read-back)", "achieved": byn / t_nr / 1e6,
                                 "peak": env.hbm, "unit": "GB/s", "frac": byn / t_nr / 1e6 / env.hbm, "bytes_per_launch": byn, "ms": t_nr}}
     # ---- K4 + K5: mvn_ll at a new theta (factorisation not cached) --------------------------------------------------------
     th1 = theta * (1 + 1e-4)
