@@ -209,6 +209,9 @@ struct gmb_cov {
     // inverses of the 64 x 64 diagonal blocks of the large blocks' factors (cov_large.cu), 64 x 64 col-major each
     double* d_linv = nullptr; size_t linv_doubles = 0;
     std::vector<long long> linv_off;     // per block: offset into d_linv (-1 for blocks that take the small / medium path)
+    // inverses of the 512 x 512 diagonal blocks of the large blocks' factors (cov_large.cu: formed beside the factorisation, used by the
+    // forward substitution), 512 x 512 col-major each
+    double* d_x512 = nullptr; std::vector<long long> x512_off;
     // Gram matrices of a model's samples (cov.cu: cov_ensure_gram), laid out like d_Lblk
     double* d_batch = nullptr; size_t batch_bytes = 0;     // work area of gmb_cov_mvn_ll_model_batch
     double* d_gram = nullptr; const gmb_model* gram_model = nullptr; unsigned long long gram_version = 0; int gram_cols = 0;
@@ -258,7 +261,7 @@ int gmb_cov_factor(gmb_cov* cv, const double* theta);   // builds + factorises a
 int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_out /* 1 double: sum_j sum_b l_b(u_j) */);
 int gmb_cov_gen_device(gmb_cov* cv, const double* theta, int chol, double* d_out, int ld);   // dense D(theta) or chol D on the device
 // cov_large.cu: in-place blocked Cholesky of a raw device matrix (see the definition)
-int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet);
+int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet, double* x512 = nullptr);
 
 // model.cu
 int gmb_model_reserve_samples(gmb_model* mdl, int m);

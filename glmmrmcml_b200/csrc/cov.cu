@@ -484,6 +484,7 @@ extern "C" void gmb_cov_destroy(gmb_cov* cv) {
     if (cv->dU) gmb_dfree(cv->ctx, cv->dU);
     if (cv->d_work) gmb_dfree(cv->ctx, cv->d_work);
     if (cv->d_linv) gmb_dfree(cv->ctx, cv->d_linv);
+    if (cv->d_x512) gmb_dfree(cv->ctx, cv->d_x512);
     if (cv->d_gram) gmb_dfree(cv->ctx, cv->d_gram);
     if (cv->d_gram_cls) gmb_dfree(cv->ctx, cv->d_gram_cls);
     gmb_dfree(cv->ctx, cv->d_cls_rep); gmb_dfree(cv->ctx, cv->d_cls_ptr); gmb_dfree(cv->ctx, cv->d_cls_mem);

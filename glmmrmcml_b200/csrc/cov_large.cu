@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ W
         for (int i = threadIdx.x; i < n; i += blockDim.x) acc += w[i] * w[i];
     }
     acc = block_sum(acc, red);
-    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+    if (threadIdx.x == 0) partials[blockIdx.x] += acc;      // slots are zeroed by the caller; launches that share a slot are ordered on one stream
 }
 
 __global__ void copy_rows_kernel(const double* __restrict__ U, int ldu, int start, int n, int ncols, double* __restrict__ W, int ldw) {
@@ -241,6 +241,19 @@ static int linv_buffer(gmb_cov* cv, int bi, double** out) {
     *out = cv->d_linv + cv->linv_off[bi];
     return GMB_OK;
 }
+static int x512_buffer(gmb_cov* cv, int bi, double** out) {
+    gmb_ctx* ctx = cv->ctx;
+    if (cv->x512_off.empty()) {
+        long long off = 0;
+        cv->x512_off.assign(cv->blocks.size(), -1);
+        for (size_t k = 0; k < cv->blocks.size(); k++)
+            if (cv->blocks[k].n > GMB_COV_SMALL_MAX) { cv->x512_off[k] = off; off += (long long)((cv->blocks[k].n + NBO - 1) / NBO) * NBO * NBO; }
+        GMB_CUDA(gmb_dmalloc(ctx, &cv->d_x512, sizeof(double) * (off > 0 ? off : 1)));
+    }
+    if (cv->x512_off[bi] < 0) return gmb_set_error(GMB_ESTATE, "block %d has no inverse-diagonal storage", bi);
+    *out = cv->d_x512 + cv->x512_off[bi];
+    return GMB_OK;
+}
 
 // the panel chain of the outer block [K0, Kend), confined to the block's own KB x KB diagonal part: per 128-column panel the diagonal factor +
 // inverse, the solve of the (at most 384) rows of the block below it and their rank-128 update (on the current stream).  With X != NULL also
@@ -261,8 +274,8 @@ static int chol_diag_chain(gmb_ctx* ctx, double* A, int ld, int K0, int Kend, in
             GMB_CUDA(cudaMemcpy2DAsync(X + j0 + (size_t)j0 * NBO, sizeof(double) * NBO, Li, sizeof(double) * NB, sizeof(double) * NB, NB,
                                        cudaMemcpyDeviceToDevice, S3));
             if (j0 > 0) {
-                GMB_TRY(gmb_dgemm(ctx, 0, 0, NB, j0, j0, 1.0, A + k0 + (size_t)K0 * ld, ld, X, NBO, 0.0, T, NB));
-                GMB_TRY(gmb_dgemm(ctx, 0, 0, NB, j0, NB, -1.0, Li, NB, T, NB, 0.0, X + j0, NBO));
+                GMB_TRY(gmb_dgemm(ctx, 0, 0, kb, j0, j0, 1.0, A + k0 + (size_t)K0 * ld, ld, X, NBO, 0.0, T, NB));
+                GMB_TRY(gmb_dgemm(ctx, 0, 0, kb, j0, kb, -1.0, Li, NB, T, NB, 0.0, X + j0, NBO));
             }
         }
         const int rows_in = Kend - (k0 + kb);
@@ -293,25 +306,28 @@ static int g_chol_reserve = [] { const char* e = getenv("GMB_CHOL_RESERVE_SMS");
 //   M: A[next diagonal block] -= W_top W_top^T (10 tiles), which releases chain(K + 1) on P
 //   M: rest of the trailing update, one PERSISTENT launch over all remaining lower tiles on (SMs - reserve) CTAs, so that chain(K + 1)
 //      always finds a free SM: the chain is hidden under the update as long as the update is the longer of the two.
-int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet) {
+int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet, double* x512) {
     cudaStream_t M = ctx->stream, P = ctx->stream2;
     const int nouter = (n + NBO - 1) / NBO;
     const bool tma = gmb_gemm_tma_available();
     double *Wp = nullptr, *Xall = nullptr, *T = nullptr;
     const int ldw = ld;
-    if (nouter > 1) {
-        if (!tma) return gmb_set_error(GMB_ECUDA, "the blocked Cholesky needs cuTensorMapEncodeTiled (TMA GEMM) for n > %d", NBO);
-        const size_t need = (size_t)ldw * NBO + (size_t)(nouter - 1) * NBO * NBO + (size_t)NB * NBO;
+    // x512 != NULL: the caller keeps the inverses of ALL 512 x 512 diagonal blocks (the forward substitution multiplies with them);
+    // otherwise only those the factorisation itself needs (all but the last) live in the scratch area
+    const int nx = x512 ? nouter : nouter - 1;
+    if (nouter > 1 || x512) {
+        if (nouter > 1 && !tma) return gmb_set_error(GMB_ECUDA, "the blocked Cholesky needs cuTensorMapEncodeTiled (TMA GEMM) for n > %d", NBO);
+        const size_t need = (size_t)ldw * NBO + (x512 ? 0 : (size_t)nx * NBO * NBO) + (size_t)NB * NBO;
         GMB_TRY(gmb_ctx_scratch(ctx, need));
-        Wp = ctx->d_scratch; Xall = Wp + (size_t)ldw * NBO; T = Xall + (size_t)(nouter - 1) * NBO * NBO;
-        GMB_CUDA(cudaMemsetAsync(Xall, 0, sizeof(double) * (size_t)(nouter - 1) * NBO * NBO, M));
+        Wp = ctx->d_scratch; Xall = x512 ? x512 : Wp + (size_t)ldw * NBO; T = Wp + (size_t)ldw * NBO + (x512 ? 0 : (size_t)nx * NBO * NBO);
+        GMB_CUDA(cudaMemsetAsync(Xall, 0, sizeof(double) * (size_t)nx * NBO * NBO, M));
     }
     int max_ctas = g_chol_reserve < 0 ? 0 : ctx->sms - g_chol_reserve;          // < 0: one CTA per tile (not persistent)
     if (g_chol_reserve >= 0 && max_ctas < 1) max_ctas = 1;
     GMB_CUDA(cudaEventRecord(ctx->evn, M));                                     // everything issued so far (the block build) precedes the first panel
     for (int K0 = 0, ko = 0; K0 < n; K0 += NBO, ko++) {
         const int Kend = K0 + NBO < n ? K0 + NBO : n, KB = Kend - K0;
-        double* X = (Kend < n) ? Xall + (size_t)ko * NBO * NBO : nullptr;
+        double* X = (ko < nx) ? Xall + (size_t)ko * NBO * NBO : nullptr;
         {
             StreamSwap sw(ctx, P);
             GMB_CUDA(cudaStreamWaitEvent(P, ctx->evn, 0));
@@ -334,7 +350,7 @@ int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int
         GMB_CUDA(cudaMemcpy2DAsync(Pn, sizeof(double) * ld, Wp, sizeof(double) * ldw, sizeof(double) * Mt, KB, cudaMemcpyDeviceToDevice, ctx->stream3));
         if (Mt > nd) GMB_TRY(gmb_dsyrk_lower_rest(ctx, Mt, KB, Wp, ldw, Ct, ld, nd, max_ctas)); // everything else, under chain(K + 1)
     }
-    if (nouter > 1) {                                                            // the last panel copy
+    if (nouter > 1 || x512) {                                                    // the last panel copy / the last block's inverse
         GMB_CUDA(cudaEventRecord(ctx->evx, ctx->stream3));
         GMB_CUDA(cudaStreamWaitEvent(M, ctx->evx, 0));
     }
@@ -353,10 +369,12 @@ int gmb_cov_factor_large(gmb_cov* cv, int bi) {
     double* A = cv->d_Lblk + b.l0;
     double* linv = nullptr;
     GMB_TRY(linv_buffer(cv, bi, &linv));
+    double* x512 = nullptr;
+    GMB_TRY(x512_buffer(cv, bi, &x512));
     dim3 blk(32, 8), grd((n + 31) / 32, (n + 7) / 8);
     build_block_kernel<<<grd, blk, 0, ctx->stream>>>(b, cv->d_fns, cv->d_data, cv->d_theta, A, ld);
     ctx->launches++;
-    return gmb_chol_blocked(ctx, A, ld, n, b.start, cv->d_status, linv, cv->d_logdet + bi);
+    return gmb_chol_blocked(ctx, A, ld, n, b.start, cv->d_status, linv, cv->d_logdet + bi, x512);
 }
 
 // d_partial: 64 doubles (zeroed by the caller); receives partial sums of ||L^{-1} u_j||^2 over the columns
@@ -369,56 +387,50 @@ int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols
     size_t max_cols = ((size_t)1 << 28) / (size_t)ldw;
     if (max_cols < 128) max_cols = 128;
     int chunk = ncols < (int)max_cols ? ncols : (int)max_cols;
-    size_t need = (size_t)ldw * chunk;
+    size_t need = (size_t)(ldw + 2 * NBO) * chunk;
     if (need > cv->work_doubles) {
         if (cv->d_work) { GMB_CUDA(cudaStreamSynchronize(ctx->stream)); gmb_dfree(ctx, cv->d_work); cv->d_work = nullptr; }
         GMB_CUDA(gmb_dmalloc(ctx, &cv->d_work, need * sizeof(double)));
         cv->work_doubles = need;
     }
     double* W = cv->d_work;
-    double* linv = nullptr;
-    GMB_TRY(linv_buffer(cv, bi, &linv));
+    double* Y[2] = {W + (size_t)ldw * chunk, W + (size_t)(ldw + NBO) * chunk};       // solved rows of the current outer block, double buffered (ld NBO)
+    double* x512 = nullptr;
+    GMB_TRY(x512_buffer(cv, bi, &x512));
     int nchunks = (ncols + chunk - 1) / chunk;
+    if (nchunks > 64) return gmb_set_error(GMB_EINVAL, "too many column chunks for a large covariance block");
     int slots = 64 / nchunks; if (slots < 1) slots = 1;
     cudaStream_t M = ctx->stream, P = ctx->stream2;
     for (int c = 0; c < nchunks; c++) {
         int c0 = c * chunk, nc = ncols - c0 < chunk ? ncols - c0 : chunk;
+        const int s0 = (c * slots) % 64;
         copy_rows_kernel<<<dim3(nc, (ldw + 255) / 256), 256, 0, ctx->stream>>>(dU + (size_t)c0 * ldu, ldu, b.start, n, nc, W, ldw);
         ctx->launches++;
-        // blocked forward substitution with the same two levels and the same look-ahead as the factorisation: 128-row diagonal solves (GEMMs
-        // with the inverted diagonal blocks) and rank-128 updates inside an outer block of 512 rows on the side stream; per outer block one
-        // rank-512 update of the rows below on the main stream — its first 512 rows (all the next outer block needs) first
+        // Blocked forward substitution on outer blocks of 512 rows.  The factorisation left the inverse X_K of every 512 x 512 diagonal block of L
+        // (gmb_chol_blocked), so a block's rows are solved by ONE triangular product Y_K = X_K W[K, :] (tri = 1 skips the zero k tiles) on the side
+        // stream, their sum of squares is taken there, and the rows below receive one rank-512 update W[below, :] -= L[below, K] Y_K on the main
+        // stream — the next block's 512 rows first, which releases Y_{K+1} underneath the rest of the update.  Round 1-2a ran four diagonal solves and
+        // three small updates per outer block instead of the one product.
         GMB_CUDA(cudaEventRecord(ctx->evn, M));
-        for (int K0 = 0; K0 < n; K0 += NBO) {
+        for (int K0 = 0, ko = 0; K0 < n; K0 += NBO, ko++) {
             const int Kend = K0 + NBO < n ? K0 + NBO : n, KB = Kend - K0;
+            double* Yk = Y[ko & 1];
             {
                 StreamSwap sw(ctx, P);
                 GMB_CUDA(cudaStreamWaitEvent(P, ctx->evn, 0));
-                for (int k0 = K0; k0 < Kend; k0 += NB) {
-                    const int kb = Kend - k0 < NB ? Kend - k0 : NB;
-                    // diagonal solve W[k0:k0+kb, :] <- L_kk^{-1} W[k0:k0+kb, :], in place
-                    GMB_TRY(gmb_dgemm_colpanel(ctx, kb, nc, kb, 1.0, linv + (size_t)(k0 / NB) * NB * NB, NB, W + k0, ldw, W + k0, ldw));
-                    const int rows_in = Kend - (k0 + kb);
-                    if (rows_in > 0)   // W[k0+kb:Kend, :] -= L[k0+kb:Kend, k0:k0+kb] W[k0:k0+kb, :]
-                        GMB_TRY(gmb_dgemm(ctx, 0, 0, rows_in, nc, kb, -1.0, A + (k0 + kb) + (size_t)k0 * ld, ld, W + k0, ldw, 1.0, W + k0 + kb, ldw));
-                }
+                GMB_TRY(gmb_dgemm_tri(ctx, 0, 0, KB, nc, KB, 1.0, x512 + (size_t)ko * NBO * NBO, NBO, W + K0, ldw, 0.0, Yk, NBO, 1));
+                sumsq_kernel<<<slots, 256, 0, ctx->stream>>>(Yk, NBO, KB, nc, d_partial + s0);
+                ctx->launches++;
                 GMB_CUDA(cudaEventRecord(ctx->evp, P));
             }
             GMB_CUDA(cudaStreamWaitEvent(M, ctx->evp, 0));
             if (Kend >= n) break;
-            const int nar = n - Kend < NBO ? n - Kend : NBO;          // W[Kend:Kend+nar, :] -= L[Kend:Kend+nar, K0:Kend] W[K0:Kend, :]
-            GMB_TRY(gmb_dgemm(ctx, 0, 0, nar, nc, KB, -1.0, A + Kend + (size_t)K0 * ld, ld, W + K0, ldw, 1.0, W + Kend, ldw));
+            const int nar = n - Kend < NBO ? n - Kend : NBO;          // W[Kend:Kend+nar, :] -= L[Kend:Kend+nar, K0:Kend] Y_K
+            GMB_TRY(gmb_dgemm(ctx, 0, 0, nar, nc, KB, -1.0, A + Kend + (size_t)K0 * ld, ld, Yk, NBO, 1.0, W + Kend, ldw));
             GMB_CUDA(cudaEventRecord(ctx->evn, M));
             const int rest = n - Kend - nar;
             if (rest > 0)
-                GMB_TRY(gmb_dgemm(ctx, 0, 0, rest, nc, KB, -1.0, A + Kend + nar + (size_t)K0 * ld, ld, W + K0, ldw, 1.0, W + Kend + nar, ldw));
-        }
-        if (c < 64) {
-            int s0 = (c * slots) % 64;
-            sumsq_kernel<<<slots, 256, 0, ctx->stream>>>(W, ldw, n, nc, d_partial + s0);
-            ctx->launches++;
-        } else {
-            return gmb_set_error(GMB_EINVAL, "too many column chunks for a large covariance block");
+                GMB_TRY(gmb_dgemm(ctx, 0, 0, rest, nc, KB, -1.0, A + Kend + nar + (size_t)K0 * ld, ld, Yk, NBO, 1.0, W + Kend + nar, ldw));
         }
     }
     GMB_CUDA(cudaGetLastError());
