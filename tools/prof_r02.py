@@ -22,12 +22,20 @@ if what == "hmc":
 elif what == "estep":
     cfg = synth.config2(m=8)
     U = np.asfortranarray(cfg["L"] @ rng.standard_normal((cfg["Q"], 250_000)))
+    g.estep_set_row_aggregation(False)           # the per-observation streaming kernels (what C3-C5 run): 1 GB per pass
     for prec in ("fp64", "fp32"):
         mdl = g.Model(ctx, cfg["X"], cfg["Z"], cfg["y"], "binomial", "logit", precision=prec)
         mdl.set_u(U)
         for rep in range(2):
             mdl.log_likelihood(cfg["beta"] * (1 + 0.01 * rep), 1.0); mdl.mcnr(cfg["beta"], 1.0)
         mdl.close()
+    g.estep_set_row_aggregation(True)            # C2's default: the same evaluations on its 50 distinct rows (100 MB), 64 evaluations per batch
+    mdl = g.Model(ctx, cfg["X"], cfg["Z"], cfg["y"], "binomial", "logit")
+    mdl.set_u(U)
+    B = np.asfortranarray(cfg["beta"][:, None] * (1 + 1e-3 * np.arange(64))[None, :])
+    for rep in range(2):
+        mdl.log_likelihood_batch(B, np.ones(64)); mdl.mcnr(cfg["beta"], 1.0)
+    mdl.close()
 elif what == "gemm":
     n, Q, m = 8192, 4096, 16384
     X = np.asfortranarray(np.ones((n, 1))); Z = np.asfortranarray(rng.standard_normal((n, Q)) / np.sqrt(Q))
