@@ -999,7 +999,7 @@ __global__ void __launch_bounds__(256) loglik_agg_kernel(int ng, int P, int ldg,
 // running along a ROW (the weight c_g factors out of the log), on ng instead of n rows.  NB evaluations share each load; blockIdx.y = group of NB
 // evaluations (a short last group overlaps the one before).  partials: [gridDim.y][NB][gridDim.x].
 template <int NB, class T>
-__global__ void __launch_bounds__(256) loglik_logit_agg_kernel(int ng, int P, int ldg, int ncols, int cols_per_cta, int CC, int n_eval,
+__global__ void __launch_bounds__(256, 2) loglik_logit_agg_kernel(int ng, int P, int ldg, int ncols, int cols_per_cta, int CC, int n_eval,
                                                                const T* __restrict__ F, const double* __restrict__ Xg, const double* __restrict__ beta,
                                                                const double* __restrict__ lc, const double* __restrict__ lys, const double* __restrict__ Tsum,
                                                                double* __restrict__ partials) {
@@ -1013,33 +1013,36 @@ __global__ void __launch_bounds__(256) loglik_logit_agg_kernel(int ng, int P, in
 #pragma unroll
     for (int e = 0; e < NB; e++) { A[e] = 0.0; acc[e] = 0.0; }
     if (g < ng) {
-        double lin[NB];
 #pragma unroll
         for (int e = 0; e < NB; e++) {
             const double* b = beta + (size_t)(e0 + e) * P;
             double xb = 0.0;
             for (int p = 0; p < P; p++) xb += Xg[g + (size_t)p * ldg] * b[p];      // same order as xb_kernel
             A[e] = exp(xb);
-            lin[e] = (cc == 0 && warp == 0) ? lys[g] * ((double)ncols * xb + Tsum[g]) : 0.0;
         }
         const T* row = F + g;
         int j = j0 + warp;
-        for (; j + 56 < j1; j += 64) {                 // 8 of this warp's columns per group
-            double f[8], pr[NB];
+        for (; j + 120 < j1; j += 128) {               // 16 of this warp's columns per group: one log per 16 factors
+            double pr[NB];
 #pragma unroll
-            for (int u = 0; u < 8; u++) f[u] = (double)row[(size_t)(j + 8 * u) * ldg];
+            for (int e = 0; e < NB; e++) pr[e] = 1.0;
 #pragma unroll
-            for (int e = 0; e < NB; e++) {
-                pr[e] = fma(A[e], f[0], 1.0);
+            for (int h = 0; h < 2; h++) {
+                double f[8];
 #pragma unroll
-                for (int u = 1; u < 8; u++) pr[e] *= fma(A[e], f[u], 1.0);
+                for (int u = 0; u < 8; u++) f[u] = (double)row[(size_t)(j + 8 * (8 * h + u)) * ldg];
+#pragma unroll
+                for (int e = 0; e < NB; e++) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) pr[e] *= fma(A[e], f[u], 1.0);
+                }
             }
 #pragma unroll
             for (int e = 0; e < NB; e++) {
                 if (pr[e] <= 1e300) acc[e] += log(pr[e]);
-                else {                                  // overflow (or NaN): term by term
-#pragma unroll
-                    for (int u = 0; u < 8; u++) acc[e] += log(fma(A[e], f[u], 1.0));
+                else {                                  // overflow (or NaN): term by term, from memory again
+#pragma unroll 1
+                    for (int u = 0; u < 16; u++) acc[e] += log(fma(A[e], (double)row[(size_t)(j + 8 * u) * ldg], 1.0));
                 }
             }
         }
@@ -1049,8 +1052,17 @@ __global__ void __launch_bounds__(256) loglik_logit_agg_kernel(int ng, int P, in
             for (int e = 0; e < NB; e++) acc[e] += log(fma(A[e], f, 1.0));
         }
         const double c = lc[g];
+        const bool first = (cc == 0 && warp == 0);             // the linear term n1 (m xb + T) once per row
+        const double n1 = first ? lys[g] : 0.0, ts = first ? Tsum[g] : 0.0;
 #pragma unroll
-        for (int e = 0; e < NB; e++) acc[e] = lin[e] - c * acc[e];
+        for (int e = 0; e < NB; e++) {
+            double xb = 0.0;
+            if (first) {
+                const double* b = beta + (size_t)(e0 + e) * P;
+                for (int p = 0; p < P; p++) xb += Xg[g + (size_t)p * ldg] * b[p];
+            }
+            acc[e] = n1 * ((double)ncols * xb + ts) - c * acc[e];
+        }
     }
 #pragma unroll
     for (int e = 0; e < NB; e++) {
@@ -1259,11 +1271,11 @@ static int launch_loglik_agg(gmb_model* mdl, const double* d_beta, int n_eval, d
             const int NBk = (n_eval - e0 >= GMB_LOGLIK_NB) ? GMB_LOGLIK_NB : 1;
             const int ne = NBk == 1 ? 1 : std::min(n_eval - e0, 8 * 32768);
             const int groups = (ne + NBk - 1) / NBk;
-            int CC = (ctx->sms * 2 + RT * groups - 1) / (RT * groups);
+            int CC = (ctx->sms * 2) / (RT * groups);            // one full wave of 2 CTAs per SM (rounded down: no tail wave)
             const int max_cc = (ncols + 63) / 64;
             if (CC > max_cc) CC = max_cc;
             if (CC < 1) CC = 1;
-            const int cpc = round_up((ncols + CC - 1) / CC, 8);
+            const int cpc = round_up((ncols + CC - 1) / CC, 128);      // whole groups of 16 columns per warp
             CC = (ncols + cpc - 1) / cpc;
             const int nb = RT * CC;
             GMB_TRY(gmb_ctx_scratch(ctx, (size_t)nb * groups * NBk));

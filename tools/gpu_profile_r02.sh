@@ -26,7 +26,7 @@ with open('gpurun_out/profiles_out/r02_launches_bench.csv', 'w') as f:
     for k, v in sorted(t.items(), key=lambda kv: -kv[1]):
         f.write('"%s",%d,%.1f,%.2f,%.4f\n' % (k, n[k], v, v / n[k], v / tot))
 PY
-for spec in "hmc:hmc_lane:2" "estep:loglik_logit_factor_kernel|mcnr_tma_kernel|mcnr_tail|loglik_logit_agg_kernel|mcnr_agg_kernel:12" "gemm:dgemm_tma_kernel|sgemm3_tf32_kernel|split_tf32:6" "chol:potrf_diag_kernel:1" "chol:dgemm_tma_kernel:4"; do
+for spec in "hmc:hmc_lane:2" "estep:loglik_logit_factor_kernel|mcnr_tma_kernel|mcnr_tail:12" "estep:loglik_logit_agg_kernel|mcnr_agg_kernel|agg_finish:6" "gemm:dgemm_tma_kernel|sgemm3_tf32_kernel|split_tf32:6" "chol:potrf_diag_kernel:1" "chol:dgemm_tma_kernel:4"; do
     IFS=: read what rx cnt <<< "$spec"
     tag=${what}_$(echo $rx | cut -c1-12 | tr '|' '_')
     python tools/prof_r02.py $what > gpurun_out/p_plain_$what.log 2>&1 &&

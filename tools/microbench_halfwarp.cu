@@ -21,13 +21,16 @@ __global__ void k(int active_lanes, int iters, double* out, long long* cyc) {
 int main() {
     double* out; long long* cyc; cudaMalloc(&out, 8 * 32 * 2048); cudaMalloc(&cyc, 8 * 2048);
     const int iters = 20000;
-    for (int wps = 1; wps <= 2; wps++)
-        for (int lanes : {32, 16, 8}) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int wps : {1, 2, 3, 4, 8})
+        for (int lanes : {32, 16}) {
             const int blocks = 148 * 4 * wps;
             k<<<blocks, 32>>>(lanes, 100, out, cyc); cudaDeviceSynchronize();
-            k<<<blocks, 32>>>(lanes, iters, out, cyc); cudaDeviceSynchronize();
+            cudaEventRecord(e0); k<<<blocks, 32>>>(lanes, iters, out, cyc); cudaEventRecord(e1); cudaDeviceSynchronize();
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
             long long h[8]; cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
-            printf("warps per scheduler %d, active lanes %2d: %.2f cycles per warp-DFMA (block 0: %lld cycles for %d DFMA)\n", wps, lanes, (double)h[0] / (8.0 * iters), h[0], 8 * iters);
+            printf("warps per scheduler %d, active lanes %2d: %.2f cycles per warp-DFMA in block 0; kernel %.3f ms = %.1f TFLOP/s over all warps (32 lanes counted)\n", wps, lanes,
+                   (double)h[0] / (8.0 * iters), ms, (double)blocks * 32 * 8.0 * iters * 2 / (ms * 1e-3) / 1e12);
         }
     return 0;
 }
