@@ -1092,7 +1092,8 @@ __global__ void __launch_bounds__(256) agg_finish_kernel(int nb, const double* _
 
 // MCNR pass 1 on the aggregated rows; writes the same partial sums as mcnr_pass1_kernel: rowpart[cc][2][ldg] (sum_j of c w and c wu per row),
 // colpart[rt][2][ncols] (sum over the tile's rows of sum_i r_i and sum_i r_i^2 per column), rt = tiles of 32 rows
-template <int FL, class T>
+// FACTOR (binomial/logit): zd points to F = exp(zd) and e^eta = exp(xb) F — a multiply instead of the table exp
+template <int FL, class T, bool FACTOR>
 __global__ void __launch_bounds__(256) mcnr_agg_kernel(int ng, int ldg, int ncols, int cols_per_cta, const T* __restrict__ zd,
                                                        const double* __restrict__ xb /* per observation */, const int* __restrict__ rep,
                                                        const double* __restrict__ cnt, const double* __restrict__ eys, const double* __restrict__ ess,
@@ -1107,11 +1108,19 @@ __global__ void __launch_bounds__(256) mcnr_agg_kernel(int ng, int ldg, int ncol
     const bool ok = g < ng;
     const double c = ok ? cnt[g] : 0.0;
     const double ybar = ok ? eys[g] / c : 0.0, sq = ok ? ess[g] : 0.0, xbg = ok ? xb[rep[g]] : 0.0;
+    const double Ag = FACTOR ? exp(xbg) : 0.0;
     const T* col = zd + (ok ? g : 0);
     double wacc = 0.0, sacc = 0.0;
     for (int j = j0 + warp; j < j1; j += 8) {
         double w = 0.0, wu = 0.0, r = 0.0;
-        if (ok) mcnr_terms<FL>(ybar, xbg + (double)col[(size_t)j * ldg], inv_phi, stab, w, wu, r);
+        if (FACTOR) {
+            if (ok) {                                    // p = e / (1 + e), p (1 - p) = e / (1 + e)^2 with e = A F (as mcnr_terms<3>)
+                const double e = Ag * (double)col[(size_t)j * ldg];
+                const double rc = dev_rcp_fast(1.0 + e);
+                const double p = e * rc;
+                r = ybar - p; w = p * rc; wu = r;
+            }
+        } else if (ok) mcnr_terms<FL>(ybar, xbg + (double)col[(size_t)j * ldg], inv_phi, stab, w, wu, r);
         wacc += w; sacc += wu;
         const double sr = warp_sum(c * r), sr2 = warp_sum(ok ? fma(c * r, r, sq) : 0.0);
         if (lane == 0) {
@@ -1473,9 +1482,15 @@ int gmb_launch_mcnr(gmb_model* mdl, const double* d_xb, double var_par, double* 
         rowpart = ctx->d_scratch; colpart = rowpart + (size_t)CCg * 2 * ldg;
         double* part = colpart + (size_t)RTC * 2 * ncols;
         dim3 gridg(RTC, CCg);
-#define GMB_NRA(F, TT, ZD) mcnr_agg_kernel<F, TT><<<gridg, 256, 0, ctx->stream>>>(ng, ldg, ncols, cpc, ZD, d_xb, a.drep, a.dcnt, a.deys, a.dess, inv_phi, rowpart, colpart)
-        if (mdl->prec == 32) { if (fl == 1) GMB_NRA(1, float, mdl->dzd32); else if (fl == 3) GMB_NRA(3, float, mdl->dzd32); else GMB_NRA(7, float, mdl->dzd32); }
-        else { if (fl == 1) GMB_NRA(1, double, mdl->dzd); else if (fl == 3) GMB_NRA(3, double, mdl->dzd); else GMB_NRA(7, double, mdl->dzd); }
+#define GMB_NRA(F, TT, FAC, ZD) mcnr_agg_kernel<F, TT, FAC><<<gridg, 256, 0, ctx->stream>>>(ng, ldg, ncols, cpc, ZD, d_xb, a.drep, a.dcnt, a.deys, a.dess, inv_phi, rowpart, colpart)
+        const bool fac = fl == 3 && mdl->f_valid;
+        if (mdl->prec == 32) {
+            if (fl == 1) GMB_NRA(1, float, false, mdl->dzd32); else if (fac) GMB_NRA(3, float, true, mdl->dF32); else if (fl == 3) GMB_NRA(3, float, false, mdl->dzd32);
+            else GMB_NRA(7, float, false, mdl->dzd32);
+        } else {
+            if (fl == 1) GMB_NRA(1, double, false, mdl->dzd); else if (fac) GMB_NRA(3, double, true, mdl->dF); else if (fl == 3) GMB_NRA(3, double, false, mdl->dzd);
+            else GMB_NRA(7, double, false, mdl->dzd);
+        }
 #undef GMB_NRA
         mcnr_tail_kernel<<<8 * RTg + NSIG2, 256, 0, ctx->stream>>>(ng, n, P, ldg, ncols, RTg, RTC, CCg, NSIG2, a.dX, rowpart, colpart, part, ctx->d_counter, d_out);
         ctx->launches += 2;
