@@ -92,7 +92,7 @@ constexpr int RASTER_GROUP = 16;
 
 template <bool A_KCONT, bool B_KCONT, class Epi>
 __global__ void __launch_bounds__(THREADS, 1) dgemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                               int M, int N, int K, Epi epi, int tri_arg, int ptiles) {
+                                                               int M, int N, int K, Epi epi, int tri_arg, int ptiles, unsigned int* queue) {
     constexpr int MT = 8, NT = 4;                          // warp tile 64 x 32: m8n8 fragment tiles per warp
     extern __shared__ unsigned char smraw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smraw) + 1023) & ~(uintptr_t)1023);
@@ -107,15 +107,35 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_tma_kernel(const __grid_cons
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // ptiles > 0 (symmetric rank-k update only): PERSISTENT — gridDim.x CTAs walk the ptiles tile pairs with stride gridDim.x, the operand ring
-    // and its barrier phases running on across tiles (it_base).  The blocked Cholesky launches its trailing update on fewer CTAs than SMs so
-    // that the panel chain of the next outer block (high-priority side stream, tiny kernels) finds a free SM at once instead of waiting for a
-    // 128 x 128 x 512 tile (~70 us) to retire.
+    // ptiles > 0: PERSISTENT — gridDim.x CTAs walk ptiles tiles, the operand ring and its barrier phases running on across tiles (it_base).
+    //  * symmetric rank-k update (tri & 0xff == 3): static stride gridDim.x over the lower tile pairs.  The blocked Cholesky launches its trailing
+    //    update on fewer CTAs than SMs so that the panel chain of the next outer block (high-priority side stream, tiny kernels) finds a free SM
+    //    at once instead of waiting for a 128 x 128 x 512 tile (~70 us) to retire.
+    //  * triangular operand (tri = 1 / 2) with queue != NULL: tiles are numbered HEAVIEST FIRST (longest k range) and handed out through an atomic
+    //    counter — a CTA takes the next tile when it is done (longest-processing-time-first): 320 unequal tiles on 148 SMs (the two contractions per
+    //    leapfrog step of config C5) finish in ~1.1 x the average load instead of 3 rounds of the longest tile.
+    __shared__ int s_next;
     int it_base = 0;
-    for (int tile = blockIdx.x; ptiles == 0 || tile < ptiles; tile += gridDim.x) {
+    const int TM = (M + BM - 1) / BM, TN = (N + BN - 1) / BN;
+    for (int tile = blockIdx.x, first_tile = 1;; first_tile = 0) {
+    if (!first_tile) {
+        if (ptiles == 0) break;
+        if (queue) {
+            __syncthreads();
+            if (tid == 0) s_next = (int)gridDim.x + (int)atomicAdd(queue, 1u);
+            __syncthreads();
+            tile = s_next;
+        } else tile += gridDim.x;
+    }
+    if (ptiles > 0 && tile >= ptiles) break;
     int tri = tri_arg;
     int bx = (tri == 1) ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, by = (tri == 4) ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
-    if (tri == 0 && gridDim.x > RASTER_GROUP) {
+    if (ptiles > 0 && (tri & 0xff) != 3) {                 // persistent, plain tile grid: heaviest tiles first
+        if (tri == 1) { bx = TM - 1 - tile / TN; by = tile % TN; }
+        else if (tri == 2) { bx = tile / TN; by = tile % TN; }
+        else if (tri == 4) { by = TN - 1 - tile / TM; bx = tile % TM; }
+        else { bx = tile % TM; by = tile / TM; }
+    } else if (tri == 0 && gridDim.x > RASTER_GROUP) {
         // grouped rasterisation: the CTAs resident at one time (one per SM, launched in linear order) cover RASTER_GROUP tile rows x ~9 tile
         // columns instead of a full column of tiles x ~2, so a wave pulls (16 + 9) operand panels through L2 instead of (M/128 + 2): at
         // 8192 x 16384 x 4096 the DRAM reads fall from 19x the algorithmic bytes (ncu, profiles/r02_ncu_gemm_dgemm_tma_ke.txt) to ~3x
@@ -140,10 +160,10 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_tma_kernel(const __grid_cons
     // tri = 4: B is triangular, B(n, k) = 0 for k > n (the transposed inverse of a lower factor: a triangular solve as a product)
     const int kt1 = (tri == 1) ? min(KT, (m0 + BM + BK - 1) / BK) : (tri == 4) ? min(KT, (n0 + BN + BK - 1) / BK) : KT;
 
-    if (ptiles == 0) {   // skip tiles whose columns are all inactive (chains that finished their trajectory)
+    if ((tri_arg & 0xff) != 3) {   // skip tiles whose columns are all inactive (chains that finished their trajectory)
         int act = 0;
         for (int c = tid; c < BN; c += THREADS) if (n0 + c < N && epi.column_active(n0 + c)) act = 1;
-        if (!__syncthreads_or(act)) return;
+        if (!__syncthreads_or(act)) { if (ptiles == 0) return; else continue; }
     }
 
     // ---- producer: lane 0 of warp 0 feeds the ring, STAGES - 1 k tiles ahead of the arithmetic ----
@@ -242,9 +262,12 @@ __global__ void __launch_bounds__(THREADS, 1) dgemm_tma_kernel(const __grid_cons
             if (n < N) epi.colsum_out(bx, n, scol[c] + scol[BN + c]);
         }
     }
-    if (ptiles == 0) break;
     it_base += max(kt1 - kt0, 0);
     }   // tile loop
+    if (queue && tid == 0) {                                 // the last CTA to leave re-arms the queue for the next launch
+        __threadfence();
+        if (atomicAdd(queue + 1, 1u) == gridDim.x - 1) { queue[0] = 0u; queue[1] = 0u; }
+    }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -278,7 +301,7 @@ inline int make_map(CUtensorMap* tm, const void* ptr, int rows, int cols, int ld
 inline int syrk_tiles_rmin(int T, int c0, int c1, int rmin) { int c = 0; for (int tj = c0; tj < c1 && tj < T; tj++) c += T - (tj > rmin ? tj : rmin); return c; }
 
 template <bool AK, bool BKC, class Epi>
-int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi, int tri, int max_ctas = 0) {
+int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const double* B, int ldb, const Epi& epi, int tri, int max_ctas = 0, bool dynamic = false) {
     CUtensorMap tmA, tmB;
     // contiguous dimension first: k for a K-contiguous operand (box 16 k x 128 rows), m / n otherwise (box 16 rows x BK k)
     if (AK) GMB_TRY(make_map(&tmA, A, K, M, lda, 16, 128)); else GMB_TRY(make_map(&tmA, A, M, K, lda, 16, BK));
@@ -296,8 +319,14 @@ int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const do
         if (tiles <= 0) return GMB_OK;
         grid = dim3(tiles, 1);
         if (max_ctas > 0) { ptiles = tiles; grid = dim3(tiles < max_ctas ? tiles : max_ctas, 1); }
+    } else if (max_ctas > 0) {
+        ptiles = (int)(grid.x * grid.y);
+        grid = dim3(ptiles < max_ctas ? ptiles : max_ctas, 1);
     }
-    kern<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, M, N, K, epi, tri, ptiles);
+    // tile queue of a dynamic launch: one pair of counters per stream of the context (zero between launches)
+    unsigned int* queue = nullptr;
+    if (dynamic && ptiles > 0) queue = ctx->d_counter + 58 + 2 * (ctx->stream == ctx->stream2 ? 1 : ctx->stream == ctx->stream3 ? 2 : 0);
+    kern<<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(tmA, tmB, M, N, K, epi, tri, ptiles, queue);
     ctx->launches++;
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;
@@ -307,6 +336,7 @@ int launch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const do
 // that are at least 90 % full — and the k loop is long enough to amortise the 3-stage ring; otherwise the cp.async kernel with 64 x 64
 // tiles (several CTAs per SM, finer wave granularity).  GMB_GEMM_TMA=0 disables the TMA kernel, =2 forces it (tests, profiling).
 inline int gemm_tma_mode() { static const int mode = [] { const char* e = getenv("GMB_GEMM_TMA"); return e ? atoi(e) : 1; }(); return mode; }
+inline bool gemm_tri_queue_enabled() { static const int on = [] { const char* e = getenv("GMB_GEMM_TRI_QUEUE"); return e ? atoi(e) : 1; }(); return on != 0; }
 inline bool use_tma(gmb_ctx* ctx, int M, int N, int K) {
     const int mode = gemm_tma_mode();
     if (mode == 0 || !get_encode()) return false;
@@ -326,6 +356,10 @@ int dispatch(gmb_ctx* ctx, int M, int N, int K, const double* A, int lda, const 
         return gmb_set_error(GMB_EINVAL, "dgemm: operands must be 16-byte aligned with even leading dimensions");
     // tri = 4 (a triangular solve as a product, the Cholesky's panel step): unequal tiles, heaviest first — worth the big tiles from half a wave on
     const bool tri4_tma = tri == 4 && gemm_tma_mode() != 0 && get_encode() && K >= 64 && 2L * ((M + BM - 1) / BM) * ((N + BN - 1) / BN) >= ctx->sms;
+    // triangular A with unequal tiles: persistent launch with a heaviest-first tile queue as soon as there is a tile per SM
+    const long tiles_all = (long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    if ((tri == 1 || tri == 2) && !Epi::COLSUM && gemm_tma_mode() != 0 && get_encode() && K >= 256 && tiles_all >= ctx->sms && gemm_tri_queue_enabled())
+        return launch<AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri, ctx->sms, true);
     if (use_tma(ctx, M, N, K) || tri4_tma) return launch<AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
     return gmbgemm::launch<64, 64, 2, 4, AK, BKC, Epi>(ctx, M, N, K, A, lda, B, ldb, epi, tri);
 }
