@@ -212,6 +212,11 @@ struct gmb_cov {
     // inverses of the 512 x 512 diagonal blocks of the large blocks' factors (cov_large.cu: formed beside the factorisation, used by the
     // forward substitution), 512 x 512 col-major each
     double* d_x512 = nullptr; std::vector<long long> x512_off;
+    // sufficient statistics of a model's samples for the LARGE blocks (cov_large.cu: gmb_cov_gram_large): C_b = chol(U_b U_b^T), so that
+    // sum_j ||L_b^-1 u_bj||^2 = ||L_b^-1 C_b||_F^2 costs n_b^3 / 3 flop per theta instead of n_b^2 m
+    struct GramLarge { double* C = nullptr; double* linv = nullptr; int state = 0; /* 0 none, 1 valid, -1 not usable */ };
+    std::vector<GramLarge> gram_large;
+    const gmb_model* gramL_model = nullptr; unsigned long long gramL_version = 0; int gramL_cols = 0;
     // Gram matrices of a model's samples (cov.cu: cov_ensure_gram), laid out like d_Lblk
     double* d_batch = nullptr; size_t batch_bytes = 0;     // work area of gmb_cov_mvn_ll_model_batch
     double* d_gram = nullptr; const gmb_model* gram_model = nullptr; unsigned long long gram_version = 0; int gram_cols = 0;
@@ -258,7 +263,8 @@ int gmb_estep_rowstats_enabled();
 
 // cov.cu
 int gmb_cov_factor(gmb_cov* cv, const double* theta);   // builds + factorises all blocks on the device
-int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_out /* 1 double: sum_j sum_b l_b(u_j) */);
+int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_out /* 1 double: sum_j sum_b l_b(u_j) */, gmb_model* gram_mdl = nullptr);
+int gmb_dsyrk_lower_set(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc);   // lower tiles of C = P P^T
 int gmb_cov_gen_device(gmb_cov* cv, const double* theta, int chol, double* d_out, int ld);   // dense D(theta) or chol D on the device
 // cov_large.cu: in-place blocked Cholesky of a raw device matrix (see the definition)
 int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet, double* x512 = nullptr);

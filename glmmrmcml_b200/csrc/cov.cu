@@ -365,7 +365,9 @@ __global__ void expand_blocks_kernel(int B, const CovBlock* __restrict__ blocks,
 }  // namespace
 
 int gmb_cov_factor_large(gmb_cov* cv, int bi);                                        // cov_large.cu
-int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols, double* d_partial);
+int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols, double* d_partial, int lower_rhs);
+int gmb_cov_gram_large(gmb_cov* cv, int bi, gmb_model* mdl, const double** C_out, int* ldc_out);
+void gmb_cov_gram_large_free(gmb_cov* cv);
 
 // ---------------------------------------------------------------------------------------------------
 // host side
@@ -415,7 +417,7 @@ extern "C" int gmb_cov_create(gmb_ctx* ctx, const int32_t* cov, int rows, const 
     GMB_CUDA(gmb_dmalloc(ctx, &cv->d_theta, sizeof(double) * (cv->R > 0 ? cv->R : 1)));
     GMB_CUDA(gmb_dmalloc(ctx, &cv->d_Lblk, sizeof(double) * (loff > 0 ? loff : 1)));
     GMB_CUDA(gmb_dmalloc(ctx, &cv->d_logdet, sizeof(double) * cv->B));
-    GMB_CUDA(gmb_dmalloc(ctx, &cv->d_status, sizeof(int)));
+    GMB_CUDA(gmb_dmalloc(ctx, &cv->d_status, 2 * sizeof(int)));      // [1]: the Gram factorisations of large blocks
     GMB_CUDA(cudaMemcpyAsync(cv->d_blocks, cv->blocks.data(), sizeof(CovBlock) * cv->B, cudaMemcpyHostToDevice, ctx->stream));
     GMB_CUDA(cudaMemcpyAsync(cv->d_fns, cv->fns.data(), sizeof(CovFn) * cv->fns.size(), cudaMemcpyHostToDevice, ctx->stream));
     GMB_CUDA(cudaMemcpyAsync(cv->d_data, data, sizeof(double) * off, cudaMemcpyHostToDevice, ctx->stream));
@@ -485,6 +487,7 @@ extern "C" void gmb_cov_destroy(gmb_cov* cv) {
     if (cv->d_work) gmb_dfree(cv->ctx, cv->d_work);
     if (cv->d_linv) gmb_dfree(cv->ctx, cv->d_linv);
     if (cv->d_x512) gmb_dfree(cv->ctx, cv->d_x512);
+    gmb_cov_gram_large_free(cv);
     if (cv->d_gram) gmb_dfree(cv->ctx, cv->d_gram);
     if (cv->d_gram_cls) gmb_dfree(cv->ctx, cv->d_gram_cls);
     gmb_dfree(cv->ctx, cv->d_cls_rep); gmb_dfree(cv->ctx, cv->d_cls_ptr); gmb_dfree(cv->ctx, cv->d_cls_mem);
@@ -530,11 +533,22 @@ int gmb_cov_factor(gmb_cov* cv, const double* theta) {
 }
 
 // d_out[0] = sum over the given columns of sum_b log N(u_j[b]; 0, D_b)   (raw sum; caller divides by m)
-int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_out) {
+static int g_cov_gram = 1;
+extern "C" int gmb_cov_set_gram(int on) { g_cov_gram = on ? 1 : 0; return GMB_OK; }
+
+// gram_mdl != NULL: dU are that model's device-resident samples; large blocks then go through the Cholesky factor of their Gram matrix
+// (gmb_cov_gram_large) when there are at least twice as many samples as rows, this rank holds all of them and the Gram path is on
+int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_out, gmb_model* gram_mdl) {
     gmb_ctx* ctx = cv->ctx;
     if (ncols <= 0) { GMB_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double), ctx->stream)); return GMB_OK; }
     int n_small = 0, n_other = 0;
     for (const auto& b : cv->blocks) { if (b.n <= QUAD_SMALL_MAX) n_small++; else n_other++; }
+    // Gram factors of the large blocks first: building one uses the context's scratch area, which the partial sums below live in
+    std::vector<const double*> gramC(cv->B, nullptr);
+    std::vector<int> gramLd(cv->B, 0);
+    if (gram_mdl && g_cov_gram && ctx->world == 1)
+        for (int bi = 0; bi < cv->B; bi++)
+            if (cv->blocks[bi].n > QUAD_MED_MAX && ncols >= 2 * cv->blocks[bi].n) GMB_TRY(gmb_cov_gram_large(cv, bi, gram_mdl, &gramC[bi], &gramLd[bi]));
     int groups = (cv->B + 31) / 32;
     int CC = 1, cols_per_cta = ncols;
     if (n_small) {
@@ -572,7 +586,8 @@ int gmb_cov_quad(gmb_cov* cv, const double* dU, int ldu, int ncols, double* d_ou
             ctx->launches++;
             GMB_CUDA(cudaGetLastError());
         } else {
-            GMB_TRY(gmb_cov_quad_large(cv, bi, dU, ldu, ncols, dst));
+            if (gramC[bi]) GMB_TRY(gmb_cov_quad_large(cv, bi, gramC[bi], gramLd[bi], b.n, dst, 1));
+            else GMB_TRY(gmb_cov_quad_large(cv, bi, dU, ldu, ncols, dst, 0));
         }
         k++;
     }
@@ -654,8 +669,6 @@ static int cov_finish_ll(gmb_cov* cv, double* d_out, int m_total, double* out) {
 }
 
 // 1 = mvn_ll on a model's samples goes through the Gram matrices when every block is <= 16 (default); 0 = always stream U
-static int g_cov_gram = 1;
-extern "C" int gmb_cov_set_gram(int on) { g_cov_gram = on ? 1 : 0; return GMB_OK; }
 
 // Gram matrices S_b = sum_j u_bj u_bj' of the model's local sample columns, cached per (model, sample version)
 static int cov_ensure_gram(gmb_cov* cv, gmb_model* mdl) {
@@ -735,7 +748,7 @@ extern "C" int gmb_cov_mvn_ll_model(gmb_cov* cv, const double* theta, gmb_model*
         return GMB_OK;
     }
     GMB_TRY(gmb_cov_factor(cv, theta));
-    GMB_TRY(gmb_cov_quad(cv, mdl->dU, mdl->ldq, mdl->m_local, cv->ctx->d_result));
+    GMB_TRY(gmb_cov_quad(cv, mdl->dU, mdl->ldq, mdl->m_local, cv->ctx->d_result, mdl));
     return cov_finish_ll(cv, cv->ctx->d_result, ncols_total > 0 ? ncols_total : mdl->m_total, out);
 }
 

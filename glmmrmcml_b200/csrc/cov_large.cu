@@ -203,10 +203,11 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const double* __restrict__ W
     if (threadIdx.x == 0) partials[blockIdx.x] += acc;      // slots are zeroed by the caller; launches that share a slot are ordered on one stream
 }
 
-__global__ void copy_rows_kernel(const double* __restrict__ U, int ldu, int start, int n, int ncols, double* __restrict__ W, int ldw) {
+// lower != 0: the source is a lower-triangular factor whose strict upper triangle holds scratch: column c0 + j is zero above row c0 + j
+__global__ void copy_rows_kernel(const double* __restrict__ U, int ldu, int start, int n, int ncols, double* __restrict__ W, int ldw, int lower, int c0) {
     int i = blockIdx.y * blockDim.x + threadIdx.x;      // grid.x runs over the columns (no 65535 limit)
     int j = blockIdx.x;
-    if (i < ldw && j < ncols) W[(size_t)j * ldw + i] = (i < n) ? U[(size_t)j * ldu + start + i] : 0.0;
+    if (i < ldw && j < ncols) W[(size_t)j * ldw + i] = (i < n && (!lower || i >= c0 + j)) ? U[(size_t)j * ldu + start + i] : 0.0;
 }
 
 }  // namespace
@@ -378,7 +379,9 @@ int gmb_cov_factor_large(gmb_cov* cv, int bi) {
 }
 
 // d_partial: 64 doubles (zeroed by the caller); receives partial sums of ||L^{-1} u_j||^2 over the columns
-int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols, double* d_partial) {
+// lower_rhs != 0: the right-hand sides are the columns of an n x n lower-triangular matrix (its own rows: start offset 0) — column j is zero above
+// row j and so is its solution, hence outer block K only touches the columns < Kend
+int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols, double* d_partial, int lower_rhs) {
     gmb_ctx* ctx = cv->ctx;
     const CovBlock& b = cv->blocks[bi];
     const int n = b.n, ld = gmb_cov_ld(n), ldw = round_up(n, 4);
@@ -404,7 +407,7 @@ int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols
     for (int c = 0; c < nchunks; c++) {
         int c0 = c * chunk, nc = ncols - c0 < chunk ? ncols - c0 : chunk;
         const int s0 = (c * slots) % 64;
-        copy_rows_kernel<<<dim3(nc, (ldw + 255) / 256), 256, 0, ctx->stream>>>(dU + (size_t)c0 * ldu, ldu, b.start, n, nc, W, ldw);
+        copy_rows_kernel<<<dim3(nc, (ldw + 255) / 256), 256, 0, ctx->stream>>>(dU + (size_t)c0 * ldu, ldu, lower_rhs ? 0 : b.start, n, nc, W, ldw, lower_rhs, c0);
         ctx->launches++;
         // Blocked forward substitution on outer blocks of 512 rows.  The factorisation left the inverse X_K of every 512 x 512 diagonal block of L
         // (gmb_chol_blocked), so a block's rows are solved by ONE triangular product Y_K = X_K W[K, :] (tri = 1 skips the zero k tiles) on the side
@@ -415,24 +418,66 @@ int gmb_cov_quad_large(gmb_cov* cv, int bi, const double* dU, int ldu, int ncols
         for (int K0 = 0, ko = 0; K0 < n; K0 += NBO, ko++) {
             const int Kend = K0 + NBO < n ? K0 + NBO : n, KB = Kend - K0;
             double* Yk = Y[ko & 1];
+            // columns of this chunk that are not identically zero in the rows of block K (all of them unless the right-hand sides are triangular)
+            const int nck = lower_rhs ? std::max(0, std::min(nc, Kend - c0)) : nc;
             {
                 StreamSwap sw(ctx, P);
                 GMB_CUDA(cudaStreamWaitEvent(P, ctx->evn, 0));
-                GMB_TRY(gmb_dgemm_tri(ctx, 0, 0, KB, nc, KB, 1.0, x512 + (size_t)ko * NBO * NBO, NBO, W + K0, ldw, 0.0, Yk, NBO, 1));
-                sumsq_kernel<<<slots, 256, 0, ctx->stream>>>(Yk, NBO, KB, nc, d_partial + s0);
-                ctx->launches++;
+                if (nck > 0) {
+                    GMB_TRY(gmb_dgemm_tri(ctx, 0, 0, KB, nck, KB, 1.0, x512 + (size_t)ko * NBO * NBO, NBO, W + K0, ldw, 0.0, Yk, NBO, 1));
+                    sumsq_kernel<<<slots, 256, 0, ctx->stream>>>(Yk, NBO, KB, nck, d_partial + s0);
+                    ctx->launches++;
+                }
                 GMB_CUDA(cudaEventRecord(ctx->evp, P));
             }
             GMB_CUDA(cudaStreamWaitEvent(M, ctx->evp, 0));
             if (Kend >= n) break;
             const int nar = n - Kend < NBO ? n - Kend : NBO;          // W[Kend:Kend+nar, :] -= L[Kend:Kend+nar, K0:Kend] Y_K
-            GMB_TRY(gmb_dgemm(ctx, 0, 0, nar, nc, KB, -1.0, A + Kend + (size_t)K0 * ld, ld, Yk, NBO, 1.0, W + Kend, ldw));
+            if (nck > 0) GMB_TRY(gmb_dgemm(ctx, 0, 0, nar, nck, KB, -1.0, A + Kend + (size_t)K0 * ld, ld, Yk, NBO, 1.0, W + Kend, ldw));
             GMB_CUDA(cudaEventRecord(ctx->evn, M));
             const int rest = n - Kend - nar;
-            if (rest > 0)
-                GMB_TRY(gmb_dgemm(ctx, 0, 0, rest, nc, KB, -1.0, A + Kend + nar + (size_t)K0 * ld, ld, Yk, NBO, 1.0, W + Kend + nar, ldw));
+            if (rest > 0 && nck > 0)
+                GMB_TRY(gmb_dgemm(ctx, 0, 0, rest, nck, KB, -1.0, A + Kend + nar + (size_t)K0 * ld, ld, Yk, NBO, 1.0, W + Kend + nar, ldw));
         }
     }
     GMB_CUDA(cudaGetLastError());
     return GMB_OK;
+}
+
+// C_b = chol(U_b U_b^T) of the model's local sample columns for large block bi, cached per (model, sample version); state -1 when the Gram matrix
+// is not (numerically) positive definite — fewer samples than rows, degenerate samples — and the caller streams the samples instead.
+int gmb_cov_gram_large(gmb_cov* cv, int bi, gmb_model* mdl, const double** C_out, int* ldc_out) {
+    gmb_ctx* ctx = cv->ctx;
+    const CovBlock& b = cv->blocks[bi];
+    const int n = b.n, ld = gmb_cov_ld(n), ncols = mdl->m_local;
+    if (cv->gram_large.size() != cv->blocks.size()) cv->gram_large.assign(cv->blocks.size(), gmb_cov::GramLarge());
+    if (!(cv->gramL_model == mdl && cv->gramL_version == mdl->u_version && cv->gramL_cols == ncols)) {
+        for (auto& g : cv->gram_large) g.state = 0;
+        cv->gramL_model = mdl; cv->gramL_version = mdl->u_version; cv->gramL_cols = ncols;
+    }
+    gmb_cov::GramLarge& g = cv->gram_large[bi];
+    *C_out = nullptr; *ldc_out = ld;
+    if (g.state < 0) return GMB_OK;
+    if (g.state == 0) {
+        if ((b.start & 1) || (mdl->ldq & 1)) { g.state = -1; return GMB_OK; }
+        if (!g.C) {
+            GMB_CUDA(gmb_dmalloc(ctx, &g.C, sizeof(double) * (size_t)ld * n));
+            GMB_CUDA(gmb_dmalloc(ctx, &g.linv, sizeof(double) * (size_t)((n + NB - 1) / NB) * NB * NB));
+        }
+        GMB_TRY(gmb_dsyrk_lower_set(ctx, n, ncols, mdl->dU + b.start, mdl->ldq, g.C, ld));
+        int* d_stat = cv->d_status + 1;                      // second status word: the Gram factorisation's
+        GMB_CUDA(cudaMemsetAsync(d_stat, 0, sizeof(int), ctx->stream));
+        GMB_TRY(gmb_chol_blocked(ctx, g.C, ld, n, 0, d_stat, g.linv, nullptr, nullptr));
+        int* hstat = reinterpret_cast<int*>(ctx->h_pinned + 66);
+        GMB_CUDA(cudaMemcpyAsync(hstat, d_stat, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        GMB_CUDA(cudaStreamSynchronize(ctx->stream));
+        g.state = (*hstat == 0) ? 1 : -1;
+        if (g.state < 0) return GMB_OK;
+    }
+    *C_out = g.C;
+    return GMB_OK;
+}
+
+void gmb_cov_gram_large_free(gmb_cov* cv) {
+    for (auto& g : cv->gram_large) { gmb_dfree(cv->ctx, g.C); gmb_dfree(cv->ctx, g.linv); g = gmb_cov::GramLarge(); }
 }

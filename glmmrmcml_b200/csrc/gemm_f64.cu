@@ -73,6 +73,11 @@ int gmb_dsyrk_lower_sub(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, d
     EpiAxpby epi{-1.0, 1.0, C, ldc};
     return gmbtma::dispatch_syrk_lower(ctx, M, K, Pm, ldp, epi, c0, c1);
 }
+// lower tiles of C = P P^T (P: M x K, m contiguous): the Gram matrix of a block's samples
+int gmb_dsyrk_lower_set(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc) {
+    EpiAxpby epi{1.0, 0.0, C, ldc};
+    return gmbtma::dispatch_syrk_lower(ctx, M, K, Pm, ldp, epi, 0, M);
+}
 // the same over ALL lower tiles except those of the leading skip x skip block (skip a multiple of 128), as one persistent launch on at most
 // max_ctas CTAs (0: one CTA per tile)
 int gmb_dsyrk_lower_rest(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, double* C, int ldc, int skip, int max_ctas) {

@@ -216,3 +216,42 @@ def test_identical_blocks_are_factorised_once(gctx, oracle):
     cv2 = g.Covariance(gctx, np.array([[0, 5, 13, 1, 0], [1, 5, 13, 1, 0]], dtype=np.int32), np.concatenate([rng.random(5), rng.random(5)]), np.zeros(2))
     assert cv2.block_classes == 2
     cv2.close(); mdl.close(); cv.close()
+
+
+def test_large_blocks_through_the_cholesky_factor_of_their_gram_matrix(gctx, oracle):
+    """mvn_ll on a model's samples, blocks beyond the warp-sized paths: with m >= 2 n_b samples on this rank the library keeps
+    C_b = chol(U_b U_b^T) per sample matrix and evaluates sum_j ||L_b^-1 u_bj||^2 = ||L_b^-1 C_b||_F^2 (n_b^3 / 3 flop per theta instead of
+    n_b^2 m).  Against the streaming evaluation and the oracle at several theta; the fall-backs (too few samples, singular Gram matrix)."""
+    import glmmrmcml_b200 as g
+    rng = np.random.default_rng(17)
+    for nloc, m in ((150, 400), (700, 1500), (1100, 2300)):
+        cfg = synth.config3(nloc=nloc, m=m)
+        cv = g.Covariance(gctx, cfg["cov"], cfg["data"], cfg["eff_range"])
+        mdl = g.Model(gctx, cfg["X"], cfg["Z"], cfg["y"], cfg["family"], cfg["link"])
+        for rep in range(2):                                   # the factor of the Gram matrix follows the samples
+            U = np.asfortranarray(cfg["U"] * (1.0 + 0.2 * rep) + 0.01 * rng.standard_normal(cfg["U"].shape))
+            mdl.set_u(U)
+            for scale in (1.0, 0.85, 1.1):
+                theta = cfg["theta"] * scale
+                want = oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], theta, U)
+                got = cv.loglik_model(theta, mdl)
+                try:
+                    g.cov_set_gram(False); stream = cv.loglik_model(theta, mdl)
+                finally:
+                    g.cov_set_gram(True)
+                assert abs(stream - want) <= 1e-10 * abs(want), (nloc, stream, want)
+                assert abs(got - want) <= 1e-10 * abs(want), (nloc, got, stream, want)
+        # fewer than 2 n samples: the samples are streamed (same value as with the Gram path off, bit for bit)
+        mdl.set_u(np.asfortranarray(U[:, : nloc + 7]))
+        a = cv.loglik_model(cfg["theta"], mdl)
+        try:
+            g.cov_set_gram(False); b = cv.loglik_model(cfg["theta"], mdl)
+        finally:
+            g.cov_set_gram(True)
+        assert a == b
+        # a singular Gram matrix (2 n + 10 columns spanning 40 dimensions): detected, streamed
+        Us = np.asfortranarray(U[:, :40] @ rng.standard_normal((40, 2 * nloc + 10)))
+        mdl.set_u(Us)
+        want = oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], cfg["theta"], Us)
+        assert abs(cv.loglik_model(cfg["theta"], mdl) - want) <= 1e-10 * abs(want)
+        mdl.close(); cv.close()
