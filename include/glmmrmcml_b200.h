@@ -198,8 +198,11 @@ int gmb_estep_set_tf32(int on);
  * values agree to rounding (1e-13 relative), not bit for bit. */
 int gmb_estep_set_multi(int on);
 
-/* mvn_ll on a model's device-resident samples when every covariance block is <= 16: 1 (default) = through the Gram matrices of the samples
- * (built once per sample matrix, each evaluation independent of the number of samples), 0 = stream the samples on every evaluation. */
+/* mvn_ll on a model's device-resident samples: 1 (default) = through sufficient statistics of the samples, built once per sample matrix —
+ * when every covariance block is <= 16, their Gram matrices (each evaluation independent of the number of samples); for a large block
+ * (> 64) on a single rank with at least twice as many samples as rows, the Cholesky factor of its Gram matrix (n^3 / 3 flop per
+ * evaluation instead of n^2 m; falls back to the samples when that matrix is not positive definite); 0 = stream the samples on every
+ * evaluation. */
 int gmb_cov_set_gram(int on);
 
 /* Gram-matrix path: 1 (default) = blocks that are IDENTICAL (same size, same function rows, same data — gr(cl)*ar1(t) repeats one block per

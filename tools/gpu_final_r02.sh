@@ -11,3 +11,4 @@ python tools/tf32_error_sweep.py > $P/r02_tf32_error_sweep.txt 2>&1; tail -4 $P/
 { echo "# python tools/prof_chol.py N M: factorisation of one N x N fexp block; mvn_ll with M device-resident sample columns (CUDA events)";
   for a in "3000 0" "5000 10000" "10000 10000"; do echo "## N M = $a"; python tools/prof_chol.py $a 2>&1 | tail -3; done; } > $P/r02_chol_timings.txt
 cat $P/r02_chol_timings.txt
+python tools/bench_mcml_full.py > $P/r02_mcml_full_fits.jsonl 2> gpurun_out/j_fits.err; tail -3 $P/r02_mcml_full_fits.jsonl | cut -c1-400
