@@ -268,6 +268,7 @@ int gmb_dsyrk_lower_set(gmb_ctx* ctx, int M, int K, const double* Pm, int ldp, d
 int gmb_cov_gen_device(gmb_cov* cv, const double* theta, int chol, double* d_out, int ld);   // dense D(theta) or chol D on the device
 // cov_large.cu: in-place blocked Cholesky of a raw device matrix (see the definition)
 int gmb_chol_blocked(gmb_ctx* ctx, double* A, int ld, int n, int row_offset, int* d_status, double* linv, double* d_logdet, double* x512 = nullptr);
+size_t gmb_chol_linv_doubles(int n);   // size of the `linv` argument for an n x n matrix
 
 // model.cu
 int gmb_model_reserve_samples(gmb_model* mdl, int m);

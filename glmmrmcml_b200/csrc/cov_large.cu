@@ -290,6 +290,8 @@ static int chol_diag_chain(gmb_ctx* ctx, double* A, int ld, int K0, int Kend, in
     return GMB_OK;
 }
 
+size_t gmb_chol_linv_doubles(int n) { return (size_t)((n + NB - 1) / NB) * NB * NB; }
+
 static int g_chol_reserve = [] { const char* e = getenv("GMB_CHOL_RESERVE_SMS"); return e ? atoi(e) : 8; }();
 
 // in-place lower Cholesky of the n x n device matrix A (lower triangle read; the strict upper triangle of the 128 x 128 diagonal blocks is
@@ -462,7 +464,7 @@ int gmb_cov_gram_large(gmb_cov* cv, int bi, gmb_model* mdl, const double** C_out
         if ((b.start & 1) || (mdl->ldq & 1)) { g.state = -1; return GMB_OK; }
         if (!g.C) {
             GMB_CUDA(gmb_dmalloc(ctx, &g.C, sizeof(double) * (size_t)ld * n));
-            GMB_CUDA(gmb_dmalloc(ctx, &g.linv, sizeof(double) * (size_t)((n + NB - 1) / NB) * NB * NB));
+            GMB_CUDA(gmb_dmalloc(ctx, &g.linv, sizeof(double) * gmb_chol_linv_doubles(n)));
         }
         GMB_TRY(gmb_dsyrk_lower_set(ctx, n, ncols, mdl->dU + b.start, mdl->ldq, g.C, ld));
         int* d_stat = cv->d_status + 1;                      // second status word: the Gram factorisation's

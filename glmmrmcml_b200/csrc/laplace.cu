@@ -88,7 +88,7 @@ struct LaFit {
         GMB_CUDA(gmb_dmalloc(ctx, &d_zu, sizeof(double) * ldn));
         GMB_CUDA(gmb_dmalloc(ctx, &d_B, sizeof(double) * (size_t)ldn * Q));
         GMB_CUDA(gmb_dmalloc(ctx, &d_M, sizeof(double) * (size_t)ldq * Q));
-        GMB_CUDA(gmb_dmalloc(ctx, &d_linv, sizeof(double) * (size_t)((Q + 63) / 64) * 64 * 64));
+        GMB_CUDA(gmb_dmalloc(ctx, &d_linv, sizeof(double) * gmb_chol_linv_doubles(Q)));       // inverted diagonal blocks, sized by the factorisation itself
         GMB_CUDA(gmb_dmalloc(ctx, &d_vec, sizeof(double) * (size_t)(ldn + ldq) * 2));
         GMB_CUDA(gmb_dmalloc(ctx, &d_status, sizeof(int)));
         GMB_CUDA(cudaMemsetAsync(d_V, 0, sizeof(double) * (size_t)ldq * kmax, ctx->stream));

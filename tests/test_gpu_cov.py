@@ -255,3 +255,32 @@ def test_large_blocks_through_the_cholesky_factor_of_their_gram_matrix(gctx, ora
         want = oracle.mvn_loglik(cfg["cov"], cfg["data"], cfg["eff_range"], cfg["theta"], Us)
         assert abs(cv.loglik_model(cfg["theta"], mdl) - want) <= 1e-10 * abs(want)
         mdl.close(); cv.close()
+
+
+def test_gram_factor_path_with_several_large_blocks(gctx, oracle):
+    """two large blocks (Gram-factor path each), one medium and a few small ones in one covariance; and an odd block offset (unaligned rows of U:
+    that block streams its samples)."""
+    import glmmrmcml_b200 as g
+    rng = np.random.default_rng(23)
+    for sizes in ((100, 130, 40, 6), (7, 101, 90)):            # second layout: the 101-block starts at row 7 (odd)
+        cov, data, b = [], [], 0
+        for nb in sizes:
+            xy = rng.random((nb, 2))
+            cov.append([b, nb, 13, 2, 0]); data += list(xy[:, 0]) + list(xy[:, 1]); b += 1
+        cov = np.array(cov, dtype=np.int32); data = np.array(data); eff = np.zeros(len(cov))
+        theta = np.array([0.3, 0.2])
+        cv = g.Covariance(gctx, cov, data, eff)
+        Q, n = cv.Q, 30
+        Z = np.zeros((n, Q), order="F"); Z[np.arange(n), rng.integers(0, Q, n)] = 1.0
+        mdl = g.Model(gctx, np.ones((n, 1), order="F"), Z, rng.standard_normal(n), "gaussian", "identity")
+        U = np.asfortranarray(cv.genD(theta, chol=True) @ rng.standard_normal((Q, 300)))
+        mdl.set_u(U)
+        for scale in (1.0, 1.2):
+            want = oracle.mvn_loglik(cov, data, eff, theta * scale, U)
+            got = cv.loglik_model(theta * scale, mdl)
+            try:
+                g.cov_set_gram(False); stream = cv.loglik_model(theta * scale, mdl)
+            finally:
+                g.cov_set_gram(True)
+            assert abs(got - want) <= 1e-10 * abs(want) and abs(stream - want) <= 1e-10 * abs(want), (sizes, got, stream, want)
+        mdl.close(); cv.close()
