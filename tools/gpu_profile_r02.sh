@@ -4,6 +4,7 @@
 set -u
 mkdir -p gpurun_out/profiles_out
 P=gpurun_out/profiles_out
+if [ -z "${SKIP_LAUNCH_LIST:-}" ]; then
 python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/p_plain_bench.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/p_launches_bench.csv \
     python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/p_ncu_bench.log 2>&1
@@ -26,9 +27,10 @@ with open('gpurun_out/profiles_out/r02_launches_bench.csv', 'w') as f:
     for k, v in sorted(t.items(), key=lambda kv: -kv[1]):
         f.write('"%s",%d,%.1f,%.2f,%.4f\n' % (k, n[k], v, v / n[k], v / tot))
 PY
-for spec in "hmc:hmc_lane:2" "estep:loglik_logit_factor_kernel|mcnr_tma_kernel|mcnr_tail:12" "estep:loglik_logit_agg_kernel|mcnr_agg_kernel|agg_finish:6" "gemm:dgemm_tma_kernel|sgemm3_tf32_kernel|split_tf32:6" "chol:potrf_diag_kernel:1" "chol:dgemm_tma_kernel:4"; do
-    IFS=: read what rx cnt <<< "$spec"
-    tag=${what}_$(echo $rx | cut -c1-12 | tr '|' '_')
+fi
+SPECS=${SPECS:-"hmc:hmc_lane:2:hmc_hmc_lane estep:loglik_logit_factor_kernel|mcnr_tma_kernel|mcnr_tail:12:estep_loglik_logit estep:loglik_logit_agg_kernel|mcnr_agg_kernel|agg_finish:6:estep_loglik_logit_agg gemm:dgemm_tma_kernel|sgemm3_tf32_kernel|split_tf32:6:gemm_dgemm_tma_ke chol:potrf_diag_kernel:1:chol_potrf_diag_k chol:dgemm_tma_kernel:4:chol_dgemm_tma_ke"}
+for spec in $SPECS; do
+    IFS=: read what rx cnt tag <<< "$spec"
     python tools/prof_r02.py $what > gpurun_out/p_plain_$what.log 2>&1 &&
     ncu --set full --clock-control none --import-source on -k regex:"$rx" -c $cnt -o gpurun_out/p_$tag -f python tools/prof_r02.py $what > gpurun_out/p_ncu_$tag.log 2>&1
     echo "$tag full rc=$?"
