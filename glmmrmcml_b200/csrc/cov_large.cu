@@ -184,6 +184,161 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
         }
 }
 
+// ---- two columns per hand-off ------------------------------------------------------------------------------------------------------
+// The elimination above pays one hand-off (publish -> mbarrier -> shared-memory read) per column, and the hand-off, not the arithmetic, is
+// what a step costs.  Here a step eliminates the PAIR of columns j, j + 1: their owners publish the raw columns c0, c1 (updates through
+// column j - 1 applied) and the raw rows b0, b1 of B; every thread derives both factor columns itself —
+//     l0 = c0 / sqrt(c0_j),   l10 = l0_{j+1},   c1' = c1 - l10 l0,   l1 = c1' / sqrt(c1'_{j+1}),      x0 = b0 / sqrt(c0_j),   x1 = (b1 - l10 x0) / sqrt(c1'_{j+1})
+// — and applies the rank-2 update A -= l0 l0' + l1 l1', B -= l0 x0' + l1 x1': two reciprocal square roots in sequence, but half the hand-offs.
+template <int JQ, int JQN>
+__device__ __forceinline__ bool potrf_step2(int js /* even */, int tx, int ty, int lane, double (&a)[8][8], double (&bm)[8][8],
+                                            double (*colbuf)[2][NB], double (*rowbuf)[2][NB], uint64_t* bars, int* status, int pivot_id) {
+    const int j = 16 * JQ + js, pr = j >> 1;                      // first column of the pair, pair index
+    pd_bar_wait(&bars[pr & 1], (pr >> 1) & 1);
+    const double* c0 = colbuf[pr & 1][0];
+    const double* c1 = colbuf[pr & 1][1];
+    const double* b0 = rowbuf[pr & 1][0];
+    const double* b1 = rowbuf[pr & 1][1];
+    const double d0 = c0[j];
+    if (!(d0 > 0.0)) { if (threadIdx.x == 0) atomicCAS(status, 0, pivot_id + j + 1); return false; }
+    const double inv0 = rsqrt(d0);
+    const double l10 = c0[j + 1] * inv0;
+    const double d1 = fma(-l10, l10, c1[j + 1]);
+    if (!(d1 > 0.0)) { if (threadIdx.x == 0) atomicCAS(status, 0, pivot_id + j + 2); return false; }
+    const double inv1 = rsqrt(d1);
+    double l0r[8], l1r[8], l0c[8], l1c[8], x0[8], x1[8];
+#pragma unroll
+    for (int i = JQ; i < 8; i++) {
+        l0r[i] = c0[tx + 16 * i] * inv0; l1r[i] = fma(-l0r[i], l10, c1[tx + 16 * i]) * inv1;
+        l0c[i] = c0[ty + 16 * i] * inv0; l1c[i] = fma(-l0c[i], l10, c1[ty + 16 * i]) * inv1;
+    }
+#pragma unroll
+    for (int jj = 0; jj <= JQ; jj++) { x0[jj] = b0[ty + 16 * jj] * inv0; x1[jj] = fma(-l10, x0[jj], b1[ty + 16 * jj]) * inv1; }
+    // rows r > j + 1 of slot i, columns c > j + 1 of slot jj
+#define PD_ROK(i) (((i) > JQ) || (tx > js + 1))
+#define PD_COK(jj) (((jj) > JQ) || (ty > js + 1))
+    if (JQN < 8) {
+        // ---- priority: column slot JQN of A (it holds the next pair's columns), row slot JQN of B ----
+#pragma unroll
+        for (int i = JQN; i < 8; i++)
+            if (PD_ROK(i) && PD_COK(JQN)) a[i][JQN] = fma(-l1r[i], l1c[JQN], fma(-l0r[i], l0c[JQN], a[i][JQN]));
+        if (PD_ROK(JQN)) {
+#pragma unroll
+            for (int jj = 0; jj <= JQ; jj++) bm[JQN][jj] = fma(-l1r[JQN], x1[jj], fma(-l0r[JQN], x0[jj], bm[JQN][jj]));
+        }
+        const int jn = j + 2, jsn = jn & 15, pn = jn >> 1;
+        if (ty == jsn || ty == jsn + 1) {         // owners of columns j + 2, j + 3 of A: rows r >= column live in slots i >= JQN
+            double* dst = colbuf[pn & 1][ty - jsn];
+#pragma unroll
+            for (int i = JQN; i < 8; i++) dst[tx + 16 * i] = a[i][JQN];
+        }
+        if (tx == jsn || tx == jsn + 1) {         // owners of rows j + 2, j + 3 of B: columns c <= row live in slots jj <= JQN
+            double* dst = rowbuf[pn & 1][tx - jsn];
+#pragma unroll
+            for (int jj = 0; jj <= JQN; jj++) dst[ty + 16 * jj] = bm[JQN][jj];
+        }
+        __syncwarp();
+        if (lane == 0) pd_bar_arrive(&bars[pn & 1]);
+    }
+    // ---- the rest of the rank-2 update ----
+#pragma unroll
+    for (int i = JQ; i < 8; i++) {
+        if (PD_ROK(i)) {
+#pragma unroll
+            for (int jj = JQ; jj <= i; jj++)
+                if (jj != JQN && PD_COK(jj)) a[i][jj] = fma(-l1r[i], l1c[jj], fma(-l0r[i], l0c[jj], a[i][jj]));
+            if (i != JQN) {
+#pragma unroll
+                for (int jj = 0; jj <= JQ; jj++) bm[i][jj] = fma(-l1r[i], x1[jj], fma(-l0r[i], x0[jj], bm[i][jj]));
+            }
+        }
+    }
+#undef PD_ROK
+#undef PD_COK
+    if (ty == js) {                               // column j of L (row j + 1 of it is l10)
+#pragma unroll
+        for (int i = JQ; i < 8; i++) {
+            if (i > JQ || tx > js) a[i][JQ] = l0r[i];
+            else if (tx == js) a[i][JQ] = d0 * inv0;
+        }
+    }
+    if (ty == js + 1) {                           // column j + 1 of L
+#pragma unroll
+        for (int i = JQ; i < 8; i++) {
+            if (i > JQ || tx > js + 1) a[i][JQ] = l1r[i];
+            else if (tx == js + 1) a[i][JQ] = d1 * inv1;
+        }
+    }
+    if (tx == js) {                               // row j of L^-1
+#pragma unroll
+        for (int jj = 0; jj <= JQ; jj++) bm[JQ][jj] = x0[jj];
+    }
+    if (tx == js + 1) {                           // row j + 1 of L^-1
+#pragma unroll
+        for (int jj = 0; jj <= JQ; jj++) bm[JQ][jj] = x1[jj];
+    }
+    return true;
+}
+
+template <int JQ>
+__device__ __forceinline__ bool potrf_phase2(int tx, int ty, int lane, double (&a)[8][8], double (&bm)[8][8], double (*colbuf)[2][NB], double (*rowbuf)[2][NB],
+                                             uint64_t* bars, int* status, int pivot_id) {
+#pragma unroll 1
+    for (int js = 0; js < 14; js += 2)
+        if (!potrf_step2<JQ, JQ>(js, tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id)) return false;
+    return potrf_step2<JQ, JQ + 1>(14, tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+}
+
+__global__ void __launch_bounds__(256) potrf_diag2_kernel(double* __restrict__ A, int ld, int k0, int kb, int row_offset, int* __restrict__ status,
+                                                          double* __restrict__ Linv) {
+    __shared__ double colbuf[2][2][NB], rowbuf[2][2][NB];
+    __shared__ uint64_t bars[2];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4, lane = tid & 31;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pd_smem(&bars[0])), "r"(8));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pd_smem(&bars[1])), "r"(8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    double a[8][8], bm[8][8];
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++)
+#pragma unroll
+        for (int i = jj; i < 8; i++) {
+            const int r = tx + 16 * i, c = ty + 16 * jj;
+            double v = (r == c) ? 1.0 : 0.0;
+            if (r < kb && c < kb && r >= c) v = A[(size_t)(k0 + r) + (size_t)(k0 + c) * ld];
+            a[i][jj] = v;
+            bm[i][jj] = (r == c) ? 1.0 : 0.0;
+        }
+    __syncthreads();                              // barriers initialised
+    if (ty < 2) {                                 // columns 0, 1 of A
+#pragma unroll
+        for (int i = 0; i < 8; i++) colbuf[0][ty][tx + 16 * i] = a[i][0];
+    }
+    if (tx < 2) rowbuf[0][tx][ty] = bm[0][0];     // rows 0, 1 of B (columns c <= 1 live in slot 0; c > row holds 0)
+    __syncwarp();
+    if (lane == 0) pd_bar_arrive(&bars[0]);
+    const int pivot_id = row_offset + k0;
+    bool ok = potrf_phase2<0>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase2<1>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase2<2>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase2<3>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase2<4>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase2<5>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase2<6>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    ok = ok && potrf_phase2<7>(tx, ty, lane, a, bm, colbuf, rowbuf, bars, status, pivot_id);
+    if (!ok) return;
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int r = tx + 16 * i, c = ty + 16 * jj;
+            const bool low = (i > jj) || (i == jj && r >= c);
+            if (r < kb && c < kb) A[(size_t)(k0 + r) + (size_t)(k0 + c) * ld] = (i >= jj && low) ? a[i >= jj ? i : jj][jj] : 0.0;
+            Linv[r + (size_t)c * NB] = (i >= jj && low && r < kb && c < kb) ? bm[i >= jj ? i : jj][jj] : 0.0;
+        }
+}
+
 __global__ void logdet_diag_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ out) {
     __shared__ double red[32];
     double c = 0.0;
@@ -256,6 +411,9 @@ static int x512_buffer(gmb_cov* cv, int bi, double** out) {
     return GMB_OK;
 }
 
+// 1 (default) = the diagonal kernel eliminates two columns per hand-off (potrf_diag2_kernel), 0 = one (GMB_POTRF_PAIRS)
+static int g_potrf_pairs = [] { const char* e = getenv("GMB_POTRF_PAIRS"); return e ? atoi(e) : 1; }();
+
 // the panel chain of the outer block [K0, Kend), confined to the block's own KB x KB diagonal part: per 128-column panel the diagonal factor +
 // inverse, the solve of the (at most 384) rows of the block below it and their rank-128 update (on the current stream).  With X != NULL also
 // the inverse of the whole KB x KB factor, block row by block row: X[j, 0:j] = -L_jj^-1 (L[j, 0:j] X[0:j, 0:j]), X[j, j] = L_jj^-1 (T: 128 x
@@ -265,7 +423,8 @@ static int chol_diag_chain(gmb_ctx* ctx, double* A, int ld, int K0, int Kend, in
     for (int k0 = K0, j = 0; k0 < Kend; k0 += NB, j++) {
         const int kb = Kend - k0 < NB ? Kend - k0 : NB;
         double* Li = linv + (size_t)(k0 / NB) * NB * NB;
-        potrf_diag_kernel<<<1, 256, 0, S>>>(A, ld, k0, kb, row_offset, d_status, Li);
+        if (g_potrf_pairs) potrf_diag2_kernel<<<1, 256, 0, S>>>(A, ld, k0, kb, row_offset, d_status, Li);
+        else potrf_diag_kernel<<<1, 256, 0, S>>>(A, ld, k0, kb, row_offset, d_status, Li);
         ctx->launches++;
         if (X) {
             GMB_CUDA(cudaEventRecord(ctx->evd[j], S));
