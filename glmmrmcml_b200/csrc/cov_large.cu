@@ -184,6 +184,20 @@ __global__ void __launch_bounds__(256) potrf_diag_kernel(double* __restrict__ A,
         }
 }
 
+// 1 / sqrt(d) for a positive, normal d: hardware seed (rsqrt.approx.ftz.f64, relative error < 2^-22) and two Newton steps y += (y/2)(1 - d y^2)
+// — six dependent FP64 operations, ~1 ulp, without the special-case handling of the library function (the callers have checked d > 0; a
+// pivot so small or large that the seed leaves the normal range is a breakdown of the factorisation anyway)
+__device__ __forceinline__ double pd_rsqrt(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const double e = fma(-d * y, y, 1.0);
+        y = fma(0.5 * y, e, y);
+    }
+    return y;
+}
+
 // ---- two columns per hand-off ------------------------------------------------------------------------------------------------------
 // The elimination above pays one hand-off (publish -> mbarrier -> shared-memory read) per column, and the hand-off, not the arithmetic, is
 // what a step costs.  Here a step eliminates the PAIR of columns j, j + 1: their owners publish the raw columns c0, c1 (updates through
@@ -201,11 +215,11 @@ __device__ __forceinline__ bool potrf_step2(int js /* even */, int tx, int ty, i
     const double* b1 = rowbuf[pr & 1][1];
     const double d0 = c0[j];
     if (!(d0 > 0.0)) { if (threadIdx.x == 0) atomicCAS(status, 0, pivot_id + j + 1); return false; }
-    const double inv0 = rsqrt(d0);
+    const double inv0 = pd_rsqrt(d0);
     const double l10 = c0[j + 1] * inv0;
     const double d1 = fma(-l10, l10, c1[j + 1]);
     if (!(d1 > 0.0)) { if (threadIdx.x == 0) atomicCAS(status, 0, pivot_id + j + 2); return false; }
-    const double inv1 = rsqrt(d1);
+    const double inv1 = pd_rsqrt(d1);
     double l0r[8], l1r[8], l0c[8], l1c[8], x0[8], x1[8];
 #pragma unroll
     for (int i = JQ; i < 8; i++) {
