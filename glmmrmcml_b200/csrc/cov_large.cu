@@ -465,7 +465,7 @@ static int chol_diag_chain(gmb_ctx* ctx, double* A, int ld, int K0, int Kend, in
 
 size_t gmb_chol_linv_doubles(int n) { return (size_t)((n + NB - 1) / NB) * NB * NB; }
 
-static int g_chol_reserve = [] { const char* e = getenv("GMB_CHOL_RESERVE_SMS"); return e ? atoi(e) : 8; }();
+static int g_chol_reserve = [] { const char* e = getenv("GMB_CHOL_RESERVE_SMS"); return e ? atoi(e) : 4; }();
 
 // in-place lower Cholesky of the n x n device matrix A (lower triangle read; the strict upper triangle of the 128 x 128 diagonal blocks is
 // zeroed, the rest of the upper triangle is left as scratch).  linv: ceil(n/128) * 128 * 128 doubles (inverted diagonal blocks), status:
