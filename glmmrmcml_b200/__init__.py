@@ -89,6 +89,11 @@ def estep_set_row_aggregation(on: bool):
     check(lib().gmb_estep_set_row_aggregation(int(bool(on))))
 
 
+def set_object_cache(on: bool):
+    """Reference-named entry points: True (default) = keep the device objects of the last few models / covariance specifications between calls."""
+    check(lib().gmb_set_object_cache(int(bool(on))))
+
+
 def cov_set_block_classes(on: bool):
     """Gram-matrix mvn_ll: True (default) = identical covariance blocks are factorised once per class; False = once per block."""
     check(lib().gmb_cov_set_block_classes(int(bool(on))))

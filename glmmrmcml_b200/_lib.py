@@ -84,6 +84,7 @@ PROTOTYPES = {
     "gmb_cov_set_gram": (C.c_int, [C.c_int]),
     "gmb_cov_set_block_classes": (C.c_int, [C.c_int]),
     "gmb_estep_set_row_aggregation": (C.c_int, [C.c_int]),
+    "gmb_set_object_cache": (C.c_int, [C.c_int]),
     "gmb_model_estep_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gmb_cov_block_classes": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "gmb_model_logprob_grad": (C.c_int, [vp, dp, dp, C.c_double, dp, C.c_int, dp, dp]),

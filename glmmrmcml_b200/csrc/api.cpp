@@ -5,6 +5,9 @@
 // callbacks the role of likelihood.h's D_/L_/F_likelihood functors (likelihood.h:31-110).
 #include "common.cuh"
 #include <map>
+#include <cstring>
+#include <string>
+#include <vector>
 #include <limits>
 #include <algorithm>
 
@@ -202,9 +205,93 @@ struct Fit {
     }
 };
 
+// ---- device objects kept between calls -----------------------------------------------------------------------------------------
+// The reference-named entry points take host arrays and (in the reference) rebuild their C++ objects on every call; an R loop calls
+// mcmc_sample / mcml_optim / mcml_hess again and again with the SAME X, Z, y and covariance specification.  Building the device objects
+// (uploads, row aggregation, sparse forms of Z, block classes) costs ~0.5-1 ms per call at C2 — 13 % of the end-to-end step — so the last few
+// models and covariance objects of a context are kept, keyed by an EXACT comparison (memcmp) of their defining arrays; everything that depends
+// on the call's other arguments (u, L, beta, theta) is set by the call as before.  Objects of more than 8 MB of host data are not kept.
+struct CachedModel { gmb_ctx* ctx; int n, P, Q; std::string fam, link; std::vector<double> X, Z, y; gmb_model* mdl; bool busy; unsigned long long stamp; };
+struct CachedCov { gmb_ctx* ctx; int rows, n_data, n_eff; std::vector<int32_t> cov; std::vector<double> data, eff; gmb_cov* cv; bool busy; unsigned long long stamp; };
+std::vector<CachedModel> g_models;
+std::vector<CachedCov> g_covs;
+unsigned long long g_stamp = 0;
+int g_object_cache = 1;
+constexpr size_t kCacheMaxDoubles = (size_t)1 << 20;
+constexpr size_t kCacheEntries = 4;
+
+int acquire_model(gmb_ctx* ctx, int n, int P, int Q, const double* X, const double* Z, const double* y, const char* family, const char* link,
+                  gmb_model** out, bool* cached) {
+    *cached = false;
+    const size_t total = (size_t)n * ((size_t)P + Q + 1);
+    if (!g_object_cache || total > kCacheMaxDoubles || !family || !link) return gmb_model_create(ctx, n, P, Q, X, Z, y, family, link, out);
+    for (auto& e : g_models)
+        if (!e.busy && e.ctx == ctx && e.n == n && e.P == P && e.Q == Q && e.fam == family && e.link == link &&
+            memcmp(e.y.data(), y, sizeof(double) * n) == 0 && memcmp(e.X.data(), X, sizeof(double) * (size_t)n * P) == 0 &&
+            memcmp(e.Z.data(), Z, sizeof(double) * (size_t)n * Q) == 0) {
+            e.busy = true; e.stamp = ++g_stamp; *out = e.mdl; *cached = true;
+            return GMB_OK;
+        }
+    GMB_TRY(gmb_model_create(ctx, n, P, Q, X, Z, y, family, link, out));
+    if (g_models.size() >= kCacheEntries) {                                   // evict the least recently used idle entry
+        int victim = -1;
+        for (size_t k = 0; k < g_models.size(); k++) if (!g_models[k].busy && (victim < 0 || g_models[k].stamp < g_models[victim].stamp)) victim = (int)k;
+        if (victim < 0) return GMB_OK;                                        // all busy: this one is not kept
+        gmb_model_destroy(g_models[victim].mdl);
+        g_models.erase(g_models.begin() + victim);
+    }
+    g_models.push_back(CachedModel{ctx, n, P, Q, family, link, std::vector<double>(X, X + (size_t)n * P), std::vector<double>(Z, Z + (size_t)n * Q),
+                                   std::vector<double>(y, y + n), *out, true, ++g_stamp});
+    *cached = true;
+    return GMB_OK;
+}
+void release_model(gmb_model* mdl, bool cached) {
+    if (!mdl) return;
+    if (cached) { for (auto& e : g_models) if (e.mdl == mdl) { e.busy = false; return; } }
+    gmb_model_destroy(mdl);
+}
+
+int acquire_cov(gmb_ctx* ctx, const int32_t* cov, int rows, const double* data, int n_data, const double* eff, int n_eff, gmb_cov** out, bool* cached) {
+    *cached = false;
+    if (!g_object_cache || !cov || !data || rows <= 0 || n_data < 0 || (size_t)n_data > kCacheMaxDoubles || (size_t)rows > kCacheMaxDoubles)
+        return gmb_cov_create(ctx, cov, rows, data, n_data, eff, n_eff, out);
+    const int ne = eff ? n_eff : 0;
+    for (auto& e : g_covs)
+        if (!e.busy && e.ctx == ctx && e.rows == rows && e.n_data == n_data && e.n_eff == ne &&
+            memcmp(e.cov.data(), cov, sizeof(int32_t) * (size_t)rows * 5) == 0 && memcmp(e.data.data(), data, sizeof(double) * n_data) == 0 &&
+            (ne == 0 || memcmp(e.eff.data(), eff, sizeof(double) * ne) == 0)) {
+            e.busy = true; e.stamp = ++g_stamp; *out = e.cv; *cached = true;
+            return GMB_OK;
+        }
+    GMB_TRY(gmb_cov_create(ctx, cov, rows, data, n_data, eff, n_eff, out));
+    if (g_covs.size() >= kCacheEntries) {
+        int victim = -1;
+        for (size_t k = 0; k < g_covs.size(); k++) if (!g_covs[k].busy && (victim < 0 || g_covs[k].stamp < g_covs[victim].stamp)) victim = (int)k;
+        if (victim < 0) return GMB_OK;
+        gmb_cov_destroy(g_covs[victim].cv);
+        g_covs.erase(g_covs.begin() + victim);
+    }
+    g_covs.push_back(CachedCov{ctx, rows, n_data, ne, std::vector<int32_t>(cov, cov + (size_t)rows * 5), std::vector<double>(data, data + n_data),
+                               ne ? std::vector<double>(eff, eff + ne) : std::vector<double>(), *out, true, ++g_stamp});
+    *cached = true;
+    return GMB_OK;
+}
+void release_cov(gmb_cov* cv, bool cached) {
+    if (!cv) return;
+    if (cached) { for (auto& e : g_covs) if (e.cv == cv) { e.busy = false; return; } }
+    gmb_cov_destroy(cv);
+}
+
 struct Handles {
     gmb_cov* cv = nullptr; gmb_model* mdl = nullptr; int m_total = 0;
-    ~Handles() { if (mdl) gmb_model_destroy(mdl); if (cv) gmb_cov_destroy(cv); }
+    bool cv_cached = false, mdl_cached = false;
+    int make_model(gmb_ctx* ctx, int n, int P, int Q, const double* X, const double* Z, const double* y, const char* family, const char* link) {
+        return acquire_model(ctx, n, P, Q, X, Z, y, family, link, &mdl, &mdl_cached);
+    }
+    int make_cov(gmb_ctx* ctx, const int32_t* cov, int rows, const double* data, int n_data, const double* eff, int n_eff) {
+        return acquire_cov(ctx, cov, rows, data, n_data, eff, n_eff, &cv, &cv_cached);
+    }
+    ~Handles() { release_model(mdl, mdl_cached); release_cov(cv, cv_cached); }
 };
 
 int check_common(const void* cov, const void* data, const void* Z, const void* X, const void* y, int n, int P, int Q) {
@@ -219,11 +306,11 @@ int setup_fixed_u(gmb_ctx* ctx, const int32_t* cov, int cov_rows, const double* 
                   const char* family, const char* link, Handles& h) {
     GMB_TRY(check_common(cov, data, Z, X, y, n, P, Q));
     if (!u || m <= 0) return gmb_set_error(GMB_EINVAL, "u must have at least one column");
-    GMB_TRY(gmb_cov_create(ctx, cov, cov_rows, data, n_data, eff_range, n_eff, &h.cv));
+    GMB_TRY(h.make_cov(ctx, cov, cov_rows, data, n_data, eff_range, n_eff));
     int B, Qc, R;
     GMB_TRY(gmb_cov_dims(h.cv, &B, &Qc, &R));
     if (Qc != Q) return gmb_set_error(GMB_EINVAL, "covariance has %d random effects, Z has %d columns", Qc, Q);
-    GMB_TRY(gmb_model_create(ctx, n, P, Q, X, Z, y, family, link, &h.mdl));
+    GMB_TRY(h.make_model(ctx, n, P, Q, X, Z, y, family, link));
     // with an NCCL-enabled default context every rank passes ITS columns of u; the averages run over all of them
     double mt = (double)m;
     GMB_TRY(gmb_comm_allreduce_host(ctx, &mt, 1));
@@ -240,6 +327,21 @@ int default_chains(int m) {
 }  // namespace
 
 int gmb_default_ctx(gmb_ctx** out) { return default_ctx(out); }   // for laplace.cu
+
+// objects kept for `ctx` are destroyed with it (called by gmb_ctx_destroy before the context's streams go away)
+void gmb_api_release_ctx(gmb_ctx* ctx) {
+    for (size_t k = g_models.size(); k-- > 0;) if (g_models[k].ctx == ctx) { gmb_model_destroy(g_models[k].mdl); g_models.erase(g_models.begin() + k); }
+    for (size_t k = g_covs.size(); k-- > 0;) if (g_covs[k].ctx == ctx) { gmb_cov_destroy(g_covs[k].cv); g_covs.erase(g_covs.begin() + k); }
+    if (g_default_ctx == ctx) { g_default_ctx = nullptr; g_default_owned = false; }
+}
+extern "C" int gmb_set_object_cache(int on) {
+    g_object_cache = on ? 1 : 0;
+    if (!on) {
+        for (size_t k = g_models.size(); k-- > 0;) if (!g_models[k].busy) { gmb_model_destroy(g_models[k].mdl); g_models.erase(g_models.begin() + k); }
+        for (size_t k = g_covs.size(); k-- > 0;) if (!g_covs[k].busy) { gmb_cov_destroy(g_covs[k].cv); g_covs.erase(g_covs.begin() + k); }
+    }
+    return GMB_OK;
+}
 
 extern "C" int gmb_mcml_set_importance_form(int reference_form) { g_importance_reference_form = reference_form ? 1 : 0; return GMB_OK; }
 
@@ -277,7 +379,7 @@ extern "C" int gmb_mvn_ll(const int32_t* cov, int cov_rows, const double* data, 
     if (!cov || !data || !gamma || !u || !out) return gmb_set_error(GMB_EINVAL, "gmb_mvn_ll: NULL argument");
     gmb_ctx* ctx; GMB_TRY(default_ctx(&ctx));
     Handles h;
-    GMB_TRY(gmb_cov_create(ctx, cov, cov_rows, data, n_data, eff_range, n_eff, &h.cv));
+    GMB_TRY(h.make_cov(ctx, cov, cov_rows, data, n_data, eff_range, n_eff));
     int B, Qc, R;
     GMB_TRY(gmb_cov_dims(h.cv, &B, &Qc, &R));
     if (n_gamma < R) return gmb_set_error(GMB_EINVAL, "gamma has %d values, the covariance has %d parameters", n_gamma, R);
@@ -295,7 +397,7 @@ extern "C" int gmb_mcmc_sample(const double* Z, const double* L, const double* X
     gmb_ctx* ctx; GMB_TRY(default_ctx(&ctx));
     GmbPhase ph(ctx->stream);
     Handles h;
-    GMB_TRY(gmb_model_create(ctx, n, P, Q, X, Z, y, family, link, &h.mdl));
+    GMB_TRY(h.make_model(ctx, n, P, Q, X, Z, y, family, link));
     ph.mark("mcmc_sample: model upload");
     const int want = nsamp + 1;                                  // Q x (nsamp + 1), mhmcmc.h:126
     int C = n_chains > 0 ? n_chains : default_chains(nsamp);
@@ -414,12 +516,12 @@ extern "C" int gmb_mcml_full(const int32_t* cov, int cov_rows, const double* dat
     GMB_TRY(check_common(cov, data, Z, X, y, n, P, Q));
     gmb_ctx* ctx; GMB_TRY(default_ctx(&ctx));
     Handles h;
-    GMB_TRY(gmb_cov_create(ctx, cov, cov_rows, data, n_data, eff_range, n_eff, &h.cv));
+    GMB_TRY(h.make_cov(ctx, cov, cov_rows, data, n_data, eff_range, n_eff));
     int B, Qc, R;
     GMB_TRY(gmb_cov_dims(h.cv, &B, &Qc, &R));
     if (Qc != Q) return gmb_set_error(GMB_EINVAL, "covariance has %d random effects, Z has %d columns", Qc, Q);
     if (n_start < P + R + 1) return gmb_set_error(GMB_EINVAL, "start needs at least P + R + 1 = %d values (src/mcml_full.cpp:73,110)", P + R + 1);
-    GMB_TRY(gmb_model_create(ctx, n, P, Q, X, Z, y, family, link, &h.mdl));
+    GMB_TRY(h.make_model(ctx, n, P, Q, X, Z, y, family, link));
     const std::string fam(family ? family : "");
     std::vector<double> theta(start + P, start + P + R), beta(start, start + P);                   // :63-64
     double var_par = (fam == "gaussian" || fam == "Gamma") ? start[n_start - 1] : 1.0;             // :65

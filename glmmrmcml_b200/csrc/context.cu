@@ -214,9 +214,12 @@ extern "C" int gmb_comm_bcast_host(gmb_ctx* ctx, double* buf, int count) {
     return GMB_OK;
 }
 
+void gmb_api_release_ctx(gmb_ctx* ctx);   // api.cpp: device objects the entry points keep between calls
+
 extern "C" void gmb_ctx_destroy(gmb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    gmb_api_release_ctx(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->nccl_comm && g_nccl.destroy) g_nccl.destroy(ctx->nccl_comm);
     if (ctx->d_scratch) { gmb_dfree(ctx, ctx->d_scratch); cudaStreamSynchronize(ctx->stream); }

@@ -216,6 +216,11 @@ int gmb_cov_set_block_classes(int on);
  * Same sums in a different order.  Needs the sampler's row view (gmb_hmc_set_row_aggregation(1), the default).
  * gmb_model_estep_rows: rows of the zd the model currently holds. */
 int gmb_estep_set_row_aggregation(int on);
+
+/* The reference-named entry points (gmb_mcmc_sample, gmb_mcml_optim, gmb_mcml_hess, ...) keep the device objects of their last few
+ * (X, Z, y, family, link) and covariance specifications between calls — an R loop passes the same arrays again and again — and reuse them when
+ * a byte-for-byte comparison of those arrays matches: 1 (default) on, 0 off (and drop what is kept).  Results do not depend on it. */
+int gmb_set_object_cache(int on);
 int gmb_model_estep_rows(gmb_model* mdl, int* rows);
 int gmb_cov_block_classes(gmb_cov* cv, int* ncls);
 

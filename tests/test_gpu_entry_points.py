@@ -191,3 +191,47 @@ def test_mcml_hess_with_many_fixed_effects(gctx, oracle):
     for k in (0, 17, 16384, 39999):
         assert abs(ll[k] - mdl.log_likelihood(B[:, k], 1.0)) <= 1e-12 * abs(ll[k])
     mdl.close()
+
+
+def test_entry_points_reuse_their_device_objects_between_calls(gctx, oracle):
+    """gmb_set_object_cache: the entry points keep the device objects of the last models / covariance specifications and reuse them on a
+    byte-for-byte match of X, Z, y (and cov, data, eff_range) — same results with the cache on and off, in any interleaving of two models, after
+    a change of a single response, and after the context that owned them is gone."""
+    import glmmrmcml_b200 as g
+    gctx.make_default()
+    c1 = synth.config2(m=300, seed=31, ncl=8, nt=4, nind=6)
+    c2 = synth.config1(m=200)
+    out = {}
+    for on in (True, False, True):
+        g.set_object_cache(on)
+        res = []
+        for rep in range(2):
+            for cfg in (c1, c2):
+                start = np.concatenate([cfg["beta"], cfg["theta"], [1.0]])
+                L = synth.dense_chol_D(cfg["cov"], cfg["data"], cfg["theta"])
+                u = g.mcmc_sample(cfg["Z"], L, cfg["X"], cfg["y"], cfg["beta"], cfg["family"], cfg["link"], 30, 99, 1.0, 1.0, 0, 500, 20, 0.9, n_chains=4, seed=7)
+                fit = g.mcml_optim(cfg["cov"], cfg["data"], cfg["eff_range"], cfg["Z"], cfg["X"], cfg["y"], u, cfg["family"], cfg["link"], start, 0, True)
+                ll = g.mvn_ll(cfg["cov"], cfg["data"], cfg["eff_range"], cfg["theta"], u)
+                res.append((u.copy(), fit["beta"].copy(), fit["theta"].copy(), ll))
+        y2 = c1["y"].copy(); y2[3] = 1.0 - y2[3]                     # one response flipped: a different model, not the cached one
+        start = np.concatenate([c1["beta"], c1["theta"], [1.0]])
+        fit2 = g.mcml_optim(c1["cov"], c1["data"], c1["eff_range"], c1["Z"], c1["X"], y2, res[0][0], c1["family"], c1["link"], start, 0, True)
+        out[len(out)] = (res, fit2["beta"].copy())
+    g.set_object_cache(True)
+    base, b2 = out[0]
+    for k in (1, 2):
+        res, bb = out[k]
+        for a, b in zip(base, res):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3]
+        assert np.array_equal(b2, bb)
+    assert not np.array_equal(b2, base[0][1])                       # the flipped response changed the fit
+    # the two repetitions inside one setting agree as well (second one runs on the kept objects)
+    assert np.array_equal(base[0][1], base[2][1]) and np.array_equal(base[1][1], base[3][1])
+    # objects kept for a context go with it
+    ctx2 = g.Context(0); ctx2.make_default()
+    start = np.concatenate([c2["beta"], c2["theta"], [1.0]])
+    f_a = g.mcml_optim(c2["cov"], c2["data"], c2["eff_range"], c2["Z"], c2["X"], c2["y"], base[1][0], c2["family"], c2["link"], start, 0, True)
+    gctx.make_default()
+    ctx2.close()
+    f_b = g.mcml_optim(c2["cov"], c2["data"], c2["eff_range"], c2["Z"], c2["X"], c2["y"], base[1][0], c2["family"], c2["link"], start, 0, True)
+    assert np.array_equal(f_a["beta"], f_b["beta"]) and np.array_equal(f_a["theta"], f_b["theta"])
