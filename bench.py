@@ -275,9 +275,9 @@ def cpu_hoisted_and_full_m(cfg, det, threads=None, quick=False):
                                 "how": "sampler, log-likelihood and mvn_ll pieces x m / m_sample; MCNR x (m / m_sample)^exponent with the exponent measured in this run"}}
 
 
-def cpu_arm(cfg, threads, quick):
+def cpu_arm(cfg, threads, quick, m_s=CPU_SAMPLE_M):
     """(seconds per bounded sample, detail, kind, sample description) of the CPU arm."""
-    t, det = cpu_reference_sample(cfg, threads=threads, quick=quick)
+    t, det = cpu_reference_sample(cfg, threads=threads, m_s=m_s, quick=quick)
     sample = ("oracle FAITHFUL (the reference's loop structure incl. its redundant Z u GEMMs and per-sample Cholesky) on m_sample = %d of the step's "
               "10^4 samples, every piece run for real: one HMC chain of %d proposals, 1 MCNR step, %d log-likelihood and %d mvn_ll evaluations; "
               "value = m_sample / time (the reference's MCNR cost grows faster than m, so the smaller sample FAVOURS the CPU arm)"
@@ -367,9 +367,13 @@ def main():
         oracle.build()
         vals, det = [], None
         ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        # bounded sample: the whole --steps K run should end within a few minutes.  A step at m_sample = 2500 takes ~12 s on 16 cores; with more than
+        # 12 timed steps the sample shrinks in proportion (never below 500).  value = m_sample / time either way — and a smaller sample favours the
+        # CPU arm, whose MCNR cost grows faster than m.
+        m_s = CPU_SAMPLE_M if args.steps <= 12 else max(500, int(CPU_SAMPLE_M * 12 / args.steps) // 100 * 100)
         for it in range(args.warmup + args.steps):
             # warm-up steps run a small sample (page-in, thread pool start); torchrun exports OMP_NUM_THREADS=1: the thread count is set explicitly
-            t, d, kind, smp = cpu_arm(cfg, ncores, args.quick or it < args.warmup)
+            t, d, kind, smp = cpu_arm(cfg, ncores, args.quick or it < args.warmup, m_s)
             if it >= args.warmup:
                 vals.append(t); det = d; sample = smp
         t_step = float(np.median(vals)) if vals else float("nan")
