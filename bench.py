@@ -86,7 +86,7 @@ def sampler_roofline(st, exec_tflops, algo_tflops, exec_per_step, cfg, Q, dense_
                     "contraction (4 n Q = 1e5 per step and chain) is `algorithmic_tflops`: the kernel does the same arithmetic on the 150 non-zeros "
                     "of the 50 distinct rows instead of 500 x 50 entries, so that figure exceeds the pipe peak.  1000 chains x 10 blocks = 313 warps "
                     "on 592 schedulers: every warp has a scheduler to itself and runs one dependent FP64 chain (ncu, profiles/r02_ncu_hmc_hmc_lane.txt: "
-                    "FP64 pipe 55 % busy on the active schedulers, 6 % of the warp slots) — bound by FP64 latency x trajectory length, not by pipe "
+                    "FP64 pipe 32 % busy averaged over the SMs — 334 one-warp CTAs, 2.3 per SM —, 3.5 % of the warp slots) — bound by FP64 latency x trajectory length, not by pipe "
                     "throughput; `dense_kernel` is the DMMA kernel a model with a dense Z L runs",
             "dense_kernel": dense_probe})
         if many_probe and many_probe.get("kernel_variant") == 3:
