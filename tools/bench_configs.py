@@ -234,21 +234,21 @@ def run_config(name, env, size="full", oracle=None, check=True):
         # the streaming evaluation (forward substitution of all m sample columns) is the roofline kernel; the default on one rank with m >= 2 n_b is
         # the Cholesky factor of the block's Gram matrix (built once per sample matrix): n_b^3 / 3 flop per theta instead of n_b^2 m
         gram_used = env.world == 1 and m_local >= 2 * int(nb.max())
-        t_stream = t_d
+        t_mvn_stream = t_d
         if gram_used:
             g.cov_set_gram(False)
             try:
                 cv.loglik_model(th1, mdl)
-                t_stream = env.max(timed(ctx, mvn_new, reps=3))
+                t_mvn_stream = env.max(timed(ctx, mvn_new, reps=3))
             finally:
                 g.cov_set_gram(True)
             out["mvn_ll"].update({"default_path": "Cholesky factor of the block's Gram matrix (one SYRK + factorisation per sample matrix), triangular right-hand sides per theta",
-                                  "ms_streaming": t_stream, "executed_flops_default": fl_fac + float(np.sum(nb ** 3) / 3)})
+                                  "ms_streaming": t_mvn_stream, "executed_flops_default": fl_fac + float(np.sum(nb ** 3) / 3)})
         out["mvn_ll"]["roofline"] = {"bound": "fp64", "kernel": "blocked Cholesky + blocked forward substitution of the m sample columns (DMMA)" + (" — the streaming evaluation, Gram path off" if gram_used else ""),
-                                     "achieved": (fl_fac + fl_solve) / t_stream / 1e9,
-                                     "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": (fl_fac + fl_solve) / t_stream / 1e9 / FP64_PEAK_TFLOPS,
-                                     "flops_per_launch": fl_fac + fl_solve, "ms": t_stream, "factor_tflops": fl_fac / t_f / 1e9, "factor_frac": fl_fac / t_f / 1e9 / FP64_PEAK_TFLOPS,
-                                     "solve_tflops": fl_solve / max(t_stream - t_f, 1e-6) / 1e9}
+                                     "achieved": (fl_fac + fl_solve) / t_mvn_stream / 1e9,
+                                     "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": (fl_fac + fl_solve) / t_mvn_stream / 1e9 / FP64_PEAK_TFLOPS,
+                                     "flops_per_launch": fl_fac + fl_solve, "ms": t_mvn_stream, "factor_tflops": fl_fac / t_f / 1e9, "factor_frac": fl_fac / t_f / 1e9 / FP64_PEAK_TFLOPS,
+                                     "solve_tflops": fl_solve / max(t_mvn_stream - t_f, 1e-6) / 1e9}
     else:
         # default path: Gram matrices of the samples, independent of m; the streaming forward substitution is the HBM-bound kernel
         g.cov_set_gram(False)
