@@ -49,6 +49,8 @@ def lib():
         _LIB.orc_mcnr_sums_zd.restype = C.c_double
         _LIB.orc_logdet.restype = C.c_double
         _LIB.orc_log_prob.restype = C.c_double
+        _LIB.orc_digamma.restype = C.c_double
+        _LIB.orc_digamma.argtypes = [C.c_double]
         _LIB.orc_rng_uniform.restype = C.c_double
         _LIB.orc_rng_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32]
     return _LIB
@@ -75,6 +77,10 @@ def flink(family: str, link: str) -> int:
 
 def family_ll(y, mu, var_par, fl):
     return lib().orc_family_ll(float(y), float(mu), float(var_par), int(fl))
+
+
+def digamma(x):
+    return lib().orc_digamma(float(x))
 
 
 def log_factorial_approx(n):

@@ -50,6 +50,14 @@ static inline double log_factorial_approx(double n) {
 
 // standard normal cdf standing in for R::pnorm (moremaths.h:70-72)
 static inline double pnorm_std(double x) { return 0.5 * std::erfc(-x / std::sqrt(2.0)); }
+// boost::math::digamma (mcmlmodel.h:271, beta family): recurrence up to x >= 6, then the asymptotic series through B10 (truncation < 1e-11; against scipy in tests/test_oracle_closed_form.py)
+static inline double digamma(double x) {
+    double r = 0;
+    while (x < 6) { r -= 1 / x; x += 1; }
+    const double f = 1 / (x * x);
+    return r + std::log(x) - 0.5 / x - f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f / 132))));
+}
+ORC_API double orc_digamma(double x) { return digamma(x); }
 
 // moremaths.h:26-102; flink codes from mcmlmodel.h:74-87
 static inline double family_ll(double y, double mu, double var_par, int flink) {
@@ -599,10 +607,18 @@ static void log_grad(int n, int Q, const double* ZL, const double* xb, const dou
                 if (y[i] == 1) mu[i] = pdf / pnorm_std(mu[i]); else if (y[i] == 0) mu[i] = -1.0 * pdf / (1 - pnorm_std(mu[i]));
             } break;
     case 7: case 8: for (int i = 0; i < n; i++) mu[i] = (y[i] - mu[i]); break;           // :233-244 (scaled below)
+    // codes 9-12: oracle only (no device kernel; the Gamma codes cannot be reached from R, whose family string is "Gamma", :83-85)
+    case 9: for (int i = 0; i < n; i++) mu[i] = y[i] * std::exp(-1.0 * mu[i]) - 1; break;          // :245-253 (scaled by var_par below)
+    case 10: for (int i = 0; i < n; i++) mu[i] = 1 / mu[i] - y[i]; break;                          // :254-259
+    case 11: for (int i = 0; i < n; i++) { const double r = 1 / mu[i]; mu[i] = y[i] * r * r - r; } break;   // :260-265
+    case 12: for (int i = 0; i < n; i++) {                                               // :266-275: the second statement reads the UPDATED mu(i)
+                 const double p = std::exp(mu[i]) / (std::exp(mu[i]) + 1);               //   (= p), so its factor is p / (1 + exp(p)) — kept as written
+                 mu[i] = (p / (1 + std::exp(p))) * var_par * (std::log(y[i]) - std::log(1 - y[i]) - digamma(p * var_par) + digamma((1 - p) * var_par));
+             } break;
     default: for (int i = 0; i < n; i++) mu[i] = NAN;
     }
     gemv_t(n, Q, ZL, mu, grad);
-    double sc = (flink == 7 || flink == 8) ? 1.0 / (var_par * var_par) : 1.0;
+    double sc = (flink == 7 || flink == 8) ? 1.0 / (var_par * var_par) : (flink >= 9 && flink <= 11) ? var_par : 1.0;
     for (int q = 0; q < Q; q++) grad[q] = -1.0 * v[q] + sc * grad[q];                    // :163, :173
 }
 

@@ -124,3 +124,11 @@ def test_rng_streams(oracle):
     assert not np.array_equal(z[:100], oracle.rng_normal_vec(123, 4, 6, 2, 100))
     u = np.array([oracle.rng_uniform(9, t, 0, 3) for t in range(2000)])
     assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.03
+
+
+def test_digamma_against_scipy(oracle):
+    """The oracle's stand-in for boost::math::digamma (beta family gradient, mcmlmodel.h:271)."""
+    from scipy.special import digamma
+    x = np.concatenate([np.linspace(0.05, 6, 60), np.linspace(6, 200, 40)])
+    got = np.array([oracle.digamma(t) for t in x])
+    assert np.max(np.abs(got - digamma(x)) / np.maximum(1.0, np.abs(digamma(x)))) <= 1e-10
