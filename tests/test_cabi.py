@@ -115,3 +115,44 @@ def test_objective_error_aborts_cleanly():
         raise RuntimeError("boom")
     with pytest.raises(g.GmbError):
         g.minimize_bounded(bad, [1.0, 2.0])
+
+
+C_CONSUMER = r"""
+/* a C99 consumer of the boundary, as cgo / a .Call shim / any FFI generator would see it */
+#include <stdio.h>
+#include <string.h>
+#include "glmmrmcml_b200.h"
+int main(void) {
+    int B = 0, Q = 0, R = 0;
+    int32_t cov[10] = {0, 1, 3, 3, 1, 1, 1, 1, 0, 1};   /* column-major 2 x 5: blocks 0 and 1 of dimension 3, each gr (id 1) on 1 variable, parameters theta[0] and theta[1] */
+    gmb_ctx* ctx = NULL;
+    if (strstr(gmb_version(), "sm_100a") == NULL) return 10;
+    if (gmb_cov_shape(cov, 2, &B, &Q, &R) != GMB_OK) { fprintf(stderr, "%s\n", gmb_last_error()); return 11; }
+    printf("B=%d Q=%d R=%d\n", B, Q, R);
+    cov[4] = 99;                                        /* unknown covariance function id */
+    if (gmb_cov_shape(cov, 2, &B, &Q, &R) == GMB_OK || strlen(gmb_last_error()) == 0) return 12;
+    if (gmb_ctx_create(0, &ctx) == GMB_OK) { gmb_ctx_destroy(ctx); printf("device present\n"); }
+    else printf("no device: %s\n", gmb_last_error());
+    return 0;
+}
+"""
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """include/glmmrmcml_b200.h compiled by a C compiler (-std=c99 -pedantic -Werror: no C++ in the boundary), linked against the
+    shared library, host-only entry points called from C."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "consumer.c"
+    src.write_text(C_CONSUMER)
+    exe = tmp_path / "consumer"
+    libdir = os.path.join(ROOT, "glmmrmcml_b200")
+    r = subprocess.run([cc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lglmmrmcml_b200", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "B=2 Q=6 R=2" in r.stdout
