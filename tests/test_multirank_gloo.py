@@ -81,6 +81,60 @@ def test_two_rank_sharded_estep_equals_single_rank():
     assert abs(res["d"] - res["d_full"]) <= 1e-12 * abs(res["d_full"])
 
 
+def _chain_worker(rank, world, port, q):
+    """One MCML iteration of src/mcml_full.cpp:83-126 with the CHAINS split over the ranks the way gmb_mcml_full does it
+    (csrc/api.cpp: C_local = ceil(C / world), rank r runs the global chains [r C_local, (r+1) C_local) on the Philox streams of their
+    global index, every rank all-reduces its MCNR sums): same samples and same Newton step as all chains on one rank."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import oracle
+    from glmmrmcml_b200 import synth
+    cfg = synth.config2(m=8)
+    fl = oracle.flink(cfg["family"], cfg["link"])
+    X, Z, y, L, beta = cfg["X"], cfg["Z"], cfg["y"], cfg["L"], cfg["beta"]
+    ZL = oracle.gemm(Z, L); xb = X @ beta
+    C_total, per, seed = 6, 4, 20221208
+    C_local = (C_total + world - 1) // world
+
+    def draw(chains):
+        cols = [oracle.hmc_chain(ZL, L, xb, y, 1.0, fl, 12, per - 1, 0.3, 20, 0.9, seed, chain=c)["u"] for c in chains]
+        return np.asfortranarray(np.concatenate(cols, axis=1))          # chain-major, per columns each (column 0 = state after warm-up)
+
+    Uloc = draw(range(rank * C_local, (rank + 1) * C_local))
+    nl, tot = Uloc.shape[1], C_total * per
+    loc = oracle.mcnr(X, Z, Uloc, y, beta, 1.0, fl)
+    P = cfg["P"]
+    pack = torch.tensor(np.concatenate([loc["xtwx"].ravel(order="F") * nl, loc["score"] * nl]))
+    dist.all_reduce(pack)
+    xtwx = pack[: P * P].numpy().reshape(P, P, order="F") / tot
+    step = np.linalg.solve(xtwx, pack[P * P:].numpy() / tot)
+    gathered = [torch.zeros(Uloc.shape, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(gathered, torch.tensor(np.ascontiguousarray(Uloc)))
+    if rank == 0:
+        Uall = draw(range(C_total))
+        full = oracle.mcnr(X, Z, Uall, y, beta, 1.0, fl)
+        q.put(dict(u_equal=bool(np.array_equal(np.concatenate([g.numpy() for g in gathered], axis=1), Uall)),
+                   step_err=float(np.max(np.abs(step - full["beta_incr"]))), cols=int(Uall.shape[1]), tot=tot))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_chain_sharding_reproduces_the_single_rank_iteration():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_chain_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res["cols"] == res["tot"] and res["u_equal"]          # same chains, same streams, chain-major order
+    assert res["step_err"] < 1e-11
+
+
 def test_shard_covers_all_columns():
     for m in (1, 7, 10_000, 100_003):
         for w in (1, 2, 4, 8):
