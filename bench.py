@@ -270,9 +270,31 @@ def cpu_hoisted_and_full_m(cfg, det, threads=None, quick=False):
     per_prop = det["hmc_s"] / det["hmc_proposals"]
     full = per_prop * (HMC["warmup"] + M_PER_GPU) + det["mcnr_s"] * f ** expo + (det["estep_s"] + det["mvn_s"]) * f
     return {"hoisted_step_s": float(hoisted), "hoisted_value": m_s / hoisted, "hoisted_loglik_s_per_eval": t_llh,
-            "mcnr_scaling_exponent_measured": expo,
+            "mcnr_scaling_exponent_measured": expo, "reference_headers": reference_headers_timing(det, threads),
             "full_m_estimate": {"m": M_PER_GPU, "step_s": float(full), "value": M_PER_GPU / full,
                                 "how": "sampler, log-likelihood and mvn_ll pieces x m / m_sample; MCNR x (m / m_sample)^exponent with the exponent measured in this run"}}
+
+
+def reference_headers_timing(det, threads):
+    """Beside the arm's value: the reference's OWN headers (oracle/_ref/libref_omp.so, compiled against the stand-in Eigen / Rcpp of
+    oracle/shim) timed piece by piece next to the port on one small sample (tools/ref_headers_timing.py, ~5 s, in a subprocess: the OpenMP
+    build of mcmloptim::mcnr races, so a fault there must not take the bench line with it).  `value_scaled` = the arm's own pieces multiplied by
+    the measured headers / port ratios — what the arm would report if it timed the headers instead of the port."""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_headers_timing.py"), str(int(threads or 1))],
+                           capture_output=True, text=True, timeout=240)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"unavailable": "rc %d: %s" % (r.returncode, (r.stderr or r.stdout)[-200:])}
+        out = json.loads(lines[-1])
+        if "unavailable" not in out:
+            scaled = (det["hmc_s"] * out["hmc_s_per_proposal"]["headers_over_port"] + det["mcnr_s"] * out["mcnr_s"]["headers_over_port"]
+                      + det["estep_s"] * out["loglik_s_per_eval"]["headers_over_port"] + det["mvn_s"] * out["mvn_ll_s_per_eval"]["headers_over_port"])
+            out["step_s_scaled"] = float(scaled)
+            out["value_scaled"] = det["m_sample"] / scaled
+        return out
+    except Exception as e:      # the port's number stands on its own
+        return {"unavailable": str(e)[:200]}
 
 
 def cpu_arm(cfg, threads, quick, m_s=CPU_SAMPLE_M):
