@@ -3,7 +3,8 @@
 pragmas on) timed piece by piece beside the oracle's FAITHFUL port on the SAME small sample of the C2 step.  bench.py runs this in a
 subprocess (the OpenMP build of mcmloptim::mcnr races, SURVEY §5 — its numbers are timings, never compared) and reports the ratios in
 `cpu_baseline.detail.reference_headers`: they show that the port, whose time is the CPU arm's value, is not slower than the headers it restates
-(the stand-in Eigen of oracle/shim evaluates products with plain loops).  Test infrastructure; prints one JSON line.
+(the stand-in Eigen of oracle/shim evaluates products with plain loops).  Also: the port's pieces on ONE thread (`port_single_thread`,
+`port_parallel_speedup` — a single HMC chain of this size does not speed up with threads).  Test infrastructure; prints one JSON line.
 Usage: ref_headers_timing.py [threads] [m_sample] [proposals]"""
 import json
 import os
@@ -66,6 +67,16 @@ def main():
     out["mvn_ll_s_per_eval"] = {"headers": t_ref, "port": t_port}
     for k in ("hmc_s_per_proposal", "mcnr_s", "loglik_s_per_eval", "mvn_ll_s_per_eval"):
         out[k]["headers_over_port"] = out[k]["headers"] / out[k]["port"]
+    # the port once more on ONE thread (SURVEY §8d asks for both thread counts): how much of the CPU arm's speed is parallelism
+    oracle.set_threads(1)
+    p1 = max(40, props // 4)
+    one = {"hmc_s_per_proposal": clock(lambda: oracle.hmc_chain(ZL, L, xb, y, 1.0, fl, p1 // 4, p1 - p1 // 4, 5.0, 100, 0.95, 12345, want_u=False)) / p1,
+           "mcnr_s": clock(lambda: oracle.mcnr(X, Z, U, y, beta, 1.0, fl, faithful=True)),
+           "loglik_s_per_eval": clock(lambda: oracle.loglik_faithful(X, Z, U, y, beta, 1.0, fl), reps=2),
+           "mvn_ll_s_per_eval": clock(lambda: oracle.mvn_loglik(*cov, theta, U, faithful=True), reps=2)}
+    out["port_single_thread"] = one
+    out["port_parallel_speedup"] = {k: one[k] / out[k]["port"] for k in one}
+    oracle.set_threads(threads)
     out["what"] = ("oracle/_ref/libref_omp.so = the reference's own headers compiled against oracle/shim (stand-in Eigen / Rcpp / glmmrBase), OpenMP on; "
                    "`port` = oracle FAITHFUL on the same inputs and thread count; ratio > 1: the headers are slower than the port the CPU arm times")
     print(json.dumps(out))
