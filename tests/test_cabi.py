@@ -156,3 +156,15 @@ def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert "B=2 Q=6 R=2" in r.stdout
+
+
+def test_missing_library_fails_loudly():
+    """Without the built .so the package raises at first use — there is nothing to fall back to."""
+    import subprocess
+    import sys
+    code = ("import numpy as np, glmmrmcml_b200 as g\n"
+            "try:\n    g.mvn_ll(np.array([[0, 1, 1, 1, 0]], dtype=np.int32), np.zeros(1), np.zeros(1), np.ones(1), np.zeros((1, 2)))\n"
+            "except Exception as e:\n    print('RAISED', type(e).__name__, e)\n")
+    env = dict(os.environ, GMB_LIB="/nonexistent/libglmmrmcml_b200.so", PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert "RAISED" in r.stdout and "libglmmrmcml_b200" in r.stdout, (r.stdout, r.stderr)
