@@ -370,7 +370,7 @@ __device__ __forceinline__ double dev_exp(double x) {
 // Table-driven exp for the sampler's inner loop: exp(x) = 2^e * T[j] * exp(r) with x = (64 e + j) ln2/64 + r,
 // |r| <= ln2/128, T = 2^(j/64) (64 doubles staged in shared memory from GMB_EXP2_TAB) and a degree-5 polynomial for
 // exp(r) - 1 (truncation error r^6/720 < 4e-17).  10 FP64-pipe operations and no branch, against ~18 + a range branch for
-// the library exp; error <= 1 ulp.  The binary exponent is saturated at +-1008 (e^+-698.7) with integer min/max: beyond
+// the library exp; error within 1.2 ulp of the exact value (tests/test_device_math_constants.py).  The binary exponent is saturated at +-1008 (e^+-698.7) with integer min/max: beyond
 // that the family residuals that use it are already saturated (1/(1 + e^698) + y - 1 == y - 1 in double precision);
 // valid for |x| < 2e7 (the integer part must fit 32 bits), NaN for NaN.
 __device__ __forceinline__ double dev_exp_tab(double x, const double* __restrict__ tab) {

@@ -77,7 +77,7 @@ __device__ __forceinline__ void dev_family_resid_w_vec(const double (&c)[N], con
 // The same residual with a 16-entry table of 2^(j/16) (128 bytes: every lookup pattern is bank-conflict free; random lookups in the 64-entry
 // table cost ~5 wavefronts each and were a quarter of the register kernel's shared-memory traffic) and a degree-6 polynomial for
 // (exp(r) - 1) / r on |r| <= ln2/32 (truncation r^8/40320 < 1.3e-18), evaluated in Estrin form: the dependent depth stays that of the
-// 64-entry variant's degree-4 Horner chain.  Error <= 1 ulp; rounding differs from dev_family_resid_w in the last bit.
+// 64-entry variant's degree-4 Horner chain.  Error within 1.1 ulp of the exact value; rounding differs from dev_family_resid_w in the last bit.
 static __constant__ double SP_EXPC16[12] = {
     23.083120654223414,             // 0: 16 / ln2
     6755399441055744.0,             // 1: 1.5 * 2^52

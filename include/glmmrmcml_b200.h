@@ -66,7 +66,7 @@ int gmb_comm_bcast_host(gmb_ctx* ctx, double* buf, int count);
 
 /* ---- model: replaces glmmr::mcmlModel ------------------------------------------------------------------ */
 /* mcmlModel ctor, mcmlmodel.h:51-98.  X is n x P, Z is n x Q, y length n.  family/link as in :74-87;
- * in scope: poisson/log (1), binomial/logit (3), gaussian/identity (7). */
+ * device kernels: codes 1-8 (1 poisson/log, 3 binomial/logit, 7 gaussian/identity on every kernel family; 2, 4, 5, 6, 8 on the general ones). */
 int  gmb_model_create(gmb_ctx* ctx, int n, int P, int Q, const double* X, const double* Z, const double* y,
                       const char* family, const char* link, gmb_model** out);
 /* The same with a storage precision for the streamed E-step matrices zd = Z u and (binomial/logit) F = exp(+-zd): 64 (what gmb_model_create
