@@ -133,3 +133,53 @@ def test_family_terms_of_the_gamma_and_beta_codes(oracle):
             sg = float(rng.uniform(0.3, 3))
             a, b = oracle.family_ll(y, mu, sg, fl), ref.family_ll(y, mu, sg, fl)
             assert np.isfinite(b) and (a == b or abs(a - b) <= 1e-15 * abs(b)), (fl, a, b)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_one_iteration_of_the_oracle_mcml_loop_is_the_reference_iteration(name, oracle):
+    """oracle/mcml_loop.py (the checker of tests/test_gpu_fit_parity.py) against the reference's own headers, piece by piece, for the first
+    MCML iteration of src/mcml_full.cpp:83-126: the samples are mcmcRunHMC::sample's on the same Philox stream (Q x (m + 1)), the beta
+    step is mcmloptim::mcnr on the first m columns (niter_ = m, App. B #1), and the theta step minimises the reference's D_likelihood over
+    all m + 1 columns (checked as a local optimum of -MCMLDmatrix::loglik; rminqa's BOBYQA itself is not available)."""
+    from oracle import mcml_loop
+    cfg = CASES[name]()
+    fam, link = cfg["family"], cfg["link"]
+    X, Z, y = cfg["X"], cfg["Z"], cfg["y"]
+    cov = (cfg["cov"], cfg["data"], cfg["eff_range"])
+    P, R = cfg["P"], cfg["theta"].size
+    start = np.concatenate([cfg["beta"] * 0.8, cfg["theta"] * 1.2, [1.0]])
+    m, warm, lam, ms, tgt, seed = 24, 30, 0.5, 20, 0.9, 777
+    fit = mcml_loop.mcml_full(*cov, Z, X, y, fam, link, start, mcnr=True, m=m, maxiter=1, warmup=warm, tol=1e-12, lam=lam, maxsteps=ms,
+                              target_accept=tgt, seed=seed)
+    assert fit["iter"] == 1 and fit["u"].shape == (cfg["Q"], m + 1)
+    L0 = oracle.genD(*cov, start[P:P + R], chol=True)
+    u_ref, _ = ref.mcmc_sample(X, Z, L0, y, start[:P], fam, link, warm, m, lam, 1.0, ms, tgt, (seed + mcml_loop.GOLDEN) & mcml_loop.MASK, chain=0)
+    assert np.max(np.abs(fit["u"] - u_ref)) <= 1e-12 * max(1.0, np.max(np.abs(u_ref)))
+    b_ref, _ = ref.mcnr(*cov, X, Z, u_ref[:, :m], y, fam, link, start)
+    assert np.max(np.abs(fit["beta"] - b_ref)) <= 1e-10 * max(1.0, np.max(np.abs(b_ref)))
+    f0 = -ref.mvn_loglik(*cov, fit["theta"], u_ref)
+    for r in range(R):
+        for h in (-1e-3, 1e-3):
+            th = fit["theta"].copy(); th[r] = max(th[r] + h, 1e-6)
+            assert -ref.mvn_loglik(*cov, th, u_ref) >= f0 - 1e-9 * abs(f0), (r, h)
+
+
+def test_the_mcem_beta_step_of_the_oracle_loop_minimises_the_reference_objective(oracle):
+    """method = 'mcem' (l_optim, mcmloptim.h:71-88): the oracle loop's beta after one iteration is a local minimum of the reference's own
+    L_likelihood (-mcmlModel::log_likelihood on the first m columns of that iteration's samples)."""
+    from oracle import mcml_loop
+    cfg = CASES["C1"]()
+    fam, link = cfg["family"], cfg["link"]
+    X, Z, y = cfg["X"], cfg["Z"], cfg["y"]
+    cov = (cfg["cov"], cfg["data"], cfg["eff_range"])
+    P = cfg["P"]
+    start = np.concatenate([cfg["beta"] * 0.8, cfg["theta"], [1.0]])
+    m = 24
+    fit = mcml_loop.mcml_full(*cov, Z, X, y, fam, link, start, mcnr=False, m=m, maxiter=1, warmup=30, tol=1e-12, lam=0.5, maxsteps=20,
+                              target_accept=0.9, seed=99)
+    U = np.asfortranarray(fit["u"][:, :m])
+    f0 = -ref.loglik(X, Z, U, y, fit["beta"], 1.0, fam, link)
+    for p in range(P):
+        for h in (-1e-3, 1e-3):
+            b = fit["beta"].copy(); b[p] += h
+            assert -ref.loglik(X, Z, U, y, b, 1.0, fam, link) >= f0 - 1e-10 * abs(f0), (p, h)
