@@ -40,6 +40,11 @@ struct ListEntry { std::string name; int rows = 0, cols = 0; std::vector<double>
 struct Named {
     std::string name;
     template <class T>
+    ListEntry operator=(const std::vector<T>& x) const {          // the *_sparse exports return std::vector members (src/mcml_optim.cpp:181-182)
+        ListEntry e; e.name = name; e.rows = (int)x.size(); e.cols = 1; e.v.assign(x.begin(), x.end());
+        return e;
+    }
+    template <class T>
     ListEntry operator=(const T& x) const {
         ListEntry e; e.name = name;
         if constexpr (std::is_arithmetic<T>::value) { e.rows = e.cols = 1; e.v.assign(1, (double)x); }

@@ -190,9 +190,12 @@ template <class S, int R, int C> struct Matrix : MatrixXd { using MatrixXd::Matr
 // Eigen::Map<M>(ptr, n [, m]) : read-only use in the reference (copy semantics suffice)
 template <class M>
 struct Map : M {
-    Map(typename M::Scalar* p, int n) : M(n) { for (int i = 0; i < n; i++) this->d[i] = p[i]; }
+    Map(typename M::Scalar* p, int n) : M(n), wp_(p) { for (int i = 0; i < n; i++) this->d[i] = p[i]; }
     Map(typename M::Scalar* p, int rr, int cc) : M(rr, cc) { for (size_t i = 0; i < this->d.size(); i++) this->d[i] = p[i]; }
     Map(const Rcpp::NumericVector& z) : M((int)z.v.size()) { for (size_t i = 0; i < z.v.size(); i++) this->d[i] = z.v[i]; }
+    // Eigen::Map<T>(ptr, n) = value : writes through to the mapped memory (sparsedmatrix.h:32-34)
+    typename M::Scalar* wp_ = nullptr;
+    Map& operator=(const M& o) { if (wp_) for (size_t i = 0; i < o.d.size() && i < this->d.size(); i++) wp_[i] = o.d[i]; this->d = o.d; return *this; }
 };
 
 template <class M>

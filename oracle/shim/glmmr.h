@@ -107,4 +107,13 @@ public:
     }
 };
 
+// DSubMatrix(b, data, gamma): one block's entry function — only the reference's sparse-D variant constructs it (sparsedmatrix.h:62-66, out of scope);
+// provided so that the reference's src/*.cpp compile as they are
+class DSubMatrix {
+public:
+    DMatrix m_;
+    DSubMatrix(int b, DData* data, const Eigen::ArrayXd& gamma) : m_(data, gamma) { if (data->b_ != b) data->subdata(b); }
+    double get_val(int i, int j) const { return m_.get_val(i, j); }
+};
+
 }  // namespace glmmr

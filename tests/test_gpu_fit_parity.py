@@ -5,6 +5,8 @@ gmb_mcml_full with n_chains = 1 is the reference's loop with its single chain (s
 oracle-side loop (oracle/mcml_loop.py: oracle chain + scipy bounded minimisers on the oracle's objectives) runs on the SAME Philox
 stream, so the two fits can be compared iterate for iterate and seed for seed — not only in the mean over seeds: over >= 10 seeds per
 configuration every seed's estimates agree far below the reference's tolerance (C1: tol 5e-3, MCEM; C2: tol 1e-2, MCNR)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -12,6 +14,20 @@ from glmmrmcml_b200 import synth
 
 pytestmark = pytest.mark.gpu
 SEEDS = list(range(101, 111))          # 10 seeds
+
+
+def _refsrc_gold(name, seed):
+    """The fit of the reference's OWN src/mcml_full.cpp (compiled unmodified against oracle/shim: oracle/refsrc_driver.cpp) for this
+    configuration, these settings and this seed's Philox stream — tests/golden/REFSRC_mcml_full.npz, made by
+    tests/golden/make_golden_refsrc.py.  On the CPU, tests/test_refsrc.py and tools/check_refsrc_golden.py hold the oracle loop to the
+    same file at 1e-6, so the tolerances below are the oracle-loop tolerances plus a margin."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "REFSRC_mcml_full.npz")
+    if not os.path.exists(path):
+        return None
+    z = np.load(path)
+    k = [int(s) for s in z["seeds"]].index(int(seed))
+    return dict(beta=z[name + "_beta"][k], theta=z[name + "_theta"][k], converged=bool(z[name + "_converged"][k]), u_last=z[name + "_u_last_column"][k],
+                start=z[name + "_start"])
 
 
 def _fit_pair(g, mcml_loop, cfg, start, seed, **kw):
@@ -37,6 +53,11 @@ def test_c2_mcnr_fit_follows_the_oracle_loop_over_10_seeds(gctx, oracle):
         assert np.max(np.abs(dev["theta"] - orc["theta"])) <= 1e-4, (seed, dev["theta"], orc["theta"])
         assert dev["u"].shape == orc["u"].shape == (cfg["Q"], 251)
         assert np.max(np.abs(dev["u"] - orc["u"])) <= 1e-4          # the last iteration's samples: the same chain
+        ref = _refsrc_gold("C2_mcnr", seed)                         # and against the reference's own src/mcml_full.cpp, directly
+        if ref is not None:
+            assert np.array_equal(ref["start"], start) and dev["converged"] == ref["converged"]
+            assert np.max(np.abs(dev["beta"] - ref["beta"])) <= 2e-4 and np.max(np.abs(dev["theta"] - ref["theta"])) <= 2e-4, (seed, dev["beta"], ref["beta"])
+            assert np.max(np.abs(dev["u"][:, -1] - ref["u_last"])) <= 2e-4
         db.append(dev["beta"]); dt.append(dev["theta"]); ob.append(orc["beta"]); ot.append(orc["theta"])
     # SURVEY §7's statement of the same thing: means over the seeds agree within the reference's tolerance
     assert np.max(np.abs(np.mean(db, 0) - np.mean(ob, 0))) <= 1e-2 and np.max(np.abs(np.mean(dt, 0) - np.mean(ot, 0))) <= 1e-2
@@ -58,6 +79,10 @@ def test_c1_mcem_fit_follows_the_oracle_loop_over_10_seeds(gctx, oracle):
         assert dev["iter"] == orc["iter"] and dev["converged"] == orc["converged"]
         assert np.max(np.abs(dev["beta"] - orc["beta"])) <= 5e-4, (seed, dev["beta"], orc["beta"])
         assert np.max(np.abs(dev["theta"] - orc["theta"])) <= 5e-4, (seed, dev["theta"], orc["theta"])
+        ref = _refsrc_gold("C1_mcem", seed)                         # the reference's own src/mcml_full.cpp (MCEM: optimiser tolerance)
+        if ref is not None:
+            assert np.array_equal(ref["start"], start) and dev["converged"] == ref["converged"]
+            assert np.max(np.abs(dev["beta"] - ref["beta"])) <= 6e-4 and np.max(np.abs(dev["theta"] - ref["theta"])) <= 6e-4, (seed, dev["beta"], ref["beta"])
         db.append(np.concatenate([dev["beta"], dev["theta"]])); ob.append(np.concatenate([orc["beta"], orc["theta"]]))
     assert np.max(np.abs(np.mean(db, 0) - np.mean(ob, 0))) <= 5e-3
     # with m = 250 the Monte-Carlo noise of an iterate is larger than tol = 5e-3 — for the oracle loop exactly as for the device loop
