@@ -201,3 +201,26 @@ def test_laplace_fits_of_the_reference_against_the_staged_replay(oracle):
     got = np.concatenate([fit["beta"], fit["theta"]])
     f_got = laplace.la_likelihood_btheta(got, cov, data, eff, Z, X, y, v1, fam, link, fl, 1.0)
     assert f_got <= rC.fun + 1e-6 * abs(rC.fun) and np.max(np.abs(got - rC.x)) <= 2e-2
+
+
+def test_golden_entry_point_values_are_the_reference_entry_points():
+    """tests/test_golden.py (GPU) asserts gmb_mvn_ll, gmb_aic_mcml and gmb_mcml_optim(mcnr) against numbers derived from the golden files
+    (outputs of the reference's HEADERS).  Here the reference's own ENTRY POINTS (src/mcml_optim.cpp) are run on the golden inputs and give
+    those same numbers — so that GPU test is a comparison with mvn_ll(), aic_mcml() and mcml_optim() of the reference themselves."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "C*_*.npz")))
+    assert len(files) == 5
+    for path in files:
+        g = np.load(path)
+        fam, link = str(g["family"]), str(g["link"])
+        X, Z, y, U = g["X"], g["Z"], g["y"], g["U"]
+        cov = (g["cov"], g["data"], g["eff_range"])
+        assert refsrc.mvn_ll(*cov, g["theta"], U) == g["mvn_ll"][0]
+        bp = np.concatenate([g["beta"], [1.0]]) if fam == "gaussian" else g["beta"]
+        want = -2 * (-(g["objectives"][0]) - g["objectives"][1]) + 2 * (bp.size + g["theta"].size)          # as in tests/test_golden.py
+        got = refsrc.aic_mcml(*cov, Z, X, y, U, fam, link, bp, g["theta"])
+        # (aic_mcml evaluates non-gaussian families at var_par = 0, src/mcml_optim.cpp:380-384, the golden objectives at 1: the same value)
+        assert abs(got - want) <= 1e-12 * abs(want)
+        opt = refsrc.mcml_optim(*cov, Z, X, y, U, fam, link, np.concatenate([g["beta"], g["theta"], [1.0]]), 0, True)
+        assert np.max(np.abs(opt["beta"] - g["mcnr_beta"])) <= 1e-12 * max(1.0, np.max(np.abs(g["mcnr_beta"])))
+        assert opt["sigma"] == float(g["mcnr_sigma"])
