@@ -37,6 +37,7 @@ def main():
         out[name + "_beta"] = np.array(B); out[name + "_theta"] = np.array(T); out[name + "_sigma"] = np.array(S)
         out[name + "_converged"] = np.array(Cv); out[name + "_u_last_column"] = np.array(Ul)
         out[name + "_start"] = start
+        out[name + "_y"] = cfg["y"].copy(); out[name + "_X"] = cfg["X"].copy()      # so that a comparison can check it runs on the same data
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "REFSRC_mcml_full.npz"), **out)
     print("written")
 
