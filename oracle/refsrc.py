@@ -16,11 +16,23 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(_HERE, "_ref", "librefsrc.so")
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
+SO_OMP = os.path.join(_HERE, "_ref", "librefsrc_omp.so")   # same sources with the reference's OpenMP pragmas on: timing only (mcnr races)
 _LIB = None
 
 
 def available() -> bool:
     return os.path.exists(SO)
+
+
+def timing_available() -> bool:
+    return os.path.exists(SO_OMP)
+
+
+def use_timing_build():
+    """Route every call of this module to librefsrc_omp.so (bench timings; results of mcml_optim(mcnr=True) are not reproducible there)."""
+    global _LIB, SO
+    SO = SO_OMP
+    _LIB = None
 
 
 def lib():

@@ -67,6 +67,24 @@ def main():
     out["mvn_ll_s_per_eval"] = {"headers": t_ref, "port": t_port}
     for k in ("hmc_s_per_proposal", "mcnr_s", "loglik_s_per_eval", "mvn_ll_s_per_eval"):
         out[k]["headers_over_port"] = out[k]["headers"] / out[k]["port"]
+    # the reference's own ENTRY POINTS (src/mcml_full.cpp, src/mcml_optim.cpp compiled against the shim, OpenMP build): the three calls the GPU
+    # arm's e2e figure makes — mcmc_sample, mcml_optim(mcnr = TRUE), mcml_hess — on the same small sample, R-default warm-up shortened like the sampler piece
+    try:
+        from oracle import refsrc
+        if refsrc.timing_available():
+            refsrc.use_timing_build()
+            start = np.concatenate([beta, theta, [1.0]])
+            ep = {"mcmc_sample_s_per_proposal": clock(lambda: refsrc.mcmc_sample(Z, L, X, y, beta, fam, link, warm, props - warm, 5.0, 1.0, 0, 500, 100, 0.95, seed=12345)) / props,
+                  "mcml_optim_mcnr_s": clock(lambda: refsrc.mcml_optim(*cov, Z, X, y, U, fam, link, start, 0, True)),
+                  "mcml_hess_s": clock(lambda: refsrc.mcml_hess(*cov, Z, X, y, U, fam, link, start[:-1], 1e-5, 0))}
+            step = ep["mcmc_sample_s_per_proposal"] * (500 + m_s) + ep["mcml_optim_mcnr_s"] + ep["mcml_hess_s"]
+            ep["step_s_at_m_sample"] = step
+            ep["value"] = m_s / step
+            ep["what"] = ("oracle/_ref/librefsrc_omp.so: the reference's own mcmc_sample + mcml_optim(mcnr) + mcml_hess bodies, one pass at m = m_sample "
+                          "(sampler: measured per proposal x (500 warm-up + m_sample)); u-samples/s = m_sample / that time")
+            out["entry_points"] = ep
+    except Exception as e:
+        out["entry_points"] = {"unavailable": str(e)[:200]}
     # the port once more on ONE thread (SURVEY §8d asks for both thread counts): how much of the CPU arm's speed is parallelism
     oracle.set_threads(1)
     p1 = max(40, props // 4)
