@@ -224,3 +224,19 @@ def test_golden_entry_point_values_are_the_reference_entry_points():
         opt = refsrc.mcml_optim(*cov, Z, X, y, U, fam, link, np.concatenate([g["beta"], g["theta"], [1.0]]), 0, True)
         assert np.max(np.abs(opt["beta"] - g["mcnr_beta"])) <= 1e-12 * max(1.0, np.max(np.abs(g["mcnr_beta"])))
         assert opt["sigma"] == float(g["mcnr_sigma"])
+
+
+def test_the_product_optimiser_on_the_oracle_objectives_reaches_the_reference_m_step(oracle):
+    """gmb_minimize_bounded (csrc/optim.cpp — host code, callable without a GPU; the library's l_optim / d_optim call it with exactly these
+    settings, csrc/api.cpp:168,175) driven by the ORACLE's objectives reproduces the M-step of the reference's own mcml_optim (its l_optim /
+    d_optim with the stand-in optimiser): both optimisers stop at the same optimum, far below the MCML tolerance."""
+    import glmmrmcml_b200 as g
+    for cfg in (small_rct(), synth.config4(ncl=9, nt=4, k=3, m=21, seed=8)):
+        P = cfg["P"]
+        L_obj, D_obj = _objectives(cfg, oracle)
+        start = np.concatenate([cfg["beta"] * 0.8, cfg["theta"] * 1.2, [1.0]])
+        ref_fit = refsrc.mcml_optim(*_args(cfg), start, 0, False)
+        b = g.minimize_bounded(lambda Xp: np.array([L_obj(Xp[:, k]) for k in range(Xp.shape[1])]), start[:P], xtol=1e-8, maxit=200)
+        t = g.minimize_bounded(lambda Xp: np.array([D_obj(Xp[:, k]) for k in range(Xp.shape[1])]), start[P:P + 2], lower=np.full(2, 1e-6), xtol=1e-8, maxit=200)
+        assert np.max(np.abs(b["x"] - ref_fit["beta"])) <= 2e-5, (b["x"], ref_fit["beta"])
+        assert np.max(np.abs(t["x"] - ref_fit["theta"])) <= 2e-5, (t["x"], ref_fit["theta"])
